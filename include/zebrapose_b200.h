@@ -1,0 +1,142 @@
+/*
+ * zebrapose_b200 -- C ABI of the B200-native post-network pose path of ZebraPose.
+ *
+ * The reference (lyltc1/ZebraPose) has no FFI for this path: the boundary is plain Python
+ * (zebrapose/binary_code_helper/CNN_output_to_pose.py, class_id_encoder_decoder.py,
+ * generate_new_dict.py, zebrapose/common_ops.py; call sites zebrapose/test.py:250-273,
+ * zebrapose/test_vivo.py:160-172).  This header is what a ctypes binding of that path binds
+ * (see INTEGRATION.md); zebrapose_b200/_lib.py is exactly that binding.
+ *
+ * Conventions
+ *   - Every pointer is a DEVICE pointer owned by the caller (e.g. a torch tensor's data_ptr())
+ *     unless its comment says "host".  The library allocates nothing the caller must free except
+ *     the context (internal workspace lives and dies with it).
+ *   - Work is enqueued on `stream` (a cudaStream_t passed as void*; NULL = legacy default stream);
+ *     no hidden synchronisation except where stated ("synchronises").
+ *   - Return value: 0 = ok, < 0 = error; zp_last_error(ctx) describes the last failure.
+ *   - One zp_ctx per (device, host thread).  Not thread-safe across threads sharing a ctx.
+ *   - Correspondence lists are SoA per crop: float corr[B][5][cap], planes u, v, X, Y, Z
+ *     (u,v = original-image pixel, float32 of an integer; X,Y,Z = model point in mm), entries
+ *     [0, counts[b]) valid, in row-major pixel order of the crop (CNN_output_to_pose.py:111,54).
+ *   - Poses are double[12] per crop/hypothesis: R row-major (9) then t (3, millimetres).
+ */
+#ifndef ZEBRAPOSE_B200_H
+#define ZEBRAPOSE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct zp_ctx zp_ctx;
+
+enum { ZP_DTYPE_F32 = 0, ZP_DTYPE_BF16 = 1 };
+/* non-existing (NaN) dictionary rows: ZERO = reference behaviour (3D point (0,0,0), pixel kept,
+ * CNN_output_to_pose.py:58-62); HAMMING = north_star extension (nearest existing code). */
+enum { ZP_NONEXIST_ZERO = 0, ZP_NONEXIST_HAMMING = 1 };
+enum { ZP_SAMPLER_CV2 = 0, ZP_SAMPLER_PHILOX = 1 };
+enum { ZP_SELECT_CV2_REPLAY = 0, ZP_SELECT_ARGMAX = 1 };
+enum { ZP_FINAL_EPNP = 0, ZP_FINAL_EPNP_GN = 1 };
+/* per-crop status written by zp_ransac */
+enum { ZP_OK = 0, ZP_NO_MASK_PIXELS = 1, ZP_TOO_FEW_POINTS = 2, ZP_RANSAC_NO_MODEL = 3 };
+
+#define ZP_MAX_OBJECTS 256
+#define ZP_MAX_HYPOTHESES 1024
+
+int zp_version(void);
+int zp_create(zp_ctx** out, int device);
+void zp_destroy(zp_ctx* ctx);
+const char* zp_last_error(zp_ctx* ctx);
+
+/* Replaces load_dict_class_id_3D_points' table + generate_new_corres_dict (generate_new_dict.py:4-33):
+ * uploads the correspondence dictionary of object slot `obj_id` (0 <= obj_id < ZP_MAX_OBJECTS).
+ * pts_xyz: HOST double [2^n_bits][3], NaN rows = non-existing codes.  For ignore_bit = k the parent table
+ * (2^(n_bits-k) rows) is built on the host in the reference's order (float64, children summed in ascending
+ * id order, then / 2^k; NaN propagates) and cast to float32 like CNN_output_to_pose.py:129.  Synchronises. */
+int zp_upload_tables(zp_ctx* ctx, int obj_id, const double* pts_xyz, int n_bits, int ignore_bit,
+                     int nonexist_mode);
+/* Debug/parity read-back of what zp_upload_tables built (HOST outputs, both nullable):
+ * pts_out float[2^(n_bits-k)][4] (x,y,z,exists), remap_out uint16[2^(n_bits-k)].  Synchronises. */
+int zp_download_tables(zp_ctx* ctx, int obj_id, float* pts_out, uint16_t* remap_out);
+
+/* Replaces common_ops.from_output_to_class_mask / from_output_to_class_binary_code (common_ops.py:5-19),
+ * class_code_images_to_class_id_image (class_id_encoder_decoder.py:17-28), build_non_unique_2D_3D_correspondence
+ * (CNN_output_to_pose.py:53-64) and mapping_pixel_position_to_original_position (:34-50), for B crops at once.
+ *   logits   [B, C, S, S] network output, any strides (elements): strides[4] = {batch, channel, row, pixel}
+ *   mask_ch  channel of the mask logit (0), bit0_ch first code-bit channel (1; v2 nets: 2), MSB first
+ *   n_bits   code length (16); ignore_bit k: only the first n_bits-k bit planes are read (test.py:267)
+ *   ext_mask nullable uint8 [B,S,S]; non-zero = masked; overrides mask_ch (mask-rcnn variants)
+ *   bbox     double [B,4] = x, y, w, h of get_final_Bbox (bop_dataset_pytorch.py:162-194)
+ *   obj_ids  nullable int32 [B] table slot per crop; NULL -> obj_default for all
+ *   codes    nullable uint16 [B,S,S] out: class id of every pixel
+ *   corr     float [B,5,cap] out; counts int32 [B] out (number of masked pixels, may exceed cap -> clipped lists)
+ */
+int zp_decode(zp_ctx* ctx, const void* logits, int dtype, int B, int S, const int64_t strides[4],
+              int mask_ch, int bit0_ch, int n_bits, int ignore_bit, const uint8_t* ext_mask,
+              const double* bbox, const int32_t* obj_ids, int obj_default,
+              uint16_t* codes, float* corr, int cap, int32_t* counts, void* stream);
+
+/* Stand-alone device forms of two small reference helpers (the batched path has them fused into zp_decode):
+ * mapping_pixel_position_to_original_position (CNN_output_to_pose.py:34-50): px int64 [N,2] (x,y) -> out int64 [N,2];
+ * h_bbox is a HOST double[4].  class_code_images_to_class_id_image (class_id_encoder_decoder.py:17-28):
+ * bits double [N,L] (values 0..base-1, channel 0 most significant) -> ids double [N] = sum bits[i]*base^(L-1-i). */
+int zp_remap_pixels(zp_ctx* ctx, const int64_t* px, int64_t N, const double* h_bbox, int S, int64_t* out, void* stream);
+int zp_codes_to_ids(zp_ctx* ctx, const double* bits, int64_t N, int L, int base, double* ids, void* stream);
+
+/* Minimal-sample index lists, exportable for parity runs.  mode CV2: replays cv::RNG(0xFFFFFFFFFFFFFFFF)
+ * exactly as cv2.solvePnPRansac draws them (depends on counts[b] only); PHILOX: counter-based, seeded.
+ * samples int32 [B,H,m] out; crops with counts[b] < m get -1. */
+int zp_make_samples(zp_ctx* ctx, const int32_t* counts, int cap, int B, int H, int m, int mode,
+                    uint64_t seed, int32_t* samples, void* stream);
+
+/* EPnP on each m-point minimal set (float64).  K double [B,9] row-major.  hyp_poses double [B,H,12] out;
+ * hypotheses of crops with too few points or degenerate samples are written as NaN. */
+int zp_solve_minimal(zp_ctx* ctx, const float* corr, int cap, const int32_t* counts, const double* K,
+                     const int32_t* samples, int B, int H, int m, double* hyp_poses, void* stream);
+
+/* Reprojection scoring of H hypotheses against all correspondences of each crop (the FP32 kernel):
+ * inlier <=> (x - u z)^2 + (y - v z)^2 <= thr^2 z^2 with [x y z] = K [R|t] [X Y Z 1], float32.
+ * hyp_inliers int32 [B,H] out.  Replaces PnPRansacCallback::computeError of cv2.solvePnPRansac
+ * (called at CNN_output_to_pose.py:155-157). */
+int zp_score(zp_ctx* ctx, const float* corr, int cap, const int32_t* counts, const double* K,
+             const double* hyp_poses, int B, int H, float thr_px, int32_t* hyp_inliers, void* stream);
+
+/* Whole RANSAC-PnP (replaces cv2.solvePnPRansac(..., reprojectionError=thr_px, iterationsCount=H,
+ * flags=SOLVEPNP_EPNP) + cv2.Rodrigues, CNN_output_to_pose.py:155-158):
+ * samples (nullable: generated internally with `sampler`/`seed`) -> minimal EPnP -> scoring -> winner
+ * (CV2_REPLAY: cv2's strictly-greater update with RANSACUpdateNumIters(confidence) replayed over the H counts;
+ * ARGMAX: most inliers, lowest index on ties) -> EPnP on the winner's inliers (+ optional Gauss-Newton polish).
+ * Outputs: poses double [B,12], n_inliers int32 [B], status int32 [B]; nullable hyp_poses double [B,H,12],
+ * hyp_inliers int32 [B,H], best_idx int32 [B], inlier_mask uint8 [B,cap]. */
+int zp_ransac(zp_ctx* ctx, const float* corr, int cap, const int32_t* counts, const double* K,
+              const int32_t* samples, int B, int H, int m, float thr_px, double confidence,
+              int sampler, uint64_t seed, int select_mode, int final_mode,
+              double* hyp_poses, int32_t* hyp_inliers, int32_t* best_idx, uint8_t* inlier_mask,
+              double* poses, int32_t* n_inliers, int32_t* status, void* stream);
+
+/* The reference-facing one-call form with HOST buffers (what a per-batch drop-in of test.py:250-273 calls):
+ * copies logits/bbox/K/obj_ids host->device, runs decode + RANSAC, copies poses/n_inliers/status back.
+ * h_logits: HOST [B,C,S,S] contiguous (dtype as above); h_bbox HOST double [B,4]; h_K HOST double [B,9];
+ * h_obj_ids nullable HOST int32 [B].  Outputs HOST: poses double [B,12], n_inliers int32 [B], status int32 [B].
+ * Pinned host memory makes the copies asynchronous; the call synchronises before returning. */
+int zp_pose_batch_host(zp_ctx* ctx, const void* h_logits, int dtype, int B, int C, int S,
+                       int mask_ch, int bit0_ch, int n_bits, int ignore_bit,
+                       const double* h_bbox, const double* h_K, const int32_t* h_obj_ids, int obj_default,
+                       int H, int m, float thr_px, double confidence, int sampler, uint64_t seed,
+                       int select_mode, int final_mode,
+                       double* h_poses, int32_t* h_n_inliers, int32_t* h_status);
+
+/* Number of kernels this ctx has launched since creation (bench.py's gpu_launches claim). */
+int64_t zp_launch_count(zp_ctx* ctx);
+
+/* FP32 FMA-chain microbenchmark (the roofline denominator for zp_score has no entry in MEASURED_PEAKS.json):
+ * runs `iters` dependent-chain FMAs x 8 chains per thread on the whole chip, returns achieved TFLOP/s in *out.
+ * Synchronises. */
+int zp_fp32_peak_probe(zp_ctx* ctx, int iters, double* out_tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

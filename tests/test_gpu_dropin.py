@@ -1,0 +1,71 @@
+"""GPU: the reference-signature drop-ins (zebrapose_b200/binary_code_helper, common_ops) against the golden outputs
+of the reference functions."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import decode, metrics
+from helpers import GOLDEN_CROPS, regen_crop
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("tag", ["c1_full", "c1_nan20", "c3_k4", "s64_k0"])
+def test_cnn_outputs_to_object_pose(golden, tables, tag):
+    from zebrapose_b200.binary_code_helper.CNN_output_to_pose import CNN_outputs_to_object_pose, CNN_outputs_to_object_info
+    from zebrapose_b200.binary_code_helper.generate_new_dict import generate_new_corres_dict
+    from zebrapose_b200 import common_ops
+    tab, c, logits, S, k = regen_crop(tables, tag)
+    lt = torch.from_numpy(logits)[None].cuda()
+    pm = common_ops.from_output_to_class_mask(lt[:, :1])
+    pc = common_ops.from_output_to_class_binary_code(lt[:, 1:], "BCE")
+    pc = pc.transpose(0, 2, 3, 1)
+    pm = pm.transpose(0, 2, 3, 1).squeeze(axis=-1).astype("uint8")
+    d = {float(i): tab[i] for i in range(len(tab))}
+    code = pc[0]
+    if k:
+        d = generate_new_corres_dict(d, 16, 16 - k)
+        code = code[:, :, :-k]
+    R, t, ok = CNN_outputs_to_object_pose(pm[0], code, c["bbox"], S, 2, d, intrinsic_matrix=torch.from_numpy(c["K"]))
+    assert ok == bool(golden[tag + "_ok"]) and R.shape == (3, 3) and t.shape == (3, 1) and R.dtype == np.float64
+    re, te = metrics.rot_err_deg(R, golden[tag + "_R"]), metrics.trans_err(t, golden[tag + "_t"])
+    print(tag, "rot %.4f deg trans %.4f mm" % (re, te))
+    assert re < 0.2 and te < 2.0          # per-crop bound; the tolerance pass RATE is asserted in test_gpu_ransac
+    R2, t2, ok2, info = CNN_outputs_to_object_info(pm[0], code, c["bbox"], S, 2, d, intrinsic_matrix=c["K"])
+    assert np.array_equal(R, R2) and info["n_correspondences"] == len(golden[tag + "_uv"])
+    assert np.array_equal(info["coord_2d"], golden[tag + "_uv"].astype(np.float32))
+    assert np.array_equal(info["coord_3d"].view(np.uint32), golden[tag + "_xyz"].view(np.uint32))
+
+
+def test_edge_cases_match_reference(golden, tables):
+    from zebrapose_b200.binary_code_helper.CNN_output_to_pose import CNN_outputs_to_object_pose
+    tab = tables["full"][0]
+    d = {float(i): tab[i] for i in range(len(tab))}
+    S = 128
+    code = np.zeros((S, S, 16))
+    m = np.zeros((S, S), np.uint8)
+    r = CNN_outputs_to_object_pose(m, code, np.array([0, 0, 128, 128]), S, 2, d)
+    assert [len(r[0]), len(r[1]), int(r[2])] == golden["edge_empty"].tolist()
+    m[3, 3:8] = 1
+    r = CNN_outputs_to_object_pose(m, code, np.array([0, 0, 128, 128]), S, 2, d)
+    assert [len(r[0]), len(r[1]), int(r[2])] == golden["edge_5px"].tolist()
+    m[3, 3:9] = 1
+    r = CNN_outputs_to_object_pose(m, code, np.array([0, 0, 128, 128]), S, 2, d)
+    assert int(r[2]) == int(golden["edge_6px_ok"])            # success stays True
+    assert np.allclose(r[0], golden["edge_6px_R"]) and np.allclose(r[1], golden["edge_6px_t"])   # R = I, t = 0
+
+
+def test_small_helpers(golden):
+    from zebrapose_b200.binary_code_helper.CNN_output_to_pose import mapping_pixel_position_to_original_position
+    from zebrapose_b200.binary_code_helper.class_id_encoder_decoder import class_code_images_to_class_id_image
+    for b, S, exp in zip(golden["remap_boxes"], golden["remap_sizes"], golden["remap_out"]):
+        px = np.stack([np.arange(S), np.arange(S)[::-1]], 1)
+        got = mapping_pixel_position_to_original_position(px, b, int(S))
+        assert got.dtype == np.int64 and np.array_equal(got, exp[:S])
+    px = np.stack([np.arange(128), np.arange(128)], 1)
+    for b, exp in zip(golden["remap_fboxes"], golden["remap_fout"]):
+        assert np.array_equal(mapping_pixel_position_to_original_position(px, b, 128), exp)
+    rng = np.random.default_rng(0)
+    bits = rng.integers(0, 2, (16, 24, 16)).astype(np.float64)
+    ids = class_code_images_to_class_id_image(bits, 2)
+    assert ids.dtype == np.float64 and np.array_equal(ids, decode.class_code_images_to_class_id_image(bits, 2))

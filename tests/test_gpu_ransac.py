@@ -1,0 +1,239 @@
+"""GPU: RANSAC-PnP pieces and the whole chain (through the C ABI) vs the oracle / cv2.
+
+Tolerances (north_star): inlier counts given identical hypothesis poses exact except points within 1e-3 px of the
+threshold; final poses within 0.05 deg / 0.5 mm of cv2.solvePnPRansac; the fraction of crops meeting it is asserted
+(the reference's own sampling noise makes 100 %% unreachable)."""
+import cv2
+import numpy as np
+import pytest
+import torch
+
+from oracle import cvransac, decode, epnp, metrics, synth
+
+pytestmark = pytest.mark.gpu
+ROT_TOL_DEG, TRANS_TOL_MM = 0.05, 0.5
+
+
+@pytest.fixture(scope="module")
+def eng():
+    import zebrapose_b200 as zp
+    return zp.Engine(0)
+
+
+@pytest.fixture(scope="module")
+def batch(eng, tables):
+    """8 'ape' crops decoded on the device + the same lists from the oracle"""
+    tab, nrm = tables["full"]
+    eng.upload_dict(0, tab)
+    crops = [synth.make_crop(tab, nrm, 1001 * 65536 + 100 + i) for i in range(8)]
+    logits = np.stack([synth.crop_to_logits(c) for c in crops])
+    bboxes = np.stack([c["bbox"] for c in crops])
+    Ks = np.stack([c["K"] for c in crops])
+    corr, counts = eng.decode(torch.from_numpy(logits).cuda(), bboxes)
+    lists = []
+    for i, c in enumerate(crops):
+        uv, xyz, _ = decode.decode_crop(decode.threshold_logits(logits[i, 0]).astype(np.uint8),
+                                        decode.threshold_logits(logits[i, 1:]).transpose(1, 2, 0), c["bbox"], 128, tab)
+        lists.append((uv, xyz))
+    return dict(crops=crops, corr=corr, counts=counts, Ks=Ks, lists=lists, logits=logits, bboxes=bboxes)
+
+
+def test_samples_replay_cv_rng(eng, batch):
+    s = eng.make_samples(batch["counts"], batch["corr"].shape[2], H=150, m=5).cpu().numpy()
+    for i, (uv, _) in enumerate(batch["lists"]):
+        assert np.array_equal(s[i], cvransac.sample_lists(len(uv), 150, 5))
+    s6 = eng.make_samples(batch["counts"], batch["corr"].shape[2], H=40, m=6, sampler="philox", seed=7).cpu().numpy()
+    assert all(len(set(r)) == 6 for r in s6.reshape(-1, 6)) and s6.min() >= 0
+    assert all(s6[i].max() < len(batch["lists"][i][0]) for i in range(len(s6)))
+
+
+def test_score_exact_given_oracle_poses(eng, batch):
+    """hypothesis poses from cv2.solvePnP on cv2's own sample lists -> counts must equal cv2's computeError counts,
+    except for points whose reprojection error is within 1e-3 px of the 2 px threshold"""
+    B, H = len(batch["lists"]), 150
+    hyp = np.full((B, H, 12), np.nan)
+    exp = np.zeros((B, H), np.int64)
+    slack = np.zeros((B, H), np.int64)
+    for i, (uv, xyz) in enumerate(batch["lists"]):
+        K = batch["Ks"][i]
+        S = cvransac.sample_lists(len(uv), H, 5)
+        for h in range(H):
+            sol = cvransac.cv2_solver(xyz[S[h]], uv[S[h]], K)
+            if sol is None:
+                continue
+            hyp[i, h, :9] = sol[0].ravel()
+            hyp[i, h, 9:] = sol[1]
+            mask, err = cvransac.score_pose(xyz, uv, K, sol[0], sol[1], 2.0)
+            exp[i, h] = mask.sum()
+            slack[i, h] = (np.abs(np.sqrt(err.astype(np.float64)) - 2.0) < 1e-3).sum()
+    got = eng.score(batch["corr"], batch["counts"], batch["Ks"], torch.from_numpy(hyp).cuda(), 2.0).cpu().numpy()
+    diff = np.abs(got - exp)
+    assert (diff <= slack).all(), (diff.max(), np.argwhere(diff > slack)[:5])
+    assert (diff == 0).mean() > 0.99
+    assert got.max() > 1000
+
+
+def test_minimal_solver_vs_oracle_m6(eng, batch):
+    """6-point sets are well conditioned: device EPnP == oracle EPnP == cv2 on every hypothesis that the
+    oracle itself reproduces under a 1-ulp perturbation"""
+    corr, counts, Ks = batch["corr"], batch["counts"], batch["Ks"]
+    H = 64
+    s = eng.make_samples(counts, corr.shape[2], H=H, m=6, sampler="philox", seed=3)
+    hp = eng.solve_minimal(corr, counts, Ks, s).cpu().numpy()
+    s = s.cpu().numpy()
+    checked = bad = 0
+    for i, (uv, xyz) in enumerate(batch["lists"][:4]):
+        for h in range(H):
+            idx = s[i, h]
+            Rc, tc = cvransac.cv2_solver(xyz[idx], uv[idx], Ks[i])
+            xyz_p = xyz[idx] * (1 + np.float32(6e-8))
+            Rp, tp = cvransac.cv2_solver(xyz_p, uv[idx], Ks[i])
+            if metrics.rot_err_deg(Rc, Rp) > 1e-3 or metrics.trans_err(tc, tp) > 1e-2:
+                continue                                   # cv2 itself is unstable on this sample
+            checked += 1
+            R, t = hp[i, h, :9].reshape(3, 3), hp[i, h, 9:]
+            if not (metrics.rot_err_deg(Rc, R) < 2e-3 and metrics.trans_err(tc, t) < 2e-2):
+                bad += 1
+    assert checked > 100
+    assert bad <= 0.02 * checked, (bad, checked)
+
+
+def test_minimal_solver_m5_stable_subset(eng, batch):
+    """cv2's own 5-point lists: agreement with cv2 on the hypotheses cv2 reproduces under perturbation"""
+    corr, counts, Ks = batch["corr"], batch["counts"], batch["Ks"]
+    s = eng.make_samples(counts, corr.shape[2], H=150, m=5)
+    hp = eng.solve_minimal(corr, counts, Ks, s).cpu().numpy()
+    s = s.cpu().numpy()
+    checked = good = unstable = 0
+    for i, (uv, xyz) in enumerate(batch["lists"][:3]):
+        for h in range(150):
+            idx = s[i, h]
+            Rc, tc = cvransac.cv2_solver(xyz[idx], uv[idx], Ks[i])
+            Rp, tp = cvransac.cv2_solver(xyz[idx] * (1 + np.float32(6e-8)), uv[idx], Ks[i])
+            if metrics.rot_err_deg(Rc, Rp) > 1e-3 or metrics.trans_err(tc, tp) > 1e-2:
+                unstable += 1
+                continue
+            checked += 1
+            R, t = hp[i, h, :9].reshape(3, 3), hp[i, h, 9:]
+            good += metrics.rot_err_deg(Rc, R) < 1e-2 and metrics.trans_err(tc, t) < 0.1
+    print("m=5: stable %d, unstable %d, device agrees on %d" % (checked, unstable, good))
+    assert checked > 50 and good >= 0.9 * checked
+
+
+def test_full_chain_vs_cv2(eng, batch):
+    res = eng.ransac(batch["corr"], batch["counts"], batch["Ks"], return_details=True)
+    poses = res["poses"].cpu().numpy()
+    ninl = res["n_inliers"].cpu().numpy()
+    status = res["status"].cpu().numpy()
+    best = res["best_idx"].cpu().numpy()
+    hyp_inl = res["hyp_inliers"].cpu().numpy()
+    im = res["inlier_mask"].cpu().numpy()
+    within = same_winner = 0
+    for i, (uv, xyz) in enumerate(batch["lists"]):
+        K = batch["Ks"][i]
+        ok, rv, tv, inl = cv2.solvePnPRansac(xyz, uv, K, None, reprojectionError=2, iterationsCount=150, flags=cv2.SOLVEPNP_EPNP)
+        Rc = cv2.Rodrigues(rv)[0]
+        R, t = poses[i, :9].reshape(3, 3), poses[i, 9:]
+        re, te = metrics.rot_err_deg(Rc, R), metrics.trans_err(tv, t)
+        ok2, R2, t2, inl2, info = cvransac.solve_pnp_ransac(xyz, uv, K)
+        same_winner += int(best[i] == info["best"])
+        within += int(re <= ROT_TOL_DEG and te <= TRANS_TOL_MM)
+        assert status[i] == 0
+        assert ninl[i] == im[i].sum() == hyp_inl[i, best[i]]
+        # replaying cv2's rule on the device counts must give the device winner
+        b2, _ = cvransac.replay_select(hyp_inl[i], len(uv))
+        assert b2 == best[i]
+        # and the pose is a sane one in any case
+        assert metrics.rot_err_deg(R, batch["crops"][i]["R"]) < 1.0
+        assert abs(np.linalg.det(R) - 1) < 1e-9
+        print("crop %d: rot %.4f deg  trans %.4f mm  winner %d/%d  inliers %d/%d" % (i, re, te, best[i], info["best"], ninl[i], len(inl)))
+    n = len(batch["lists"])
+    assert within >= 0.75 * n, (within, n)
+
+
+def test_final_epnp_on_given_inliers(eng, batch):
+    """a 1-hypothesis RANSAC whose sample is cv2's winning sample: the device's final EPnP on (nearly) cv2's inlier set
+    must land within the pose tolerance of cv2's answer (the final solve is well conditioned, n ~ thousands)"""
+    B = len(batch["lists"])
+    exp, smp = [], []
+    for i, (uv, xyz) in enumerate(batch["lists"]):
+        ok2, R2, t2, inl2, info = cvransac.solve_pnp_ransac(xyz, uv, batch["Ks"][i])
+        exp.append((R2, t2, len(inl2)))
+        smp.append(info["samples"][[info["best"]]])
+    samples = torch.from_numpy(np.stack(smp)).cuda().contiguous()
+    res = eng.ransac(batch["corr"], batch["counts"], batch["Ks"], samples=samples, return_details=True)
+    poses = res["poses"].cpu().numpy()
+    ninl = res["n_inliers"].cpu().numpy()
+    ok = 0
+    for i in range(B):
+        R, t = poses[i, :9].reshape(3, 3), poses[i, 9:]
+        re, te = metrics.rot_err_deg(exp[i][0], R), metrics.trans_err(exp[i][1], t)
+        print("crop %d: rot %.5f deg trans %.5f mm inliers %d / cv2 %d" % (i, re, te, ninl[i], exp[i][2]))
+        ok += int(re < ROT_TOL_DEG and te < TRANS_TOL_MM)
+    assert ok >= B - 1, ok
+
+
+def test_statuses_and_edge_cases(eng, tables):
+    tab, nrm = tables["full"]
+    eng.upload_dict(0, tab)
+    S = 128
+    c = synth.make_crop(tab, nrm, 5)
+    logits = np.stack([synth.crop_to_logits(c)] * 4)
+    logits[0, 0] = -3.0                                   # no mask pixel
+    logits[1, 0] = -3.0
+    logits[1, 0, 3, 3:8] = 2.0                            # 5 px -> too few
+    logits[2, 0] = -3.0
+    logits[2, 0, 3, 3:9] = 2.0                            # 6 px of (almost) one code -> RANSAC may find no model
+    logits[2, 1:] = -3.0
+    bb = np.stack([c["bbox"]] * 4)
+    poses, ninl, status = eng.decode_and_pose_batch(torch.from_numpy(logits).cuda(), bb, c["K"])
+    status = status.cpu().numpy()
+    assert status[0] == 1 and status[1] == 2 and status[3] == 0
+    assert status[2] in (0, 3)
+    p = poses.cpu().numpy()
+    assert np.isfinite(p).all()
+    for i in (0, 1):
+        assert np.array_equal(p[i], [1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0])
+    # argmax selection + GN polish run and stay close to the EPnP answer
+    p2, _, st2 = eng.decode_and_pose_batch(torch.from_numpy(logits[3:]).cuda(), bb[3:], c["K"], select="argmax", final="epnp+gn")
+    p2 = p2.cpu().numpy()[0]
+    assert st2.item() == 0
+    assert metrics.rot_err_deg(p2[:9].reshape(3, 3), p[3, :9].reshape(3, 3)) < 0.2
+    assert metrics.rot_err_deg(p2[:9].reshape(3, 3), c["R"]) < 0.5
+
+
+def test_host_entry_matches_device_entry(eng, batch):
+    """zp_pose_batch_host (host buffers, copies inside) == device-resident chain, bit for bit"""
+    res = eng.ransac(batch["corr"], batch["counts"], batch["Ks"])
+    pin = torch.from_numpy(batch["logits"]).pin_memory()
+    poses, ninl, status = eng.pose_batch_host(pin, batch["bboxes"], batch["Ks"])
+    assert np.array_equal(poses, res["poses"].cpu().numpy())
+    assert np.array_equal(ninl, res["n_inliers"].cpu().numpy())
+    assert (status == 0).all()
+
+
+def test_add_metric_agreement(eng, tables):
+    """ADD(-S) @ 0.1 d must agree with the reference path within 0.5 %% (north_star): 32 crops"""
+    tab, nrm = tables["full"]
+    eng.upload_dict(0, tab)
+    B = 32
+    crops = [synth.make_crop(tab, nrm, 2000 + i) for i in range(B)]
+    logits = np.stack([synth.crop_to_logits(c) for c in crops])
+    bboxes = np.stack([c["bbox"] for c in crops])
+    poses, _, _ = eng.decode_and_pose_batch(torch.from_numpy(logits).cuda(), bboxes, crops[0]["K"])
+    poses = poses.cpu().numpy()
+    pts = tab[::64]
+    diam = 102.0
+    pass_dev = pass_ref = within = 0
+    for i, c in enumerate(crops):
+        uv, xyz, _ = decode.decode_crop(decode.threshold_logits(logits[i, 0]).astype(np.uint8),
+                                        decode.threshold_logits(logits[i, 1:]).transpose(1, 2, 0), c["bbox"], 128, tab)
+        ok, rv, tv, inl = cv2.solvePnPRansac(xyz, uv, c["K"], None, reprojectionError=2, iterationsCount=150, flags=cv2.SOLVEPNP_EPNP)
+        Rc = cv2.Rodrigues(rv)[0]
+        R, t = poses[i, :9].reshape(3, 3), poses[i, 9:]
+        pass_ref += metrics.add(Rc, tv.ravel(), c["R"], c["t"], pts) < 0.1 * diam
+        pass_dev += metrics.add(R, t, c["R"], c["t"], pts) < 0.1 * diam
+        within += metrics.rot_err_deg(Rc, R) <= ROT_TOL_DEG and metrics.trans_err(tv, t) <= TRANS_TOL_MM
+    print("ADD@0.1d pass: device %d/%d reference %d/%d; pose tolerance pass rate %d/%d" % (pass_dev, B, pass_ref, B, within, B))
+    assert abs(pass_dev - pass_ref) / B <= 0.005 + 1e-9
+    assert within >= 0.8 * B

@@ -1,0 +1,31 @@
+"""Mirror of zebrapose/common_ops.py:5-19 (BCE / L1 branch).  The reference pulls all logits to the host and
+thresholds there; here the comparison runs on the device the logits already live on and only the {0,1} result is
+copied.  sigmoid(x) > t  <=>  x > log(t / (1 - t)); for t = 0.5 that is float32(x) > 0.
+The batched path (Engine.decode_and_pose_batch) never calls these: its decode kernel thresholds in registers."""
+import math
+
+import numpy as np
+import torch
+
+
+def _threshold(pred, thershold):
+    cut = math.log(thershold / (1.0 - thershold)) if thershold != 0.5 else 0.0
+    x = pred.detach().to(torch.float32)
+    return (x > cut).to(torch.float64).cpu().numpy()
+
+
+def from_output_to_class_mask(pred_mask_prob, thershold=0.5):
+    return _threshold(pred_mask_prob, thershold)
+
+
+def from_output_to_class_binary_code(pred_code_prob, BinaryCode_Loss_Type, thershold=0.5, divided_num_each_interation=2,
+                                     binary_code_length=16):
+    if BinaryCode_Loss_Type in ("BCE", "L1"):
+        return _threshold(pred_code_prob, thershold)
+    raise NotImplementedError("BinaryCode_Loss_Type %r: only the binary (BCE / L1) heads are on the B200 path; the CE "
+                              "ablation branch (common_ops.py:21-30) is out of scope" % (BinaryCode_Loss_Type,))
+
+
+def get_batch_size(second_dataset_ratio, batch_size):
+    second = int(batch_size * second_dataset_ratio)
+    return batch_size - second, second

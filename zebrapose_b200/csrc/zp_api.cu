@@ -1,0 +1,326 @@
+// C ABI of libzebrapose_b200.so (declared in include/zebrapose_b200.h): context, dictionary tables, orchestration.
+#include <algorithm>
+#include <cmath>
+#include "zp_common.cuh"
+
+int zp_launch_samples(zp_ctx*, const int32_t*, int, int, int, int, int, uint64_t, int32_t*, cudaStream_t);
+int zp_launch_minimal(zp_ctx*, const float*, int, const int32_t*, const double*, const int32_t*, int, int, int, double*,
+                      cudaStream_t);
+int zp_launch_score(zp_ctx*, const float*, int, const int32_t*, const double*, const double*, int, int, float, int32_t*,
+                    cudaStream_t);
+int zp_launch_select(zp_ctx*, const int32_t*, int, const int32_t*, int, int, int, double, int, int32_t*, int32_t*,
+                     cudaStream_t);
+int zp_launch_final(zp_ctx*, const float*, int, const int32_t*, const double*, const double*, const int32_t*,
+                    const int32_t*, int, int, float, int, double*, int32_t*, uint8_t*, cudaStream_t);
+int zp_launch_fma_probe(zp_ctx*, int, double*);
+int zp_launch_remap_pixels(zp_ctx*, const int64_t*, int64_t, const double*, int, int64_t*, cudaStream_t);
+int zp_launch_codes_to_ids(zp_ctx*, const double*, int64_t, int, int, double*, cudaStream_t);
+
+static thread_local std::string g_err;
+
+int zp_ws_reserve(zp_ctx* ctx, size_t bytes) {
+    if (bytes <= ctx->ws_bytes) return 0;
+    // growing the workspace must not race with work still using the old one
+    ZP_CUDA(ctx, cudaDeviceSynchronize());
+    if (ctx->ws) cudaFree(ctx->ws);
+    ctx->ws = nullptr; ctx->ws_bytes = 0;
+    size_t want = bytes + bytes / 4 + 4096;
+    ZP_CUDA(ctx, cudaMalloc(&ctx->ws, want));
+    ctx->ws_bytes = want;
+    return 0;
+}
+
+static int hws_reserve(zp_ctx* ctx, size_t bytes) {
+    if (bytes <= ctx->hws_bytes) return 0;
+    ZP_CUDA(ctx, cudaDeviceSynchronize());
+    if (ctx->hws) cudaFree(ctx->hws);
+    ctx->hws = nullptr; ctx->hws_bytes = 0;
+    size_t want = bytes + bytes / 4 + 4096;
+    ZP_CUDA(ctx, cudaMalloc(&ctx->hws, want));
+    ctx->hws_bytes = want;
+    return 0;
+}
+
+extern "C" {
+
+int zp_version(void) { return 100; }
+
+int zp_create(zp_ctx** out, int device) {
+    if (!out) return -1;
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) { g_err = "no CUDA device: zebrapose_b200 has no CPU fallback"; return -2; }
+    if (device < 0 || device >= ndev) { g_err = "bad device index"; return -1; }
+    zp_ctx* ctx = new zp_ctx();
+    ctx->device = device;
+    if (cudaSetDevice(device) != cudaSuccess) { delete ctx; g_err = "cudaSetDevice failed"; return -2; }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete ctx; g_err = "cudaGetDeviceProperties failed"; return -2; }
+    if (prop.major < 9) { delete ctx; g_err = "device too old: built for sm_100a (thread-block clusters, TMA)"; return -2; }
+    ctx->sm_count = prop.multiProcessorCount;
+    if (cudaMalloc((void**)&ctx->d_table_ptrs, ZP_MAX_OBJECTS * sizeof(float4*)) != cudaSuccess ||
+        cudaMemset((void*)ctx->d_table_ptrs, 0, ZP_MAX_OBJECTS * sizeof(float4*)) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete ctx; g_err = "context allocation failed"; return -2;
+    }
+    *out = ctx;
+    return 0;
+}
+
+void zp_destroy(zp_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    for (auto& t : ctx->tables) { if (t.pts) cudaFree(t.pts); if (t.remap) cudaFree(t.remap); }
+    if (ctx->d_table_ptrs) cudaFree((void*)ctx->d_table_ptrs);
+    if (ctx->ws) cudaFree(ctx->ws);
+    if (ctx->hws) cudaFree(ctx->hws);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+}
+
+const char* zp_last_error(zp_ctx* ctx) { return ctx ? ctx->err.c_str() : g_err.c_str(); }
+
+int64_t zp_launch_count(zp_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int zp_upload_tables(zp_ctx* ctx, int obj_id, const double* pts, int n_bits, int ignore_bit, int mode) {
+    if (!ctx) return -1;
+    if (obj_id < 0 || obj_id >= ZP_MAX_OBJECTS) ZP_FAIL(ctx, -1, "obj_id %d out of range [0,%d)", obj_id, ZP_MAX_OBJECTS);
+    if (n_bits < 1 || n_bits > 16 || ignore_bit < 0 || ignore_bit >= n_bits) ZP_FAIL(ctx, -1, "bad n_bits/ignore_bit %d/%d", n_bits, ignore_bit);
+    if (mode != ZP_NONEXIST_ZERO && mode != ZP_NONEXIST_HAMMING) ZP_FAIL(ctx, -1, "bad nonexist mode %d", mode);
+    if (!pts) ZP_FAIL(ctx, -1, "null table");
+    ZP_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int k = ignore_bit, nb = n_bits - k;
+    const size_t np = (size_t)1 << nb, nc = (size_t)1 << k;
+    std::vector<double> val(np * 3);
+    std::vector<uint8_t> exists(np);
+    for (size_t p = 0; p < np; p++) {
+        double acc[3] = {0, 0, 0};
+        int cnt = 0;
+        for (size_t j = 0; j < nc; j++) {             // ascending child id, sequential float64 adds (generate_new_dict.py:25-31)
+            const double* c = pts + (p * nc + j) * 3;
+            bool nanrow = std::isnan(c[0]) || std::isnan(c[1]) || std::isnan(c[2]);
+            if (mode == ZP_NONEXIST_HAMMING && nanrow) continue;
+            acc[0] = acc[0] + c[0]; acc[1] = acc[1] + c[1]; acc[2] = acc[2] + c[2];
+            cnt++;
+        }
+        double div = mode == ZP_NONEXIST_HAMMING ? (double)cnt : (double)nc;
+        if (k == 0) { for (int e = 0; e < 3; e++) val[p * 3 + e] = mode == ZP_NONEXIST_HAMMING && cnt == 0 ? NAN : pts[p * 3 + e]; }
+        else { for (int e = 0; e < 3; e++) val[p * 3 + e] = cnt ? acc[e] / div : NAN; }
+        exists[p] = !(std::isnan(val[p * 3]) || std::isnan(val[p * 3 + 1]) || std::isnan(val[p * 3 + 2]));
+    }
+    std::vector<uint16_t> remap(np);
+    for (size_t p = 0; p < np; p++) remap[p] = (uint16_t)p;
+    if (mode == ZP_NONEXIST_HAMMING) {
+        // xor patterns ordered by (popcount, value): fewest flipped bits, then the least significant (finest) flips
+        std::vector<uint32_t> pat(np);
+        for (size_t x = 0; x < np; x++) pat[x] = (uint32_t)x;
+        std::sort(pat.begin(), pat.end(), [](uint32_t a, uint32_t b) {
+            int pa = __builtin_popcount(a), pb = __builtin_popcount(b);
+            return pa != pb ? pa < pb : a < b;
+        });
+        bool any = false;
+        for (size_t p = 0; p < np; p++) any = any || exists[p];
+        for (size_t p = 0; p < np && any; p++) {
+            if (exists[p]) continue;
+            for (size_t q = 1; q < np; q++) {
+                size_t e = p ^ pat[q];
+                if (exists[e]) { remap[p] = (uint16_t)e; break; }
+            }
+        }
+        if (!any) for (size_t p = 0; p < np; p++) remap[p] = 0;
+    }
+    std::vector<float> tab(np * 4);
+    for (size_t p = 0; p < np; p++) {
+        size_t s = remap[p];
+        bool ex = exists[s];
+        // non-existing rows: 3D point stays (0,0,0) and the pixel is kept (CNN_output_to_pose.py:58-62)
+        tab[p * 4 + 0] = ex ? (float)val[s * 3 + 0] : 0.f;
+        tab[p * 4 + 1] = ex ? (float)val[s * 3 + 1] : 0.f;
+        tab[p * 4 + 2] = ex ? (float)val[s * 3 + 2] : 0.f;
+        tab[p * 4 + 3] = exists[p] ? 1.f : 0.f;
+    }
+    ZpTable& t = ctx->tables[obj_id];
+    ZP_CUDA(ctx, cudaDeviceSynchronize());
+    if (t.pts) cudaFree(t.pts);
+    if (t.remap) cudaFree(t.remap);
+    t.pts = nullptr; t.remap = nullptr;
+    ZP_CUDA(ctx, cudaMalloc((void**)&t.pts, np * sizeof(float4)));
+    ZP_CUDA(ctx, cudaMalloc((void**)&t.remap, np * sizeof(uint16_t)));
+    ZP_CUDA(ctx, cudaMemcpy(t.pts, tab.data(), np * sizeof(float4), cudaMemcpyHostToDevice));
+    ZP_CUDA(ctx, cudaMemcpy(t.remap, remap.data(), np * sizeof(uint16_t), cudaMemcpyHostToDevice));
+    ZP_CUDA(ctx, cudaMemcpy((void*)(ctx->d_table_ptrs + obj_id), &t.pts, sizeof(float4*), cudaMemcpyHostToDevice));
+    t.n_bits = n_bits; t.ignore_bit = k; t.mode = mode;
+    return 0;
+}
+
+int zp_download_tables(zp_ctx* ctx, int obj_id, float* pts_out, uint16_t* remap_out) {
+    if (!ctx) return -1;
+    if (obj_id < 0 || obj_id >= ZP_MAX_OBJECTS || !ctx->tables[obj_id].pts) ZP_FAIL(ctx, -1, "no table in slot %d", obj_id);
+    const ZpTable& t = ctx->tables[obj_id];
+    size_t np = (size_t)1 << (t.n_bits - t.ignore_bit);
+    ZP_CUDA(ctx, cudaDeviceSynchronize());
+    if (pts_out) ZP_CUDA(ctx, cudaMemcpy(pts_out, t.pts, np * sizeof(float4), cudaMemcpyDeviceToHost));
+    if (remap_out) ZP_CUDA(ctx, cudaMemcpy(remap_out, t.remap, np * sizeof(uint16_t), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int zp_decode(zp_ctx* ctx, const void* logits, int dtype, int B, int S, const int64_t strides[4], int mask_ch,
+              int bit0_ch, int n_bits, int ignore_bit, const uint8_t* ext_mask, const double* bbox,
+              const int32_t* obj_ids, int obj_default, uint16_t* codes, float* corr, int cap, int32_t* counts,
+              void* stream) {
+    if (!ctx) return -1;
+    if (B == 0) return 0;
+    if (!logits || !bbox || !corr || !counts || !strides) ZP_FAIL(ctx, -1, "zp_decode: null argument");
+    if (dtype != ZP_DTYPE_F32 && dtype != ZP_DTYPE_BF16) ZP_FAIL(ctx, -1, "zp_decode: dtype %d not supported", dtype);
+    if (B < 0 || S <= 0 || S > 4096 || cap <= 0) ZP_FAIL(ctx, -1, "zp_decode: bad B/S/cap %d/%d/%d", B, S, cap);
+    if (n_bits < 1 || n_bits > 16 || ignore_bit < 0 || ignore_bit >= n_bits) ZP_FAIL(ctx, -1, "zp_decode: bad n_bits/ignore_bit");
+    if (!obj_ids) {
+        if (obj_default < 0 || obj_default >= ZP_MAX_OBJECTS || !ctx->tables[obj_default].pts)
+            ZP_FAIL(ctx, -1, "zp_decode: no dictionary uploaded for object slot %d", obj_default);
+        const ZpTable& t = ctx->tables[obj_default];
+        if (t.n_bits != n_bits || t.ignore_bit != ignore_bit)
+            ZP_FAIL(ctx, -1, "zp_decode: slot %d holds a %d-bit/ignore %d table, call asks %d/%d", obj_default, t.n_bits, t.ignore_bit, n_bits, ignore_bit);
+    }
+    ZP_CUDA(ctx, cudaSetDevice(ctx->device));
+    return zp_launch_decode(ctx, logits, dtype, B, S, strides, mask_ch, bit0_ch, n_bits - ignore_bit, ext_mask, bbox,
+                            obj_ids, obj_default, codes, corr, cap, counts, (cudaStream_t)stream);
+}
+
+int zp_remap_pixels(zp_ctx* ctx, const int64_t* px, int64_t N, const double* h_bbox, int S, int64_t* out, void* stream) {
+    if (!ctx) return -1;
+    if (N < 0 || S <= 0 || !h_bbox || (N > 0 && (!px || !out))) ZP_FAIL(ctx, -1, "zp_remap_pixels: bad argument");
+    ZP_CUDA(ctx, cudaSetDevice(ctx->device));
+    return zp_launch_remap_pixels(ctx, px, N, h_bbox, S, out, (cudaStream_t)stream);
+}
+
+int zp_codes_to_ids(zp_ctx* ctx, const double* bits, int64_t N, int L, int base, double* ids, void* stream) {
+    if (!ctx) return -1;
+    if (N < 0 || L < 1 || L > 64 || base < 2 || (N > 0 && (!bits || !ids))) ZP_FAIL(ctx, -1, "zp_codes_to_ids: bad argument");
+    ZP_CUDA(ctx, cudaSetDevice(ctx->device));
+    return zp_launch_codes_to_ids(ctx, bits, N, L, base, ids, (cudaStream_t)stream);
+}
+
+int zp_make_samples(zp_ctx* ctx, const int32_t* counts, int cap, int B, int H, int m, int mode, uint64_t seed,
+                    int32_t* samples, void* stream) {
+    if (!ctx) return -1;
+    if (B == 0) return 0;
+    if (!counts || !samples) ZP_FAIL(ctx, -1, "zp_make_samples: null argument");
+    if (m < 4 || m > 8 || H < 1 || H > ZP_MAX_HYPOTHESES) ZP_FAIL(ctx, -1, "zp_make_samples: bad m/H %d/%d", m, H);
+    ZP_CUDA(ctx, cudaSetDevice(ctx->device));
+    return zp_launch_samples(ctx, counts, cap, B, H, m, mode, seed, samples, (cudaStream_t)stream);
+}
+
+int zp_solve_minimal(zp_ctx* ctx, const float* corr, int cap, const int32_t* counts, const double* K,
+                     const int32_t* samples, int B, int H, int m, double* hyp_poses, void* stream) {
+    if (!ctx) return -1;
+    if (B == 0) return 0;
+    if (!corr || !counts || !K || !samples || !hyp_poses) ZP_FAIL(ctx, -1, "zp_solve_minimal: null argument");
+    if (m < 4 || m > 8 || H < 1 || H > ZP_MAX_HYPOTHESES) ZP_FAIL(ctx, -1, "zp_solve_minimal: bad m/H %d/%d", m, H);
+    ZP_CUDA(ctx, cudaSetDevice(ctx->device));
+    return zp_launch_minimal(ctx, corr, cap, counts, K, samples, B, H, m, hyp_poses, (cudaStream_t)stream);
+}
+
+static int check_corr(zp_ctx* ctx, const float* corr, int cap, const char* who) {
+    if (cap <= 0 || cap % 4 != 0) ZP_FAIL(ctx, -1, "%s: cap must be a positive multiple of 4 (TMA 16-byte granules), got %d", who, cap);
+    if ((uintptr_t)corr % 16 != 0) ZP_FAIL(ctx, -1, "%s: corr must be 16-byte aligned", who);
+    return 0;
+}
+
+int zp_score(zp_ctx* ctx, const float* corr, int cap, const int32_t* counts, const double* K, const double* hyp_poses,
+             int B, int H, float thr_px, int32_t* hyp_inliers, void* stream) {
+    if (!ctx) return -1;
+    if (B == 0) return 0;
+    if (!corr || !counts || !K || !hyp_poses || !hyp_inliers) ZP_FAIL(ctx, -1, "zp_score: null argument");
+    if (H < 1 || H > ZP_MAX_HYPOTHESES) ZP_FAIL(ctx, -1, "zp_score: bad H %d", H);
+    if (check_corr(ctx, corr, cap, "zp_score")) return -1;
+    ZP_CUDA(ctx, cudaSetDevice(ctx->device));
+    return zp_launch_score(ctx, corr, cap, counts, K, hyp_poses, B, H, thr_px, hyp_inliers, (cudaStream_t)stream);
+}
+
+static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+int zp_ransac(zp_ctx* ctx, const float* corr, int cap, const int32_t* counts, const double* K, const int32_t* samples,
+              int B, int H, int m, float thr_px, double confidence, int sampler, uint64_t seed, int select_mode,
+              int final_mode, double* hyp_poses, int32_t* hyp_inliers, int32_t* best_idx, uint8_t* inlier_mask,
+              double* poses, int32_t* n_inliers, int32_t* status, void* stream) {
+    if (!ctx) return -1;
+    if (B == 0) return 0;
+    if (!corr || !counts || !K || !poses || !n_inliers || !status) ZP_FAIL(ctx, -1, "zp_ransac: null argument");
+    if (m < 4 || m > 8 || H < 1 || H > ZP_MAX_HYPOTHESES) ZP_FAIL(ctx, -1, "zp_ransac: bad m/H %d/%d", m, H);
+    if (cap > 65536) ZP_FAIL(ctx, -1, "zp_ransac: cap %d > 65536 not supported", cap);
+    if (check_corr(ctx, corr, cap, "zp_ransac")) return -1;
+    ZP_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    // workspace: samples | hyp_poses | hyp_inliers | best_idx (only what the caller did not supply)
+    size_t o_s = 0, o_p = o_s + (samples ? 0 : align256((size_t)B * H * m * 4));
+    size_t o_i = o_p + (hyp_poses ? 0 : align256((size_t)B * H * 12 * 8));
+    size_t o_b = o_i + (hyp_inliers ? 0 : align256((size_t)B * H * 4));
+    size_t total = o_b + (best_idx ? 0 : align256((size_t)B * 4));
+    if (total && zp_ws_reserve(ctx, total)) return -2;
+    char* ws = (char*)ctx->ws;
+    int32_t* d_samples = nullptr;
+    if (!samples) {
+        d_samples = (int32_t*)(ws + o_s);
+        if (int r = zp_launch_samples(ctx, counts, cap, B, H, m, sampler, seed, d_samples, st)) return r;
+    }
+    double* d_hp = hyp_poses ? hyp_poses : (double*)(ws + o_p);
+    int32_t* d_hi = hyp_inliers ? hyp_inliers : (int32_t*)(ws + o_i);
+    int32_t* d_bi = best_idx ? best_idx : (int32_t*)(ws + o_b);
+    if (int r = zp_launch_minimal(ctx, corr, cap, counts, K, samples ? samples : d_samples, B, H, m, d_hp, st)) return r;
+    if (int r = zp_launch_score(ctx, corr, cap, counts, K, d_hp, B, H, thr_px, d_hi, st)) return r;
+    if (int r = zp_launch_select(ctx, counts, cap, d_hi, B, H, m, confidence, select_mode, d_bi, status, st)) return r;
+    return zp_launch_final(ctx, corr, cap, counts, K, d_hp, d_bi, status, B, H, thr_px, final_mode, poses, n_inliers,
+                           inlier_mask, st);
+}
+
+int zp_pose_batch_host(zp_ctx* ctx, const void* h_logits, int dtype, int B, int C, int S, int mask_ch, int bit0_ch,
+                       int n_bits, int ignore_bit, const double* h_bbox, const double* h_K, const int32_t* h_obj_ids,
+                       int obj_default, int H, int m, float thr_px, double confidence, int sampler, uint64_t seed,
+                       int select_mode, int final_mode, double* h_poses, int32_t* h_n_inliers, int32_t* h_status) {
+    if (!ctx) return -1;
+    if (B == 0) return 0;
+    if (!h_logits || !h_bbox || !h_K || !h_poses || !h_n_inliers || !h_status) ZP_FAIL(ctx, -1, "zp_pose_batch_host: null argument");
+    if (dtype != ZP_DTYPE_F32 && dtype != ZP_DTYPE_BF16) ZP_FAIL(ctx, -1, "zp_pose_batch_host: bad dtype");
+    ZP_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t esz = dtype == ZP_DTYPE_F32 ? 4 : 2;
+    const int cap = ((S * S + 3) / 4) * 4;
+    const size_t b_log = align256((size_t)B * C * S * S * esz), b_box = align256((size_t)B * 4 * 8), b_K = align256((size_t)B * 9 * 8),
+                 b_obj = align256((size_t)B * 4), b_corr = align256((size_t)B * 5 * cap * 4), b_cnt = align256((size_t)B * 4),
+                 b_pose = align256((size_t)B * 12 * 8), b_ni = align256((size_t)B * 4), b_st = align256((size_t)B * 4);
+    if (hws_reserve(ctx, b_log + b_box + b_K + b_obj + b_corr + b_cnt + b_pose + b_ni + b_st)) return -2;
+    char* p = (char*)ctx->hws;
+    void* d_log = p; p += b_log;
+    double* d_box = (double*)p; p += b_box;
+    double* d_K = (double*)p; p += b_K;
+    int32_t* d_obj = (int32_t*)p; p += b_obj;
+    float* d_corr = (float*)p; p += b_corr;
+    int32_t* d_cnt = (int32_t*)p; p += b_cnt;
+    double* d_pose = (double*)p; p += b_pose;
+    int32_t* d_ni = (int32_t*)p; p += b_ni;
+    int32_t* d_st = (int32_t*)p;
+    cudaStream_t st = ctx->own_stream;
+    ZP_CUDA(ctx, cudaMemcpyAsync(d_log, h_logits, (size_t)B * C * S * S * esz, cudaMemcpyHostToDevice, st));
+    ZP_CUDA(ctx, cudaMemcpyAsync(d_box, h_bbox, (size_t)B * 4 * 8, cudaMemcpyHostToDevice, st));
+    ZP_CUDA(ctx, cudaMemcpyAsync(d_K, h_K, (size_t)B * 9 * 8, cudaMemcpyHostToDevice, st));
+    if (h_obj_ids) ZP_CUDA(ctx, cudaMemcpyAsync(d_obj, h_obj_ids, (size_t)B * 4, cudaMemcpyHostToDevice, st));
+    int64_t strides[4] = {(int64_t)C * S * S, (int64_t)S * S, S, 1};
+    if (int r = zp_decode(ctx, d_log, dtype, B, S, strides, mask_ch, bit0_ch, n_bits, ignore_bit, nullptr, d_box,
+                          h_obj_ids ? d_obj : nullptr, obj_default, nullptr, d_corr, cap, d_cnt, st)) return r;
+    if (int r = zp_ransac(ctx, d_corr, cap, d_cnt, d_K, nullptr, B, H, m, thr_px, confidence, sampler, seed, select_mode,
+                          final_mode, nullptr, nullptr, nullptr, nullptr, d_pose, d_ni, d_st, st)) return r;
+    ZP_CUDA(ctx, cudaMemcpyAsync(h_poses, d_pose, (size_t)B * 12 * 8, cudaMemcpyDeviceToHost, st));
+    ZP_CUDA(ctx, cudaMemcpyAsync(h_n_inliers, d_ni, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
+    ZP_CUDA(ctx, cudaMemcpyAsync(h_status, d_st, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
+    ZP_CUDA(ctx, cudaStreamSynchronize(st));
+    return 0;
+}
+
+int zp_fp32_peak_probe(zp_ctx* ctx, int iters, double* out_tflops) {
+    if (!ctx || !out_tflops) return -1;
+    ZP_CUDA(ctx, cudaSetDevice(ctx->device));
+    return zp_launch_fma_probe(ctx, iters, out_tflops);
+}
+
+}  // extern "C"

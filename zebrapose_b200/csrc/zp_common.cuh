@@ -1,0 +1,73 @@
+// Shared declarations of the zebrapose_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include <vector>
+#include "../../include/zebrapose_b200.h"
+
+#define ZP_SM_COUNT_FALLBACK 148
+
+struct ZpTable {
+    float4* pts = nullptr;      // [2^(n_bits-k)] x,y,z,exists  (L2-resident, gathered per masked pixel)
+    uint16_t* remap = nullptr;  // [2^(n_bits-k)] Hamming-nearest existing code (identity in ZERO mode)
+    int n_bits = 0, ignore_bit = 0, mode = 0;
+};
+
+struct zp_ctx {
+    int device = 0;
+    int sm_count = ZP_SM_COUNT_FALLBACK;
+    std::string err;
+    ZpTable tables[ZP_MAX_OBJECTS];
+    const float4** d_table_ptrs = nullptr;   // device array [ZP_MAX_OBJECTS]
+    // growable device workspace
+    void* ws = nullptr;
+    size_t ws_bytes = 0;
+    // second workspace for the host-buffer entry (device copies of inputs/outputs)
+    void* hws = nullptr;
+    size_t hws_bytes = 0;
+    cudaStream_t own_stream = nullptr;
+    int64_t launches = 0;
+};
+
+#define ZP_FAIL(ctx, code, ...)                                  \
+    do {                                                         \
+        char _b[512];                                            \
+        snprintf(_b, sizeof(_b), __VA_ARGS__);                   \
+        (ctx)->err = _b;                                         \
+        return (code);                                           \
+    } while (0)
+
+#define ZP_CUDA(ctx, call)                                                                   \
+    do {                                                                                     \
+        cudaError_t _e = (call);                                                             \
+        if (_e != cudaSuccess)                                                               \
+            ZP_FAIL(ctx, -2, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__); \
+    } while (0)
+
+#define ZP_CHECK_LAUNCH(ctx, name)                                                           \
+    do {                                                                                     \
+        cudaError_t _e = cudaGetLastError();                                                 \
+        if (_e != cudaSuccess)                                                               \
+            ZP_FAIL(ctx, -3, "launch of %s failed: %s", name, cudaGetErrorString(_e));       \
+        (ctx)->launches++;                                                                   \
+    } while (0)
+
+int zp_ws_reserve(zp_ctx* ctx, size_t bytes);
+
+// streaming 128-bit load: read once, do not pollute L1
+__device__ __forceinline__ uint4 zp_ldg_stream(const void* p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+
+// kernels' host launchers (defined in the .cu files)
+int zp_launch_decode(zp_ctx* ctx, const void* logits, int dtype, int B, int S, const int64_t strides[4],
+                     int mask_ch, int bit0_ch, int nb, const uint8_t* ext_mask, const double* bbox,
+                     const int32_t* obj_ids, int obj_default, uint16_t* codes, float* corr, int cap,
+                     int32_t* counts, cudaStream_t st);

@@ -1,0 +1,261 @@
+"""Host side of the B200 pose path: device-resident batched API over the C ABI (include/zebrapose_b200.h).
+
+PyTorch is used for device memory, streams and torch.distributed only; all compute is in libzebrapose_b200.so.
+There is no CPU fallback: constructing an Engine without the library or without a CUDA device raises.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+
+_DT = {torch.float32: _lib.DTYPE_F32, torch.bfloat16: _lib.DTYPE_BF16}
+
+
+def dict_to_table(d, n_bits):
+    """Reference dictionary (load_dict_class_id_3D_points / generate_new_corres_dict: keys float or int, values
+    (3,) or (1,3) float64, NaN = non-existing) -> float64 [2^n_bits, 3] table.  Missing keys become NaN rows."""
+    if isinstance(d, np.ndarray):
+        t = np.ascontiguousarray(d, dtype=np.float64)
+        if t.shape != (1 << n_bits, 3):
+            raise ValueError("table must have shape (2^n_bits, 3), got %s" % (t.shape,))
+        return t
+    n = 1 << n_bits
+    if len(d) == n:
+        try:
+            return np.ascontiguousarray(np.stack([np.asarray(d[i], np.float64).reshape(3) for i in range(n)]))
+        except KeyError:
+            pass
+    tab = np.full((n, 3), np.nan)
+    for k, v in d.items():
+        tab[int(k)] = np.asarray(v, np.float64).reshape(3)
+    return tab
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p()
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class Engine:
+    """One context per device.  All tensor arguments live on that device; every call is asynchronous on the current
+    torch CUDA stream unless stated otherwise."""
+
+    def __init__(self, device=None):
+        if not torch.cuda.is_available():
+            raise _lib.ZpError("zebrapose_b200 needs a CUDA device (no CPU fallback)")
+        self.device = torch.device("cuda", torch.cuda.current_device() if device is None else
+                                   (device if isinstance(device, int) else torch.device(device).index or 0))
+        self.ctx = _lib.Context(self.device.index)
+        self.lib = self.ctx.lib
+        self._slots = {}
+
+    # ------------------------------------------------------------------ dictionaries
+    def upload_dict(self, obj_id, table_or_dict, n_bits=16, ignore_bit=0, nonexist="zero"):
+        """Replaces the per-crop dict look-ups (CNN_output_to_pose.py:58-62) + generate_new_corres_dict
+        (generate_new_dict.py:4-33): uploads the full n_bits dictionary; the ignore-bit parent table and the
+        non-existing-code handling are built by the library.  Synchronises."""
+        tab = dict_to_table(table_or_dict, n_bits)
+        rc = self.lib.zp_upload_tables(self.ctx.handle, int(obj_id), tab.ctypes.data_as(C.c_void_p), int(n_bits),
+                                       int(ignore_bit), _lib.NONEXIST[nonexist])
+        self.ctx.check(rc, "zp_upload_tables")
+        self._slots[int(obj_id)] = (int(n_bits), int(ignore_bit), nonexist)
+
+    def download_tables(self, obj_id):
+        n_bits, k, _ = self._slots[int(obj_id)]
+        n = 1 << (n_bits - k)
+        pts = np.empty((n, 4), np.float32)
+        remap = np.empty(n, np.uint16)
+        rc = self.lib.zp_download_tables(self.ctx.handle, int(obj_id), pts.ctypes.data_as(C.c_void_p),
+                                         remap.ctypes.data_as(C.c_void_p))
+        self.ctx.check(rc, "zp_download_tables")
+        return pts, remap
+
+    # ------------------------------------------------------------------ decode
+    def decode(self, logits, bboxes, obj_ids=None, *, obj_default=0, mask_ch=0, bit0_ch=1, n_bits=16, ignore_bit=0,
+               ext_mask=None, return_codes=False, cap=None):
+        """logits: cuda tensor [B,C,S,S] (fp32 | bf16, any strides) or the tuple (mask_logits, code_logits) the
+        reference network returns (views of one tensor, model/BinaryCodeNet.py:172).  bboxes [B,4] (x,y,w,h).
+        Returns corr f32 [B,5,cap], counts i32 [B] (, codes u16 [B,S,S])."""
+        if isinstance(logits, (tuple, list)):
+            logits, mask_ch, bit0_ch = self._join_views(*logits)
+        if logits.dim() != 4 or logits.shape[2] != logits.shape[3]:
+            raise ValueError("logits must be [B,C,S,S]")
+        if logits.dtype not in _DT:
+            raise TypeError("logits dtype %s not supported (float32 | bfloat16)" % logits.dtype)
+        if logits.device != self.device:
+            raise ValueError("logits live on %s, engine on %s" % (logits.device, self.device))
+        B, Cc, S, _ = logits.shape
+        if bit0_ch + (n_bits - ignore_bit) > Cc or mask_ch >= Cc:
+            raise ValueError("channel layout exceeds the %d channels of logits" % Cc)
+        cap = int(cap or ((S * S + 3) // 4) * 4)
+        bb = torch.as_tensor(bboxes).to(device=self.device, dtype=torch.float64).contiguous().reshape(B, 4)
+        oid = None
+        if obj_ids is not None:
+            oid = torch.as_tensor(obj_ids).to(device=self.device, dtype=torch.int32).contiguous()
+        em = None
+        if ext_mask is not None:
+            em = torch.as_tensor(ext_mask).to(device=self.device)
+            em = (em != 0).to(torch.uint8).contiguous().reshape(B, S, S)
+        corr = torch.empty((B, 5, cap), dtype=torch.float32, device=self.device)
+        counts = torch.empty((B,), dtype=torch.int32, device=self.device)
+        codes = torch.empty((B, S, S), dtype=torch.uint16, device=self.device) if return_codes else None
+        strides = (C.c_int64 * 4)(*logits.stride())
+        rc = self.lib.zp_decode(self.ctx.handle, _ptr(logits), _DT[logits.dtype], B, S, strides, int(mask_ch),
+                                int(bit0_ch), int(n_bits), int(ignore_bit), _ptr(em), _ptr(bb), _ptr(oid),
+                                int(obj_default), _ptr(codes), _ptr(corr), cap, _ptr(counts), _stream())
+        self.ctx.check(rc, "zp_decode")
+        return (corr, counts, codes) if return_codes else (corr, counts)
+
+    @staticmethod
+    def _join_views(mask_logits, code_logits):
+        """(mask, code) views of one [B,C,S,S] tensor -> (base tensor view, mask_ch, bit0_ch) without a copy."""
+        m, c = mask_logits, code_logits
+        same = (m.untyped_storage().data_ptr() == c.untyped_storage().data_ptr() and m.stride() == c.stride()
+                and m.dtype == c.dtype and m.shape[0] == c.shape[0] and m.shape[2:] == c.shape[2:])
+        if same:
+            sc = m.stride(1)
+            d = c.storage_offset() - m.storage_offset()
+            if sc > 0 and d % sc == 0 and d // sc >= m.shape[1]:
+                n_ch = d // sc + c.shape[1]
+                base = torch.as_strided(m, (m.shape[0], n_ch, m.shape[2], m.shape[3]), m.stride(), m.storage_offset())
+                return base, 0, d // sc
+        return torch.cat([m, c], 1), 0, m.shape[1]      # separate tensors: one device-side copy
+
+    # ------------------------------------------------------------------ RANSAC pieces
+    def make_samples(self, counts, cap, H=150, m=5, sampler="cv2", seed=0):
+        B = counts.shape[0]
+        s = torch.empty((B, H, m), dtype=torch.int32, device=self.device)
+        rc = self.lib.zp_make_samples(self.ctx.handle, _ptr(counts), int(cap), B, H, m, _lib.SAMPLER[sampler],
+                                      int(seed), _ptr(s), _stream())
+        self.ctx.check(rc, "zp_make_samples")
+        return s
+
+    def _Ks(self, Ks, B):
+        K = torch.as_tensor(Ks).to(device=self.device, dtype=torch.float64)
+        if K.numel() == 9:
+            K = K.reshape(1, 9).expand(B, 9)
+        return K.reshape(B, 9).contiguous()
+
+    def solve_minimal(self, corr, counts, Ks, samples):
+        B, _, cap = corr.shape
+        _, H, m = samples.shape
+        K = self._Ks(Ks, B)
+        hp = torch.empty((B, H, 12), dtype=torch.float64, device=self.device)
+        rc = self.lib.zp_solve_minimal(self.ctx.handle, _ptr(corr), cap, _ptr(counts), _ptr(K), _ptr(samples), B, H, m,
+                                       _ptr(hp), _stream())
+        self.ctx.check(rc, "zp_solve_minimal")
+        return hp
+
+    def score(self, corr, counts, Ks, hyp_poses, thr=2.0):
+        B, _, cap = corr.shape
+        H = hyp_poses.shape[1]
+        K = self._Ks(Ks, B)
+        hp = torch.as_tensor(hyp_poses).to(device=self.device, dtype=torch.float64).contiguous()
+        out = torch.empty((B, H), dtype=torch.int32, device=self.device)
+        rc = self.lib.zp_score(self.ctx.handle, _ptr(corr), cap, _ptr(counts), _ptr(K), _ptr(hp), B, H, float(thr),
+                               _ptr(out), _stream())
+        self.ctx.check(rc, "zp_score")
+        return out
+
+    def ransac(self, corr, counts, Ks, *, samples=None, H=150, m=5, thr=2.0, conf=0.99, sampler="cv2", seed=0,
+               select="cv2_replay", final="epnp", return_details=False):
+        """Returns dict(poses f64 [B,12], n_inliers i32 [B], status i32 [B] [, hyp_poses, hyp_inliers, best_idx,
+        inlier_mask])."""
+        B, _, cap = corr.shape
+        if samples is not None:
+            H, m = samples.shape[1], samples.shape[2]
+        K = self._Ks(Ks, B)
+        out = dict(poses=torch.empty((B, 12), dtype=torch.float64, device=self.device),
+                   n_inliers=torch.empty((B,), dtype=torch.int32, device=self.device),
+                   status=torch.empty((B,), dtype=torch.int32, device=self.device))
+        hp = hi = bi = im = None
+        if return_details:
+            hp = out["hyp_poses"] = torch.empty((B, H, 12), dtype=torch.float64, device=self.device)
+            hi = out["hyp_inliers"] = torch.empty((B, H), dtype=torch.int32, device=self.device)
+            bi = out["best_idx"] = torch.empty((B,), dtype=torch.int32, device=self.device)
+            im = out["inlier_mask"] = torch.empty((B, cap), dtype=torch.uint8, device=self.device)
+        rc = self.lib.zp_ransac(self.ctx.handle, _ptr(corr), cap, _ptr(counts), _ptr(K), _ptr(samples), B, int(H),
+                                int(m), float(thr), float(conf), _lib.SAMPLER[sampler], int(seed),
+                                _lib.SELECT[select], _lib.FINAL[final], _ptr(hp), _ptr(hi), _ptr(bi), _ptr(im),
+                                _ptr(out["poses"]), _ptr(out["n_inliers"]), _ptr(out["status"]), _stream())
+        self.ctx.check(rc, "zp_ransac")
+        return out
+
+    # ------------------------------------------------------------------ the batched entry (what the bench times)
+    def decode_and_pose_batch(self, logits, bboxes, Ks, obj_ids=None, *, obj_default=0, mask_ch=0, bit0_ch=1,
+                              n_bits=16, ignore_bit=0, ext_mask=None, m=5, iters=150, thr=2.0, conf=0.99,
+                              sampler="cv2", seed=0, select="cv2_replay", final="epnp"):
+        """Device logits in, device poses out, no host copy: poses f64 [B,12] (R row-major | t mm),
+        n_inliers i32 [B], status i32 [B] (0 ok, 1 no mask pixel, 2 < 6 correspondences, 3 RANSAC found no model)."""
+        corr, counts = self.decode(logits, bboxes, obj_ids, obj_default=obj_default, mask_ch=mask_ch, bit0_ch=bit0_ch,
+                                   n_bits=n_bits, ignore_bit=ignore_bit, ext_mask=ext_mask)
+        r = self.ransac(corr, counts, Ks, H=iters, m=m, thr=thr, conf=conf, sampler=sampler, seed=seed, select=select,
+                        final=final)
+        return r["poses"], r["n_inliers"], r["status"]
+
+    def pose_batch_host(self, logits, bboxes, Ks, obj_ids=None, *, obj_default=0, mask_ch=0, bit0_ch=1, n_bits=16,
+                        ignore_bit=0, m=5, iters=150, thr=2.0, conf=0.99, sampler="cv2", seed=0, select="cv2_replay",
+                        final="epnp", out=None):
+        """HOST numpy / pinned-tensor buffers in, HOST results out, through zp_pose_batch_host (H2D + chain + D2H
+        inside one C call; synchronous).  logits [B,C,S,S] contiguous float32 (numpy) or a CPU torch tensor."""
+        lg = logits if isinstance(logits, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(logits))
+        if lg.is_cuda or not lg.is_contiguous():
+            raise ValueError("pose_batch_host takes contiguous HOST logits")
+        B, Cc, S, _ = lg.shape
+        bb = np.ascontiguousarray(np.asarray(bboxes, np.float64).reshape(B, 4))
+        K = np.asarray(Ks, np.float64)
+        K = np.ascontiguousarray(np.broadcast_to(K.reshape(-1, 9), (B, 9)))
+        oid = None if obj_ids is None else np.ascontiguousarray(np.asarray(obj_ids, np.int32))
+        if out is None:
+            out = (np.empty((B, 12)), np.empty(B, np.int32), np.empty(B, np.int32))
+        poses, ninl, status = out
+        rc = self.lib.zp_pose_batch_host(
+            self.ctx.handle, C.c_void_p(lg.data_ptr()), _DT[lg.dtype], B, Cc, S, int(mask_ch), int(bit0_ch), int(n_bits),
+            int(ignore_bit), bb.ctypes.data_as(C.c_void_p), K.ctypes.data_as(C.c_void_p),
+            oid.ctypes.data_as(C.c_void_p) if oid is not None else C.c_void_p(), int(obj_default), int(iters), int(m),
+            float(thr), float(conf), _lib.SAMPLER[sampler], int(seed), _lib.SELECT[select], _lib.FINAL[final],
+            poses.ctypes.data_as(C.c_void_p), ninl.ctypes.data_as(C.c_void_p), status.ctypes.data_as(C.c_void_p))
+        self.ctx.check(rc, "zp_pose_batch_host")
+        return poses, ninl, status
+
+    # ------------------------------------------------------------------ small stand-alone helpers
+    def remap_pixels(self, pixels, bbox, S):
+        px = torch.as_tensor(np.ascontiguousarray(pixels, dtype=np.int64)).to(self.device)
+        out = torch.empty_like(px)
+        bb = np.ascontiguousarray(np.asarray(bbox, np.float64).reshape(4))
+        rc = self.lib.zp_remap_pixels(self.ctx.handle, _ptr(px), px.shape[0], bb.ctypes.data_as(C.c_void_p), int(S),
+                                      _ptr(out), _stream())
+        self.ctx.check(rc, "zp_remap_pixels")
+        return out
+
+    def codes_to_ids(self, bits, base=2):
+        b = torch.as_tensor(np.ascontiguousarray(bits, dtype=np.float64)).to(self.device)
+        N, L = b.shape
+        out = torch.empty((N,), dtype=torch.float64, device=self.device)
+        rc = self.lib.zp_codes_to_ids(self.ctx.handle, _ptr(b), N, L, int(base), _ptr(out), _stream())
+        self.ctx.check(rc, "zp_codes_to_ids")
+        return out
+
+    def launch_count(self):
+        return int(self.lib.zp_launch_count(self.ctx.handle))
+
+    def fp32_peak_tflops(self, iters=20000):
+        v = C.c_double()
+        self.ctx.check(self.lib.zp_fp32_peak_probe(self.ctx.handle, int(iters), C.byref(v)), "zp_fp32_peak_probe")
+        return v.value
+
+
+_default = {}
+
+
+def default_engine(device=None):
+    """Process-wide engine per device, created on first use (what the drop-in functions call)."""
+    idx = torch.cuda.current_device() if device is None else device
+    if idx not in _default:
+        _default[idx] = Engine(idx)
+    return _default[idx]
