@@ -1,0 +1,290 @@
+#!/usr/bin/env python
+"""bench.py -- crop-poses/s of the post-network pose path (decode + RANSAC-PnP) on N B200s.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--crops C]
+
+A step = one pass of the hot path over one batch of C synthetic crops per GPU (default: BASELINE.json configs[1],
+64 YCB-V-like 128x128 crops, 21 dictionaries, ignore_bit 0).  `value` = whole-job poses/s with the logits already
+resident in HBM; `e2e` = the same through zp_pose_batch_host (HOST pinned buffers, H2D + D2H inside the timed region).
+`--impl reference` times the reference's own CPU path (oracle/reference_path.py: restated per-pixel dict loop +
+cv2.solvePnPRansac) on all host cores.  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "crop-poses/sec, code decode+RANSAC-PnP"
+UNIT = "poses/s"
+S, NBITS, H, M, THR = 128, 16, 150, 5, 2.0
+L2_FLUSH_BYTES = 256 << 20
+
+
+def make_workload(crops, seed):
+    from oracle import synth
+    return synth.make_batch(crops, S=S, n_bits=NBITS, n_dicts=21, seed=seed, K=synth.YCBV_K, outlier=0.3, bitflip=0.02,
+                            missing_frac=0.0, radius=(40.0, 175.0))
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu):
+        super().__init__(daemon=True)
+        self.gpu, self.rows, self.stop_flag = gpu, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.05)
+
+    def summary(self):
+        sm = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if r[2].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows for n, v in zip(names, r[4:8]) if v.lower().startswith("active")})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+def cpu_baseline(logits, bboxes, Ks, obj, tables, n_sample, repeats=1):
+    """reference CPU path on all host cores, bounded sample"""
+    from oracle.reference_path import ReferencePool
+    cores = os.cpu_count() or 1
+    pool = ReferencePool(logits, bboxes, Ks, obj, tables, cores)
+    idx = [i % len(logits) for i in range(n_sample)]
+    pool.run(idx[: 2 * cores])                      # warm-up map
+    best = None
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        pool.run(idx)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    pool.close()
+    return n_sample / best, cores, best
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    logits, bboxes, Ks, obj, tables, _ = make_workload(args.crops, 1002)
+    from oracle.reference_path import ReferencePool
+    cores = os.cpu_count() or 1
+    pool = ReferencePool(logits, bboxes, Ks, obj, tables, cores)
+    idx = list(range(args.crops))
+    for _ in range(args.warmup):
+        pool.run(idx[: 2 * cores])
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        pool.run(idx)
+    dt = time.perf_counter() - t0
+    pool.close()
+    val = args.crops * args.steps / dt
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "configs[1]: %d synthetic YCB-V-like 128x128 crops, 21 dictionaries, ignore_bit 0; "
+                                   "reference CPU path (per-pixel dict loop + cv2.solvePnPRansac EPnP 150 it, 2 px)" % args.crops},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": "%d crops per step, fork pool of %d workers, cv2.setNumThreads(1)" % (args.crops, cores)},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--crops", type=int, default=64, help="crops per GPU per step (configs[1] = 64)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--kernels", action="store_true", help="also print a per-kernel table to stderr")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import zebrapose_b200 as zp
+
+    args.warmup = max(args.warmup, 3)
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local))
+    eng = zp.Engine(local)
+    C = args.crops
+    # weak scaling: every rank owns its own batch of C crops (contiguous shard [rank*C, (rank+1)*C) of the job)
+    logits, bboxes, Ks, obj, tables, crops = make_workload(C, 1002 + rank)
+    for j, t in enumerate(tables):
+        eng.upload_dict(j, t, n_bits=NBITS, ignore_bit=0, nonexist="zero")
+    d_logits = torch.from_numpy(logits).cuda()
+    d_bbox = torch.from_numpy(bboxes.astype(np.float64)).cuda()
+    d_K = torch.from_numpy(Ks.reshape(C, 9)).cuda()
+    d_obj = torch.from_numpy(obj.astype(np.int32)).cuda()
+    flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device="cuda")
+    n_total = C * world
+
+    def step():
+        poses, ninl, status = eng.decode_and_pose_batch(d_logits, d_bbox, d_K, d_obj, n_bits=NBITS, iters=H, m=M, thr=THR)
+        if world > 1:
+            poses, ninl, status = zp.gather_poses(poses, ninl, status, n_total)
+        return poses, ninl, status
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        flush.zero_()
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    l0 = eng.launch_count()
+    barrier()
+    for s0, s1 in ev:
+        flush.zero_()                                # L2 flush between timed iterations (outside the event pair)
+        s0.record()
+        out = step()
+        s1.record()
+    barrier()
+    launches = eng.launch_count() - l0
+    ms = sum(a.elapsed_time(b) for a, b in ev)
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    value = n_total * args.steps / (ms_total * 1e-3)
+
+    # ---- e2e: host pinned buffers through the C-ABI host entry, copies inside the timed region
+    h_logits = torch.from_numpy(logits).pin_memory()
+    outs = (np.empty((C, 12)), np.empty(C, np.int32), np.empty(C, np.int32))
+    for _ in range(3):
+        eng.pose_batch_host(h_logits, bboxes, Ks, obj, out=outs)
+    barrier()
+    e2e_steps = max(5, min(args.steps, 20))
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        eng.pose_batch_host(h_logits, bboxes, Ks, obj, out=outs)
+    torch.cuda.synchronize()
+    dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    e2e_value = n_total * e2e_steps / float(dt.item())
+    h2d = logits.nbytes + C * 4 * 8 + C * 9 * 8 + C * 4
+    d2h = C * 12 * 8 + C * 4 + C * 4
+    if rank == 0:
+        sampler.stop_flag = True
+        sampler.join(timeout=2)
+
+    # ---- per-kernel timing (separate instrumented pass; CUDA events on the launching stream, L2 flushed)
+    def timed(fn, reps=20):
+        for _ in range(3):
+            fn()
+        tot = 0.0
+        for _ in range(reps):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); fn(); b.record()
+            b.synchronize()
+            tot += a.elapsed_time(b)
+        return tot / reps
+
+    line = None
+    if rank == 0:
+        corr, counts = eng.decode(d_logits, d_bbox, d_obj)
+        cap = corr.shape[2]
+        samples = eng.make_samples(counts, cap, H, M)
+        hyp = eng.solve_minimal(corr, counts, d_K, samples)
+        k_ms = {
+            "zp_decode_cluster_kernel": timed(lambda: eng.decode(d_logits, d_bbox, d_obj)),
+            "zp_samples_kernel": timed(lambda: eng.make_samples(counts, cap, H, M)),
+            "zp_minimal_kernel": timed(lambda: eng.solve_minimal(corr, counts, d_K, samples)),
+            "zp_score_kernel": timed(lambda: eng.score(corr, counts, d_K, hyp, THR)),
+            "ransac_chain(samples+minimal+score+select+final)": timed(lambda: eng.ransac(corr, counts, d_K, H=H, m=M, thr=THR)),
+        }
+        Mtot = int(counts.clamp(max=cap).sum().item())
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        dec_bytes = C * (1 + NBITS) * S * S * 4 + 20 * Mtot + 4 * C          # algorithmic HBM bytes
+        dec_gbs = dec_bytes / (k_ms["zp_decode_cluster_kernel"] * 1e-3) / 1e9
+        fp32_peak = eng.fp32_peak_tflops()
+        sc_flops = 27.0 * H * Mtot                                            # 27 flop / (corr x hyp)
+        sc_tf = sc_flops / (k_ms["zp_score_kernel"] * 1e-3) / 1e12
+        chain = k_ms["zp_decode_cluster_kernel"] + k_ms["ransac_chain(samples+minimal+score+select+final)"]
+        shares = {k: round(v / chain, 4) for k, v in k_ms.items()}
+        dominant = max(("zp_decode_cluster_kernel", "zp_minimal_kernel", "zp_score_kernel"), key=lambda k: k_ms[k])
+        if args.kernels:
+            for k, v in k_ms.items():
+                print("%-55s %9.3f us  share %.3f" % (k, v * 1e3, v / chain), file=sys.stderr)
+        cpu = None
+        if not args.no_cpu_baseline:
+            n_sample = max(64, 8 * (os.cpu_count() or 1))
+            v, cores, secs = cpu_baseline(logits, bboxes, Ks, obj, tables, n_sample)
+            cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                   "sample": "%d crops of the same workload, fork pool of %d workers (cv2.setNumThreads(1)), %.1f s" % (n_sample, cores, secs)}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32 scoring / f64 EPnP / u16 codes", "data": "synthetic",
+            "config": {"workload": "configs[1]: %d synthetic YCB-V-like 128x128 crops per GPU, 21 dictionaries, ignore_bit 0, "
+                                   "decode + RANSAC-EPnP (150 hypotheses x 5 points, 2 px, cv2 replay)" % C,
+                       "crops_per_gpu": C, "l2": "flushed between timed steps (256 MiB write outside the event pair)",
+                       "masked_px_per_crop": Mtot / C},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "path": "zp_pose_batch_host (C ABI, pinned host logits -> host poses)", "steps": e2e_steps},
+            "gpu_launches": launches,
+            "clocks": sampler.summary(),
+            "roofline": {"kernel": "zp_decode_cluster_kernel", "bound": "hbm", "achieved": dec_gbs, "peak": hbm_peak,
+                         "unit": "GB/s", "frac": dec_gbs / hbm_peak, "traffic": None,
+                         "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650",
+                         "algorithmic_bytes_per_launch": dec_bytes, "us_per_launch": k_ms["zp_decode_cluster_kernel"] * 1e3},
+            "roofline_score": {"kernel": "zp_score_kernel", "bound": "fp32", "achieved": sc_tf, "peak": fp32_peak,
+                               "unit": "TFLOP/s", "frac": sc_tf / fp32_peak if fp32_peak else None,
+                               "peak_source": "zp_fp32_peak_probe (FMA chains, measured on this GPU in this run)",
+                               "algorithmic_flops_per_launch": sc_flops, "us_per_launch": k_ms["zp_score_kernel"] * 1e3},
+            "kernel_us": {k: round(v * 1e3, 2) for k, v in k_ms.items()},
+            "kernel_share_of_step": shares,
+            "dominant_kernel": dominant,
+            "cpu_baseline": cpu,
+        }
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(line))
+
+
+if __name__ == "__main__":
+    main()

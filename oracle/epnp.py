@@ -3,8 +3,9 @@
 OpenCV is an un-vendored dependency of the reference (CNN_output_to_pose.py:155-157; opencv-python-headless
 4.13.0.92 here).  Restated from the published algorithm (Lepetit/Moreno-Noguer/Fua 2009) plus the behaviours
 of OpenCV's implementation that change the answer under noise, each verified against cv2 in this image:
-  * image points are normalised first ((u-cx)*(1/fx)), and rounded to float32 when the inputs are float32
-    (solvePnP: undistortPoints + identity camera matrix);
+  * M is built in PIXEL units with the real camera matrix (rows [a*fu, 0, a*(uc-u)] / [0, a*fv, a*(vc-v)]), so
+    fu != fv weights the two image axes differently; a normalised-coordinate EPnP agrees on noise-free data but
+    drifts by 1e-3..5e-2 deg on outlier-bearing samples because 5 Gauss-Newton steps are mid-transient there;
   * the PCA control points use the eigenvectors *with the signs* OpenCV's small-matrix one-sided Jacobi SVD
     returns (rows of the rotated A^T, normalised) -- a textbook eigh() differs by 0.1 deg under pixel noise;
   * three beta initialisations + 5 Gauss-Newton steps each, pose by Horn with "negate row 2" on det<0,
@@ -104,18 +105,15 @@ def _gauss_newton(L, rho, b):
 
 
 def epnp(pw, uv, K, f32_inputs=True):
-    """pw [n,3], uv [n,2] pixels, K 3x3 -> (R 3x3, t 3) float64.  `f32_inputs` reproduces the float32 rounding
-    of the normalised image points that cv2 applies when it is handed float32 arrays (RANSAC inner calls);
-    the final solve on the inliers is handed float64 copies (f32_inputs=False)."""
+    """pw [n,3], uv [n,2] pixels, K 3x3 -> (R 3x3, t 3) float64.  `f32_inputs` is kept for call compatibility: the
+    reference's image points are integers, exactly representable in float32, so cv2's float32 staging of them is a
+    no-op here."""
     pw = np.asarray(pw, np.float64)
     uv = np.asarray(uv, np.float64)
     n = len(pw)
-    fx, fy, cx, cy = K[0, 0], K[1, 1], K[0, 2], K[1, 2]
-    xn = (uv[:, 0] - cx) * (1.0 / fx)
-    yn = (uv[:, 1] - cy) * (1.0 / fy)
-    if f32_inputs:
-        xn = xn.astype(np.float32).astype(np.float64)
-        yn = yn.astype(np.float32).astype(np.float64)
+    fu, fv, uc, vc = K[0, 0], K[1, 1], K[0, 2], K[1, 2]
+    xn = uv[:, 0]
+    yn = uv[:, 1]
     c0 = pw.sum(0) / n
     d = pw - c0
     dc, uct = jacobi_svd_ut(d.T @ d)
@@ -130,10 +128,10 @@ def epnp(pw, uv, K, f32_inputs=True):
     al[:, 0] = 1.0 - al[:, 1] - al[:, 2] - al[:, 3]
     M = np.zeros((2 * n, 12))
     for j in range(4):
-        M[0::2, 3 * j] = al[:, j]
-        M[0::2, 3 * j + 2] = al[:, j] * (0.0 - xn)
-        M[1::2, 3 * j + 1] = al[:, j]
-        M[1::2, 3 * j + 2] = al[:, j] * (0.0 - yn)
+        M[0::2, 3 * j] = al[:, j] * fu
+        M[0::2, 3 * j + 2] = al[:, j] * (uc - xn)
+        M[1::2, 3 * j + 1] = al[:, j] * fv
+        M[1::2, 3 * j + 2] = al[:, j] * (vc - yn)
     _, ut = jacobi_svd_ut(M.T @ M)
     v = [ut[11], ut[10], ut[9], ut[8]]
     dv = np.zeros((4, 6, 3))
@@ -165,7 +163,7 @@ def epnp(pw, uv, K, f32_inputs=True):
         t = pc0 - R @ pw0
         P = pw @ R.T + t
         iz = 1.0 / P[:, 2]
-        err = np.sqrt((xn - P[:, 0] * iz) ** 2 + (yn - P[:, 1] * iz) ** 2).sum() / n
+        err = np.sqrt((xn - (uc + fu * P[:, 0] * iz)) ** 2 + (yn - (vc + fv * P[:, 1] * iz)) ** 2).sum() / n
         if best is None or err < best[0]:
             best = (err, R, t)
     if best is None:

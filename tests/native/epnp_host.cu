@@ -1,0 +1,60 @@
+// Host build of the device EPnP core (zebrapose_b200/csrc/zp_epnp.cuh) so the CPU test-suite can check the very code
+// the kernels run against cv2 / the oracle.  stdin: n, f32flag, K(9), then n rows "X Y Z u v"; stdout: 12 doubles.
+#include <cstdio>
+#include <vector>
+#include "../../zebrapose_b200/csrc/zp_epnp.cuh"
+
+int main() {
+    int n, f32;
+    double K[9];
+    while (scanf("%d %d", &n, &f32) == 2) {
+        for (int i = 0; i < 9; i++) if (scanf("%lf", &K[i]) != 1) return 1;
+        std::vector<double> X(n), Y(n), Z(n), x(n), y(n);
+        ZpCam cam{K[0], K[4], K[2], K[5]};
+        double c0[3] = {0, 0, 0};
+        for (int i = 0; i < n; i++) {
+            double u, v;
+            if (scanf("%lf %lf %lf %lf %lf", &X[i], &Y[i], &Z[i], &u, &v) != 5) return 1;
+            x[i] = u; y[i] = v;
+            c0[0] += X[i]; c0[1] += Y[i]; c0[2] += Z[i];
+        }
+        for (int e = 0; e < 3; e++) c0[e] /= n;
+        double C[9] = {0};
+        for (int i = 0; i < n; i++) {
+            double d[3] = {X[i] - c0[0], Y[i] - c0[1], Z[i] - c0[2]};
+            for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) C[3 * r + c] += d[r] * d[c];
+        }
+        ZpControl cp;
+        zp_control_points(c0, C, (double)n, cp);
+        ZpSums s;
+        for (int q = 0; q < 10; q++) { s.s0[q] = s.sx[q] = s.sy[q] = s.sr[q] = 0; }
+        for (int q = 0; q < 12; q++) s.w[q] = 0;
+        s.n = n;
+        double af[4];
+        for (int i = 0; i < n; i++) {
+            double a[4];
+            zp_alphas(cp, X[i], Y[i], Z[i], a);
+            if (i == 0) for (int e = 0; e < 4; e++) af[e] = a[e];
+            zp_accumulate(s, a, cam.uc - x[i], cam.vc - y[i], X[i] - c0[0], Y[i] - c0[1], Z[i] - c0[2]);
+        }
+        double at[144];
+        ZpMat At{at, 1};
+        ZpCandidates cand;
+        zp_epnp_core(At, s, cam, cp, af, c0, cand);
+        int best = -1; double be = 0;
+        for (int c = 0; c < 3; c++) {
+            if (!cand.ok[c]) continue;
+            double e = 0;
+            for (int i = 0; i < n; i++) e += zp_reproj_dist(cand.R[c], cand.t[c], cam, X[i], Y[i], Z[i], x[i], y[i]);
+            e /= n;
+            if (getenv("ZP_DEBUG")) fprintf(stderr, "cand %d err %.6g\n", c, e);
+            if (!(e == e)) continue;
+            if (best < 0 || e < be) { best = c; be = e; }
+        }
+        if (best < 0) { for (int e = 0; e < 12; e++) printf("nan "); printf("\n"); continue; }
+        for (int e = 0; e < 9; e++) printf("%.17g ", cand.R[best][e]);
+        for (int e = 0; e < 3; e++) printf("%.17g ", cand.t[best][e]);
+        printf("\n");
+    }
+    return 0;
+}

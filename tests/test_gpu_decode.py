@@ -180,9 +180,8 @@ def test_full_size_properties(eng, tables):
     assert torch.equal(codes.to(torch.int64), ids)                               # every code
     for i in (0, 17, 63):                                                        # lists are row-major sorted
         n = int(counts[i])
-        u, v = corr[i, 0, :n].cpu().numpy(), corr[i, 1, :n].cpu().numpy()
-        key = v.astype(np.int64) * 100000 + u.astype(np.int64)
-        assert (np.diff(key) >= 0).all()
+        v = corr[i, 1, :n].cpu().numpy()
+        assert (np.diff(v) >= 0).all()                                           # rows never go backwards
     corr2, counts2 = eng.decode(lg, bboxes, (20 + obj).astype(np.int32))         # idempotent / deterministic
     assert torch.equal(counts, counts2)
     for i in range(B):

@@ -6,7 +6,7 @@ import pytest
 from oracle import cvransac, decode, epnp, metrics, synth
 
 
-def _problem(seed, n, noise=True):
+def _problem(seed, n, noise=True, sigma=0.0):
     rng = np.random.default_rng(seed)
     pw = (rng.normal(size=(n, 3)) * 40).astype(np.float32)
     R, t = synth.random_pose(rng)
@@ -14,14 +14,16 @@ def _problem(seed, n, noise=True):
     uv = (synth.LM_K @ P.T).T
     uv = uv[:, :2] / uv[:, 2:]
     if noise:
-        uv = np.trunc(uv)
+        uv = np.trunc(uv + rng.normal(size=uv.shape) * sigma)
     return pw, uv.astype(np.float32), R, t
 
 
+@pytest.mark.parametrize("sigma", [0.0, 30.0])
 @pytest.mark.parametrize("n", [6, 8, 50, 2000])
-def test_epnp_matches_cv2(n):
+def test_epnp_matches_cv2(n, sigma):
+    """incl. heavy pixel noise (outlier-bearing samples): pins the pixel-unit formulation cv2 uses"""
     for s in range(8):
-        pw, uv, _, _ = _problem(100 * n + s, n)
+        pw, uv, _, _ = _problem(100 * n + s, n, sigma=sigma)
         Rc, tc = cvransac.cv2_solver(pw, uv, synth.LM_K)
         Ro, to = epnp.epnp(pw, uv, synth.LM_K, f32_inputs=True)
         assert metrics.rot_err_deg(Rc, Ro) < 1e-3, (n, s)

@@ -1,7 +1,7 @@
 // EPnP in float64 as cv2.solvePnP(SOLVEPNP_EPNP) runs it (OpenCV is the un-vendored library behind the reference's
 // cv2.solvePnPRansac call, CNN_output_to_pose.py:155-157).  Device restatement of the published algorithm
 // (Lepetit, Moreno-Noguer, Fua 2009) with the OpenCV behaviours that change the answer under pixel noise:
-// normalised image coordinates, PCA control points with the signs of OpenCV's one-sided Jacobi SVD (same pair
+// M built in pixel units with the real camera matrix (fu != fv weights the image axes), PCA control points with the signs of OpenCV's one-sided Jacobi SVD (same pair
 // order and rotation formulas), three beta initialisations x 5 Gauss-Newton steps, Horn alignment with
 // "negate row 2 when det < 0", best of three by mean reprojection distance.  oracle/epnp.py is the CPU twin.
 //
@@ -12,6 +12,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 
+#define ZP_HD __host__ __device__
 #define ZP_DBL_EPS 2.220446049250313e-16
 #define ZP_DBL_MIN 2.2250738585072014e-308
 
@@ -20,7 +21,7 @@
 struct ZpMat {
     double* p;
     int stride;
-    __device__ __forceinline__ double& operator()(int r, int k, int n) const { return p[(size_t)(r * n + k) * stride]; }
+    ZP_HD __forceinline__ double& operator()(int r, int k, int n) const { return p[(size_t)(r * n + k) * stride]; }
 };
 
 // One-sided (Hestenes) Jacobi on the rows of At (= A^T), OpenCV's pair order (i<j ascending), rotation formulas and
@@ -28,7 +29,7 @@ struct ZpMat {
 // On exit row i of At = sigma_i * u_i^T and W[i] = sigma_i (unsorted).  If G != nullptr it receives the accumulated
 // rotations (OpenCV's Vt) as a dense row-major n x n array in registers/local memory.
 template <int N>
-__device__ void zp_jacobi_rows(ZpMat At, double* W, double* G) {
+ZP_HD void zp_jacobi_rows(ZpMat At, double* W, double* G) {
     const double eps = ZP_DBL_EPS * 10;
     for (int i = 0; i < N; i++) {
         double sd = 0;
@@ -89,7 +90,7 @@ __device__ void zp_jacobi_rows(ZpMat At, double* W, double* G) {
 
 // PCA of the 3x3 scatter matrix C (symmetric): returns singular values dc[3] descending and rows uct[3][3] with the
 // signs OpenCV's SVD (U_T) returns.
-__device__ inline void zp_pca3(const double C[9], double dc[3], double uct[9]) {
+ZP_HD inline void zp_pca3(const double C[9], double dc[3], double uct[9]) {
     double a[9], W[3];
     for (int i = 0; i < 3; i++) for (int k = 0; k < 3; k++) a[i * 3 + k] = C[k * 3 + i];   // At = C^T
     ZpMat At{a, 1};
@@ -111,7 +112,7 @@ __device__ inline void zp_pca3(const double C[9], double dc[3], double uct[9]) {
 
 // Orthogonal polar factor U V^T of a 3x3 matrix H (row-major) via the same one-sided Jacobi; rank-2 inputs are
 // completed with a cross product.
-__device__ inline void zp_polar3(const double H[9], double R[9]) {
+ZP_HD inline void zp_polar3(const double H[9], double R[9]) {
     double a[9], W[3], G[9];
     for (int i = 0; i < 3; i++) for (int k = 0; k < 3; k++) a[i * 3 + k] = H[k * 3 + i];   // At = H^T
     ZpMat At{a, 1};
@@ -141,7 +142,7 @@ __device__ inline void zp_polar3(const double H[9], double R[9]) {
 
 // Least squares min ||A x - b|| for a 6 x NC system by Householder QR (A row-major 6 x NC, destroyed).
 template <int NC>
-__device__ inline void zp_ls6(double* A, double* b, double* x) {
+ZP_HD inline void zp_ls6(double* A, double* b, double* x) {
     const int NR = 6;
 #pragma unroll
     for (int k = 0; k < NC; k++) {
@@ -178,13 +179,16 @@ __device__ inline void zp_ls6(double* A, double* b, double* x) {
 }
 
 // The 52 sums over the points that EPnP needs once the control points are fixed.
+struct ZpCam { double fu, fv, uc, vc; };
+
 struct ZpSums {
-    double s0[10], sx[10], sy[10], sr[10];   // sum a_j a_k {1, x, y, x^2+y^2}, (j<=k) packed: 00 01 02 03 11 12 13 22 23 33
+    // sum a_j a_k {1, x, y, x^2+y^2} with x = uc - u, y = vc - v (pixels), (j<=k) packed: 00 01 02 03 11 12 13 22 23 33
+    double s0[10], sx[10], sy[10], sr[10];
     double w[12];                            // W_j = sum_i a_ij (pw_i - pw0), j = 0..3
     double n;
 };
 
-__device__ __forceinline__ int zp_pk(int j, int k) {     // packed index of the symmetric 4x4 (j<=k)
+ZP_HD __forceinline__ int zp_pk(int j, int k) {     // packed index of the symmetric 4x4 (j<=k)
     const int base[4] = {0, 4, 7, 9};
     return base[j] + (k - j);
 }
@@ -195,7 +199,7 @@ struct ZpControl {
 };
 
 // control points + barycentric basis from the centroid c0, the 3x3 scatter matrix C = sum (p-c0)(p-c0)^T and n
-__device__ inline void zp_control_points(const double c0[3], const double C[9], double n, ZpControl& cp) {
+ZP_HD inline void zp_control_points(const double c0[3], const double C[9], double n, ZpControl& cp) {
     double dc[3], uct[9];
     zp_pca3(C, dc, uct);
     double kk[3];
@@ -212,7 +216,7 @@ __device__ inline void zp_control_points(const double c0[3], const double C[9], 
     }
 }
 
-__device__ __forceinline__ void zp_alphas(const ZpControl& cp, double X, double Y, double Z, double a[4]) {
+ZP_HD __forceinline__ void zp_alphas(const ZpControl& cp, double X, double Y, double Z, double a[4]) {
     double dx = X - cp.cws[0], dy = Y - cp.cws[1], dz = Z - cp.cws[2];
     a[1] = cp.cci[0] * dx + cp.cci[1] * dy + cp.cci[2] * dz;
     a[2] = cp.cci[3] * dx + cp.cci[4] * dy + cp.cci[5] * dz;
@@ -220,7 +224,7 @@ __device__ __forceinline__ void zp_alphas(const ZpControl& cp, double X, double 
     a[0] = 1.0 - a[1] - a[2] - a[3];
 }
 
-__device__ __forceinline__ void zp_accumulate(ZpSums& s, const double a[4], double x, double y, double dX, double dY,
+ZP_HD __forceinline__ void zp_accumulate(ZpSums& s, const double a[4], double x, double y, double dX, double dY,
                                               double dZ) {
     double r = x * x + y * y;
     int q = 0;
@@ -241,14 +245,16 @@ __device__ __forceinline__ void zp_accumulate(ZpSums& s, const double a[4], doub
 }
 
 // M^T M (12x12) from the sums, written into At (symmetric, so At = MtM).
-__device__ inline void zp_fill_mtm(ZpMat At, const ZpSums& s) {
+// rows of M (epnp::fill_M): [a_j fu, 0, a_j (uc - u)] and [0, a_j fv, a_j (vc - v)]
+ZP_HD inline void zp_fill_mtm(ZpMat At, const ZpSums& s, const ZpCam& cam) {
+    const double fu2 = cam.fu * cam.fu, fv2 = cam.fv * cam.fv;
     for (int j = 0; j < 4; j++)
         for (int k = 0; k < 4; k++) {
             int q = j <= k ? zp_pk(j, k) : zp_pk(k, j);
-            double g00 = s.s0[q], gx = -s.sx[q], gy = -s.sy[q], gr = s.sr[q];
+            double g00 = fu2 * s.s0[q], g11 = fv2 * s.s0[q], gx = cam.fu * s.sx[q], gy = cam.fv * s.sy[q], gr = s.sr[q];
             int r = 3 * j, c = 3 * k;
             At(r + 0, c + 0, 12) = g00; At(r + 0, c + 1, 12) = 0;   At(r + 0, c + 2, 12) = gx;
-            At(r + 1, c + 0, 12) = 0;   At(r + 1, c + 1, 12) = g00; At(r + 1, c + 2, 12) = gy;
+            At(r + 1, c + 0, 12) = 0;   At(r + 1, c + 1, 12) = g11; At(r + 1, c + 2, 12) = gy;
             At(r + 2, c + 0, 12) = gx;  At(r + 2, c + 1, 12) = gy;  At(r + 2, c + 2, 12) = gr;
         }
 }
@@ -260,9 +266,9 @@ struct ZpCandidates {
 
 // Everything after the sums: null space of M^T M, L/rho, three beta initialisations + Gauss-Newton, Horn alignment.
 // a_first = alphas of the first correspondence (solve_for_sign looks at its camera-frame depth), pw0 = centroid.
-__device__ inline void zp_epnp_core(ZpMat At, const ZpSums& sums, const ZpControl& cp, const double a_first[4],
-                                    const double pw0[3], ZpCandidates& out) {
-    zp_fill_mtm(At, sums);
+ZP_HD inline void zp_epnp_core(ZpMat At, const ZpSums& sums, const ZpCam& cam, const ZpControl& cp,
+                                const double a_first[4], const double pw0[3], ZpCandidates& out) {
+    zp_fill_mtm(At, sums, cam);
     double W[12];
     zp_jacobi_rows<12>(At, W, nullptr);
     // indices of the four smallest singular values, v[0] = smallest (OpenCV sorts descending and takes rows 11..8)
@@ -387,12 +393,12 @@ __device__ inline void zp_epnp_core(ZpMat At, const ZpSums& sums, const ZpContro
 #undef ZPV
 }
 
-// normalised-coordinate reprojection distance of one point (epnp::reprojection_error with K = I)
-__device__ __forceinline__ double zp_reproj_dist(const double* R, const double* t, double X, double Y, double Z,
-                                                 double x, double y) {
+// pixel reprojection distance of one point (epnp::reprojection_error)
+ZP_HD __forceinline__ double zp_reproj_dist(const double* R, const double* t, const ZpCam& cam, double X, double Y,
+                                            double Z, double u, double v) {
     double Xc = R[0] * X + R[1] * Y + R[2] * Z + t[0];
     double Yc = R[3] * X + R[4] * Y + R[5] * Z + t[1];
     double iz = 1.0 / (R[6] * X + R[7] * Y + R[8] * Z + t[2]);
-    double du = x - Xc * iz, dv = y - Yc * iz;
+    double du = u - (cam.uc + cam.fu * Xc * iz), dv = v - (cam.vc + cam.fv * Yc * iz);
     return sqrt(du * du + dv * dv);
 }

@@ -92,16 +92,14 @@ zp_minimal_kernel(const float* __restrict__ corr, int cap, const int32_t* __rest
         return;
     }
     const double* Kb = Kmat + 9 * (size_t)b;
-    const double fx = Kb[0], fy = Kb[4], cx = Kb[2], cy = Kb[5];
-    const double ifx = 1.0 / fx, ify = 1.0 / fy;
+    const ZpCam cam{Kb[0], Kb[4], Kb[2], Kb[5]};
     const float* cb = corr + (size_t)b * 5 * cap;
-    double X[ZP_MAX_M], Y[ZP_MAX_M], Z[ZP_MAX_M], xn[ZP_MAX_M], yn[ZP_MAX_M];
+    double X[ZP_MAX_M], Y[ZP_MAX_M], Z[ZP_MAX_M], xn[ZP_MAX_M], yn[ZP_MAX_M];   // xn, yn: pixel coordinates
     double c0[3] = {0, 0, 0};
     for (int j = 0; j < m; j++) {
         int i = sidx[j];
-        // cv2 hands float32 points to solvePnP inside RANSAC: undistortPoints rounds the normalised coords to float32
-        xn[j] = (double)(float)(((double)cb[i] - cx) * ifx);
-        yn[j] = (double)(float)(((double)cb[cap + i] - cy) * ify);
+        xn[j] = (double)cb[i];
+        yn[j] = (double)cb[cap + i];
         X[j] = cb[2 * (size_t)cap + i]; Y[j] = cb[3 * (size_t)cap + i]; Z[j] = cb[4 * (size_t)cap + i];
         c0[0] += X[j]; c0[1] += Y[j]; c0[2] += Z[j];
     }
@@ -123,17 +121,17 @@ zp_minimal_kernel(const float* __restrict__ corr, int cap, const int32_t* __rest
         double a[4];
         zp_alphas(cp, X[j], Y[j], Z[j], a);
         if (j == 0) { a_first[0] = a[0]; a_first[1] = a[1]; a_first[2] = a[2]; a_first[3] = a[3]; }
-        zp_accumulate(sums, a, xn[j], yn[j], X[j] - c0[0], Y[j] - c0[1], Z[j] - c0[2]);
+        zp_accumulate(sums, a, cam.uc - xn[j], cam.vc - yn[j], X[j] - c0[0], Y[j] - c0[1], Z[j] - c0[2]);
     }
     ZpMat At{smem_d + threadIdx.x, MIN_THREADS};
     ZpCandidates cand;
-    zp_epnp_core(At, sums, cp, a_first, c0, cand);
+    zp_epnp_core(At, sums, cam, cp, a_first, c0, cand);
     int best = -1;
     double best_err = 0;
     for (int c = 0; c < 3; c++) {
         if (!cand.ok[c]) continue;
         double e = 0;
-        for (int j = 0; j < m; j++) e += zp_reproj_dist(cand.R[c], cand.t[c], X[j], Y[j], Z[j], xn[j], yn[j]);
+        for (int j = 0; j < m; j++) e += zp_reproj_dist(cand.R[c], cand.t[c], cam, X[j], Y[j], Z[j], xn[j], yn[j]);
         e /= m;
         if (!(e == e)) continue;
         if (best < 0 || e < best_err) { best = c; best_err = e; }
@@ -434,7 +432,8 @@ __global__ void __launch_bounds__(FIN_THREADS) zp_final_kernel(FinalArgs a) {
     }
     __syncthreads();
     // ---- pass 2: the 52 EPnP sums
-    const double fx = Kb[0], fy = Kb[4], cx = Kb[2], cy = Kb[5], ifx = 1.0 / fx, ify = 1.0 / fy;
+    const double fx = Kb[0], fy = Kb[4], cx = Kb[2], cy = Kb[5];
+    const ZpCam cam{fx, fy, cx, cy};
     {
         ZpSums s;
         for (int q = 0; q < 10; q++) { s.s0[q] = 0; s.sx[q] = 0; s.sy[q] = 0; s.sr[q] = 0; }
@@ -443,8 +442,7 @@ __global__ void __launch_bounds__(FIN_THREADS) zp_final_kernel(FinalArgs a) {
         for (int i = tid; i < n; i += FIN_THREADS)
             if (s_mask[i >> 5] >> (i & 31) & 1u) {
                 double X = cb[2 * (size_t)a.cap + i], Y = cb[3 * (size_t)a.cap + i], Z = cb[4 * (size_t)a.cap + i];
-                // the final solvePnP gets float64 copies of the inliers: no float32 rounding of the normalised coords
-                double x = ((double)cb[i] - cx) * ifx, y = ((double)cb[a.cap + i] - cy) * ify;
+                double x = cx - (double)cb[i], y = cy - (double)cb[a.cap + i];
                 double al[4];
                 zp_alphas(cp, X, Y, Z, al);
                 zp_accumulate(s, al, x, y, X - c0[0], Y - c0[1], Z - c0[2]);
@@ -463,7 +461,7 @@ __global__ void __launch_bounds__(FIN_THREADS) zp_final_kernel(FinalArgs a) {
         double af[4];
         zp_alphas(s_cp, cb[2 * (size_t)a.cap + f], cb[3 * (size_t)a.cap + f], cb[4 * (size_t)a.cap + f], af);
         ZpMat At{s_At, 1};
-        zp_epnp_core(At, s, s_cp, af, c0, s_cand);
+        zp_epnp_core(At, s, cam, s_cp, af, c0, s_cand);
     }
     __syncthreads();
     // ---- pass 3: mean reprojection distance of the three candidates, pick the best
@@ -471,9 +469,8 @@ __global__ void __launch_bounds__(FIN_THREADS) zp_final_kernel(FinalArgs a) {
     for (int i = tid; i < n; i += FIN_THREADS)
         if (s_mask[i >> 5] >> (i & 31) & 1u) {
             double X = cb[2 * (size_t)a.cap + i], Y = cb[3 * (size_t)a.cap + i], Z = cb[4 * (size_t)a.cap + i];
-            double x = ((double)cb[i] - cx) * ifx, y = ((double)cb[a.cap + i] - cy) * ify;
             for (int c = 0; c < 3; c++)
-                if (s_cand.ok[c]) acc[c] += zp_reproj_dist(s_cand.R[c], s_cand.t[c], X, Y, Z, x, y);
+                if (s_cand.ok[c]) acc[c] += zp_reproj_dist(s_cand.R[c], s_cand.t[c], cam, X, Y, Z, (double)cb[i], (double)cb[a.cap + i]);
         }
     block_reduce<3>(acc, s_red, s_sum);
     if (tid == 0) {
