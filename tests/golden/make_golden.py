@@ -134,6 +134,10 @@ def main():
     crop_case("c3_k4", tab16n, nrm16n, 1003 * 65536 + 1, 128, 4, out)
     crop_case("c3_k8", tab16n, nrm16n, 1003 * 65536 + 2, 128, 8, out)
     crop_case("s64_k0", tab16, nrm16, 77, 64, 0, out)
+    # ignore-bit crops on the NaN-free dictionary: the only ones where the reference's POSE is meaningful
+    # (with 20 % NaN rows a parent is NaN if any child is, so k=4 turns 97 % of the 3D points into (0,0,0))
+    crop_case("c3f_k2", tab16, nrm16, 1003 * 65536 + 10, 128, 2, out)
+    crop_case("c3f_k4", tab16, nrm16, 1003 * 65536 + 11, 128, 4, out)
     out["tab16_seed"] = np.array([3, 51.0, 0.0])
     out["tab16n_seed"] = np.array([11, 51.0, 0.2])
 

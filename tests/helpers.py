@@ -12,6 +12,8 @@ GOLDEN_CROPS = {  # tag -> (table key, seed, S, ignore_bit)
     "c3_k4": ("nan20", 1003 * 65536 + 1, 128, 4),
     "c3_k8": ("nan20", 1003 * 65536 + 2, 128, 8),
     "s64_k0": ("full", 77, 64, 0),
+    "c3f_k2": ("full", 1003 * 65536 + 10, 128, 2),
+    "c3f_k4": ("full", 1003 * 65536 + 11, 128, 4),
 }
 
 

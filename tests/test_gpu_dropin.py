@@ -10,7 +10,7 @@ from helpers import GOLDEN_CROPS, regen_crop
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("tag", ["c1_full", "c1_nan20", "c3_k4", "s64_k0"])
+@pytest.mark.parametrize("tag", ["c1_full", "c1_nan20", "c3f_k2", "c3f_k4", "s64_k0"])
 def test_cnn_outputs_to_object_pose(golden, tables, tag):
     from zebrapose_b200.binary_code_helper.CNN_output_to_pose import CNN_outputs_to_object_pose, CNN_outputs_to_object_info
     from zebrapose_b200.binary_code_helper.generate_new_dict import generate_new_corres_dict

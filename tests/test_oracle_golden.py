@@ -71,7 +71,7 @@ def test_decode_crop(golden, tables, tag):
     assert np.array_equal(p3.astype(np.float32), xyz)
 
 
-@pytest.mark.parametrize("tag", ["c1_full", "c3_k4", "s64_k0"])
+@pytest.mark.parametrize("tag", ["c1_full", "c3f_k4", "s64_k0"])
 def test_pose_vs_reference(golden, tables, tag):
     """oracle decode + RANSAC emulation (cv2 EPnP inside) == the reference's CNN_outputs_to_object_pose."""
     tab, c, logits, S, k = regen_crop(tables, tag)
