@@ -39,21 +39,22 @@ int main() {
         }
         double at[144];
         ZpMat At{at, 1};
-        ZpCandidates cand;
-        zp_epnp_core(At, s, cam, cp, af, c0, cand);
-        int best = -1; double be = 0;
+        zp_nullspace_serial(At, s, cam);
+        double L[60], rho[6];
+        zp_L_rho(At, cp, L, rho);
+        int best = -1; double be = 0, Rb[9], tb[3];
         for (int c = 0; c < 3; c++) {
-            if (!cand.ok[c]) continue;
+            double R[9], t[3];
+            if (!zp_candidate(c, L, rho, At, s, af, c0, R, t)) continue;
             double e = 0;
-            for (int i = 0; i < n; i++) e += zp_reproj_dist(cand.R[c], cand.t[c], cam, X[i], Y[i], Z[i], x[i], y[i]);
+            for (int i = 0; i < n; i++) e += zp_reproj_dist(R, t, cam, X[i], Y[i], Z[i], x[i], y[i]);
             e /= n;
-            if (getenv("ZP_DEBUG")) fprintf(stderr, "cand %d err %.6g\n", c, e);
             if (!(e == e)) continue;
-            if (best < 0 || e < be) { best = c; be = e; }
+            if (best < 0 || e < be) { best = c; be = e; for (int q = 0; q < 9; q++) Rb[q] = R[q]; for (int q = 0; q < 3; q++) tb[q] = t[q]; }
         }
         if (best < 0) { for (int e = 0; e < 12; e++) printf("nan "); printf("\n"); continue; }
-        for (int e = 0; e < 9; e++) printf("%.17g ", cand.R[best][e]);
-        for (int e = 0; e < 3; e++) printf("%.17g ", cand.t[best][e]);
+        for (int e = 0; e < 9; e++) printf("%.17g ", Rb[e]);
+        for (int e = 0; e < 3; e++) printf("%.17g ", tb[e]);
         printf("\n");
     }
     return 0;

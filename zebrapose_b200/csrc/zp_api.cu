@@ -8,10 +8,8 @@ int zp_launch_minimal(zp_ctx*, const float*, int, const int32_t*, const double*,
                       cudaStream_t);
 int zp_launch_score(zp_ctx*, const float*, int, const int32_t*, const double*, const double*, int, int, float, int32_t*,
                     cudaStream_t);
-int zp_launch_select(zp_ctx*, const int32_t*, int, const int32_t*, int, int, int, double, int, int32_t*, int32_t*,
-                     cudaStream_t);
-int zp_launch_final(zp_ctx*, const float*, int, const int32_t*, const double*, const double*, const int32_t*,
-                    const int32_t*, int, int, float, int, double*, int32_t*, uint8_t*, cudaStream_t);
+int zp_launch_final(zp_ctx*, const float*, int, const int32_t*, const double*, const double*, const int32_t*, int, int, int,
+                    double, int, float, int, double*, int32_t*, int32_t*, int32_t*, uint8_t*, cudaStream_t);
 int zp_launch_fma_probe(zp_ctx*, int, double*);
 int zp_launch_remap_pixels(zp_ctx*, const int64_t*, int64_t, const double*, int, int64_t*, cudaStream_t);
 int zp_launch_codes_to_ids(zp_ctx*, const double*, int64_t, int, int, double*, cudaStream_t);
@@ -64,6 +62,20 @@ int zp_create(zp_ctx** out, int device) {
         cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
         delete ctx; g_err = "context allocation failed"; return -2;
     }
+    {   // raw stream of cv::RNG(0xFFFFFFFFFFFFFFFF) (multiply-with-carry), replayed by zp_samples_kernel
+        const int n = 16384;
+        std::vector<uint32_t> tab(n);
+        uint64_t state = 0xFFFFFFFFFFFFFFFFull;
+        for (int i = 0; i < n; i++) {
+            state = (uint64_t)(uint32_t)state * 4164903690ull + (state >> 32);
+            tab[i] = (uint32_t)state;
+        }
+        if (cudaMalloc((void**)&ctx->d_rng, n * sizeof(uint32_t)) != cudaSuccess ||
+            cudaMemcpy(ctx->d_rng, tab.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice) != cudaSuccess) {
+            delete ctx; g_err = "context allocation failed"; return -2;
+        }
+        ctx->n_rng = n;
+    }
     *out = ctx;
     return 0;
 }
@@ -74,6 +86,7 @@ void zp_destroy(zp_ctx* ctx) {
     cudaDeviceSynchronize();
     for (auto& t : ctx->tables) { if (t.pts) cudaFree(t.pts); if (t.remap) cudaFree(t.remap); }
     if (ctx->d_table_ptrs) cudaFree((void*)ctx->d_table_ptrs);
+    if (ctx->d_rng) cudaFree(ctx->d_rng);
     if (ctx->ws) cudaFree(ctx->ws);
     if (ctx->hws) cudaFree(ctx->hws);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -253,11 +266,10 @@ int zp_ransac(zp_ctx* ctx, const float* corr, int cap, const int32_t* counts, co
     if (check_corr(ctx, corr, cap, "zp_ransac")) return -1;
     ZP_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = (cudaStream_t)stream;
-    // workspace: samples | hyp_poses | hyp_inliers | best_idx (only what the caller did not supply)
+    // workspace: samples | hyp_poses | hyp_inliers (only what the caller did not supply)
     size_t o_s = 0, o_p = o_s + (samples ? 0 : align256((size_t)B * H * m * 4));
     size_t o_i = o_p + (hyp_poses ? 0 : align256((size_t)B * H * 12 * 8));
-    size_t o_b = o_i + (hyp_inliers ? 0 : align256((size_t)B * H * 4));
-    size_t total = o_b + (best_idx ? 0 : align256((size_t)B * 4));
+    size_t total = o_i + (hyp_inliers ? 0 : align256((size_t)B * H * 4));
     if (total && zp_ws_reserve(ctx, total)) return -2;
     char* ws = (char*)ctx->ws;
     int32_t* d_samples = nullptr;
@@ -267,12 +279,10 @@ int zp_ransac(zp_ctx* ctx, const float* corr, int cap, const int32_t* counts, co
     }
     double* d_hp = hyp_poses ? hyp_poses : (double*)(ws + o_p);
     int32_t* d_hi = hyp_inliers ? hyp_inliers : (int32_t*)(ws + o_i);
-    int32_t* d_bi = best_idx ? best_idx : (int32_t*)(ws + o_b);
     if (int r = zp_launch_minimal(ctx, corr, cap, counts, K, samples ? samples : d_samples, B, H, m, d_hp, st)) return r;
     if (int r = zp_launch_score(ctx, corr, cap, counts, K, d_hp, B, H, thr_px, d_hi, st)) return r;
-    if (int r = zp_launch_select(ctx, counts, cap, d_hi, B, H, m, confidence, select_mode, d_bi, status, st)) return r;
-    return zp_launch_final(ctx, corr, cap, counts, K, d_hp, d_bi, status, B, H, thr_px, final_mode, poses, n_inliers,
-                           inlier_mask, st);
+    return zp_launch_final(ctx, corr, cap, counts, K, d_hp, d_hi, B, H, m, confidence, select_mode, thr_px, final_mode,
+                           poses, n_inliers, status, best_idx, inlier_mask, st);
 }
 
 int zp_pose_batch_host(zp_ctx* ctx, const void* h_logits, int dtype, int B, int C, int S, int mask_ch, int bit0_ch,

@@ -23,6 +23,8 @@ struct zp_ctx {
     std::string err;
     ZpTable tables[ZP_MAX_OBJECTS];
     const float4** d_table_ptrs = nullptr;   // device array [ZP_MAX_OBJECTS]
+    uint32_t* d_rng = nullptr;               // raw outputs of cv::RNG(0xFFFFFFFFFFFFFFFF), replayed by zp_samples_kernel
+    int n_rng = 0;
     // growable device workspace
     void* ws = nullptr;
     size_t ws_bytes = 0;

@@ -1,13 +1,17 @@
 // EPnP in float64 as cv2.solvePnP(SOLVEPNP_EPNP) runs it (OpenCV is the un-vendored library behind the reference's
 // cv2.solvePnPRansac call, CNN_output_to_pose.py:155-157).  Device restatement of the published algorithm
 // (Lepetit, Moreno-Noguer, Fua 2009) with the OpenCV behaviours that change the answer under pixel noise:
-// M built in pixel units with the real camera matrix (fu != fv weights the image axes), PCA control points with the signs of OpenCV's one-sided Jacobi SVD (same pair
-// order and rotation formulas), three beta initialisations x 5 Gauss-Newton steps, Horn alignment with
-// "negate row 2 when det < 0", best of three by mean reprojection distance.  oracle/epnp.py is the CPU twin.
+// M built in pixel units with the real camera matrix (fu != fv weights the image axes), PCA control points with the
+// signs of OpenCV's one-sided Jacobi SVD (same pair order and rotation rule), three beta initialisations x 5
+// Gauss-Newton steps, Horn alignment with "negate row 2 when det < 0", best of three by mean reprojection distance.
+// oracle/epnp.py is the CPU twin; tests/native/epnp_host.cu compiles this header for the host.
 //
 // The per-point work is reduced to 52 sums (ZpSums) so the same core serves the 4/5/6-point minimal solver (one
-// thread per hypothesis, sums over m points in registers) and the final solve on thousands of inliers (one CTA
-// per crop, block reduction of the sums).
+// thread per hypothesis) and the final solve on thousands of inliers (one CTA per crop, block reduction of the sums).
+// The 12x12 null-space problem has two implementations: a serial one-sided Jacobi (row i cached in registers, matrix
+// interleaved in shared memory) for the thread-per-hypothesis kernel, and a 16-lane cooperative one with a
+// round-robin (tournament) pair order for the final solve.  The signs / order of the 12x12 singular vectors do not
+// change EPnP's answer (the betas absorb them), so only the 3x3 PCA has to follow OpenCV's pair order.
 #pragma once
 #include <cuda_runtime.h>
 #include <math.h>
@@ -16,67 +20,109 @@
 #define ZP_DBL_EPS 2.220446049250313e-16
 #define ZP_DBL_MIN 2.2250738585072014e-308
 
-// strided view of an n x n double matrix (row-major) living in shared memory; `stride` interleaves the matrices
-// of the threads of a CTA so that a warp touching element (r,k) of its 32 matrices hits 32 consecutive doubles.
+// strided view of an n x n double matrix (row-major); `stride` interleaves the matrices of the threads of a CTA so
+// that a warp touching element (r,k) of its 32 matrices hits 32 consecutive doubles (conflict-free).
 struct ZpMat {
     double* p;
     int stride;
     ZP_HD __forceinline__ double& operator()(int r, int k, int n) const { return p[(size_t)(r * n + k) * stride]; }
 };
 
-// One-sided (Hestenes) Jacobi on the rows of At (= A^T), OpenCV's pair order (i<j ascending), rotation formulas and
-// stopping rule (JacobiSVDImpl_, modules/core/src/lapack.cpp: eps = 10*DBL_EPSILON, max(n,30) sweeps).
-// On exit row i of At = sigma_i * u_i^T and W[i] = sigma_i (unsorted).  If G != nullptr it receives the accumulated
-// rotations (OpenCV's Vt) as a dense row-major n x n array in registers/local memory.
+ZP_HD __forceinline__ double zp_rsqrt(double x) {
+#ifdef __CUDA_ARCH__
+    return rsqrt(x);
+#else
+    return 1.0 / sqrt(x);
+#endif
+}
+
+// Jacobi rotation that orthogonalises two rows with squared norms a, b and dot product p (Hestenes / OpenCV
+// JacobiSVDImpl_ rule, written with two reciprocal square roots instead of hypot + 2 sqrt + 2 div):
+//   beta = a - b, gamma = sqrt(4p^2 + beta^2);  beta < 0: s = sqrt((gamma-beta)/(2 gamma)), c = p/(gamma s)
+//                                               else    : c = sqrt((gamma+beta)/(2 gamma)), s = p/(gamma c)
+ZP_HD __forceinline__ void zp_rot(double a, double b, double p, double& c, double& s) {
+    double p2 = 2 * p, beta = a - b;
+    double g2 = fma(p2, p2, beta * beta);
+    double ig = zp_rsqrt(g2);                    // 1/gamma
+    double h = fma(0.5 * fabs(beta), ig, 0.5);   // (gamma + |beta|) / (2 gamma)  in [0.5, 1]
+    double rh = zp_rsqrt(h);
+    double big = h * rh;                         // sqrt(h)
+    double small = p * ig * rh;                  // p / (gamma * sqrt(h))
+    if (beta < 0) { s = big; c = small; } else { c = big; s = small; }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// serial one-sided Jacobi on the rows of At (N x N), OpenCV's cyclic pair order (i<j ascending) and stopping rule
+// (eps = 10*DBL_EPSILON, max(N,30) sweeps).  Row i is held in registers across the j loop; squared norms follow the
+// rotation recurrences and are recomputed exactly at the start of every sweep.  On exit W[i] = sigma_i (unsorted) and
+// row i of At = sigma_i u_i^T.  G (nullable, dense row-major) accumulates the rotations (OpenCV's Vt).
+// ------------------------------------------------------------------------------------------------------------------
 template <int N>
-ZP_HD void zp_jacobi_rows(ZpMat At, double* W, double* G) {
+ZP_HD inline void zp_jacobi_rows(ZpMat At, double* W, double* G) {
     const double eps = ZP_DBL_EPS * 10;
-    for (int i = 0; i < N; i++) {
-        double sd = 0;
-        for (int k = 0; k < N; k++) { double t = At(i, k, N); sd = fma(t, t, sd); }
-        W[i] = sd;
-    }
     if (G) {
         for (int i = 0; i < N * N; i++) G[i] = 0;
         for (int i = 0; i < N; i++) G[i * N + i] = 1;
     }
     const int max_iter = N > 30 ? N : 30;
     for (int iter = 0; iter < max_iter; iter++) {
-        bool changed = false;
-        for (int i = 0; i < N - 1; i++)
-            for (int j = i + 1; j < N; j++) {
-                double a = W[i], b = W[j], p = 0;
+        for (int i = 0; i < N; i++) {
+            double s0 = 0, s1 = 0;
 #pragma unroll
-                for (int k = 0; k < N; k++) p = fma(At(i, k, N), At(j, k, N), p);
-                if (fabs(p) <= eps * sqrt(a * b)) continue;
-                p *= 2;
-                double beta = a - b, gamma = hypot(p, beta), c, s;
-                if (beta < 0) {
-                    double delta = (gamma - beta) * 0.5;
-                    s = sqrt(delta / gamma);
-                    c = p / (gamma * s * 2);
-                } else {
-                    c = sqrt((gamma + beta) / (gamma * 2));
-                    s = p / (gamma * c * 2);
+            for (int k = 0; k + 1 < N; k += 2) {
+                double t0 = At(i, k, N), t1 = At(i, k + 1, N);
+                s0 = fma(t0, t0, s0); s1 = fma(t1, t1, s1);
+            }
+            if (N & 1) { double t = At(i, N - 1, N); s0 = fma(t, t, s0); }
+            W[i] = s0 + s1;
+        }
+        bool changed = false;
+        for (int i = 0; i < N - 1; i++) {
+            double ri[N];
+#pragma unroll
+            for (int k = 0; k < N; k++) ri[k] = At(i, k, N);
+            double a = W[i];
+            bool touched = false;
+            for (int j = i + 1; j < N; j++) {
+                double rj[N];
+#pragma unroll
+                for (int k = 0; k < N; k++) rj[k] = At(j, k, N);
+                double p0 = 0, p1 = 0, p2 = 0;
+#pragma unroll
+                for (int k = 0; k < N; k += 3) {
+                    p0 = fma(ri[k], rj[k], p0);
+                    if (k + 1 < N) p1 = fma(ri[k + 1], rj[k + 1], p1);
+                    if (k + 2 < N) p2 = fma(ri[k + 2], rj[k + 2], p2);
                 }
-                a = 0; b = 0;
+                double p = p0 + p1 + p2, b = W[j];
+                if (fabs(p) <= eps * sqrt(a * b)) continue;
+                double c, s;
+                zp_rot(a, b, p, c, s);
 #pragma unroll
                 for (int k = 0; k < N; k++) {
-                    double x = At(i, k, N), y = At(j, k, N);
-                    double t0 = c * x + s * y, t1 = -s * x + c * y;
-                    At(i, k, N) = t0; At(j, k, N) = t1;
-                    a = fma(t0, t0, a); b = fma(t1, t1, b);
+                    double x = ri[k], y = rj[k];
+                    ri[k] = fma(c, x, s * y);
+                    At(j, k, N) = fma(c, y, -s * x);
                 }
-                W[i] = a; W[j] = b;
-                changed = true;
+                double cc = c * c, ss = s * s, cs2 = 2 * c * s * p;
+                double na = fma(cc, a, fma(ss, b, cs2)), nb = fma(ss, a, fma(cc, b, -cs2));
+                a = na > 0 ? na : 0;
+                W[j] = nb > 0 ? nb : 0;
+                changed = true; touched = true;
                 if (G) {
 #pragma unroll
                     for (int k = 0; k < N; k++) {
                         double x = G[i * N + k], y = G[j * N + k];
-                        G[i * N + k] = c * x + s * y; G[j * N + k] = -s * x + c * y;
+                        G[i * N + k] = fma(c, x, s * y); G[j * N + k] = fma(c, y, -s * x);
                     }
                 }
             }
+            if (touched) {
+#pragma unroll
+                for (int k = 0; k < N; k++) At(i, k, N) = ri[k];
+                W[i] = a;
+            }
+        }
         if (!changed) break;
     }
     for (int i = 0; i < N; i++) {
@@ -86,18 +132,17 @@ ZP_HD void zp_jacobi_rows(ZpMat At, double* W, double* G) {
     }
 }
 
-// 3x3 SVD-type helpers on a private (stride 1) matrix --------------------------------------------------------------
+// 3x3 helpers on a private (stride 1) matrix -----------------------------------------------------------------------
 
-// PCA of the 3x3 scatter matrix C (symmetric): returns singular values dc[3] descending and rows uct[3][3] with the
-// signs OpenCV's SVD (U_T) returns.
+// PCA of the 3x3 scatter matrix C (symmetric): singular values dc[3] descending and rows uct[3][3] with the signs
+// OpenCV's SVD (U_T) returns.
 ZP_HD inline void zp_pca3(const double C[9], double dc[3], double uct[9]) {
     double a[9], W[3];
     for (int i = 0; i < 3; i++) for (int k = 0; k < 3; k++) a[i * 3 + k] = C[k * 3 + i];   // At = C^T
     ZpMat At{a, 1};
     zp_jacobi_rows<3>(At, W, nullptr);
     int idx[3] = {0, 1, 2};
-    // selection sort descending, as OpenCV sorts W (swap on strict <)
-    for (int i = 0; i < 2; i++) {
+    for (int i = 0; i < 2; i++) {          // selection sort descending, as OpenCV sorts W (swap on strict <)
         int j = i;
         for (int k = i + 1; k < 3; k++) if (W[idx[j]] < W[idx[k]]) j = k;
         int t = idx[i]; idx[i] = idx[j]; idx[j] = t;
@@ -178,9 +223,9 @@ ZP_HD inline void zp_ls6(double* A, double* b, double* x) {
     }
 }
 
-// The 52 sums over the points that EPnP needs once the control points are fixed.
 struct ZpCam { double fu, fv, uc, vc; };
 
+// The 52 sums over the points that EPnP needs once the control points are fixed.
 struct ZpSums {
     // sum a_j a_k {1, x, y, x^2+y^2} with x = uc - u, y = vc - v (pixels), (j<=k) packed: 00 01 02 03 11 12 13 22 23 33
     double s0[10], sx[10], sy[10], sr[10];
@@ -225,7 +270,7 @@ ZP_HD __forceinline__ void zp_alphas(const ZpControl& cp, double X, double Y, do
 }
 
 ZP_HD __forceinline__ void zp_accumulate(ZpSums& s, const double a[4], double x, double y, double dX, double dY,
-                                              double dZ) {
+                                         double dZ) {
     double r = x * x + y * y;
     int q = 0;
 #pragma unroll
@@ -244,153 +289,143 @@ ZP_HD __forceinline__ void zp_accumulate(ZpSums& s, const double a[4], double x,
     }
 }
 
-// M^T M (12x12) from the sums, written into At (symmetric, so At = MtM).
-// rows of M (epnp::fill_M): [a_j fu, 0, a_j (uc - u)] and [0, a_j fv, a_j (vc - v)]
-ZP_HD inline void zp_fill_mtm(ZpMat At, const ZpSums& s, const ZpCam& cam) {
-    const double fu2 = cam.fu * cam.fu, fv2 = cam.fv * cam.fv;
-    for (int j = 0; j < 4; j++)
-        for (int k = 0; k < 4; k++) {
-            int q = j <= k ? zp_pk(j, k) : zp_pk(k, j);
-            double g00 = fu2 * s.s0[q], g11 = fv2 * s.s0[q], gx = cam.fu * s.sx[q], gy = cam.fv * s.sy[q], gr = s.sr[q];
-            int r = 3 * j, c = 3 * k;
-            At(r + 0, c + 0, 12) = g00; At(r + 0, c + 1, 12) = 0;   At(r + 0, c + 2, 12) = gx;
-            At(r + 1, c + 0, 12) = 0;   At(r + 1, c + 1, 12) = g11; At(r + 1, c + 2, 12) = gy;
-            At(r + 2, c + 0, 12) = gx;  At(r + 2, c + 1, 12) = gy;  At(r + 2, c + 2, 12) = gr;
-        }
+// element (r, c) of M^T M; rows of M (epnp::fill_M): [a_j fu, 0, a_j (uc - u)] and [0, a_j fv, a_j (vc - v)]
+ZP_HD __forceinline__ double zp_mtm(const ZpSums& s, const ZpCam& cam, int r, int c) {
+    int j = r / 3, rr = r - 3 * j, k = c / 3, cc = c - 3 * k;
+    int q = j <= k ? zp_pk(j, k) : zp_pk(k, j);
+    if (rr == 0) return cc == 0 ? cam.fu * cam.fu * s.s0[q] : cc == 1 ? 0.0 : cam.fu * s.sx[q];
+    if (rr == 1) return cc == 0 ? 0.0 : cc == 1 ? cam.fv * cam.fv * s.s0[q] : cam.fv * s.sy[q];
+    return cc == 0 ? cam.fu * s.sx[q] : cc == 1 ? cam.fv * s.sy[q] : s.sr[q];
 }
 
-struct ZpCandidates {
-    double R[3][9], t[3][3];
-    bool ok[3];
-};
+ZP_HD inline void zp_fill_mtm(ZpMat At, const ZpSums& s, const ZpCam& cam) {
+    for (int r = 0; r < 12; r++)
+        for (int c = 0; c < 12; c++) At(r, c, 12) = zp_mtm(s, cam, r, c);
+}
 
-// Everything after the sums: null space of M^T M, L/rho, three beta initialisations + Gauss-Newton, Horn alignment.
-// a_first = alphas of the first correspondence (solve_for_sign looks at its camera-frame depth), pw0 = centroid.
-ZP_HD inline void zp_epnp_core(ZpMat At, const ZpSums& sums, const ZpCam& cam, const ZpControl& cp,
-                                const double a_first[4], const double pw0[3], ZpCandidates& out) {
+// L (6x10) and rho (6) from the four null-space vectors V(q, e) (q = 0 smallest) and the control points
+ZP_HD inline void zp_L_rho(ZpMat V, const ZpControl& cp, double* L, double* rho) {
+    const int pa[6] = {0, 0, 0, 1, 1, 2}, pb[6] = {1, 2, 3, 2, 3, 3};
+    for (int r = 0; r < 6; r++) {
+        double dv[4][3];
+        for (int q = 0; q < 4; q++)
+            for (int e = 0; e < 3; e++) dv[q][e] = V(q, 3 * pa[r] + e, 12) - V(q, 3 * pb[r] + e, 12);
+#define ZPD(x, y) (dv[x][0] * dv[y][0] + dv[x][1] * dv[y][1] + dv[x][2] * dv[y][2])
+        double* l = L + 10 * r;
+        l[0] = ZPD(0, 0); l[1] = 2 * ZPD(0, 1); l[2] = ZPD(1, 1); l[3] = 2 * ZPD(0, 2); l[4] = 2 * ZPD(1, 2);
+        l[5] = ZPD(2, 2); l[6] = 2 * ZPD(0, 3); l[7] = 2 * ZPD(1, 3); l[8] = 2 * ZPD(2, 3); l[9] = ZPD(3, 3);
+#undef ZPD
+        double d0 = cp.cws[3 * pa[r]] - cp.cws[3 * pb[r]], d1 = cp.cws[3 * pa[r] + 1] - cp.cws[3 * pb[r] + 1],
+               d2 = cp.cws[3 * pa[r] + 2] - cp.cws[3 * pb[r] + 2];
+        rho[r] = d0 * d0 + d1 * d1 + d2 * d2;
+    }
+}
+
+// One of EPnP's three candidates: beta initialisation `cand` (find_betas_approx_1/2/3), 5 Gauss-Newton steps,
+// camera-frame control points, sign, Horn.  a_first = alphas of the first correspondence (solve_for_sign looks at its
+// camera-frame depth), pw0 = centroid.  Returns false when the pose is not finite.
+ZP_HD inline bool zp_candidate(int cand, const double* L, const double* rho, ZpMat V, const ZpSums& sums,
+                               const double a_first[4], const double pw0[3], double* R, double* t) {
+    double be[4] = {0, 0, 0, 0};
+    if (cand == 0) {
+        double A[24], b[6], x[4];
+        for (int r = 0; r < 6; r++) {
+            A[4 * r + 0] = L[10 * r + 0]; A[4 * r + 1] = L[10 * r + 1]; A[4 * r + 2] = L[10 * r + 3];
+            A[4 * r + 3] = L[10 * r + 6]; b[r] = rho[r];
+        }
+        zp_ls6<4>(A, b, x);
+        double sgn = x[0] < 0 ? -1.0 : 1.0;
+        be[0] = sqrt(sgn * x[0]);
+        be[1] = sgn * x[1] / be[0]; be[2] = sgn * x[2] / be[0]; be[3] = sgn * x[3] / be[0];
+    } else if (cand == 1) {
+        double A[18], b[6], x[3];
+        for (int r = 0; r < 6; r++) {
+            A[3 * r + 0] = L[10 * r + 0]; A[3 * r + 1] = L[10 * r + 1]; A[3 * r + 2] = L[10 * r + 2]; b[r] = rho[r];
+        }
+        zp_ls6<3>(A, b, x);
+        if (x[0] < 0) { be[0] = sqrt(-x[0]); be[1] = x[2] < 0 ? sqrt(-x[2]) : 0.0; }
+        else { be[0] = sqrt(x[0]); be[1] = x[2] > 0 ? sqrt(x[2]) : 0.0; }
+        if (x[1] < 0) be[0] = -be[0];
+    } else {
+        double A[30], b[6], x[5];
+        for (int r = 0; r < 6; r++) {
+            for (int c = 0; c < 5; c++) A[5 * r + c] = L[10 * r + c];
+            b[r] = rho[r];
+        }
+        zp_ls6<5>(A, b, x);
+        if (x[0] < 0) { be[0] = sqrt(-x[0]); be[1] = x[2] < 0 ? sqrt(-x[2]) : 0.0; }
+        else { be[0] = sqrt(x[0]); be[1] = x[2] > 0 ? sqrt(x[2]) : 0.0; }
+        if (x[1] < 0) be[0] = -be[0];
+        be[2] = x[3] / be[0];
+    }
+    for (int it = 0; it < 5; it++) {           // gauss_newton / compute_A_and_b_gauss_newton
+        double A[24], b[6], x[4];
+        for (int r = 0; r < 6; r++) {
+            const double* l = L + 10 * r;
+            A[4 * r + 0] = 2 * l[0] * be[0] + l[1] * be[1] + l[3] * be[2] + l[6] * be[3];
+            A[4 * r + 1] = l[1] * be[0] + 2 * l[2] * be[1] + l[4] * be[2] + l[7] * be[3];
+            A[4 * r + 2] = l[3] * be[0] + l[4] * be[1] + 2 * l[5] * be[2] + l[8] * be[3];
+            A[4 * r + 3] = l[6] * be[0] + l[7] * be[1] + l[8] * be[2] + 2 * l[9] * be[3];
+            b[r] = rho[r] - (l[0] * be[0] * be[0] + l[1] * be[0] * be[1] + l[2] * be[1] * be[1] +
+                             l[3] * be[0] * be[2] + l[4] * be[1] * be[2] + l[5] * be[2] * be[2] +
+                             l[6] * be[0] * be[3] + l[7] * be[1] * be[3] + l[8] * be[2] * be[3] +
+                             l[9] * be[3] * be[3]);
+        }
+        zp_ls6<4>(A, b, x);
+        for (int q = 0; q < 4; q++) be[q] += x[q];
+    }
+    double ccs[12];
+    for (int e = 0; e < 12; e++)
+        ccs[e] = be[0] * V(0, e, 12) + be[1] * V(1, e, 12) + be[2] * V(2, e, 12) + be[3] * V(3, e, 12);
+    double z_first = a_first[0] * ccs[2] + a_first[1] * ccs[5] + a_first[2] * ccs[8] + a_first[3] * ccs[11];
+    if (z_first < 0)
+        for (int e = 0; e < 12; e++) ccs[e] = -ccs[e];
+    double am[4];       // mean alphas: sum_i a_ij = sum_k sum_i a_ij a_ik because sum_k a_ik = 1
+    for (int j = 0; j < 4; j++) {
+        double s = 0;
+        for (int k = 0; k < 4; k++) s += sums.s0[j <= k ? zp_pk(j, k) : zp_pk(k, j)];
+        am[j] = s / sums.n;
+    }
+    double pc0[3];
+    for (int e = 0; e < 3; e++) pc0[e] = am[0] * ccs[e] + am[1] * ccs[3 + e] + am[2] * ccs[6 + e] + am[3] * ccs[9 + e];
+    double H[9];        // sum_i (pc_i - pc0)(pw_i - pw0)^T = sum_j ccs_j W_j^T
+    for (int r = 0; r < 3; r++)
+        for (int c = 0; c < 3; c++)
+            H[3 * r + c] = ccs[r] * sums.w[c] + ccs[3 + r] * sums.w[3 + c] + ccs[6 + r] * sums.w[6 + c] +
+                           ccs[9 + r] * sums.w[9 + c];
+    zp_polar3(H, R);
+    double det = R[0] * (R[4] * R[8] - R[5] * R[7]) - R[1] * (R[3] * R[8] - R[5] * R[6]) +
+                 R[2] * (R[3] * R[7] - R[4] * R[6]);
+    if (det < 0) { R[6] = -R[6]; R[7] = -R[7]; R[8] = -R[8]; }
+    for (int r = 0; r < 3; r++) t[r] = pc0[r] - (R[3 * r] * pw0[0] + R[3 * r + 1] * pw0[1] + R[3 * r + 2] * pw0[2]);
+    bool ok = true;
+    for (int e = 0; e < 9; e++) ok = ok && isfinite(R[e]);
+    for (int e = 0; e < 3; e++) ok = ok && isfinite(t[e]);
+    return ok;
+}
+
+// serial null space: fills At with M^T M, runs the Jacobi, and leaves the four normalised singular vectors of the
+// smallest singular values in rows 0..3 of At (row 0 = smallest), i.e. At doubles as the V view afterwards.
+ZP_HD inline void zp_nullspace_serial(ZpMat At, const ZpSums& sums, const ZpCam& cam) {
     zp_fill_mtm(At, sums, cam);
     double W[12];
     zp_jacobi_rows<12>(At, W, nullptr);
-    // indices of the four smallest singular values, v[0] = smallest (OpenCV sorts descending and takes rows 11..8)
     int vi[4];
-    {
-        bool used[12];
-        for (int i = 0; i < 12; i++) used[i] = false;
-        for (int q = 0; q < 4; q++) {
-            int best = -1;
-            for (int i = 11; i >= 0; i--)            // ties: later rows end up last after OpenCV's selection sort
-                if (!used[i] && (best < 0 || W[i] < W[best])) best = i;
-            used[best] = true; vi[q] = best;
-        }
+    bool used[12];
+    for (int i = 0; i < 12; i++) used[i] = false;
+    for (int q = 0; q < 4; q++) {
+        int best = -1;
+        for (int i = 11; i >= 0; i--)
+            if (!used[i] && (best < 0 || W[i] < W[best])) best = i;
+        used[best] = true; vi[q] = best;
     }
-    double vs[4];
-    for (int q = 0; q < 4; q++) vs[q] = W[vi[q]] > ZP_DBL_MIN ? 1.0 / W[vi[q]] : 0.0;
-#define ZPV(q, e) (At(vi[q], (e), 12) * vs[q])
-    // L (6x10) and rho
-    double L[60], rho[6];
-    {
-        const int pa[6] = {0, 0, 0, 1, 1, 2}, pb[6] = {1, 2, 3, 2, 3, 3};
-        for (int r = 0; r < 6; r++) {
-            double dv[4][3];
-            for (int q = 0; q < 4; q++)
-                for (int e = 0; e < 3; e++) dv[q][e] = ZPV(q, 3 * pa[r] + e) - ZPV(q, 3 * pb[r] + e);
-#define ZPD(x, y) (dv[x][0] * dv[y][0] + dv[x][1] * dv[y][1] + dv[x][2] * dv[y][2])
-            double* l = L + 10 * r;
-            l[0] = ZPD(0, 0); l[1] = 2 * ZPD(0, 1); l[2] = ZPD(1, 1); l[3] = 2 * ZPD(0, 2); l[4] = 2 * ZPD(1, 2);
-            l[5] = ZPD(2, 2); l[6] = 2 * ZPD(0, 3); l[7] = 2 * ZPD(1, 3); l[8] = 2 * ZPD(2, 3); l[9] = ZPD(3, 3);
-#undef ZPD
-            double d0 = cp.cws[3 * pa[r]] - cp.cws[3 * pb[r]], d1 = cp.cws[3 * pa[r] + 1] - cp.cws[3 * pb[r] + 1],
-                   d2 = cp.cws[3 * pa[r] + 2] - cp.cws[3 * pb[r] + 2];
-            rho[r] = d0 * d0 + d1 * d1 + d2 * d2;
-        }
+    double v[48];
+    for (int q = 0; q < 4; q++) {
+        double s = W[vi[q]] > ZP_DBL_MIN ? 1.0 / W[vi[q]] : 0.0;
+        for (int e = 0; e < 12; e++) v[q * 12 + e] = At(vi[q], e, 12) * s;
     }
-    for (int cand = 0; cand < 3; cand++) {
-        double be[4] = {0, 0, 0, 0};
-        // ---- initial betas (find_betas_approx_1/2/3)
-        if (cand == 0) {
-            double A[24], b[6], x[4];
-            for (int r = 0; r < 6; r++) {
-                A[4 * r + 0] = L[10 * r + 0]; A[4 * r + 1] = L[10 * r + 1]; A[4 * r + 2] = L[10 * r + 3];
-                A[4 * r + 3] = L[10 * r + 6]; b[r] = rho[r];
-            }
-            zp_ls6<4>(A, b, x);
-            double sgn = x[0] < 0 ? -1.0 : 1.0;
-            be[0] = sqrt(sgn * x[0]);
-            be[1] = sgn * x[1] / be[0]; be[2] = sgn * x[2] / be[0]; be[3] = sgn * x[3] / be[0];
-        } else if (cand == 1) {
-            double A[18], b[6], x[3];
-            for (int r = 0; r < 6; r++) {
-                A[3 * r + 0] = L[10 * r + 0]; A[3 * r + 1] = L[10 * r + 1]; A[3 * r + 2] = L[10 * r + 2]; b[r] = rho[r];
-            }
-            zp_ls6<3>(A, b, x);
-            if (x[0] < 0) { be[0] = sqrt(-x[0]); be[1] = x[2] < 0 ? sqrt(-x[2]) : 0.0; }
-            else { be[0] = sqrt(x[0]); be[1] = x[2] > 0 ? sqrt(x[2]) : 0.0; }
-            if (x[1] < 0) be[0] = -be[0];
-        } else {
-            double A[30], b[6], x[5];
-            for (int r = 0; r < 6; r++) {
-                for (int c = 0; c < 5; c++) A[5 * r + c] = L[10 * r + c];
-                b[r] = rho[r];
-            }
-            zp_ls6<5>(A, b, x);
-            if (x[0] < 0) { be[0] = sqrt(-x[0]); be[1] = x[2] < 0 ? sqrt(-x[2]) : 0.0; }
-            else { be[0] = sqrt(x[0]); be[1] = x[2] > 0 ? sqrt(x[2]) : 0.0; }
-            if (x[1] < 0) be[0] = -be[0];
-            be[2] = x[3] / be[0];
-        }
-        // ---- 5 Gauss-Newton steps (gauss_newton / compute_A_and_b_gauss_newton)
-        for (int it = 0; it < 5; it++) {
-            double A[24], b[6], x[4];
-            for (int r = 0; r < 6; r++) {
-                const double* l = L + 10 * r;
-                A[4 * r + 0] = 2 * l[0] * be[0] + l[1] * be[1] + l[3] * be[2] + l[6] * be[3];
-                A[4 * r + 1] = l[1] * be[0] + 2 * l[2] * be[1] + l[4] * be[2] + l[7] * be[3];
-                A[4 * r + 2] = l[3] * be[0] + l[4] * be[1] + 2 * l[5] * be[2] + l[8] * be[3];
-                A[4 * r + 3] = l[6] * be[0] + l[7] * be[1] + l[8] * be[2] + 2 * l[9] * be[3];
-                b[r] = rho[r] - (l[0] * be[0] * be[0] + l[1] * be[0] * be[1] + l[2] * be[1] * be[1] +
-                                 l[3] * be[0] * be[2] + l[4] * be[1] * be[2] + l[5] * be[2] * be[2] +
-                                 l[6] * be[0] * be[3] + l[7] * be[1] * be[3] + l[8] * be[2] * be[3] +
-                                 l[9] * be[3] * be[3]);
-            }
-            zp_ls6<4>(A, b, x);
-            for (int q = 0; q < 4; q++) be[q] += x[q];
-        }
-        // ---- camera-frame control points, sign, Horn
-        double ccs[12];
-        for (int e = 0; e < 12; e++)
-            ccs[e] = be[0] * ZPV(0, e) + be[1] * ZPV(1, e) + be[2] * ZPV(2, e) + be[3] * ZPV(3, e);
-        double z_first = a_first[0] * ccs[2] + a_first[1] * ccs[5] + a_first[2] * ccs[8] + a_first[3] * ccs[11];
-        if (z_first < 0)
-            for (int e = 0; e < 12; e++) ccs[e] = -ccs[e];
-        // pc0 = sum_j mean(alpha_j) ccs_j ; mean alphas = (s0 row sums)/n is exact only via the sums: use them
-        double am[4];
-        {   // sum_i a_ij = sum_k sum_i a_ij a_ik  (because sum_k a_ik = 1)
-            for (int j = 0; j < 4; j++) {
-                double t = 0;
-                for (int k = 0; k < 4; k++) t += sums.s0[j <= k ? zp_pk(j, k) : zp_pk(k, j)];
-                am[j] = t / sums.n;
-            }
-        }
-        double pc0[3];
-        for (int e = 0; e < 3; e++) pc0[e] = am[0] * ccs[e] + am[1] * ccs[3 + e] + am[2] * ccs[6 + e] + am[3] * ccs[9 + e];
-        double H[9];
-        for (int r = 0; r < 3; r++)
-            for (int c = 0; c < 3; c++)
-                H[3 * r + c] = ccs[r] * sums.w[c] + ccs[3 + r] * sums.w[3 + c] + ccs[6 + r] * sums.w[6 + c] +
-                               ccs[9 + r] * sums.w[9 + c];
-        double* R = out.R[cand];
-        zp_polar3(H, R);
-        double det = R[0] * (R[4] * R[8] - R[5] * R[7]) - R[1] * (R[3] * R[8] - R[5] * R[6]) +
-                     R[2] * (R[3] * R[7] - R[4] * R[6]);
-        if (det < 0) { R[6] = -R[6]; R[7] = -R[7]; R[8] = -R[8]; }
-        for (int r = 0; r < 3; r++)
-            out.t[cand][r] = pc0[r] - (R[3 * r] * pw0[0] + R[3 * r + 1] * pw0[1] + R[3 * r + 2] * pw0[2]);
-        bool ok = true;
-        for (int e = 0; e < 9; e++) ok = ok && isfinite(R[e]);
-        for (int e = 0; e < 3; e++) ok = ok && isfinite(out.t[cand][e]);
-        out.ok[cand] = ok;
-    }
-#undef ZPV
+    for (int q = 0; q < 4; q++)
+        for (int e = 0; e < 12; e++) At(q, e, 12) = v[q * 12 + e];
 }
 
 // pixel reprojection distance of one point (epnp::reprojection_error)
@@ -402,3 +437,64 @@ ZP_HD __forceinline__ double zp_reproj_dist(const double* R, const double* t, co
     double du = u - (cam.uc + cam.fu * Xc * iz), dv = v - (cam.vc + cam.fv * Yc * iz);
     return sqrt(du * du + dv * dv);
 }
+
+#ifdef __CUDACC__
+// ------------------------------------------------------------------------------------------------------------------
+// 16-lane cooperative one-sided Jacobi for the 12x12 problem.  Lane g (0..15, lanes 12..15 idle) of the group owns
+// COLUMN g of At: a[r] = At[r][g].  Six disjoint row pairs are rotated per round in a round-robin (tournament)
+// order, 11 rounds per sweep; dot products are 16-lane butterfly reductions, the rotation of pair q is computed by
+// lane q and broadcast.  On exit W[r] = sigma_r (uniform across the group) and a[r] = column element of sigma_r u_r^T.
+// Call with all 32 lanes of the warp converged (both half-warps run the same trip counts via a warp vote).
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double zp_sum16(double x) {
+#pragma unroll
+    for (int d = 8; d > 0; d >>= 1) x += __shfl_xor_sync(0xffffffffu, x, d, 16);
+    return x;
+}
+
+__device__ inline void zp_jacobi12_coop(double a[12], double W[12], int g) {
+    const double eps = ZP_DBL_EPS * 10;
+    for (int sweep = 0; sweep < 30; sweep++) {
+#pragma unroll
+        for (int r = 0; r < 12; r++) W[r] = zp_sum16(a[r] * a[r]);
+        bool changed = false;
+        for (int round = 0; round < 11; round++) {
+            double p[6];
+#pragma unroll
+            for (int q = 0; q < 6; q++) p[q] = zp_sum16(a[2 * q] * a[2 * q + 1]);
+            // lane q owns pair q
+            double pq = p[0], aq = W[0], bq = W[1];
+#pragma unroll
+            for (int q = 1; q < 6; q++)
+                if (g == q) { pq = p[q]; aq = W[2 * q]; bq = W[2 * q + 1]; }
+            double c = 1.0, s = 0.0;
+            bool rot = g < 6 && fabs(pq) > eps * sqrt(aq * bq);
+            if (rot) zp_rot(aq, bq, pq, c, s);
+            changed |= rot;
+#pragma unroll
+            for (int q = 0; q < 6; q++) {
+                double cq = __shfl_sync(0xffffffffu, c, q, 16), sq = __shfl_sync(0xffffffffu, s, q, 16);
+                double x = a[2 * q], y = a[2 * q + 1];
+                a[2 * q] = fma(cq, x, sq * y);
+                a[2 * q + 1] = fma(cq, y, -sq * x);
+                double A = W[2 * q], B = W[2 * q + 1], cc = cq * cq, ss = sq * sq, cs2 = 2 * cq * sq * p[q];
+                double na = fma(cc, A, fma(ss, B, cs2)), nb = fma(ss, A, fma(cc, B, -cs2));
+                W[2 * q] = na > 0 ? na : 0;
+                W[2 * q + 1] = nb > 0 ? nb : 0;
+            }
+            // tournament rotation of the slots (slot 0 fixed): bot0 -> top1 -> ... -> top5 -> bot5 -> ... -> bot1 -> bot0
+            {
+                double t1 = a[1], w1 = W[1];
+                a[1] = a[3]; a[3] = a[5]; a[5] = a[7]; a[7] = a[9]; a[9] = a[11];
+                W[1] = W[3]; W[3] = W[5]; W[5] = W[7]; W[7] = W[9]; W[9] = W[11];
+                a[11] = a[10]; a[10] = a[8]; a[8] = a[6]; a[6] = a[4]; a[4] = a[2];
+                W[11] = W[10]; W[10] = W[8]; W[8] = W[6]; W[6] = W[4]; W[4] = W[2];
+                a[2] = t1; W[2] = w1;
+            }
+        }
+        if (!__any_sync(0xffffffffu, changed)) break;
+    }
+#pragma unroll
+    for (int r = 0; r < 12; r++) W[r] = sqrt(zp_sum16(a[r] * a[r]));
+}
+#endif

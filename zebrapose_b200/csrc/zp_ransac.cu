@@ -1,17 +1,20 @@
 // Kernel family 2: batched RANSAC-PnP (replaces cv2.solvePnPRansac(..., reprojectionError=2, iterationsCount=150,
 // flags=SOLVEPNP_EPNP) + cv2.Rodrigues, /root/reference/zebrapose/binary_code_helper/CNN_output_to_pose.py:155-158).
 //
-//   zp_samples_kernel   one thread per crop replays cv::RNG(0xFFFFFFFFFFFFFFFF) (or Philox4x32-10) -> [B,H,m] index lists
+//   zp_samples_kernel   one CTA per crop, one thread per hypothesis: cv::RNG(0xFFFFFFFFFFFFFFFF) replayed from a
+//                       precomputed table of its raw 32-bit outputs; redraws on duplicates shift later hypotheses, which
+//                       is resolved by a fixed-point iteration over a block prefix sum (exact; usually 1-2 rounds).
+//                       Philox4x32-10 mode is counter based and needs no iteration.
 //   zp_minimal_kernel   one thread per hypothesis: float64 EPnP on the m sampled points (12x12 problem interleaved in
-//                       shared memory so a warp's accesses are conflict-free)
+//                       shared memory so a warp's accesses are conflict-free, row i of the Jacobi held in registers)
 //   zp_score_kernel     FP32-FMA bound: every correspondence x every hypothesis.  Correspondence tiles (SoA planes) are
 //                       staged into shared memory with 1-D TMA bulk copies (cp.async.bulk + mbarrier, double buffered),
 //                       hypotheses K[R|t] live in shared memory and are broadcast; the test is division free:
 //                       (x - u z)^2 + (y - v z)^2 <= thr^2 z^2.  Counts: per-thread -> warp REDUX -> shared -> global.
-//   zp_select_kernel    one thread per crop: cv2's sequential "strictly greater + RANSACUpdateNumIters" rule replayed
-//                       over the H counts (or plain argmax)
-//   zp_final_kernel     one CTA per crop: EPnP on all inliers of the winner (block reductions of the 52 EPnP sums),
-//                       optional Gauss-Newton polish of the reprojection error
+//   zp_final_kernel     one CTA per crop: cv2's sequential "strictly greater + RANSACUpdateNumIters" rule replayed over
+//                       the H counts (or argmax), then EPnP on all inliers of the winner: block reductions of the 52
+//                       EPnP sums, 16-lane cooperative Jacobi for the 12x12 null space, the three beta candidates on
+//                       three lanes, optional Gauss-Newton polish of the reprojection error
 //
 // Algorithmic FP32 work of scoring: 27 flop per (correspondence, hypothesis).
 #include "zp_common.cuh"
@@ -31,39 +34,112 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c[4], uint32_t k0, uint32
     }
 }
 
-__global__ void zp_samples_kernel(const int32_t* __restrict__ counts, int cap, int B, int H, int m, int mode,
-                                  uint64_t seed, int32_t* __restrict__ samples) {
-    int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= B) return;
-    int n = min(counts[b], cap);
+constexpr int SMP_THREADS = 256;
+
+// draws m distinct indices in [0,n) from the raw stream starting at table position `pos`; returns the number of raw
+// values consumed, or -1 if the table would be overrun
+__device__ __forceinline__ int draw_from_table(const uint32_t* __restrict__ tab, int n_tab, int pos, int n, int m, int* idx) {
+    int p = pos;
+    for (int j = 0; j < m; j++) {
+        int v;
+        bool dup;
+        do {
+            if (p >= n_tab) return -1;
+            v = (int)(tab[p++] % (uint32_t)n);
+            dup = false;
+            for (int q = 0; q < j; q++) dup |= idx[q] == v;
+        } while (dup);
+        idx[j] = v;
+    }
+    return p - pos;
+}
+
+// grid = B, block = SMP_THREADS; thread h handles hypotheses h, h + SMP_THREADS, ...
+__global__ void __launch_bounds__(SMP_THREADS)
+zp_samples_kernel(const int32_t* __restrict__ counts, int cap, int B, int H, int m, int mode, uint64_t seed,
+                  const uint32_t* __restrict__ rng_tab, int n_tab, int32_t* __restrict__ samples) {
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const int n = min(counts[b], cap);
     int32_t* out = samples + (size_t)b * H * m;
     if (n < m) {
-        for (int i = 0; i < H * m; i++) out[i] = -1;
+        for (int i = tid; i < H * m; i += SMP_THREADS) out[i] = -1;
         return;
     }
-    uint64_t state = 0xFFFFFFFFFFFFFFFFull;       // cv::RNG default state used by RANSACPointSetRegistrator
-    uint32_t ctr = 0;
-    for (int h = 0; h < H; h++) {
-        int idx[8];
-        for (int j = 0; j < m; j++) {
-            int v;
-            bool dup;
-            do {
-                uint32_t r;
-                if (mode == ZP_SAMPLER_CV2) {
-                    state = (uint64_t)(uint32_t)state * 4164903690ull + (state >> 32);   // multiply-with-carry
-                    r = (uint32_t)state;
-                } else {
-                    uint32_t c[4] = {ctr++, (uint32_t)h, (uint32_t)b, (uint32_t)j};
+    if (mode != ZP_SAMPLER_CV2) {                  // counter based: (attempt, hypothesis, crop, slot) -> value
+        for (int h = tid; h < H; h += SMP_THREADS) {
+            int idx[8];
+            for (int j = 0; j < m; j++) {
+                int v;
+                bool dup;
+                uint32_t attempt = 0;
+                do {
+                    uint32_t c[4] = {attempt++, (uint32_t)h, (uint32_t)b, (uint32_t)j};
                     philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
-                    r = c[0];
-                }
-                v = (int)(r % (uint32_t)n);
-                dup = false;
-                for (int q = 0; q < j; q++) dup |= idx[q] == v;
-            } while (dup);
-            idx[j] = v;
-            out[h * m + j] = v;
+                    v = (int)(c[0] % (uint32_t)n);
+                    dup = false;
+                    for (int q = 0; q < j; q++) dup |= idx[q] == v;
+                } while (dup);
+                idx[j] = v;
+                out[h * m + j] = v;
+            }
+        }
+        return;
+    }
+    // cv2 replay.  off[h] = first raw value hypothesis h consumes = m*h + (redraws of all earlier hypotheses).
+    __shared__ int s_cons[ZP_MAX_HYPOTHESES];
+    __shared__ int s_off[ZP_MAX_HYPOTHESES];
+    __shared__ int s_flag;
+    for (int h = tid; h < H; h += SMP_THREADS) s_off[h] = m * h;
+    __syncthreads();
+    bool overflow = false;
+    for (int round = 0; round <= H; round++) {
+        if (tid == 0) s_flag = 0;
+        __syncthreads();
+        for (int h = tid; h < H; h += SMP_THREADS) {
+            int idx[8];
+            int c = draw_from_table(rng_tab, n_tab, s_off[h], n, m, idx);
+            if (c < 0) { c = m; atomicOr(&s_flag, 2); }
+            s_cons[h] = c;
+        }
+        __syncthreads();
+        if (s_flag & 2) { overflow = true; break; }
+        if (tid == 0) {                            // H <= 1024: a serial scan is a few hundred cycles
+            int run = 0, chg = 0;
+            for (int h = 0; h < H; h++) {
+                chg |= s_off[h] != run;
+                s_off[h] = run;
+                run += s_cons[h];
+            }
+            if (chg) s_flag = 1;
+        }
+        __syncthreads();
+        if (!(s_flag & 1)) break;
+        __syncthreads();
+    }
+    if (!overflow) {
+        for (int h = tid; h < H; h += SMP_THREADS) {
+            int idx[8];
+            draw_from_table(rng_tab, n_tab, s_off[h], n, m, idx);
+            for (int j = 0; j < m; j++) out[h * m + j] = idx[j];
+        }
+        return;
+    }
+    if (tid == 0) {                                // pathological (tiny n): sequential generator, no table
+        uint64_t state = 0xFFFFFFFFFFFFFFFFull;
+        for (int h = 0; h < H; h++) {
+            int idx[8];
+            for (int j = 0; j < m; j++) {
+                int v;
+                bool dup;
+                do {
+                    state = (uint64_t)(uint32_t)state * 4164903690ull + (state >> 32);
+                    v = (int)((uint32_t)state % (uint32_t)n);
+                    dup = false;
+                    for (int q = 0; q < j; q++) dup |= idx[q] == v;
+                } while (dup);
+                idx[j] = v;
+                out[h * m + j] = v;
+            }
         }
     }
 }
@@ -124,24 +200,30 @@ zp_minimal_kernel(const float* __restrict__ corr, int cap, const int32_t* __rest
         zp_accumulate(sums, a, cam.uc - xn[j], cam.vc - yn[j], X[j] - c0[0], Y[j] - c0[1], Z[j] - c0[2]);
     }
     ZpMat At{smem_d + threadIdx.x, MIN_THREADS};
-    ZpCandidates cand;
-    zp_epnp_core(At, sums, cam, cp, a_first, c0, cand);
-    int best = -1;
-    double best_err = 0;
+    zp_nullspace_serial(At, sums, cam);            // rows 0..3 of At now hold the null-space vectors
+    double L[60], rho[6];
+    zp_L_rho(At, cp, L, rho);
+    bool have = false;
+    double best_err = 0, Rb[9], tb[3];
     for (int c = 0; c < 3; c++) {
-        if (!cand.ok[c]) continue;
+        double R[9], t[3];
+        if (!zp_candidate(c, L, rho, At, sums, a_first, c0, R, t)) continue;
         double e = 0;
-        for (int j = 0; j < m; j++) e += zp_reproj_dist(cand.R[c], cand.t[c], cam, X[j], Y[j], Z[j], xn[j], yn[j]);
+        for (int j = 0; j < m; j++) e += zp_reproj_dist(R, t, cam, X[j], Y[j], Z[j], xn[j], yn[j]);
         e /= m;
         if (!(e == e)) continue;
-        if (best < 0 || e < best_err) { best = c; best_err = e; }
+        if (!have || e < best_err) {
+            have = true; best_err = e;
+            for (int q = 0; q < 9; q++) Rb[q] = R[q];
+            for (int q = 0; q < 3; q++) tb[q] = t[q];
+        }
     }
-    if (best < 0) {
+    if (!have) {
         for (int e = 0; e < 12; e++) out[e] = nan("");
         return;
     }
-    for (int e = 0; e < 9; e++) out[e] = cand.R[best][e];
-    for (int e = 0; e < 3; e++) out[9 + e] = cand.t[best][e];
+    for (int e = 0; e < 9; e++) out[e] = Rb[e];
+    for (int e = 0; e < 3; e++) out[9 + e] = tb[e];
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -282,7 +364,7 @@ __global__ void __launch_bounds__(SC_THREADS) zp_score_kernel(ScoreArgs a) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// winner selection
+// winner selection + final solve on the inliers of the winner: one CTA per crop
 // ---------------------------------------------------------------------------------------------------------------
 __device__ inline int zp_update_iters(double p, double ep, int m, int maxit) {   // cv::RANSACUpdateNumIters
     p = fmin(fmax(p, 0.0), 1.0);
@@ -295,41 +377,6 @@ __device__ inline int zp_update_iters(double p, double ep, int m, int maxit) {  
     return (den >= 0 || -num >= maxit * (-den)) ? maxit : (int)rint(num / den);
 }
 
-__global__ void zp_select_kernel(const int32_t* __restrict__ counts, int cap, const int32_t* __restrict__ hyp_inliers,
-                                 int B, int H, int m, double conf, int mode, int32_t* __restrict__ best_idx,
-                                 int32_t* __restrict__ status) {
-    int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= B) return;
-    int n_raw = counts[b];
-    int n = min(n_raw, cap);
-    int best = -1, st = ZP_OK;
-    if (n_raw == 0) st = ZP_NO_MASK_PIXELS;
-    else if (n < 6) st = ZP_TOO_FEW_POINTS;          // CNN_output_to_pose.py:126
-    else {
-        const int32_t* c = hyp_inliers + (size_t)b * H;
-        int maxgood = 0;
-        if (mode == ZP_SELECT_CV2_REPLAY) {
-            int niters = max(H, 1);
-            for (int it = 0; it < niters && it < H; it++) {
-                int good = c[it];
-                if (good > max(maxgood, m - 1)) {
-                    best = it; maxgood = good;
-                    niters = zp_update_iters(conf, (double)(n - good) / n, m, niters);
-                }
-            }
-        } else {
-            for (int it = 0; it < H; it++)
-                if (c[it] > max(maxgood, m - 1)) { best = it; maxgood = c[it]; }
-        }
-        if (best < 0) st = ZP_RANSAC_NO_MODEL;
-    }
-    best_idx[b] = best;
-    status[b] = st;
-}
-
-// ---------------------------------------------------------------------------------------------------------------
-// final solve on the inliers of the winner: one CTA per crop
-// ---------------------------------------------------------------------------------------------------------------
 constexpr int FIN_THREADS = 256;
 
 template <int NV>
@@ -353,23 +400,60 @@ __device__ __forceinline__ void block_reduce(double* v, double* s_red /* [FIN_TH
 
 struct FinalArgs {
     const float* corr; int cap; const int32_t* counts; const double* K; const double* hyp_poses;
-    const int32_t* best_idx; const int32_t* status; int B, H; float thr2; int final_mode;
-    double* poses; int32_t* n_inliers; uint8_t* inlier_mask;
+    const int32_t* hyp_inliers; int B, H, m; double conf; int select_mode; float thr2; int final_mode;
+    double* poses; int32_t* n_inliers; int32_t* status; int32_t* best_idx; uint8_t* inlier_mask;
 };
 
 __global__ void __launch_bounds__(FIN_THREADS) zp_final_kernel(FinalArgs a) {
-    const int b = blockIdx.x, tid = threadIdx.x;
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
     __shared__ double s_red[(FIN_THREADS / 32) * 52];
     __shared__ double s_sum[52];
-    __shared__ double s_At[144];
+    __shared__ double s_V[48];
     __shared__ ZpControl s_cp;
-    __shared__ ZpCandidates s_cand;
+    __shared__ ZpSums s_sums;
+    __shared__ double s_candR[3][9], s_candt[3][3];
+    __shared__ int s_candok[3];
     __shared__ double s_pose[12];
-    __shared__ int s_first, s_n;
-    extern __shared__ uint32_t s_mask[];              // inlier bitset, (cap+31)/32 words (dynamic)
+    __shared__ int s_first, s_n, s_best, s_status;
+    extern __shared__ uint32_t s_dyn[];               // inlier bitset (cap+31)/32 words, then H counts
+    uint32_t* s_mask = s_dyn;
+    int* s_hi = (int*)(s_dyn + (a.cap + 31) / 32);
 
     double* out = a.poses + 12 * (size_t)b;
-    const int best = a.best_idx[b];
+    const int n_raw = a.counts[b];
+    const int n = min(n_raw, a.cap);
+    // ---- winner: cv2's rule replayed over the H counts (PnPRansac / RANSACPointSetRegistrator::run)
+    for (int h = tid; h < a.H; h += FIN_THREADS) s_hi[h] = a.hyp_inliers[(size_t)b * a.H + h];
+    __syncthreads();
+    if (tid == 0) {
+        int best = -1, st = ZP_OK;
+        if (n_raw == 0) st = ZP_NO_MASK_PIXELS;
+        else if (n < 6) st = ZP_TOO_FEW_POINTS;       // CNN_output_to_pose.py:126
+        else {
+            int maxgood = 0;
+            if (a.select_mode == ZP_SELECT_CV2_REPLAY) {
+                int niters = max(a.H, 1);
+                for (int it = 0; it < niters && it < a.H; it++) {
+                    int good = s_hi[it];
+                    if (good > max(maxgood, a.m - 1)) {
+                        best = it; maxgood = good;
+                        niters = zp_update_iters(a.conf, (double)(n - good) / n, a.m, niters);
+                    }
+                }
+            } else {
+                for (int it = 0; it < a.H; it++)
+                    if (s_hi[it] > max(maxgood, a.m - 1)) { best = it; maxgood = s_hi[it]; }
+            }
+            if (best < 0) st = ZP_RANSAC_NO_MODEL;
+        }
+        s_best = best; s_status = st;
+        a.status[b] = st;
+        if (a.best_idx) a.best_idx[b] = best;
+        s_first = 0x7fffffff; s_n = 0;
+    }
+    for (int i = tid; i < (a.cap + 31) / 32; i += FIN_THREADS) s_mask[i] = 0;
+    __syncthreads();
+    const int best = s_best;
     if (best < 0) {     // no model: cv2 leaves rvec = tvec = 0 and the reference reports R = I, t = 0
         if (tid < 12) out[tid] = (tid == 0 || tid == 4 || tid == 8) ? 1.0 : 0.0;
         if (tid == 0) a.n_inliers[b] = 0;
@@ -377,39 +461,38 @@ __global__ void __launch_bounds__(FIN_THREADS) zp_final_kernel(FinalArgs a) {
             for (int i = tid; i < a.cap; i += FIN_THREADS) a.inlier_mask[(size_t)b * a.cap + i] = 0;
         return;
     }
-    const int n = min(a.counts[b], a.cap);
     const float* cb = a.corr + (size_t)b * 5 * a.cap;
+    const float *pu = cb, *pv = cb + a.cap, *pX = cb + 2 * (size_t)a.cap, *pY = cb + 3 * (size_t)a.cap, *pZ = cb + 4 * (size_t)a.cap;
     const double* Kb = a.K + 9 * (size_t)b;
     const double* hp = a.hyp_poses + ((size_t)b * a.H + best) * 12;
     float P[12];
     zp_make_P(hp, Kb, P);
     const float4 p0 = make_float4(P[0], P[1], P[2], P[3]), p1 = make_float4(P[4], P[5], P[6], P[7]),
                  p2 = make_float4(P[8], P[9], P[10], P[11]);
-    if (tid == 0) { s_first = 0x7fffffff; s_n = 0; }
-    for (int i = tid; i < (a.cap + 31) / 32; i += FIN_THREADS) s_mask[i] = 0;
-    __syncthreads();
     // ---- pass 0: inlier set of the winner (same predicate as zp_score_kernel), centroid
     double acc[52];
     for (int q = 0; q < 52; q++) acc[q] = 0;
     int my_n = 0, my_first = 0x7fffffff;
-    for (int i = tid; i < n; i += FIN_THREADS) {
-        bool in = zp_is_inlier(p0, p1, p2, cb[i], cb[a.cap + i], cb[2 * (size_t)a.cap + i], cb[3 * (size_t)a.cap + i],
-                               cb[4 * (size_t)a.cap + i], a.thr2);
-        if (a.inlier_mask) a.inlier_mask[(size_t)b * a.cap + i] = in;
+    for (int i0 = 0; i0 < n; i0 += FIN_THREADS) {     // warp-aligned so the bitset is built with ballots
+        int i = i0 + tid;
+        bool in = i < n && zp_is_inlier(p0, p1, p2, pu[i], pv[i], pX[i], pY[i], pZ[i], a.thr2);
+        unsigned bal = __ballot_sync(0xffffffffu, in);
+        if (lane == 0 && i < a.cap) s_mask[i >> 5] = bal;
+        if (a.inlier_mask && i < n) a.inlier_mask[(size_t)b * a.cap + i] = in;
         if (in) {
-            atomicOr(&s_mask[i >> 5], 1u << (i & 31));
             my_n++; my_first = min(my_first, i);
-            acc[0] += cb[2 * (size_t)a.cap + i]; acc[1] += cb[3 * (size_t)a.cap + i]; acc[2] += cb[4 * (size_t)a.cap + i];
+            acc[0] += pX[i]; acc[1] += pY[i]; acc[2] += pZ[i];
         }
     }
     if (a.inlier_mask)
         for (int i = n + tid; i < a.cap; i += FIN_THREADS) a.inlier_mask[(size_t)b * a.cap + i] = 0;
-    atomicAdd(&s_n, my_n);
-    atomicMin(&s_first, my_first);
+    my_n = __reduce_add_sync(0xffffffffu, my_n);
+    my_first = __reduce_min_sync(0xffffffffu, my_first);
+    if (lane == 0) { atomicAdd(&s_n, my_n); atomicMin(&s_first, my_first); }
     block_reduce<3>(acc, s_red, s_sum);
     const int ni = s_n;
     if (tid == 0) a.n_inliers[b] = ni;
-    if (ni < 4) {       // cannot happen after selection (good > m-1 >= 4) but keep the output defined
+    if (ni < 4) {       // cannot happen after selection (good > m-1 >= 3) but keep the output defined
         if (tid < 12) out[tid] = hp[tid];
         return;
     }
@@ -419,9 +502,9 @@ __global__ void __launch_bounds__(FIN_THREADS) zp_final_kernel(FinalArgs a) {
     for (int q = 0; q < 9; q++) acc[q] = 0;
     for (int i = tid; i < n; i += FIN_THREADS)
         if (s_mask[i >> 5] >> (i & 31) & 1u) {
-            double d[3] = {cb[2 * (size_t)a.cap + i] - c0[0], cb[3 * (size_t)a.cap + i] - c0[1], cb[4 * (size_t)a.cap + i] - c0[2]};
-            acc[0] = fma(d[0], d[0], acc[0]); acc[1] = fma(d[0], d[1], acc[1]); acc[2] = fma(d[0], d[2], acc[2]);
-            acc[4] = fma(d[1], d[1], acc[4]); acc[5] = fma(d[1], d[2], acc[5]); acc[8] = fma(d[2], d[2], acc[8]);
+            double d0 = pX[i] - c0[0], d1 = pY[i] - c0[1], d2 = pZ[i] - c0[2];
+            acc[0] = fma(d0, d0, acc[0]); acc[1] = fma(d0, d1, acc[1]); acc[2] = fma(d0, d2, acc[2]);
+            acc[4] = fma(d1, d1, acc[4]); acc[5] = fma(d1, d2, acc[5]); acc[8] = fma(d2, d2, acc[8]);
         }
     acc[3] = acc[1]; acc[6] = acc[2]; acc[7] = acc[5];
     block_reduce<9>(acc, s_red, s_sum);
@@ -432,8 +515,7 @@ __global__ void __launch_bounds__(FIN_THREADS) zp_final_kernel(FinalArgs a) {
     }
     __syncthreads();
     // ---- pass 2: the 52 EPnP sums
-    const double fx = Kb[0], fy = Kb[4], cx = Kb[2], cy = Kb[5];
-    const ZpCam cam{fx, fy, cx, cy};
+    const ZpCam cam{Kb[0], Kb[4], Kb[2], Kb[5]};
     {
         ZpSums s;
         for (int q = 0; q < 10; q++) { s.s0[q] = 0; s.sx[q] = 0; s.sy[q] = 0; s.sr[q] = 0; }
@@ -441,56 +523,80 @@ __global__ void __launch_bounds__(FIN_THREADS) zp_final_kernel(FinalArgs a) {
         const ZpControl cp = s_cp;
         for (int i = tid; i < n; i += FIN_THREADS)
             if (s_mask[i >> 5] >> (i & 31) & 1u) {
-                double X = cb[2 * (size_t)a.cap + i], Y = cb[3 * (size_t)a.cap + i], Z = cb[4 * (size_t)a.cap + i];
-                double x = cx - (double)cb[i], y = cy - (double)cb[a.cap + i];
+                double X = pX[i], Y = pY[i], Z = pZ[i];
                 double al[4];
                 zp_alphas(cp, X, Y, Z, al);
-                zp_accumulate(s, al, x, y, X - c0[0], Y - c0[1], Z - c0[2]);
+                zp_accumulate(s, al, cam.uc - (double)pu[i], cam.vc - (double)pv[i], X - c0[0], Y - c0[1], Z - c0[2]);
             }
         for (int q = 0; q < 10; q++) { acc[q] = s.s0[q]; acc[10 + q] = s.sx[q]; acc[20 + q] = s.sy[q]; acc[30 + q] = s.sr[q]; }
         for (int q = 0; q < 12; q++) acc[40 + q] = s.w[q];
     }
     block_reduce<52>(acc, s_red, s_sum);
-    // ---- serial core (thread 0): 12x12 null space, betas, Horn
-    if (tid == 0) {
-        ZpSums s;
-        for (int q = 0; q < 10; q++) { s.s0[q] = s_sum[q]; s.sx[q] = s_sum[10 + q]; s.sy[q] = s_sum[20 + q]; s.sr[q] = s_sum[30 + q]; }
-        for (int q = 0; q < 12; q++) s.w[q] = s_sum[40 + q];
-        s.n = ni;
-        int f = s_first;
-        double af[4];
-        zp_alphas(s_cp, cb[2 * (size_t)a.cap + f], cb[3 * (size_t)a.cap + f], cb[4 * (size_t)a.cap + f], af);
-        ZpMat At{s_At, 1};
-        zp_epnp_core(At, s, cam, s_cp, af, c0, s_cand);
+    if (tid < 10) { s_sums.s0[tid] = s_sum[tid]; s_sums.sx[tid] = s_sum[10 + tid]; s_sums.sy[tid] = s_sum[20 + tid]; s_sums.sr[tid] = s_sum[30 + tid]; }
+    if (tid < 12) s_sums.w[tid] = s_sum[40 + tid];
+    if (tid == 0) s_sums.n = ni;
+    __syncthreads();
+    // ---- 12x12 null space on warp 0 (16-lane cooperative Jacobi; both half-warps run the same problem)
+    if (tid < 32) {
+        const int g = lane & 15;
+        double col[12], W[12];
+#pragma unroll
+        for (int r = 0; r < 12; r++) col[r] = g < 12 ? zp_mtm(s_sums, cam, r, g) : 0.0;
+        zp_jacobi12_coop(col, W, g);
+        bool used[12];
+#pragma unroll
+        for (int r = 0; r < 12; r++) used[r] = false;
+        for (int q = 0; q < 4; q++) {
+            int bi = -1;
+            double bw = 0, bv = 0;
+#pragma unroll
+            for (int r = 11; r >= 0; r--)
+                if (!used[r] && (bi < 0 || W[r] < bw)) { bi = r; bw = W[r]; bv = col[r]; }
+#pragma unroll
+            for (int r = 0; r < 12; r++) used[r] = used[r] || r == bi;
+            if (lane < 12) s_V[q * 12 + g] = bw > ZP_DBL_MIN ? bv / bw : 0.0;
+        }
+        __syncwarp();
+        // ---- the three beta candidates on three lanes
+        if (lane < 3) {
+            ZpMat V{s_V, 1};
+            double L[60], rho[6], af[4];
+            zp_L_rho(V, s_cp, L, rho);
+            int f = s_first;
+            zp_alphas(s_cp, pX[f], pY[f], pZ[f], af);
+            s_candok[lane] = zp_candidate(lane, L, rho, V, s_sums, af, c0, s_candR[lane], s_candt[lane]) ? 1 : 0;
+        }
     }
     __syncthreads();
     // ---- pass 3: mean reprojection distance of the three candidates, pick the best
     for (int q = 0; q < 3; q++) acc[q] = 0;
     for (int i = tid; i < n; i += FIN_THREADS)
         if (s_mask[i >> 5] >> (i & 31) & 1u) {
-            double X = cb[2 * (size_t)a.cap + i], Y = cb[3 * (size_t)a.cap + i], Z = cb[4 * (size_t)a.cap + i];
+            double X = pX[i], Y = pY[i], Z = pZ[i], u = pu[i], v = pv[i];
+#pragma unroll
             for (int c = 0; c < 3; c++)
-                if (s_cand.ok[c]) acc[c] += zp_reproj_dist(s_cand.R[c], s_cand.t[c], cam, X, Y, Z, (double)cb[i], (double)cb[a.cap + i]);
+                if (s_candok[c]) acc[c] += zp_reproj_dist(s_candR[c], s_candt[c], cam, X, Y, Z, u, v);
         }
     block_reduce<3>(acc, s_red, s_sum);
     if (tid == 0) {
         int pick = -1;
         double be = 0;
         for (int c = 0; c < 3; c++) {
-            if (!s_cand.ok[c]) continue;
+            if (!s_candok[c]) continue;
             double e = s_sum[c] / ni;
             if (!(e == e)) continue;
             if (pick < 0 || e < be) { pick = c; be = e; }
         }
         if (pick < 0) for (int e = 0; e < 12; e++) s_pose[e] = hp[e];
         else {
-            for (int e = 0; e < 9; e++) s_pose[e] = s_cand.R[pick][e];
-            for (int e = 0; e < 3; e++) s_pose[9 + e] = s_cand.t[pick][e];
+            for (int e = 0; e < 9; e++) s_pose[e] = s_candR[pick][e];
+            for (int e = 0; e < 3; e++) s_pose[9 + e] = s_candt[pick][e];
         }
     }
     __syncthreads();
     // ---- optional Gauss-Newton polish of the pixel reprojection error over the inliers (north_star extension)
     if (a.final_mode == ZP_FINAL_EPNP_GN) {
+        const double fx = cam.fu, fy = cam.fv, cx = cam.uc, cy = cam.vc;
         for (int iter = 0; iter < 5; iter++) {
             double R[9], t[3];
             for (int e = 0; e < 9; e++) R[e] = s_pose[e];
@@ -498,11 +604,10 @@ __global__ void __launch_bounds__(FIN_THREADS) zp_final_kernel(FinalArgs a) {
             for (int q = 0; q < 27; q++) acc[q] = 0;     // 21 JtJ (upper) + 6 Jtr
             for (int i = tid; i < n; i += FIN_THREADS)
                 if (s_mask[i >> 5] >> (i & 31) & 1u) {
-                    double X = cb[2 * (size_t)a.cap + i], Y = cb[3 * (size_t)a.cap + i], Z = cb[4 * (size_t)a.cap + i];
+                    double X = pX[i], Y = pY[i], Z = pZ[i];
                     double px = R[0] * X + R[1] * Y + R[2] * Z, py = R[3] * X + R[4] * Y + R[5] * Z, pz = R[6] * X + R[7] * Y + R[8] * Z;
                     double xc = px + t[0], yc = py + t[1], zc = pz + t[2], iz = 1.0 / zc;
-                    double ru = fx * xc * iz + cx - (double)cb[i], rv = fy * yc * iz + cy - (double)cb[a.cap + i];
-                    // d(proj)/d(cam point)
+                    double ru = fx * xc * iz + cx - (double)pu[i], rv = fy * yc * iz + cy - (double)pv[i];
                     double ju[3] = {fx * iz, 0, -fx * xc * iz * iz}, jv[3] = {0, fy * iz, -fy * yc * iz * iz};
                     // cam point = exp(w) (R X) + t + dt  ->  d/dw = -[R X]_x , d/dt = I
                     double Ju[6] = {ju[1] * (-pz) + ju[2] * py, ju[0] * pz + ju[2] * (-px), ju[0] * (-py) + ju[1] * px, ju[0], ju[1], ju[2]};
@@ -519,8 +624,7 @@ __global__ void __launch_bounds__(FIN_THREADS) zp_final_kernel(FinalArgs a) {
                 for (int r = 0; r < 6; r++)
                     for (int c = r; c < 6; c++) { A[6 * r + c] = s_sum[q]; A[6 * c + r] = s_sum[q]; q++; }
                 for (int r = 0; r < 6; r++) g[r] = -s_sum[21 + r];
-                // Cholesky solve A d = g
-                bool okc = true;
+                bool okc = true;                         // Cholesky solve A d = g
                 for (int r = 0; r < 6 && okc; r++) {
                     for (int c = 0; c <= r; c++) {
                         double sacc = A[6 * r + c];
@@ -532,7 +636,6 @@ __global__ void __launch_bounds__(FIN_THREADS) zp_final_kernel(FinalArgs a) {
                 if (okc) {
                     for (int r = 0; r < 6; r++) { double sacc = g[r]; for (int k = 0; k < r; k++) sacc -= A[6 * r + k] * d[k]; d[r] = sacc / A[6 * r + r]; }
                     for (int r = 5; r >= 0; r--) { double sacc = d[r]; for (int k = r + 1; k < 6; k++) sacc -= A[6 * k + r] * d[k]; d[r] = sacc / A[6 * r + r]; }
-                    // R <- exp([w]_x) R (Rodrigues), t <- t + dt   (left perturbation of the rotated point)
                     double th = sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
                     double E[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
                     if (th > 1e-300) {
@@ -571,7 +674,7 @@ __global__ void zp_fma_probe_kernel(float* out, int iters, float a, float b) {
 // ---------------------------------------------------------------------------------------------------------------
 int zp_launch_samples(zp_ctx* ctx, const int32_t* counts, int cap, int B, int H, int m, int mode, uint64_t seed,
                       int32_t* samples, cudaStream_t st) {
-    zp_samples_kernel<<<(B + 63) / 64, 64, 0, st>>>(counts, cap, B, H, m, mode, seed, samples);
+    zp_samples_kernel<<<B, SMP_THREADS, 0, st>>>(counts, cap, B, H, m, mode, seed, ctx->d_rng, ctx->n_rng, samples);
     ZP_CHECK_LAUNCH(ctx, "zp_samples_kernel");
     return 0;
 }
@@ -613,21 +716,17 @@ int zp_launch_score(zp_ctx* ctx, const float* corr, int cap, const int32_t* coun
     return 0;
 }
 
-int zp_launch_select(zp_ctx* ctx, const int32_t* counts, int cap, const int32_t* hyp_inliers, int B, int H, int m,
-                     double conf, int mode, int32_t* best_idx, int32_t* status, cudaStream_t st) {
-    zp_select_kernel<<<(B + 127) / 128, 128, 0, st>>>(counts, cap, hyp_inliers, B, H, m, conf, mode, best_idx, status);
-    ZP_CHECK_LAUNCH(ctx, "zp_select_kernel");
-    return 0;
-}
-
 int zp_launch_final(zp_ctx* ctx, const float* corr, int cap, const int32_t* counts, const double* K,
-                    const double* hyp_poses, const int32_t* best_idx, const int32_t* status, int B, int H, float thr_px,
-                    int final_mode, double* poses, int32_t* n_inliers, uint8_t* inlier_mask, cudaStream_t st) {
+                    const double* hyp_poses, const int32_t* hyp_inliers, int B, int H, int m, double conf, int select_mode,
+                    float thr_px, int final_mode, double* poses, int32_t* n_inliers, int32_t* status, int32_t* best_idx,
+                    uint8_t* inlier_mask, cudaStream_t st) {
     FinalArgs a;
-    a.corr = corr; a.cap = cap; a.counts = counts; a.K = K; a.hyp_poses = hyp_poses; a.best_idx = best_idx;
-    a.status = status; a.B = B; a.H = H; a.thr2 = thr_px * thr_px; a.final_mode = final_mode; a.poses = poses;
-    a.n_inliers = n_inliers; a.inlier_mask = inlier_mask;
-    zp_final_kernel<<<B, FIN_THREADS, ((cap + 31) / 32) * sizeof(uint32_t), st>>>(a);
+    a.corr = corr; a.cap = cap; a.counts = counts; a.K = K; a.hyp_poses = hyp_poses; a.hyp_inliers = hyp_inliers;
+    a.B = B; a.H = H; a.m = m; a.conf = conf; a.select_mode = select_mode; a.thr2 = thr_px * thr_px;
+    a.final_mode = final_mode; a.poses = poses; a.n_inliers = n_inliers; a.status = status; a.best_idx = best_idx;
+    a.inlier_mask = inlier_mask;
+    size_t smem = ((size_t)(cap + 31) / 32 + H) * sizeof(uint32_t);
+    zp_final_kernel<<<B, FIN_THREADS, smem, st>>>(a);
     ZP_CHECK_LAUNCH(ctx, "zp_final_kernel");
     return 0;
 }
