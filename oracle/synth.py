@@ -20,6 +20,17 @@ def make_dict(n_bits=16, seed=0, radius=50.0, missing_frac=0.0):
     v = rng.normal(size=(n, 3))
     v /= np.linalg.norm(v, axis=1, keepdims=True)
     pts = v * radius * rng.uniform(0.7, 1.0, (n, 1))
+    # hierarchical codes like Generate_Mesh_with_GT_Color.cpp's balanced 2-means (:61, :396): bit l splits every
+    # group of the previous level in two equal halves along its widest axis, so sibling codes are spatial neighbours
+    # and the ignore-bit parents (mean of the children) stay on the surface
+    order = np.arange(n)
+    for level in range(n_bits):
+        g = pts[order].reshape(1 << level, n >> level, 3)
+        axis = g.var(1).argmax(1)
+        key = np.take_along_axis(g, axis[:, None, None], 2)[:, :, 0]
+        sub = np.argsort(key, 1, kind="stable")
+        order = np.take_along_axis(order.reshape(1 << level, n >> level), sub, 1).ravel()
+    pts, v = pts[order], v[order]
     pts = np.array([[float("%.6g" % c) for c in p] for p in pts]) if n <= 4096 else _round6(pts)
     missing = rng.random(n) < missing_frac
     tab = pts.copy()

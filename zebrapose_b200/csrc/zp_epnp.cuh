@@ -51,6 +51,19 @@ ZP_HD __forceinline__ void zp_rot(double a, double b, double p, double& c, doubl
     if (beta < 0) { s = big; c = small; } else { c = big; s = small; }
 }
 
+// Same orthogonalising rotation with the SMALL angle (|theta| <= pi/4, no implicit row swap): required for
+// convergence under the parallel round-robin order of the cooperative Jacobi.
+ZP_HD __forceinline__ void zp_rot_small(double a, double b, double p, double& c, double& s) {
+    double p2 = 2 * p, beta = a - b;
+    double g2 = fma(p2, p2, beta * beta);
+    double ig = zp_rsqrt(g2);
+    double h = fma(0.5 * fabs(beta), ig, 0.5);
+    double rh = zp_rsqrt(h);
+    c = h * rh;
+    s = p * ig * rh;
+    if (beta < 0) s = -s;
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 // serial one-sided Jacobi on the rows of At (N x N), OpenCV's cyclic pair order (i<j ascending) and stopping rule
 // (eps = 10*DBL_EPSILON, max(N,30) sweeps).  Row i is held in registers across the j loop; squared norms follow the
@@ -469,7 +482,7 @@ __device__ inline void zp_jacobi12_coop(double a[12], double W[12], int g) {
                 if (g == q) { pq = p[q]; aq = W[2 * q]; bq = W[2 * q + 1]; }
             double c = 1.0, s = 0.0;
             bool rot = g < 6 && fabs(pq) > eps * sqrt(aq * bq);
-            if (rot) zp_rot(aq, bq, pq, c, s);
+            if (rot) zp_rot_small(aq, bq, pq, c, s);
             changed |= rot;
 #pragma unroll
             for (int q = 0; q < 6; q++) {
