@@ -131,6 +131,9 @@ int zp_pose_batch_host(zp_ctx* ctx, const void* h_logits, int dtype, int B, int 
 /* Number of kernels this ctx has launched since creation (bench.py's gpu_launches claim). */
 int64_t zp_launch_count(zp_ctx* ctx);
 
+/* Profiling aid: SM-clock timestamps of the phases of CTA 0 of the last final-solve launch (16 slots; synchronises). */
+int zp_debug_clocks(zp_ctx* ctx, int64_t* out16);
+
 /* FP32 FMA-chain microbenchmark (the roofline denominator for zp_score has no entry in MEASURED_PEAKS.json):
  * runs `iters` dependent-chain FMAs x 8 chains per thread on the whole chip, returns achieved TFLOP/s in *out.
  * Synchronises. */

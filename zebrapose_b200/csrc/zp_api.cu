@@ -11,6 +11,7 @@ int zp_launch_score(zp_ctx*, const float*, int, const int32_t*, const double*, c
 int zp_launch_final(zp_ctx*, const float*, int, const int32_t*, const double*, const double*, const int32_t*, int, int, int,
                     double, int, float, int, double*, int32_t*, int32_t*, int32_t*, uint8_t*, cudaStream_t);
 int zp_launch_fma_probe(zp_ctx*, int, double*);
+int zp_read_debug_clocks(long long*);
 int zp_launch_remap_pixels(zp_ctx*, const int64_t*, int64_t, const double*, int, int64_t*, cudaStream_t);
 int zp_launch_codes_to_ids(zp_ctx*, const double*, int64_t, int, int, double*, cudaStream_t);
 
@@ -325,6 +326,12 @@ int zp_pose_batch_host(zp_ctx* ctx, const void* h_logits, int dtype, int B, int 
     ZP_CUDA(ctx, cudaMemcpyAsync(h_status, d_st, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
     ZP_CUDA(ctx, cudaStreamSynchronize(st));
     return 0;
+}
+
+int zp_debug_clocks(zp_ctx* ctx, int64_t* out16) {
+    if (!ctx || !out16) return -1;
+    ZP_CUDA(ctx, cudaDeviceSynchronize());
+    return zp_read_debug_clocks((long long*)out16);
 }
 
 int zp_fp32_peak_probe(zp_ctx* ctx, int iters, double* out_tflops) {

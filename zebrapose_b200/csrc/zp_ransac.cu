@@ -379,6 +379,10 @@ __device__ inline int zp_update_iters(double p, double ep, int m, int maxit) {  
 
 constexpr int FIN_THREADS = 256;
 
+// phase timestamps of CTA 0 of the last zp_final_kernel launch (debug / profiling aid, read with zp_debug_clocks)
+__device__ long long zp_dbg_clk[16];
+#define ZP_STAMP(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) zp_dbg_clk[i] = clock64(); } while (0)
+
 template <int NV>
 __device__ __forceinline__ void block_reduce(double* v, double* s_red /* [FIN_THREADS/32][NV] */, double* s_out) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -419,6 +423,7 @@ __global__ void __launch_bounds__(FIN_THREADS) zp_final_kernel(FinalArgs a) {
     uint32_t* s_mask = s_dyn;
     int* s_hi = (int*)(s_dyn + (a.cap + 31) / 32);
 
+    ZP_STAMP(0);
     double* out = a.poses + 12 * (size_t)b;
     const int n_raw = a.counts[b];
     const int n = min(n_raw, a.cap);
@@ -469,6 +474,7 @@ __global__ void __launch_bounds__(FIN_THREADS) zp_final_kernel(FinalArgs a) {
     zp_make_P(hp, Kb, P);
     const float4 p0 = make_float4(P[0], P[1], P[2], P[3]), p1 = make_float4(P[4], P[5], P[6], P[7]),
                  p2 = make_float4(P[8], P[9], P[10], P[11]);
+    ZP_STAMP(1);
     // ---- pass 0: inlier set of the winner (same predicate as zp_score_kernel), centroid
     double acc[52];
     for (int q = 0; q < 52; q++) acc[q] = 0;
@@ -498,6 +504,7 @@ __global__ void __launch_bounds__(FIN_THREADS) zp_final_kernel(FinalArgs a) {
     }
     const double c0[3] = {s_sum[0] / ni, s_sum[1] / ni, s_sum[2] / ni};
     __syncthreads();
+    ZP_STAMP(2);
     // ---- pass 1: scatter matrix
     for (int q = 0; q < 9; q++) acc[q] = 0;
     for (int i = tid; i < n; i += FIN_THREADS)
@@ -508,12 +515,14 @@ __global__ void __launch_bounds__(FIN_THREADS) zp_final_kernel(FinalArgs a) {
         }
     acc[3] = acc[1]; acc[6] = acc[2]; acc[7] = acc[5];
     block_reduce<9>(acc, s_red, s_sum);
+    ZP_STAMP(3);
     if (tid == 0) {
         double C[9];
         for (int q = 0; q < 9; q++) C[q] = s_sum[q];
         zp_control_points(c0, C, (double)ni, s_cp);
     }
     __syncthreads();
+    ZP_STAMP(4);
     // ---- pass 2: the 52 EPnP sums
     const ZpCam cam{Kb[0], Kb[4], Kb[2], Kb[5]};
     {
@@ -536,6 +545,7 @@ __global__ void __launch_bounds__(FIN_THREADS) zp_final_kernel(FinalArgs a) {
     if (tid < 12) s_sums.w[tid] = s_sum[40 + tid];
     if (tid == 0) s_sums.n = ni;
     __syncthreads();
+    ZP_STAMP(5);
     // ---- 12x12 null space on warp 0 (16-lane cooperative Jacobi; both half-warps run the same problem)
     if (tid < 32) {
         const int g = lane & 15;
@@ -543,6 +553,7 @@ __global__ void __launch_bounds__(FIN_THREADS) zp_final_kernel(FinalArgs a) {
 #pragma unroll
         for (int r = 0; r < 12; r++) col[r] = g < 12 ? zp_mtm(s_sums, cam, r, g) : 0.0;
         zp_jacobi12_coop(col, W, g);
+        ZP_STAMP(6);
         bool used[12];
 #pragma unroll
         for (int r = 0; r < 12; r++) used[r] = false;
@@ -557,6 +568,7 @@ __global__ void __launch_bounds__(FIN_THREADS) zp_final_kernel(FinalArgs a) {
             if (lane < 12) s_V[q * 12 + g] = bw > ZP_DBL_MIN ? bv / bw : 0.0;
         }
         __syncwarp();
+        ZP_STAMP(7);
         // ---- the three beta candidates on three lanes
         if (lane < 3) {
             ZpMat V{s_V, 1};
@@ -568,6 +580,7 @@ __global__ void __launch_bounds__(FIN_THREADS) zp_final_kernel(FinalArgs a) {
         }
     }
     __syncthreads();
+    ZP_STAMP(8);
     // ---- pass 3: mean reprojection distance of the three candidates, pick the best
     for (int q = 0; q < 3; q++) acc[q] = 0;
     for (int i = tid; i < n; i += FIN_THREADS)
@@ -654,6 +667,7 @@ __global__ void __launch_bounds__(FIN_THREADS) zp_final_kernel(FinalArgs a) {
             __syncthreads();
         }
     }
+    ZP_STAMP(9);
     if (tid < 12) out[tid] = s_pose[tid];
 }
 
@@ -729,6 +743,10 @@ int zp_launch_final(zp_ctx* ctx, const float* corr, int cap, const int32_t* coun
     zp_final_kernel<<<B, FIN_THREADS, smem, st>>>(a);
     ZP_CHECK_LAUNCH(ctx, "zp_final_kernel");
     return 0;
+}
+
+int zp_read_debug_clocks(long long* host16) {
+    return cudaMemcpyFromSymbol(host16, zp_dbg_clk, sizeof(long long) * 16) == cudaSuccess ? 0 : -2;
 }
 
 int zp_launch_fma_probe(zp_ctx* ctx, int iters, double* out_tflops) {
