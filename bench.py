@@ -239,7 +239,9 @@ def main():
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         dec_bytes = C * (1 + NBITS) * S * S * 4 + 20 * Mtot + 4 * C          # algorithmic HBM bytes
         dec_gbs = dec_bytes / (k_ms["zp_decode_cluster_kernel"] * 1e-3) / 1e9
-        fp32_peak = eng.fp32_peak_tflops()
+        fp32_scalar = eng.fp32_peak_tflops()
+        fp32_packed = eng.fp32_peak_tflops(packed=True)
+        fp32_peak = max(fp32_scalar, fp32_packed)
         sc_flops = 27.0 * H * Mtot                                            # 27 flop / (corr x hyp)
         sc_tf = sc_flops / (k_ms["zp_score_kernel"] * 1e-3) / 1e12
         chain = k_ms["zp_decode_cluster_kernel"] + k_ms["ransac_chain(samples+minimal+score+select+final)"]
@@ -272,7 +274,7 @@ def main():
                          "algorithmic_bytes_per_launch": dec_bytes, "us_per_launch": k_ms["zp_decode_cluster_kernel"] * 1e3},
             "roofline_score": {"kernel": "zp_score_kernel", "bound": "fp32", "achieved": sc_tf, "peak": fp32_peak,
                                "unit": "TFLOP/s", "frac": sc_tf / fp32_peak if fp32_peak else None,
-                               "peak_source": "zp_fp32_peak_probe (FMA chains, measured on this GPU in this run)",
+                               "peak_source": "max of zp_fp32_peak_probe (scalar FFMA chains, %.1f) and zp_fp32x2_peak_probe (packed FFMA2 chains, %.1f), measured on this GPU in this run" % (fp32_scalar, fp32_packed),
                                "algorithmic_flops_per_launch": sc_flops, "us_per_launch": k_ms["zp_score_kernel"] * 1e3},
             "kernel_us": {k: round(v * 1e3, 2) for k, v in k_ms.items()},
             "kernel_share_of_step": shares,

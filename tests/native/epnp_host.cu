@@ -42,10 +42,12 @@ int main() {
         zp_nullspace_serial(At, s, cam);
         double L[60], rho[6];
         zp_L_rho(At, cp, L, rho);
+        ZpHorn hs;
+        zp_horn_inputs(s, hs);
         int best = -1; double be = 0, Rb[9], tb[3];
         for (int c = 0; c < 3; c++) {
             double R[9], t[3];
-            if (!zp_candidate(c, L, rho, At, s, af, c0, R, t)) continue;
+            if (!zp_candidate(c, L, rho, At, hs, af, c0, R, t)) continue;
             double e = 0;
             for (int i = 0; i < n; i++) e += zp_reproj_dist(R, t, cam, X[i], Y[i], Z[i], x[i], y[i]);
             e /= n;

@@ -35,6 +35,7 @@ SIGNATURES = {
     "zp_launch_count": (_i64, [_vp]),
     "zp_debug_clocks": (_i, [_vp, _vp]),
     "zp_fp32_peak_probe": (_i, [_vp, _i, C.POINTER(_d)]),
+    "zp_fp32x2_peak_probe": (_i, [_vp, _i, C.POINTER(_d)]),
 }
 
 _lib = None

@@ -4,13 +4,13 @@
 #include "zp_common.cuh"
 
 int zp_launch_samples(zp_ctx*, const int32_t*, int, int, int, int, int, uint64_t, int32_t*, cudaStream_t);
-int zp_launch_minimal(zp_ctx*, const float*, int, const int32_t*, const double*, const int32_t*, int, int, int, double*,
-                      cudaStream_t);
-int zp_launch_score(zp_ctx*, const float*, int, const int32_t*, const double*, const double*, int, int, float, int32_t*,
-                    cudaStream_t);
+int zp_launch_minimal(zp_ctx*, const float*, int, const int32_t*, const double*, const int32_t*, int, int, int, float,
+                      double*, float*, cudaStream_t);
+int zp_launch_poses_to_P(zp_ctx*, const double*, const double*, int, int, float, float*, cudaStream_t);
+int zp_launch_score(zp_ctx*, const float*, int, const int32_t*, const float*, int, int, float, int32_t*, cudaStream_t);
 int zp_launch_final(zp_ctx*, const float*, int, const int32_t*, const double*, const double*, const int32_t*, int, int, int,
                     double, int, float, int, double*, int32_t*, int32_t*, int32_t*, uint8_t*, cudaStream_t);
-int zp_launch_fma_probe(zp_ctx*, int, double*);
+int zp_launch_fma_probe(zp_ctx*, int, int, double*);
 int zp_read_debug_clocks(long long*);
 int zp_launch_remap_pixels(zp_ctx*, const int64_t*, int64_t, const double*, int, int64_t*, cudaStream_t);
 int zp_launch_codes_to_ids(zp_ctx*, const double*, int64_t, int, int, double*, cudaStream_t);
@@ -76,6 +76,10 @@ int zp_create(zp_ctx** out, int device) {
             delete ctx; g_err = "context allocation failed"; return -2;
         }
         ctx->n_rng = n;
+        if (cudaMalloc((void**)&ctx->d_counters, 2 * sizeof(int)) != cudaSuccess ||
+            cudaMemset(ctx->d_counters, 0, 2 * sizeof(int)) != cudaSuccess) {
+            delete ctx; g_err = "context allocation failed"; return -2;
+        }
     }
     *out = ctx;
     return 0;
@@ -88,6 +92,7 @@ void zp_destroy(zp_ctx* ctx) {
     for (auto& t : ctx->tables) { if (t.pts) cudaFree(t.pts); if (t.remap) cudaFree(t.remap); }
     if (ctx->d_table_ptrs) cudaFree((void*)ctx->d_table_ptrs);
     if (ctx->d_rng) cudaFree(ctx->d_rng);
+    if (ctx->d_counters) cudaFree(ctx->d_counters);
     if (ctx->ws) cudaFree(ctx->ws);
     if (ctx->hws) cudaFree(ctx->hws);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -233,7 +238,9 @@ int zp_solve_minimal(zp_ctx* ctx, const float* corr, int cap, const int32_t* cou
     if (!corr || !counts || !K || !samples || !hyp_poses) ZP_FAIL(ctx, -1, "zp_solve_minimal: null argument");
     if (m < 4 || m > 8 || H < 1 || H > ZP_MAX_HYPOTHESES) ZP_FAIL(ctx, -1, "zp_solve_minimal: bad m/H %d/%d", m, H);
     ZP_CUDA(ctx, cudaSetDevice(ctx->device));
-    return zp_launch_minimal(ctx, corr, cap, counts, K, samples, B, H, m, hyp_poses, (cudaStream_t)stream);
+    if (zp_ws_reserve(ctx, (size_t)B * H * 24 * sizeof(float))) return -2;
+    return zp_launch_minimal(ctx, corr, cap, counts, K, samples, B, H, m, 2.0f, hyp_poses, (float*)ctx->ws,
+                             (cudaStream_t)stream);
 }
 
 static int check_corr(zp_ctx* ctx, const float* corr, int cap, const char* who) {
@@ -249,8 +256,11 @@ int zp_score(zp_ctx* ctx, const float* corr, int cap, const int32_t* counts, con
     if (!corr || !counts || !K || !hyp_poses || !hyp_inliers) ZP_FAIL(ctx, -1, "zp_score: null argument");
     if (H < 1 || H > ZP_MAX_HYPOTHESES) ZP_FAIL(ctx, -1, "zp_score: bad H %d", H);
     if (check_corr(ctx, corr, cap, "zp_score")) return -1;
+    if (!(thr_px > 0)) ZP_FAIL(ctx, -1, "zp_score: thr_px must be > 0");
     ZP_CUDA(ctx, cudaSetDevice(ctx->device));
-    return zp_launch_score(ctx, corr, cap, counts, K, hyp_poses, B, H, thr_px, hyp_inliers, (cudaStream_t)stream);
+    if (zp_ws_reserve(ctx, (size_t)B * H * 24 * sizeof(float))) return -2;
+    if (int r = zp_launch_poses_to_P(ctx, hyp_poses, K, B, H, thr_px, (float*)ctx->ws, (cudaStream_t)stream)) return r;
+    return zp_launch_score(ctx, corr, cap, counts, (const float*)ctx->ws, B, H, thr_px, hyp_inliers, (cudaStream_t)stream);
 }
 
 static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
@@ -267,8 +277,10 @@ int zp_ransac(zp_ctx* ctx, const float* corr, int cap, const int32_t* counts, co
     if (check_corr(ctx, corr, cap, "zp_ransac")) return -1;
     ZP_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = (cudaStream_t)stream;
-    // workspace: samples | hyp_poses | hyp_inliers (only what the caller did not supply)
-    size_t o_s = 0, o_p = o_s + (samples ? 0 : align256((size_t)B * H * m * 4));
+    if (!(thr_px > 0)) ZP_FAIL(ctx, -1, "zp_ransac: thr_px must be > 0");
+    // workspace: hyp_P | samples | hyp_poses | hyp_inliers (the last three only if the caller did not supply them)
+    size_t o_P = 0, o_s = o_P + align256((size_t)B * H * 24 * 4);
+    size_t o_p = o_s + (samples ? 0 : align256((size_t)B * H * m * 4));
     size_t o_i = o_p + (hyp_poses ? 0 : align256((size_t)B * H * 12 * 8));
     size_t total = o_i + (hyp_inliers ? 0 : align256((size_t)B * H * 4));
     if (total && zp_ws_reserve(ctx, total)) return -2;
@@ -280,8 +292,9 @@ int zp_ransac(zp_ctx* ctx, const float* corr, int cap, const int32_t* counts, co
     }
     double* d_hp = hyp_poses ? hyp_poses : (double*)(ws + o_p);
     int32_t* d_hi = hyp_inliers ? hyp_inliers : (int32_t*)(ws + o_i);
-    if (int r = zp_launch_minimal(ctx, corr, cap, counts, K, samples ? samples : d_samples, B, H, m, d_hp, st)) return r;
-    if (int r = zp_launch_score(ctx, corr, cap, counts, K, d_hp, B, H, thr_px, d_hi, st)) return r;
+    float* d_P = (float*)(ws + o_P);
+    if (int r = zp_launch_minimal(ctx, corr, cap, counts, K, samples ? samples : d_samples, B, H, m, thr_px, d_hp, d_P, st)) return r;
+    if (int r = zp_launch_score(ctx, corr, cap, counts, d_P, B, H, thr_px, d_hi, st)) return r;
     return zp_launch_final(ctx, corr, cap, counts, K, d_hp, d_hi, B, H, m, confidence, select_mode, thr_px, final_mode,
                            poses, n_inliers, status, best_idx, inlier_mask, st);
 }
@@ -337,7 +350,13 @@ int zp_debug_clocks(zp_ctx* ctx, int64_t* out16) {
 int zp_fp32_peak_probe(zp_ctx* ctx, int iters, double* out_tflops) {
     if (!ctx || !out_tflops) return -1;
     ZP_CUDA(ctx, cudaSetDevice(ctx->device));
-    return zp_launch_fma_probe(ctx, iters, out_tflops);
+    return zp_launch_fma_probe(ctx, iters, 0, out_tflops);
+}
+
+int zp_fp32x2_peak_probe(zp_ctx* ctx, int iters, double* out_tflops) {
+    if (!ctx || !out_tflops) return -1;
+    ZP_CUDA(ctx, cudaSetDevice(ctx->device));
+    return zp_launch_fma_probe(ctx, iters, 1, out_tflops);
 }
 
 }  // extern "C"

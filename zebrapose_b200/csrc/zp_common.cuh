@@ -25,6 +25,7 @@ struct zp_ctx {
     const float4** d_table_ptrs = nullptr;   // device array [ZP_MAX_OBJECTS]
     uint32_t* d_rng = nullptr;               // raw outputs of cv::RNG(0xFFFFFFFFFFFFFFFF), replayed by zp_samples_kernel
     int n_rng = 0;
+    int* d_counters = nullptr;               // [2] work-queue ticket + done counter of zp_score_kernel (self re-arming)
     // growable device workspace
     void* ws = nullptr;
     size_t ws_bytes = 0;

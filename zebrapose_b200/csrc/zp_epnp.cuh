@@ -246,6 +246,9 @@ struct ZpSums {
     double n;
 };
 
+// what the pose-from-betas step needs from the sums: mean alphas and W_j (17 doubles instead of 53)
+struct ZpHorn { double am[4]; double w[12]; };
+
 ZP_HD __forceinline__ int zp_pk(int j, int k) {     // packed index of the symmetric 4x4 (j<=k)
     const int base[4] = {0, 4, 7, 9};
     return base[j] + (k - j);
@@ -337,9 +340,8 @@ ZP_HD inline void zp_L_rho(ZpMat V, const ZpControl& cp, double* L, double* rho)
 // One of EPnP's three candidates: beta initialisation `cand` (find_betas_approx_1/2/3), 5 Gauss-Newton steps,
 // camera-frame control points, sign, Horn.  a_first = alphas of the first correspondence (solve_for_sign looks at its
 // camera-frame depth), pw0 = centroid.  Returns false when the pose is not finite.
-ZP_HD inline bool zp_candidate(int cand, const double* L, const double* rho, ZpMat V, const ZpSums& sums,
-                               const double a_first[4], const double pw0[3], double* R, double* t) {
-    double be[4] = {0, 0, 0, 0};
+ZP_HD inline void zp_betas_init(int cand, const double* L, const double* rho, double be[4]) {
+    be[0] = be[1] = be[2] = be[3] = 0;
     if (cand == 0) {
         double A[24], b[6], x[4];
         for (int r = 0; r < 6; r++) {
@@ -371,41 +373,63 @@ ZP_HD inline bool zp_candidate(int cand, const double* L, const double* rho, ZpM
         if (x[1] < 0) be[0] = -be[0];
         be[2] = x[3] / be[0];
     }
-    for (int it = 0; it < 5; it++) {           // gauss_newton / compute_A_and_b_gauss_newton
+}
+
+// one Gauss-Newton system (compute_A_and_b_gauss_newton)
+ZP_HD __forceinline__ void zp_gn_system(const double* L, const double* rho, const double be[4], double* A, double* b) {
+    for (int r = 0; r < 6; r++) {
+        const double* l = L + 10 * r;
+        A[4 * r + 0] = 2 * l[0] * be[0] + l[1] * be[1] + l[3] * be[2] + l[6] * be[3];
+        A[4 * r + 1] = l[1] * be[0] + 2 * l[2] * be[1] + l[4] * be[2] + l[7] * be[3];
+        A[4 * r + 2] = l[3] * be[0] + l[4] * be[1] + 2 * l[5] * be[2] + l[8] * be[3];
+        A[4 * r + 3] = l[6] * be[0] + l[7] * be[1] + l[8] * be[2] + 2 * l[9] * be[3];
+        b[r] = rho[r] - (l[0] * be[0] * be[0] + l[1] * be[0] * be[1] + l[2] * be[1] * be[1] +
+                         l[3] * be[0] * be[2] + l[4] * be[1] * be[2] + l[5] * be[2] * be[2] +
+                         l[6] * be[0] * be[3] + l[7] * be[1] * be[3] + l[8] * be[2] * be[3] +
+                         l[9] * be[3] * be[3]);
+    }
+}
+
+ZP_HD inline void zp_horn_inputs(const ZpSums& sums, ZpHorn& h) {
+    for (int j = 0; j < 4; j++) {       // mean alphas: sum_i a_ij = sum_k sum_i a_ij a_ik because sum_k a_ik = 1
+        double s = 0;
+        for (int k = 0; k < 4; k++) s += sums.s0[j <= k ? zp_pk(j, k) : zp_pk(k, j)];
+        h.am[j] = s / sums.n;
+    }
+    for (int e = 0; e < 12; e++) h.w[e] = sums.w[e];
+}
+
+ZP_HD inline bool zp_pose_from_betas(const double be[4], ZpMat V, const ZpHorn& hs, const double a_first[4],
+                                     const double pw0[3], double* R, double* t);
+
+ZP_HD inline bool zp_candidate(int cand, const double* L, const double* rho, ZpMat V, const ZpHorn& hs,
+                               const double a_first[4], const double pw0[3], double* R, double* t) {
+    double be[4];
+    zp_betas_init(cand, L, rho, be);
+    for (int it = 0; it < 5; it++) {           // gauss_newton
         double A[24], b[6], x[4];
-        for (int r = 0; r < 6; r++) {
-            const double* l = L + 10 * r;
-            A[4 * r + 0] = 2 * l[0] * be[0] + l[1] * be[1] + l[3] * be[2] + l[6] * be[3];
-            A[4 * r + 1] = l[1] * be[0] + 2 * l[2] * be[1] + l[4] * be[2] + l[7] * be[3];
-            A[4 * r + 2] = l[3] * be[0] + l[4] * be[1] + 2 * l[5] * be[2] + l[8] * be[3];
-            A[4 * r + 3] = l[6] * be[0] + l[7] * be[1] + l[8] * be[2] + 2 * l[9] * be[3];
-            b[r] = rho[r] - (l[0] * be[0] * be[0] + l[1] * be[0] * be[1] + l[2] * be[1] * be[1] +
-                             l[3] * be[0] * be[2] + l[4] * be[1] * be[2] + l[5] * be[2] * be[2] +
-                             l[6] * be[0] * be[3] + l[7] * be[1] * be[3] + l[8] * be[2] * be[3] +
-                             l[9] * be[3] * be[3]);
-        }
+        zp_gn_system(L, rho, be, A, b);
         zp_ls6<4>(A, b, x);
         for (int q = 0; q < 4; q++) be[q] += x[q];
     }
+    return zp_pose_from_betas(be, V, hs, a_first, pw0, R, t);
+}
+
+ZP_HD inline bool zp_pose_from_betas(const double be[4], ZpMat V, const ZpHorn& hs, const double a_first[4],
+                                     const double pw0[3], double* R, double* t) {
     double ccs[12];
     for (int e = 0; e < 12; e++)
         ccs[e] = be[0] * V(0, e, 12) + be[1] * V(1, e, 12) + be[2] * V(2, e, 12) + be[3] * V(3, e, 12);
     double z_first = a_first[0] * ccs[2] + a_first[1] * ccs[5] + a_first[2] * ccs[8] + a_first[3] * ccs[11];
     if (z_first < 0)
         for (int e = 0; e < 12; e++) ccs[e] = -ccs[e];
-    double am[4];       // mean alphas: sum_i a_ij = sum_k sum_i a_ij a_ik because sum_k a_ik = 1
-    for (int j = 0; j < 4; j++) {
-        double s = 0;
-        for (int k = 0; k < 4; k++) s += sums.s0[j <= k ? zp_pk(j, k) : zp_pk(k, j)];
-        am[j] = s / sums.n;
-    }
+    const double* am = hs.am;
     double pc0[3];
     for (int e = 0; e < 3; e++) pc0[e] = am[0] * ccs[e] + am[1] * ccs[3 + e] + am[2] * ccs[6 + e] + am[3] * ccs[9 + e];
     double H[9];        // sum_i (pc_i - pc0)(pw_i - pw0)^T = sum_j ccs_j W_j^T
     for (int r = 0; r < 3; r++)
         for (int c = 0; c < 3; c++)
-            H[3 * r + c] = ccs[r] * sums.w[c] + ccs[3 + r] * sums.w[3 + c] + ccs[6 + r] * sums.w[6 + c] +
-                           ccs[9 + r] * sums.w[9 + c];
+            H[3 * r + c] = ccs[r] * hs.w[c] + ccs[3 + r] * hs.w[3 + c] + ccs[6 + r] * hs.w[6 + c] + ccs[9 + r] * hs.w[9 + c];
     zp_polar3(H, R);
     double det = R[0] * (R[4] * R[8] - R[5] * R[7]) - R[1] * (R[3] * R[8] - R[5] * R[6]) +
                  R[2] * (R[3] * R[7] - R[4] * R[6]);
@@ -453,61 +477,138 @@ ZP_HD __forceinline__ double zp_reproj_dist(const double* R, const double* t, co
 
 #ifdef __CUDACC__
 // ------------------------------------------------------------------------------------------------------------------
-// 16-lane cooperative one-sided Jacobi for the 12x12 problem.  Lane g (0..15, lanes 12..15 idle) of the group owns
-// COLUMN g of At: a[r] = At[r][g].  Six disjoint row pairs are rotated per round in a round-robin (tournament)
-// order, 11 rounds per sweep; dot products are 16-lane butterfly reductions, the rotation of pair q is computed by
-// lane q and broadcast.  On exit W[r] = sigma_r (uniform across the group) and a[r] = column element of sigma_r u_r^T.
-// Call with all 32 lanes of the warp converged (both half-warps run the same trip counts via a warp vote).
+// Group-cooperative one-sided Jacobi for the 12x12 problem: G lanes per problem (G = 4: 8 problems per warp, each lane
+// owns 3 columns of At; G = 16: 2 problems per warp, lanes 0..11 own one column each).  a[r][c] = At[r][col0 + c].
+// Six disjoint row pairs are rotated per round in a round-robin (tournament) order, 11 rounds per sweep.  Per round:
+//   - the six dot products: local FMAs + a log2(G)-step butterfly (shuffles);
+//   - the rotation (small angle) and the new squared norms of pair t are computed by ONE owner lane (t mod G) -- the
+//     FP64 pipe issues one warp instruction every 2 cycles, so redundant rotation math was the bottleneck -- and
+//     broadcast with shuffles;
+//   - every lane rotates its own columns; the slots are permuted by register moves.
+// Norms are recomputed exactly every sweep.  All 32 lanes of the warp must call it together; the sweep loop runs until
+// every problem of the warp has converged (extra sweeps are identity rotations).
+// On exit W[r] = sigma_r (uniform in the group) and a[r][*] = this lane's columns of sigma_r u_r^T.
 // ------------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ double zp_sum16(double x) {
+template <int G>
+__device__ __forceinline__ double zp_groupsum(double x) {
 #pragma unroll
-    for (int d = 8; d > 0; d >>= 1) x += __shfl_xor_sync(0xffffffffu, x, d, 16);
+    for (int d = 1; d < G; d <<= 1) x += __shfl_xor_sync(0xffffffffu, x, d);
     return x;
 }
 
-__device__ inline void zp_jacobi12_coop(double a[12], double W[12], int g) {
-    const double eps = ZP_DBL_EPS * 10;
+template <int G>
+__device__ inline void zp_jacobi12_group(double (*a)[(G == 4) ? 3 : 1], double* W, int gl /* lane in group */) {
+    constexpr int CPL = (G == 4) ? 3 : 1;
+    constexpr int PASSES = (6 + G - 1) / G;
+    const double eps2 = (ZP_DBL_EPS * 10) * (ZP_DBL_EPS * 10);
     for (int sweep = 0; sweep < 30; sweep++) {
 #pragma unroll
-        for (int r = 0; r < 12; r++) W[r] = zp_sum16(a[r] * a[r]);
+        for (int r = 0; r < 12; r++) {
+            double v = 0;
+#pragma unroll
+            for (int k = 0; k < CPL; k++) v = fma(a[r][k], a[r][k], v);
+            W[r] = zp_groupsum<G>(v);
+        }
         bool changed = false;
+#pragma unroll 1
         for (int round = 0; round < 11; round++) {
             double p[6];
 #pragma unroll
-            for (int q = 0; q < 6; q++) p[q] = zp_sum16(a[2 * q] * a[2 * q + 1]);
-            // lane q owns pair q
-            double pq = p[0], aq = W[0], bq = W[1];
+            for (int t = 0; t < 6; t++) {
+                double v = 0;
 #pragma unroll
-            for (int q = 1; q < 6; q++)
-                if (g == q) { pq = p[q]; aq = W[2 * q]; bq = W[2 * q + 1]; }
-            double c = 1.0, s = 0.0;
-            bool rot = g < 6 && fabs(pq) > eps * sqrt(aq * bq);
-            if (rot) zp_rot_small(aq, bq, pq, c, s);
-            changed |= rot;
+                for (int k = 0; k < CPL; k++) v = fma(a[2 * t][k], a[2 * t + 1][k], v);
+                p[t] = zp_groupsum<G>(v);
+            }
+            double rc[PASSES], rs[PASSES], ra[PASSES], rb[PASSES];
 #pragma unroll
-            for (int q = 0; q < 6; q++) {
-                double cq = __shfl_sync(0xffffffffu, c, q, 16), sq = __shfl_sync(0xffffffffu, s, q, 16);
-                double x = a[2 * q], y = a[2 * q + 1];
-                a[2 * q] = fma(cq, x, sq * y);
-                a[2 * q + 1] = fma(cq, y, -sq * x);
-                double A = W[2 * q], B = W[2 * q + 1], cc = cq * cq, ss = sq * sq, cs2 = 2 * cq * sq * p[q];
-                double na = fma(cc, A, fma(ss, B, cs2)), nb = fma(ss, A, fma(cc, B, -cs2));
-                W[2 * q] = na > 0 ? na : 0;
-                W[2 * q + 1] = nb > 0 ? nb : 0;
+            for (int ps = 0; ps < PASSES; ps++) {
+                // this lane owns pair t = ps*G + gl (if < 6): pick its inputs with a select chain
+                double pq = p[ps * G], A = W[2 * ps * G], Bn = W[2 * ps * G + 1];
+#pragma unroll
+                for (int t = ps * G + 1; t < 6 && t < (ps + 1) * G; t++)
+                    if (gl == t - ps * G) { pq = p[t]; A = W[2 * t]; Bn = W[2 * t + 1]; }
+                bool mine = ps * G + gl < 6;
+                bool rot = mine && pq * pq > eps2 * A * Bn;
+                double cc, ss;
+                zp_rot_small(A, Bn, rot ? pq : 1.0, cc, ss);
+                cc = rot ? cc : 1.0;
+                ss = rot ? ss : 0.0;
+                changed |= rot;
+                double c2 = cc * cc, s2 = ss * ss, cs2 = 2 * cc * ss * pq;
+                double na = fma(c2, A, fma(s2, Bn, cs2)), nb = fma(s2, A, fma(c2, Bn, -cs2));
+                rc[ps] = cc; rs[ps] = ss; ra[ps] = na > 0 ? na : 0; rb[ps] = nb > 0 ? nb : 0;
+            }
+#pragma unroll
+            for (int t = 0; t < 6; t++) {
+                const int ps = t / G, src = t % G;
+                double c = __shfl_sync(0xffffffffu, rc[ps], src, G), s = __shfl_sync(0xffffffffu, rs[ps], src, G);
+                W[2 * t] = __shfl_sync(0xffffffffu, ra[ps], src, G);
+                W[2 * t + 1] = __shfl_sync(0xffffffffu, rb[ps], src, G);
+#pragma unroll
+                for (int k = 0; k < CPL; k++) {
+                    double x = a[2 * t][k], y = a[2 * t + 1][k];
+                    a[2 * t][k] = fma(c, x, s * y);
+                    a[2 * t + 1][k] = fma(c, y, -s * x);
+                }
             }
             // tournament rotation of the slots (slot 0 fixed): bot0 -> top1 -> ... -> top5 -> bot5 -> ... -> bot1 -> bot0
+#pragma unroll
+            for (int k = 0; k < CPL; k++) {
+                double t1 = a[1][k];
+                a[1][k] = a[3][k]; a[3][k] = a[5][k]; a[5][k] = a[7][k]; a[7][k] = a[9][k]; a[9][k] = a[11][k];
+                a[11][k] = a[10][k]; a[10][k] = a[8][k]; a[8][k] = a[6][k]; a[6][k] = a[4][k]; a[4][k] = a[2][k];
+                a[2][k] = t1;
+            }
             {
-                double t1 = a[1], w1 = W[1];
-                a[1] = a[3]; a[3] = a[5]; a[5] = a[7]; a[7] = a[9]; a[9] = a[11];
+                double w1 = W[1];
                 W[1] = W[3]; W[3] = W[5]; W[5] = W[7]; W[7] = W[9]; W[9] = W[11];
-                a[11] = a[10]; a[10] = a[8]; a[8] = a[6]; a[6] = a[4]; a[4] = a[2];
                 W[11] = W[10]; W[10] = W[8]; W[8] = W[6]; W[6] = W[4]; W[4] = W[2];
-                a[2] = t1; W[2] = w1;
+                W[2] = w1;
             }
         }
         if (!__any_sync(0xffffffffu, changed)) break;
     }
 #pragma unroll
-    for (int r = 0; r < 12; r++) W[r] = sqrt(zp_sum16(a[r] * a[r]));
+    for (int r = 0; r < 12; r++) {
+        double v = 0;
+#pragma unroll
+        for (int k = 0; k < CPL; k++) v = fma(a[r][k], a[r][k], v);
+        W[r] = sqrt(zp_groupsum<G>(v));
+    }
+}
+
+// Null space by a group of G lanes: builds this lane's columns of M^T M from the sums, runs the Jacobi and writes the
+// four normalised singular vectors of the smallest singular values to V (v = 0 smallest): V[v * 12 + e], 48 doubles.
+template <int G>
+__device__ inline void zp_nullspace_group(const ZpSums& sums, const ZpCam& cam, int gl, double* V) {
+    constexpr int CPL = (G == 4) ? 3 : 1;
+    double a[12][CPL], W[12];
+    const bool has_cols = gl * CPL < 12;
+#pragma unroll
+    for (int r = 0; r < 12; r++)
+#pragma unroll
+        for (int c = 0; c < CPL; c++) a[r][c] = has_cols ? zp_mtm(sums, cam, r, gl * CPL + c) : 0.0;
+    zp_jacobi12_group<G>(a, W, gl);
+    bool used[12];
+#pragma unroll
+    for (int r = 0; r < 12; r++) used[r] = false;
+    for (int v = 0; v < 4; v++) {
+        int bi = -1;
+        double bw = 0, bv[CPL];
+#pragma unroll
+        for (int r = 11; r >= 0; r--)
+            if (!used[r] && (bi < 0 || W[r] < bw)) {
+                bi = r; bw = W[r];
+#pragma unroll
+                for (int c = 0; c < CPL; c++) bv[c] = a[r][c];
+            }
+#pragma unroll
+        for (int r = 0; r < 12; r++) used[r] = used[r] || r == bi;
+        double inv = bw > ZP_DBL_MIN ? 1.0 / bw : 0.0;
+        if (has_cols)
+#pragma unroll
+            for (int c = 0; c < CPL; c++) V[v * 12 + gl * CPL + c] = bv[c] * inv;
+    }
 }
 #endif

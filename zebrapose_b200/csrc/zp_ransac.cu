@@ -147,36 +147,104 @@ zp_samples_kernel(const int32_t* __restrict__ counts, int cap, int B, int H, int
 // ---------------------------------------------------------------------------------------------------------------
 // minimal solver
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int MIN_THREADS = 64;
+// ---------------------------------------------------------------------------------------------------------------
+// projection matrices and the inlier predicate shared by the minimal solver (writes P), scoring and the final solve
+// ---------------------------------------------------------------------------------------------------------------
+// P = diag(1/thr, 1/thr, 1) K [R|t] evaluated in double, rounded once to float32.  Folding the threshold into rows 0,1
+// (and into u, v: see zp_inlier_d) turns the test into (x - u z)^2 + (y - v z)^2 <= z^2.  A non-finite pose gives P = 0,
+// for which the predicate is false for every point.
+__device__ __forceinline__ void zp_make_P(const double* pose, const double* K, double inv_thr, float P[12]) {
+    const double fx = K[0], sk = K[1], cx = K[2], fy = K[4], cy = K[5];
+    bool fin = true;
+#pragma unroll
+    for (int e = 0; e < 12; e++) fin = fin && isfinite(pose[e]);
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+        double r0 = c < 3 ? pose[c] : pose[9], r1 = c < 3 ? pose[3 + c] : pose[10], r2 = c < 3 ? pose[6 + c] : pose[11];
+        P[c] = fin ? (float)((fx * r0 + sk * r1 + cx * r2) * inv_thr) : 0.f;
+        P[4 + c] = fin ? (float)((fy * r1 + cy * r2) * inv_thr) : 0.f;
+        P[8 + c] = fin ? (float)r2 : 0.f;
+    }
+}
+
+// d = (x - u z)^2 + (y - v z)^2 - z^2 with [x y z] = P [X Y Z 1] and u, v already divided by thr; the point is an inlier
+// iff d < 0, i.e. iff the SIGN BIT of d is set (14 FP32-pipe instructions, no compare; explicit fmaf so every kernel
+// rounds identically).
+__device__ __forceinline__ float zp_inlier_d(const float4& p0, const float4& p1, const float4& p2, float u, float v,
+                                             float X, float Y, float Z) {
+    float x = fmaf(p0.x, X, fmaf(p0.y, Y, fmaf(p0.z, Z, p0.w)));
+    float y = fmaf(p1.x, X, fmaf(p1.y, Y, fmaf(p1.z, Z, p1.w)));
+    float z = fmaf(p2.x, X, fmaf(p2.y, Y, fmaf(p2.z, Z, p2.w)));
+    float dx = fmaf(-u, z, x);
+    float dy = fmaf(-v, z, y);
+    float e = fmaf(dx, dx, __fmul_rn(dy, dy));
+    return fmaf(-z, z, e);                         // same roundings as the packed (FFMA2) form in zp_score_kernel
+}
+
+// packed FP32 pairs (Blackwell FFMA2 / FMUL2 / FADD2): two independent IEEE fma.rn per instruction, one issue slot and
+// one 64-bit operand read per source
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 zp_fma2(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ f32x2 zp_mul2(f32x2 a, f32x2 b) {
+    f32x2 d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ f32x2 zp_sub2(f32x2 a, f32x2 b) {
+    f32x2 d;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ f32x2 zp_pack2(float lo, float hi) {
+    return (f32x2)__float_as_uint(lo) | ((f32x2)__float_as_uint(hi) << 32);
+}
+__device__ __forceinline__ bool zp_is_inlier(const float4& p0, const float4& p1, const float4& p2, float u, float v,
+                                             float X, float Y, float Z) {
+    return __float_as_int(zp_inlier_d(p0, p1, p2, u, v, X, Y, Z)) < 0;
+}
+
+// phase timestamps of thread 0 of CTA 0 (profiling aid, read with zp_debug_clocks): slots 0-9 final kernel, 10-15 minimal
+__device__ long long zp_dbg_clk[16];
+#define ZP_STAMP(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) zp_dbg_clk[i] = clock64(); } while (0)
+
+constexpr int MIN_THREADS = 128;                 // 4 lanes per hypothesis -> 32 hypotheses per CTA
 constexpr int ZP_MAX_M = 8;
 
-__global__ void __launch_bounds__(MIN_THREADS)
+// One QUAD (4 lanes) per hypothesis.  The cheap serial setup (control points, 52 sums over the m points) is computed
+// redundantly by the 4 lanes; the 12x12 null space is the quad-cooperative Jacobi; the three beta candidates run on
+// lanes 0..2; the winner (smallest mean reprojection distance over the m points, EPnP's rule) writes the pose.
+__global__ void __launch_bounds__(MIN_THREADS, 3)
 zp_minimal_kernel(const float* __restrict__ corr, int cap, const int32_t* __restrict__ counts,
                   const double* __restrict__ Kmat, const int32_t* __restrict__ samples, int B, int H, int m,
-                  double* __restrict__ hyp_poses) {
-    extern __shared__ double smem_d[];
-    const int g = blockIdx.x * MIN_THREADS + threadIdx.x;
-    if (g >= B * H) return;
+                  double inv_thr, double* __restrict__ hyp_poses, float* __restrict__ hyp_P) {
+    __shared__ double s_V[MIN_THREADS / 4][48];
+    const int tid = threadIdx.x, lane = tid & 31, q = lane & 3, quad = tid >> 2;
+    const int total = B * H;
+    const int g_raw = blockIdx.x * (MIN_THREADS / 4) + quad;
+    const bool live = g_raw < total;
+    const int g = live ? g_raw : total - 1;        // dead quads shadow the last hypothesis (all lanes take part in shuffles)
     const int b = g / H;
-    double* out = hyp_poses + (size_t)g * 12;
+    ZP_STAMP(10);
     const int32_t* sidx = samples + (size_t)g * m;
     const int n = min(counts[b], cap);
     bool valid = n >= m;
     for (int j = 0; j < m; j++) valid = valid && sidx[j] >= 0 && sidx[j] < n;
-    if (!valid) {
-        for (int e = 0; e < 12; e++) out[e] = nan("");
-        return;
-    }
     const double* Kb = Kmat + 9 * (size_t)b;
     const ZpCam cam{Kb[0], Kb[4], Kb[2], Kb[5]};
     const float* cb = corr + (size_t)b * 5 * cap;
-    double X[ZP_MAX_M], Y[ZP_MAX_M], Z[ZP_MAX_M], xn[ZP_MAX_M], yn[ZP_MAX_M];   // xn, yn: pixel coordinates
+    double X[ZP_MAX_M], Y[ZP_MAX_M], Z[ZP_MAX_M], U[ZP_MAX_M], Vv[ZP_MAX_M];
     double c0[3] = {0, 0, 0};
     for (int j = 0; j < m; j++) {
-        int i = sidx[j];
-        xn[j] = (double)cb[i];
-        yn[j] = (double)cb[cap + i];
-        X[j] = cb[2 * (size_t)cap + i]; Y[j] = cb[3 * (size_t)cap + i]; Z[j] = cb[4 * (size_t)cap + i];
+        int i = valid ? sidx[j] : 0;
+        U[j] = valid ? (double)cb[i] : (double)j;
+        Vv[j] = valid ? (double)cb[cap + i] : (double)(j * j);
+        X[j] = valid ? (double)cb[2 * (size_t)cap + i] : (double)j;
+        Y[j] = valid ? (double)cb[3 * (size_t)cap + i] : (double)(j & 1);
+        Z[j] = valid ? (double)cb[4 * (size_t)cap + i] : (double)(j & 2);
         c0[0] += X[j]; c0[1] += Y[j]; c0[2] += Z[j];
     }
     c0[0] /= m; c0[1] /= m; c0[2] /= m;
@@ -188,76 +256,75 @@ zp_minimal_kernel(const float* __restrict__ corr, int cap, const int32_t* __rest
     }
     ZpControl cp;
     zp_control_points(c0, C, (double)m, cp);
-    ZpSums sums;
-    for (int q = 0; q < 10; q++) { sums.s0[q] = 0; sums.sx[q] = 0; sums.sy[q] = 0; sums.sr[q] = 0; }
-    for (int q = 0; q < 12; q++) sums.w[q] = 0;
-    sums.n = m;
+    ZpHorn hs;
     double a_first[4];
-    for (int j = 0; j < m; j++) {
-        double a[4];
-        zp_alphas(cp, X[j], Y[j], Z[j], a);
-        if (j == 0) { a_first[0] = a[0]; a_first[1] = a[1]; a_first[2] = a[2]; a_first[3] = a[3]; }
-        zp_accumulate(sums, a, cam.uc - xn[j], cam.vc - yn[j], X[j] - c0[0], Y[j] - c0[1], Z[j] - c0[2]);
+    ZP_STAMP(11);
+    {
+        ZpSums sums;
+        for (int e = 0; e < 10; e++) { sums.s0[e] = 0; sums.sx[e] = 0; sums.sy[e] = 0; sums.sr[e] = 0; }
+        for (int e = 0; e < 12; e++) sums.w[e] = 0;
+        sums.n = m;
+        for (int j = 0; j < m; j++) {
+            double a[4];
+            zp_alphas(cp, X[j], Y[j], Z[j], a);
+            if (j == 0) { a_first[0] = a[0]; a_first[1] = a[1]; a_first[2] = a[2]; a_first[3] = a[3]; }
+            zp_accumulate(sums, a, cam.uc - U[j], cam.vc - Vv[j], X[j] - c0[0], Y[j] - c0[1], Z[j] - c0[2]);
+        }
+        zp_horn_inputs(sums, hs);
+        zp_nullspace_group<4>(sums, cam, q, s_V[quad]);
     }
-    ZpMat At{smem_d + threadIdx.x, MIN_THREADS};
-    zp_nullspace_serial(At, sums, cam);            // rows 0..3 of At now hold the null-space vectors
+    __syncwarp();
+    ZP_STAMP(12);
+    ZpMat V{s_V[quad], 1};
     double L[60], rho[6];
-    zp_L_rho(At, cp, L, rho);
-    bool have = false;
-    double best_err = 0, Rb[9], tb[3];
+    zp_L_rho(V, cp, L, rho);
+    ZP_STAMP(13);
+    double R[9], t[3];
+    bool ok = zp_candidate(q < 3 ? q : 2, L, rho, V, hs, a_first, c0, R, t);
+    double err = 0;
+    for (int j = 0; j < m; j++) err += zp_reproj_dist(R, t, cam, X[j], Y[j], Z[j], U[j], Vv[j]);
+    err /= m;
+    ok = ok && err == err && q < 3;
+    ZP_STAMP(14);
+    // EPnP's choice: N = 1; if (err2 < err1) N = 2; if (err3 < err_N) N = 3 -- with non-finite candidates skipped
+    const int base = lane & ~3;
+    int pick = -1;
+    double pe = 0;
     for (int c = 0; c < 3; c++) {
-        double R[9], t[3];
-        if (!zp_candidate(c, L, rho, At, sums, a_first, c0, R, t)) continue;
-        double e = 0;
-        for (int j = 0; j < m; j++) e += zp_reproj_dist(R, t, cam, X[j], Y[j], Z[j], xn[j], yn[j]);
-        e /= m;
-        if (!(e == e)) continue;
-        if (!have || e < best_err) {
-            have = true; best_err = e;
-            for (int q = 0; q < 9; q++) Rb[q] = R[q];
-            for (int q = 0; q < 3; q++) tb[q] = t[q];
+        double ec = __shfl_sync(0xffffffffu, err, base + c);
+        int oc = __shfl_sync(0xffffffffu, (int)ok, base + c);
+        if (oc && (pick < 0 || ec < pe)) { pick = c; pe = ec; }
+    }
+    if (live) {
+        double* out = hyp_poses + (size_t)g * 12;
+        float4* outP = (float4*)(hyp_P + (size_t)g * 24);       // every element twice: (P,P) pairs for FFMA2
+        if (!valid || pick < 0) {
+            if (q == 0) {
+                for (int e = 0; e < 12; e++) out[e] = nan("");
+                for (int e = 0; e < 6; e++) outP[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        } else if (q == pick) {
+            double pose[12];
+            for (int e = 0; e < 9; e++) pose[e] = R[e];
+            for (int e = 0; e < 3; e++) pose[9 + e] = t[e];
+            for (int e = 0; e < 12; e++) out[e] = pose[e];
+            float P[12];
+            zp_make_P(pose, Kb, inv_thr, P);
+            for (int e = 0; e < 6; e++) outP[e] = make_float4(P[2 * e], P[2 * e], P[2 * e + 1], P[2 * e + 1]);
         }
     }
-    if (!have) {
-        for (int e = 0; e < 12; e++) out[e] = nan("");
-        return;
-    }
-    for (int e = 0; e < 9; e++) out[e] = Rb[e];
-    for (int e = 0; e < 3; e++) out[9 + e] = tb[e];
+    ZP_STAMP(15);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
 // scoring
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int SC_THREADS = 256;
-constexpr int SC_PPT = 4;                          // correspondences per thread
-constexpr int SC_TILE = SC_THREADS * SC_PPT;       // correspondences per tile
-constexpr int SC_STAGES = 2;
-
-// projection rows in float32 from a float64 pose: P = K [R|t] evaluated in double, rounded once
-__device__ __forceinline__ void zp_make_P(const double* pose, const double* K, float P[12]) {
-    const double fx = K[0], sk = K[1], cx = K[2], fy = K[4], cy = K[5];
-#pragma unroll
-    for (int c = 0; c < 4; c++) {
-        double r0 = c < 3 ? pose[c] : pose[9], r1 = c < 3 ? pose[3 + c] : pose[10], r2 = c < 3 ? pose[6 + c] : pose[11];
-        P[c] = (float)(fx * r0 + sk * r1 + cx * r2);
-        P[4 + c] = (float)(fy * r1 + cy * r2);
-        P[8 + c] = (float)r2;
-    }
-}
-
-// the inlier test, shared verbatim by scoring and the final solve (explicit fmaf so both kernels round identically)
-__device__ __forceinline__ bool zp_is_inlier(const float4& p0, const float4& p1, const float4& p2, float u, float v,
-                                             float X, float Y, float Z, float thr2) {
-    float x = fmaf(p0.x, X, fmaf(p0.y, Y, fmaf(p0.z, Z, p0.w)));
-    float y = fmaf(p1.x, X, fmaf(p1.y, Y, fmaf(p1.z, Z, p1.w)));
-    float z = fmaf(p2.x, X, fmaf(p2.y, Y, fmaf(p2.z, Z, p2.w)));
-    float dx = fmaf(-u, z, x);
-    float dy = fmaf(-v, z, y);
-    float e = fmaf(dy, dy, __fmul_rn(dx, dx));
-    float lim = __fmul_rn(__fmul_rn(z, z), thr2);
-    return e <= lim;                               // NaN poses compare false -> 0 inliers
-}
+constexpr int SC_GROUP = 128;                      // threads that together cover one tile of correspondences
+constexpr int SC_NG = 1;                           // warp-groups per CTA: they split the hypotheses of the item
+constexpr int SC_THREADS = SC_GROUP * SC_NG;
+constexpr int SC_PPT = 8;                          // correspondences per thread (registers)
+constexpr int SC_TILE = SC_GROUP * SC_PPT;         // correspondences per work item
+constexpr int SC_HB = 160;                         // hypotheses staged in shared memory at a time (multiple of 32)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -282,84 +349,153 @@ __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t
                      smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
+// float64 poses -> float32 projection matrices (only for zp_score with caller-supplied poses; the RANSAC chain gets P
+// straight from the minimal solver)
+__global__ void zp_poses_to_P_kernel(const double* __restrict__ poses, const double* __restrict__ K, int B, int H,
+                                     double inv_thr, float* __restrict__ hyp_P) {
+    int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= B * H) return;
+    float P[12];
+    zp_make_P(poses + (size_t)g * 12, K + 9 * (size_t)(g / H), inv_thr, P);
+    float4* o = (float4*)(hyp_P + (size_t)g * 24);
+    for (int e = 0; e < 6; e++) o[e] = make_float4(P[2 * e], P[2 * e], P[2 * e + 1], P[2 * e + 1]);
+}
+
 struct ScoreArgs {
-    const float* corr; int cap; const int32_t* counts; const double* K; const double* hyp_poses;
-    int B, H; float thr2; int32_t* hyp_inliers; int nsplit;
+    const float* corr; int cap; const int32_t* counts; const float* hyp_P;
+    int B, H; float inv_thr; int32_t* hyp_inliers; int* counters; int n_items;
 };
 
-// grid = (nsplit, B).  CTA (split s of crop b) walks tiles s, s+nsplit, ... of the crop's correspondences.
+// Persistent CTAs pulling work items (crop b, tile of SC_TILE correspondences) from a global ticket counter; items are
+// ordered tile-major (w -> b = w % B, tile = w / B) so the empty tiles of short lists sit at the end of the queue.
+// Per item: one elected thread issues TMA bulk copies of the 5 correspondence planes and of the crop's projection
+// matrices into shared memory (mbarrier completion); each thread keeps SC_PPT correspondences in registers and walks
+// the hypotheses (3 x LDS.128 broadcast each); the sign bits of d are funnel-shifted into one register (1 instruction
+// per evaluation), popc'ed, warp-reduced with REDUX and accumulated lane-distributed (lane h%32 owns hypothesis h).
 __global__ void __launch_bounds__(SC_THREADS) zp_score_kernel(ScoreArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    float* s_pts = (float*)smem_raw;                                   // [SC_STAGES][5][SC_TILE]
-    float4* s_P = (float4*)(s_pts + SC_STAGES * 5 * SC_TILE);          // [H][3]
-    int* s_cnt = (int*)(s_P + 3 * a.H);                                // [H]
-    __shared__ __align__(8) uint64_t s_bar[SC_STAGES];
-
-    const int b = blockIdx.y, split = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
-    const int n = min(a.counts[b], a.cap);
-    const int n_tiles = (n + SC_TILE - 1) / SC_TILE;
-    const int H = a.H;
-    const bool direct = a.nsplit == 1;
-    if (split >= n_tiles && !(direct || split == 0)) return;           // nothing to do (outputs pre-zeroed)
-
+    float* s_pts = (float*)smem_raw;                                   // [5][SC_TILE]
+    ulonglong2* s_P = (ulonglong2*)(s_pts + 5 * SC_TILE);              // [SC_HB][6]: (P,P) pairs, 96 B per hypothesis
+    int* s_cnt = (int*)(s_P + 6 * SC_HB);                              // [SC_HB]
+    __shared__ __align__(8) uint64_t s_bar;
+    __shared__ int s_item;
+    const int tid = threadIdx.x, lane = tid & 31, grp = tid / SC_GROUP, gt = tid % SC_GROUP;
     if (tid == 0) {
-        for (int s = 0; s < SC_STAGES; s++) mbar_init(&s_bar[s], 1);
+        mbar_init(&s_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    for (int h = tid; h < H; h += SC_THREADS) {
-        float P[12];
-        zp_make_P(a.hyp_poses + ((size_t)b * H + h) * 12, a.K + 9 * (size_t)b, P);
-        s_P[3 * h + 0] = make_float4(P[0], P[1], P[2], P[3]);
-        s_P[3 * h + 1] = make_float4(P[4], P[5], P[6], P[7]);
-        s_P[3 * h + 2] = make_float4(P[8], P[9], P[10], P[11]);
-        s_cnt[h] = 0;
-    }
-    __syncthreads();
-
-    const float* cb = a.corr + (size_t)b * 5 * a.cap;
-    auto issue = [&](int tile, int stage) {
-        int start = tile * SC_TILE;
-        int cnt = min(SC_TILE, n - start);
-        uint32_t bytes = (uint32_t)((cnt + 3) & ~3) * 4u;              // 16-byte granules; cap % 4 == 0 keeps it in bounds
-        mbar_expect_tx(&s_bar[stage], 5 * bytes);
-        for (int pl = 0; pl < 5; pl++)
-            tma_load_1d(s_pts + (stage * 5 + pl) * SC_TILE, cb + (size_t)pl * a.cap + start, bytes, &s_bar[stage]);
-    };
-    if (tid == 0 && split < n_tiles) issue(split, 0);
-
-    int it = 0;
-    for (int tile = split; tile < n_tiles; tile += a.nsplit, it++) {
-        const int stage = it & 1;
-        if (tid == 0 && tile + a.nsplit < n_tiles) issue(tile + a.nsplit, stage ^ 1);   // prefetch next tile
-        mbar_wait(&s_bar[stage], (it >> 1) & 1);
-        const float* tp = s_pts + stage * 5 * SC_TILE;
+    for (int h = tid; h < SC_HB; h += SC_THREADS) s_cnt[h] = 0;
+    uint32_t phase = 0;
+    const int H = a.H;
+    for (;;) {
+        __syncthreads();                                               // everybody is done with s_item / the buffers
+        if (tid == 0) s_item = atomicAdd(&a.counters[0], 1);
+        __syncthreads();
+        int w = s_item;
+        if (w >= 2 * a.n_items) break;
+        // pass 0 hands out the full tiles, pass 1 the partial (last) tile of every list: the small items come last,
+        // which bounds the finishing skew between SMs
+        const bool second = w >= a.n_items;
+        if (second) w -= a.n_items;
+        const int b = w % a.B, tile = w / a.B;
+        const int n = min(a.counts[b], a.cap);
         const int start = tile * SC_TILE;
-        float u[SC_PPT], v[SC_PPT], X[SC_PPT], Y[SC_PPT], Z[SC_PPT];
-        bool live[SC_PPT];
+        if (start >= n) continue;
+        const int cnt = min(SC_TILE, n - start);
+        if ((cnt == SC_TILE) == second) continue;
+        const float* cb = a.corr + (size_t)b * 5 * a.cap + start;
+        const uint32_t bytes = (uint32_t)((cnt + 3) & ~3) * 4u;        // 16-byte granules; cap % 4 == 0 keeps it in bounds
+        f32x2 nu[SC_PPT / 2], nv[SC_PPT / 2], X[SC_PPT / 2], Y[SC_PPT / 2], Z[SC_PPT / 2];   // point pairs (j, j+1)
+        for (int h0 = 0; h0 < H; h0 += SC_HB) {
+            const int hb = min(SC_HB, H - h0);
+            if (tid == 0) {
+                const uint32_t pbytes = (uint32_t)hb * 96u;
+                mbar_expect_tx(&s_bar, (h0 == 0 ? 5 * bytes : 0) + pbytes);
+                if (h0 == 0)
+                    for (int pl = 0; pl < 5; pl++) tma_load_1d(s_pts + pl * SC_TILE, cb + (size_t)pl * a.cap, bytes, &s_bar);
+                tma_load_1d(s_P, a.hyp_P + ((size_t)b * H + h0) * 24, pbytes, &s_bar);
+            }
+            mbar_wait(&s_bar, phase);
+            phase ^= 1;
+            if (h0 == 0) {
 #pragma unroll
-        for (int j = 0; j < SC_PPT; j++) {
-            int i = tid + j * SC_THREADS;
-            live[j] = start + i < n;
-            u[j] = tp[i]; v[j] = tp[SC_TILE + i]; X[j] = tp[2 * SC_TILE + i]; Y[j] = tp[3 * SC_TILE + i];
-            Z[j] = tp[4 * SC_TILE + i];
-            if (!live[j]) { u[j] = 0.f; v[j] = 0.f; X[j] = 0.f; Y[j] = 0.f; Z[j] = __int_as_float(0x7fc00000); }  // NaN -> never an inlier
-        }
+                for (int k = 0; k < SC_PPT / 2; k++) {
+                    float f[2][5];
+#pragma unroll
+                    for (int q = 0; q < 2; q++) {
+                        int i = gt + (2 * k + q) * SC_GROUP;
+                        bool live = i < cnt;
+                        // a dead slot gets u = 1e30: d >= +0 for every finite projection, never counted
+                        f[q][0] = live ? -(s_pts[i] * a.inv_thr) : -1e30f;
+                        f[q][1] = live ? -(s_pts[SC_TILE + i] * a.inv_thr) : 0.f;
+                        f[q][2] = live ? s_pts[2 * SC_TILE + i] : 0.f;
+                        f[q][3] = live ? s_pts[3 * SC_TILE + i] : 0.f;
+                        f[q][4] = live ? s_pts[4 * SC_TILE + i] : 0.f;
+                    }
+                    nu[k] = zp_pack2(f[0][0], f[1][0]); nv[k] = zp_pack2(f[0][1], f[1][1]);
+                    X[k] = zp_pack2(f[0][2], f[1][2]); Y[k] = zp_pack2(f[0][3], f[1][3]); Z[k] = zp_pack2(f[0][4], f[1][4]);
+                }
+            }
+            // group g takes hypotheses h = SC_NG * i + g; lane (i % 32) of every warp accumulates hypothesis i's count
+            const int ni = (hb - grp + SC_NG - 1) / SC_NG;
+            for (int iq = 0; iq < ni; iq += 32) {
+                int acc = 0;
+                const int iend = min(32, ni - iq);
 #pragma unroll 2
-        for (int h = 0; h < H; h++) {
-            const float4 p0 = s_P[3 * h], p1 = s_P[3 * h + 1], p2 = s_P[3 * h + 2];
-            int c = 0;
+                for (int il = 0; il < iend; il++) {
+                    const ulonglong2* pp = s_P + 6 * (SC_NG * (iq + il) + grp);
+                    const ulonglong2 q0 = pp[0], q1 = pp[1], q2 = pp[2], q3 = pp[3], q4 = pp[4], q5 = pp[5];
+                    // element-major order: every projection element is applied to all point pairs back to back, so
+                    // consecutive FFMA2s share a source operand (operand-reuse cache) -- an FFMA2 with three distinct
+                    // 64-bit register sources needs 3 even + 3 odd register reads and issues every 3 cycles instead of 2
+                    constexpr int NPAIR = SC_PPT / 2;
+                    f32x2 x[NPAIR], y[NPAIR], z[NPAIR];
 #pragma unroll
-            for (int j = 0; j < SC_PPT; j++) c += zp_is_inlier(p0, p1, p2, u[j], v[j], X[j], Y[j], Z[j], a.thr2) ? 1 : 0;
-            c = __reduce_add_sync(0xffffffffu, c);
-            if (lane == 0 && c) atomicAdd(&s_cnt[h], c);
+                    for (int k = 0; k < NPAIR; k++) z[k] = zp_fma2(q5.x, Z[k], q5.y);
+#pragma unroll
+                    for (int k = 0; k < NPAIR; k++) z[k] = zp_fma2(q4.y, Y[k], z[k]);
+#pragma unroll
+                    for (int k = 0; k < NPAIR; k++) z[k] = zp_fma2(q4.x, X[k], z[k]);
+#pragma unroll
+                    for (int k = 0; k < NPAIR; k++) x[k] = zp_fma2(q1.x, Z[k], q1.y);
+#pragma unroll
+                    for (int k = 0; k < NPAIR; k++) x[k] = zp_fma2(q0.y, Y[k], x[k]);
+#pragma unroll
+                    for (int k = 0; k < NPAIR; k++) x[k] = zp_fma2(q0.x, X[k], x[k]);
+#pragma unroll
+                    for (int k = 0; k < NPAIR; k++) y[k] = zp_fma2(q3.x, Z[k], q3.y);
+#pragma unroll
+                    for (int k = 0; k < NPAIR; k++) y[k] = zp_fma2(q2.y, Y[k], y[k]);
+#pragma unroll
+                    for (int k = 0; k < NPAIR; k++) y[k] = zp_fma2(q2.x, X[k], y[k]);
+                    uint32_t bits = 0;
+#pragma unroll
+                    for (int k = 0; k < NPAIR; k++) {
+                        f32x2 dx = zp_fma2(nu[k], z[k], x[k]), dy = zp_fma2(nv[k], z[k], y[k]);
+                        f32x2 e = zp_fma2(dx, dx, zp_mul2(dy, dy));
+                        f32x2 d = zp_fma2(z[k] ^ 0x8000000080000000ull, z[k], e);   // e - z*z; the sign flip runs on the ALU pipe
+                        bits = __funnelshift_l((uint32_t)d, bits, 1);
+                        bits = __funnelshift_l((uint32_t)(d >> 32), bits, 1);
+                    }
+                    int c = __reduce_add_sync(0xffffffffu, __popc(bits));
+                    if (lane == il) acc += c;
+                }
+                if (acc) atomicAdd(&s_cnt[SC_NG * (iq + lane) + grp], acc);
+            }
+            __syncthreads();
+            int32_t* out = a.hyp_inliers + (size_t)b * H + h0;
+            for (int h = tid; h < hb; h += SC_THREADS) {
+                int c = s_cnt[h];
+                if (c) { atomicAdd(&out[h], c); s_cnt[h] = 0; }
+            }
+            __syncthreads();
         }
-        __syncthreads();        // everyone is done with this stage before it is refilled two iterations later
     }
-    __syncthreads();
-    int32_t* out = a.hyp_inliers + (size_t)b * H;
-    for (int h = tid; h < H; h += SC_THREADS) {
-        if (direct) out[h] = s_cnt[h];
-        else if (s_cnt[h]) atomicAdd(&out[h], s_cnt[h]);
+    // the last CTA to leave re-arms the queue for the next launch
+    if (tid == 0) {
+        __threadfence();
+        int done = atomicAdd(&a.counters[1], 1);
+        if (done == (int)gridDim.x - 1) { a.counters[0] = 0; a.counters[1] = 0; __threadfence(); }
     }
 }
 
@@ -378,10 +514,6 @@ __device__ inline int zp_update_iters(double p, double ep, int m, int maxit) {  
 }
 
 constexpr int FIN_THREADS = 256;
-
-// phase timestamps of CTA 0 of the last zp_final_kernel launch (debug / profiling aid, read with zp_debug_clocks)
-__device__ long long zp_dbg_clk[16];
-#define ZP_STAMP(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) zp_dbg_clk[i] = clock64(); } while (0)
 
 template <int NV>
 __device__ __forceinline__ void block_reduce(double* v, double* s_red /* [FIN_THREADS/32][NV] */, double* s_out) {
@@ -404,7 +536,7 @@ __device__ __forceinline__ void block_reduce(double* v, double* s_red /* [FIN_TH
 
 struct FinalArgs {
     const float* corr; int cap; const int32_t* counts; const double* K; const double* hyp_poses;
-    const int32_t* hyp_inliers; int B, H, m; double conf; int select_mode; float thr2; int final_mode;
+    const int32_t* hyp_inliers; int B, H, m; double conf; int select_mode; float inv_thr; int final_mode;
     double* poses; int32_t* n_inliers; int32_t* status; int32_t* best_idx; uint8_t* inlier_mask;
 };
 
@@ -471,7 +603,7 @@ __global__ void __launch_bounds__(FIN_THREADS) zp_final_kernel(FinalArgs a) {
     const double* Kb = a.K + 9 * (size_t)b;
     const double* hp = a.hyp_poses + ((size_t)b * a.H + best) * 12;
     float P[12];
-    zp_make_P(hp, Kb, P);
+    zp_make_P(hp, Kb, (double)a.inv_thr, P);
     const float4 p0 = make_float4(P[0], P[1], P[2], P[3]), p1 = make_float4(P[4], P[5], P[6], P[7]),
                  p2 = make_float4(P[8], P[9], P[10], P[11]);
     ZP_STAMP(1);
@@ -481,7 +613,7 @@ __global__ void __launch_bounds__(FIN_THREADS) zp_final_kernel(FinalArgs a) {
     int my_n = 0, my_first = 0x7fffffff;
     for (int i0 = 0; i0 < n; i0 += FIN_THREADS) {     // warp-aligned so the bitset is built with ballots
         int i = i0 + tid;
-        bool in = i < n && zp_is_inlier(p0, p1, p2, pu[i], pv[i], pX[i], pY[i], pZ[i], a.thr2);
+        bool in = i < n && zp_is_inlier(p0, p1, p2, pu[i] * a.inv_thr, pv[i] * a.inv_thr, pX[i], pY[i], pZ[i]);
         unsigned bal = __ballot_sync(0xffffffffu, in);
         if (lane == 0 && i < a.cap) s_mask[i >> 5] = bal;
         if (a.inlier_mask && i < n) a.inlier_mask[(size_t)b * a.cap + i] = in;
@@ -548,25 +680,8 @@ __global__ void __launch_bounds__(FIN_THREADS) zp_final_kernel(FinalArgs a) {
     ZP_STAMP(5);
     // ---- 12x12 null space on warp 0 (16-lane cooperative Jacobi; both half-warps run the same problem)
     if (tid < 32) {
-        const int g = lane & 15;
-        double col[12], W[12];
-#pragma unroll
-        for (int r = 0; r < 12; r++) col[r] = g < 12 ? zp_mtm(s_sums, cam, r, g) : 0.0;
-        zp_jacobi12_coop(col, W, g);
+        zp_nullspace_group<16>(s_sums, cam, lane & 15, s_V);  // identical values from both halves: benign duplicate stores
         ZP_STAMP(6);
-        bool used[12];
-#pragma unroll
-        for (int r = 0; r < 12; r++) used[r] = false;
-        for (int q = 0; q < 4; q++) {
-            int bi = -1;
-            double bw = 0, bv = 0;
-#pragma unroll
-            for (int r = 11; r >= 0; r--)
-                if (!used[r] && (bi < 0 || W[r] < bw)) { bi = r; bw = W[r]; bv = col[r]; }
-#pragma unroll
-            for (int r = 0; r < 12; r++) used[r] = used[r] || r == bi;
-            if (lane < 12) s_V[q * 12 + g] = bw > ZP_DBL_MIN ? bv / bw : 0.0;
-        }
         __syncwarp();
         ZP_STAMP(7);
         // ---- the three beta candidates on three lanes
@@ -574,9 +689,11 @@ __global__ void __launch_bounds__(FIN_THREADS) zp_final_kernel(FinalArgs a) {
             ZpMat V{s_V, 1};
             double L[60], rho[6], af[4];
             zp_L_rho(V, s_cp, L, rho);
+            ZpHorn hs;
+            zp_horn_inputs(s_sums, hs);
             int f = s_first;
             zp_alphas(s_cp, pX[f], pY[f], pZ[f], af);
-            s_candok[lane] = zp_candidate(lane, L, rho, V, s_sums, af, c0, s_candR[lane], s_candt[lane]) ? 1 : 0;
+            s_candok[lane] = zp_candidate(lane, L, rho, V, hs, af, c0, s_candR[lane], s_candt[lane]) ? 1 : 0;
         }
     }
     __syncthreads();
@@ -694,38 +811,45 @@ int zp_launch_samples(zp_ctx* ctx, const int32_t* counts, int cap, int B, int H,
 }
 
 int zp_launch_minimal(zp_ctx* ctx, const float* corr, int cap, const int32_t* counts, const double* K,
-                      const int32_t* samples, int B, int H, int m, double* hyp_poses, cudaStream_t st) {
-    static bool attr_set = false;
-    const int smem = MIN_THREADS * 144 * sizeof(double);
-    if (!attr_set) {
-        ZP_CUDA(ctx, cudaFuncSetAttribute(zp_minimal_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr_set = true;
-    }
+                      const int32_t* samples, int B, int H, int m, float thr_px, double* hyp_poses, float* hyp_P,
+                      cudaStream_t st) {
+    const int per_cta = MIN_THREADS / 4;
     int total = B * H;
-    zp_minimal_kernel<<<(total + MIN_THREADS - 1) / MIN_THREADS, MIN_THREADS, smem, st>>>(corr, cap, counts, K, samples, B, H, m, hyp_poses);
+    zp_minimal_kernel<<<(total + per_cta - 1) / per_cta, MIN_THREADS, 0, st>>>(corr, cap, counts, K, samples, B, H, m,
+                                                                              1.0 / (double)thr_px, hyp_poses, hyp_P);
     ZP_CHECK_LAUNCH(ctx, "zp_minimal_kernel");
     return 0;
 }
 
-int zp_launch_score(zp_ctx* ctx, const float* corr, int cap, const int32_t* counts, const double* K,
-                    const double* hyp_poses, int B, int H, float thr_px, int32_t* hyp_inliers, cudaStream_t st) {
-    static int attr_smem = 0;
+int zp_launch_poses_to_P(zp_ctx* ctx, const double* poses, const double* K, int B, int H, float thr_px, float* hyp_P,
+                         cudaStream_t st) {
+    zp_poses_to_P_kernel<<<(B * H + 127) / 128, 128, 0, st>>>(poses, K, B, H, 1.0 / (double)thr_px, hyp_P);
+    ZP_CHECK_LAUNCH(ctx, "zp_poses_to_P_kernel");
+    return 0;
+}
+
+int zp_launch_score(zp_ctx* ctx, const float* corr, int cap, const int32_t* counts, const float* hyp_P, int B, int H,
+                    float thr_px, int32_t* hyp_inliers, cudaStream_t st) {
+    static bool attr_set = false;
     ScoreArgs a;
-    a.corr = corr; a.cap = cap; a.counts = counts; a.K = K; a.hyp_poses = hyp_poses; a.B = B; a.H = H;
-    a.thr2 = thr_px * thr_px; a.hyp_inliers = hyp_inliers;
+    a.corr = corr; a.cap = cap; a.counts = counts; a.hyp_P = hyp_P; a.B = B; a.H = H; a.inv_thr = 1.0f / thr_px;
+    a.hyp_inliers = hyp_inliers; a.counters = ctx->d_counters;
     const int max_tiles = (cap + SC_TILE - 1) / SC_TILE;
-    // enough CTAs to fill the chip a few times over; one CTA per crop once the batch alone does that
-    int nsplit = 1;
-    while (nsplit < max_tiles && (long)B * nsplit < 4L * ctx->sm_count) nsplit <<= 1;
-    if (nsplit > max_tiles) nsplit = max_tiles;
-    a.nsplit = nsplit;
-    const int smem = SC_STAGES * 5 * SC_TILE * sizeof(float) + H * (3 * sizeof(float4) + sizeof(int));
-    if (smem > attr_smem) {
+    a.n_items = B * max_tiles;
+    const int smem = 5 * SC_TILE * sizeof(float) + SC_HB * (6 * sizeof(ulonglong2) + sizeof(int));
+    if (!attr_set) {
         ZP_CUDA(ctx, cudaFuncSetAttribute(zp_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr_smem = smem;
+        attr_set = true;
     }
-    if (nsplit > 1) ZP_CUDA(ctx, cudaMemsetAsync(hyp_inliers, 0, (size_t)B * H * sizeof(int32_t), st));
-    zp_score_kernel<<<dim3(nsplit, B), SC_THREADS, smem, st>>>(a);
+    static int per_sm = 0;
+    if (!per_sm) {
+        ZP_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, zp_score_kernel, SC_THREADS, smem));
+        if (per_sm < 1) per_sm = 1;
+    }
+    int grid = ctx->sm_count * per_sm;
+    if (grid > 2 * a.n_items) grid = 2 * a.n_items;
+    ZP_CUDA(ctx, cudaMemsetAsync(hyp_inliers, 0, (size_t)B * H * sizeof(int32_t), st));
+    zp_score_kernel<<<grid, SC_THREADS, smem, st>>>(a);
     ZP_CHECK_LAUNCH(ctx, "zp_score_kernel");
     return 0;
 }
@@ -736,7 +860,7 @@ int zp_launch_final(zp_ctx* ctx, const float* corr, int cap, const int32_t* coun
                     uint8_t* inlier_mask, cudaStream_t st) {
     FinalArgs a;
     a.corr = corr; a.cap = cap; a.counts = counts; a.K = K; a.hyp_poses = hyp_poses; a.hyp_inliers = hyp_inliers;
-    a.B = B; a.H = H; a.m = m; a.conf = conf; a.select_mode = select_mode; a.thr2 = thr_px * thr_px;
+    a.B = B; a.H = H; a.m = m; a.conf = conf; a.select_mode = select_mode; a.inv_thr = 1.0f / thr_px;
     a.final_mode = final_mode; a.poses = poses; a.n_inliers = n_inliers; a.status = status; a.best_idx = best_idx;
     a.inlier_mask = inlier_mask;
     size_t smem = ((size_t)(cap + 31) / 32 + H) * sizeof(uint32_t);
@@ -745,11 +869,23 @@ int zp_launch_final(zp_ctx* ctx, const float* corr, int cap, const int32_t* coun
     return 0;
 }
 
+__global__ void zp_fma2_probe_kernel(float* out, int iters, float a, float b) {
+    f32x2 pa = zp_pack2(a, a), pb = zp_pack2(b, b);
+    f32x2 x0 = zp_pack2(threadIdx.x, 1.f), x1 = zp_pack2(2.f, threadIdx.x), x2 = zp_pack2(3.f, 4.f), x3 = zp_pack2(5.f, 6.f),
+          x4 = zp_pack2(7.f, 8.f), x5 = zp_pack2(9.f, 1.5f), x6 = zp_pack2(2.5f, 3.5f), x7 = zp_pack2(4.5f, 5.5f);
+    for (int i = 0; i < iters; i++) {
+        x0 = zp_fma2(x0, pa, pb); x1 = zp_fma2(x1, pa, pb); x2 = zp_fma2(x2, pa, pb); x3 = zp_fma2(x3, pa, pb);
+        x4 = zp_fma2(x4, pa, pb); x5 = zp_fma2(x5, pa, pb); x6 = zp_fma2(x6, pa, pb); x7 = zp_fma2(x7, pa, pb);
+    }
+    f32x2 s = x0 ^ x1 ^ x2 ^ x3 ^ x4 ^ x5 ^ x6 ^ x7;
+    out[blockIdx.x * blockDim.x + threadIdx.x] = __uint_as_float((uint32_t)s ^ (uint32_t)(s >> 32));
+}
+
 int zp_read_debug_clocks(long long* host16) {
     return cudaMemcpyFromSymbol(host16, zp_dbg_clk, sizeof(long long) * 16) == cudaSuccess ? 0 : -2;
 }
 
-int zp_launch_fma_probe(zp_ctx* ctx, int iters, double* out_tflops) {
+int zp_launch_fma_probe(zp_ctx* ctx, int iters, int packed, double* out_tflops) {
     const int blocks = ctx->sm_count * 8, threads = 256;
     float* d = nullptr;
     ZP_CUDA(ctx, cudaMalloc(&d, (size_t)blocks * threads * sizeof(float)));
@@ -758,13 +894,14 @@ int zp_launch_fma_probe(zp_ctx* ctx, int iters, double* out_tflops) {
     double best = 0;
     for (int rep = 0; rep < 5; rep++) {
         cudaEventRecord(e0);
-        zp_fma_probe_kernel<<<blocks, threads>>>(d, iters, 0.999f, 0.001f);
+        if (packed) zp_fma2_probe_kernel<<<blocks, threads>>>(d, iters, 0.999f, 0.001f);
+        else zp_fma_probe_kernel<<<blocks, threads>>>(d, iters, 0.999f, 0.001f);
         cudaEventRecord(e1);
         cudaEventSynchronize(e1);
         ctx->launches++;
         float ms = 0;
         cudaEventElapsedTime(&ms, e0, e1);
-        double tf = 2.0 * 8.0 * (double)iters * blocks * threads / (ms * 1e-3) / 1e12;
+        double tf = (packed ? 2.0 : 1.0) * 2.0 * 8.0 * (double)iters * blocks * threads / (ms * 1e-3) / 1e12;
         if (rep > 0 && tf > best) best = tf;
     }
     cudaEventDestroy(e0); cudaEventDestroy(e1);

@@ -244,9 +244,11 @@ class Engine:
     def launch_count(self):
         return int(self.lib.zp_launch_count(self.ctx.handle))
 
-    def fp32_peak_tflops(self, iters=20000):
+    def fp32_peak_tflops(self, iters=20000, packed=False):
+        """measured FP32 FMA throughput of this GPU: scalar FFMA chains, or packed FFMA2 chains (packed=True)"""
         v = C.c_double()
-        self.ctx.check(self.lib.zp_fp32_peak_probe(self.ctx.handle, int(iters), C.byref(v)), "zp_fp32_peak_probe")
+        fn = self.lib.zp_fp32x2_peak_probe if packed else self.lib.zp_fp32_peak_probe
+        self.ctx.check(fn(self.ctx.handle, int(iters), C.byref(v)), "zp_fp32_peak_probe")
         return v.value
 
 
