@@ -128,6 +128,14 @@ int zp_pose_batch_host(zp_ctx* ctx, const void* h_logits, int dtype, int B, int 
                        int select_mode, int final_mode,
                        double* h_poses, int32_t* h_n_inliers, int32_t* h_status);
 
+/* Test / profiling aid: pin zp_decode to one kernel family.  0 = automatic (fused register-staged kernel with
+ * independent CTAs; crops of more than 16 runs of 2048 (fp32) / 4096 (bf16) pixels take the two-kernel path, layouts
+ * neither can take the generic kernel), 1 = fused kernel with the compaction bases exchanged through a thread-block
+ * cluster (DSMEM), 2 = generic strided kernel, 3 = fused TMA-ring streaming kernel, 4 = two kernels (plane stream ->
+ * codes + mask bits, then rank/gather/emit).  All produce identical output; DESIGN.md section 4 has the measured
+ * comparison. */
+int zp_set_decode_path(zp_ctx* ctx, int path);
+
 /* Number of kernels this ctx has launched since creation (bench.py's gpu_launches claim). */
 int64_t zp_launch_count(zp_ctx* ctx);
 

@@ -37,9 +37,9 @@ int main() {
             if (i == 0) for (int e = 0; e < 4; e++) af[e] = a[e];
             zp_accumulate(s, a, cam.uc - x[i], cam.vc - y[i], X[i] - c0[0], Y[i] - c0[1], Z[i] - c0[2]);
         }
-        double at[144];
+        double zbuf[ZP_SYM_DOUBLES], dd[12], ee[12], at[48];
+        zp_nullspace_ql<1>(ZpSym12{zbuf}, dd, ee, s, cam, 0, 0u, 0u, at);
         ZpMat At{at, 1};
-        zp_nullspace_serial(At, s, cam);
         double L[60], rho[6];
         zp_L_rho(At, cp, L, rho);
         ZpHorn hs;

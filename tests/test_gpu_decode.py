@@ -187,3 +187,42 @@ def test_full_size_properties(eng, tables):
     for i in range(B):
         n = int(counts[i])
         assert torch.equal(corr[i, :, :n], corr2[i, :, :n])
+
+
+@pytest.mark.parametrize("B,S,dtype,ext,k", [(1, 128, "f32", False, 0), (3, 128, "bf16", False, 4), (70, 128, "f32", False, 0),
+                                             (5, 64, "f32", True, 0), (2, 100, "f32", False, 2), (40, 128, "bf16", True, 0),
+                                             (2, 20, "f32", False, 0), (300, 32, "f32", False, 0)])
+def test_decode_paths_identical(eng, tables, B, S, dtype, ext, k):
+    """the five decode paths (two-kernel stream + emit, fused register-staged with a DSMEM cluster exchange, generic
+    strided, fused TMA-ring streaming, fused register-staged with independent CTAs) write identical lists, counts and
+    codes; crop 0 is also checked against the oracle"""
+    tab, nrm = tables["nan20"]
+    eng.upload_dict(6, tab, n_bits=16, ignore_bit=k)
+    crops = [synth.make_crop(tab, nrm, 5000 + (i % 7), S=S) for i in range(B)]
+    logits = np.stack([synth.crop_to_logits(c) for c in crops])
+    rng = np.random.default_rng(B * 1000 + S)
+    logits[:, 0] *= np.where(rng.random((B, 1, 1)) < 0.15, -1.0, 1.0)          # some inverted (large / small) masks
+    if B > 2:
+        logits[1, 0] = -1.0                                                   # an empty crop in the middle
+    bboxes = np.stack([c["bbox"] for c in crops])
+    lg = torch.from_numpy(logits).cuda()
+    if dtype == "bf16":
+        lg = lg.to(torch.bfloat16)
+    em = (rng.random((B, S, S)) < 0.4).astype(np.uint8) if ext else None
+    outs = []
+    try:
+        for path in (0, 1, 2, 3, 4):
+            eng.set_decode_path(path)
+            corr, counts, codes = eng.decode(lg, bboxes, obj_default=6, ignore_bit=k, ext_mask=em, return_codes=True)
+            outs.append((corr.cpu().numpy(), counts.cpu().numpy(), codes.cpu().numpy()))
+    finally:
+        eng.set_decode_path(0)
+    c0, n0, k0 = outs[0]
+    for c1, n1, k1 in outs[1:]:
+        assert np.array_equal(n0, n1) and np.array_equal(k0, k1)
+        for i in range(B):
+            assert np.array_equal(c0[i, :, :n0[i]].view(np.uint32), c1[i, :, :n1[i]].view(np.uint32))
+    lg0 = lg[0].float().cpu().numpy()
+    uv, xyz, ids = _oracle_decode(lg0, bboxes[0], S, tab, k=k, ext_mask=None if em is None else em[0])
+    assert n0[0] == len(uv) and np.array_equal(k0[0].astype(np.int64), ids)
+    assert np.array_equal(c0[0, 0:2, :n0[0]].T, uv) and np.array_equal(c0[0, 2:5, :n0[0]].T.view(np.uint32), xyz.view(np.uint32))

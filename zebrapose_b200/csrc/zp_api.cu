@@ -95,6 +95,7 @@ void zp_destroy(zp_ctx* ctx) {
     if (ctx->d_counters) cudaFree(ctx->d_counters);
     if (ctx->ws) cudaFree(ctx->ws);
     if (ctx->hws) cudaFree(ctx->hws);
+    if (ctx->dws) cudaFree(ctx->dws);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }
@@ -102,6 +103,13 @@ void zp_destroy(zp_ctx* ctx) {
 const char* zp_last_error(zp_ctx* ctx) { return ctx ? ctx->err.c_str() : g_err.c_str(); }
 
 int64_t zp_launch_count(zp_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int zp_set_decode_path(zp_ctx* ctx, int path) {
+    if (!ctx) return -1;
+    if (path < 0 || path > 4) ZP_FAIL(ctx, -1, "zp_set_decode_path: path must be 0..4");
+    ctx->force_decode_path = path;
+    return 0;
+}
 
 int zp_upload_tables(zp_ctx* ctx, int obj_id, const double* pts, int n_bits, int ignore_bit, int mode) {
     if (!ctx) return -1;

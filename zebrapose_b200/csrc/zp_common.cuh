@@ -32,8 +32,12 @@ struct zp_ctx {
     // second workspace for the host-buffer entry (device copies of inputs/outputs)
     void* hws = nullptr;
     size_t hws_bytes = 0;
+    // decode workspace of the two-kernel path (codes when the caller does not want them, mask ballot words)
+    void* dws = nullptr;
+    size_t dws_bytes = 0;
     cudaStream_t own_stream = nullptr;
     int64_t launches = 0;
+    int force_decode_path = 0;               // 0 auto, 1 register-staged cluster kernel, 2 generic kernel (tests)
 };
 
 #define ZP_FAIL(ctx, code, ...)                                  \

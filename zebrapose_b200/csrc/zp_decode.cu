@@ -22,6 +22,7 @@ namespace cg = cooperative_groups;
 constexpr int DEC_THREADS = 512;
 constexpr int DEC_WARPS = DEC_THREADS / 32;
 constexpr int DEC_MAX_CLUSTER = 8;
+constexpr int DEC_MAX_RUNS = 16;               // runs (CTAs) per crop of the cluster-free kernel: run r re-counts r mask runs
 
 struct DecodeArgs {
     const void* logits;
@@ -69,22 +70,89 @@ __device__ __forceinline__ float remap_coord(double extent, double origin, int S
     return (float)__double2ll_rz(v);
 }
 
+// Emission through shared memory: every thread drops its <= PPT correspondences at their CTA-local ranks into a
+// [5][DEC_THREADS * PPT] staging buffer, then the CTA copies the compacted run out with consecutive lanes on consecutive
+// addresses.  Writing straight from the owning threads costs one partially filled 32-byte sector per lane and store
+// (lanes are ~3 floats apart, and a sector is touched again by each of the PPT unrolled stores): ncu counted 32.7 M
+// sector writes for 12.6 M correspondences, which -- not DRAM -- was what bounded the first kernels (bf16 input, half
+// the bytes, took exactly as long as fp32).
+template <int PPT>
+__device__ __forceinline__ void emit_staged(float* s_out, uint32_t mbits, const uint32_t* code2, int local_pos,
+                                            const float4* __restrict__ tab, const float* s_x, int col, float yv,
+                                            int total, int cta_base, float* __restrict__ cb, int cap) {
+    constexpr int RUN = DEC_THREADS * PPT;
+    if (mbits) {
+        int pos = local_pos;
+#pragma unroll
+        for (int j = 0; j < PPT; j++) {
+            if ((mbits >> j) & 1u) {
+                float4 P = __ldg(tab + ((code2[j >> 1] >> (16 * (j & 1))) & 0xFFFFu));
+                s_out[pos] = s_x[col + j];
+                s_out[RUN + pos] = yv;
+                s_out[2 * RUN + pos] = P.x;
+                s_out[3 * RUN + pos] = P.y;
+                s_out[4 * RUN + pos] = P.z;
+                pos++;
+            }
+        }
+    }
+    __syncthreads();
+    const int n = min(total, max(cap - cta_base, 0));
+#pragma unroll
+    for (int pl = 0; pl < 5; pl++) {
+        float* dst = cb + (size_t)pl * cap + cta_base;
+        const float* src = s_out + pl * RUN;
+        for (int i = threadIdx.x; i < n; i += DEC_THREADS) dst[i] = src[i];
+    }
+}
+
 // -------------------------------------------------------------------------------------------------------------
-// Fast path: cluster per crop, vector loads.  grid.x = B * cluster_size.
+// Fast path: vector loads, one CTA per run of 512*PPT pixels.  grid.x = B * ctas_per_crop.
+// The compaction base of a CTA (masked pixels in the earlier runs of its crop) comes either from the other CTAs of a
+// thread-block cluster through DSMEM (CLUSTER = true), or from re-counting the earlier part of the mask plane itself
+// (CLUSTER = false: <= 7 extra 128-bit loads per thread, served by L2 because the owners of those runs stream the same
+// lines; no cross-CTA dependency at all, so CTAs are scheduled and retire independently).
+// Sign tests are one FSET (fp32) / HSET2 (bf16) per value producing an all-ones mask, and one LOP3 ors the plane's
+// bit into codes kept two pixels per register: 2 issue slots per (pixel, plane) for fp32, 1 for bf16 -- the decode is
+// as much issue-bound as HBM-bound (the first version spent ~7 slots per (pixel, plane)).
 // -------------------------------------------------------------------------------------------------------------
-template <int DT>
-__global__ void __launch_bounds__(DEC_THREADS, 2) zp_decode_cluster_kernel(DecodeArgs a) {
+__device__ __forceinline__ uint32_t gt0_mask_f32(uint32_t bits) {            // 0xFFFFFFFF if float(bits) > 0 (NaN, +-0 -> 0)
+    uint32_t m;
+    asm("set.gt.u32.f32 %0, %1, 0f00000000;" : "=r"(m) : "f"(__uint_as_float(bits)));
+    return m;
+}
+__device__ __forceinline__ uint32_t gt0_mask_bf16x2(uint32_t two) {          // 0xFFFF per half that is > 0
+    __nv_bfloat162 v;
+    memcpy(&v, &two, 4);
+    return __hgt2_mask(v, __nv_bfloat162(__float2bfloat16(0.f), __float2bfloat16(0.f)));
+}
+// ors bit `k` (a constant with the same 16-bit pattern in both halves) into the packed codes of the pixels of one
+// 16-byte vector whose value is > 0.  code2[q] holds pixels 2q (low half) and 2q+1 (high half).
+template <int DT> __device__ __forceinline__ void or_plane_bits(const uint4& v, uint32_t k, uint32_t* code2) {
+    if (DT == ZP_DTYPE_F32) {
+        code2[0] |= (gt0_mask_f32(v.x) & (k & 0xFFFFu)) | (gt0_mask_f32(v.y) & (k & 0xFFFF0000u));
+        code2[1] |= (gt0_mask_f32(v.z) & (k & 0xFFFFu)) | (gt0_mask_f32(v.w) & (k & 0xFFFF0000u));
+    } else {
+        code2[0] |= gt0_mask_bf16x2(v.x) & k; code2[1] |= gt0_mask_bf16x2(v.y) & k;
+        code2[2] |= gt0_mask_bf16x2(v.z) & k; code2[3] |= gt0_mask_bf16x2(v.w) & k;
+    }
+}
+
+// FULL16: nb == 16 and the mask comes from the tensor (every shipped config at ignore_bit 0) -- compile-time plane count,
+// no per-plane guards.
+template <int DT, bool CLUSTER, bool FULL16>
+__global__ void __launch_bounds__(DEC_THREADS, 2) zp_decode_cluster_kernel(DecodeArgs a, int ctas_per_crop) {
     constexpr int PPT = Px<DT>::N;
     constexpr int ESZ = Px<DT>::ESZ;
-    cg::cluster_group cluster = cg::this_cluster();
-    const unsigned csize = cluster.num_blocks();
-    const unsigned rank = cluster.block_rank();
+    const unsigned csize = (unsigned)ctas_per_crop;
     const int b = blockIdx.x / csize;
+    const unsigned rank = blockIdx.x - b * csize;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int S = a.S, N = S * S;
 
     __shared__ float s_x[1024], s_y[1024];     // remapped coordinates per column / row (S <= 1024 on this path)
     __shared__ int s_warp[DEC_WARPS];
+    __shared__ int s_pre[DEC_WARPS];
     __shared__ int s_total;                    // read by the other CTAs of the cluster (DSMEM)
 
     {   // per-crop coordinate LUTs
@@ -99,20 +167,23 @@ __global__ void __launch_bounds__(DEC_THREADS, 2) zp_decode_cluster_kernel(Decod
     const int p0 = ((int)rank * DEC_THREADS + tid) * PPT;       // first pixel of this thread
     const bool active = p0 < N;
     const int row = active ? p0 / S : 0, col = active ? p0 - row * S : 0;
-    const char* base = (const char*)a.logits + ((size_t)b * a.sb + (size_t)row * a.sh + col) * ESZ;
+    const char* crop = (const char*)a.logits + (size_t)b * a.sb * ESZ;
+    const char* base = crop + ((size_t)row * a.sh + col) * ESZ;
     const size_t plane = (size_t)a.sc * ESZ;
 
     // ---- issue the mask load and the first half of the bit planes together (memory-level parallelism)
     uint32_t mbits = 0;
     uint4 v[8];
-    const int nb = a.nb;
+    const int nb = FULL16 ? 16 : a.nb;
+    const bool own_mask = FULL16 || a.ext_mask == nullptr;
+    int pre = 0;
     if (active) {
         uint4 mv = make_uint4(0, 0, 0, 0);
-        if (a.ext_mask == nullptr) mv = zp_ldg_stream(base + (size_t)a.mask_ch * plane);
+        if (own_mask) mv = zp_ldg_stream(base + (size_t)a.mask_ch * plane);
 #pragma unroll
         for (int i = 0; i < 8; i++)
-            if (i < nb) v[i] = zp_ldg_stream(base + (size_t)(a.bit0_ch + i) * plane);
-        if (a.ext_mask == nullptr) {
+            if (FULL16 || i < nb) v[i] = zp_ldg_stream(base + (size_t)(a.bit0_ch + i) * plane);
+        if (own_mask) {
             mbits = positive_bits<DT>(mv);
         } else {
             const uint8_t* em = a.ext_mask + (size_t)b * N + p0;
@@ -120,7 +191,23 @@ __global__ void __launch_bounds__(DEC_THREADS, 2) zp_decode_cluster_kernel(Decod
             for (int j = 0; j < PPT; j++) mbits |= (uint32_t)(em[j] != 0) << j;
         }
     }
-    // ---- ranks of the masked pixels: thread -> warp -> CTA -> cluster
+    if (!CLUSTER) {
+        // masked pixels of runs 0..rank-1: thread t re-counts the pixels thread t of each earlier run owns (plain loads:
+        // the lines stay in L1/L2 for the owners)
+        for (unsigned r = 0; r < rank; r++) {
+            const int q0 = ((int)r * DEC_THREADS + tid) * PPT;
+            const int qrow = q0 / S, qcol = q0 - qrow * S;
+            if (own_mask) {
+                uint4 mv = __ldg((const uint4*)(crop + ((size_t)a.mask_ch * a.sc + (size_t)qrow * a.sh + qcol) * ESZ));
+                pre += __popc(positive_bits<DT>(mv));
+            } else {
+                const uint8_t* em = a.ext_mask + (size_t)b * N + q0;
+#pragma unroll
+                for (int j = 0; j < PPT; j++) pre += em[j] != 0;
+            }
+        }
+    }
+    // ---- ranks of the masked pixels: thread -> warp -> CTA -> crop
     const int cnt = __popc(mbits);
     int incl = cnt;
 #pragma unroll
@@ -128,7 +215,9 @@ __global__ void __launch_bounds__(DEC_THREADS, 2) zp_decode_cluster_kernel(Decod
         int t = __shfl_up_sync(0xffffffffu, incl, d);
         if (lane >= d) incl += t;
     }
+    if (!CLUSTER) pre = __reduce_add_sync(0xffffffffu, pre);
     if (lane == 31) s_warp[warp] = incl;
+    if (!CLUSTER && lane == 0) s_pre[warp] = pre;
     __syncthreads();
     if (warp == 0) {
         int w = lane < DEC_WARPS ? s_warp[lane] : 0;
@@ -139,78 +228,500 @@ __global__ void __launch_bounds__(DEC_THREADS, 2) zp_decode_cluster_kernel(Decod
             if (lane >= d) wi += t;
         }
         if (lane < DEC_WARPS) s_warp[lane] = wi - w;      // exclusive warp offsets
+        int pr = (!CLUSTER && lane < DEC_WARPS) ? s_pre[lane] : 0;
+        pr = __reduce_add_sync(0xffffffffu, pr);
         if (lane == DEC_WARPS - 1) s_total = wi;
+        if (lane == 0) s_pre[0] = pr;
     }
     __syncthreads();
-    if (csize > 1) cluster.barrier_arrive();              // release s_total; the wait is after the code planes
+    cg::cluster_group cluster = cg::this_cluster();
+    if (CLUSTER && csize > 1) cluster.barrier_arrive();   // release s_total; the wait is after the code planes
 
-    // ---- pack the code while the exchange is in flight
-    uint32_t code[PPT];
+    // ---- pack the code (two pixels per register, MSB-first at bit 15 - plane) while the exchange is in flight
+    uint32_t code2[PPT / 2];
 #pragma unroll
-    for (int j = 0; j < PPT; j++) code[j] = 0;
+    for (int j = 0; j < PPT / 2; j++) code2[j] = 0;
     if (active) {
 #pragma unroll
         for (int i = 0; i < 8; i++)
-            if (i < nb) {
-                uint32_t pb = positive_bits<DT>(v[i]);
-#pragma unroll
-                for (int j = 0; j < PPT; j++) code[j] |= ((pb >> j) & 1u) << (nb - 1 - i);
-            }
-        if (nb > 8) {
+            if (FULL16 || i < nb) or_plane_bits<DT>(v[i], 0x80008000u >> i, code2);
+        if (FULL16 || nb > 8) {
 #pragma unroll
             for (int i = 0; i < 8; i++)
-                if (8 + i < nb) v[i] = zp_ldg_stream(base + (size_t)(a.bit0_ch + 8 + i) * plane);
+                if (FULL16 || 8 + i < nb) v[i] = zp_ldg_stream(base + (size_t)(a.bit0_ch + 8 + i) * plane);
 #pragma unroll
             for (int i = 0; i < 8; i++)
-                if (8 + i < nb) {
-                    uint32_t pb = positive_bits<DT>(v[i]);
-#pragma unroll
-                    for (int j = 0; j < PPT; j++) code[j] |= ((pb >> j) & 1u) << (nb - 9 - i);
-                }
+                if (FULL16 || 8 + i < nb) or_plane_bits<DT>(v[i], 0x00800080u >> i, code2);
         }
+        const int sh = 16 - nb;                                 // planes were placed as if nb == 16
+#pragma unroll
+        for (int j = 0; j < PPT / 2; j++) code2[j] = (code2[j] >> sh) & (0xFFFFu >> sh) * 0x00010001u;
         if (a.codes) {
             uint16_t* cp = a.codes + (size_t)b * N + p0;
-            if (PPT == 4) {
-                *(uint2*)cp = make_uint2(code[0] | (code[1] << 16), code[2] | (code[3] << 16));
-            } else {
-                *(uint4*)cp = make_uint4(code[0] | (code[1] << 16), code[2] | (code[3] << 16),
-                                         code[4 % PPT] | (code[5 % PPT] << 16), code[6 % PPT] | (code[7 % PPT] << 16));
-            }
+            if (PPT == 4) *(uint2*)cp = make_uint2(code2[0], code2[1]);
+            else *(uint4*)cp = make_uint4(code2[0], code2[1], code2[2 % (PPT / 2)], code2[3 % (PPT / 2)]);
         }
     }
 
-    // ---- cluster-wide exclusive prefix of the CTA totals
+    // ---- crop-wide exclusive prefix of the CTA totals
     int cta_base = 0;
-    if (csize > 1) {
-        cluster.barrier_wait();
-        for (unsigned r = 0; r < rank; r++) cta_base += *cluster.map_shared_rank(&s_total, r);
-        cluster.barrier_arrive();                         // peers may retire once everybody has read
+    if (CLUSTER) {
+        if (csize > 1) {
+            cluster.barrier_wait();
+            for (unsigned r = 0; r < rank; r++) cta_base += *cluster.map_shared_rank(&s_total, r);
+            cluster.barrier_arrive();                         // peers may retire once everybody has read
+        }
+    } else {
+        cta_base = s_pre[0];
     }
     if (rank == csize - 1 && tid == 0) a.counts[b] = cta_base + s_total;
 
-    // ---- gather the 3D points and emit this thread's correspondences in row-major order
-    if (cnt) {
+    // ---- gather the 3D points and emit the run in row-major order (staged through shared memory)
+    {
+        extern __shared__ __align__(16) float s_out[];
         const int obj = a.obj_ids ? a.obj_ids[b] : a.obj_default;
-        const float4* tab = a.tables[obj];
-        int pos = cta_base + s_warp[warp] + incl - cnt;
-        float* cb = a.corr + (size_t)b * 5 * a.cap;
-        const float yv = s_y[row];
+        emit_staged<PPT>(s_out, mbits, code2, s_warp[warp] + incl - cnt, a.tables[obj], s_x, col, s_y[row], s_total, cta_base,
+                         a.corr + (size_t)b * 5 * a.cap, a.cap);
+    }
+    if (CLUSTER && csize > 1) cluster.barrier_wait();
+}
+
+// -------------------------------------------------------------------------------------------------------------
+// Two-kernel path (default).  The fused kernels above and below are bound by the LIFETIME of a CTA, not by bytes: load
+// -> block scan -> load -> table gather -> scattered stores are five dependent memory round trips during most of which
+// the CTA has no plane loads in flight (bf16 input, half the bytes, takes the same time as fp32).  Splitting the work
+// removes every dependency from the part that moves 97 % of the bytes:
+//   zp_decode_planes_kernel  pure stream: a thread issues the 128-bit loads of ALL planes of its PPT pixels at once,
+//                            packs the codes (FSET/HSET2 + LOP3) and writes 2 B/pixel of codes + 1 bit/pixel of mask
+//                            (warp ballots).  No shared memory, no barrier, one memory round trip per thread.
+//   zp_decode_emit_kernel    per run of 512*PPT pixels: ranks from the mask bits (the base of a run = popcount of the
+//                            earlier runs' ballot words, <= 2 KB), table gather, emit.  Touches 2.1 + 15 B/pixel.
+// -------------------------------------------------------------------------------------------------------------
+constexpr int PL_THREADS = 128;
+
+template <int DT>
+__global__ void __launch_bounds__(PL_THREADS, 5) zp_decode_planes_kernel(DecodeArgs a, uint16_t* __restrict__ codes,
+                                                                          uint32_t* __restrict__ maskw, int segs_per_crop) {
+    constexpr int PPT = Px<DT>::N;
+    constexpr int ESZ = Px<DT>::ESZ;
+    const int S = a.S, N = S * S, nb = a.nb;
+    const int lane = threadIdx.x & 31;
+    const int seg = blockIdx.x * (PL_THREADS / 32) + (threadIdx.x >> 5);        // 32*PPT consecutive pixels of one crop
+    const int b = seg / segs_per_crop, sg = seg - b * segs_per_crop;
+    if (b >= a.B) return;
+    const int p0 = (sg * 32 + lane) * PPT;
+    const bool active = p0 < N;
+    uint32_t mbits = 0;
+    if (active) {
+        const int row = p0 / S, col = p0 - row * S;
+        const char* base = (const char*)a.logits + ((size_t)b * a.sb + (size_t)row * a.sh + col) * ESZ;
+        const size_t plane = (size_t)a.sc * ESZ;
+        uint4 mv = make_uint4(0, 0, 0, 0), v[16];
+        if (a.ext_mask == nullptr) mv = zp_ldg_stream(base + (size_t)a.mask_ch * plane);
 #pragma unroll
-        for (int j = 0; j < PPT; j++) {
-            if ((mbits >> j) & 1u) {
-                if (pos < a.cap) {
-                    float4 P = __ldg(tab + code[j]);
-                    cb[pos] = s_x[col + j];
-                    cb[a.cap + pos] = yv;
-                    cb[2 * (size_t)a.cap + pos] = P.x;
-                    cb[3 * (size_t)a.cap + pos] = P.y;
-                    cb[4 * (size_t)a.cap + pos] = P.z;
-                }
-                pos++;
-            }
+        for (int i = 0; i < 16; i++)
+            if (i < nb) v[i] = zp_ldg_stream(base + (size_t)(a.bit0_ch + i) * plane);
+        if (a.ext_mask == nullptr) {
+            mbits = positive_bits<DT>(mv);
+        } else {
+            const uint8_t* em = a.ext_mask + (size_t)b * N + p0;
+#pragma unroll
+            for (int j = 0; j < PPT; j++) mbits |= (uint32_t)(em[j] != 0) << j;
+        }
+        uint32_t code2[PPT / 2];
+#pragma unroll
+        for (int j = 0; j < PPT / 2; j++) code2[j] = 0;
+#pragma unroll
+        for (int i = 0; i < 16; i++)
+            if (i < nb) or_plane_bits<DT>(v[i], 0x80008000u >> i, code2);
+        const int sh = 16 - nb;                                     // planes were placed as if nb == 16
+#pragma unroll
+        for (int j = 0; j < PPT / 2; j++) code2[j] = (code2[j] >> sh) & (0xFFFFu >> sh) * 0x00010001u;
+        uint16_t* cp = codes + (size_t)b * N + p0;
+        if (PPT == 4) *(uint2*)cp = make_uint2(code2[0], code2[1]);
+        else *(uint4*)cp = make_uint4(code2[0], code2[1], code2[2 % (PPT / 2)], code2[3 % (PPT / 2)]);
+    }
+    // mask bits of the segment: word j, bit i = pixel PPT*i + j masked
+    uint32_t mine = 0;
+#pragma unroll
+    for (int j = 0; j < PPT; j++) {
+        uint32_t bal = __ballot_sync(0xffffffffu, (mbits >> j) & 1u);
+        if (lane == j) mine = bal;
+    }
+    if (lane < PPT) maskw[((size_t)b * segs_per_crop + sg) * PPT + lane] = mine;
+}
+
+template <int PPT>
+__global__ void __launch_bounds__(DEC_THREADS, 3) zp_decode_emit_kernel(DecodeArgs a, const uint16_t* __restrict__ codes,
+                                                                        const uint32_t* __restrict__ maskw,
+                                                                        int segs_per_crop, int runs_per_crop) {
+    const int b = blockIdx.x / runs_per_crop, run = blockIdx.x - b * runs_per_crop;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int S = a.S, N = S * S;
+    __shared__ float s_x[1024], s_y[1024];
+    __shared__ int s_warp[DEC_WARPS];
+    __shared__ int s_pre[DEC_WARPS];
+    __shared__ int s_total;
+    {
+        const double* bb = a.bbox + 4 * (size_t)b;
+        double x0 = bb[0], y0 = bb[1], w = bb[2], h = bb[3];
+        for (int i = tid; i < S; i += DEC_THREADS) {
+            s_x[i] = remap_coord(w, x0, S, i);
+            s_y[i] = remap_coord(h, y0, S, i);
         }
     }
-    if (csize > 1) cluster.barrier_wait();
+    const uint32_t* mw = maskw + (size_t)b * segs_per_crop * PPT;
+    const int sg = run * DEC_WARPS + warp;                           // this warp's segment
+    const int p0 = (sg * 32 + lane) * PPT;
+    const bool active = p0 < N;
+    uint32_t mbits = 0;
+    uint32_t c2[PPT / 2];
+#pragma unroll
+    for (int j = 0; j < PPT / 2; j++) c2[j] = 0;
+    if (sg < segs_per_crop) {
+#pragma unroll
+        for (int j = 0; j < PPT; j++) mbits |= ((__ldg(mw + (size_t)sg * PPT + j) >> lane) & 1u) << j;
+    }
+    if (active && mbits) {
+        const uint16_t* cp = codes + (size_t)b * N + p0;
+        if (PPT == 4) { uint2 t = __ldg((const uint2*)cp); c2[0] = t.x; c2[1] = t.y; }
+        else { uint4 t = __ldg((const uint4*)cp); c2[0] = t.x; c2[1] = t.y; c2[2 % (PPT / 2)] = t.z; c2[3 % (PPT / 2)] = t.w; }
+    }
+    // masked pixels of the earlier runs: popcount of their ballot words
+    int pre = 0;
+    for (int i = tid; i < run * DEC_WARPS * PPT; i += DEC_THREADS) pre += __popc(__ldg(mw + i));
+    const int cnt = __popc(mbits);
+    int incl = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += t;
+    }
+    pre = __reduce_add_sync(0xffffffffu, pre);
+    if (lane == 31) s_warp[warp] = incl;
+    if (lane == 0) s_pre[warp] = pre;
+    __syncthreads();
+    if (warp == 0) {
+        int w = lane < DEC_WARPS ? s_warp[lane] : 0;
+        int wi = w;
+#pragma unroll
+        for (int d = 1; d < DEC_WARPS; d <<= 1) {
+            int t = __shfl_up_sync(0xffffffffu, wi, d);
+            if (lane >= d) wi += t;
+        }
+        if (lane < DEC_WARPS) s_warp[lane] = wi - w;
+        int pr = lane < DEC_WARPS ? s_pre[lane] : 0;
+        pr = __reduce_add_sync(0xffffffffu, pr);
+        if (lane == DEC_WARPS - 1) s_total = wi;
+        if (lane == 0) s_pre[0] = pr;
+    }
+    __syncthreads();
+    const int cta_base = s_pre[0];
+    if (run == runs_per_crop - 1 && tid == 0) a.counts[b] = cta_base + s_total;
+    {
+        extern __shared__ __align__(16) float s_out[];
+        const int obj = a.obj_ids ? a.obj_ids[b] : a.obj_default;
+        const int row = active ? p0 / S : 0, col = active ? p0 - row * S : 0;
+        emit_staged<PPT>(s_out, mbits, c2, s_warp[warp] + incl - cnt, a.tables[obj], s_x, col, s_y[row], s_total, cta_base,
+                         a.corr + (size_t)b * 5 * a.cap, a.cap);
+    }
+}
+
+static int dws_reserve(zp_ctx* ctx, size_t bytes) {
+    if (bytes <= ctx->dws_bytes) return 0;
+    ZP_CUDA(ctx, cudaDeviceSynchronize());
+    if (ctx->dws) cudaFree(ctx->dws);
+    ctx->dws = nullptr; ctx->dws_bytes = 0;
+    size_t want = bytes + bytes / 4 + 4096;
+    ZP_CUDA(ctx, cudaMalloc(&ctx->dws, want));
+    ctx->dws_bytes = want;
+    return 0;
+}
+
+template <int DT>
+static int launch_split(zp_ctx* ctx, const DecodeArgs& a, cudaStream_t st) {
+    constexpr int PPT = Px<DT>::N;
+    const int N = a.S * a.S;
+    const int segs = (N + 32 * PPT - 1) / (32 * PPT);
+    const int runs = (segs + DEC_WARPS - 1) / DEC_WARPS;
+    const size_t code_bytes = a.codes ? 0 : (((size_t)a.B * N * sizeof(uint16_t) + 255) & ~(size_t)255);
+    const size_t mask_bytes = (size_t)a.B * segs * PPT * sizeof(uint32_t);
+    if (dws_reserve(ctx, code_bytes + mask_bytes)) return -2;
+    uint16_t* codes = a.codes ? a.codes : (uint16_t*)ctx->dws;
+    uint32_t* maskw = (uint32_t*)((char*)ctx->dws + code_bytes);
+    const long long total_segs = (long long)a.B * segs;
+    const unsigned grid1 = (unsigned)((total_segs + PL_THREADS / 32 - 1) / (PL_THREADS / 32));
+    zp_decode_planes_kernel<DT><<<grid1, PL_THREADS, 0, st>>>(a, codes, maskw, segs);
+    ZP_CHECK_LAUNCH(ctx, "zp_decode_planes_kernel");
+    const int smem = 5 * DEC_THREADS * PPT * (int)sizeof(float);
+    static bool attr_set = false;
+    if (!attr_set) {
+        ZP_CUDA(ctx, cudaFuncSetAttribute(zp_decode_emit_kernel<PPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_set = true;
+    }
+    zp_decode_emit_kernel<PPT><<<(unsigned)(a.B * runs), DEC_THREADS, smem, st>>>(a, codes, maskw, segs, runs);
+    ZP_CHECK_LAUNCH(ctx, "zp_decode_emit_kernel");
+    return 0;
+}
+
+// -------------------------------------------------------------------------------------------------------------
+// Streaming path (contiguous planes): a producer warp pulls the logits of a crop part through a shared-memory ring of
+// 8 KB plane segments with 1-D TMA bulk copies (cp.async.bulk + full/empty mbarriers, SASS UBLKCP), so the memory
+// system always has up to 12 x 8 KB per CTA in flight while the four consumer warps pack codes, rank, gather and
+// store -- the register-staged kernel above has no loads in flight during its scan / gather / store phases and tops
+// out at ~36 % (64 crops) .. 56 % (1024 crops) of HBM peak.  (Copies are 8 KB because the TMA unit spends a fixed
+// ~250 cycles per bulk copy: a first version with 2 KB copies reached only 2.4 TB/s.)
+// Work: a crop is split into `parts` contiguous pixel ranges, one CTA each, launched as a cluster of `parts` CTAs; a
+// CTA walks its range in blocks of 8 KB / sizeof(logit) pixels, plane by plane, keeping the partial codes of its
+// pixels in registers, with a running output offset.  The only cross-CTA dependency -- the number of masked pixels in
+// the earlier parts -- is resolved once, up front, by counting the own mask range (plain vector loads) and exchanging
+// the totals through DSMEM while the ring fills.
+// -------------------------------------------------------------------------------------------------------------
+constexpr int TMA_CONSUMERS = 128;
+constexpr int TMA_THREADS = TMA_CONSUMERS + 32;  // + one producer warp
+constexpr int TMA_SLOT_BYTES = 8192;
+constexpr int TMA_SLOTS = 12;
+constexpr int TMA_MAX_PARTS = 8;
+
+__device__ __forceinline__ uint32_t dsm_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void dec_mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(dsm_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void dec_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(dsm_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void dec_mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(dsm_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void dec_mbar_wait(uint64_t* bar, uint32_t phase) {
+    asm volatile(
+        "{\n\t.reg .pred P1;\n\t"
+        "DEC_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra DEC_DONE;\n\t"
+        "bra DEC_WAIT;\n\t"
+        "DEC_DONE:\n\t}" ::"r"(dsm_u32(bar)), "r"(phase) : "memory");
+}
+__device__ __forceinline__ void dec_tma_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     dsm_u32(dst)), "l"(src), "r"(bytes), "r"(dsm_u32(bar)) : "memory");
+}
+
+// 4 consecutive pixels (index q4 = pixel / 4 within the slot) -> 4 sign bits
+template <int DT> __device__ __forceinline__ uint32_t slot_bits4(const unsigned char* slot, int q4) {
+    if (DT == ZP_DTYPE_F32) {
+        uint4 v = *(const uint4*)(slot + (size_t)q4 * 16);
+        return (uint32_t)pos_f32(v.x) | ((uint32_t)pos_f32(v.y) << 1) | ((uint32_t)pos_f32(v.z) << 2) |
+               ((uint32_t)pos_f32(v.w) << 3);
+    } else {
+        uint2 v = *(const uint2*)(slot + (size_t)q4 * 8);
+        return (uint32_t)pos_bf16(v.x) | ((uint32_t)pos_bf16(v.x >> 16) << 1) | ((uint32_t)pos_bf16(v.y) << 2) |
+               ((uint32_t)pos_bf16(v.y >> 16) << 3);
+    }
+}
+
+template <int DT>
+__global__ void __launch_bounds__(TMA_THREADS, 2) zp_decode_tma_kernel(DecodeArgs a, int parts, int part_px) {
+    constexpr int ESZ = Px<DT>::ESZ;
+    constexpr int BLK = TMA_SLOT_BYTES / ESZ;                         // pixels per block (= per ring slot)
+    constexpr int G = BLK / (TMA_CONSUMERS * 4);                      // 4-pixel groups per consumer thread and block
+    extern __shared__ __align__(128) unsigned char s_ring[];          // [TMA_SLOTS][TMA_SLOT_BYTES]
+    __shared__ __align__(8) uint64_t s_full[TMA_SLOTS], s_empty[TMA_SLOTS];
+    __shared__ unsigned long long s_warp[2][TMA_CONSUMERS / 32];
+    __shared__ int s_total;                                           // masked pixels of this part (read by peers)
+    __shared__ int s_red[TMA_THREADS / 32];
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rank = parts > 1 ? (int)cluster.block_rank() : 0;
+    const int b = blockIdx.x / parts;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int S = a.S, N = S * S, nb = a.nb;
+    const bool own_mask = a.ext_mask == nullptr;
+    const int n_planes = nb + (own_mask ? 1 : 0);                     // planes per block; the mask plane (if any) first
+    const int px0 = min(N, rank * part_px), px1 = min(N, px0 + part_px);
+    const int n_blocks = (px1 - px0 + BLK - 1) / BLK;
+    const int n_copies = n_blocks * n_planes;
+    const char* crop = (const char*)a.logits + (size_t)b * a.sb * ESZ;
+    const bool producer = warp == TMA_CONSUMERS / 32;
+
+    auto issue = [&](int q) {                                         // copy q = (block, plane) into slot q % TMA_SLOTS
+        const int blk = q / n_planes, pl = q - blk * n_planes, slot = q % TMA_SLOTS;
+        const int p = px0 + blk * BLK;
+        const uint32_t bytes = (uint32_t)(min(BLK, px1 - p) * ESZ);
+        const int ch = own_mask ? (pl == 0 ? a.mask_ch : a.bit0_ch + pl - 1) : a.bit0_ch + pl;
+        dec_mbar_expect_tx(&s_full[slot], bytes);
+        dec_tma_load_1d(s_ring + (size_t)slot * TMA_SLOT_BYTES, crop + ((size_t)ch * a.sc + p) * ESZ, bytes, &s_full[slot]);
+    };
+    if (tid == TMA_CONSUMERS) {
+        for (int s = 0; s < TMA_SLOTS; s++) { dec_mbar_init(&s_full[s], 1); dec_mbar_init(&s_empty[s], TMA_CONSUMERS / 32); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        for (int q = 0; q < TMA_SLOTS && q < n_copies; q++) issue(q);
+    }
+    // ---- masked pixels in the earlier parts of this crop (only when the crop is split)
+    int running = 0;
+    if (parts > 1) {
+        int cnt = 0;
+        if (!producer)
+            for (int p = px0 + tid * 4; p < px1; p += TMA_CONSUMERS * 4) {
+                if (own_mask) {
+                    const char* src = crop + ((size_t)a.mask_ch * a.sc + p) * ESZ;
+                    if (DT == ZP_DTYPE_F32) {
+                        uint4 v = zp_ldg_stream(src);
+                        cnt += (int)pos_f32(v.x) + (int)pos_f32(v.y) + (int)pos_f32(v.z) + (int)pos_f32(v.w);
+                    } else {
+                        uint2 v = *(const uint2*)src;
+                        cnt += (int)pos_bf16(v.x) + (int)pos_bf16(v.x >> 16) + (int)pos_bf16(v.y) + (int)pos_bf16(v.y >> 16);
+                    }
+                } else {
+                    uchar4 m = *(const uchar4*)(a.ext_mask + (size_t)b * N + p);
+                    cnt += (m.x != 0) + (m.y != 0) + (m.z != 0) + (m.w != 0);
+                }
+            }
+        cnt = __reduce_add_sync(0xffffffffu, cnt);
+        if (lane == 0) s_red[warp] = cnt;
+        __syncthreads();
+        if (tid == 0) { int t = 0; for (int w = 0; w < TMA_THREADS / 32; w++) t += s_red[w]; s_total = t; }
+        cluster.sync();
+        for (int r = 0; r < rank; r++) running += *cluster.map_shared_rank(&s_total, r);
+        cluster.sync();                                               // peers may exit once everybody has read
+    } else {
+        __syncthreads();                                              // mbarrier init visible to the waiting threads
+    }
+    if (producer) {
+        if (lane == 0)
+            for (int q = TMA_SLOTS; q < n_copies; q++) {
+                const int slot = q % TMA_SLOTS;
+                dec_mbar_wait(&s_empty[slot], (uint32_t)(q / TMA_SLOTS - 1) & 1u);
+                issue(q);
+            }
+        return;
+    }
+    // ---- consumers
+    const double* bb = a.bbox + 4 * (size_t)b;
+    const double x0 = bb[0], y0 = bb[1], rx = bb[2] / (double)S, ry = bb[3] / (double)S;
+    const int obj = a.obj_ids ? a.obj_ids[b] : a.obj_default;
+    const float4* tab = a.tables[obj];
+    float* cb = a.corr + (size_t)b * 5 * a.cap;
+    const size_t cap = (size_t)a.cap;
+    int q = 0;
+    for (int blk = 0; blk < n_blocks; blk++) {
+        const int pb = px0 + blk * BLK;                               // first pixel of the block
+        uint32_t mbits[G], code[G][4];
+#pragma unroll
+        for (int g = 0; g < G; g++) { mbits[g] = 0; code[g][0] = code[g][1] = code[g][2] = code[g][3] = 0; }
+        if (!own_mask) {
+#pragma unroll
+            for (int g = 0; g < G; g++) {
+                const int p = pb + (g * TMA_CONSUMERS + tid) * 4;
+                if (p < px1) {
+                    uchar4 m = *(const uchar4*)(a.ext_mask + (size_t)b * N + p);
+                    mbits[g] = (uint32_t)(m.x != 0) | ((uint32_t)(m.y != 0) << 1) | ((uint32_t)(m.z != 0) << 2) | ((uint32_t)(m.w != 0) << 3);
+                }
+            }
+        }
+        for (int pl = 0; pl < n_planes; pl++, q++) {
+            const int slot = q % TMA_SLOTS;
+            dec_mbar_wait(&s_full[slot], (uint32_t)(q / TMA_SLOTS) & 1u);
+            const unsigned char* sl = s_ring + (size_t)slot * TMA_SLOT_BYTES;
+            uint32_t pbits[G];
+#pragma unroll
+            for (int g = 0; g < G; g++) pbits[g] = slot_bits4<DT>(sl, g * TMA_CONSUMERS + tid);
+            __syncwarp();
+            if (lane == 0) dec_mbar_arrive(&s_empty[slot]);           // this warp is done with the slot
+            if (own_mask && pl == 0) {
+#pragma unroll
+                for (int g = 0; g < G; g++) mbits[g] = (pb + (g * TMA_CONSUMERS + tid) * 4 < px1) ? pbits[g] : 0u;
+            } else {
+                const int sh = nb - 1 - (own_mask ? pl - 1 : pl);
+#pragma unroll
+                for (int g = 0; g < G; g++) {
+                    code[g][0] |= (pbits[g] & 1u) << sh; code[g][1] |= ((pbits[g] >> 1) & 1u) << sh;
+                    code[g][2] |= ((pbits[g] >> 2) & 1u) << sh; code[g][3] |= ((pbits[g] >> 3) & 1u) << sh;
+                }
+            }
+        }
+        if (a.codes) {
+#pragma unroll
+            for (int g = 0; g < G; g++) {
+                const int p = pb + (g * TMA_CONSUMERS + tid) * 4;
+                if (p < px1) *(uint2*)(a.codes + (size_t)b * N + p) = make_uint2(code[g][0] | (code[g][1] << 16), code[g][2] | (code[g][3] << 16));
+            }
+        }
+        // ---- ranks: the G per-group counts (<= 4 per thread, <= 128 per warp) ride in the bytes of one 64-bit word
+        unsigned long long pk = 0;
+#pragma unroll
+        for (int g = 0; g < G; g++) pk |= (unsigned long long)__popc(mbits[g]) << (8 * g);
+        unsigned long long incl = pk;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            unsigned long long t = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += t;
+        }
+        if (lane == 31) s_warp[blk & 1][warp] = incl;
+        asm volatile("bar.sync 1, %0;" ::"n"(TMA_CONSUMERS) : "memory");
+        unsigned long long wv[TMA_CONSUMERS / 32];
+#pragma unroll
+        for (int w = 0; w < TMA_CONSUMERS / 32; w++) wv[w] = s_warp[blk & 1][w];
+        int gbase = running;
+#pragma unroll
+        for (int g = 0; g < G; g++) {
+            int before = 0, total = 0;
+#pragma unroll
+            for (int w = 0; w < TMA_CONSUMERS / 32; w++) {
+                const int v = (int)((wv[w] >> (8 * g)) & 0xffu);
+                before += w < warp ? v : 0;
+                total += v;
+            }
+            const int cnt = (int)((pk >> (8 * g)) & 0xffu);
+            if (cnt) {
+                size_t pos = (size_t)(gbase + before + (int)((incl >> (8 * g)) & 0xffu) - cnt);
+                const int p = pb + (g * TMA_CONSUMERS + tid) * 4;
+                const int row = p / S, col = p - row * S;             // 4 | S: the 4 pixels share the row
+                const float yv = (float)__double2ll_rz(__dadd_rn(__dmul_rn(ry, (double)row), y0));
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    if ((mbits[g] >> j) & 1u) {
+                        if (pos < cap) {
+                            float4 P = __ldg(tab + code[g][j]);
+                            cb[pos] = (float)__double2ll_rz(__dadd_rn(__dmul_rn(rx, (double)(col + j)), x0));
+                            cb[cap + pos] = yv;
+                            cb[2 * cap + pos] = P.x;
+                            cb[3 * cap + pos] = P.y;
+                            cb[4 * cap + pos] = P.z;
+                        }
+                        pos++;
+                    }
+                }
+            }
+            gbase += total;
+        }
+        running = gbase;
+    }
+    if (rank == parts - 1 && tid == 0) a.counts[b] = running;
+}
+
+template <int DT>
+static int launch_tma(zp_ctx* ctx, const DecodeArgs& a, int parts, int part_px, cudaStream_t st) {
+    const size_t smem = (size_t)TMA_SLOTS * TMA_SLOT_BYTES;
+    static bool smem_set = false;
+    if (!smem_set) {
+        ZP_CUDA(ctx, cudaFuncSetAttribute(zp_decode_tma_kernel<DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        smem_set = true;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(a.B * parts));
+    cfg.blockDim = dim3(TMA_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = parts;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    ZP_CUDA(ctx, cudaLaunchKernelEx(&cfg, zp_decode_tma_kernel<DT>, a, parts, part_px));
+    ctx->launches++;
+    return 0;
 }
 
 // -------------------------------------------------------------------------------------------------------------
@@ -281,20 +792,33 @@ __global__ void __launch_bounds__(DEC_THREADS) zp_decode_generic_kernel(DecodeAr
 }
 
 template <int DT>
-static int launch_cluster(zp_ctx* ctx, const DecodeArgs& a, int csize, cudaStream_t st) {
+static int launch_cluster(zp_ctx* ctx, const DecodeArgs& a, int csize, bool use_cluster, cudaStream_t st) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(a.B * csize));
     cfg.blockDim = dim3(DEC_THREADS);
-    cfg.dynamicSmemBytes = 0;
+    const int smem = 5 * DEC_THREADS * Px<DT>::N * (int)sizeof(float);
+    static bool attr_set = false;
+    if (!attr_set) {
+        ZP_CUDA(ctx, cudaFuncSetAttribute(zp_decode_cluster_kernel<DT, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        ZP_CUDA(ctx, cudaFuncSetAttribute(zp_decode_cluster_kernel<DT, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        ZP_CUDA(ctx, cudaFuncSetAttribute(zp_decode_cluster_kernel<DT, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        ZP_CUDA(ctx, cudaFuncSetAttribute(zp_decode_cluster_kernel<DT, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_set = true;
+    }
+    cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = csize;
+    at[0].val.clusterDim.x = use_cluster ? csize : 1;
     at[0].val.clusterDim.y = 1;
     at[0].val.clusterDim.z = 1;
     cfg.attrs = at;
     cfg.numAttrs = 1;
-    ZP_CUDA(ctx, cudaLaunchKernelEx(&cfg, zp_decode_cluster_kernel<DT>, a));
+    const bool full16 = a.nb == 16 && a.ext_mask == nullptr;
+    if (use_cluster && full16) ZP_CUDA(ctx, cudaLaunchKernelEx(&cfg, zp_decode_cluster_kernel<DT, true, true>, a, csize));
+    else if (use_cluster) ZP_CUDA(ctx, cudaLaunchKernelEx(&cfg, zp_decode_cluster_kernel<DT, true, false>, a, csize));
+    else if (full16) ZP_CUDA(ctx, cudaLaunchKernelEx(&cfg, zp_decode_cluster_kernel<DT, false, true>, a, csize));
+    else ZP_CUDA(ctx, cudaLaunchKernelEx(&cfg, zp_decode_cluster_kernel<DT, false, false>, a, csize));
     ctx->launches++;
     return 0;
 }
@@ -316,14 +840,38 @@ int zp_launch_decode(zp_ctx* ctx, const void* logits, int dtype, int B, int S, c
     const int per_cta = DEC_THREADS * ppt;
     const int ctas = (N + per_cta - 1) / per_cta;
     bool vec_ok = a.sw == 1 && S % ppt == 0 && S <= 1024 && a.sh % ppt == 0 && a.sc % ppt == 0 && a.sb % ppt == 0 &&
-                  ((uintptr_t)logits % 16) == 0 && ctas <= DEC_MAX_CLUSTER &&
+                  ((uintptr_t)logits % 16) == 0 && ctas <= (ctx->force_decode_path == 1 ? DEC_MAX_CLUSTER : DEC_MAX_RUNS) &&
                   (codes == nullptr || ((uintptr_t)codes % 16) == 0);
-    (void)esz;
-    if (vec_ok) {
-        int csize = 1;
-        while (csize < ctas) csize <<= 1;
-        if (dtype == ZP_DTYPE_F32) return launch_cluster<ZP_DTYPE_F32>(ctx, a, csize, st);
-        return launch_cluster<ZP_DTYPE_BF16>(ctx, a, csize, st);
+    // streaming (TMA) path: contiguous planes, rows that hold whole 4-pixel groups, 16-byte aligned plane segments
+    const bool tma_ok = a.sw == 1 && a.sh == S && S % 4 == 0 && (N * esz) % 16 == 0 && ((size_t)a.sc * esz) % 16 == 0 &&
+                        ((size_t)a.sb * esz) % 16 == 0 && ((uintptr_t)logits % 16) == 0 &&
+                        (codes == nullptr || ((uintptr_t)codes % 8) == 0) && (ext_mask == nullptr || ((uintptr_t)ext_mask % 4) == 0);
+    if (tma_ok && ctx->force_decode_path == 3) {
+        // one wave of 2 CTAs per SM when the batch is small: split crops until the grid fills it
+        int parts = 1;
+        const int slots = 2 * ctx->sm_count;
+        const int blk = TMA_SLOT_BYTES / esz;
+        const int max_parts = (N + blk - 1) / blk;
+        while (parts * 2 <= TMA_MAX_PARTS && parts * 2 <= max_parts && B * parts * 2 <= slots) parts *= 2;
+        int part_px = (N + parts - 1) / parts;
+        part_px = ((part_px + blk - 1) / blk) * blk;
+        if (dtype == ZP_DTYPE_F32) return launch_tma<ZP_DTYPE_F32>(ctx, a, parts, part_px, st);
+        return launch_tma<ZP_DTYPE_BF16>(ctx, a, parts, part_px, st);
+    }
+    // two-kernel path: rows of whole PPT-pixel groups, 16-byte aligned vectors; the emit kernel's base pre-count reads
+    // <= runs * 16 * PPT words per CTA, so cap the runs per crop
+    const bool split_ok = a.sw == 1 && S % ppt == 0 && S <= 1024 && a.sh % ppt == 0 && a.sc % ppt == 0 && a.sb % ppt == 0 &&
+                          ((uintptr_t)logits % 16) == 0 && ctas <= 64 && (codes == nullptr || ((uintptr_t)codes % 16) == 0);
+    if (split_ok && (ctx->force_decode_path == 4 || (ctx->force_decode_path == 0 && !vec_ok))) {
+        if (dtype == ZP_DTYPE_F32) return launch_split<ZP_DTYPE_F32>(ctx, a, st);
+        return launch_split<ZP_DTYPE_BF16>(ctx, a, st);
+    }
+    if (vec_ok && ctx->force_decode_path != 2) {
+        const bool use_cluster = ctx->force_decode_path == 1;
+        int csize = ctas;
+        if (use_cluster) { csize = 1; while (csize < ctas) csize <<= 1; }
+        if (dtype == ZP_DTYPE_F32) return launch_cluster<ZP_DTYPE_F32>(ctx, a, csize, use_cluster, st);
+        return launch_cluster<ZP_DTYPE_BF16>(ctx, a, csize, use_cluster, st);
     }
     // generic path
     a.n_chunks = (N + DEC_THREADS - 1) / DEC_THREADS;

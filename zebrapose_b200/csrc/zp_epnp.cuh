@@ -441,6 +441,198 @@ ZP_HD inline bool zp_pose_from_betas(const double be[4], ZpMat V, const ZpHorn& 
     return ok;
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Symmetric 12x12 eigen-decomposition for the EPnP null space: Householder tridiagonalisation (reflectors kept in the
+// strict lower triangle, Q accumulated backwards in place) followed by the implicit-shift QL iteration on (d, e) with the
+// plane rotations applied to the columns of Q.  About 10x fewer FP64 operations than the cyclic Jacobi it replaces
+// (the Jacobi was 60 % of the minimal solver and 25 % of the final solve, profiles/r1d_phases.txt).  The signs / order
+// of the 12x12 singular vectors do not change EPnP's answer, so only the 3x3 problems keep OpenCV's Jacobi.
+//
+// G lanes work on one matrix (G = 1: plain serial code, also what the host build runs; G = 4: a quad per hypothesis
+// in the minimal solver; G = 16: half a warp in the final solve).  Lane gl owns the columns (tridiagonalisation,
+// accumulation) resp. rows (QL) congruent to gl mod G; scalar recurrences are computed redundantly by every lane from
+// the shared d/e arrays, and zp_gsync (a __syncwarp over the group's lanes) orders shared-memory writes against the
+// other lanes' reads.  The matrix is stored with a row stride of 13 doubles: with that, and matrices 4 (mod 16)
+// doubles apart, both the row- and the column-ownership access patterns of the 8 quads of a warp are conflict free.
+// ------------------------------------------------------------------------------------------------------------------
+#define ZP_RS 13
+#define ZP_SYM_DOUBLES (12 * ZP_RS)
+
+struct ZpSym12 {
+    double* p;
+    ZP_HD __forceinline__ double& operator()(int r, int c) const { return p[r * ZP_RS + c]; }
+};
+
+ZP_HD __forceinline__ void zp_gsync(unsigned mask) {
+#ifdef __CUDA_ARCH__
+    __syncwarp(mask);
+#else
+    (void)mask;
+#endif
+}
+ZP_HD __forceinline__ bool zp_any(unsigned wmask, bool pred) {
+#ifdef __CUDA_ARCH__
+    return __any_sync(wmask, pred) != 0;
+#else
+    (void)wmask;
+    return pred;
+#endif
+}
+
+// z: symmetric matrix in, eigenvectors (columns) out; d[12]: eigenvalues (unsorted); e[12]: scratch.
+template <int G>
+ZP_HD inline void zp_symeig12(ZpSym12 z, double* d, double* e, int gl, unsigned mask, unsigned wmask) {
+    constexpr int N = 12;
+    // ---- Householder tridiagonalisation: step k annihilates z(k+2.., k); u_k (|u|^2 = 2, H = I - u u^T) is left in
+    //      column k below the diagonal
+    for (int k = 0; k < N - 2; k++) {
+        const int b0 = k + 1;
+        double x0 = z(b0, k), sig = 0;
+        for (int i = b0 + 1; i < N; i++) { double t = z(i, k); sig = fma(t, t, sig); }
+        const double tot = fma(x0, x0, sig), dk = z(k, k);
+        const bool refl = sig > 0 && tot < 1.7e308;            // false for an already tridiagonal column and for NaN/inf
+        double alpha = x0, scale = 0, v0 = 0;
+        if (refl) {
+            double nrm = sqrt(tot);
+            alpha = x0 > 0 ? -nrm : nrm;
+            v0 = x0 - alpha;
+            scale = zp_rsqrt(tot - alpha * x0);
+        }
+        zp_gsync(mask);                                        // everybody has read column k
+        for (int i = b0 + gl; i < N; i += G) z(i, k) = (i == b0 ? v0 : z(i, k)) * scale;
+        if (gl == 0) { d[k] = dk; e[k] = alpha; }
+        zp_gsync(mask);
+        if (refl) {
+            for (int c = b0 + gl; c < N; c += G) {             // p = A22 u (A22 symmetric: column c = row c)
+                double s0 = 0, s1 = 0;
+                int r = b0;
+                for (; r + 1 < N; r += 2) { s0 = fma(z(r, c), z(r, k), s0); s1 = fma(z(r + 1, c), z(r + 1, k), s1); }
+                if (r < N) s0 = fma(z(r, c), z(r, k), s0);
+                e[c] = s0 + s1;
+            }
+            zp_gsync(mask);
+            double K = 0;
+            for (int c = b0; c < N; c++) K = fma(z(c, k), e[c], K);
+            K *= 0.5;
+            for (int c = b0 + gl; c < N; c += G) {             // A22 -= u w^T + w u^T with w = p - K u
+                const double uc = z(c, k), wc = fma(-K, uc, e[c]);
+                for (int r = b0; r < N; r++) {
+                    const double ur = z(r, k), wr = fma(-K, ur, e[r]);
+                    z(r, c) -= fma(ur, wc, wr * uc);
+                }
+            }
+        }
+        zp_gsync(mask);
+    }
+    {
+        const double d10 = z(N - 2, N - 2), d11 = z(N - 1, N - 1), e10 = z(N - 1, N - 2);
+        zp_gsync(mask);
+        if (gl == 0) { d[N - 2] = d10; d[N - 1] = d11; e[N - 2] = e10; e[N - 1] = 0; }
+    }
+    // ---- Q = H_0 H_1 ... H_9 accumulated backwards in place (column j always belongs to lane j mod G)
+    if ((N - 1) % G == gl) z(N - 1, N - 1) = 1;
+    for (int k = N - 3; k >= 0; k--) {
+        const int b0 = k + 1;
+        for (int j = b0 + ((gl - b0) % G + G) % G; j < N; j += G) {
+            const double ub = z(b0, k);
+            if (j == b0) {
+                z(b0, b0) = fma(-ub, ub, 1.0);
+                for (int i = b0 + 1; i < N; i++) z(i, b0) = -ub * z(i, k);
+            } else {
+                double s = 0;
+                for (int i = b0 + 1; i < N; i++) s = fma(z(i, k), z(i, j), s);
+                z(b0, j) = -s * ub;
+                for (int i = b0 + 1; i < N; i++) z(i, j) = fma(-s, z(i, k), z(i, j));
+            }
+        }
+        zp_gsync(mask);                                        // column k (u_k) is overwritten in the next step
+    }
+    for (int j = gl; j < N; j += G) {
+        if (j == 0) { z(0, 0) = 1; for (int i = 1; i < N; i++) z(i, 0) = 0; }
+        else z(0, j) = 0;
+    }
+    zp_gsync(mask);
+    // ---- implicit-shift QL on (d, e); rows of z are now owned (row r belongs to lane r mod G).  The control flow is
+    //      uniform over the whole warp (wmask = every lane that entered this call): all groups walk the same
+    //      l / sweep / i loops and groups that have nothing to do at a position are predicated off, because data-dependent
+    //      loop bounds would make the 8 quads of a warp diverge and execute one after the other.
+    double anorm = 0;
+    for (int i = 0; i < N; i++) anorm = fmax(anorm, fabs(d[i]) + fabs(e[i]));
+    const double small = anorm * ZP_DBL_EPS;
+    for (int l = 0; l < N - 1; l++) {
+        for (int iter = 0; iter < 40; iter++) {
+            int m = N - 1;
+            for (int j = N - 2; j >= l; j--) m = fabs(e[j]) <= small ? j : m;     // first negligible e[j], j >= l
+            const bool active = m != l && anorm < 1.7e308;    // a non-finite matrix is left alone
+            if (!zp_any(wmask, active)) break;
+            const double dl = d[l], el = e[l];
+            double g = (d[l + 1] - dl) / (2 * (active ? el : 1.0));
+            double r = sqrt(fma(g, g, 1.0));
+            g = d[m] - dl + el / (g + (g >= 0 ? r : -r));     // d[m] - shift
+            double s = 1, c = 1, p = 0;
+            bool live = active;                               // false after an underflow recovery
+            for (int i = N - 2; i >= l; i--) {
+                const bool on = live && i < m;
+                const double ei = e[i], di = d[i], di1 = d[i + 1];
+                const double f = s * ei, b = c * ei;
+                const double r2 = fma(f, f, g * g);
+                zp_gsync(mask);                                // reads of this step done by every lane before the writes
+                if (on) {
+                    if (!(r2 > 0)) {                           // underflow (or NaN): deflate here and end this sweep
+                        if (gl == 0) { e[i + 1] = 0; d[i + 1] = di1 - p; e[m] = 0; }
+                        live = false;
+                    } else {
+                        const double ir = zp_rsqrt(r2);
+                        r = r2 * ir;
+                        s = f * ir;
+                        c = g * ir;
+                        g = di1 - p;
+                        const double t = fma(di - g, s, 2 * c * b);
+                        p = s * t;
+                        if (gl == 0) { e[i + 1] = r; d[i + 1] = g + p; }
+                        g = fma(c, t, -b);
+                        for (int k = gl; k < N; k += G) {
+                            const double zk1 = z(k, i + 1), zk0 = z(k, i);
+                            z(k, i + 1) = fma(s, zk0, c * zk1);
+                            z(k, i) = fma(c, zk0, -s * zk1);
+                        }
+                    }
+                }
+            }
+            zp_gsync(mask);
+            if (live && gl == 0) { d[l] = dl - p; e[l] = g; e[m] = 0; }
+            zp_gsync(mask);
+        }
+    }
+}
+
+// Null space with the QL eigen-solver: fills z with M^T M (lane gl its own columns), decomposes, and writes the four
+// eigenvectors of the smallest eigenvalues to V[v * 12 + e] (v = 0 smallest).  d, e: 12 doubles each, shared by the
+// group.  All lanes of the group must call it together.
+template <int G>
+ZP_HD inline void zp_nullspace_ql(ZpSym12 z, double* d, double* e, const ZpSums& sums, const ZpCam& cam, int gl,
+                                  unsigned mask, unsigned wmask, double* V) {
+    for (int c = gl; c < 12; c += G)
+        for (int r = 0; r < 12; r++) z(r, c) = zp_mtm(sums, cam, r, c);
+    zp_gsync(mask);
+    zp_symeig12<G>(z, d, e, gl, mask, wmask);
+    int vi[4];
+    unsigned used = 0;
+    for (int q = 0; q < 4; q++) {
+        int best = -1;
+        double bw = 0;
+        for (int i = 0; i < 12; i++) {
+            double w = d[i];
+            if (!((used >> i) & 1u) && (best < 0 || w < bw)) { best = i; bw = w; }
+        }
+        used |= 1u << best;
+        vi[q] = best;
+    }
+    for (int q = 0; q < 4; q++)
+        for (int r = gl; r < 12; r += G) V[q * 12 + r] = z(r, vi[q]);
+    zp_gsync(mask);
+}
+
 // serial null space: fills At with M^T M, runs the Jacobi, and leaves the four normalised singular vectors of the
 // smallest singular values in rows 0..3 of At (row 0 = smallest), i.e. At doubles as the V view afterwards.
 ZP_HD inline void zp_nullspace_serial(ZpMat At, const ZpSums& sums, const ZpCam& cam) {

@@ -213,6 +213,10 @@ __device__ long long zp_dbg_clk[16];
 
 constexpr int MIN_THREADS = 128;                 // 4 lanes per hypothesis -> 32 hypotheses per CTA
 constexpr int ZP_MAX_M = 8;
+// doubles of shared memory per hypothesis; 236 = 12 (mod 16) keeps the 8 quads of a warp on distinct banks (zp_epnp.cuh)
+constexpr int MIN_HYP_DOUBLES = 236;
+static_assert(MIN_HYP_DOUBLES >= ZP_SYM_DOUBLES + 24 + 48, "per-hypothesis shared memory layout");
+constexpr int MIN_SMEM_BYTES = (MIN_THREADS / 4) * MIN_HYP_DOUBLES * (int)sizeof(double);
 
 // One QUAD (4 lanes) per hypothesis.  The cheap serial setup (control points, 52 sums over the m points) is computed
 // redundantly by the 4 lanes; the 12x12 null space is the quad-cooperative Jacobi; the three beta candidates run on
@@ -221,8 +225,10 @@ __global__ void __launch_bounds__(MIN_THREADS, 3)
 zp_minimal_kernel(const float* __restrict__ corr, int cap, const int32_t* __restrict__ counts,
                   const double* __restrict__ Kmat, const int32_t* __restrict__ samples, int B, int H, int m,
                   double inv_thr, double* __restrict__ hyp_poses, float* __restrict__ hyp_P) {
-    __shared__ double s_V[MIN_THREADS / 4][48];
+    extern __shared__ __align__(16) double s_min[];            // per hypothesis: z[12x13] | d[12] | e[12] | V[4x12]
     const int tid = threadIdx.x, lane = tid & 31, q = lane & 3, quad = tid >> 2;
+    double* s_z = s_min + (size_t)quad * MIN_HYP_DOUBLES;
+    double* s_Vq = s_z + ZP_SYM_DOUBLES + 24;
     const int total = B * H;
     const int g_raw = blockIdx.x * (MIN_THREADS / 4) + quad;
     const bool live = g_raw < total;
@@ -271,11 +277,12 @@ zp_minimal_kernel(const float* __restrict__ corr, int cap, const int32_t* __rest
             zp_accumulate(sums, a, cam.uc - U[j], cam.vc - Vv[j], X[j] - c0[0], Y[j] - c0[1], Z[j] - c0[2]);
         }
         zp_horn_inputs(sums, hs);
-        zp_nullspace_group<4>(sums, cam, q, s_V[quad]);
+        zp_nullspace_ql<4>(ZpSym12{s_z}, s_z + ZP_SYM_DOUBLES, s_z + ZP_SYM_DOUBLES + 12, sums, cam, q,
+                           0xFu << (lane & 28), 0xffffffffu, s_Vq);
     }
     __syncwarp();
     ZP_STAMP(12);
-    ZpMat V{s_V[quad], 1};
+    ZpMat V{s_Vq, 1};
     double L[60], rho[6];
     zp_L_rho(V, cp, L, rho);
     ZP_STAMP(13);
@@ -545,6 +552,7 @@ __global__ void __launch_bounds__(FIN_THREADS) zp_final_kernel(FinalArgs a) {
     __shared__ double s_red[(FIN_THREADS / 32) * 52];
     __shared__ double s_sum[52];
     __shared__ double s_V[48];
+    __shared__ __align__(16) double s_eig[ZP_SYM_DOUBLES + 24];
     __shared__ ZpControl s_cp;
     __shared__ ZpSums s_sums;
     __shared__ double s_candR[3][9], s_candt[3][3];
@@ -678,9 +686,9 @@ __global__ void __launch_bounds__(FIN_THREADS) zp_final_kernel(FinalArgs a) {
     if (tid == 0) s_sums.n = ni;
     __syncthreads();
     ZP_STAMP(5);
-    // ---- 12x12 null space on warp 0 (16-lane cooperative Jacobi; both half-warps run the same problem)
+    // ---- 12x12 null space on 16 lanes of warp 0 (cooperative Householder + QL)
     if (tid < 32) {
-        zp_nullspace_group<16>(s_sums, cam, lane & 15, s_V);  // identical values from both halves: benign duplicate stores
+        if (tid < 16) zp_nullspace_ql<16>(ZpSym12{s_eig}, s_eig + ZP_SYM_DOUBLES, s_eig + ZP_SYM_DOUBLES + 12, s_sums, cam, tid, 0xFFFFu, 0xFFFFu, s_V);
         ZP_STAMP(6);
         __syncwarp();
         ZP_STAMP(7);
@@ -815,8 +823,13 @@ int zp_launch_minimal(zp_ctx* ctx, const float* corr, int cap, const int32_t* co
                       cudaStream_t st) {
     const int per_cta = MIN_THREADS / 4;
     int total = B * H;
-    zp_minimal_kernel<<<(total + per_cta - 1) / per_cta, MIN_THREADS, 0, st>>>(corr, cap, counts, K, samples, B, H, m,
-                                                                              1.0 / (double)thr_px, hyp_poses, hyp_P);
+    static bool attr_set = false;
+    if (!attr_set) {
+        ZP_CUDA(ctx, cudaFuncSetAttribute(zp_minimal_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MIN_SMEM_BYTES));
+        attr_set = true;
+    }
+    zp_minimal_kernel<<<(total + per_cta - 1) / per_cta, MIN_THREADS, MIN_SMEM_BYTES, st>>>(
+        corr, cap, counts, K, samples, B, H, m, 1.0 / (double)thr_px, hyp_poses, hyp_P);
     ZP_CHECK_LAUNCH(ctx, "zp_minimal_kernel");
     return 0;
 }

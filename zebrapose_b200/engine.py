@@ -75,6 +75,11 @@ class Engine:
         self.ctx.check(rc, "zp_download_tables")
         return pts, remap
 
+    def set_decode_path(self, path):
+        """0 auto (fused, independent CTAs) | 1 fused, cluster exchange | 2 generic strided | 3 fused TMA ring | 4 two
+        kernels (stream + emit) -- identical results (include/zebrapose_b200.h)"""
+        self.ctx.check(self.lib.zp_set_decode_path(self.ctx.handle, int(path)), "zp_set_decode_path")
+
     # ------------------------------------------------------------------ decode
     def decode(self, logits, bboxes, obj_ids=None, *, obj_default=0, mask_ch=0, bit0_ch=1, n_bits=16, ignore_bit=0,
                ext_mask=None, return_codes=False, cap=None):
