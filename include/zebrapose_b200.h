@@ -136,6 +136,12 @@ int zp_pose_batch_host(zp_ctx* ctx, const void* h_logits, int dtype, int B, int 
  * comparison. */
 int zp_set_decode_path(zp_ctx* ctx, int path);
 
+/* Tuning aid for zp_score / zp_ransac: `groups` = warp-groups (128 threads each) per scoring CTA that split the
+ * hypotheses of a work item (0 = automatic = 1, else 1, 2 or 4); `hyp_chunk` = hypotheses per work item (0 = automatic:
+ * H/2 when the batch has about one correspondence tile per CTA slot, all of them otherwise; -1 = never cut; else the chunk).
+ * Results do not depend on either. */
+int zp_set_score_groups(zp_ctx* ctx, int groups, int hyp_chunk);
+
 /* Number of kernels this ctx has launched since creation (bench.py's gpu_launches claim). */
 int64_t zp_launch_count(zp_ctx* ctx);
 

@@ -239,3 +239,19 @@ def test_add_metric_agreement(eng, tables):
     print("ADD@0.1d pass: device %d/%d reference %d/%d; pose tolerance pass rate %d/%d" % (pass_dev, B, pass_ref, B, within, B))
     assert abs(pass_dev - pass_ref) / B <= 0.005 + 1e-9
     assert within >= 0.8 * B
+
+
+def test_score_groups_identical(eng, batch):
+    """splitting the hypotheses across warp-groups of a CTA or across work items is a scheduling choice only"""
+    B, H = len(batch["lists"]), 150
+    samples = eng.make_samples(batch["counts"], batch["corr"].shape[2], H=H, m=5)
+    hyp = eng.solve_minimal(batch["corr"], batch["counts"], batch["Ks"], samples)
+    outs = []
+    try:
+        for g, hc in ((1, -1), (2, -1), (4, -1), (1, 32), (1, 7), (2, 50), (0, 0)):
+            eng.set_score_groups(g, hc)
+            outs.append(eng.score(batch["corr"], batch["counts"], batch["Ks"], hyp, 2.0).cpu().numpy())
+    finally:
+        eng.set_score_groups(0, 0)
+    assert outs[0].max() > 1000
+    assert all(np.array_equal(outs[0], o) for o in outs[1:])

@@ -104,6 +104,15 @@ const char* zp_last_error(zp_ctx* ctx) { return ctx ? ctx->err.c_str() : g_err.c
 
 int64_t zp_launch_count(zp_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
+int zp_set_score_groups(zp_ctx* ctx, int groups, int hyp_chunk) {
+    if (!ctx) return -1;
+    if (groups != 0 && groups != 1 && groups != 2 && groups != 4) ZP_FAIL(ctx, -1, "zp_set_score_groups: groups must be 0, 1, 2 or 4");
+    if (hyp_chunk < -1 || hyp_chunk > ZP_MAX_HYPOTHESES) ZP_FAIL(ctx, -1, "zp_set_score_groups: bad hyp_chunk %d", hyp_chunk);
+    ctx->score_groups = groups;
+    ctx->score_hchunk = hyp_chunk;
+    return 0;
+}
+
 int zp_set_decode_path(zp_ctx* ctx, int path) {
     if (!ctx) return -1;
     if (path < 0 || path > 4) ZP_FAIL(ctx, -1, "zp_set_decode_path: path must be 0..4");

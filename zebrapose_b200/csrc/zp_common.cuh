@@ -37,6 +37,8 @@ struct zp_ctx {
     size_t dws_bytes = 0;
     cudaStream_t own_stream = nullptr;
     int64_t launches = 0;
+    int score_groups = 0;                    // 0 auto, else 1 | 2 | 4 warp-groups per scoring CTA (tests / tuning)
+    int score_hchunk = 0;                    // 0 auto, -1 never cut, else hypotheses per scoring work item
     int force_decode_path = 0;               // 0 auto, 1 register-staged cluster kernel, 2 generic kernel (tests)
 };
 

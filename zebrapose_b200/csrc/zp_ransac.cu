@@ -327,8 +327,10 @@ zp_minimal_kernel(const float* __restrict__ corr, int cap, const int32_t* __rest
 // scoring
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int SC_GROUP = 128;                      // threads that together cover one tile of correspondences
-constexpr int SC_NG = 1;                           // warp-groups per CTA: they split the hypotheses of the item
-constexpr int SC_THREADS = SC_GROUP * SC_NG;
+// SC_NG (template parameter) = warp-groups per CTA that split the hypotheses of one item: 1 for big batches; 4 when
+// there are only a few items per CTA slot (64 crops = 832 items on 740 slots: with one group per CTA some CTAs get two
+// items while the others idle after one -- 56 % balance; four groups per CTA make the CTAs 4x fewer and the items 4x
+// shorter, so every CTA sees 4-5 items)
 constexpr int SC_PPT = 8;                          // correspondences per thread (registers)
 constexpr int SC_TILE = SC_GROUP * SC_PPT;         // correspondences per work item
 constexpr int SC_HB = 160;                         // hypotheses staged in shared memory at a time (multiple of 32)
@@ -371,6 +373,7 @@ __global__ void zp_poses_to_P_kernel(const double* __restrict__ poses, const dou
 struct ScoreArgs {
     const float* corr; int cap; const int32_t* counts; const float* hyp_P;
     int B, H; float inv_thr; int32_t* hyp_inliers; int* counters; int n_items;
+    int hchunk, n_hc;            // hypotheses per work item and items per tile (small batches are cut finer)
 };
 
 // Persistent CTAs pulling work items (crop b, tile of SC_TILE correspondences) from a global ticket counter; items are
@@ -379,7 +382,9 @@ struct ScoreArgs {
 // matrices into shared memory (mbarrier completion); each thread keeps SC_PPT correspondences in registers and walks
 // the hypotheses (3 x LDS.128 broadcast each); the sign bits of d are funnel-shifted into one register (1 instruction
 // per evaluation), popc'ed, warp-reduced with REDUX and accumulated lane-distributed (lane h%32 owns hypothesis h).
-__global__ void __launch_bounds__(SC_THREADS) zp_score_kernel(ScoreArgs a) {
+template <int SC_NG>
+__global__ void __launch_bounds__(SC_GROUP * SC_NG) zp_score_kernel(ScoreArgs a) {
+    constexpr int SC_THREADS = SC_GROUP * SC_NG;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float* s_pts = (float*)smem_raw;                                   // [5][SC_TILE]
     ulonglong2* s_P = (ulonglong2*)(s_pts + 5 * SC_TILE);              // [SC_HB][6]: (P,P) pairs, 96 B per hypothesis
@@ -399,11 +404,14 @@ __global__ void __launch_bounds__(SC_THREADS) zp_score_kernel(ScoreArgs a) {
         if (tid == 0) s_item = atomicAdd(&a.counters[0], 1);
         __syncthreads();
         int w = s_item;
-        if (w >= 2 * a.n_items) break;
+        const int per_pass = a.n_items * a.n_hc;
+        if (w >= 2 * per_pass) break;
         // pass 0 hands out the full tiles, pass 1 the partial (last) tile of every list: the small items come last,
-        // which bounds the finishing skew between SMs
-        const bool second = w >= a.n_items;
-        if (second) w -= a.n_items;
+        // which bounds the finishing skew between SMs.  A tile is cut into n_hc items of hchunk hypotheses.
+        const bool second = w >= per_pass;
+        if (second) w -= per_pass;
+        const int hc = w % a.n_hc;
+        w /= a.n_hc;
         const int b = w % a.B, tile = w / a.B;
         const int n = min(a.counts[b], a.cap);
         const int start = tile * SC_TILE;
@@ -413,18 +421,19 @@ __global__ void __launch_bounds__(SC_THREADS) zp_score_kernel(ScoreArgs a) {
         const float* cb = a.corr + (size_t)b * 5 * a.cap + start;
         const uint32_t bytes = (uint32_t)((cnt + 3) & ~3) * 4u;        // 16-byte granules; cap % 4 == 0 keeps it in bounds
         f32x2 nu[SC_PPT / 2], nv[SC_PPT / 2], X[SC_PPT / 2], Y[SC_PPT / 2], Z[SC_PPT / 2];   // point pairs (j, j+1)
-        for (int h0 = 0; h0 < H; h0 += SC_HB) {
-            const int hb = min(SC_HB, H - h0);
+        const int h_begin = hc * a.hchunk, h_end = min(H, h_begin + a.hchunk);
+        for (int h0 = h_begin; h0 < h_end; h0 += SC_HB) {
+            const int hb = min(SC_HB, h_end - h0);
             if (tid == 0) {
                 const uint32_t pbytes = (uint32_t)hb * 96u;
-                mbar_expect_tx(&s_bar, (h0 == 0 ? 5 * bytes : 0) + pbytes);
-                if (h0 == 0)
+                mbar_expect_tx(&s_bar, (h0 == h_begin ? 5 * bytes : 0) + pbytes);
+                if (h0 == h_begin)
                     for (int pl = 0; pl < 5; pl++) tma_load_1d(s_pts + pl * SC_TILE, cb + (size_t)pl * a.cap, bytes, &s_bar);
                 tma_load_1d(s_P, a.hyp_P + ((size_t)b * H + h0) * 24, pbytes, &s_bar);
             }
             mbar_wait(&s_bar, phase);
             phase ^= 1;
-            if (h0 == 0) {
+            if (h0 == h_begin) {
 #pragma unroll
                 for (int k = 0; k < SC_PPT / 2; k++) {
                     float f[2][5];
@@ -841,30 +850,44 @@ int zp_launch_poses_to_P(zp_ctx* ctx, const double* poses, const double* K, int 
     return 0;
 }
 
+template <int NG>
+static int launch_score_ng(zp_ctx* ctx, ScoreArgs& a, int smem, cudaStream_t st) {
+    static bool attr_set = false;
+    static int per_sm = 0;
+    if (!attr_set) {
+        ZP_CUDA(ctx, cudaFuncSetAttribute(zp_score_kernel<NG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        ZP_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, zp_score_kernel<NG>, SC_GROUP * NG, smem));
+        if (per_sm < 1) per_sm = 1;
+        attr_set = true;
+    }
+    int grid = ctx->sm_count * per_sm;
+    // about one tile per CTA slot (64 crops: 832 tiles on 740 slots): cut the tiles into two items of H/2 hypotheses so
+    // that the last round is short (measured -6 %; finer cuts or bigger batches lose more to the extra tile loads)
+    a.hchunk = a.H; a.n_hc = 1;
+    const int hc_req = ctx->score_hchunk;
+    if (hc_req > 0 || (hc_req == 0 && a.n_items <= 2 * grid && a.H >= 64)) {
+        a.hchunk = hc_req > 0 ? hc_req : (a.H + 1) / 2;
+        a.n_hc = (a.H + a.hchunk - 1) / a.hchunk;
+    }
+    if (grid > 2 * a.n_items * a.n_hc) grid = 2 * a.n_items * a.n_hc;
+    zp_score_kernel<NG><<<grid, SC_GROUP * NG, smem, st>>>(a);
+    ZP_CHECK_LAUNCH(ctx, "zp_score_kernel");
+    return 0;
+}
+
 int zp_launch_score(zp_ctx* ctx, const float* corr, int cap, const int32_t* counts, const float* hyp_P, int B, int H,
                     float thr_px, int32_t* hyp_inliers, cudaStream_t st) {
-    static bool attr_set = false;
     ScoreArgs a;
     a.corr = corr; a.cap = cap; a.counts = counts; a.hyp_P = hyp_P; a.B = B; a.H = H; a.inv_thr = 1.0f / thr_px;
     a.hyp_inliers = hyp_inliers; a.counters = ctx->d_counters;
     const int max_tiles = (cap + SC_TILE - 1) / SC_TILE;
     a.n_items = B * max_tiles;
     const int smem = 5 * SC_TILE * sizeof(float) + SC_HB * (6 * sizeof(ulonglong2) + sizeof(int));
-    if (!attr_set) {
-        ZP_CUDA(ctx, cudaFuncSetAttribute(zp_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr_set = true;
-    }
-    static int per_sm = 0;
-    if (!per_sm) {
-        ZP_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, zp_score_kernel, SC_THREADS, smem));
-        if (per_sm < 1) per_sm = 1;
-    }
-    int grid = ctx->sm_count * per_sm;
-    if (grid > 2 * a.n_items) grid = 2 * a.n_items;
     ZP_CUDA(ctx, cudaMemsetAsync(hyp_inliers, 0, (size_t)B * H * sizeof(int32_t), st));
-    zp_score_kernel<<<grid, SC_THREADS, smem, st>>>(a);
-    ZP_CHECK_LAUNCH(ctx, "zp_score_kernel");
-    return 0;
+    const int ng = ctx->score_groups ? ctx->score_groups : 1;
+    if (ng == 1) return launch_score_ng<1>(ctx, a, smem, st);
+    if (ng == 2) return launch_score_ng<2>(ctx, a, smem, st);
+    return launch_score_ng<4>(ctx, a, smem, st);
 }
 
 int zp_launch_final(zp_ctx* ctx, const float* corr, int cap, const int32_t* counts, const double* K,

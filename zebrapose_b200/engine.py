@@ -80,6 +80,10 @@ class Engine:
         kernels (stream + emit) -- identical results (include/zebrapose_b200.h)"""
         self.ctx.check(self.lib.zp_set_decode_path(self.ctx.handle, int(path)), "zp_set_decode_path")
 
+    def set_score_groups(self, groups=0, hyp_chunk=0):
+        """scheduling knobs of the scoring kernel (include/zebrapose_b200.h); results do not depend on them"""
+        self.ctx.check(self.lib.zp_set_score_groups(self.ctx.handle, int(groups), int(hyp_chunk)), "zp_set_score_groups")
+
     # ------------------------------------------------------------------ decode
     def decode(self, logits, bboxes, obj_ids=None, *, obj_default=0, mask_ch=0, bit0_ch=1, n_bits=16, ignore_bit=0,
                ext_mask=None, return_codes=False, cap=None):
