@@ -142,6 +142,19 @@ int zp_set_decode_path(zp_ctx* ctx, int path);
  * Results do not depend on either. */
 int zp_set_score_groups(zp_ctx* ctx, int groups, int hyp_chunk);
 
+/* Asynchronous form of zp_pose_batch_host: enqueues the copies and the kernels on the ctx's own stream and returns; the
+ * outputs are valid after zp_sync(ctx).  The host buffers (inputs AND outputs) must stay alive and unmodified until
+ * then and should be pinned (pageable memory makes the copies synchronous).  One submission may be in flight per ctx;
+ * several ctxs ("lanes") overlap the host->device copy of one batch with the kernels of another. */
+int zp_pose_batch_host_async(zp_ctx* ctx, const void* h_logits, int dtype, int B, int C, int S,
+                             int mask_ch, int bit0_ch, int n_bits, int ignore_bit,
+                             const double* h_bbox, const double* h_K, const int32_t* h_obj_ids, int obj_default,
+                             int H, int m, float thr_px, double confidence, int sampler, uint64_t seed,
+                             int select_mode, int final_mode,
+                             double* h_poses, int32_t* h_n_inliers, int32_t* h_status);
+/* Waits for everything enqueued on the ctx's own stream (zp_pose_batch_host_async). */
+int zp_sync(zp_ctx* ctx);
+
 /* Number of kernels this ctx has launched since creation (bench.py's gpu_launches claim). */
 int64_t zp_launch_count(zp_ctx* ctx);
 

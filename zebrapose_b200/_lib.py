@@ -30,6 +30,9 @@ SIGNATURES = {
     "zp_ransac": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _f, _d, _i, _u64, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "zp_pose_batch_host": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _i, _i, _f, _d, _i, _u64, _i, _i,
                                 _vp, _vp, _vp]),
+    "zp_pose_batch_host_async": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _i, _i, _f, _d, _i, _u64, _i, _i,
+                                      _vp, _vp, _vp]),
+    "zp_sync": (_i, [_vp]),
     "zp_remap_pixels": (_i, [_vp, _vp, _i64, _vp, _i, _vp, _vp]),
     "zp_codes_to_ids": (_i, [_vp, _vp, _i64, _i, _i, _vp, _vp]),
     "zp_launch_count": (_i64, [_vp]),

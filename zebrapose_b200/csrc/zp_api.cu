@@ -316,10 +316,10 @@ int zp_ransac(zp_ctx* ctx, const float* corr, int cap, const int32_t* counts, co
                            poses, n_inliers, status, best_idx, inlier_mask, st);
 }
 
-int zp_pose_batch_host(zp_ctx* ctx, const void* h_logits, int dtype, int B, int C, int S, int mask_ch, int bit0_ch,
-                       int n_bits, int ignore_bit, const double* h_bbox, const double* h_K, const int32_t* h_obj_ids,
-                       int obj_default, int H, int m, float thr_px, double confidence, int sampler, uint64_t seed,
-                       int select_mode, int final_mode, double* h_poses, int32_t* h_n_inliers, int32_t* h_status) {
+int zp_pose_batch_host_async(zp_ctx* ctx, const void* h_logits, int dtype, int B, int C, int S, int mask_ch, int bit0_ch,
+                             int n_bits, int ignore_bit, const double* h_bbox, const double* h_K, const int32_t* h_obj_ids,
+                             int obj_default, int H, int m, float thr_px, double confidence, int sampler, uint64_t seed,
+                             int select_mode, int final_mode, double* h_poses, int32_t* h_n_inliers, int32_t* h_status) {
     if (!ctx) return -1;
     if (B == 0) return 0;
     if (!h_logits || !h_bbox || !h_K || !h_poses || !h_n_inliers || !h_status) ZP_FAIL(ctx, -1, "zp_pose_batch_host: null argument");
@@ -354,8 +354,25 @@ int zp_pose_batch_host(zp_ctx* ctx, const void* h_logits, int dtype, int B, int 
     ZP_CUDA(ctx, cudaMemcpyAsync(h_poses, d_pose, (size_t)B * 12 * 8, cudaMemcpyDeviceToHost, st));
     ZP_CUDA(ctx, cudaMemcpyAsync(h_n_inliers, d_ni, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
     ZP_CUDA(ctx, cudaMemcpyAsync(h_status, d_st, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
-    ZP_CUDA(ctx, cudaStreamSynchronize(st));
     return 0;
+}
+
+int zp_sync(zp_ctx* ctx) {
+    if (!ctx) return -1;
+    ZP_CUDA(ctx, cudaSetDevice(ctx->device));
+    ZP_CUDA(ctx, cudaStreamSynchronize(ctx->own_stream));
+    return 0;
+}
+
+int zp_pose_batch_host(zp_ctx* ctx, const void* h_logits, int dtype, int B, int C, int S, int mask_ch, int bit0_ch,
+                       int n_bits, int ignore_bit, const double* h_bbox, const double* h_K, const int32_t* h_obj_ids,
+                       int obj_default, int H, int m, float thr_px, double confidence, int sampler, uint64_t seed,
+                       int select_mode, int final_mode, double* h_poses, int32_t* h_n_inliers, int32_t* h_status) {
+    if (int r = zp_pose_batch_host_async(ctx, h_logits, dtype, B, C, S, mask_ch, bit0_ch, n_bits, ignore_bit, h_bbox, h_K,
+                                         h_obj_ids, obj_default, H, m, thr_px, confidence, sampler, seed, select_mode,
+                                         final_mode, h_poses, h_n_inliers, h_status)) return r;
+    if (B == 0) return 0;
+    return zp_sync(ctx);
 }
 
 int zp_debug_clocks(zp_ctx* ctx, int64_t* out16) {

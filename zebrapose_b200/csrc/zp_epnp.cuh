@@ -552,58 +552,96 @@ ZP_HD inline void zp_symeig12(ZpSym12 z, double* d, double* e, int gl, unsigned 
         else z(0, j) = 0;
     }
     zp_gsync(mask);
-    // ---- implicit-shift QL on (d, e); rows of z are now owned (row r belongs to lane r mod G).  The control flow is
-    //      uniform over the whole warp (wmask = every lane that entered this call): all groups walk the same
-    //      l / sweep / i loops and groups that have nothing to do at a position are predicated off, because data-dependent
-    //      loop bounds would make the 8 quads of a warp diverge and execute one after the other.
+    // ---- implicit-shift QL on (d, e).  Every lane keeps a private copy of d and e and its own rows of Q (row r belongs
+    //      to lane r mod G) in REGISTERS: the l and i loops are fully unrolled so that every index is static, the scalar
+    //      recurrence is computed redundantly by the lanes of a group and nothing is exchanged until the end.  (The first
+    //      version kept d, e and Q in shared memory: 100 issue slots per rotation, half of them address arithmetic,
+    //      LDS/STS and the group barrier that ordered the shared d/e updates.)
+    //      The control flow is uniform over the whole warp (wmask = every lane that entered this call): all groups walk
+    //      the same l / sweep / i loops and a group that has nothing to do at a position is predicated off, because
+    //      data-dependent loop bounds would make the 8 quads of a warp diverge and run one after the other.
+    constexpr int ROWS = (N + G - 1) / G;
+    double dd[N], ee[N], zr[ROWS][N];
+#pragma unroll
+    for (int i = 0; i < N; i++) { dd[i] = d[i]; ee[i] = e[i]; }
+#pragma unroll
+    for (int k = 0; k < ROWS; k++) {
+        const int r = gl + k * G;
+#pragma unroll
+        for (int c = 0; c < N; c++) zr[k][c] = r < N ? z(r, c) : 0.0;
+    }
     double anorm = 0;
-    for (int i = 0; i < N; i++) anorm = fmax(anorm, fabs(d[i]) + fabs(e[i]));
+#pragma unroll
+    for (int i = 0; i < N; i++) anorm = fmax(anorm, fabs(dd[i]) + fabs(ee[i]));
     const double small = anorm * ZP_DBL_EPS;
+    const bool finite = anorm < 1.7e308;                      // a non-finite matrix is left alone
+#pragma unroll
     for (int l = 0; l < N - 1; l++) {
         for (int iter = 0; iter < 40; iter++) {
             int m = N - 1;
-            for (int j = N - 2; j >= l; j--) m = fabs(e[j]) <= small ? j : m;     // first negligible e[j], j >= l
-            const bool active = m != l && anorm < 1.7e308;    // a non-finite matrix is left alone
+            double dm = dd[N - 1];
+#pragma unroll
+            for (int j = N - 2; j >= l; j--) {                // first negligible e[j], j >= l
+                const bool neg = fabs(ee[j]) <= small;
+                m = neg ? j : m;
+                dm = neg ? dd[j] : dm;
+            }
+            const bool active = m != l && finite;
             if (!zp_any(wmask, active)) break;
-            const double dl = d[l], el = e[l];
-            double g = (d[l + 1] - dl) / (2 * (active ? el : 1.0));
+            const double dl = dd[l], el = ee[l];
+            double g = (dd[l + 1] - dl) / (2 * (active ? el : 1.0));
             double r = sqrt(fma(g, g, 1.0));
-            g = d[m] - dl + el / (g + (g >= 0 ? r : -r));     // d[m] - shift
+            g = dm - dl + el / (g + (g >= 0 ? r : -r));       // d[m] - shift
             double s = 1, c = 1, p = 0;
             bool live = active;                               // false after an underflow recovery
+#pragma unroll
             for (int i = N - 2; i >= l; i--) {
                 const bool on = live && i < m;
-                const double ei = e[i], di = d[i], di1 = d[i + 1];
-                const double f = s * ei, b = c * ei;
+                const double f = s * ee[i], b = c * ee[i];
                 const double r2 = fma(f, f, g * g);
-                zp_gsync(mask);                                // reads of this step done by every lane before the writes
-                if (on) {
-                    if (!(r2 > 0)) {                           // underflow (or NaN): deflate here and end this sweep
-                        if (gl == 0) { e[i + 1] = 0; d[i + 1] = di1 - p; e[m] = 0; }
-                        live = false;
-                    } else {
-                        const double ir = zp_rsqrt(r2);
-                        r = r2 * ir;
-                        s = f * ir;
-                        c = g * ir;
-                        g = di1 - p;
-                        const double t = fma(di - g, s, 2 * c * b);
-                        p = s * t;
-                        if (gl == 0) { e[i + 1] = r; d[i + 1] = g + p; }
-                        g = fma(c, t, -b);
-                        for (int k = gl; k < N; k += G) {
-                            const double zk1 = z(k, i + 1), zk0 = z(k, i);
-                            z(k, i + 1) = fma(s, zk0, c * zk1);
-                            z(k, i) = fma(c, zk0, -s * zk1);
-                        }
+                const bool ok = r2 > 0;                        // false: underflow (or NaN) -> deflate here, end this sweep
+                const double ir = zp_rsqrt(ok ? r2 : 1.0);
+                const double rn = r2 * ir, sn = f * ir, cn = g * ir;
+                const double gn = dd[i + 1] - p;
+                const double t = fma(dd[i] - gn, sn, 2 * cn * b);
+                const double pn = sn * t;
+                if (on && ok) {
+                    ee[i + 1] = rn; dd[i + 1] = gn + pn;
+                    s = sn; c = cn; p = pn; g = fma(cn, t, -b);
+#pragma unroll
+                    for (int k = 0; k < ROWS; k++) {
+                        const double z1 = zr[k][i + 1], z0 = zr[k][i];
+                        zr[k][i + 1] = fma(sn, z0, cn * z1);
+                        zr[k][i] = fma(cn, z0, -sn * z1);
                     }
+                } else if (on) {
+                    ee[i + 1] = 0; dd[i + 1] -= p;
+#pragma unroll
+                    for (int j = l; j < N - 1; j++) if (j == m) ee[j] = 0;
+                    live = false;
                 }
             }
-            zp_gsync(mask);
-            if (live && gl == 0) { d[l] = dl - p; e[l] = g; e[m] = 0; }
-            zp_gsync(mask);
+            if (live) {
+                dd[l] = dl - p; ee[l] = g;
+#pragma unroll
+                for (int j = l; j < N - 1; j++) if (j == m) ee[j] = 0;
+            }
         }
     }
+    zp_gsync(mask);                                           // every lane has loaded its rows before anybody stores
+#pragma unroll
+    for (int k = 0; k < ROWS; k++) {
+        const int r = gl + k * G;
+        if (r < N) {
+#pragma unroll
+            for (int c = 0; c < N; c++) z(r, c) = zr[k][c];
+        }
+    }
+    if (gl == 0) {
+#pragma unroll
+        for (int i = 0; i < N; i++) d[i] = dd[i];
+    }
+    zp_gsync(mask);
 }
 
 // Null space with the QL eigen-solver: fills z with M^T M (lane gl its own columns), decomposes, and writes the four

@@ -209,9 +209,10 @@ class Engine:
 
     def pose_batch_host(self, logits, bboxes, Ks, obj_ids=None, *, obj_default=0, mask_ch=0, bit0_ch=1, n_bits=16,
                         ignore_bit=0, m=5, iters=150, thr=2.0, conf=0.99, sampler="cv2", seed=0, select="cv2_replay",
-                        final="epnp", out=None):
+                        final="epnp", out=None, asynchronous=False):
         """HOST numpy / pinned-tensor buffers in, HOST results out, through zp_pose_batch_host (H2D + chain + D2H
-        inside one C call; synchronous).  logits [B,C,S,S] contiguous float32 (numpy) or a CPU torch tensor."""
+        inside one C call; synchronous).  logits [B,C,S,S] contiguous float32 (numpy) or a CPU torch tensor.
+        asynchronous=True enqueues only (zp_pose_batch_host_async): `out` is valid after sync(); use pinned buffers."""
         lg = logits if isinstance(logits, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(logits))
         if lg.is_cuda or not lg.is_contiguous():
             raise ValueError("pose_batch_host takes contiguous HOST logits")
@@ -223,7 +224,10 @@ class Engine:
         if out is None:
             out = (np.empty((B, 12)), np.empty(B, np.int32), np.empty(B, np.int32))
         poses, ninl, status = out
-        rc = self.lib.zp_pose_batch_host(
+        fn = self.lib.zp_pose_batch_host_async if asynchronous else self.lib.zp_pose_batch_host
+        if asynchronous:                      # the C side reads these after we return: keep them alive until sync()
+            self._inflight = (lg, bb, K, oid, out)
+        rc = fn(
             self.ctx.handle, C.c_void_p(lg.data_ptr()), _DT[lg.dtype], B, Cc, S, int(mask_ch), int(bit0_ch), int(n_bits),
             int(ignore_bit), bb.ctypes.data_as(C.c_void_p), K.ctypes.data_as(C.c_void_p),
             oid.ctypes.data_as(C.c_void_p) if oid is not None else C.c_void_p(), int(obj_default), int(iters), int(m),
@@ -231,6 +235,11 @@ class Engine:
             poses.ctypes.data_as(C.c_void_p), ninl.ctypes.data_as(C.c_void_p), status.ctypes.data_as(C.c_void_p))
         self.ctx.check(rc, "zp_pose_batch_host")
         return poses, ninl, status
+
+    def sync(self):
+        """waits for an asynchronous pose_batch_host submission"""
+        self.ctx.check(self.lib.zp_sync(self.ctx.handle), "zp_sync")
+        self._inflight = None
 
     # ------------------------------------------------------------------ small stand-alone helpers
     def remap_pixels(self, pixels, bbox, S):
@@ -259,6 +268,73 @@ class Engine:
         fn = self.lib.zp_fp32x2_peak_probe if packed else self.lib.zp_fp32_peak_probe
         self.ctx.check(fn(self.ctx.handle, int(iters), C.byref(v)), "zp_fp32_peak_probe")
         return v.value
+
+
+class Pipeline:
+    """Several engines ("lanes": one zp_ctx + one CUDA stream each) used round-robin, so that consecutive batches
+    overlap on the GPU: the kernels of this path are latency-bound at BASELINE's 64-crop batches (a step keeps well
+    under half of the SMs' issue slots busy), and the host->device copy of one batch runs under the kernels of the
+    previous one.  Every lane holds its own copy of the dictionaries and its own workspace."""
+
+    def __init__(self, device=None, lanes=3):
+        self.engines = [Engine(device) for _ in range(int(lanes))]
+        self.device = self.engines[0].device
+        self.streams = [torch.cuda.Stream(device=self.device) for _ in self.engines]
+        self._next = 0
+        self._busy = [False] * len(self.engines)
+
+    @property
+    def next_lane(self):
+        return self._next
+
+    def upload_dict(self, *args, **kw):
+        for e in self.engines:
+            e.upload_dict(*args, **kw)
+
+    def submit(self, logits, bboxes, Ks, obj_ids=None, post=None, **kw):
+        """device-resident batch on the next lane; returns (poses, n_inliers, status, done_event).  The inputs must have
+        been produced on (or be visible to) the current stream: the lane's stream waits for it first.  `post`, if given,
+        maps the result tuple inside the lane's stream context (e.g. the multi-GPU pose gather)."""
+        i = self._next
+        self._next = (i + 1) % len(self.engines)
+        s = self.streams[i]
+        s.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(s):
+            out = self.engines[i].decode_and_pose_batch(logits, bboxes, Ks, obj_ids, **kw)
+            if post is not None:
+                out = tuple(post(out))
+            ev = torch.cuda.Event()
+            ev.record(s)
+        for t in (logits, bboxes, Ks, obj_ids):
+            if isinstance(t, torch.Tensor) and t.is_cuda:
+                t.record_stream(s)
+        return out + (ev,)
+
+    def join(self):
+        """makes the current stream wait for every lane"""
+        cur = torch.cuda.current_stream(self.device)
+        for s in self.streams:
+            cur.wait_stream(s)
+
+    def submit_host(self, logits, bboxes, Ks, obj_ids=None, **kw):
+        """host buffers on the next lane (asynchronous); returns the lane index to pass to wait_host().  A lane that
+        still has a submission in flight is waited for first."""
+        i = self._next
+        self._next = (i + 1) % len(self.engines)
+        if self._busy[i]:
+            self.wait_host(i)
+        self.engines[i].pose_batch_host(logits, bboxes, Ks, obj_ids, asynchronous=True, **kw)
+        self._busy[i] = True
+        return i
+
+    def wait_host(self, lane=None):
+        for i in (range(len(self.engines)) if lane is None else [lane]):
+            if self._busy[i]:
+                self.engines[i].sync()
+                self._busy[i] = False
+
+    def launch_count(self):
+        return sum(e.launch_count() for e in self.engines)
 
 
 _default = {}
