@@ -28,6 +28,8 @@ METRIC = "crop-poses/sec, code decode+RANSAC-PnP"
 UNIT = "poses/s"
 S, NBITS, H, M, THR = 128, 16, 150, 5, 2.0
 L2_FLUSH_BYTES = 256 << 20
+WORKLOAD = ("configs[1]: %d synthetic YCB-V-like 128x128 crops per GPU, 21 dictionaries, ignore_bit 0, "
+            "decode + RANSAC-EPnP (150 hypotheses x 5 points, 2 px, cv2 replay)")
 
 
 def make_workload(crops, seed):
@@ -66,6 +68,21 @@ class ClockSampler(threading.Thread):
                 "reasons": reasons, "samples": len(self.rows)}
 
 
+class StdoutToStderr:
+    """fd-level redirect: libraries that write to stdout (NCCL's version banner) must not pollute the one JSON line"""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+
+
 def cpu_baseline(logits, bboxes, Ks, obj, tables, n_sample, repeats=1):
     """reference CPU path on all host cores, bounded sample"""
     from oracle.reference_path import ReferencePool
@@ -102,8 +119,9 @@ def run_reference(args, rank, world):
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "configs[1]: %d synthetic YCB-V-like 128x128 crops, 21 dictionaries, ignore_bit 0; "
-                                   "reference CPU path (per-pixel dict loop + cv2.solvePnPRansac EPnP 150 it, 2 px)" % args.crops},
+            "config": {"workload": WORKLOAD % args.crops, "crops_per_gpu": args.crops,
+                       "arm": "reference CPU path (host threshold of all logits, per-pixel dict loop, cv2.solvePnPRansac EPnP), "
+                              "one step = the same batch on all host cores"},
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": "%d crops per step, fork pool of %d workers, cv2.setNumThreads(1)" % (args.crops, cores)},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -137,7 +155,10 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local))
+        with StdoutToStderr():
+            dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local))
+            dist.barrier()
+            torch.cuda.synchronize()
     pipe = zp.Pipeline(local, lanes=args.lanes)
     eng = pipe.engines[0]
     C = args.crops
@@ -283,8 +304,7 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32 scoring / f64 EPnP / u16 codes", "data": "synthetic",
-            "config": {"workload": "configs[1]: %d synthetic YCB-V-like 128x128 crops per GPU, 21 dictionaries, ignore_bit 0, "
-                                   "decode + RANSAC-EPnP (150 hypotheses x 5 points, 2 px, cv2 replay)" % C,
+            "config": {"workload": WORKLOAD % C,
                        "crops_per_gpu": C, "lanes": args.lanes,
                        "l2": "inputs larger than L2: %d rotating device batches of %.0f MB, a step never re-reads the buffer of "
                              "the previous %d steps (per-kernel figures: 256 MiB flush write before each launch)" % (n_buf, logits.nbytes / 1e6, n_buf - 1),
