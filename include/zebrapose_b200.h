@@ -158,8 +158,9 @@ int zp_sync(zp_ctx* ctx);
 /* Number of kernels this ctx has launched since creation (bench.py's gpu_launches claim). */
 int64_t zp_launch_count(zp_ctx* ctx);
 
-/* Profiling aid: SM-clock timestamps of the phases of CTA 0 of the last final-solve launch (16 slots; synchronises). */
-int zp_debug_clocks(zp_ctx* ctx, int64_t* out16);
+/* Profiling aid: SM-clock timestamps of the phases of CTA 0 of the last RANSAC launches (24 slots: 0-9 final solve,
+ * 10-15 minimal solver, 16-19 eigen-solver; synchronises). */
+int zp_debug_clocks(zp_ctx* ctx, int64_t* out24);
 
 /* FP32 FMA-chain microbenchmark (the roofline denominator for zp_score has no entry in MEASURED_PEAKS.json):
  * runs `iters` dependent-chain FMAs x 8 chains per thread on the whole chip, returns achieved TFLOP/s in *out.

@@ -38,7 +38,7 @@ int main() {
             zp_accumulate(s, a, cam.uc - x[i], cam.vc - y[i], X[i] - c0[0], Y[i] - c0[1], Z[i] - c0[2]);
         }
         double zbuf[ZP_SYM_DOUBLES], dd[12], ee[12], at[48];
-        zp_nullspace_ql<1>(ZpSym12{zbuf}, dd, ee, s, cam, 0, 0u, 0u, at);
+        zp_nullspace4<1>(ZpSym12{zbuf}, dd, ee, s.s0, cam, 0, 0u, at);
         ZpMat At{at, 1};
         double L[60], rho[6];
         zp_L_rho(At, cp, L, rho);

@@ -19,10 +19,12 @@ def exe(tmp_path_factory):
     return out
 
 
-def _run(exe, mats):
+def _run(exe, mats, mode="full"):
     txt = "\n".join(" ".join("%.17g" % v for v in A.ravel()) for A in mats) + "\n"
-    out = subprocess.run([exe], input=txt, capture_output=True, text=True, check=True).stdout
+    out = subprocess.run([exe, mode], input=txt, capture_output=True, text=True, check=True).stdout
     a = np.array([[float(v) for v in line.split()] for line in out.strip().split("\n")])
+    if mode == "small4":
+        return a[:, :4], a[:, 4:].reshape(-1, 4, 12)
     return a[:, :12], a[:, 12:].reshape(-1, 12, 12)
 
 
@@ -58,3 +60,20 @@ def test_symeig12_nan_terminates(exe):
     A = np.full((12, 12), np.nan)
     d, Z = _run(exe, [A])                                 # must return (garbage allowed), not hang
     assert d.shape == (1, 12)
+
+
+def test_smallest4_matches_eigh(exe):
+    """zp_smallest4_12 (bisection + inverse iteration, what the kernels run): eigenvalues, residuals, orthonormality, and
+    -- where eigenvalues coincide (rank-deficient Gram matrices) -- the right invariant subspace"""
+    mats = [A for A in _cases() if np.abs(A).max() > 0]
+    lam, V = _run(exe, mats, "small4")
+    for A, w, v in zip(mats, lam, V):
+        nrm = np.abs(A).sum(1).max()
+        ew, ev = np.linalg.eigh(A)
+        assert np.allclose(w, ew[:4], rtol=0, atol=2e-13 * nrm)
+        assert np.abs(v @ v.T - np.eye(4)).max() < 1e-10
+        assert np.abs(A @ v.T - v.T * w).max() < 2e-12 * nrm
+        # eigenvalues 0..3 separated from the rest: the span must be the span of eigh's four vectors
+        if ew[4] - ew[3] > 1e-6 * nrm:
+            P = ev[:, :4] @ ev[:, :4].T
+            assert np.abs(v @ P - v).max() < 1e-7

@@ -375,7 +375,7 @@ int zp_pose_batch_host(zp_ctx* ctx, const void* h_logits, int dtype, int B, int 
     return zp_sync(ctx);
 }
 
-int zp_debug_clocks(zp_ctx* ctx, int64_t* out16) {
+int zp_debug_clocks(zp_ctx* ctx, int64_t* out16) {   // 24 slots
     if (!ctx || !out16) return -1;
     ZP_CUDA(ctx, cudaDeviceSynchronize());
     return zp_read_debug_clocks((long long*)out16);

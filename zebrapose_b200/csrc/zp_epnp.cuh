@@ -15,8 +15,13 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <math.h>
+#include <cmath>
 
 #define ZP_HD __host__ __device__
+#if !defined(ZP_EIG_STAMP) || !defined(__CUDA_ARCH__)
+#undef ZP_EIG_STAMP
+#define ZP_EIG_STAMP(i)
+#endif
 #define ZP_DBL_EPS 2.220446049250313e-16
 #define ZP_DBL_MIN 2.2250738585072014e-308
 
@@ -480,8 +485,10 @@ ZP_HD __forceinline__ bool zp_any(unsigned wmask, bool pred) {
 }
 
 // z: symmetric matrix in, eigenvectors (columns) out; d[12]: eigenvalues (unsorted); e[12]: scratch.
+// Householder tridiagonalisation T = Q^T A Q, Q = H_0 ... H_9: on exit d[0..11] / e[0..10] hold the diagonal / subdiagonal
+// of T and column k of z, below the diagonal, the reflector u_k (|u_k|^2 = 2, H_k = I - u_k u_k^T; u_k = 0 if none).
 template <int G>
-ZP_HD inline void zp_symeig12(ZpSym12 z, double* d, double* e, int gl, unsigned mask, unsigned wmask) {
+ZP_HD inline void zp_tridiag12(ZpSym12 z, double* d, double* e, int gl, unsigned mask) {
     constexpr int N = 12;
     // ---- Householder tridiagonalisation: step k annihilates z(k+2.., k); u_k (|u|^2 = 2, H = I - u u^T) is left in
     //      column k below the diagonal
@@ -529,6 +536,15 @@ ZP_HD inline void zp_symeig12(ZpSym12 z, double* d, double* e, int gl, unsigned 
         zp_gsync(mask);
         if (gl == 0) { d[N - 2] = d10; d[N - 1] = d11; e[N - 2] = e10; e[N - 1] = 0; }
     }
+}
+
+// z: symmetric matrix in, eigenvectors (columns) out; d[12]: eigenvalues (unsorted); e[12]: scratch.  Full decomposition
+// (tridiagonalisation + accumulated Q + implicit QL with vectors): reference implementation for the host tests; the
+// kernels use zp_smallest4_12 below, which needs only 4 eigenpairs.
+template <int G>
+ZP_HD inline void zp_symeig12(ZpSym12 z, double* d, double* e, int gl, unsigned mask, unsigned wmask) {
+    constexpr int N = 12;
+    zp_tridiag12<G>(z, d, e, gl, mask);
     // ---- Q = H_0 H_1 ... H_9 accumulated backwards in place (column j always belongs to lane j mod G)
     if ((N - 1) % G == gl) z(N - 1, N - 1) = 1;
     for (int k = N - 3; k >= 0; k--) {
@@ -642,6 +658,281 @@ ZP_HD inline void zp_symeig12(ZpSym12 z, double* d, double* e, int gl, unsigned 
         for (int i = 0; i < N; i++) d[i] = dd[i];
     }
     zp_gsync(mask);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// The four smallest eigenpairs of the 12x12 matrix -- all EPnP needs -- without the QL iteration: after the
+// tridiagonalisation, "eigen-lane" k (k = 0..3: the first four lanes of the group, or a loop on the host) finds the k-th
+// smallest eigenvalue of T by bisection on the Sturm sequence (division-free determinant recurrence on T / |T|, 46
+// halvings: fixed trip count, no divergence), then its eigenvector by inverse iteration on T - lambda I (tridiagonal LU
+// with partial pivoting, 3 solves, modified Gram-Schmidt against the eigen-lanes below it after every solve, which is
+// what makes a multiple eigenvalue -- the 2-dimensional null space of a 5-point M^T M -- come out as an orthonormal
+// basis), and finally multiplies by the Householder reflectors (Q is never formed).  ~2.5 k issue slots against ~20 k for
+// accumulating Q and running QL with vectors, and the chain of dependent operations is 10x shorter.
+// ------------------------------------------------------------------------------------------------------------------
+struct ZpTriLU { double dl[11], dg[12], du[11], du2[10]; unsigned piv; };
+
+// number of eigenvalues of the (normalised) tridiagonal (td, e2 = squared off-diagonals) that are < x
+ZP_HD __forceinline__ unsigned zp_signbit(double v) {
+#ifdef __CUDA_ARCH__
+    return (unsigned)__double2hiint(v) >> 31;
+#else
+    return std::signbit(v) ? 1u : 0u;
+#endif
+}
+
+ZP_HD __forceinline__ int zp_sturm_count(const double* td, const double* e2, double x) {
+    // p_i = (d_i - x) p_{i-1} - e_{i-1}^2 p_{i-2}: one dependent DFMA per step (the product with p_{i-2} is off the chain);
+    // the count is the number of sign changes along 1, p_1, .., p_12.  Signs are taken from the sign BIT: a p_i that is
+    // exactly zero is followed by -e^2 p_{i-2}, so whichever sign the zero carries, p_{i-2} -> p_i -> p_{i+1} shows exactly
+    // one change, as it must.  With |T| = 1 the p_i stay far from overflow; they can only become tiny next to a multiple
+    // eigenvalue, so the pair is rescaled once, half way.
+    double pm1 = 1.0, p0 = td[0] - x;
+    unsigned signs = zp_signbit(p0);                     // bit i (from the top of the 12 collected) = sign of p_{i+1}
+#pragma unroll
+    for (int i = 1; i < 12; i++) {
+        const double pn = fma(td[i] - x, p0, -e2[i - 1] * pm1);
+        signs = (signs << 1) | zp_signbit(pn);
+        pm1 = p0; p0 = pn;
+        if (i == 6 && fabs(p0) < 1e-100) { p0 *= 1e150; pm1 *= 1e150; }
+    }
+    // signs = s_1 .. s_12 (s_12 in bit 0), s_0 = 0: changes = popcount(s ^ (s >> 1)) over the 12 adjacent pairs
+    const unsigned ch = (signs ^ (signs >> 1)) & 0xFFFu;
+#ifdef __CUDA_ARCH__
+    return __popc(ch);
+#else
+    return __builtin_popcount(ch);
+#endif
+}
+
+ZP_HD __forceinline__ double zp_bisect_kth(const double* td, const double* e2, int k) {
+    double lo = -1.01, hi = 1.01;                         // |T| is normalised: every eigenvalue lies in [-1, 1]
+    for (int it = 0; it < 46; it++) {                     // 2.02 * 2^-46 = 3e-14 |T|: ample for the inverse iteration
+        const double mid = 0.5 * (lo + hi);
+        const bool below = zp_sturm_count(td, e2, mid) > k;    // more than k eigenvalues < mid -> the k-th is below mid
+        hi = below ? mid : hi;
+        lo = below ? lo : mid;
+    }
+    return 0.5 * (lo + hi);
+}
+
+// LU with partial pivoting of the tridiagonal T - lam I (sub/super-diagonals te)
+ZP_HD __forceinline__ void zp_tri_lu(const double* td, const double* te, double lam, ZpTriLU& f) {
+    const double tiny = 1e-290;
+#pragma unroll
+    for (int i = 0; i < 12; i++) f.dg[i] = td[i] - lam;
+#pragma unroll
+    for (int i = 0; i < 11; i++) { f.dl[i] = te[i]; f.du[i] = te[i]; }
+#pragma unroll
+    for (int i = 0; i < 10; i++) f.du2[i] = 0;
+    f.piv = 0;
+#pragma unroll
+    for (int i = 0; i < 11; i++) {
+        if (fabs(f.dg[i]) >= fabs(f.dl[i])) {
+            if (f.dg[i] == 0) f.dg[i] = tiny;
+            const double m = f.dl[i] / f.dg[i];
+            f.dl[i] = m;
+            f.dg[i + 1] = fma(-m, f.du[i], f.dg[i + 1]);
+        } else {                                         // interchange rows i and i + 1
+            const double m = f.dg[i] / f.dl[i];
+            f.dg[i] = f.dl[i];
+            f.dl[i] = m;
+            const double t = f.du[i];
+            f.du[i] = f.dg[i + 1];
+            f.dg[i + 1] = fma(-m, f.dg[i + 1], t);
+            if (i < 10) { f.du2[i] = f.du[i + 1]; f.du[i + 1] = -m * f.du[i + 1]; }
+            f.piv |= 1u << i;
+        }
+    }
+    if (f.dg[11] == 0) f.dg[11] = tiny;
+#pragma unroll
+    for (int i = 0; i < 12; i++) f.dg[i] = 1.0 / f.dg[i];  // the solves multiply
+}
+
+ZP_HD __forceinline__ void zp_tri_solve(const ZpTriLU& f, double* x) {
+#pragma unroll
+    for (int i = 0; i < 11; i++) {
+        if ((f.piv >> i) & 1u) { const double t = x[i]; x[i] = x[i + 1]; x[i + 1] = fma(-f.dl[i], x[i], t); }
+        else x[i + 1] = fma(-f.dl[i], x[i], x[i + 1]);
+    }
+    x[11] *= f.dg[11];
+    x[10] = fma(-f.du[10], x[11], x[10]) * f.dg[10];
+#pragma unroll
+    for (int i = 9; i >= 0; i--) x[i] = fma(-f.du2[i], x[i + 2], fma(-f.du[i], x[i + 1], x[i])) * f.dg[i];
+}
+
+// x <- x / |x|.  safe = true first brings the entries to O(1) with an exact power-of-two factor (a solve against a nearly
+// singular matrix grows them by up to 1e16 or more)
+ZP_HD __forceinline__ void zp_normalise12(double* x, bool safe) {
+    if (safe) {
+        double a = 0;
+#pragma unroll
+        for (int i = 0; i < 12; i++) a = fmax(a, fabs(x[i]));
+        double sc = 1.0;
+        if (a > 0 && a < 1.7e308) {
+#ifdef __CUDA_ARCH__
+            const int ex = (__double2hiint(a) >> 20) & 0x7ff;                 // biased exponent of the largest entry
+            sc = __hiloint2double((2046 - (ex < 1 ? 1 : ex > 2045 ? 2045 : ex)) << 20, 0);
+#else
+            int ex;
+            frexp(a, &ex);
+            sc = ldexp(1.0, 1 - ex);
+#endif
+        }
+#pragma unroll
+        for (int i = 0; i < 12; i++) x[i] *= sc;
+    }
+    double n0 = 0, n1 = 0;
+#pragma unroll
+    for (int i = 0; i < 12; i += 2) { n0 = fma(x[i], x[i], n0); n1 = fma(x[i + 1], x[i + 1], n1); }
+    const double n2 = n0 + n1;
+    const double inv = n2 > 0 ? zp_rsqrt(n2) : 0.0;
+#pragma unroll
+    for (int i = 0; i < 12; i++) x[i] *= inv;
+}
+
+// x <- Q x with Q = H_0 ... H_9 (reflectors in the columns of z)
+ZP_HD __forceinline__ void zp_apply_reflectors(ZpSym12 z, double* x) {
+#pragma unroll
+    for (int k = 9; k >= 0; k--) {
+        double u[12], s0 = 0, s1 = 0;
+#pragma unroll
+        for (int i = k + 1; i < 12; i++) u[i] = z(i, k);
+#pragma unroll
+        for (int i = k + 1; i < 12; i += 2) { s0 = fma(u[i], x[i], s0); if (i + 1 < 12) s1 = fma(u[i + 1], x[i + 1], s1); }
+        const double s = s0 + s1;
+#pragma unroll
+        for (int i = k + 1; i < 12; i++) x[i] = fma(-s, u[i], x[i]);
+    }
+}
+
+ZP_HD __forceinline__ double zp_bcast(double v, int src, int width, unsigned mask) {
+#ifdef __CUDA_ARCH__
+    return __shfl_sync(mask, v, src, width);
+#else
+    (void)src; (void)width; (void)mask;
+    return v;
+#endif
+}
+
+// z: symmetric matrix in (destroyed); V[v * 12 + i]: eigenvector of the v-th smallest eigenvalue; lam4 (nullable): the four
+// eigenvalues.  d, e: 12 doubles each of scratch shared by the group.  All G lanes of the group call it together
+// (G >= 4 on the device; G = 1 = serial host code).
+template <int G>
+ZP_HD inline void zp_smallest4_12(ZpSym12 z, double* d, double* e, int gl, unsigned mask, double* V, double* lam4) {
+    ZP_EIG_STAMP(16);
+    zp_tridiag12<G>(z, d, e, gl, mask);
+    zp_gsync(mask);
+    ZP_EIG_STAMP(17);
+    double td[12], te[11], e2[11];
+    double anorm = 0;
+#pragma unroll
+    for (int i = 0; i < 12; i++) anorm = fmax(anorm, fabs(d[i]) + (i < 11 ? fabs(e[i]) : 0.0) + (i > 0 ? fabs(e[i - 1]) : 0.0));
+    const double inv = anorm > 0 && anorm < 1.7e308 ? 1.0 / anorm : 1.0;
+#pragma unroll
+    for (int i = 0; i < 12; i++) td[i] = d[i] * inv;
+#pragma unroll
+    // the Sturm recurrence needs an unreduced matrix: an off-diagonal of at least 1e-15 |T| (a change of the
+    // eigenvalues below rounding) keeps it from decoupling into exact zeros
+    for (int i = 0; i < 11; i++) { te[i] = e[i] * inv; e2[i] = fmax(te[i] * te[i], 1e-30); }
+    constexpr int NL = G == 1 ? 4 : 1;                    // eigen-lanes handled by this thread
+    double lam[4], x[NL][12];
+    // ---- eigenvalues
+#ifdef __CUDA_ARCH__
+    {
+        const double mine = zp_bisect_kth(td, e2, gl < 4 ? gl : 3);
+#pragma unroll
+        for (int k = 0; k < 4; k++) lam[k] = zp_bcast(mine, k, G, mask);
+    }
+#else
+    for (int k = 0; k < 4; k++) lam[k] = zp_bisect_kth(td, e2, k);
+#endif
+    if (lam4) { if (gl == 0) for (int k = 0; k < 4; k++) lam4[k] = lam[k] * anorm; }
+    ZP_EIG_STAMP(18);
+    // separate coinciding eigenvalues a little so that the shifted matrices differ (LAPACK dstein does the same)
+    double lp[4];
+    lp[0] = lam[0];
+#pragma unroll
+    for (int k = 1; k < 4; k++) lp[k] = fmax(lam[k], lp[k - 1] + 1e-14);
+    // ---- inverse iteration
+#pragma unroll
+    for (int q = 0; q < NL; q++) {
+        const int k = G == 1 ? q : (gl < 4 ? gl : 3);
+#pragma unroll
+        for (int i = 0; i < 12; i++) x[q][i] = 1.0 + 0.25 * (double)((i * 5 + k * 3) % 7);
+    }
+#ifdef __CUDA_ARCH__
+    ZpTriLU f;
+    zp_tri_lu(td, te, lp[gl < 4 ? gl : 3], f);
+    for (int it = 0; it < 3; it++) {
+        zp_tri_solve(f, x[0]);
+        zp_normalise12(x[0], true);
+        // modified Gram-Schmidt down the eigen-lanes: the lanes above j remove their component along x_j and renormalise
+        // (every lane runs the same instructions; only the lanes above j keep the result)
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+            double xj[12], dot0 = 0, dot1 = 0, dot2 = 0;
+#pragma unroll
+            for (int i = 0; i < 12; i++) xj[i] = zp_bcast(x[0][i], j, G, mask);
+#pragma unroll
+            for (int i = 0; i < 12; i += 3) { dot0 = fma(xj[i], x[0][i], dot0); dot1 = fma(xj[i + 1], x[0][i + 1], dot1); dot2 = fma(xj[i + 2], x[0][i + 2], dot2); }
+            const double dot = dot0 + dot1 + dot2;
+            const double w = gl > j && gl < 4 ? dot : 0.0;
+#pragma unroll
+            for (int i = 0; i < 12; i++) x[0][i] = fma(-w, xj[i], x[0][i]);
+            zp_normalise12(x[0], false);
+        }
+    }
+    zp_apply_reflectors(z, x[0]);
+    if (gl < 4) {
+#pragma unroll
+        for (int i = 0; i < 12; i++) V[gl * 12 + i] = x[0][i];
+    }
+#else
+    ZpTriLU f[4];
+    for (int k = 0; k < 4; k++) zp_tri_lu(td, te, lp[k], f[k]);
+    for (int it = 0; it < 3; it++) {
+        for (int k = 0; k < 4; k++) zp_tri_solve(f[k], x[k]);
+        for (int k = 0; k < 4; k++) zp_normalise12(x[k], true);
+        for (int j = 0; j < 3; j++) {
+            for (int k = j + 1; k < 4; k++) {
+                double dot = 0;
+                for (int i = 0; i < 12; i++) dot = fma(x[j][i], x[k][i], dot);
+                for (int i = 0; i < 12; i++) x[k][i] = fma(-dot, x[j][i], x[k][i]);
+                zp_normalise12(x[k], false);
+            }
+        }
+    }
+    for (int k = 0; k < 4; k++) {
+        zp_apply_reflectors(z, x[k]);
+        for (int i = 0; i < 12; i++) V[k * 12 + i] = x[k][i];
+    }
+#endif
+    zp_gsync(mask);
+    ZP_EIG_STAMP(19);
+}
+
+// Null space for EPnP: fills z with M^T M (lane gl its own columns) from the 40 sums S (memory every lane of the group
+// can index dynamically: shared memory on the device) and writes the four eigenvectors of the smallest eigenvalues to
+// V[v * 12 + e] (v = 0 smallest).  d, e: 12 doubles each, shared by the group.
+template <int G>
+ZP_HD inline void zp_nullspace4(ZpSym12 z, double* d, double* e, const double* S, const ZpCam& cam, int gl,
+                                unsigned mask, double* V) {
+    // column c = 3k + cc of M^T M; its 3x3 blocks are [fu^2 s0, 0, fu sx; 0, fv^2 s0, fv sy; fu sx, fv sy, sr](j,k)
+    for (int c = gl; c < 12; c += G) {
+        const int k = c / 3, cc = c - 3 * k;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int lo = j < k ? j : k, hi = j < k ? k : j;
+            const int q = 4 * lo - (lo * (lo - 1)) / 2 + (hi - lo);         // packed index of the symmetric 4x4: 0 4 7 9
+            const double s0 = S[q], sx = S[10 + q], sy = S[20 + q], sr = S[30 + q];
+            z(3 * j + 0, c) = cc == 0 ? cam.fu * cam.fu * s0 : cc == 1 ? 0.0 : cam.fu * sx;
+            z(3 * j + 1, c) = cc == 0 ? 0.0 : cc == 1 ? cam.fv * cam.fv * s0 : cam.fv * sy;
+            z(3 * j + 2, c) = cc == 0 ? cam.fu * sx : cc == 1 ? cam.fv * sy : sr;
+        }
+    }
+    zp_gsync(mask);
+    zp_smallest4_12<G>(z, d, e, gl, mask, V, nullptr);
 }
 
 // Null space with the QL eigen-solver: fills z with M^T M (lane gl its own columns), decomposes, and writes the four

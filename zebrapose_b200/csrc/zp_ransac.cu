@@ -18,6 +18,12 @@
 //
 // Algorithmic FP32 work of scoring: 27 flop per (correspondence, hypothesis).
 #include "zp_common.cuh"
+
+// phase timestamps of thread 0 of CTA 0 (profiling aid, read with zp_debug_clocks): slots 0-9 final kernel, 10-15 minimal
+// kernel, 16-19 inside the eigen-solver (last caller wins)
+__device__ long long zp_dbg_clk[24];
+#define ZP_STAMP(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) zp_dbg_clk[i] = clock64(); } while (0)
+#define ZP_EIG_STAMP(i) ZP_STAMP(i)
 #include "zp_epnp.cuh"
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -207,9 +213,6 @@ __device__ __forceinline__ bool zp_is_inlier(const float4& p0, const float4& p1,
     return __float_as_int(zp_inlier_d(p0, p1, p2, u, v, X, Y, Z)) < 0;
 }
 
-// phase timestamps of thread 0 of CTA 0 (profiling aid, read with zp_debug_clocks): slots 0-9 final kernel, 10-15 minimal
-__device__ long long zp_dbg_clk[16];
-#define ZP_STAMP(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) zp_dbg_clk[i] = clock64(); } while (0)
 
 constexpr int MIN_THREADS = 128;                 // 4 lanes per hypothesis -> 32 hypotheses per CTA
 constexpr int ZP_MAX_M = 8;
@@ -277,8 +280,15 @@ zp_minimal_kernel(const float* __restrict__ corr, int cap, const int32_t* __rest
             zp_accumulate(sums, a, cam.uc - U[j], cam.vc - Vv[j], X[j] - c0[0], Y[j] - c0[1], Z[j] - c0[2]);
         }
         zp_horn_inputs(sums, hs);
-        zp_nullspace_ql<4>(ZpSym12{s_z}, s_z + ZP_SYM_DOUBLES, s_z + ZP_SYM_DOUBLES + 12, sums, cam, q,
-                           0xFu << (lane & 28), 0xffffffffu, s_Vq);
+        // the 40 M^T M sums go through shared memory (the V slot is free until the solver returns) so that the fill can
+        // index them dynamically; lane q of the quad stores the q-th group of ten
+        {
+            double* S = s_Vq;
+#pragma unroll
+            for (int e = 0; e < 10; e++) S[10 * q + e] = q == 0 ? sums.s0[e] : q == 1 ? sums.sx[e] : q == 2 ? sums.sy[e] : sums.sr[e];
+            __syncwarp(0xFu << (lane & 28));
+        }
+        zp_nullspace4<4>(ZpSym12{s_z}, s_z + ZP_SYM_DOUBLES, s_z + ZP_SYM_DOUBLES + 12, s_Vq, cam, q, 0xFu << (lane & 28), s_Vq);
     }
     __syncwarp();
     ZP_STAMP(12);
@@ -695,9 +705,9 @@ __global__ void __launch_bounds__(FIN_THREADS) zp_final_kernel(FinalArgs a) {
     if (tid == 0) s_sums.n = ni;
     __syncthreads();
     ZP_STAMP(5);
-    // ---- 12x12 null space on 16 lanes of warp 0 (cooperative Householder + QL)
+    // ---- 12x12 null space on 16 lanes of warp 0 (cooperative Householder; bisection + inverse iteration on 4 of them)
     if (tid < 32) {
-        if (tid < 16) zp_nullspace_ql<16>(ZpSym12{s_eig}, s_eig + ZP_SYM_DOUBLES, s_eig + ZP_SYM_DOUBLES + 12, s_sums, cam, tid, 0xFFFFu, 0xFFFFu, s_V);
+        if (tid < 16) zp_nullspace4<16>(ZpSym12{s_eig}, s_eig + ZP_SYM_DOUBLES, s_eig + ZP_SYM_DOUBLES + 12, s_sums.s0, cam, tid, 0xFFFFu, s_V);
         ZP_STAMP(6);
         __syncwarp();
         ZP_STAMP(7);
@@ -918,7 +928,7 @@ __global__ void zp_fma2_probe_kernel(float* out, int iters, float a, float b) {
 }
 
 int zp_read_debug_clocks(long long* host16) {
-    return cudaMemcpyFromSymbol(host16, zp_dbg_clk, sizeof(long long) * 16) == cudaSuccess ? 0 : -2;
+    return cudaMemcpyFromSymbol(host16, zp_dbg_clk, sizeof(long long) * 24) == cudaSuccess ? 0 : -2;
 }
 
 int zp_launch_fma_probe(zp_ctx* ctx, int iters, int packed, double* out_tflops) {
