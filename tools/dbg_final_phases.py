@@ -13,7 +13,7 @@ eng.lib.zp_debug_clocks(eng.ctx.handle, buf)
 c=np.array(list(buf))
 names=['select','pass0','pass1','pca','pass2','jacobi','pick4','cands','pass3+pick']
 d=np.diff(c[:10])
-for n,v in zip(names[:-1],d): print('%-10s %8d cycles %7.1f us'%(n,v,v/1965.0))
+for n,v in zip(names,d): print('%-10s %8d cycles %7.1f us'%(n,v,v/1965.0))
 print('total', (c[9]-c[0])/1965.0,'us')
 nm=['setup','nullspace(jacobi)','L_rho','candidates','errors+write']
 for n,v in zip(nm,np.diff(c[10:16])): print('minimal %-18s %8d cycles %7.1f us'%(n,v,v/1965.0))

@@ -17,6 +17,7 @@
 //                       three lanes, optional Gauss-Newton polish of the reprojection error
 //
 // Algorithmic FP32 work of scoring: 27 flop per (correspondence, hypothesis).
+#include <climits>
 #include "zp_common.cuh"
 
 // phase timestamps of thread 0 of CTA 0 (profiling aid, read with zp_debug_clocks): slots 0-9 final kernel, 10-15 minimal
@@ -42,20 +43,29 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c[4], uint32_t k0, uint32
 
 constexpr int SMP_THREADS = 256;
 
+constexpr int SMP_WINDOW = 2048;                 // raw RNG values staged in shared memory (150 x 5 draws need ~760)
+
 // draws m distinct indices in [0,n) from the raw stream starting at table position `pos`; returns the number of raw
-// values consumed, or -1 if the table would be overrun
-__device__ __forceinline__ int draw_from_table(const uint32_t* __restrict__ tab, int n_tab, int pos, int n, int m, int* idx) {
+// values consumed, or -1 if the table would be overrun.  The first SMP_WINDOW values come from shared memory.
+__device__ __forceinline__ int draw_from_table(const uint32_t* __restrict__ tab, const uint32_t* s_tab, int n_tab, int pos,
+                                               int n, int m, int* idx) {
     int p = pos;
-    for (int j = 0; j < m; j++) {
-        int v;
-        bool dup;
-        do {
-            if (p >= n_tab) return -1;
-            v = (int)(tab[p++] % (uint32_t)n);
-            dup = false;
-            for (int q = 0; q < j; q++) dup |= idx[q] == v;
-        } while (dup);
-        idx[j] = v;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {                     // m <= 8; static indices keep idx[] in registers
+        if (j < m) {
+            int v;
+            bool dup;
+            do {
+                if (p >= n_tab) return -1;
+                const uint32_t raw = p < SMP_WINDOW ? s_tab[p] : tab[p];
+                p++;
+                v = (int)(raw % (uint32_t)n);
+                dup = false;
+#pragma unroll
+                for (int q = 0; q < 8; q++) dup |= q < j && idx[q] == v;
+            } while (dup);
+            idx[j] = v;
+        }
     }
     return p - pos;
 }
@@ -64,7 +74,7 @@ __device__ __forceinline__ int draw_from_table(const uint32_t* __restrict__ tab,
 __global__ void __launch_bounds__(SMP_THREADS)
 zp_samples_kernel(const int32_t* __restrict__ counts, int cap, int B, int H, int m, int mode, uint64_t seed,
                   const uint32_t* __restrict__ rng_tab, int n_tab, int32_t* __restrict__ samples) {
-    const int b = blockIdx.x, tid = threadIdx.x;
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n = min(counts[b], cap);
     int32_t* out = samples + (size_t)b * H * m;
     if (n < m) {
@@ -91,42 +101,58 @@ zp_samples_kernel(const int32_t* __restrict__ counts, int cap, int B, int H, int
         }
         return;
     }
-    // cv2 replay.  off[h] = first raw value hypothesis h consumes = m*h + (redraws of all earlier hypotheses).
-    __shared__ int s_cons[ZP_MAX_HYPOTHESES];
+    // cv2 replay.  off[h] = first raw value hypothesis h consumes = m*h + (redraws of all earlier hypotheses): a fixed
+    // point of "draw from the current offsets -> block exclusive scan of the consumed counts", usually reached in 1-2
+    // rounds (a redraw needs a duplicate among m indices in [0, n)).
+    __shared__ uint32_t s_tab[SMP_WINDOW];
     __shared__ int s_off[ZP_MAX_HYPOTHESES];
+    __shared__ int s_wsum[SMP_THREADS / 32];
     __shared__ int s_flag;
+    for (int i = tid; i < SMP_WINDOW && i < n_tab; i += SMP_THREADS) s_tab[i] = rng_tab[i];
     for (int h = tid; h < H; h += SMP_THREADS) s_off[h] = m * h;
+    if (tid == 0) s_flag = 0;
     __syncthreads();
     bool overflow = false;
     for (int round = 0; round <= H; round++) {
-        if (tid == 0) s_flag = 0;
-        __syncthreads();
-        for (int h = tid; h < H; h += SMP_THREADS) {
-            int idx[8];
-            int c = draw_from_table(rng_tab, n_tab, s_off[h], n, m, idx);
-            if (c < 0) { c = m; atomicOr(&s_flag, 2); }
-            s_cons[h] = c;
-        }
-        __syncthreads();
-        if (s_flag & 2) { overflow = true; break; }
-        if (tid == 0) {                            // H <= 1024: a serial scan is a few hundred cycles
-            int run = 0, chg = 0;
-            for (int h = 0; h < H; h++) {
-                chg |= s_off[h] != run;
-                s_off[h] = run;
-                run += s_cons[h];
+        int carry = 0, changed = 0, over = 0;
+        for (int c0 = 0; c0 < H; c0 += SMP_THREADS) {         // H <= SMP_THREADS: one pass
+            const int h = c0 + tid;
+            int cons = 0;
+            if (h < H) {
+                int idx[8];
+                cons = draw_from_table(rng_tab, s_tab, n_tab, s_off[h], n, m, idx);
+                if (cons < 0) { cons = m; over = 1; }
             }
-            if (chg) s_flag = 1;
+            int incl = cons;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                int t = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += t;
+            }
+            if (lane == 31) s_wsum[warp] = incl;
+            __syncthreads();
+            int base = carry;
+            for (int w = 0; w < warp; w++) base += s_wsum[w];
+            const int off = base + incl - cons;
+            if (h < H) { changed |= s_off[h] != off; s_off[h] = off; }
+            for (int w = 0; w < SMP_THREADS / 32; w++) carry += s_wsum[w];
+            __syncthreads();
         }
+        if (changed | over) atomicOr(&s_flag, changed | (over << 1));
         __syncthreads();
-        if (!(s_flag & 1)) break;
+        const int f = s_flag;
         __syncthreads();
+        if (tid == 0) s_flag = 0;
+        if (f & 2) { overflow = true; break; }
+        if (!(f & 1)) break;
     }
+    __syncthreads();
     if (!overflow) {
         for (int h = tid; h < H; h += SMP_THREADS) {
             int idx[8];
-            draw_from_table(rng_tab, n_tab, s_off[h], n, m, idx);
-            for (int j = 0; j < m; j++) out[h * m + j] = idx[j];
+            draw_from_table(rng_tab, s_tab, n_tab, s_off[h], n, m, idx);
+#pragma unroll
+            for (int j = 0; j < 8; j++) if (j < m) out[h * m + j] = idx[j];
         }
         return;
     }
@@ -578,42 +604,88 @@ __global__ void __launch_bounds__(FIN_THREADS) zp_final_kernel(FinalArgs a) {
     __shared__ int s_candok[3];
     __shared__ double s_pose[12];
     __shared__ int s_first, s_n, s_best, s_status;
-    extern __shared__ uint32_t s_dyn[];               // inlier bitset (cap+31)/32 words, then H counts
-    uint32_t* s_mask = s_dyn;
-    int* s_hi = (int*)(s_dyn + (a.cap + 31) / 32);
+    extern __shared__ __align__(8) unsigned char s_dynb[];   // H log(den) | inlier bitset (cap+31)/32 words | H counts | H ratios | record bits
+    double* s_ld = (double*)s_dynb;
+    uint32_t* s_mask = (uint32_t*)(s_ld + a.H);
+    int* s_hi = (int*)(s_mask + (a.cap + 31) / 32);
+    int* s_rt = s_hi + a.H;
+    unsigned* s_rec = (unsigned*)(s_rt + a.H);
+    __shared__ int s_wmax[FIN_THREADS / 32];
 
     ZP_STAMP(0);
     double* out = a.poses + 12 * (size_t)b;
     const int n_raw = a.counts[b];
     const int n = min(n_raw, a.cap);
-    // ---- winner: cv2's rule replayed over the H counts (PnPRansac / RANSACPointSetRegistrator::run)
+    // ---- winner: cv2's rule replayed over the H counts (PnPRansac / RANSACPointSetRegistrator::run):
+    //        niters = H; for it < niters: if good[it] > max(maxGood, m-1): best = it, maxGood = good[it],
+    //                                        niters = RANSACUpdateNumIters(conf, (n - good)/n, m, niters)
+    //      Only "records" (counts above everything before them) can change the state, so: a block-wide exclusive prefix
+    //      maximum flags the records, every record evaluates its own log/pow in parallel, and one thread walks the
+    //      handful of records in order (the serial loop over all H counts with a pow + 2 logs per record cost 20 us).
     for (int h = tid; h < a.H; h += FIN_THREADS) s_hi[h] = a.hyp_inliers[(size_t)b * a.H + h];
     __syncthreads();
-    if (tid == 0) {
-        int best = -1, st = ZP_OK;
-        if (n_raw == 0) st = ZP_NO_MASK_PIXELS;
-        else if (n < 6) st = ZP_TOO_FEW_POINTS;       // CNN_output_to_pose.py:126
-        else {
-            int maxgood = 0;
-            if (a.select_mode == ZP_SELECT_CV2_REPLAY) {
+    {
+        const double lognum = log(fmax(1.0 - fmin(fmax(a.conf, 0.0), 1.0), ZP_DBL_MIN));
+        int carry = a.m - 1;
+        for (int c0 = 0; c0 < a.H; c0 += FIN_THREADS) {
+            const int h = c0 + tid;
+            const int good = h < a.H ? s_hi[h] : INT_MIN;
+            int v = good;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                int t = __shfl_up_sync(0xffffffffu, v, d);
+                if (lane >= d) v = max(v, t);
+            }
+            if (lane == 31) s_wmax[tid >> 5] = v;
+            int prev = __shfl_up_sync(0xffffffffu, v, 1);
+            if (lane == 0) prev = INT_MIN;
+            __syncthreads();
+            int base = carry;
+            for (int w = 0; w < (tid >> 5); w++) base = max(base, s_wmax[w]);
+            const bool rec = h < a.H && good > max(base, prev);
+            if (rec) {
+                const double ep = fmin(fmax((double)(n - good) / n, 0.0), 1.0);
+                const double den = 1.0 - pow(1.0 - ep, (double)a.m);
+                const double ld = den < ZP_DBL_MIN ? 1.0 : log(den);       // 1.0 (> 0) marks "return 0"
+                s_ld[h] = ld;
+                s_rt[h] = den < ZP_DBL_MIN ? 0 : (ld >= 0 ? INT_MAX : (int)rint(lognum / ld));
+            }
+            const unsigned bal = __ballot_sync(0xffffffffu, rec);
+            if (lane == 0) s_rec[(c0 >> 5) + (tid >> 5)] = bal;
+            for (int w = 0; w < FIN_THREADS / 32; w++) carry = max(carry, s_wmax[w]);
+            __syncthreads();
+        }
+        if (tid == 0) {
+            int best = -1, st = ZP_OK;
+            if (n_raw == 0) st = ZP_NO_MASK_PIXELS;
+            else if (n < 6) st = ZP_TOO_FEW_POINTS;       // CNN_output_to_pose.py:126
+            else {
                 int niters = max(a.H, 1);
-                for (int it = 0; it < niters && it < a.H; it++) {
-                    int good = s_hi[it];
-                    if (good > max(maxgood, a.m - 1)) {
-                        best = it; maxgood = good;
-                        niters = zp_update_iters(a.conf, (double)(n - good) / n, a.m, niters);
+                const int nwords = (a.H + 31) / 32;
+                for (int w = 0; w < nwords; w++) {
+                    unsigned bits = s_rec[w];
+                    while (bits) {
+                        const int h = 32 * w + __ffs(bits) - 1;
+                        bits &= bits - 1;
+                        if (a.select_mode == ZP_SELECT_CV2_REPLAY) {
+                            if (h >= niters) { w = nwords; break; }
+                            best = h;
+                            const double ld = s_ld[h];
+                            // cv::RANSACUpdateNumIters: den < DBL_MIN -> 0; log(den) >= 0 or -num >= maxIters * -den -> maxIters
+                            if (ld > 0.5) niters = 0;
+                            else if (!(ld >= 0 || -lognum >= niters * (-ld))) niters = s_rt[h];
+                        } else {
+                            best = h;
+                        }
                     }
                 }
-            } else {
-                for (int it = 0; it < a.H; it++)
-                    if (s_hi[it] > max(maxgood, a.m - 1)) { best = it; maxgood = s_hi[it]; }
+                if (best < 0) st = ZP_RANSAC_NO_MODEL;
             }
-            if (best < 0) st = ZP_RANSAC_NO_MODEL;
+            s_best = best; s_status = st;
+            a.status[b] = st;
+            if (a.best_idx) a.best_idx[b] = best;
+            s_first = 0x7fffffff; s_n = 0;
         }
-        s_best = best; s_status = st;
-        a.status[b] = st;
-        if (a.best_idx) a.best_idx[b] = best;
-        s_first = 0x7fffffff; s_n = 0;
     }
     for (int i = tid; i < (a.cap + 31) / 32; i += FIN_THREADS) s_mask[i] = 0;
     __syncthreads();
@@ -638,6 +710,7 @@ __global__ void __launch_bounds__(FIN_THREADS) zp_final_kernel(FinalArgs a) {
     double acc[52];
     for (int q = 0; q < 52; q++) acc[q] = 0;
     int my_n = 0, my_first = 0x7fffffff;
+#pragma unroll 4
     for (int i0 = 0; i0 < n; i0 += FIN_THREADS) {     // warp-aligned so the bitset is built with ballots
         int i = i0 + tid;
         bool in = i < n && zp_is_inlier(p0, p1, p2, pu[i] * a.inv_thr, pv[i] * a.inv_thr, pX[i], pY[i], pZ[i]);
@@ -666,6 +739,7 @@ __global__ void __launch_bounds__(FIN_THREADS) zp_final_kernel(FinalArgs a) {
     ZP_STAMP(2);
     // ---- pass 1: scatter matrix
     for (int q = 0; q < 9; q++) acc[q] = 0;
+#pragma unroll 4
     for (int i = tid; i < n; i += FIN_THREADS)
         if (s_mask[i >> 5] >> (i & 31) & 1u) {
             double d0 = pX[i] - c0[0], d1 = pY[i] - c0[1], d2 = pZ[i] - c0[2];
@@ -689,13 +763,22 @@ __global__ void __launch_bounds__(FIN_THREADS) zp_final_kernel(FinalArgs a) {
         for (int q = 0; q < 10; q++) { s.s0[q] = 0; s.sx[q] = 0; s.sy[q] = 0; s.sr[q] = 0; }
         for (int q = 0; q < 12; q++) s.w[q] = 0;
         const ZpControl cp = s_cp;
-        for (int i = tid; i < n; i += FIN_THREADS)
-            if (s_mask[i >> 5] >> (i & 31) & 1u) {
-                double X = pX[i], Y = pY[i], Z = pZ[i];
+        // the five loads of the next point are issued before the ~80 FP64 operations of the current one
+        int i = tid;
+        bool in = i < n && (s_mask[i >> 5] >> (i & 31) & 1u);
+        float fX = in ? pX[i] : 0.f, fY = in ? pY[i] : 0.f, fZ = in ? pZ[i] : 0.f, fu = in ? pu[i] : 0.f, fv = in ? pv[i] : 0.f;
+        while (i < n) {
+            const int i2 = i + FIN_THREADS;
+            const bool in2 = i2 < n && (s_mask[i2 >> 5] >> (i2 & 31) & 1u);
+            const float gX = in2 ? pX[i2] : 0.f, gY = in2 ? pY[i2] : 0.f, gZ = in2 ? pZ[i2] : 0.f, gu = in2 ? pu[i2] : 0.f, gv = in2 ? pv[i2] : 0.f;
+            if (in) {
+                double X = fX, Y = fY, Z = fZ;
                 double al[4];
                 zp_alphas(cp, X, Y, Z, al);
-                zp_accumulate(s, al, cam.uc - (double)pu[i], cam.vc - (double)pv[i], X - c0[0], Y - c0[1], Z - c0[2]);
+                zp_accumulate(s, al, cam.uc - (double)fu, cam.vc - (double)fv, X - c0[0], Y - c0[1], Z - c0[2]);
             }
+            i = i2; in = in2; fX = gX; fY = gY; fZ = gZ; fu = gu; fv = gv;
+        }
         for (int q = 0; q < 10; q++) { acc[q] = s.s0[q]; acc[10 + q] = s.sx[q]; acc[20 + q] = s.sy[q]; acc[30 + q] = s.sr[q]; }
         for (int q = 0; q < 12; q++) acc[40 + q] = s.w[q];
     }
@@ -727,13 +810,30 @@ __global__ void __launch_bounds__(FIN_THREADS) zp_final_kernel(FinalArgs a) {
     ZP_STAMP(8);
     // ---- pass 3: mean reprojection distance of the three candidates, pick the best
     for (int q = 0; q < 3; q++) acc[q] = 0;
-    for (int i = tid; i < n; i += FIN_THREADS)
-        if (s_mask[i >> 5] >> (i & 31) & 1u) {
-            double X = pX[i], Y = pY[i], Z = pZ[i], u = pu[i], v = pv[i];
+    // branch-free (a non-inlier contributes 0 through a select) so that the unrolled iterations interleave: with 8
+    // warps per SM the FP64 divide / square-root chains are latency-bound otherwise
+    {
+        double cR[3][9], ct[3][3];
+        bool cok[3];
 #pragma unroll
-            for (int c = 0; c < 3; c++)
-                if (s_candok[c]) acc[c] += zp_reproj_dist(s_candR[c], s_candt[c], cam, X, Y, Z, u, v);
+        for (int c = 0; c < 3; c++) {
+            cok[c] = s_candok[c] != 0;
+#pragma unroll
+            for (int e = 0; e < 9; e++) cR[c][e] = cok[c] ? s_candR[c][e] : (e % 4 == 0 ? 1.0 : 0.0);
+#pragma unroll
+            for (int e = 0; e < 3; e++) ct[c][e] = cok[c] ? s_candt[c][e] : (e == 2 ? 1.0 : 0.0);
         }
+#pragma unroll 2
+        for (int i = tid; i < n; i += FIN_THREADS) {
+            const bool in = s_mask[i >> 5] >> (i & 31) & 1u;
+            const double X = pX[i], Y = pY[i], Z = pZ[i], u = pu[i], v = pv[i];
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                const double dist = zp_reproj_dist(cR[c], ct[c], cam, X, Y, Z, u, v);
+                acc[c] += in ? dist : 0.0;
+            }
+        }
+    }
     block_reduce<3>(acc, s_red, s_sum);
     if (tid == 0) {
         int pick = -1;
@@ -909,7 +1009,7 @@ int zp_launch_final(zp_ctx* ctx, const float* corr, int cap, const int32_t* coun
     a.B = B; a.H = H; a.m = m; a.conf = conf; a.select_mode = select_mode; a.inv_thr = 1.0f / thr_px;
     a.final_mode = final_mode; a.poses = poses; a.n_inliers = n_inliers; a.status = status; a.best_idx = best_idx;
     a.inlier_mask = inlier_mask;
-    size_t smem = ((size_t)(cap + 31) / 32 + H) * sizeof(uint32_t);
+    size_t smem = (size_t)H * sizeof(double) + ((size_t)(cap + 31) / 32 + 2 * (size_t)H + (H + 31) / 32 + FIN_THREADS / 32) * sizeof(uint32_t);
     zp_final_kernel<<<B, FIN_THREADS, smem, st>>>(a);
     ZP_CHECK_LAUNCH(ctx, "zp_final_kernel");
     return 0;
