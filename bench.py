@@ -285,6 +285,11 @@ def main():
         except Exception:
             pass
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["zp_decode_cluster_kernel"].get(str(C))
+        except Exception:
+            pass
         dec_bytes = C * (1 + NBITS) * S * S * 4 + 20 * Mtot + 4 * C          # algorithmic HBM bytes
         dec_gbs = dec_bytes / (k_ms["zp_decode_cluster_kernel"] * 1e-3) / 1e9
         fp32_scalar = eng.fp32_peak_tflops()
@@ -320,7 +325,8 @@ def main():
             "gpu_launches": launches,
             "clocks": sampler.summary(),
             "roofline": {"kernel": "zp_decode_cluster_kernel", "bound": "hbm", "achieved": dec_gbs, "peak": hbm_peak,
-                         "unit": "GB/s", "frac": dec_gbs / hbm_peak, "traffic": None,
+                         "unit": "GB/s", "frac": dec_gbs / hbm_peak, "traffic": traffic["bytes"] if traffic else None,
+                         "traffic_source": traffic["source"] if traffic else None,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650",
                          "algorithmic_bytes_per_launch": dec_bytes, "us_per_launch": k_ms["zp_decode_cluster_kernel"] * 1e3},
             "roofline_score": {"kernel": "zp_score_kernel", "bound": "fp32", "achieved": sc_tf, "peak": fp32_peak,
