@@ -128,13 +128,18 @@ int zp_pose_batch_host(zp_ctx* ctx, const void* h_logits, int dtype, int B, int 
                        int select_mode, int final_mode,
                        double* h_poses, int32_t* h_n_inliers, int32_t* h_status);
 
-/* Test / profiling aid: pin zp_decode to one kernel family.  0 = automatic (fused register-staged kernel with
- * independent CTAs; crops of more than 16 runs of 2048 (fp32) / 4096 (bf16) pixels take the two-kernel path, layouts
- * neither can take the generic kernel), 1 = fused kernel with the compaction bases exchanged through a thread-block
- * cluster (DSMEM), 2 = generic strided kernel, 3 = fused TMA-ring streaming kernel, 4 = two kernels (plane stream ->
- * codes + mask bits, then rank/gather/emit).  All produce identical output; DESIGN.md section 4 has the measured
- * comparison. */
+/* Test / profiling aid: pin zp_decode to one kernel family.  0 = automatic (fused register-staged streaming kernel: a
+ * CTA walks several consecutive runs of 2048 fp32 / 4096 bf16 pixels of a crop and prefetches the next run under the
+ * emission of the current one; crops of more than 16 runs take the two-kernel path, layouts neither can take the
+ * generic kernel), 1 = single-run fused kernel with the compaction bases exchanged through a thread-block cluster
+ * (DSMEM), 2 = generic strided kernel, 3 = fused TMA-ring streaming kernel, 4 = two kernels (plane stream -> codes +
+ * mask bits, then rank/gather/emit), 6 = single-run fused kernel with independent CTAs; 100 + r = path 0 with r runs
+ * per CTA (100 = automatic again).  All produce identical output; DESIGN.md section 4 has the measured comparison. */
 int zp_set_decode_path(zp_ctx* ctx, int path);
+
+/* Profiling aid: when set (device pointer to 4 uint64 per decode CTA, or NULL to switch off), the fused decode kernel
+ * stores %globaltimer stamps per CTA: [0] start, [1] planes read + ranks known, [3] end (tools/dbg_decode_ctas.py). */
+int zp_debug_buffer(zp_ctx* ctx, void* dev_u64);
 
 /* Tuning aid for zp_score / zp_ransac: `groups` = warp-groups (128 threads each) per scoring CTA that split the
  * hypotheses of a work item (0 = automatic = 1, else 1, 2 or 4); `hyp_chunk` = hypotheses per work item (0 = automatic:

@@ -193,9 +193,9 @@ def test_full_size_properties(eng, tables):
                                              (5, 64, "f32", True, 0), (2, 100, "f32", False, 2), (40, 128, "bf16", True, 0),
                                              (2, 20, "f32", False, 0), (300, 32, "f32", False, 0)])
 def test_decode_paths_identical(eng, tables, B, S, dtype, ext, k):
-    """the five decode paths (two-kernel stream + emit, fused register-staged with a DSMEM cluster exchange, generic
-    strided, fused TMA-ring streaming, fused register-staged with independent CTAs) write identical lists, counts and
-    codes; crop 0 is also checked against the oracle"""
+    """the decode paths (fused streaming kernel with 1/3/8/automatic runs per CTA, single-run fused with a DSMEM cluster
+    exchange or independent CTAs, generic strided, fused TMA ring, two-kernel stream + emit) write identical lists,
+    counts and codes; crop 0 is also checked against the oracle"""
     tab, nrm = tables["nan20"]
     eng.upload_dict(6, tab, n_bits=16, ignore_bit=k)
     crops = [synth.make_crop(tab, nrm, 5000 + (i % 7), S=S) for i in range(B)]
@@ -211,7 +211,7 @@ def test_decode_paths_identical(eng, tables, B, S, dtype, ext, k):
     em = (rng.random((B, S, S)) < 0.4).astype(np.uint8) if ext else None
     outs = []
     try:
-        for path in (0, 1, 2, 3, 4):
+        for path in (0, 1, 2, 3, 4, 6, 101, 103, 108, 100):
             eng.set_decode_path(path)
             corr, counts, codes = eng.decode(lg, bboxes, obj_default=6, ignore_bit=k, ext_mask=em, return_codes=True)
             outs.append((corr.cpu().numpy(), counts.cpu().numpy(), codes.cpu().numpy()))

@@ -15,7 +15,7 @@ for C in [int(x) for x in argv] or [64, 1024]:
         flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
         flush2 = torch.zeros(64 << 20, dtype=torch.float32, device="cuda")
         clean = len(os.environ.get("ZP_CLEAN_FLUSH", "")) > 0
-        for path in (0, 4):
+        for path in (0, 6, 102, 104, 108):
             eng.set_decode_path(path)
             for _ in range(3): corr, counts = eng.decode(lg, bb, oi)
             tot = 0.0
@@ -29,4 +29,4 @@ for C in [int(x) for x in argv] or [64, 1024]:
             M = int(counts.sum())
             byts = C * 17 * 128 * 128 * lg.element_size() + 20 * M + 4 * C
             print("crops %5d %s path %d: %8.2f us  %7.1f GB/s  (%.1f%% of 6546.6)" % (C, str(dt)[6:], path, us, byts / us / 1e3, byts / us / 1e3 / 65.466))
-        eng.set_decode_path(0)
+        eng.set_decode_path(100); eng.set_decode_path(0)

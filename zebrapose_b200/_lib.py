@@ -37,6 +37,7 @@ SIGNATURES = {
     "zp_codes_to_ids": (_i, [_vp, _vp, _i64, _i, _i, _vp, _vp]),
     "zp_launch_count": (_i64, [_vp]),
     "zp_set_decode_path": (_i, [_vp, _i]),
+    "zp_debug_buffer": (_i, [_vp, _vp]),
     "zp_set_score_groups": (_i, [_vp, _i, _i]),
     "zp_debug_clocks": (_i, [_vp, _vp]),
     "zp_fp32_peak_probe": (_i, [_vp, _i, C.POINTER(_d)]),

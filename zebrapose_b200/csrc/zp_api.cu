@@ -113,10 +113,17 @@ int zp_set_score_groups(zp_ctx* ctx, int groups, int hyp_chunk) {
     return 0;
 }
 
+int zp_debug_buffer(zp_ctx* ctx, void* dev_u64) {
+    if (!ctx) return -1;
+    ctx->dbg_buf = dev_u64;
+    return 0;
+}
+
 int zp_set_decode_path(zp_ctx* ctx, int path) {
     if (!ctx) return -1;
-    if (path < 0 || path > 4) ZP_FAIL(ctx, -1, "zp_set_decode_path: path must be 0..4");
-    ctx->force_decode_path = path;
+    if (path < 0 || (path > 6 && path < 100) || path > 116) ZP_FAIL(ctx, -1, "zp_set_decode_path: path must be 0..6 or 100+runs_per_cta");
+    if (path >= 100) { ctx->force_decode_path = 0; ctx->decode_rpc = path - 100; }      // 100 = automatic again
+    else { ctx->force_decode_path = path; }
     return 0;
 }
 

@@ -39,6 +39,8 @@ struct zp_ctx {
     int64_t launches = 0;
     int score_groups = 0;                    // 0 auto, else 1 | 2 | 4 warp-groups per scoring CTA (tests / tuning)
     int score_hchunk = 0;                    // 0 auto, -1 never cut, else hypotheses per scoring work item
+    void* dbg_buf = nullptr;                 // device buffer for per-CTA timestamps of the decode kernel (zp_debug_buffer)
+    int decode_rpc = 0;                      // runs per CTA of the streaming decode kernel (0 = automatic)
     int force_decode_path = 0;               // 0 auto, 1 register-staged cluster kernel, 2 generic kernel (tests)
 };
 

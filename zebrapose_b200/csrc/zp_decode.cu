@@ -39,7 +39,14 @@ struct DecodeArgs {
     int32_t* counts;
     int32_t* chunk_counts;       // generic path only: [B, n_chunks]
     int n_chunks;
+    unsigned long long* dbg;     // nullable profiling aid: per-CTA (start, loads done, ranks done, end) %globaltimer stamps
 };
+__device__ __forceinline__ unsigned long long zp_gtimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+#define DEC_STAMP(k) do { if (a.dbg && threadIdx.x == 0) a.dbg[4 * (size_t)blockIdx.x + (k)] = zp_gtimer(); } while (0)
 
 __device__ __forceinline__ bool pos_f32(uint32_t bits) { return __uint_as_float(bits) > 0.0f; }
 // bf16 > 0  <=>  sign clear, not zero, not NaN  <=>  bits in [0x0001, 0x7F80]
@@ -149,6 +156,7 @@ __global__ void __launch_bounds__(DEC_THREADS, 2) zp_decode_cluster_kernel(Decod
     const unsigned rank = blockIdx.x - b * csize;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int S = a.S, N = S * S;
+    DEC_STAMP(0);
 
     __shared__ float s_x[1024], s_y[1024];     // remapped coordinates per column / row (S <= 1024 on this path)
     __shared__ int s_warp[DEC_WARPS];
@@ -263,6 +271,7 @@ __global__ void __launch_bounds__(DEC_THREADS, 2) zp_decode_cluster_kernel(Decod
         }
     }
 
+    DEC_STAMP(1);
     // ---- crop-wide exclusive prefix of the CTA totals
     int cta_base = 0;
     if (CLUSTER) {
@@ -284,6 +293,173 @@ __global__ void __launch_bounds__(DEC_THREADS, 2) zp_decode_cluster_kernel(Decod
                          a.corr + (size_t)b * 5 * a.cap, a.cap);
     }
     if (CLUSTER && csize > 1) cluster.barrier_wait();
+    DEC_STAMP(3);
+}
+
+// -------------------------------------------------------------------------------------------------------------
+// Default path: the fused kernel above, but a CTA walks `rpc` CONSECUTIVE runs of its crop and issues the mask + first
+// eight plane loads of run i+1 before it gathers / stages / writes run i.  Per-CTA %globaltimer stamps of the single-run
+// kernel (tools/dbg_decode_ctas.py, 64 crops) showed why it stops at 39 % of HBM peak: all 296 resident CTAs start
+// together, so they all read (8 us, HBM saturated), then all emit (3.6 us, HBM idle), then the second wave does the same:
+// the phases are in lock-step across the whole chip.  With several runs per CTA the grid fits in one wave (64 crops:
+// 256 CTAs of 2 runs) and every emit phase is covered by the next run's loads; the base of a later run is the running
+// total, so only the first run of a CTA re-counts earlier mask pixels.
+// -------------------------------------------------------------------------------------------------------------
+template <int DT, bool FULL16>
+__global__ void __launch_bounds__(DEC_THREADS, 2) zp_decode_stream_kernel(DecodeArgs a, int ctas_per_crop, int rpc, int runs_per_crop) {
+    constexpr int PPT = Px<DT>::N;
+    constexpr int ESZ = Px<DT>::ESZ;
+    const int b = blockIdx.x / ctas_per_crop;
+    const int rank0 = (blockIdx.x - b * ctas_per_crop) * rpc;            // first run of this CTA
+    const int n_runs = min(rpc, runs_per_crop - rank0);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int S = a.S, N = S * S;
+    DEC_STAMP(0);
+    __shared__ float s_x[1024], s_y[1024];
+    __shared__ int s_warp[2][DEC_WARPS];
+    __shared__ int s_pre[DEC_WARPS];
+    __shared__ int s_total[2];
+    extern __shared__ __align__(16) float s_out[];
+    const char* crop = (const char*)a.logits + (size_t)b * a.sb * ESZ;
+    const size_t plane = (size_t)a.sc * ESZ;
+    const int nb = FULL16 ? 16 : a.nb;
+    const bool own_mask = FULL16 || a.ext_mask == nullptr;
+    const int obj = a.obj_ids ? a.obj_ids[b] : a.obj_default;
+    const float4* tab = a.tables[obj];
+    float* cb = a.corr + (size_t)b * 5 * a.cap;
+
+    uint4 mv = make_uint4(0, 0, 0, 0), v[8];
+    auto issue_first = [&](int rank) {                       // mask + planes 0..7 of run `rank`
+        const int p0 = (rank * DEC_THREADS + tid) * PPT;
+        if (p0 < N) {
+            const int row = p0 / S, col = p0 - row * S;
+            const char* base = crop + ((size_t)row * a.sh + col) * ESZ;
+            if (own_mask) mv = zp_ldg_stream(base + (size_t)a.mask_ch * plane);
+#pragma unroll
+            for (int i = 0; i < 8; i++)
+                if (FULL16 || i < nb) v[i] = zp_ldg_stream(base + (size_t)(a.bit0_ch + i) * plane);
+        }
+    };
+    issue_first(rank0);
+    // masked pixels of the runs before this CTA's first one (plain loads: L2 hits, the owners stream the same lines)
+    int pre = 0;
+    for (int r = 0; r < rank0; r++) {
+        const int q0 = (r * DEC_THREADS + tid) * PPT;
+        const int qrow = q0 / S, qcol = q0 - qrow * S;
+        if (own_mask) {
+            uint4 m = __ldg((const uint4*)(crop + ((size_t)a.mask_ch * a.sc + (size_t)qrow * a.sh + qcol) * ESZ));
+            pre += __popc(positive_bits<DT>(m));
+        } else {
+            const uint8_t* em = a.ext_mask + (size_t)b * N + q0;
+#pragma unroll
+            for (int j = 0; j < PPT; j++) pre += em[j] != 0;
+        }
+    }
+    {   // per-crop coordinate LUTs (after the loads are in flight)
+        const double* bb = a.bbox + 4 * (size_t)b;
+        double x0 = bb[0], y0 = bb[1], w = bb[2], h = bb[3];
+        for (int i = tid; i < S; i += DEC_THREADS) {
+            s_x[i] = remap_coord(w, x0, S, i);
+            s_y[i] = remap_coord(h, y0, S, i);
+        }
+    }
+    pre = __reduce_add_sync(0xffffffffu, pre);
+    if (lane == 0) s_pre[warp] = pre;
+    int cta_base = -1;                                       // known after the first barrier
+
+    for (int it = 0; it < n_runs; it++) {
+        const int rank = rank0 + it;
+        const int p0 = (rank * DEC_THREADS + tid) * PPT;
+        const bool active = p0 < N;
+        const int row = active ? p0 / S : 0, col = active ? p0 - row * S : 0;
+        const char* base = crop + ((size_t)row * a.sh + col) * ESZ;
+        uint32_t mbits = 0;
+        if (active) {
+            if (own_mask) mbits = positive_bits<DT>(mv);
+            else {
+                const uint8_t* em = a.ext_mask + (size_t)b * N + p0;
+#pragma unroll
+                for (int j = 0; j < PPT; j++) mbits |= (uint32_t)(em[j] != 0) << j;
+            }
+        }
+        const int cnt = __popc(mbits);
+        int incl = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            int t = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += t;
+        }
+        if (lane == 31) s_warp[it & 1][warp] = incl;
+        // ---- pack the code while the other warps arrive
+        uint32_t code2[PPT / 2];
+#pragma unroll
+        for (int j = 0; j < PPT / 2; j++) code2[j] = 0;
+        if (active) {
+#pragma unroll
+            for (int i = 0; i < 8; i++)
+                if (FULL16 || i < nb) or_plane_bits<DT>(v[i], 0x80008000u >> i, code2);
+            if (FULL16 || nb > 8) {
+#pragma unroll
+                for (int i = 0; i < 8; i++)
+                    if (FULL16 || 8 + i < nb) v[i] = zp_ldg_stream(base + (size_t)(a.bit0_ch + 8 + i) * plane);
+#pragma unroll
+                for (int i = 0; i < 8; i++)
+                    if (FULL16 || 8 + i < nb) or_plane_bits<DT>(v[i], 0x00800080u >> i, code2);
+            }
+            const int sh = 16 - nb;
+#pragma unroll
+            for (int j = 0; j < PPT / 2; j++) code2[j] = (code2[j] >> sh) & (0xFFFFu >> sh) * 0x00010001u;
+            if (a.codes) {
+                uint16_t* cp = a.codes + (size_t)b * N + p0;
+                if (PPT == 4) *(uint2*)cp = make_uint2(code2[0], code2[1]);
+                else *(uint4*)cp = make_uint4(code2[0], code2[1], code2[2 % (PPT / 2)], code2[3 % (PPT / 2)]);
+            }
+        }
+        if (it + 1 < n_runs) issue_first(rank + 1);          // next run's loads fly during this run's emit
+        __syncthreads();                                      // warp totals (and, first time, s_pre and the LUTs) visible
+        int wbase = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < DEC_WARPS; w++) {
+            const int t = s_warp[it & 1][w];
+            wbase += w < warp ? t : 0;
+            total += t;
+        }
+        if (cta_base < 0) {
+            cta_base = 0;
+#pragma unroll
+            for (int w = 0; w < DEC_WARPS; w++) cta_base += s_pre[w];
+        }
+        if (it == 0) DEC_STAMP(1);
+        emit_staged<PPT>(s_out, mbits, code2, wbase + incl - cnt, tab, s_x, col, s_y[row], total, cta_base, cb, a.cap);
+        cta_base += total;
+        __syncthreads();                                      // s_out is reused by the next run
+    }
+    if (rank0 + n_runs == runs_per_crop && tid == 0) a.counts[b] = cta_base;
+    DEC_STAMP(3);
+}
+
+template <int DT>
+static int launch_stream(zp_ctx* ctx, const DecodeArgs& a, int runs, cudaStream_t st) {
+    const int smem = 5 * DEC_THREADS * Px<DT>::N * (int)sizeof(float);
+    static bool attr_set = false;
+    if (!attr_set) {
+        ZP_CUDA(ctx, cudaFuncSetAttribute(zp_decode_stream_kernel<DT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        ZP_CUDA(ctx, cudaFuncSetAttribute(zp_decode_stream_kernel<DT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_set = true;
+    }
+    // runs per CTA: the smallest count that brings the grid into one wave of 2 CTAs per SM, but at most 4 (measured at
+    // 1024 crops: 1 run 71 %, 2 runs 75.5 %, 4 runs 77.8 %, 8 runs 68 % of HBM peak -- long CTAs lose to the tail)
+    const int slots = 2 * ctx->sm_count;
+    int rpc = ctx->decode_rpc > 0 ? ctx->decode_rpc : 1;
+    if (ctx->decode_rpc <= 0)
+        while (rpc < runs && rpc < 4 && 2 * (rpc + 1) <= runs && (long long)a.B * ((runs + rpc - 1) / rpc) > slots) rpc++;   // >= 2 CTAs per crop
+    if (rpc > runs) rpc = runs;
+    const int cpc = (runs + rpc - 1) / rpc;
+    const bool full16 = a.nb == 16 && a.ext_mask == nullptr;
+    if (full16) zp_decode_stream_kernel<DT, true><<<(unsigned)(a.B * cpc), DEC_THREADS, smem, st>>>(a, cpc, rpc, runs);
+    else zp_decode_stream_kernel<DT, false><<<(unsigned)(a.B * cpc), DEC_THREADS, smem, st>>>(a, cpc, rpc, runs);
+    ZP_CHECK_LAUNCH(ctx, "zp_decode_stream_kernel");
+    return 0;
 }
 
 // -------------------------------------------------------------------------------------------------------------
@@ -834,6 +1010,7 @@ int zp_launch_decode(zp_ctx* ctx, const void* logits, int dtype, int B, int S, c
     a.tables = (const float4* const*)ctx->d_table_ptrs;
     a.codes = codes; a.corr = corr; a.cap = cap; a.counts = counts;
     a.chunk_counts = nullptr; a.n_chunks = 0;
+    a.dbg = (unsigned long long*)ctx->dbg_buf;
     const int ppt = dtype == ZP_DTYPE_F32 ? 4 : 8;
     const int esz = dtype == ZP_DTYPE_F32 ? 4 : 2;
     const int N = S * S;
@@ -865,6 +1042,10 @@ int zp_launch_decode(zp_ctx* ctx, const void* logits, int dtype, int B, int S, c
     if (split_ok && (ctx->force_decode_path == 4 || (ctx->force_decode_path == 0 && !vec_ok))) {
         if (dtype == ZP_DTYPE_F32) return launch_split<ZP_DTYPE_F32>(ctx, a, st);
         return launch_split<ZP_DTYPE_BF16>(ctx, a, st);
+    }
+    if (vec_ok && ctx->force_decode_path == 0) {
+        if (dtype == ZP_DTYPE_F32) return launch_stream<ZP_DTYPE_F32>(ctx, a, ctas, st);
+        return launch_stream<ZP_DTYPE_BF16>(ctx, a, ctas, st);
     }
     if (vec_ok && ctx->force_decode_path != 2) {
         const bool use_cluster = ctx->force_decode_path == 1;

@@ -76,8 +76,8 @@ class Engine:
         return pts, remap
 
     def set_decode_path(self, path):
-        """0 auto (fused, independent CTAs) | 1 fused, cluster exchange | 2 generic strided | 3 fused TMA ring | 4 two
-        kernels (stream + emit) -- identical results (include/zebrapose_b200.h)"""
+        """0 auto (fused streaming kernel) | 1 single-run fused, cluster exchange | 2 generic strided | 3 fused TMA ring |
+        4 two kernels | 6 single-run fused, independent CTAs | 100+r: r runs per CTA -- identical results"""
         self.ctx.check(self.lib.zp_set_decode_path(self.ctx.handle, int(path)), "zp_set_decode_path")
 
     def set_score_groups(self, groups=0, hyp_chunk=0):
