@@ -91,8 +91,8 @@ def test_common_ops_threshold(golden):
     assert ours.dtype == np.float64 and ours.shape == ref.shape
     assert np.array_equal(ours[~tiny], ref[~tiny])
     assert np.array_equal(common_ops.from_output_to_class_binary_code(x, "BCE")[~tiny], golden["thr_code"][~tiny])
-    with pytest.raises(NotImplementedError):
-        common_ops.from_output_to_class_binary_code(x, "CE")
+    with pytest.raises(ValueError):
+        common_ops.from_output_to_class_binary_code(x, "focal")
 
 
 def test_shard_range():
@@ -134,3 +134,17 @@ def test_gather_gloo_world2(tmp_path, n):
                               stderr=subprocess.STDOUT, text=True) for r in range(2)]
     outs = [p.communicate(timeout=120)[0] for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
+
+
+def test_common_ops_ce_branch():
+    """CE heads (softmax over channel groups + argmax, common_ops.py:21-30) against the reference's own outputs,
+    including exact ties, 1-ulp differences and saturated softmax; base 2 and base 3"""
+    import torch
+    from zebrapose_b200 import common_ops
+    g = np.load(os.path.join(ROOT, "tests", "golden", "golden_ce_v1.npz"))
+    got = common_ops.from_output_to_class_binary_code(torch.from_numpy(g["ce_in"]), "CE", divided_num_each_interation=2,
+                                                      binary_code_length=16)
+    assert got.shape == g["ce_code_16"].shape and np.array_equal(got, g["ce_code_16"])
+    got3 = common_ops.from_output_to_class_binary_code(torch.from_numpy(g["ce_in_b3"]), "CE", divided_num_each_interation=3,
+                                                       binary_code_length=8)
+    assert np.array_equal(got3, g["ce_code_b3"]) and got3.max() == 2

@@ -1,6 +1,9 @@
-"""Mirror of zebrapose/common_ops.py:5-19 (BCE / L1 branch).  The reference pulls all logits to the host and
-thresholds there; here the comparison runs on the device the logits already live on and only the {0,1} result is
-copied.  sigmoid(x) > t  <=>  x > log(t / (1 - t)); for t = 0.5 that is float32(x) > 0.
+"""Mirror of zebrapose/common_ops.py:5-30.  The reference pulls all logits to the host and thresholds there; here the
+comparison runs on the device the logits already live on and only the {0,1} result is copied.
+BCE / L1 heads: sigmoid(x) > t  <=>  x > log(t / (1 - t)); for t = 0.5 that is float32(x) > 0.
+CE heads (ablation configs, class_base = divided_num_each_interation): softmax over each group of `base` consecutive
+channels, argmax (first maximum on ties) -- the same torch softmax the reference applies, on the tensor's device, then
+argmax there instead of on the host.
 The batched path (Engine.decode_and_pose_batch) never calls these: its decode kernel thresholds in registers."""
 import math
 
@@ -22,8 +25,13 @@ def from_output_to_class_binary_code(pred_code_prob, BinaryCode_Loss_Type, thers
                                      binary_code_length=16):
     if BinaryCode_Loss_Type in ("BCE", "L1"):
         return _threshold(pred_code_prob, thershold)
-    raise NotImplementedError("BinaryCode_Loss_Type %r: only the binary (BCE / L1) heads are on the B200 path; the CE "
-                              "ablation branch (common_ops.py:21-30) is out of scope" % (BinaryCode_Loss_Type,))
+    if BinaryCode_Loss_Type == "CE":                  # common_ops.py:21-30
+        x = pred_code_prob.detach()
+        base = int(divided_num_each_interation)
+        p = torch.softmax(x.reshape(-1, base, x.shape[2], x.shape[3]), dim=1)
+        code = torch.argmax(p, dim=1, keepdim=True)   # first maximal index, as numpy.argmax
+        return code.reshape(-1, int(binary_code_length), x.shape[2], x.shape[3]).cpu().numpy()
+    raise ValueError("unknown BinaryCode_Loss_Type %r" % (BinaryCode_Loss_Type,))
 
 
 def get_batch_size(second_dataset_ratio, batch_size):
