@@ -42,6 +42,10 @@ enum { ZP_FINAL_EPNP = 0, ZP_FINAL_EPNP_GN = 1 };
 /* per-crop status written by zp_ransac */
 enum { ZP_OK = 0, ZP_NO_MASK_PIXELS = 1, ZP_TOO_FEW_POINTS = 2, ZP_RANSAC_NO_MODEL = 3 };
 
+/* resize_method of get_final_Bbox (bop_dataset_pytorch.py:169,184; config key `resize_method`) */
+/* ZP_CROP_KEEP: no final step (padding_Bbox only; get_final_Bbox returns the box unchanged for any other string). */
+enum { ZP_CROP_RESIZE = 0, ZP_CROP_SQUARE_RESIZE = 1, ZP_CROP_RESIZE_BY_WARP_AFFINE = 2, ZP_CROP_KEEP = 3 };
+
 #define ZP_MAX_OBJECTS 256
 #define ZP_MAX_HYPOTHESES 1024
 
@@ -173,6 +177,28 @@ int zp_debug_clocks(zp_ctx* ctx, int64_t* out24);
 int zp_fp32_peak_probe(zp_ctx* ctx, int iters, double* out_tflops);
 /* Same with packed FFMA2 (fma.rn.f32x2) chains: the form zp_score_kernel uses. */
 int zp_fp32x2_peak_probe(zp_ctx* ctx, int iters, double* out_tflops);
+
+/* ---- the steps either side of the pose path ---- */
+
+/* Replaces padding_Bbox + get_final_Bbox (bop_dataset_pytorch.py:123-139, 162-194; called per detection at
+ * test_vivo.py:147-150 and in the dataset's __getitem__) for B detection boxes at once, on the device, so the crop box
+ * zp_decode consumes never visits the host.  det_boxes double [B,4] = x, y, w, h; padding_ratio <= 0 skips padding_Bbox;
+ * max_x / max_y are the image bounds of the "crop_resize" clamp.  out_boxes double [B,4] (integral values): float64
+ * arithmetic with truncation toward zero exactly as the reference's int(). */
+int zp_final_bbox(zp_ctx* ctx, const double* det_boxes, int B, double padding_ratio, int resize_method,
+                  double max_x, double max_y, double* out_boxes, void* stream);
+
+/* Model vertices of object slot `obj_id` for the pose-error metrics: HOST double [V][3] in mm (the `vertices` argument
+ * of metric.py:8-18).  Synchronises. */
+int zp_upload_model(zp_ctx* ctx, int obj_id, const double* pts_xyz, int V);
+
+/* Replaces Calculate_ADD_Error_BOP / Calculate_ADI_Error_BOP (metric.py:8-18 -> pose_error.add / adi,
+ * lib/pysixd/pose_error.py:297-336; evaluated per crop at test.py:465-483) for B pose pairs at once.
+ * poses_est / poses_gt double [B,12] (R row-major | t in mm); obj_ids nullable int32 [B] model slot per pair.
+ * add_out / adi_out double [B], either may be NULL.  ADD is float64; ADI is the exact nearest neighbour (brute force
+ * instead of the reference's cKDTree) on float32 squared distances of points recentred by -t_est. */
+int zp_pose_errors(zp_ctx* ctx, const double* poses_est, const double* poses_gt, const int32_t* obj_ids,
+                   int obj_default, int B, double* add_out, double* adi_out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,126 @@
+"""GPU: the steps either side of the pose path through the C ABI (zp_final_bbox, zp_upload_model, zp_pose_errors)
+against the fixtures produced by the reference's own functions and against the CPU oracle.
+
+Tolerances: crop boxes bit-exact (integer results of float64 expressions).  ADD: float64 on both sides, only the
+summation order differs -> relative 1e-12.  ADI: exact nearest neighbour on float32 squared distances of points
+recentred by -t_est (|coordinate| <= object radius) -> absolute 1e-4 mm (measured ~1e-5)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import evalside, metrics, synth_eval
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ADD_RTOL, ADI_ATOL = 1e-12, 1e-4
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return np.load(os.path.join(ROOT, "tests", "golden", "golden_eval_v1.npz"), allow_pickle=False)
+
+
+@pytest.fixture(scope="module")
+def eng():
+    import zebrapose_b200 as zp
+    return zp.Engine(0)
+
+
+def test_boxes_match_reference(eng, gold):
+    boxes = synth_eval.make_boxes(synth_eval.N_BOXES, 7)
+    inp = boxes.copy()
+    inp[::2] = inp[::2].astype(np.int64)              # even rows were given to the reference as int arrays
+    for ratio in synth_eval.PAD_RATIOS:
+        pad = eng.final_bboxes(inp, ratio, "none").cpu().numpy()
+        assert np.array_equal(pad, gold["box_pad_%g" % ratio].astype(np.float64))
+        for method in synth_eval.METHODS:
+            fin = eng.final_bboxes(inp, ratio, method, 640, 480).cpu().numpy()
+            assert np.array_equal(fin, gold["box_final_%g_%s" % (ratio, method)].astype(np.float64)), (ratio, method)
+    for method in synth_eval.METHODS:
+        fin = eng.final_bboxes(inp, 0.0, method, 640, 480).cpu().numpy()
+        assert np.array_equal(fin, gold["box_finalonly_%s" % method]), method
+
+
+def test_boxes_large_batch_vs_oracle(eng):
+    boxes = synth_eval.make_boxes(20000, 99)
+    fin = eng.final_bboxes(boxes, 1.5, "crop_square_resize", 640, 480).cpu().numpy()
+    idx = np.random.default_rng(0).integers(0, len(boxes), 500)
+    want = np.array([evalside.final_box(evalside.padding_box(boxes[i], 1.5), "crop_square_resize", 640, 480) for i in idx])
+    assert np.array_equal(fin[idx], want.astype(np.float64))
+    assert eng.final_bboxes(np.zeros((0, 4)), 1.5).shape == (0, 4)
+
+
+def test_box_wrappers_keep_reference_signatures(eng):
+    from zebrapose_b200 import crop_boxes
+    b = np.array([100, 120, 37, 81])
+    p = crop_boxes.padding_Bbox(b, 1.5)
+    assert p.tolist() == evalside.padding_box(b, 1.5)
+    f = crop_boxes.get_final_Bbox(p, "crop_square_resize", 640, 480)
+    assert f.tolist() == evalside.final_box(p, "crop_square_resize", 640, 480)
+    assert crop_boxes.get_final_Bbox(p, "unknown", 640, 480) is p
+
+
+@pytest.mark.parametrize("tag,V,seed", synth_eval.MODELS)
+def test_pose_errors_match_reference(eng, gold, tag, V, seed):
+    pts = synth_eval.make_model(V, seed)
+    est, gt = synth_eval.make_pose_pairs(synth_eval.N_PAIRS, seed + 1)
+    eng.upload_model(3, pts)
+    add, adi = eng.pose_errors(est, gt, obj_default=3)
+    add, adi = add.cpu().numpy(), adi.cpu().numpy()
+    np.testing.assert_allclose(add, gold["err_%s_add" % tag], rtol=ADD_RTOL, atol=1e-12)
+    np.testing.assert_allclose(adi, gold["err_%s_adi" % tag], rtol=0, atol=ADI_ATOL)
+    assert add[0] == 0.0 and adi[0] == 0.0
+    only_add, none = eng.pose_errors(est, gt, obj_default=3, adi=False)
+    assert none is None and torch.equal(only_add.cpu(), torch.from_numpy(add))
+
+
+def test_pose_errors_batched_objects_and_splits(eng):
+    """a batch mixing objects of different sizes (obj_ids), large enough that the target set is NOT split, must agree
+    with the same pairs evaluated one by one (target set split over many CTAs, merged with atomicMin)"""
+    models = {0: synth_eval.make_model(700, 5), 1: synth_eval.make_model(4099, 6), 2: synth_eval.make_model(2048, 7)}
+    for k, v in models.items():
+        eng.upload_model(k, v)
+    B = 300
+    est, gt = synth_eval.make_pose_pairs(B, 31)
+    obj = np.random.default_rng(1).integers(0, 3, B).astype(np.int32)
+    add, adi = eng.pose_errors(est, gt, obj)
+    add, adi = add.cpu().numpy(), adi.cpu().numpy()
+    for i in range(0, B, 17):
+        a1, s1 = eng.pose_errors(est[i:i + 1], gt[i:i + 1], obj[i:i + 1])
+        assert a1.item() == add[i] and s1.item() == adi[i]
+        e, g = est[i], gt[i]
+        wa = metrics.add(e[:9].reshape(3, 3), e[9:], g[:9].reshape(3, 3), g[9:], models[int(obj[i])])
+        ws = metrics.adi(e[:9].reshape(3, 3), e[9:], g[:9].reshape(3, 3), g[9:], models[int(obj[i])])
+        assert abs(add[i] - wa) <= ADD_RTOL * max(1.0, wa) and abs(adi[i] - ws) <= ADI_ATOL, (i, add[i], wa, adi[i], ws)
+
+
+def test_pose_errors_edge_cases(eng):
+    import zebrapose_b200 as zp
+    pts = synth_eval.make_model(5, 1)                   # fewer vertices than one SIMD quad + padding
+    eng.upload_model(9, pts)
+    est, gt = synth_eval.make_pose_pairs(3, 2)
+    est[1, 4] = np.nan                                   # failed crop upstream: NaN pose -> NaN errors (test.py:467-468 maps NaN to 10000)
+    add, adi = eng.pose_errors(est, gt, obj_default=9)
+    add, adi = add.cpu().numpy(), adi.cpu().numpy()
+    assert np.isnan(add[1]) and np.isnan(adi[1])
+    for i in (0, 2):
+        e, g = est[i], gt[i]
+        assert abs(adi[i] - metrics.adi(e[:9].reshape(3, 3), e[9:], g[:9].reshape(3, 3), g[9:], pts)) <= ADI_ATOL
+    with pytest.raises(zp.ZpError):
+        eng.pose_errors(est, gt, obj_default=77)         # no model in that slot
+    a0, s0 = eng.pose_errors(np.zeros((0, 12)), np.zeros((0, 12)), obj_default=9)
+    assert a0.shape == (0,) and s0.shape == (0,)
+
+
+def test_metric_wrappers_keep_reference_signatures(eng, gold):
+    from zebrapose_b200 import metric
+    tag, V, seed = synth_eval.MODELS[0]
+    pts = synth_eval.make_model(V, seed)
+    est, gt = synth_eval.make_pose_pairs(synth_eval.N_PAIRS, seed + 1)
+    i = 3
+    Rg, tg, Re, te = gt[i, :9].reshape(3, 3), gt[i, 9:], est[i, :9].reshape(3, 3), est[i, 9:].reshape(3, 1)
+    a = metric.Calculate_ADD_Error_BOP(Rg, tg, Re, te, pts)
+    s = metric.Calculate_ADI_Error_BOP(Rg, tg, Re, te, pts)
+    assert abs(a - gold["err_%s_add" % tag][i]) <= ADD_RTOL * a and abs(s - gold["err_%s_adi" % tag][i]) <= ADI_ATOL

@@ -1,0 +1,65 @@
+"""CPU: the evaluation-side restatements (oracle/metrics.py ADD / ADI, oracle/evalside.py boxes + csv) and the pure-Python
+csv mirror against the fixtures produced by the reference's own functions (tests/golden/make_golden_eval.py)."""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+from oracle import evalside, metrics, synth_eval
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return np.load(os.path.join(ROOT, "tests", "golden", "golden_eval_v1.npz"), allow_pickle=False)
+
+
+def _sha(*arrs):
+    h = hashlib.sha256()
+    for a in arrs:
+        h.update(np.ascontiguousarray(a).tobytes())
+    return h.hexdigest()
+
+
+@pytest.mark.parametrize("tag,V,seed", synth_eval.MODELS)
+def test_add_adi_oracle_matches_reference(gold, tag, V, seed):
+    pts = synth_eval.make_model(V, seed)
+    est, gt = synth_eval.make_pose_pairs(synth_eval.N_PAIRS, seed + 1)
+    assert _sha(pts, est, gt) == str(gold["err_%s_sha" % tag]), "synthetic generator drifted: regenerate the fixture"
+    for i, (e, g) in enumerate(zip(est, gt)):
+        a = metrics.add(e[:9].reshape(3, 3), e[9:], g[:9].reshape(3, 3), g[9:], pts)
+        s = metrics.adi(e[:9].reshape(3, 3), e[9:], g[:9].reshape(3, 3), g[9:], pts)
+        assert a == gold["err_%s_add" % tag][i]          # same numpy expression: bit-identical
+        assert s == gold["err_%s_adi" % tag][i]
+    assert gold["err_%s_add" % tag][0] == 0.0 and gold["err_%s_adi" % tag][0] == 0.0      # identical pose pair
+
+
+def test_boxes_oracle_matches_reference(gold):
+    boxes = synth_eval.make_boxes(synth_eval.N_BOXES, 7)
+    assert _sha(boxes) == str(gold["box_sha"])
+    for ratio in synth_eval.PAD_RATIOS:
+        pad = np.array([evalside.padding_box(b, ratio) for b in boxes])
+        assert np.array_equal(pad, gold["box_pad_%g" % ratio])
+        for method in synth_eval.METHODS:
+            fin = np.array([evalside.final_box(p, method, 640, 480) for p in pad])
+            assert np.array_equal(fin, gold["box_final_%g_%s" % (ratio, method)]), (ratio, method)
+    for method in synth_eval.METHODS:
+        fin = np.array([evalside.final_box(b, method, 640, 480) for b in boxes], np.float64)
+        assert np.array_equal(fin, gold["box_finalonly_%s" % method]), method
+    assert evalside.final_box([1, 2, 3, 4], "something_else", 640, 480) == [1, 2, 3, 4]
+
+
+def test_csv_matches_reference(gold, tmp_path):
+    scene, img, Rs, ts, scores = synth_eval.make_csv_rows(9)
+    want = str(gold["csv_text"])
+    assert evalside.bop_csv_text(1, scene, img, Rs, ts, scores) == want
+    from zebrapose_b200.tools_for_BOP import write_to_cvs
+    write_to_cvs.write_cvs(str(tmp_path), "lmo_ape", 1, scene, img, Rs, ts, scores)
+    assert open(tmp_path / "lmo_ape.csv").read() == want
+    assert want.count("\n") == 1 + sum(1 for s in scores if s != -1)
+    # batched form: same rows from [B,12] records
+    poses = np.array([np.concatenate([np.asarray(r).ravel(), np.asarray(t).ravel()]) for r, t in zip(Rs, ts)])
+    write_to_cvs.write_batch(str(tmp_path), "batch", 1, scene, img, poses, scores)
+    assert open(tmp_path / "batch.csv").read() == want

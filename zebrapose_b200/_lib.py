@@ -11,6 +11,7 @@ NONEXIST = {"zero": 0, "hamming": 1}
 SAMPLER = {"cv2": 0, "philox": 1}
 SELECT = {"cv2_replay": 0, "argmax": 1}
 FINAL = {"epnp": 0, "epnp+gn": 1}
+RESIZE = {"crop_resize": 0, "crop_square_resize": 1, "crop_resize_by_warp_affine": 2, "none": 3}
 STATUS_OK, STATUS_NO_MASK, STATUS_TOO_FEW, STATUS_NO_MODEL = 0, 1, 2, 3
 
 _vp, _i, _i64, _u64, _f, _d = C.c_void_p, C.c_int, C.c_int64, C.c_uint64, C.c_float, C.c_double
@@ -42,6 +43,9 @@ SIGNATURES = {
     "zp_debug_clocks": (_i, [_vp, _vp]),
     "zp_fp32_peak_probe": (_i, [_vp, _i, C.POINTER(_d)]),
     "zp_fp32x2_peak_probe": (_i, [_vp, _i, C.POINTER(_d)]),
+    "zp_final_bbox": (_i, [_vp, _vp, _i, _d, _i, _d, _d, _vp, _vp]),
+    "zp_upload_model": (_i, [_vp, _i, _vp, _i]),
+    "zp_pose_errors": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp]),
 }
 
 _lib = None

@@ -96,6 +96,10 @@ void zp_destroy(zp_ctx* ctx) {
     if (ctx->ws) cudaFree(ctx->ws);
     if (ctx->hws) cudaFree(ctx->hws);
     if (ctx->dws) cudaFree(ctx->dws);
+    for (auto& m : ctx->models) if (m.pts) cudaFree(m.pts);
+    if (ctx->d_model_ptrs) cudaFree((void*)ctx->d_model_ptrs);
+    if (ctx->d_model_V) cudaFree(ctx->d_model_V);
+    if (ctx->ews) cudaFree(ctx->ews);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }

@@ -17,6 +17,11 @@ struct ZpTable {
     int n_bits = 0, ignore_bit = 0, mode = 0;
 };
 
+struct ZpModel {
+    double* pts = nullptr;      // [V][3] model vertices in mm (float64, as pose_error.add/adi get them)
+    int V = 0;
+};
+
 struct zp_ctx {
     int device = 0;
     int sm_count = ZP_SM_COUNT_FALLBACK;
@@ -35,6 +40,12 @@ struct zp_ctx {
     // decode workspace of the two-kernel path (codes when the caller does not want them, mask ballot words)
     void* dws = nullptr;
     size_t dws_bytes = 0;
+    // evaluation (zp_eval.cu): model vertices per object slot + workspace of zp_pose_errors
+    ZpModel models[ZP_MAX_OBJECTS];
+    const double** d_model_ptrs = nullptr;   // device array [ZP_MAX_OBJECTS]
+    int* d_model_V = nullptr;                // device array [ZP_MAX_OBJECTS]
+    void* ews = nullptr;
+    size_t ews_bytes = 0;
     cudaStream_t own_stream = nullptr;
     int64_t launches = 0;
     int score_groups = 0;                    // 0 auto, else 1 | 2 | 4 warp-groups per scoring CTA (tests / tuning)

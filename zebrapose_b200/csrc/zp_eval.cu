@@ -1,0 +1,335 @@
+// The two steps either side of the pose path, batched on the device:
+//   * zp_final_bbox   = padding_Bbox + get_final_Bbox (zebrapose/bop_dataset_pytorch.py:123-139, 162-194): the crop box
+//                       the decode kernel consumes, computed from detection boxes without leaving the GPU;
+//   * zp_pose_errors  = ADD and ADI (zebrapose/lib/pysixd/pose_error.py:297-336 through zebrapose/metric.py:8-18,
+//                       evaluated per crop at zebrapose/test.py:465-483) of B pose pairs against the model vertices.
+// ADD is float64 like the reference.  ADI replaces the reference's cKDTree by an exact brute-force nearest neighbour:
+// every (ground-truth point, estimated point) pair is one FP32 squared distance on packed FFMA2/FADD2 pairs; the
+// points are translated by -t_est in float64 before the float32 rounding so their magnitude is the object's radius
+// (|error| of a distance <= ~2e-5 mm for a 150 mm object; the tolerance is written in tests/test_gpu_eval.py).
+#include <algorithm>
+#include <cmath>
+#include "zp_common.cuh"
+
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 ev_fma2(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ f32x2 ev_mul2(f32x2 a, f32x2 b) {
+    f32x2 d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ f32x2 ev_sub2(f32x2 a, f32x2 b) {
+    f32x2 d;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ f32x2 ev_dup(float x) {
+    return (f32x2)__float_as_uint(x) | ((f32x2)__float_as_uint(x) << 32);
+}
+__device__ __forceinline__ float ev_lo(f32x2 v) { return __uint_as_float((uint32_t)v); }
+__device__ __forceinline__ float ev_hi(f32x2 v) { return __uint_as_float((uint32_t)(v >> 32)); }
+
+// ---------------------------------------------------------------------------------------------------------------
+// crop boxes
+// ---------------------------------------------------------------------------------------------------------------
+// Python's int() on a float truncates toward zero; all arithmetic below is the reference's float64 expression tree.
+__device__ __forceinline__ double ev_trunc(double x) { return (double)__double2ll_rz(x); }
+
+__global__ void zp_bbox_kernel(const double* __restrict__ in, int B, double pad_ratio, int method, double max_x,
+                               double max_y, double* __restrict__ out) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    double bx = in[4 * b], by = in[4 * b + 1], bw = in[4 * b + 2], bh = in[4 * b + 3];
+    if (pad_ratio > 0) {   // padding_Bbox (bop_dataset_pytorch.py:123-139)
+        double x1 = bx, x2 = bx + bw, y1 = by, y2 = by + bh;
+        double cx = 0.5 * (x1 + x2), cy = 0.5 * (y1 + y2);
+        double h = y2 - y1, w = x2 - x1;
+        double pw = ev_trunc(w * pad_ratio), ph = ev_trunc(h * pad_ratio);
+        bx = ev_trunc(cx - pw / 2); by = ev_trunc(cy - ph / 2); bw = pw; bh = ph;
+    }
+    // get_final_Bbox (bop_dataset_pytorch.py:162-194)
+    double x1 = bx, x2 = bx + bw, y1 = by, y2 = by + bh;
+    if (method == ZP_CROP_SQUARE_RESIZE || method == ZP_CROP_RESIZE_BY_WARP_AFFINE) {
+        double cx = 0.5 * (x1 + x2), cy = 0.5 * (y1 + y2);
+        if (bh > bw) { x1 = cx - bh / 2; x2 = cx + bh / 2; }
+        else { y1 = cy - bw / 2; y2 = cy + bw / 2; }
+        x1 = ev_trunc(x1); y1 = ev_trunc(y1); x2 = ev_trunc(x2); y2 = ev_trunc(y2);
+        bx = x1; by = y1; bw = x2 - x1; bh = y2 - y1;
+    } else if (method == ZP_CROP_RESIZE) {
+        x1 = fmax(x1, 0.0); y1 = fmax(y1, 0.0); x2 = fmin(x2, max_x); y2 = fmin(y2, max_y);
+        x1 = ev_trunc(x1); y1 = ev_trunc(y1); x2 = ev_trunc(x2); y2 = ev_trunc(y2);
+        bx = x1; by = y1; bw = x2 - x1; bh = y2 - y1;
+    }
+    out[4 * b] = bx; out[4 * b + 1] = by; out[4 * b + 2] = bw; out[4 * b + 3] = bh;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// ADD / ADI
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int EV_PREP_THREADS = 256;
+constexpr int EV_THREADS = 128;          // ADI: threads per CTA
+constexpr int EV_Q = 4;                  // query (ground-truth) points per thread, in registers
+constexpr int EV_QTILE = EV_THREADS * EV_Q;
+constexpr int EV_CHUNK = 2048;           // target (estimated) points staged in shared memory at a time (24 KB)
+constexpr float EV_FAR = 1.0e18f;        // padding coordinate: squared distance 1e36 stays finite in float32
+constexpr float EV_INIT = 3.0e38f;
+
+struct ErrArgs {
+    const double* est; const double* gt;          // [B,12] R row-major | t
+    const int32_t* obj_ids; int obj_default;
+    const double* const* model_ptrs; const int* model_V;
+    int B, Vs;                                    // Vs = plane stride of E/G (multiple of 4)
+    float* E; float* G;                           // [B][3][Vs]: R_e p  and  R_g p + (t_g - t_e), float32
+    double* add_partial; int n_prep_blocks;       // [B][n_prep_blocks]
+    uint32_t* qmin;                               // [B][Vs] float32 bit patterns of the smallest squared distance per query
+    int nsplit, tlen;                             // target ranges per crop (tlen multiple of 4)
+    double* add_out; double* adi_out;
+};
+
+__device__ __forceinline__ double ev_block_sum(double v, double* s_red) {
+    // fixed-shape tree: warp shuffles, then warp 0 over the per-warp sums (deterministic for a given launch shape)
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    __syncthreads();
+    if (lane == 0) s_red[w] = v;
+    __syncthreads();
+    double r = 0;
+    if (w == 0) {
+        r = lane < nw ? s_red[lane] : 0.0;
+        for (int o = 16; o > 0; o >>= 1) r += __shfl_down_sync(0xffffffffu, r, o);
+    }
+    return r;            // valid on thread 0
+}
+
+// One thread per (crop, vertex): both rigid transforms in float64 (pose_error.py:308-309, misc.py:895-905), the ADD
+// term ||p_est - p_gt||, and the float32 point sets of the ADI search.
+__global__ void __launch_bounds__(EV_PREP_THREADS)
+zp_err_prepare_kernel(ErrArgs a) {
+    __shared__ double s_red[EV_PREP_THREADS / 32];
+    const int b = blockIdx.y;
+    const int obj = a.obj_ids ? a.obj_ids[b] : a.obj_default;
+    const bool okobj = obj >= 0 && obj < ZP_MAX_OBJECTS && a.model_ptrs[obj] != nullptr;
+    const int V = okobj ? a.model_V[obj] : 0;
+    const int i = blockIdx.x * EV_PREP_THREADS + threadIdx.x;
+    double term = 0;
+    if (i < V) {
+        const double* p = a.model_ptrs[obj] + 3 * (size_t)i;
+        const double x = p[0], y = p[1], z = p[2];
+        const double* e = a.est + 12 * (size_t)b;
+        const double* g = a.gt + 12 * (size_t)b;
+        double re[3], rg[3], d2 = 0;
+#pragma unroll
+        for (int r = 0; r < 3; r++) {
+            re[r] = e[3 * r] * x + e[3 * r + 1] * y + e[3 * r + 2] * z;
+            rg[r] = g[3 * r] * x + g[3 * r + 1] * y + g[3 * r + 2] * z;
+            const double d = (re[r] + e[9 + r]) - (rg[r] + g[9 + r]);
+            d2 += d * d;
+        }
+        term = sqrt(d2);
+        if (a.E) {
+#pragma unroll
+            for (int r = 0; r < 3; r++) {
+                a.E[((size_t)b * 3 + r) * a.Vs + i] = (float)re[r];
+                a.G[((size_t)b * 3 + r) * a.Vs + i] = (float)(rg[r] + (g[9 + r] - e[9 + r]));
+            }
+        }
+    } else if (i < a.Vs && a.E) {
+#pragma unroll
+        for (int r = 0; r < 3; r++) {
+            a.E[((size_t)b * 3 + r) * a.Vs + i] = EV_FAR;
+            a.G[((size_t)b * 3 + r) * a.Vs + i] = 0.f;
+        }
+    }
+    const double s = ev_block_sum(term, s_red);
+    if (threadIdx.x == 0) a.add_partial[(size_t)b * a.n_prep_blocks + blockIdx.x] = s;
+}
+
+// CTA = (tile of EV_QTILE ground-truth points, target range, crop).  Estimated points stream through shared memory in
+// SoA quads (three LDS.128 broadcasts feed 4 targets x EV_Q queries); per target pair: 3 FADD2 + FMUL2 + 2 FFMA2, then
+// the running minimum.  No tensor cores: a min-reduction over distances is not a contraction.
+__global__ void __launch_bounds__(EV_THREADS)
+zp_adi_kernel(ErrArgs a) {
+    __shared__ __align__(16) float s_t[3][EV_CHUNK];
+    const int b = blockIdx.z;
+    const int obj = a.obj_ids ? a.obj_ids[b] : a.obj_default;
+    const bool okobj = obj >= 0 && obj < ZP_MAX_OBJECTS && a.model_ptrs[obj] != nullptr;
+    const int V = okobj ? a.model_V[obj] : 0;
+    const int V4 = (V + 3) & ~3;
+    const int q0 = blockIdx.x * EV_QTILE;
+    const int t_begin = blockIdx.y * a.tlen, t_end = min(V4, t_begin + a.tlen);
+    if (q0 >= V || t_begin >= t_end) return;
+    const float* Eb = a.E + (size_t)b * 3 * a.Vs;
+    const float* Gb = a.G + (size_t)b * 3 * a.Vs;
+    f32x2 qx[EV_Q], qy[EV_Q], qz[EV_Q];
+    float m[EV_Q];
+#pragma unroll
+    for (int k = 0; k < EV_Q; k++) {
+        const int i = min(q0 + k * EV_THREADS + threadIdx.x, a.Vs - 1);     // consecutive lanes, consecutive points
+        qx[k] = ev_dup(Gb[i]); qy[k] = ev_dup(Gb[a.Vs + i]); qz[k] = ev_dup(Gb[2 * (size_t)a.Vs + i]);
+        m[k] = EV_INIT;
+    }
+    for (int c0 = t_begin; c0 < t_end; c0 += EV_CHUNK) {
+        const int cn = min(EV_CHUNK, t_end - c0);               // multiple of 4
+        __syncthreads();
+#pragma unroll
+        for (int pl = 0; pl < 3; pl++) {
+            const float4* src = reinterpret_cast<const float4*>(Eb + (size_t)pl * a.Vs + c0);
+            for (int j = threadIdx.x; j < (cn >> 2); j += EV_THREADS) reinterpret_cast<float4*>(s_t[pl])[j] = src[j];
+        }
+        __syncthreads();
+        const ulonglong2* sx = reinterpret_cast<const ulonglong2*>(s_t[0]);
+        const ulonglong2* sy = reinterpret_cast<const ulonglong2*>(s_t[1]);
+        const ulonglong2* sz = reinterpret_cast<const ulonglong2*>(s_t[2]);
+#pragma unroll 2
+        for (int t = 0; t < (cn >> 2); t++) {
+            const ulonglong2 X = sx[t], Y = sy[t], Z = sz[t];
+#pragma unroll
+            for (int k = 0; k < EV_Q; k++) {
+                const f32x2 dx0 = ev_sub2(X.x, qx[k]), dx1 = ev_sub2(X.y, qx[k]);
+                const f32x2 dy0 = ev_sub2(Y.x, qy[k]), dy1 = ev_sub2(Y.y, qy[k]);
+                const f32x2 dz0 = ev_sub2(Z.x, qz[k]), dz1 = ev_sub2(Z.y, qz[k]);
+                const f32x2 e0 = ev_fma2(dz0, dz0, ev_fma2(dy0, dy0, ev_mul2(dx0, dx0)));
+                const f32x2 e1 = ev_fma2(dz1, dz1, ev_fma2(dy1, dy1, ev_mul2(dx1, dx1)));
+                m[k] = fminf(fminf(m[k], ev_lo(e0)), ev_hi(e0));
+                m[k] = fminf(fminf(m[k], ev_lo(e1)), ev_hi(e1));
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < EV_Q; k++) {
+        const int i = q0 + k * EV_THREADS + threadIdx.x;
+        if (i < V) {
+            uint32_t* dst = a.qmin + (size_t)b * a.Vs + i;
+            if (a.nsplit > 1) atomicMin(dst, __float_as_uint(m[k]));     // non-negative floats order like their bit patterns
+            else *dst = __float_as_uint(m[k]);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(EV_PREP_THREADS)
+zp_err_final_kernel(ErrArgs a) {
+    __shared__ double s_red[EV_PREP_THREADS / 32];
+    const int b = blockIdx.x;
+    const int obj = a.obj_ids ? a.obj_ids[b] : a.obj_default;
+    const bool okobj = obj >= 0 && obj < ZP_MAX_OBJECTS && a.model_ptrs[obj] != nullptr;
+    const int V = okobj ? a.model_V[obj] : 0;
+    const int nb = (V + EV_PREP_THREADS - 1) / EV_PREP_THREADS;
+    double s = 0;
+    for (int j = threadIdx.x; j < nb; j += EV_PREP_THREADS) s += a.add_partial[(size_t)b * a.n_prep_blocks + j];
+    const double add_sum = ev_block_sum(s, s_red);
+    __shared__ double s_add;
+    if (threadIdx.x == 0) {
+        s_add = V > 0 ? add_sum / V : nan("");
+        if (a.add_out) a.add_out[b] = s_add;
+    }
+    if (!a.adi_out) return;
+    double q = 0;
+    for (int i = threadIdx.x; i < V; i += EV_PREP_THREADS) q += sqrt((double)__uint_as_float(a.qmin[(size_t)b * a.Vs + i]));
+    const double adi_sum = ev_block_sum(q, s_red);       // contains the __syncthreads that publish s_add
+    // a NaN pose makes every ADD term NaN; the float32 minimum would silently skip NaN distances, so mirror it here
+    if (threadIdx.x == 0) a.adi_out[b] = (V > 0 && s_add == s_add) ? adi_sum / V : nan("");
+}
+
+static int ews_reserve(zp_ctx* ctx, size_t bytes) {
+    if (bytes <= ctx->ews_bytes) return 0;
+    ZP_CUDA(ctx, cudaDeviceSynchronize());
+    if (ctx->ews) cudaFree(ctx->ews);
+    ctx->ews = nullptr; ctx->ews_bytes = 0;
+    const size_t want = bytes + bytes / 4 + 4096;
+    ZP_CUDA(ctx, cudaMalloc(&ctx->ews, want));
+    ctx->ews_bytes = want;
+    return 0;
+}
+
+static size_t ev_align(size_t x) { return (x + 255) & ~(size_t)255; }
+
+extern "C" {
+
+int zp_final_bbox(zp_ctx* ctx, const double* det_boxes, int B, double padding_ratio, int resize_method, double max_x,
+                  double max_y, double* out_boxes, void* stream) {
+    if (!ctx) return -1;
+    if (B == 0) return 0;
+    if (B < 0 || !det_boxes || !out_boxes) ZP_FAIL(ctx, -1, "zp_final_bbox: bad argument");
+    if (resize_method < ZP_CROP_RESIZE || resize_method > ZP_CROP_KEEP)
+        ZP_FAIL(ctx, -1, "zp_final_bbox: unknown resize method %d", resize_method);
+    ZP_CUDA(ctx, cudaSetDevice(ctx->device));
+    zp_bbox_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(det_boxes, B, padding_ratio, resize_method, max_x, max_y, out_boxes);
+    ZP_CHECK_LAUNCH(ctx, "zp_bbox_kernel");
+    return 0;
+}
+
+int zp_upload_model(zp_ctx* ctx, int obj_id, const double* pts_xyz, int V) {
+    if (!ctx) return -1;
+    if (obj_id < 0 || obj_id >= ZP_MAX_OBJECTS) ZP_FAIL(ctx, -1, "obj_id %d out of range [0,%d)", obj_id, ZP_MAX_OBJECTS);
+    if (!pts_xyz || V < 1 || V > (1 << 22)) ZP_FAIL(ctx, -1, "zp_upload_model: bad vertex array (V = %d)", V);
+    ZP_CUDA(ctx, cudaSetDevice(ctx->device));
+    ZP_CUDA(ctx, cudaDeviceSynchronize());
+    if (!ctx->d_model_ptrs) {
+        ZP_CUDA(ctx, cudaMalloc((void**)&ctx->d_model_ptrs, ZP_MAX_OBJECTS * sizeof(double*)));
+        ZP_CUDA(ctx, cudaMemset((void*)ctx->d_model_ptrs, 0, ZP_MAX_OBJECTS * sizeof(double*)));
+        ZP_CUDA(ctx, cudaMalloc((void**)&ctx->d_model_V, ZP_MAX_OBJECTS * sizeof(int)));
+        ZP_CUDA(ctx, cudaMemset(ctx->d_model_V, 0, ZP_MAX_OBJECTS * sizeof(int)));
+    }
+    ZpModel& m = ctx->models[obj_id];
+    if (m.pts) cudaFree(m.pts);
+    m.pts = nullptr; m.V = 0;
+    ZP_CUDA(ctx, cudaMalloc((void**)&m.pts, (size_t)V * 3 * sizeof(double)));
+    ZP_CUDA(ctx, cudaMemcpy(m.pts, pts_xyz, (size_t)V * 3 * sizeof(double), cudaMemcpyHostToDevice));
+    m.V = V;
+    ZP_CUDA(ctx, cudaMemcpy((void*)(ctx->d_model_ptrs + obj_id), &m.pts, sizeof(double*), cudaMemcpyHostToDevice));
+    ZP_CUDA(ctx, cudaMemcpy(ctx->d_model_V + obj_id, &V, sizeof(int), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+int zp_pose_errors(zp_ctx* ctx, const double* poses_est, const double* poses_gt, const int32_t* obj_ids, int obj_default,
+                   int B, double* add_out, double* adi_out, void* stream) {
+    if (!ctx) return -1;
+    if (B == 0) return 0;
+    if (B < 0 || !poses_est || !poses_gt || (!add_out && !adi_out)) ZP_FAIL(ctx, -1, "zp_pose_errors: bad argument");
+    int Vmax = 0;
+    if (obj_ids) { for (const auto& m : ctx->models) Vmax = std::max(Vmax, m.V); }
+    else {
+        if (obj_default < 0 || obj_default >= ZP_MAX_OBJECTS || !ctx->models[obj_default].pts)
+            ZP_FAIL(ctx, -1, "zp_pose_errors: no model uploaded for object slot %d", obj_default);
+        Vmax = ctx->models[obj_default].V;
+    }
+    if (Vmax == 0) ZP_FAIL(ctx, -1, "zp_pose_errors: no model uploaded (zp_upload_model)");
+    ZP_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    ErrArgs a{};
+    a.est = poses_est; a.gt = poses_gt; a.obj_ids = obj_ids; a.obj_default = obj_default;
+    a.model_ptrs = ctx->d_model_ptrs; a.model_V = ctx->d_model_V;
+    a.B = B; a.Vs = (Vmax + 3) & ~3;
+    a.n_prep_blocks = (a.Vs + EV_PREP_THREADS - 1) / EV_PREP_THREADS;
+    a.add_out = add_out; a.adi_out = adi_out;
+    const size_t b_part = ev_align((size_t)B * a.n_prep_blocks * sizeof(double));
+    const size_t b_pts = adi_out ? ev_align((size_t)B * 3 * a.Vs * sizeof(float)) : 0;
+    const size_t b_min = adi_out ? ev_align((size_t)B * a.Vs * sizeof(uint32_t)) : 0;
+    if (ews_reserve(ctx, b_part + 2 * b_pts + b_min)) return -2;
+    char* p = (char*)ctx->ews;
+    a.add_partial = (double*)p; p += b_part;
+    if (adi_out) { a.E = (float*)p; p += b_pts; a.G = (float*)p; p += b_pts; a.qmin = (uint32_t*)p; }
+    zp_err_prepare_kernel<<<dim3(a.n_prep_blocks, B), EV_PREP_THREADS, 0, st>>>(a);
+    ZP_CHECK_LAUNCH(ctx, "zp_err_prepare_kernel");
+    if (adi_out) {
+        const int qtiles = (Vmax + EV_QTILE - 1) / EV_QTILE;
+        // enough CTAs for ~8 per SM: small batches split the target set and merge with atomicMin
+        const long want = (long)ctx->sm_count * 8;
+        int nsplit = (int)std::min<long>(std::max<long>(1, (want + (long)qtiles * B - 1) / ((long)qtiles * B)), std::max(1, a.Vs / 256));
+        int tlen = ((a.Vs + nsplit - 1) / nsplit + 3) & ~3;
+        nsplit = (a.Vs + tlen - 1) / tlen;
+        a.nsplit = nsplit; a.tlen = tlen;
+        if (nsplit > 1) ZP_CUDA(ctx, cudaMemsetAsync(a.qmin, 0x7f, (size_t)B * a.Vs * sizeof(uint32_t), st));   // 3.39e38f
+        zp_adi_kernel<<<dim3(qtiles, nsplit, B), EV_THREADS, 0, st>>>(a);
+        ZP_CHECK_LAUNCH(ctx, "zp_adi_kernel");
+    }
+    zp_err_final_kernel<<<B, EV_PREP_THREADS, 0, st>>>(a);
+    ZP_CHECK_LAUNCH(ctx, "zp_err_final_kernel");
+    return 0;
+}
+
+}  // extern "C"

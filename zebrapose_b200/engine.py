@@ -259,6 +259,42 @@ class Engine:
         self.ctx.check(rc, "zp_codes_to_ids")
         return out
 
+    # ------------------------------------------------------------------ either side of the path
+    def final_bboxes(self, det_boxes, padding_ratio=1.5, resize_method="crop_square_resize", max_x=640, max_y=480):
+        """padding_Bbox + get_final_Bbox (bop_dataset_pytorch.py:123-139, 162-194) for [B,4] detection boxes (x,y,w,h)
+        on the device.  padding_ratio <= 0 skips padding_Bbox.  Returns float64 [B,4] with integral values, the
+        `bboxes` argument of decode()."""
+        bb = torch.as_tensor(det_boxes).to(device=self.device, dtype=torch.float64).contiguous().reshape(-1, 4)
+        out = torch.empty_like(bb)
+        rc = self.lib.zp_final_bbox(self.ctx.handle, _ptr(bb), bb.shape[0], float(padding_ratio),
+                                    _lib.RESIZE[resize_method], float(max_x), float(max_y), _ptr(out), _stream())
+        self.ctx.check(rc, "zp_final_bbox")
+        return out
+
+    def upload_model(self, obj_id, vertices):
+        """Model vertices [V,3] (mm) of object slot obj_id for pose_errors().  Synchronises."""
+        v = np.ascontiguousarray(np.asarray(vertices, np.float64).reshape(-1, 3))
+        rc = self.lib.zp_upload_model(self.ctx.handle, int(obj_id), v.ctypes.data_as(C.c_void_p), int(v.shape[0]))
+        self.ctx.check(rc, "zp_upload_model")
+
+    def pose_errors(self, poses_est, poses_gt, obj_ids=None, *, obj_default=0, add=True, adi=True):
+        """ADD / ADI (lib/pysixd/pose_error.py:297-336) of B pose pairs, poses float64 [B,12] (R row-major | t mm).
+        Returns (add [B] | None, adi [B] | None), float64 on the device."""
+        pe = torch.as_tensor(poses_est).to(device=self.device, dtype=torch.float64).contiguous().reshape(-1, 12)
+        pg = torch.as_tensor(poses_gt).to(device=self.device, dtype=torch.float64).contiguous().reshape(-1, 12)
+        if pe.shape != pg.shape:
+            raise ValueError("poses_est and poses_gt must have the same shape")
+        B = pe.shape[0]
+        oid = None
+        if obj_ids is not None:
+            oid = torch.as_tensor(obj_ids).to(device=self.device, dtype=torch.int32).contiguous()
+        o_add = torch.empty((B,), dtype=torch.float64, device=self.device) if add else None
+        o_adi = torch.empty((B,), dtype=torch.float64, device=self.device) if adi else None
+        rc = self.lib.zp_pose_errors(self.ctx.handle, _ptr(pe), _ptr(pg), _ptr(oid), int(obj_default), B,
+                                     _ptr(o_add), _ptr(o_adi), _stream())
+        self.ctx.check(rc, "zp_pose_errors")
+        return o_add, o_adi
+
     def launch_count(self):
         return int(self.lib.zp_launch_count(self.ctx.handle))
 
