@@ -7,7 +7,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libzebrapose_b200.so")
-SOURCES = ["zp_api.cu", "zp_decode.cu", "zp_ransac.cu", "zp_eval.cu"]
+SOURCES = ["zp_api.cu", "zp_decode.cu", "zp_ransac.cu", "zp_eval.cu", "zp_head.cu"]
 HEADERS = ["zp_common.cuh", "zp_epnp.cuh", os.path.join("..", "..", "include", "zebrapose_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]

@@ -46,6 +46,8 @@ SIGNATURES = {
     "zp_final_bbox": (_i, [_vp, _vp, _i, _d, _i, _d, _d, _vp, _vp]),
     "zp_upload_model": (_i, [_vp, _i, _vp, _i]),
     "zp_pose_errors": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp]),
+    "zp_upload_head": (_i, [_vp, _vp, _vp, _i, _i]),
+    "zp_head_decode": (_i, [_vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _i, _vp, _vp]),
 }
 
 _lib = None

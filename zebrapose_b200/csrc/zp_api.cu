@@ -100,6 +100,8 @@ void zp_destroy(zp_ctx* ctx) {
     if (ctx->d_model_ptrs) cudaFree((void*)ctx->d_model_ptrs);
     if (ctx->d_model_V) cudaFree(ctx->d_model_V);
     if (ctx->ews) cudaFree(ctx->ews);
+    if (ctx->head_w) cudaFree(ctx->head_w);
+    if (ctx->hdws) cudaFree(ctx->hdws);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }

@@ -46,6 +46,12 @@ struct zp_ctx {
     int* d_model_V = nullptr;                // device array [ZP_MAX_OBJECTS]
     void* ews = nullptr;
     size_t ews_bytes = 0;
+    // fused network head (zp_head.cu): bf16 weights [32][c_in] (rows >= n_out zero), bias, workspace (codes + mask words)
+    void* head_w = nullptr;
+    float head_bias[32] = {0};
+    int head_n_out = 0, head_c_in = 0;
+    void* hdws = nullptr;
+    size_t hdws_bytes = 0;
     cudaStream_t own_stream = nullptr;
     int64_t launches = 0;
     int score_groups = 0;                    // 0 auto, else 1 | 2 | 4 warp-groups per scoring CTA (tests / tuning)

@@ -640,6 +640,31 @@ static int launch_split(zp_ctx* ctx, const DecodeArgs& a, cudaStream_t st) {
     return 0;
 }
 
+// Second half of the two-kernel path on its own, for producers that already hold 2 B/pixel codes + mask ballot words
+// in the fp32 flavour's layout (segments of 128 pixels, word j bit i = pixel 4i + j): the fused network head
+// (zp_head.cu) writes exactly that from its tensor-core epilogue.
+int zp_launch_emit_codes(zp_ctx* ctx, int B, int S, const double* bbox, const int32_t* obj_ids, int obj_default,
+                         const uint16_t* codes, const uint32_t* maskw, float* corr, int cap, int32_t* counts, cudaStream_t st) {
+    constexpr int PPT = 4;
+    DecodeArgs a{};
+    a.B = B; a.S = S; a.bbox = bbox; a.obj_ids = obj_ids; a.obj_default = obj_default;
+    a.tables = (const float4* const*)ctx->d_table_ptrs;
+    a.corr = corr; a.cap = cap; a.counts = counts;
+    const int N = S * S;
+    const int segs = (N + 32 * PPT - 1) / (32 * PPT);
+    const int runs = (segs + DEC_WARPS - 1) / DEC_WARPS;
+    if (S % PPT != 0 || S > 1024 || runs > 64) ZP_FAIL(ctx, -1, "emit from codes: crop size %d not supported", S);
+    const int smem = 5 * DEC_THREADS * PPT * (int)sizeof(float);
+    static bool attr_set = false;
+    if (!attr_set) {
+        ZP_CUDA(ctx, cudaFuncSetAttribute(zp_decode_emit_kernel<PPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_set = true;
+    }
+    zp_decode_emit_kernel<PPT><<<(unsigned)(B * runs), DEC_THREADS, smem, st>>>(a, codes, maskw, segs, runs);
+    ZP_CHECK_LAUNCH(ctx, "zp_decode_emit_kernel");
+    return 0;
+}
+
 // -------------------------------------------------------------------------------------------------------------
 // Streaming path (contiguous planes): a producer warp pulls the logits of a crop part through a shared-memory ring of
 // 8 KB plane segments with 1-D TMA bulk copies (cp.async.bulk + full/empty mbarriers, SASS UBLKCP), so the memory

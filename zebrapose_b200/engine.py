@@ -259,6 +259,55 @@ class Engine:
         self.ctx.check(rc, "zp_codes_to_ids")
         return out
 
+    # ------------------------------------------------------------------ fused network tail
+    def upload_head(self, weight, bias=None):
+        """Weights of the network's last 1x1 convolution (model/aspp.py:58 conv_1x1_4): weight [n_out, c_in] or the
+        Conv2d's [n_out, c_in, 1, 1]; bias [n_out] or None.  Rounded to bfloat16 by the library.  Synchronises."""
+        w = torch.as_tensor(weight).detach().to("cpu", torch.float32)
+        w = w.reshape(w.shape[0], -1).contiguous().numpy()
+        b = None if bias is None else np.ascontiguousarray(torch.as_tensor(bias).detach().to("cpu", torch.float32).numpy())
+        rc = self.lib.zp_upload_head(self.ctx.handle, w.ctypes.data_as(C.c_void_p),
+                                     b.ctypes.data_as(C.c_void_p) if b is not None else C.c_void_p(),
+                                     int(w.shape[0]), int(w.shape[1]))
+        self.ctx.check(rc, "zp_upload_head")
+        self._head = (int(w.shape[0]), int(w.shape[1]))
+
+    @staticmethod
+    def _channels_last_ptr(t, name):
+        if t.dim() != 4 or t.dtype != torch.bfloat16:
+            raise TypeError("%s must be a 4-D bfloat16 tensor [B,C,S,S] in channels_last memory format" % name)
+        if not t.permute(0, 2, 3, 1).is_contiguous():
+            raise ValueError("%s must be channels_last (x.contiguous(memory_format=torch.channels_last))" % name)
+        return t
+
+    def head_decode(self, x, x_skip, bboxes, obj_ids=None, *, obj_default=0, mask_ch=0, bit0_ch=1, n_bits=16, ignore_bit=0,
+                    return_codes=False, cap=None):
+        """`conv_1x1_4(torch.cat([x, x_skip], 1))` (model/aspp.py:112) + decode() in one pass on the tensor cores; the
+        logits are never written.  x [B,c1,S,S], x_skip [B,c2,S,S] | None: bfloat16, channels_last.  Returns like decode()."""
+        x = self._channels_last_ptr(x, "x")
+        B, c1, S, S2 = x.shape
+        c2 = 0
+        if x_skip is not None:
+            x_skip = self._channels_last_ptr(x_skip, "x_skip")
+            if x_skip.shape[0] != B or x_skip.shape[2:] != x.shape[2:]:
+                raise ValueError("x and x_skip must agree in batch and spatial size")
+            c2 = x_skip.shape[1]
+        if S != S2 or x.device != self.device:
+            raise ValueError("x must be [B,C,S,S] on %s" % self.device)
+        cap = int(cap or ((S * S + 3) // 4) * 4)
+        bb = torch.as_tensor(bboxes).to(device=self.device, dtype=torch.float64).contiguous().reshape(B, 4)
+        oid = None
+        if obj_ids is not None:
+            oid = torch.as_tensor(obj_ids).to(device=self.device, dtype=torch.int32).contiguous()
+        corr = torch.empty((B, 5, cap), dtype=torch.float32, device=self.device)
+        counts = torch.empty((B,), dtype=torch.int32, device=self.device)
+        codes = torch.empty((B, S, S), dtype=torch.uint16, device=self.device) if return_codes else None
+        rc = self.lib.zp_head_decode(self.ctx.handle, _ptr(x), int(c1), _ptr(x_skip), int(c2), B, S, int(mask_ch),
+                                     int(bit0_ch), int(n_bits), int(ignore_bit), _ptr(bb), _ptr(oid), int(obj_default),
+                                     _ptr(codes), _ptr(corr), cap, _ptr(counts), _stream())
+        self.ctx.check(rc, "zp_head_decode")
+        return (corr, counts, codes) if return_codes else (corr, counts)
+
     # ------------------------------------------------------------------ either side of the path (SURVEY 8(f) N2, N3)
     def final_bboxes(self, det_boxes, padding_ratio=1.5, resize_method="crop_square_resize", max_x=640, max_y=480):
         """padding_Bbox + get_final_Bbox (bop_dataset_pytorch.py:123-139, 162-194) for [B,4] detection boxes (x,y,w,h)
