@@ -308,6 +308,16 @@ class Engine:
         self.ctx.check(rc, "zp_head_decode")
         return (corr, counts, codes) if return_codes else (corr, counts)
 
+    def head_pose_batch(self, x, x_skip, bboxes, Ks, obj_ids=None, *, obj_default=0, mask_ch=0, bit0_ch=1, n_bits=16,
+                        ignore_bit=0, m=5, iters=150, thr=2.0, conf=0.99, sampler="cv2", seed=0, select="cv2_replay",
+                        final="epnp"):
+        """decode_and_pose_batch() fed by the network's last activations instead of its logits (head_decode + ransac)."""
+        corr, counts = self.head_decode(x, x_skip, bboxes, obj_ids, obj_default=obj_default, mask_ch=mask_ch,
+                                        bit0_ch=bit0_ch, n_bits=n_bits, ignore_bit=ignore_bit)
+        r = self.ransac(corr, counts, Ks, H=iters, m=m, thr=thr, conf=conf, sampler=sampler, seed=seed, select=select,
+                        final=final)
+        return r["poses"], r["n_inliers"], r["status"]
+
     # ------------------------------------------------------------------ either side of the path (SURVEY 8(f) N2, N3)
     def final_bboxes(self, det_boxes, padding_ratio=1.5, resize_method="crop_square_resize", max_x=640, max_y=480):
         """padding_Bbox + get_final_Bbox (bop_dataset_pytorch.py:123-139, 162-194) for [B,4] detection boxes (x,y,w,h)
