@@ -141,3 +141,25 @@ def test_head_argument_checks(eng):
         eng.upload_head(torch.randn(40, 320))                            # more than 32 outputs
     with pytest.raises(zp.ZpError):
         eng.upload_head(torch.randn(17, 100))                            # c_in not a multiple of 64
+
+
+def test_head_pose_batch_equals_logit_path(eng):
+    """network activations -> poses in one call == the same crops through decode_and_pose_batch on materialised logits"""
+    S, B = 128, 4
+    tab, nrm, _ = synth.make_dict(16, seed=3, radius=51.0, missing_frac=0.0)
+    eng.upload_dict(0, tab, n_bits=16, ignore_bit=0, nonexist="zero")
+    crops = [synth.make_crop(tab, nrm, 9100 + i, S=S) for i in range(B)]
+    logits = np.stack([synth.crop_to_logits(c) for c in crops])
+    bboxes = np.stack([c["bbox"] for c in crops])
+    Ks = np.stack([c["K"] for c in crops]).reshape(B, 9)
+    g = torch.Generator(device="cpu").manual_seed(2)
+    W = _bf16_round(torch.randn(17, 320, generator=g) * 0.3).cuda()
+    bias = (torch.randn(17, generator=g) * 0.2).cuda()
+    xall = _features_for(logits, W, bias)
+    x = xall[:, :256].contiguous(memory_format=torch.channels_last)
+    xs = xall[:, 256:].contiguous(memory_format=torch.channels_last)
+    eng.upload_head(W, bias)
+    p1, n1, s1 = eng.head_pose_batch(x, xs, bboxes, Ks)
+    p2, n2, s2 = eng.decode_and_pose_batch(torch.from_numpy(logits).cuda(), bboxes, Ks)
+    assert torch.equal(p1, p2) and torch.equal(n1, n2) and torch.equal(s1, s2)
+    assert int(s1.sum()) == 0
