@@ -255,16 +255,22 @@ def main():
     n_total = C * world
     kw = dict(n_bits=NBITS, iters=H, m=M, thr=THR)
 
-    def post(res):
-        return zp.gather_poses(res[0], res[1], res[2], n_total) if world > 1 else res
+    def final_gather(outs):
+        """SURVEY 8(e) / configs[3]: the path has ONE exchange step, at the very end of the job -- the poses of all K
+        steps of all ranks in one all_gather (112 B per crop), inside the timed region."""
+        if world == 1:
+            return outs
+        poses = torch.cat([o[0] for o in outs]); ninl = torch.cat([o[1] for o in outs]); st = torch.cat([o[2] for o in outs])
+        return zp.gather_poses(poses, ninl, st, poses.shape[0] * world)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for i in range(max(args.warmup, args.lanes)):
-        pipe.submit(*bufs[i % n_buf], post=post, **kw)
+    outs = [pipe.submit(*bufs[i % n_buf], **kw) for i in range(max(args.warmup, args.lanes))]
+    pipe.join()
+    final_gather(outs)
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:
@@ -274,9 +280,9 @@ def main():
     barrier()
     # ---- timed region: exactly K steps, enqueued round-robin over the lanes, bracketed by barrier + synchronize
     e0.record()
-    for i in range(args.steps):
-        out = pipe.submit(*bufs[i % n_buf], post=post, **kw)
+    outs = [pipe.submit(*bufs[i % n_buf], **kw) for i in range(args.steps)]
     pipe.join()
+    gathered = final_gather(outs)
     e1.record()
     barrier()
     launches = pipe.launch_count() - l0
@@ -394,6 +400,7 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "collective": None if world == 1 else "one NCCL all_gather_into_tensor of the K steps' pose records (112 B/crop) at the end of the timed region",
             "dtype": "f32 scoring / f64 EPnP / u16 codes", "data": "synthetic",
             "config": {"workload": WORKLOAD % C,
                        "crops_per_gpu": C, "lanes": args.lanes,

@@ -18,6 +18,7 @@
 //
 // Algorithmic FP32 work of scoring: 27 flop per (correspondence, hypothesis).
 #include <climits>
+#include <stdlib.h>
 #include "zp_common.cuh"
 
 // phase timestamps of thread 0 of CTA 0 (profiling aid, read with zp_debug_clocks): slots 0-9 final kernel, 10-15 minimal
@@ -250,7 +251,8 @@ constexpr int MIN_SMEM_BYTES = (MIN_THREADS / 4) * MIN_HYP_DOUBLES * (int)sizeof
 // One QUAD (4 lanes) per hypothesis.  The cheap serial setup (control points, 52 sums over the m points) is computed
 // redundantly by the 4 lanes; the 12x12 null space is the quad-cooperative Jacobi; the three beta candidates run on
 // lanes 0..2; the winner (smallest mean reprojection distance over the m points, EPnP's rule) writes the pose.
-__global__ void __launch_bounds__(MIN_THREADS, 3)
+template <int MINB>
+__global__ void __launch_bounds__(MIN_THREADS, MINB)
 zp_minimal_kernel(const float* __restrict__ corr, int cap, const int32_t* __restrict__ counts,
                   const double* __restrict__ Kmat, const int32_t* __restrict__ samples, int B, int H, int m,
                   double inv_thr, double* __restrict__ hyp_poses, float* __restrict__ hyp_P) {
@@ -943,12 +945,22 @@ int zp_launch_minimal(zp_ctx* ctx, const float* corr, int cap, const int32_t* co
     const int per_cta = MIN_THREADS / 4;
     int total = B * H;
     static bool attr_set = false;
+    static int force = 0;
     if (!attr_set) {
-        ZP_CUDA(ctx, cudaFuncSetAttribute(zp_minimal_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MIN_SMEM_BYTES));
+        ZP_CUDA(ctx, cudaFuncSetAttribute(zp_minimal_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, MIN_SMEM_BYTES));
+        ZP_CUDA(ctx, cudaFuncSetAttribute(zp_minimal_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, MIN_SMEM_BYTES));
+        const char* e = getenv("ZP_MIN_BLOCKS");
+        force = e ? atoi(e) : 0;
         attr_set = true;
     }
-    zp_minimal_kernel<<<(total + per_cta - 1) / per_cta, MIN_THREADS, MIN_SMEM_BYTES, st>>>(
-        corr, cap, counts, K, samples, B, H, m, 1.0 / (double)thr_px, hyp_poses, hyp_P);
+    const int grid = (total + per_cta - 1) / per_cta;
+    // register budget (measured, profiles/README.md): a saturating grid runs fastest with the 255-register build (two CTAs
+    // per SM, 312 instead of 1220 bytes of spill stores on the FP64 dependency chains: 1267 vs 1396 us at 1024 crops);
+    // a grid of about one wave (64 crops) takes the same time either way when alone, but the 168-register build leaves
+    // room for another lane's kernels on the SM (257 k vs 236 k poses/s with 3 lanes).  ZP_MIN_BLOCKS=2|3 pins it.
+    const bool two = force ? force == 2 : grid > 4 * ctx->sm_count;
+    if (two) zp_minimal_kernel<2><<<grid, MIN_THREADS, MIN_SMEM_BYTES, st>>>(corr, cap, counts, K, samples, B, H, m, 1.0 / (double)thr_px, hyp_poses, hyp_P);
+    else zp_minimal_kernel<3><<<grid, MIN_THREADS, MIN_SMEM_BYTES, st>>>(corr, cap, counts, K, samples, B, H, m, 1.0 / (double)thr_px, hyp_poses, hyp_P);
     ZP_CHECK_LAUNCH(ctx, "zp_minimal_kernel");
     return 0;
 }
