@@ -594,6 +594,8 @@ struct FinalArgs {
     double* poses; int32_t* n_inliers; int32_t* status; int32_t* best_idx; uint8_t* inlier_mask;
 };
 
+// (register budget measured: 255 regs / 1 CTA per SM beats 128 regs / 2 and 80 regs / 3 at 64 AND at 1024 crops --
+// 3.72 vs 3.89 vs 4.26 ms per 1024-crop step; profiles/README.md)
 __global__ void __launch_bounds__(FIN_THREADS) zp_final_kernel(FinalArgs a) {
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
     __shared__ double s_red[(FIN_THREADS / 32) * 52];
@@ -956,9 +958,10 @@ int zp_launch_minimal(zp_ctx* ctx, const float* corr, int cap, const int32_t* co
     const int grid = (total + per_cta - 1) / per_cta;
     // register budget (measured, profiles/README.md): a saturating grid runs fastest with the 255-register build (two CTAs
     // per SM, 312 instead of 1220 bytes of spill stores on the FP64 dependency chains: 1267 vs 1396 us at 1024 crops);
-    // a grid of about one wave (64 crops) takes the same time either way when alone, but the 168-register build leaves
+    // a grid of a few waves is quantised in favour of three resident CTAs (256 crops: 351 vs 392 us), and at one wave (64 crops)
+    // both take the same time alone but the 168-register build leaves
     // room for another lane's kernels on the SM (257 k vs 236 k poses/s with 3 lanes).  ZP_MIN_BLOCKS=2|3 pins it.
-    const bool two = force ? force == 2 : grid > 4 * ctx->sm_count;
+    const bool two = force ? force == 2 : grid > 12 * ctx->sm_count;
     if (two) zp_minimal_kernel<2><<<grid, MIN_THREADS, MIN_SMEM_BYTES, st>>>(corr, cap, counts, K, samples, B, H, m, 1.0 / (double)thr_px, hyp_poses, hyp_P);
     else zp_minimal_kernel<3><<<grid, MIN_THREADS, MIN_SMEM_BYTES, st>>>(corr, cap, counts, K, samples, B, H, m, 1.0 / (double)thr_px, hyp_poses, hyp_P);
     ZP_CHECK_LAUNCH(ctx, "zp_minimal_kernel");
