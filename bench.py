@@ -33,7 +33,7 @@ WORKLOAD = ("configs[1]: %d synthetic YCB-V-like 128x128 crops per GPU, 21 dicti
 
 
 def make_workload(crops, seed):
-    from oracle import synth
+    from workloads import synth
     return synth.make_batch(crops, S=S, n_bits=NBITS, n_dicts=21, seed=seed, K=synth.YCBV_K, outlier=0.3, bitflip=0.02,
                             missing_frac=0.0, radius=(40.0, 175.0))
 
@@ -169,7 +169,7 @@ def next_rows(eng, timed, d_bbox, d_K, d_obj, crops, tables, C, hbm_peak, fp32_p
     ADD / ADI of the batch's poses against ground truth (N3; 5841-vertex models = LM-O ape size)."""
     import numpy as np
     import torch
-    from oracle import synth_eval
+    from workloads import synth_eval
     out = {}
     g = torch.Generator(device="cpu").manual_seed(0)
     c1, c2 = 256, 64

@@ -5,7 +5,7 @@ import json, sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 import zebrapose_b200 as zp
-from oracle import synth_eval
+from workloads import synth_eval
 
 args = [int(x) for x in sys.argv[1:]] or [64, 5841, 64, 8192, 1024, 5841, 1, 5841]
 eng = zp.Engine(0)

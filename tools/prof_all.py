@@ -4,7 +4,7 @@ import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 import zebrapose_b200 as zp
-from oracle import synth_eval
+from workloads import synth_eval
 argv = sys.argv[1:]; sys.argv = ['x']
 import bench
 C = int(argv[0]) if argv else 64

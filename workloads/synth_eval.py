@@ -1,0 +1,58 @@
+"""Seeded synthetic inputs for the evaluation-side fixtures (test infrastructure): model vertices, pose pairs,
+detection boxes, csv rows.  Shared by tests/golden/make_golden_eval.py and the tests so both see identical inputs."""
+import numpy as np
+import cv2
+
+MODELS = [("v1500", 1500, 21), ("v5841", 5841, 22)]     # (tag, vertices, seed); 5841 = LM-O ape model size
+N_PAIRS = 6
+N_BOXES = 120
+PAD_RATIOS = (1.5, 1.2)
+METHODS = ("crop_resize", "crop_square_resize", "crop_resize_by_warp_affine")
+
+
+def make_model(V, seed):
+    """vertices of a bumpy ellipsoid, ~100 mm across, 6-decimal values like a .ply file"""
+    rng = np.random.default_rng(seed)
+    d = rng.normal(size=(V, 3))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    r = 1.0 + 0.15 * np.sin(5 * d[:, :1]) * np.cos(3 * d[:, 1:2])
+    return np.round(d * r * np.array([55.0, 40.0, 30.0]), 6)
+
+
+def make_pose_pairs(n, seed):
+    """(est, gt) float64 [n,12]: gt random; est = gt perturbed by 0.05 .. 20 degrees / 0.1 .. 30 mm (one pair identical)"""
+    rng = np.random.default_rng(seed)
+    est, gt = [], []
+    for i in range(n):
+        Rg = cv2.Rodrigues(rng.normal(size=3))[0]
+        tg = np.array([rng.uniform(-100, 100), rng.uniform(-80, 80), rng.uniform(600, 1200)])
+        ang = np.radians([0.0, 0.05, 0.5, 2.0, 8.0, 20.0][i % 6])
+        ax = rng.normal(size=3); ax /= np.linalg.norm(ax)
+        Re = cv2.Rodrigues(ax * ang)[0] @ Rg
+        te = tg + rng.normal(size=3) * [0.0, 0.1, 0.5, 2.0, 8.0, 30.0][i % 6]
+        gt.append(np.concatenate([Rg.ravel(), tg]))
+        est.append(np.concatenate([Re.ravel(), te]))
+    return np.array(est), np.array(gt)
+
+
+def make_boxes(n, seed):
+    """detection boxes x,y,w,h: partly outside a 640x480 image, negative origins, fractional values on odd rows"""
+    rng = np.random.default_rng(seed)
+    b = np.stack([rng.uniform(-60, 600, n), rng.uniform(-60, 440, n), rng.uniform(3, 300, n), rng.uniform(3, 300, n)], 1)
+    b[::2] = np.round(b[::2])
+    b[5] = [10, 20, 50, 50]          # square
+    b[6] = [-30, -40, 700, 500]      # larger than the image
+    return b
+
+
+def make_csv_rows(seed):
+    rng = np.random.default_rng(seed)
+    n = 7
+    Rs = [cv2.Rodrigues(rng.normal(size=3))[0] for _ in range(n)]
+    Rs[2] = np.eye(3)                                   # failed crop: identity / zeros (test.py:457-463)
+    ts = [rng.normal(size=(3, 1)) * [[100], [80], [900]] for _ in range(n)]
+    ts[2] = np.zeros((3, 1))
+    scene = [int(v) for v in rng.integers(1, 60, n)]
+    img = [int(v) for v in rng.integers(0, 2000, n)]
+    scores = [1, 0.75, 1, -1, np.float64(0.5), 1, np.float32(0.25)]
+    return scene, img, Rs, ts, scores
