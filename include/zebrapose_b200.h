@@ -188,6 +188,18 @@ int zp_fp32x2_peak_probe(zp_ctx* ctx, int iters, double* out_tflops);
 int zp_final_bbox(zp_ctx* ctx, const double* det_boxes, int B, double padding_ratio, int resize_method,
                   double max_x, double max_y, double* out_boxes, void* stream);
 
+/* Replaces get_roi(x, Bbox, crop_size_img, cv2.INTER_LINEAR, resize_method) + transforms.ToTensor() + Normalize
+ * (bop_dataset_pytorch.py:36-89, 110-121, 303, 334-347; test_vivo.py:152-159): the network's input crops, straight from
+ * device-resident images.  images uint8 [n_img,H,W,3] (RGB, contiguous); img_ids nullable int32 [B] (NULL: image 0);
+ * boxes double [B,4] = the PADDED box (output of padding_Bbox; get_roi squares / clips it itself), integral values.
+ * resize_method ZP_CROP_RESIZE | ZP_CROP_SQUARE_RESIZE.  mean3 / std3 HOST float[3] or NULL (ImageNet constants of the
+ * reference).  out: float32 or bfloat16 (out_dtype), [B,3,cs,cs] NCHW or channels-last memory; out_u8 nullable uint8
+ * [B,cs,cs,3] = the resized crop before ToTensor.  The uint8 crop and the float32 tensor are bit-identical to the
+ * reference's (cv2's fixed-point bilinear resize is restated exactly); bfloat16 is that tensor rounded to nearest even. */
+int zp_crop_input(zp_ctx* ctx, const uint8_t* images, int n_img, int H, int W, const int32_t* img_ids,
+                  const double* boxes, int B, int crop_size, int resize_method, const float* mean3, const float* std3,
+                  int out_dtype, int channels_last, void* out, uint8_t* out_u8, void* stream);
+
 /* Model vertices of object slot `obj_id` for the pose-error metrics: HOST double [V][3] in mm (the `vertices` argument
  * of metric.py:8-18).  Synchronises. */
 int zp_upload_model(zp_ctx* ctx, int obj_id, const double* pts_xyz, int V);

@@ -124,3 +124,60 @@ def test_metric_wrappers_keep_reference_signatures(eng, gold):
     a = metric.Calculate_ADD_Error_BOP(Rg, tg, Re, te, pts)
     s = metric.Calculate_ADI_Error_BOP(Rg, tg, Re, te, pts)
     assert abs(a - gold["err_%s_add" % tag][i]) <= ADD_RTOL * a and abs(s - gold["err_%s_adi" % tag][i]) <= ADI_ATOL
+
+
+# ---- input crops: get_roi + ToTensor + Normalize -----------------------------------------------------------------------
+import hashlib
+
+
+def _sha(*arrs):
+    h = hashlib.sha256()
+    for a in arrs:
+        h.update(np.ascontiguousarray(a).tobytes())
+    return h.hexdigest()
+
+
+def test_input_crops_match_reference_bit_exactly(eng):
+    """uint8 crop and float32 tensor vs the sha256 of what the reference's get_roi + transform_pre produced"""
+    g = np.load(os.path.join(ROOT, "tests", "golden", "golden_crop_v1.npz"), allow_pickle=False)
+    img = synth_eval.make_image(5)
+    boxes = synth_eval.make_crop_boxes(synth_eval.N_CROP_BOXES, 6)
+    assert _sha(img, boxes) == str(g["in_sha"])
+    d_img = torch.from_numpy(img).cuda()
+    for cs, method in synth_eval.CROP_CASES:
+        t, u8 = eng.crop_inputs(d_img, boxes, crop_size=cs, resize_method=method, return_u8=True)
+        t, u8 = t.cpu().numpy(), u8.cpu().numpy()
+        for i in range(len(boxes)):
+            want = evalside.get_roi_u8(img, boxes[i], cs, method)
+            assert np.array_equal(u8[i], want), (cs, method, i, int(np.abs(u8[i].astype(int) - want.astype(int)).max()))
+            assert _sha(u8[i]) == str(g["u8_%d_%s" % (cs, method)][i]), (cs, method, i)
+            assert _sha(t[i]) == str(g["f32_%d_%s" % (cs, method)][i]), (cs, method, i)
+
+
+def test_input_crops_layouts_and_batches(eng):
+    """several images, bf16 / channels_last outputs, degenerate boxes, and a random sweep against the CPU restatement"""
+    imgs = np.stack([synth_eval.make_image(11, 120, 160), synth_eval.make_image(12, 120, 160)])
+    rng = np.random.default_rng(3)
+    B = 40
+    boxes = np.stack([rng.integers(-60, 150, B), rng.integers(-60, 110, B), rng.integers(1, 200, B), rng.integers(1, 200, B)], 1)
+    boxes[0] = [400, 300, 50, 50]            # completely outside: zero canvas
+    boxes[1] = [10, 10, 128, 128]            # exact 2x of crop 64
+    ids = rng.integers(0, 2, B).astype(np.int32)
+    d = torch.from_numpy(imgs).cuda()
+    for method in ("crop_square_resize", "crop_resize"):
+        if method == "crop_resize":
+            boxes[0] = [150, 100, 5, 5]      # clipped to a 5 x 5 region (an empty region makes cv2 raise in the reference)
+        f32, u8 = eng.crop_inputs(d, boxes, ids, crop_size=64, resize_method=method, return_u8=True)
+        cl = eng.crop_inputs(d, boxes, ids, crop_size=64, resize_method=method, dtype=torch.bfloat16, channels_last=True)
+        assert cl.is_contiguous(memory_format=torch.channels_last)
+        assert torch.equal(cl, f32.to(torch.bfloat16))
+        f32c = eng.crop_inputs(d, boxes, ids, crop_size=64, resize_method=method, channels_last=True)
+        assert torch.equal(f32c, f32)
+        u8 = u8.cpu().numpy(); f = f32.cpu().numpy()
+        for i in range(B):
+            want = evalside.get_roi_u8(imgs[ids[i]], boxes[i], 64, method)
+            assert np.array_equal(u8[i], want), (method, i)
+            assert np.array_equal(f[i], evalside.to_tensor_normalize(want)), (method, i)
+    import zebrapose_b200 as zp
+    with pytest.raises(zp.ZpError):
+        eng.crop_inputs(d, boxes, ids, resize_method="crop_resize_by_warp_affine")

@@ -63,3 +63,35 @@ def test_csv_matches_reference(gold, tmp_path):
     poses = np.array([np.concatenate([np.asarray(r).ravel(), np.asarray(t).ravel()]) for r, t in zip(Rs, ts)])
     write_to_cvs.write_batch(str(tmp_path), "batch", 1, scene, img, poses, scores)
     assert open(tmp_path / "batch.csv").read() == want
+
+
+def _crop_gold():
+    return np.load(os.path.join(ROOT, "tests", "golden", "golden_crop_v1.npz"), allow_pickle=False)
+
+
+def test_resize_restatement_matches_cv2():
+    import cv2
+    rng = np.random.default_rng(1)
+    for t in range(120):
+        sh, sw = int(rng.integers(1, 500)), int(rng.integers(1, 500))
+        d = int(rng.choice([64, 128, 256]))
+        if t % 10 == 0:
+            sh = sw = 2 * d                      # cv2 switches to INTER_AREA for an exact 2x2 decimation
+        img = rng.integers(0, 256, (sh, sw, 3), dtype=np.uint8)
+        assert np.array_equal(cv2.resize(img, (d, d), interpolation=cv2.INTER_LINEAR), evalside.resize_linear_u8(img, d, d)), (sh, sw, d)
+
+
+def test_input_crops_oracle_matches_reference():
+    g = _crop_gold()
+    img = synth_eval.make_image(5)
+    boxes = synth_eval.make_crop_boxes(synth_eval.N_CROP_BOXES, 6)
+    assert _sha(img, boxes) == str(g["in_sha"])
+    for cs, method in synth_eval.CROP_CASES:
+        for i, b in enumerate(boxes):
+            roi = evalside.get_roi_u8(img, b, cs, method)
+            assert _sha(roi) == str(g["u8_%d_%s" % (cs, method)][i]), (cs, method, i)
+            assert _sha(evalside.to_tensor_normalize(roi)) == str(g["f32_%d_%s" % (cs, method)][i]), (cs, method, i)
+    for i in range(3):
+        roi = evalside.get_roi_u8(img, boxes[i], 64, "crop_resize")
+        assert np.array_equal(roi, g["full_u8_%d" % i])
+        assert np.array_equal(evalside.to_tensor_normalize(roi), g["full_f32_%d" % i])

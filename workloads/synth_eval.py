@@ -56,3 +56,26 @@ def make_csv_rows(seed):
     img = [int(v) for v in rng.integers(0, 2000, n)]
     scores = [1, 0.75, 1, -1, np.float64(0.5), 1, np.float32(0.25)]
     return scene, img, Rs, ts, scores
+
+
+CROP_CASES = [(256, "crop_square_resize"), (256, "crop_resize"), (128, "crop_square_resize"), (64, "crop_resize")]
+N_CROP_BOXES = 14
+
+
+def make_image(seed, H=480, W=640):
+    """uint8 RGB test image: smooth gradients + texture + noise (edges and flat areas both present)"""
+    rng = np.random.default_rng(seed)
+    y, x = np.mgrid[0:H, 0:W]
+    img = np.stack([127 + 120 * np.sin(x / 37.0) * np.cos(y / 23.0), (x * 255.0 / W + y) % 256, 40 + 0.3 * ((x // 16 + y // 16) % 2) * 600], -1)
+    img = img + rng.normal(0, 12, img.shape)
+    return np.clip(np.rint(img), 0, 255).astype(np.uint8)
+
+
+def make_crop_boxes(n, seed, H=480, W=640):
+    """integer boxes x,y,w,h as padding_Bbox returns them: inside, partly outside on every side, tall, wide, tiny,
+    exactly 2 x the crop size (the INTER_AREA switch of cv2.resize)"""
+    rng = np.random.default_rng(seed)
+    b = np.stack([rng.integers(-80, W - 40, n), rng.integers(-80, H - 40, n), rng.integers(8, 330, n), rng.integers(8, 330, n)], 1)
+    b[0] = [100, 60, 256, 256]; b[1] = [40, 30, 512, 512]; b[2] = [-50, -40, 200, 120]; b[3] = [500, 380, 300, 90]
+    b[4] = [320, 200, 9, 31]; b[5] = [10, 10, 128, 128]
+    return b.astype(np.int64)

@@ -68,6 +68,128 @@ __global__ void zp_bbox_kernel(const double* __restrict__ in, int B, double pad_
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// input crops: get_roi (crop_resize / crop_square_resize + cv2.resize INTER_LINEAR) + ToTensor + Normalize
+// (bop_dataset_pytorch.py:36-89, 110-121, 334-347).  One thread per output pixel; the zero-padded square canvas of
+// crop_square_resize is never materialised (a tap outside the copied rectangle reads 0).  The resize is OpenCV's 8-bit
+// fixed-point bilinear, restated instruction for instruction so that the crop is bit-identical to the reference's:
+// float32 tap position from a float64 product, 11-bit coefficients rounded half-to-even, columns clamped with the
+// fraction reset, rows clamped without, vertical pass (((b0*(S0>>4))>>16) + ((b1*(S1>>4))>>16) + 2) >> 2, and the
+// INTER_AREA switch for an exact 2x2 decimation.  HBM-bound on the output write (3 * sizeof(out) bytes per pixel).
+// ---------------------------------------------------------------------------------------------------------------
+struct CropArgs {
+    const uint8_t* images; int n_img, H, W;
+    const int32_t* img_ids; const double* boxes;
+    int B, cs, method, out_bf16, channels_last;
+    float mean[3], stdv[3];
+    void* out; uint8_t* out_u8;
+};
+
+struct CropGeom {      // canvas (cw x ch) and the rectangle of it that holds image pixels
+    int cw, ch, rx1, ry1, rx2, ry2, x1, y1;
+};
+
+__device__ __forceinline__ CropGeom zp_crop_geom(const double* bb, int method, int H, int W) {
+    CropGeom g;
+    const long long bx = __double2ll_rz(bb[0]), by = __double2ll_rz(bb[1]);
+    if (method == ZP_CROP_SQUARE_RESIZE) {
+        const long long bw = max(__double2ll_rz(bb[2]), 0ll), bh = max(__double2ll_rz(bb[3]), 0ll);
+        double fx1 = (double)bx, fx2 = (double)(bx + bw), fy1 = (double)by, fy2 = (double)(by + bh);
+        const double cx = 0.5 * (fx1 + fx2), cy = 0.5 * (fy1 + fy2);
+        if (bh > bw) { fx1 = cx - (double)bh / 2; fx2 = cx + (double)bh / 2; }
+        else { fy1 = cy - (double)bw / 2; fy2 = cy + (double)bw / 2; }
+        long long x1 = __double2ll_rz(fx1), y1 = __double2ll_rz(fy1), x2 = __double2ll_rz(fx2), y2 = __double2ll_rz(fy2);
+        const long long side = max(bh, bw);
+        long long rx1 = max(-x1, 0ll); x1 = max(x1, 0ll);
+        long long rx2 = rx1 + min((long long)W - x1, x2 - x1);
+        long long ry1 = max(-y1, 0ll); y1 = max(y1, 0ll);
+        long long ry2 = ry1 + min((long long)H - y1, y2 - y1);
+        g.cw = g.ch = (int)side;
+        g.rx1 = (int)min(rx1, side); g.ry1 = (int)min(ry1, side);
+        g.rx2 = (int)min(max(rx2, rx1), side); g.ry2 = (int)min(max(ry2, ry1), side);     // numpy clips the slice to the canvas
+        g.x1 = (int)x1; g.y1 = (int)y1;
+    } else {
+        const long long bw = __double2ll_rz(bb[2]), bh = __double2ll_rz(bb[3]);
+        const long long x1 = max(0ll, bx), x2 = min((long long)W, bx + bw), y1 = max(0ll, by), y2 = min((long long)H, by + bh);
+        g.cw = (int)max(x2 - x1, 0ll); g.ch = (int)max(y2 - y1, 0ll);
+        g.rx1 = 0; g.ry1 = 0; g.rx2 = g.cw; g.ry2 = g.ch;
+        g.x1 = (int)x1; g.y1 = (int)y1;
+    }
+    return g;
+}
+
+// cv2's per-axis tap: position, neighbour and the two 11-bit weights (reset = columns: fraction zeroed at the borders)
+__device__ __forceinline__ void zp_resize_tap(int d, int dn, int sn, bool reset, int& i0, int& i1, int& w0, int& w1) {
+    const double scale = __ddiv_rn(1.0, __ddiv_rn((double)dn, (double)sn));
+    float f = (float)__dsub_rn(__dmul_rn((double)d + 0.5, scale), 0.5);      // no FMA contraction: cv2 rounds twice
+    int s = (int)floorf(f);
+    f = __fsub_rn(f, (float)s);
+    if (reset) {
+        if (s < 0) { f = 0.f; s = 0; }
+        if (s >= sn - 1) { f = 0.f; s = sn - 1; }
+        i0 = s; i1 = min(s + 1, sn - 1);
+    } else {
+        i0 = min(max(s, 0), sn - 1); i1 = min(max(s + 1, 0), sn - 1);
+    }
+    w0 = __float2int_rn(__fmul_rn(__fsub_rn(1.f, f), 2048.f));
+    w1 = __float2int_rn(__fmul_rn(f, 2048.f));
+}
+
+__global__ void __launch_bounds__(256) zp_crop_kernel(CropArgs a) {
+    const int b = blockIdx.y;
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    const int cs = a.cs;
+    if (p >= cs * cs) return;
+    const int oy = p / cs, ox = p - oy * cs;
+    const CropGeom g = zp_crop_geom(a.boxes + 4 * (size_t)b, a.method, a.H, a.W);
+    const int id = a.img_ids ? a.img_ids[b] : 0;
+    const uint8_t* img = a.images + (size_t)min(max(id, 0), a.n_img - 1) * a.H * a.W * 3;
+    int v[3] = {0, 0, 0};
+    if (g.cw > 0 && g.ch > 0) {
+        auto tap = [&](int r, int c, int* o) {
+            if (r >= g.ry1 && r < g.ry2 && c >= g.rx1 && c < g.rx2) {
+                const int sy = g.y1 + r - g.ry1, sx = g.x1 + c - g.rx1;
+                if (sy < a.H && sx < a.W) {
+                    const uint8_t* q = img + ((size_t)sy * a.W + sx) * 3;
+                    o[0] = q[0]; o[1] = q[1]; o[2] = q[2];
+                    return;
+                }
+            }
+            o[0] = o[1] = o[2] = 0;
+        };
+        if (g.cw == 2 * cs && g.ch == 2 * cs) {          // exact 2x2 decimation: cv2 uses INTER_AREA's rounded mean
+            int t00[3], t01[3], t10[3], t11[3];
+            tap(2 * oy, 2 * ox, t00); tap(2 * oy, 2 * ox + 1, t01); tap(2 * oy + 1, 2 * ox, t10); tap(2 * oy + 1, 2 * ox + 1, t11);
+#pragma unroll
+            for (int c = 0; c < 3; c++) v[c] = (t00[c] + t01[c] + t10[c] + t11[c] + 2) >> 2;
+        } else {
+            int x0, x1, a0, a1, r0, r1, b0, b1;
+            zp_resize_tap(ox, cs, g.cw, true, x0, x1, a0, a1);
+            zp_resize_tap(oy, cs, g.ch, false, r0, r1, b0, b1);
+            int t00[3], t01[3], t10[3], t11[3];
+            tap(r0, x0, t00); tap(r0, x1, t01); tap(r1, x0, t10); tap(r1, x1, t11);
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                const int S0 = t00[c] * a0 + t01[c] * a1, S1 = t10[c] * a0 + t11[c] * a1;
+                v[c] = ((((b0 * (S0 >> 4)) >> 16) + ((b1 * (S1 >> 4)) >> 16) + 2) >> 2) & 0xff;
+            }
+        }
+    }
+    if (a.out_u8) {
+        uint8_t* o = a.out_u8 + ((size_t)b * cs * cs + p) * 3;
+        o[0] = (uint8_t)v[0]; o[1] = (uint8_t)v[1]; o[2] = (uint8_t)v[2];
+    }
+    if (!a.out) return;
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        // ToTensor: uint8 -> float32 / 255; Normalize: (x - mean) / std, all IEEE float32 like torch's CPU kernels
+        const float f = __fdiv_rn(__fsub_rn(__fdiv_rn((float)v[c], 255.f), a.mean[c]), a.stdv[c]);
+        const size_t idx = a.channels_last ? ((size_t)b * cs * cs + p) * 3 + c : ((size_t)b * 3 + c) * cs * cs + p;
+        if (a.out_bf16) ((__nv_bfloat16*)a.out)[idx] = __float2bfloat16_rn(f);
+        else ((float*)a.out)[idx] = f;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // ADD / ADI
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int EV_PREP_THREADS = 256;
@@ -259,6 +381,28 @@ int zp_final_bbox(zp_ctx* ctx, const double* det_boxes, int B, double padding_ra
     ZP_CUDA(ctx, cudaSetDevice(ctx->device));
     zp_bbox_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(det_boxes, B, padding_ratio, resize_method, max_x, max_y, out_boxes);
     ZP_CHECK_LAUNCH(ctx, "zp_bbox_kernel");
+    return 0;
+}
+
+int zp_crop_input(zp_ctx* ctx, const uint8_t* images, int n_img, int H, int W, const int32_t* img_ids, const double* boxes,
+                  int B, int crop_size, int resize_method, const float* mean3, const float* std3, int out_dtype,
+                  int channels_last, void* out, uint8_t* out_u8, void* stream) {
+    if (!ctx) return -1;
+    if (B == 0) return 0;
+    if (B < 0 || !images || !boxes || (!out && !out_u8) || n_img < 1 || H < 1 || W < 1) ZP_FAIL(ctx, -1, "zp_crop_input: bad argument");
+    if (crop_size < 1 || crop_size > 4096) ZP_FAIL(ctx, -1, "zp_crop_input: bad crop size %d", crop_size);
+    if (resize_method != ZP_CROP_RESIZE && resize_method != ZP_CROP_SQUARE_RESIZE)
+        ZP_FAIL(ctx, -1, "zp_crop_input: resize method %d not supported (crop_resize | crop_square_resize; the warp-affine variant is not on this path)", resize_method);
+    if (out_dtype != ZP_DTYPE_F32 && out_dtype != ZP_DTYPE_BF16) ZP_FAIL(ctx, -1, "zp_crop_input: bad output dtype %d", out_dtype);
+    ZP_CUDA(ctx, cudaSetDevice(ctx->device));
+    CropArgs a{};
+    a.images = images; a.n_img = n_img; a.H = H; a.W = W; a.img_ids = img_ids; a.boxes = boxes;
+    a.B = B; a.cs = crop_size; a.method = resize_method; a.out_bf16 = out_dtype == ZP_DTYPE_BF16; a.channels_last = channels_last != 0;
+    const float dm[3] = {0.485f, 0.456f, 0.406f}, ds[3] = {0.229f, 0.224f, 0.225f};       // bop_dataset_pytorch.py:336
+    for (int c = 0; c < 3; c++) { a.mean[c] = mean3 ? mean3[c] : dm[c]; a.stdv[c] = std3 ? std3[c] : ds[c]; }
+    a.out = out; a.out_u8 = out_u8;
+    zp_crop_kernel<<<dim3((crop_size * crop_size + 255) / 256, B), 256, 0, (cudaStream_t)stream>>>(a);
+    ZP_CHECK_LAUNCH(ctx, "zp_crop_kernel");
     return 0;
 }
 

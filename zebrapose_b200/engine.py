@@ -330,6 +330,30 @@ class Engine:
         self.ctx.check(rc, "zp_final_bbox")
         return out
 
+    def crop_inputs(self, images, padded_boxes, img_ids=None, *, crop_size=256, resize_method="crop_square_resize",
+                    dtype=torch.float32, channels_last=False, return_u8=False):
+        """get_roi(INTER_LINEAR) + ToTensor + Normalize (bop_dataset_pytorch.py:110-121, 334-347) for B boxes at once:
+        images uint8 [n_img,H,W,3] | [H,W,3] on the device, padded_boxes [B,4] (output of padding_Bbox), img_ids [B] | None.
+        Returns the network input [B,3,cs,cs] (float32 | bfloat16; channels_last memory format if asked) (, uint8 crops)."""
+        im = torch.as_tensor(images)
+        if im.dim() == 3:
+            im = im.unsqueeze(0)
+        if im.dtype != torch.uint8 or im.dim() != 4 or im.shape[3] != 3:
+            raise TypeError("images must be uint8 [n_img,H,W,3]")
+        im = im.to(self.device).contiguous()
+        bb = torch.as_tensor(padded_boxes).to(device=self.device, dtype=torch.float64).contiguous().reshape(-1, 4)
+        B = bb.shape[0]
+        ids = None if img_ids is None else torch.as_tensor(img_ids).to(device=self.device, dtype=torch.int32).contiguous()
+        cs = int(crop_size)
+        out = torch.empty((B, 3, cs, cs), dtype=dtype, device=self.device,
+                          memory_format=torch.channels_last if channels_last else torch.contiguous_format)
+        u8 = torch.empty((B, cs, cs, 3), dtype=torch.uint8, device=self.device) if return_u8 else None
+        rc = self.lib.zp_crop_input(self.ctx.handle, _ptr(im), im.shape[0], im.shape[1], im.shape[2], _ptr(ids), _ptr(bb), B,
+                                    cs, _lib.RESIZE[resize_method], C.c_void_p(), C.c_void_p(), _DT[dtype],
+                                    1 if channels_last else 0, _ptr(out), _ptr(u8), _stream())
+        self.ctx.check(rc, "zp_crop_input")
+        return (out, u8) if return_u8 else out
+
     def upload_model(self, obj_id, vertices):
         """Model vertices [V,3] (mm) of object slot obj_id for pose_errors().  Synchronises."""
         v = np.ascontiguousarray(np.asarray(vertices, np.float64).reshape(-1, 3))
