@@ -184,6 +184,16 @@ def next_rows(eng, timed, d_bbox, d_K, d_obj, crops, tables, C, hbm_peak, fp32_p
                           "frac_of_hbm_peak": round(alg / ms / 1e6 / hbm_peak, 3), "crops_per_s": round(C / ms * 1e3),
                           "kernels": "zp_head_codes_kernel (tcgen05 + TMA) + zp_decode_emit_kernel"}
     del x, xs
+    # N2: the network's input crops from a device-resident 480 x 640 frame (get_roi + ToTensor + Normalize), fp32 NCHW as
+    # the reference feeds its network and bf16 channels_last as a B200 network wants them
+    img = torch.from_numpy(synth_eval.make_image(5)).cuda()
+    boxes = torch.from_numpy(synth_eval.make_crop_boxes(C, 8).astype(np.float64)).cuda()
+    ms32 = timed(lambda: eng.crop_inputs(img, boxes, crop_size=256), reps=10)
+    ms16 = timed(lambda: eng.crop_inputs(img, boxes, crop_size=256, dtype=torch.bfloat16, channels_last=True), reps=10)
+    out["input_crops"] = {"us_f32_nchw": round(ms32 * 1e3, 1), "us_bf16_channels_last": round(ms16 * 1e3, 1),
+                          "GBps_written_f32": round(C * 3 * 256 * 256 * 4 / ms32 / 1e6, 1),
+                          "frac_of_hbm_peak_f32": round(C * 3 * 256 * 256 * 4 / ms32 / 1e6 / hbm_peak, 3),
+                          "crops_per_s_f32": round(C / ms32 * 1e3)}
     V = 5841
     n_obj = len(tables)
     for j in range(n_obj):

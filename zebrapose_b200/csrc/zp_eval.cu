@@ -109,7 +109,12 @@ __device__ __forceinline__ CropGeom zp_crop_geom(const double* bb, int method, i
         g.x1 = (int)x1; g.y1 = (int)y1;
     } else {
         const long long bw = __double2ll_rz(bb[2]), bh = __double2ll_rz(bb[3]);
-        const long long x1 = max(0ll, bx), x2 = min((long long)W, bx + bw), y1 = max(0ll, by), y2 = min((long long)H, by + bh);
+        const long long x1 = max(0ll, bx), y1 = max(0ll, by);
+        long long x2 = min((long long)W, bx + bw), y2 = min((long long)H, by + bh);
+        // the reference slices img[y1:y2, x1:x2] (bop_dataset_pytorch.py:86): a NEGATIVE stop (box entirely above / left of
+        // the image) counts from the far edge in numpy, so such a box crops almost the whole image -- reproduced, not fixed
+        if (x2 < 0) x2 = max((long long)W + x2, 0ll);
+        if (y2 < 0) y2 = max((long long)H + y2, 0ll);
         g.cw = (int)max(x2 - x1, 0ll); g.ch = (int)max(y2 - y1, 0ll);
         g.rx1 = 0; g.ry1 = 0; g.rx2 = g.cw; g.ry2 = g.ch;
         g.x1 = (int)x1; g.y1 = (int)y1;
