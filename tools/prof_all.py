@@ -20,10 +20,14 @@ x = torch.randn(C, 256, 128, 128, generator=g).cuda().to(torch.bfloat16).contigu
 xs = torch.randn(C, 64, 128, 128, generator=g).cuda().to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
 for j in range(len(tables)): eng.upload_model(j, synth_eval.make_model(5841, 100 + j))
 gt = torch.from_numpy(bench.gt_poses(crops)).cuda()
+img = torch.from_numpy(synth_eval.make_image(5)).cuda()
+cboxes = torch.from_numpy(synth_eval.make_crop_boxes(C, 8).astype(np.float64)).cuda()
 for _ in range(2):
     corr, counts = eng.decode(lg, bb, oi)
     r = eng.ransac(corr, counts, K)
     eng.head_decode(x, xs, bb, oi)
     eng.pose_errors(r["poses"], gt, oi)
+    eng.crop_inputs(img, cboxes, crop_size=256)
+    eng.final_bboxes(cboxes, 1.5, "crop_square_resize", 640, 480)
 torch.cuda.synchronize()
 print("ok", int(counts.sum()))

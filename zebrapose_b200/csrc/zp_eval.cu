@@ -69,7 +69,8 @@ __global__ void zp_bbox_kernel(const double* __restrict__ in, int B, double pad_
 
 // ---------------------------------------------------------------------------------------------------------------
 // input crops: get_roi (crop_resize / crop_square_resize + cv2.resize INTER_LINEAR) + ToTensor + Normalize
-// (bop_dataset_pytorch.py:36-89, 110-121, 334-347).  One thread per output pixel; the zero-padded square canvas of
+// (bop_dataset_pytorch.py:36-89, 110-121, 334-347).  A CTA = 16 output rows, a thread = one column (its tap position and
+// weights computed once; the rows' taps and the 3 x 256 ToTensor+Normalize values sit in shared memory); the zero-padded square canvas of
 // crop_square_resize is never materialised (a tap outside the copied rectangle reads 0).  The resize is OpenCV's 8-bit
 // fixed-point bilinear, restated instruction for instruction so that the crop is bit-identical to the reference's:
 // float32 tap position from a float64 product, 11-bit coefficients rounded half-to-even, columns clamped with the
@@ -139,58 +140,73 @@ __device__ __forceinline__ void zp_resize_tap(int d, int dn, int sn, bool reset,
     w1 = __float2int_rn(__fmul_rn(f, 2048.f));
 }
 
+constexpr int CROP_ROWS = 16;          // output rows per CTA: a thread owns a column, its tap and weights are computed once
+
 __global__ void __launch_bounds__(256) zp_crop_kernel(CropArgs a) {
-    const int b = blockIdx.y;
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    const int cs = a.cs;
-    if (p >= cs * cs) return;
-    const int oy = p / cs, ox = p - oy * cs;
+    __shared__ float s_lut[3][256];      // ToTensor + Normalize of every uint8 value, per channel (exact IEEE divisions, once)
+    __shared__ int s_row[CROP_ROWS][4];  // byte offset of source row r0 / r1 (-1: outside the copied rectangle), b0, b1
+    const int b = blockIdx.y, cs = a.cs, tid = threadIdx.x;
+    const int oy0 = blockIdx.x * CROP_ROWS;
     const CropGeom g = zp_crop_geom(a.boxes + 4 * (size_t)b, a.method, a.H, a.W);
     const int id = a.img_ids ? a.img_ids[b] : 0;
     const uint8_t* img = a.images + (size_t)min(max(id, 0), a.n_img - 1) * a.H * a.W * 3;
-    int v[3] = {0, 0, 0};
-    if (g.cw > 0 && g.ch > 0) {
-        auto tap = [&](int r, int c, int* o) {
-            if (r >= g.ry1 && r < g.ry2 && c >= g.rx1 && c < g.rx2) {
-                const int sy = g.y1 + r - g.ry1, sx = g.x1 + c - g.rx1;
-                if (sy < a.H && sx < a.W) {
-                    const uint8_t* q = img + ((size_t)sy * a.W + sx) * 3;
-                    o[0] = q[0]; o[1] = q[1]; o[2] = q[2];
-                    return;
-                }
-            }
-            o[0] = o[1] = o[2] = 0;
-        };
-        if (g.cw == 2 * cs && g.ch == 2 * cs) {          // exact 2x2 decimation: cv2 uses INTER_AREA's rounded mean
-            int t00[3], t01[3], t10[3], t11[3];
-            tap(2 * oy, 2 * ox, t00); tap(2 * oy, 2 * ox + 1, t01); tap(2 * oy + 1, 2 * ox, t10); tap(2 * oy + 1, 2 * ox + 1, t11);
+    const bool empty = g.cw <= 0 || g.ch <= 0;
+    const bool area2 = g.cw == 2 * cs && g.ch == 2 * cs;     // exact 2x2 decimation: cv2 uses INTER_AREA's rounded mean
 #pragma unroll
-            for (int c = 0; c < 3; c++) v[c] = (t00[c] + t01[c] + t10[c] + t11[c] + 2) >> 2;
-        } else {
-            int x0, x1, a0, a1, r0, r1, b0, b1;
-            zp_resize_tap(ox, cs, g.cw, true, x0, x1, a0, a1);
-            zp_resize_tap(oy, cs, g.ch, false, r0, r1, b0, b1);
-            int t00[3], t01[3], t10[3], t11[3];
-            tap(r0, x0, t00); tap(r0, x1, t01); tap(r1, x0, t10); tap(r1, x1, t11);
+    for (int c = 0; c < 3; c++)          // ToTensor: uint8 -> float32 / 255; Normalize: (x - mean) / std, IEEE float32 like torch
+        s_lut[c][tid] = __fdiv_rn(__fsub_rn(__fdiv_rn((float)tid, 255.f), a.mean[c]), a.stdv[c]);
+    auto row_off = [&](int r) { return (r >= g.ry1 && r < g.ry2 && g.y1 + r - g.ry1 < a.H) ? (g.y1 + r - g.ry1) * a.W * 3 : -1; };
+    auto col_off = [&](int c) { return (c >= g.rx1 && c < g.rx2 && g.x1 + c - g.rx1 < a.W) ? (g.x1 + c - g.rx1) * 3 : -1; };
+    if (tid < CROP_ROWS && oy0 + tid < cs && !empty) {
+        int r0, r1, b0 = 0, b1 = 0;
+        if (area2) { r0 = 2 * (oy0 + tid); r1 = r0 + 1; }
+        else zp_resize_tap(oy0 + tid, cs, g.ch, false, r0, r1, b0, b1);
+        s_row[tid][0] = row_off(r0); s_row[tid][1] = row_off(r1); s_row[tid][2] = b0; s_row[tid][3] = b1;
+    }
+    __syncthreads();
+    const size_t plane = (size_t)cs * cs;
+    for (int ox = tid; ox < cs; ox += blockDim.x) {
+        int x0 = 0, x1 = 0, a0 = 0, a1 = 0;
+        if (!empty) {
+            if (area2) { x0 = 2 * ox; x1 = x0 + 1; }
+            else zp_resize_tap(ox, cs, g.cw, true, x0, x1, a0, a1);
+        }
+        const int c0 = empty ? -1 : col_off(x0), c1 = empty ? -1 : col_off(x1);
+        for (int j = 0; j < CROP_ROWS && oy0 + j < cs; j++) {
+            const int ro0 = s_row[j][0], ro1 = s_row[j][1], b0 = s_row[j][2], b1 = s_row[j][3];
+            // a tap outside the copied rectangle reads the zero padding of the canvas
+            const uint8_t* q00 = img + ro0 + c0; const bool v00 = !empty && (ro0 | c0) >= 0;
+            const uint8_t* q01 = img + ro0 + c1; const bool v01 = !empty && (ro0 | c1) >= 0;
+            const uint8_t* q10 = img + ro1 + c0; const bool v10 = !empty && (ro1 | c0) >= 0;
+            const uint8_t* q11 = img + ro1 + c1; const bool v11 = !empty && (ro1 | c1) >= 0;
+            int v[3];
 #pragma unroll
             for (int c = 0; c < 3; c++) {
-                const int S0 = t00[c] * a0 + t01[c] * a1, S1 = t10[c] * a0 + t11[c] * a1;
-                v[c] = ((((b0 * (S0 >> 4)) >> 16) + ((b1 * (S1 >> 4)) >> 16) + 2) >> 2) & 0xff;
+                const int t00 = v00 ? q00[c] : 0, t01 = v01 ? q01[c] : 0, t10 = v10 ? q10[c] : 0, t11 = v11 ? q11[c] : 0;
+                if (area2) v[c] = (t00 + t01 + t10 + t11 + 2) >> 2;
+                else {
+                    const int S0 = t00 * a0 + t01 * a1, S1 = t10 * a0 + t11 * a1;
+                    v[c] = ((((b0 * (S0 >> 4)) >> 16) + ((b1 * (S1 >> 4)) >> 16) + 2) >> 2) & 0xff;
+                }
+            }
+            const size_t p = (size_t)(oy0 + j) * cs + ox;
+            if (a.out_u8) {
+                uint8_t* o = a.out_u8 + ((size_t)b * plane + p) * 3;
+                o[0] = (uint8_t)v[0]; o[1] = (uint8_t)v[1]; o[2] = (uint8_t)v[2];
+            }
+            if (a.out) {
+                const float f0 = s_lut[0][v[0]], f1 = s_lut[1][v[1]], f2 = s_lut[2][v[2]];
+                if (a.channels_last) {
+                    const size_t i3 = ((size_t)b * plane + p) * 3;
+                    if (a.out_bf16) { __nv_bfloat16* o = (__nv_bfloat16*)a.out + i3; o[0] = __float2bfloat16_rn(f0); o[1] = __float2bfloat16_rn(f1); o[2] = __float2bfloat16_rn(f2); }
+                    else { float* o = (float*)a.out + i3; o[0] = f0; o[1] = f1; o[2] = f2; }
+                } else {
+                    const size_t i0 = (size_t)b * 3 * plane + p;
+                    if (a.out_bf16) { __nv_bfloat16* o = (__nv_bfloat16*)a.out + i0; o[0] = __float2bfloat16_rn(f0); o[plane] = __float2bfloat16_rn(f1); o[2 * plane] = __float2bfloat16_rn(f2); }
+                    else { float* o = (float*)a.out + i0; o[0] = f0; o[plane] = f1; o[2 * plane] = f2; }
+                }
             }
         }
-    }
-    if (a.out_u8) {
-        uint8_t* o = a.out_u8 + ((size_t)b * cs * cs + p) * 3;
-        o[0] = (uint8_t)v[0]; o[1] = (uint8_t)v[1]; o[2] = (uint8_t)v[2];
-    }
-    if (!a.out) return;
-#pragma unroll
-    for (int c = 0; c < 3; c++) {
-        // ToTensor: uint8 -> float32 / 255; Normalize: (x - mean) / std, all IEEE float32 like torch's CPU kernels
-        const float f = __fdiv_rn(__fsub_rn(__fdiv_rn((float)v[c], 255.f), a.mean[c]), a.stdv[c]);
-        const size_t idx = a.channels_last ? ((size_t)b * cs * cs + p) * 3 + c : ((size_t)b * 3 + c) * cs * cs + p;
-        if (a.out_bf16) ((__nv_bfloat16*)a.out)[idx] = __float2bfloat16_rn(f);
-        else ((float*)a.out)[idx] = f;
     }
 }
 
@@ -396,6 +412,7 @@ int zp_crop_input(zp_ctx* ctx, const uint8_t* images, int n_img, int H, int W, c
     if (B == 0) return 0;
     if (B < 0 || !images || !boxes || (!out && !out_u8) || n_img < 1 || H < 1 || W < 1) ZP_FAIL(ctx, -1, "zp_crop_input: bad argument");
     if (crop_size < 1 || crop_size > 4096) ZP_FAIL(ctx, -1, "zp_crop_input: bad crop size %d", crop_size);
+    if ((long long)H * W * 3 > 0x7fffffffll) ZP_FAIL(ctx, -1, "zp_crop_input: image of %d x %d too large (32-bit byte offsets)", H, W);
     if (resize_method != ZP_CROP_RESIZE && resize_method != ZP_CROP_SQUARE_RESIZE)
         ZP_FAIL(ctx, -1, "zp_crop_input: resize method %d not supported (crop_resize | crop_square_resize; the warp-affine variant is not on this path)", resize_method);
     if (out_dtype != ZP_DTYPE_F32 && out_dtype != ZP_DTYPE_BF16) ZP_FAIL(ctx, -1, "zp_crop_input: bad output dtype %d", out_dtype);
@@ -406,7 +423,7 @@ int zp_crop_input(zp_ctx* ctx, const uint8_t* images, int n_img, int H, int W, c
     const float dm[3] = {0.485f, 0.456f, 0.406f}, ds[3] = {0.229f, 0.224f, 0.225f};       // bop_dataset_pytorch.py:336
     for (int c = 0; c < 3; c++) { a.mean[c] = mean3 ? mean3[c] : dm[c]; a.stdv[c] = std3 ? std3[c] : ds[c]; }
     a.out = out; a.out_u8 = out_u8;
-    zp_crop_kernel<<<dim3((crop_size * crop_size + 255) / 256, B), 256, 0, (cudaStream_t)stream>>>(a);
+    zp_crop_kernel<<<dim3((crop_size + CROP_ROWS - 1) / CROP_ROWS, B), 256, 0, (cudaStream_t)stream>>>(a);
     ZP_CHECK_LAUNCH(ctx, "zp_crop_kernel");
     return 0;
 }
