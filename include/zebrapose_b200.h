@@ -82,6 +82,17 @@ int zp_decode(zp_ctx* ctx, const void* logits, int dtype, int B, int S, const in
               const double* bbox, const int32_t* obj_ids, int obj_default,
               uint16_t* codes, float* corr, int cap, int32_t* counts, void* stream);
 
+/* zp_decode for the CE heads of the ablation configs (common_ops.py:21-30 + class_code_images_to_class_id_image with
+ * class_base = `base`, class_id_encoder_decoder.py:17-28): the code logits are n_digits groups of `base` consecutive
+ * channels starting at digit0_ch; a digit is the first maximum of the float32 softmax of its group, the class id the
+ * base-`base` number with digit 0 most significant.  base^n_digits <= 65536; the slot's table must hold at least that
+ * many rows with ignore_bit 0.  Everything else as zp_decode.  (A digit can differ from the reference's only where
+ * float32 softmax rounding creates or breaks an exact tie differently in torch's exp than in CUDA's.) */
+int zp_decode_ce(zp_ctx* ctx, const void* logits, int dtype, int B, int S, const int64_t strides[4],
+                 int mask_ch, int digit0_ch, int base, int n_digits, const uint8_t* ext_mask,
+                 const double* bbox, const int32_t* obj_ids, int obj_default,
+                 uint16_t* codes, float* corr, int cap, int32_t* counts, void* stream);
+
 /* Stand-alone device forms of two small reference helpers (the batched path has them fused into zp_decode):
  * mapping_pixel_position_to_original_position (CNN_output_to_pose.py:34-50): px int64 [N,2] (x,y) -> out int64 [N,2];
  * h_bbox is a HOST double[4].  class_code_images_to_class_id_image (class_id_encoder_decoder.py:17-28):

@@ -25,6 +25,7 @@ SIGNATURES = {
     "zp_upload_tables": (_i, [_vp, _i, _vp, _i, _i, _i]),
     "zp_download_tables": (_i, [_vp, _i, _vp, _vp]),
     "zp_decode": (_i, [_vp, _vp, _i, _i, _i, C.POINTER(_i64), _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _i, _vp, _vp]),
+    "zp_decode_ce": (_i, [_vp, _vp, _i, _i, _i, C.POINTER(_i64), _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _i, _vp, _vp]),
     "zp_make_samples": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _u64, _vp, _vp]),
     "zp_solve_minimal": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
     "zp_score": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _i, _i, _f, _vp, _vp]),

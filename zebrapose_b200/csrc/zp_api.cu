@@ -13,6 +13,8 @@ int zp_launch_final(zp_ctx*, const float*, int, const int32_t*, const double*, c
 int zp_launch_fma_probe(zp_ctx*, int, int, double*);
 int zp_read_debug_clocks(long long*);
 int zp_launch_remap_pixels(zp_ctx*, const int64_t*, int64_t, const double*, int, int64_t*, cudaStream_t);
+int zp_launch_decode_ce(zp_ctx*, const void*, int, int, int, const int64_t*, int, int, int, int, const uint8_t*, const double*,
+                        const int32_t*, int, uint16_t*, float*, int, int32_t*, cudaStream_t);
 int zp_launch_codes_to_ids(zp_ctx*, const double*, int64_t, int, int, double*, cudaStream_t);
 
 static thread_local std::string g_err;
@@ -235,6 +237,31 @@ int zp_decode(zp_ctx* ctx, const void* logits, int dtype, int B, int S, const in
     ZP_CUDA(ctx, cudaSetDevice(ctx->device));
     return zp_launch_decode(ctx, logits, dtype, B, S, strides, mask_ch, bit0_ch, n_bits - ignore_bit, ext_mask, bbox,
                             obj_ids, obj_default, codes, corr, cap, counts, (cudaStream_t)stream);
+}
+
+int zp_decode_ce(zp_ctx* ctx, const void* logits, int dtype, int B, int S, const int64_t strides[4], int mask_ch,
+                 int digit0_ch, int base, int n_digits, const uint8_t* ext_mask, const double* bbox,
+                 const int32_t* obj_ids, int obj_default, uint16_t* codes, float* corr, int cap, int32_t* counts,
+                 void* stream) {
+    if (!ctx) return -1;
+    if (B == 0) return 0;
+    if (!logits || !bbox || !corr || !counts || !strides) ZP_FAIL(ctx, -1, "zp_decode_ce: null argument");
+    if (dtype != ZP_DTYPE_F32 && dtype != ZP_DTYPE_BF16) ZP_FAIL(ctx, -1, "zp_decode_ce: dtype %d not supported", dtype);
+    if (B < 0 || S <= 0 || S > 1024 || S % 4 != 0 || cap <= 0) ZP_FAIL(ctx, -1, "zp_decode_ce: bad B/S/cap %d/%d/%d (S a multiple of 4)", B, S, cap);
+    if (base < 2 || base > 256 || n_digits < 1 || n_digits > 16) ZP_FAIL(ctx, -1, "zp_decode_ce: bad base/n_digits %d/%d", base, n_digits);
+    double classes = 1;
+    for (int d = 0; d < n_digits; d++) classes *= base;
+    if (classes > 65536.0) ZP_FAIL(ctx, -1, "zp_decode_ce: base^n_digits = %.0f exceeds the 16-bit class ids of the path", classes);
+    for (int o = 0; o < ZP_MAX_OBJECTS; o++) {
+        if (obj_ids ? !ctx->tables[o].pts : o != obj_default) continue;
+        const ZpTable& t = ctx->tables[o];
+        if (!t.pts) ZP_FAIL(ctx, -1, "zp_decode_ce: no dictionary uploaded for object slot %d", o);
+        if (t.ignore_bit != 0 || (double)((size_t)1 << t.n_bits) < classes)
+            ZP_FAIL(ctx, -1, "zp_decode_ce: slot %d holds a %d-bit/ignore %d table, %0.f classes need ignore_bit 0 and 2^n_bits >= classes", o, t.n_bits, t.ignore_bit, classes);
+    }
+    ZP_CUDA(ctx, cudaSetDevice(ctx->device));
+    return zp_launch_decode_ce(ctx, logits, dtype, B, S, strides, mask_ch, digit0_ch, base, n_digits, ext_mask, bbox, obj_ids,
+                               obj_default, codes, corr, cap, counts, (cudaStream_t)stream);
 }
 
 int zp_remap_pixels(zp_ctx* ctx, const int64_t* px, int64_t N, const double* h_bbox, int S, int64_t* out, void* stream) {

@@ -666,6 +666,76 @@ int zp_launch_emit_codes(zp_ctx* ctx, int B, int S, const double* bbox, const in
 }
 
 // -------------------------------------------------------------------------------------------------------------
+// CE heads (ablation configs, class_base = divided_num_each_interation > 2 or CE loss; common_ops.py:21-30): the code
+// logits are n_digits groups of `base` consecutive channels; the digit is the FIRST maximum of the float32 softmax of its
+// group (np.argmax of torch.softmax), the class id the base-`base` number with digit 0 most significant
+// (class_id_encoder_decoder.py:17-28).  One thread per pixel, one 128-pixel segment per CTA; writes the same 2 B/pixel
+// codes + mask ballot words as the binary plane kernel, so zp_decode_emit_kernel finishes the job.  Not a hot path.
+// -------------------------------------------------------------------------------------------------------------
+template <int DT>
+__global__ void __launch_bounds__(128) zp_decode_ce_kernel(DecodeArgs a, int base, int n_digits, uint16_t* __restrict__ codes,
+                                                            uint32_t* __restrict__ maskw, int segs_per_crop) {
+    const int S = a.S, N = S * S;
+    const int b = blockIdx.x / segs_per_crop, sg = blockIdx.x - b * segs_per_crop;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int p = sg * 128 + threadIdx.x;
+    bool masked = false;
+    if (p < N) {
+        const int row = p / S, col = p - row * S;
+        auto at = [&](int ch) -> float {
+            const size_t off = (size_t)b * a.sb + (size_t)ch * a.sc + (size_t)row * a.sh + (size_t)col * a.sw;
+            if (DT == ZP_DTYPE_F32) return ((const float*)a.logits)[off];
+            return __bfloat162float(((const __nv_bfloat16*)a.logits)[off]);
+        };
+        masked = a.ext_mask ? a.ext_mask[(size_t)b * N + p] != 0 : at(a.mask_ch) > 0.0f;
+        uint32_t id = 0;
+        for (int d = 0; d < n_digits; d++) {
+            const int c0 = a.bit0_ch + d * base;
+            float m = at(c0);
+            for (int k = 1; k < base; k++) m = fmaxf(m, at(c0 + k));
+            float sum = 0.f;
+            for (int k = 0; k < base; k++) sum = __fadd_rn(sum, expf(__fsub_rn(at(c0 + k), m)));
+            int best = 0;
+            float pb = -1.f;
+            for (int k = 0; k < base; k++) {
+                const float pk = __fdiv_rn(expf(__fsub_rn(at(c0 + k), m)), sum);
+                if (pk > pb) { pb = pk; best = k; }          // strictly greater: first maximum, as numpy.argmax
+            }
+            id = id * (uint32_t)base + (uint32_t)best;
+        }
+        codes[(size_t)b * N + p] = (uint16_t)id;
+    }
+    // mask ballot: pixel 4i + j of the segment -> bit i of word j (byte `warp` of each word belongs to this warp)
+    const uint32_t bal = __ballot_sync(0xffffffffu, masked);
+    if (lane < 4) {
+        uint32_t byte = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) byte |= ((bal >> (4 * k + lane)) & 1u) << k;
+        ((uint8_t*)maskw)[((size_t)(b * segs_per_crop + sg) * 4 + lane) * 4 + warp] = (uint8_t)byte;
+    }
+}
+
+int zp_launch_decode_ce(zp_ctx* ctx, const void* logits, int dtype, int B, int S, const int64_t strides[4], int mask_ch,
+                        int digit0_ch, int base, int n_digits, const uint8_t* ext_mask, const double* bbox,
+                        const int32_t* obj_ids, int obj_default, uint16_t* codes, float* corr, int cap, int32_t* counts,
+                        cudaStream_t st) {
+    DecodeArgs a{};
+    a.logits = logits; a.sb = strides[0]; a.sc = strides[1]; a.sh = strides[2]; a.sw = strides[3];
+    a.B = B; a.S = S; a.mask_ch = mask_ch; a.bit0_ch = digit0_ch; a.ext_mask = ext_mask;
+    const int N = S * S;
+    const int segs = (N + 127) / 128;
+    const size_t code_bytes = codes ? 0 : (((size_t)B * N * sizeof(uint16_t) + 255) & ~(size_t)255);
+    const size_t mask_bytes = (size_t)B * segs * 4 * sizeof(uint32_t);
+    if (dws_reserve(ctx, code_bytes + mask_bytes)) return -2;
+    uint16_t* d_codes = codes ? codes : (uint16_t*)ctx->dws;
+    uint32_t* maskw = (uint32_t*)((char*)ctx->dws + code_bytes);
+    if (dtype == ZP_DTYPE_F32) zp_decode_ce_kernel<ZP_DTYPE_F32><<<(unsigned)(B * segs), 128, 0, st>>>(a, base, n_digits, d_codes, maskw, segs);
+    else zp_decode_ce_kernel<ZP_DTYPE_BF16><<<(unsigned)(B * segs), 128, 0, st>>>(a, base, n_digits, d_codes, maskw, segs);
+    ZP_CHECK_LAUNCH(ctx, "zp_decode_ce_kernel");
+    return zp_launch_emit_codes(ctx, B, S, bbox, obj_ids, obj_default, d_codes, maskw, corr, cap, counts, st);
+}
+
+// -------------------------------------------------------------------------------------------------------------
 // Streaming path (contiguous planes): a producer warp pulls the logits of a crop part through a shared-memory ring of
 // 8 KB plane segments with 1-D TMA bulk copies (cp.async.bulk + full/empty mbarriers, SASS UBLKCP), so the memory
 // system always has up to 12 x 8 KB per CTA in flight while the four consumer warps pack codes, rank, gather and

@@ -120,6 +120,33 @@ class Engine:
         self.ctx.check(rc, "zp_decode")
         return (corr, counts, codes) if return_codes else (corr, counts)
 
+    def decode_ce(self, logits, bboxes, obj_ids=None, *, base, n_digits, obj_default=0, mask_ch=0, digit0_ch=1, ext_mask=None,
+                  return_codes=False, cap=None):
+        """decode() for the CE heads of the ablation configs (common_ops.py:21-30): `n_digits` groups of `base`
+        consecutive code channels, digit = first maximum of the group's float32 softmax, id in base `base`."""
+        if isinstance(logits, (tuple, list)):
+            logits, mask_ch, digit0_ch = self._join_views(*logits)
+        if logits.dim() != 4 or logits.shape[2] != logits.shape[3] or logits.dtype not in _DT:
+            raise ValueError("logits must be float32 | bfloat16 [B,C,S,S]")
+        B, Cc, S, _ = logits.shape
+        if digit0_ch + base * n_digits > Cc or mask_ch >= Cc:
+            raise ValueError("channel layout exceeds the %d channels of logits" % Cc)
+        cap = int(cap or ((S * S + 3) // 4) * 4)
+        bb = torch.as_tensor(bboxes).to(device=self.device, dtype=torch.float64).contiguous().reshape(B, 4)
+        oid = None if obj_ids is None else torch.as_tensor(obj_ids).to(device=self.device, dtype=torch.int32).contiguous()
+        em = None
+        if ext_mask is not None:
+            em = (torch.as_tensor(ext_mask).to(device=self.device) != 0).to(torch.uint8).contiguous().reshape(B, S, S)
+        corr = torch.empty((B, 5, cap), dtype=torch.float32, device=self.device)
+        counts = torch.empty((B,), dtype=torch.int32, device=self.device)
+        codes = torch.empty((B, S, S), dtype=torch.uint16, device=self.device) if return_codes else None
+        strides = (C.c_int64 * 4)(*logits.stride())
+        rc = self.lib.zp_decode_ce(self.ctx.handle, _ptr(logits), _DT[logits.dtype], B, S, strides, int(mask_ch),
+                                   int(digit0_ch), int(base), int(n_digits), _ptr(em), _ptr(bb), _ptr(oid), int(obj_default),
+                                   _ptr(codes), _ptr(corr), cap, _ptr(counts), _stream())
+        self.ctx.check(rc, "zp_decode_ce")
+        return (corr, counts, codes) if return_codes else (corr, counts)
+
     @staticmethod
     def _join_views(mask_logits, code_logits):
         """(mask, code) views of one [B,C,S,S] tensor -> (base tensor view, mask_ch, bit0_ch) without a copy."""
