@@ -233,13 +233,16 @@ int zp_upload_head(zp_ctx* ctx, const float* weight, const float* bias, int n_ou
 /* Replaces `conv_1x1_4(torch.cat([x, x_128], 1))` (model/aspp.py:112) + the whole of zp_decode: the 1x1 convolution runs
  * on the tensor cores (tcgen05, accumulators in TMEM, activations streamed by TMA), its epilogue thresholds and packs
  * the bits, and the correspondence lists are emitted from 2 B/pixel codes -- the logits are never written.
- *   x      bfloat16 [B,S,S,c1] (channels-last: the memory of a torch channels_last [B,c1,S,S] tensor), 16-byte aligned
- *   x_skip bfloat16 [B,S,S,c2] or NULL with c2 = 0 (the skip connection the reference concatenates); c1 + c2 = c_in
+ *   x      [B,S,S,c1] (channels-last: the memory of a torch channels_last [B,c1,S,S] tensor), 16-byte aligned;
+ *          dtype ZP_DTYPE_BF16 (kind::f16 MMA; c1, c2 multiples of 64) or ZP_DTYPE_F32 (kind::tf32 MMA: the products use
+ *          the operands' top 10 mantissa bits, accumulation is fp32; c1, c2 multiples of 32)
+ *   x_skip [B,S,S,c2] or NULL with c2 = 0 (the skip connection the reference concatenates); c1 + c2 = c_in
  *   mask_ch / bit0_ch / n_bits / ignore_bit: output-channel layout as in zp_decode (0 / 1 / 16 / k)
  *   other arguments and outputs exactly as zp_decode.  S*S must be a multiple of 128.
- * A pixel's bit is (sum_c bf16(w[o][c]) * x[c] in fp32 + bias[o]) > 0: it equals the reference's fp32 convolution of the
- * same bf16 values except where |logit| is within fp32 summation-order noise of zero (tests/test_gpu_head.py). */
-int zp_head_decode(zp_ctx* ctx, const void* x, int c1, const void* x_skip, int c2, int B, int S,
+ * A pixel's bit is (sum_c w[o][c] * x[c] accumulated in fp32 + bias[o]) > 0 with w, x in bf16 (or tf32): it equals the
+ * reference's fp32 convolution of the same bf16 values except where |logit| is within fp32 summation-order noise of zero;
+ * for fp32 activations the tf32 products add a relative 2^-10 per term (tolerances in tests/test_gpu_head.py). */
+int zp_head_decode(zp_ctx* ctx, const void* x, int c1, const void* x_skip, int c2, int dtype, int B, int S,
                    int mask_ch, int bit0_ch, int n_bits, int ignore_bit,
                    const double* bbox, const int32_t* obj_ids, int obj_default,
                    uint16_t* codes, float* corr, int cap, int32_t* counts, void* stream);

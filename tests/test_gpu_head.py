@@ -163,3 +163,53 @@ def test_head_pose_batch_equals_logit_path(eng):
     p2, n2, s2 = eng.decode_and_pose_batch(torch.from_numpy(logits).cuda(), bboxes, Ks)
     assert torch.equal(p1, p2) and torch.equal(n1, n2) and torch.equal(s1, s2)
     assert int(s1.sum()) == 0
+
+
+def test_head_fp32_activations_tf32(eng):
+    """float32 channels_last activations take the kind::tf32 tensor-core path: products of the operands' top 10 mantissa
+    bits, fp32 accumulation.  Against the float64 convolution of the full-precision values a bit may differ only where
+    |logit| <= TF32_TOL = 3e-2 (320 terms of relative error <= 2^-10 on products of magnitude <= ~1); on the structured
+    activations (|logit| > 0.5) the correspondence lists equal the oracle's exactly."""
+    TF32_TOL = 3e-2
+    S, B = 128, 3
+    tab, nrm, _ = synth.make_dict(16, seed=3, radius=51.0, missing_frac=0.1)
+    eng.upload_dict(0, tab, n_bits=16, ignore_bit=0, nonexist="zero")
+    crops = [synth.make_crop(tab, nrm, 9200 + i, S=S) for i in range(B)]
+    logits = np.stack([synth.crop_to_logits(c) for c in crops])
+    bboxes = np.stack([c["bbox"] for c in crops])
+    g = torch.Generator(device="cpu").manual_seed(4)
+    W = (torch.randn(17, 320, generator=g) * 0.3).cuda()
+    bias = (torch.randn(17, generator=g) * 0.2).cuda()
+    B_, Co = logits.shape[0], logits.shape[1]
+    L = torch.from_numpy(logits).cuda().double().permute(0, 2, 3, 1).reshape(-1, Co) - bias.double()
+    xall = (L @ torch.linalg.pinv(W.double()).T).float().reshape(B_, S, S, -1).permute(0, 3, 1, 2).contiguous(memory_format=torch.channels_last)
+    x = xall[:, :256].contiguous(memory_format=torch.channels_last)
+    xs = xall[:, 256:].contiguous(memory_format=torch.channels_last)
+    ref = _ref_logits(x, xs, W, bias)
+    assert ref.abs().min().item() > 0.5
+    eng.upload_head(W, bias)
+    corr, counts, codes = eng.head_decode(x, xs, bboxes, return_codes=True)
+    want_codes, _ = _expected_codes(ref, 0, 1, 16)
+    assert torch.equal(codes.long(), want_codes)
+    corr, counts = corr.cpu().numpy(), counts.cpu().numpy()
+    for i, c in enumerate(crops):
+        mask = odec.threshold_logits(logits[i, 0]).astype(np.uint8)
+        code = odec.threshold_logits(logits[i, 1:]).transpose(1, 2, 0)
+        uv, xyz, _ = odec.decode_crop(mask, code, c["bbox"], S, tab)
+        n = counts[i]
+        assert n == len(uv) and np.array_equal(corr[i, 0:2, :n].T, uv)
+        assert np.array_equal(corr[i, 2:5, :n].T.view(np.uint32), xyz.view(np.uint32))
+    # noise activations: bits away from zero must match
+    bb = np.tile(np.array([[0.0, 0.0, 64.0, 64.0]]), (2, 1))
+    Wr = (torch.randn(17, 128, generator=g) * 0.1).cuda()
+    xr = torch.randn(2, 128, 64, 64, generator=g).cuda().contiguous(memory_format=torch.channels_last)
+    eng.upload_head(Wr, None)
+    codes = eng.head_decode(xr[:, :96].contiguous(memory_format=torch.channels_last), xr[:, 96:].contiguous(memory_format=torch.channels_last),
+                            bb, return_codes=True)[2]              # 96 + 32: multiples of 32 are enough for fp32
+    ref = _ref_logits(xr, None, Wr, torch.zeros(17, device="cuda"))
+    want, _ = _expected_codes(ref, 0, 1, 16)
+    sure = ref[:, 1:17].abs() > TF32_TOL
+    w = (2 ** torch.arange(15, -1, -1, device="cuda")).view(1, 16, 1, 1)
+    bit_diff = ((((codes.long() ^ want).unsqueeze(1)) // w) % 2).bool()
+    assert not (bit_diff & sure).any()
+    assert sure.float().mean().item() > 0.9

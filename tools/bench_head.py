@@ -33,6 +33,8 @@ def timed(fn, reps=10):
     return tot / reps * 1e3
 
 
+W32c = W.cuda().reshape(17, c1 + c2, 1, 1).contiguous(memory_format=torch.channels_last)
+b32c = bias.cuda()
 for B in [int(v) for v in sys.argv[1:]] or [64, 256]:
     x = torch.randn(B, c1, S, S, generator=g).cuda().to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
     xs = torch.randn(B, c2, S, S, generator=g).cuda().to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
@@ -55,6 +57,16 @@ for B in [int(v) for v in sys.argv[1:]] or [64, 256]:
     n_px = B * S * S
     in_bytes = n_px * 2 * (c1 + c2)
     alg = in_bytes + n_px * 2.125 + n_px * 2.125 + 20 * M + 4 * B        # head kernel in+out, emit kernel in+out
+    # float32 activations: kind::tf32 tensor-core path vs torch fp32 (TF32 allowed, as a B200 deployment would set it)
+    x32, xs32 = x.float().contiguous(memory_format=torch.channels_last), xs.float().contiguous(memory_format=torch.channels_last)
+    torch.backends.cudnn.allow_tf32 = True; torch.backends.cuda.matmul.allow_tf32 = True
+    t_f32 = timed(lambda: eng.head_decode(x32, xs32, bbt))
+    t_u32 = timed(lambda: eng.decode(F.conv2d(torch.cat([x32, xs32], 1), W32c, b32c), bbt))
+    alg32 = 2 * in_bytes + n_px * 2.125 + n_px * 2.125 + 20 * M + 4 * B
+    print(json.dumps({"B": B, "dtype": "float32 activations (tf32 MMA)", "fused_us": round(t_f32, 1), "unfused_us": round(t_u32, 1),
+                      "speedup": round(t_u32 / t_f32, 2), "fused_GBps": round(alg32 / t_f32 / 1e3, 1),
+                      "frac_of_hbm_peak": round(alg32 / t_f32 / 1e3 / peak, 3)}))
+    del x32, xs32
     print(json.dumps({"B": B, "fused_us": round(t_f, 1), "unfused_us": round(t_u, 1), "cat_conv_only_us": round(t_c, 1),
                       "speedup": round(t_u / t_f, 2), "algorithmic_bytes": int(alg), "fused_GBps": round(alg / t_f / 1e3, 1),
                       "frac_of_hbm_peak": round(alg / t_f / 1e3 / peak, 3), "hbm_peak_GBps": peak,

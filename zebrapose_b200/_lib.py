@@ -49,7 +49,7 @@ SIGNATURES = {
     "zp_upload_model": (_i, [_vp, _i, _vp, _i]),
     "zp_pose_errors": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp]),
     "zp_upload_head": (_i, [_vp, _vp, _vp, _i, _i]),
-    "zp_head_decode": (_i, [_vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _i, _vp, _vp]),
+    "zp_head_decode": (_i, [_vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _i, _vp, _vp]),
 }
 
 _lib = None

@@ -103,6 +103,7 @@ void zp_destroy(zp_ctx* ctx) {
     if (ctx->d_model_V) cudaFree(ctx->d_model_V);
     if (ctx->ews) cudaFree(ctx->ews);
     if (ctx->head_w) cudaFree(ctx->head_w);
+    if (ctx->head_w32) cudaFree(ctx->head_w32);
     if (ctx->hdws) cudaFree(ctx->hdws);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;

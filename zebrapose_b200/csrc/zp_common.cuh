@@ -48,6 +48,7 @@ struct zp_ctx {
     size_t ews_bytes = 0;
     // fused network head (zp_head.cu): bf16 weights [32][c_in] (rows >= n_out zero), bias, workspace (codes + mask words)
     void* head_w = nullptr;
+    void* head_w32 = nullptr;
     float head_bias[32] = {0};
     int head_n_out = 0, head_c_in = 0;
     void* hdws = nullptr;

@@ -26,17 +26,18 @@ int zp_launch_emit_codes(zp_ctx* ctx, int B, int S, const double* bbox, const in
 
 constexpr int HD_TILE_M = 128;                 // pixels per tile = UMMA M
 constexpr int HD_N = 32;                       // output channels padded to the UMMA N granule (17 used)
-constexpr int HD_KB = 64;                      // channels per k-block: 64 bf16 = one 128-byte swizzle row
-constexpr int HD_UMMA_K = 16;
+constexpr int HD_ROW_BYTES = 128;               // one k-block = one 128-byte swizzle row per pixel: 64 bf16 or 32 fp32 channels
+constexpr int HD_KSTEPS = 4;                    // tcgen05.mma per k-block: 4 x (K = 16 bf16 | K = 8 tf32) = 4 x 32 bytes
 constexpr int HD_STAGES = 6;
-constexpr int HD_A_BYTES = HD_TILE_M * HD_KB * 2;      // 16 KB
-constexpr int HD_W_BYTES = HD_N * HD_KB * 2;           // 4 KB per k-block
-constexpr int HD_MAX_KB = 8;                           // C_in <= 512
+constexpr int HD_A_BYTES = HD_TILE_M * HD_ROW_BYTES;   // 16 KB
+constexpr int HD_W_BYTES = HD_N * HD_ROW_BYTES;        // 4 KB per k-block
+constexpr int HD_MAX_KB = 16;                          // C_in <= 1024 (bf16) | 512 (fp32)
 constexpr int HD_THREADS = 192;
 constexpr int HD_TMEM_COLS = 64;                       // 2 accumulator stages x 32 columns
 
 struct HeadParams {
-    int n_tiles, kb_x, kb_total;
+    int n_tiles, kb_x, kb_total, kb_ch;      // kb_ch = channels per k-block (64 bf16 | 32 fp32)
+    uint32_t idesc;
     int mask_ch, bit0_ch, nb;
     uint16_t* codes;                 // [n_tiles * 128]
     uint8_t* maskb;                  // mask ballot words as bytes: [n_tiles][4 words][4 bytes]
@@ -74,19 +75,30 @@ __device__ __forceinline__ uint64_t hd_desc(uint32_t smem_addr) {
 }
 // instruction descriptor (kind::f16): D = F32 [4,6) = 1, A = BF16 [7,10) = 1, B = BF16 [10,13) = 1, both K-major,
 // N >> 3 at [17,23), M >> 4 at [24,29)
-constexpr uint32_t HD_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(HD_N >> 3) << 17) | ((uint32_t)(HD_TILE_M >> 4) << 24);
+constexpr uint32_t hd_idesc(uint32_t fmt) {     // fmt: 1 = BF16, 2 = TF32 (fp32 operands, 10-bit mantissa products, fp32 accumulate)
+    return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(HD_N >> 3) << 17) | ((uint32_t)(HD_TILE_M >> 4) << 24);
+}
 
-__device__ __forceinline__ void hd_mma(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(da), "l"(db), "r"(HD_IDESC), "r"(accumulate) : "memory");
+template <bool TF32>
+__device__ __forceinline__ void hd_mma(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    if (TF32)
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+    else
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
 }
 __device__ __forceinline__ void hd_commit(uint64_t* bar) {      // arrives on `bar` when all MMAs issued so far have completed
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(hd_smem(bar)) : "memory");
 }
 
+template <bool TF32>
 __global__ void __launch_bounds__(HD_THREADS, 1)
 zp_head_codes_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_s,
                      const __grid_constant__ CUtensorMap map_w, const __grid_constant__ HeadParams p) {
@@ -126,7 +138,7 @@ zp_head_codes_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
         // ===== TMA producer =====
         if (lane == 0) {
             hd_mbar_expect_tx(wfull, (uint32_t)p.kb_total * HD_W_BYTES);
-            for (int kb = 0; kb < p.kb_total; kb++) hd_tma_2d(s_w + kb * HD_W_BYTES, &map_w, kb * HD_KB, 0, wfull);
+            for (int kb = 0; kb < p.kb_total; kb++) hd_tma_2d(s_w + kb * HD_W_BYTES, &map_w, kb * p.kb_ch, 0, wfull);
         }
         int stage = 0; uint32_t phase = 0;
         for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
@@ -134,8 +146,8 @@ zp_head_codes_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
                 hd_mbar_wait(&empty[stage], phase ^ 1);
                 if (lane == 0) {
                     hd_mbar_expect_tx(&full[stage], HD_A_BYTES);
-                    if (kb < p.kb_x) hd_tma_2d(s_a + stage * HD_A_BYTES, &map_x, kb * HD_KB, tile * HD_TILE_M, &full[stage]);
-                    else hd_tma_2d(s_a + stage * HD_A_BYTES, &map_s, (kb - p.kb_x) * HD_KB, tile * HD_TILE_M, &full[stage]);
+                    if (kb < p.kb_x) hd_tma_2d(s_a + stage * HD_A_BYTES, &map_x, kb * p.kb_ch, tile * HD_TILE_M, &full[stage]);
+                    else hd_tma_2d(s_a + stage * HD_A_BYTES, &map_s, (kb - p.kb_x) * p.kb_ch, tile * HD_TILE_M, &full[stage]);
                 }
                 __syncwarp();
                 if (++stage == HD_STAGES) { stage = 0; phase ^= 1; }
@@ -156,8 +168,8 @@ zp_head_codes_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
                     const uint64_t da = hd_desc(hd_smem(s_a + stage * HD_A_BYTES));
                     const uint64_t db = hd_desc(hd_smem(s_w + kb * HD_W_BYTES));
 #pragma unroll
-                    for (int k = 0; k < HD_KB / HD_UMMA_K; k++)       // +32 bytes (2 x 16 B) per K = 16 step inside the swizzle row
-                        hd_mma(tmem_base + acc * HD_N, da + 2 * k, db + 2 * k, (kb | k) != 0);
+                    for (int k = 0; k < HD_KSTEPS; k++)               // +32 bytes (2 x 16 B) per K step inside the swizzle row
+                        hd_mma<TF32>(tmem_base + acc * HD_N, da + 2 * k, db + 2 * k, p.idesc, (kb | k) != 0);
                     hd_commit(&empty[stage]);                         // slot free once these MMAs have read it
                     if (kb == p.kb_total - 1) hd_commit(&tfull[acc]); // accumulator complete
                 }
@@ -233,18 +245,18 @@ static EncodeTiledFn hd_encode_fn() {
     return fn;
 }
 
-// [rows, cols] bf16 row-major (cols contiguous), box = 64 columns x box_rows rows, 128-byte swizzle
-static int hd_make_map(zp_ctx* ctx, CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+// [rows, cols] bf16 | fp32 row-major (cols contiguous), box = one 128-byte row segment x box_rows rows, 128-byte swizzle
+static int hd_make_map(zp_ctx* ctx, CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows, int esz) {
     EncodeTiledFn fn = hd_encode_fn();
     if (!fn) ZP_FAIL(ctx, -2, "cuTensorMapEncodeTiled not available from the driver");
     cuuint64_t dims[2] = {cols, rows};
-    cuuint64_t strides[1] = {cols * 2};
-    cuuint32_t box[2] = {HD_KB, box_rows};
+    cuuint64_t strides[1] = {cols * (uint64_t)esz};
+    cuuint32_t box[2] = {(cuuint32_t)(HD_ROW_BYTES / esz), box_rows};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+    CUresult r = fn(map, esz == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(ptr), dims, strides, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) ZP_FAIL(ctx, -2, "cuTensorMapEncodeTiled failed (%d) for a [%llu x %llu] bf16 tensor", (int)r,
+    if (r != CUDA_SUCCESS) ZP_FAIL(ctx, -2, "cuTensorMapEncodeTiled failed (%d) for a [%llu x %llu] tensor", (int)r,
                                    (unsigned long long)rows, (unsigned long long)cols);
     return 0;
 }
@@ -264,8 +276,7 @@ extern "C" {
 int zp_upload_head(zp_ctx* ctx, const float* weight, const float* bias, int n_out, int c_in) {
     if (!ctx) return -1;
     if (!weight || n_out < 1 || n_out > HD_N) ZP_FAIL(ctx, -1, "zp_upload_head: n_out must be 1..%d, got %d", HD_N, n_out);
-    if (c_in < HD_KB || c_in % HD_KB != 0 || c_in > HD_KB * HD_MAX_KB)
-        ZP_FAIL(ctx, -1, "zp_upload_head: c_in must be a multiple of %d up to %d, got %d", HD_KB, HD_KB * HD_MAX_KB, c_in);
+    if (c_in < 64 || c_in % 64 != 0 || c_in > 512) ZP_FAIL(ctx, -1, "zp_upload_head: c_in must be a multiple of 64 up to 512, got %d", c_in);
     ZP_CUDA(ctx, cudaSetDevice(ctx->device));
     std::vector<uint16_t> w((size_t)HD_N * c_in, 0);
     for (int o = 0; o < n_out; o++)
@@ -275,20 +286,31 @@ int zp_upload_head(zp_ctx* ctx, const float* weight, const float* bias, int n_ou
     ctx->head_w = nullptr;
     ZP_CUDA(ctx, cudaMalloc(&ctx->head_w, w.size() * 2));
     ZP_CUDA(ctx, cudaMemcpy(ctx->head_w, w.data(), w.size() * 2, cudaMemcpyHostToDevice));
+    // float32 copy for the TF32 path (fp32 activations): the tensor core reads the top 19 bits of each operand
+    std::vector<float> w32((size_t)HD_N * c_in, 0.f);
+    for (int o = 0; o < n_out; o++)
+        for (int c = 0; c < c_in; c++) w32[(size_t)o * c_in + c] = weight[(size_t)o * c_in + c];
+    if (ctx->head_w32) cudaFree(ctx->head_w32);
+    ctx->head_w32 = nullptr;
+    ZP_CUDA(ctx, cudaMalloc(&ctx->head_w32, w32.size() * 4));
+    ZP_CUDA(ctx, cudaMemcpy(ctx->head_w32, w32.data(), w32.size() * 4, cudaMemcpyHostToDevice));
     for (int o = 0; o < HD_N; o++) ctx->head_bias[o] = (bias && o < n_out) ? bias[o] : 0.f;
     ctx->head_n_out = n_out; ctx->head_c_in = c_in;
     return 0;
 }
 
-int zp_head_decode(zp_ctx* ctx, const void* x, int c1, const void* x_skip, int c2, int B, int S, int mask_ch, int bit0_ch,
+int zp_head_decode(zp_ctx* ctx, const void* x, int c1, const void* x_skip, int c2, int dtype, int B, int S, int mask_ch, int bit0_ch,
                    int n_bits, int ignore_bit, const double* bbox, const int32_t* obj_ids, int obj_default,
                    uint16_t* codes, float* corr, int cap, int32_t* counts, void* stream) {
     if (!ctx) return -1;
     if (B == 0) return 0;
     if (!ctx->head_w) ZP_FAIL(ctx, -1, "zp_head_decode: no head weights uploaded (zp_upload_head)");
     if (!x || !bbox || !corr || !counts || B < 0) ZP_FAIL(ctx, -1, "zp_head_decode: null argument");
-    if (c2 < 0 || (c2 > 0 && !x_skip) || c1 < HD_KB || c1 % HD_KB || c2 % HD_KB || c1 + c2 != ctx->head_c_in)
-        ZP_FAIL(ctx, -1, "zp_head_decode: channel split %d + %d does not match the uploaded head (c_in %d, multiples of %d)", c1, c2, ctx->head_c_in, HD_KB);
+    if (dtype != ZP_DTYPE_F32 && dtype != ZP_DTYPE_BF16) ZP_FAIL(ctx, -1, "zp_head_decode: dtype %d not supported", dtype);
+    const int esz = dtype == ZP_DTYPE_BF16 ? 2 : 4;
+    const int kb_ch = HD_ROW_BYTES / esz;
+    if (c2 < 0 || (c2 > 0 && !x_skip) || c1 < kb_ch || c1 % kb_ch || c2 % kb_ch || c1 + c2 != ctx->head_c_in)
+        ZP_FAIL(ctx, -1, "zp_head_decode: channel split %d + %d does not match the uploaded head (c_in %d, multiples of %d)", c1, c2, ctx->head_c_in, kb_ch);
     const int nb = n_bits - ignore_bit;
     if (n_bits < 1 || n_bits > 16 || ignore_bit < 0 || nb < 1) ZP_FAIL(ctx, -1, "zp_head_decode: bad n_bits/ignore_bit");
     if (mask_ch < 0 || mask_ch >= ctx->head_n_out || bit0_ch < 0 || bit0_ch + nb > ctx->head_n_out)
@@ -320,23 +342,26 @@ int zp_head_decode(zp_ctx* ctx, const void* x, int c1, const void* x_skip, int c
     uint16_t* d_codes = codes ? codes : (uint16_t*)ctx->hdws;
     uint8_t* d_mask = (uint8_t*)ctx->hdws + b_codes;
     CUtensorMap mx, ms, mw;
-    if (int r = hd_make_map(ctx, &mx, x, (uint64_t)n_px, (uint64_t)c1, HD_TILE_M)) return r;
-    if (c2 > 0) { if (int r = hd_make_map(ctx, &ms, x_skip, (uint64_t)n_px, (uint64_t)c2, HD_TILE_M)) return r; }
+    if (int r = hd_make_map(ctx, &mx, x, (uint64_t)n_px, (uint64_t)c1, HD_TILE_M, esz)) return r;
+    if (c2 > 0) { if (int r = hd_make_map(ctx, &ms, x_skip, (uint64_t)n_px, (uint64_t)c2, HD_TILE_M, esz)) return r; }
     else ms = mx;
-    if (int r = hd_make_map(ctx, &mw, ctx->head_w, HD_N, (uint64_t)ctx->head_c_in, HD_N)) return r;
+    if (int r = hd_make_map(ctx, &mw, esz == 2 ? ctx->head_w : ctx->head_w32, HD_N, (uint64_t)ctx->head_c_in, HD_N, esz)) return r;
     HeadParams p{};
-    p.n_tiles = n_tiles; p.kb_x = c1 / HD_KB; p.kb_total = (c1 + c2) / HD_KB;
+    p.n_tiles = n_tiles; p.kb_x = c1 / kb_ch; p.kb_total = (c1 + c2) / kb_ch; p.kb_ch = kb_ch;
+    p.idesc = hd_idesc(esz == 2 ? 1u : 2u);
     p.mask_ch = mask_ch; p.bit0_ch = bit0_ch; p.nb = nb;
     p.codes = d_codes; p.maskb = d_mask;
     for (int o = 0; o < HD_N; o++) p.bias[o] = ctx->head_bias[o];
     const int smem = HD_STAGES * HD_A_BYTES + HD_MAX_KB * HD_W_BYTES + 256 + 1024;
     static bool attr_set = false;
     if (!attr_set) {
-        ZP_CUDA(ctx, cudaFuncSetAttribute(zp_head_codes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        ZP_CUDA(ctx, cudaFuncSetAttribute(zp_head_codes_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        ZP_CUDA(ctx, cudaFuncSetAttribute(zp_head_codes_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr_set = true;
     }
     const int grid = std::min(n_tiles, ctx->sm_count);
-    zp_head_codes_kernel<<<grid, HD_THREADS, smem, st>>>(mx, ms, mw, p);
+    if (esz == 2) zp_head_codes_kernel<false><<<grid, HD_THREADS, smem, st>>>(mx, ms, mw, p);
+    else zp_head_codes_kernel<true><<<grid, HD_THREADS, smem, st>>>(mx, ms, mw, p);
     ZP_CHECK_LAUNCH(ctx, "zp_head_codes_kernel");
     return zp_launch_emit_codes(ctx, B, S, bbox, obj_ids, obj_default, d_codes, (const uint32_t*)d_mask, corr, cap, counts, st);
 }

@@ -301,8 +301,8 @@ class Engine:
 
     @staticmethod
     def _channels_last_ptr(t, name):
-        if t.dim() != 4 or t.dtype != torch.bfloat16:
-            raise TypeError("%s must be a 4-D bfloat16 tensor [B,C,S,S] in channels_last memory format" % name)
+        if t.dim() != 4 or t.dtype not in _DT:
+            raise TypeError("%s must be a 4-D bfloat16 | float32 tensor [B,C,S,S] in channels_last memory format" % name)
         if not t.permute(0, 2, 3, 1).is_contiguous():
             raise ValueError("%s must be channels_last (x.contiguous(memory_format=torch.channels_last))" % name)
         return t
@@ -310,7 +310,8 @@ class Engine:
     def head_decode(self, x, x_skip, bboxes, obj_ids=None, *, obj_default=0, mask_ch=0, bit0_ch=1, n_bits=16, ignore_bit=0,
                     return_codes=False, cap=None):
         """`conv_1x1_4(torch.cat([x, x_skip], 1))` (model/aspp.py:112) + decode() in one pass on the tensor cores; the
-        logits are never written.  x [B,c1,S,S], x_skip [B,c2,S,S] | None: bfloat16, channels_last.  Returns like decode()."""
+        logits are never written.  x [B,c1,S,S], x_skip [B,c2,S,S] | None: bfloat16 (or float32: TF32 tensor-core products),
+        channels_last.  Returns like decode()."""
         x = self._channels_last_ptr(x, "x")
         B, c1, S, S2 = x.shape
         c2 = 0
@@ -319,6 +320,8 @@ class Engine:
             if x_skip.shape[0] != B or x_skip.shape[2:] != x.shape[2:]:
                 raise ValueError("x and x_skip must agree in batch and spatial size")
             c2 = x_skip.shape[1]
+            if x_skip.dtype != x.dtype:
+                raise TypeError("x and x_skip must have the same dtype")
         if S != S2 or x.device != self.device:
             raise ValueError("x must be [B,C,S,S] on %s" % self.device)
         cap = int(cap or ((S * S + 3) // 4) * 4)
@@ -329,7 +332,7 @@ class Engine:
         corr = torch.empty((B, 5, cap), dtype=torch.float32, device=self.device)
         counts = torch.empty((B,), dtype=torch.int32, device=self.device)
         codes = torch.empty((B, S, S), dtype=torch.uint16, device=self.device) if return_codes else None
-        rc = self.lib.zp_head_decode(self.ctx.handle, _ptr(x), int(c1), _ptr(x_skip), int(c2), B, S, int(mask_ch),
+        rc = self.lib.zp_head_decode(self.ctx.handle, _ptr(x), int(c1), _ptr(x_skip), int(c2), _DT[x.dtype], B, S, int(mask_ch),
                                      int(bit0_ch), int(n_bits), int(ignore_bit), _ptr(bb), _ptr(oid), int(obj_default),
                                      _ptr(codes), _ptr(corr), cap, _ptr(counts), _stream())
         self.ctx.check(rc, "zp_head_decode")
