@@ -83,6 +83,24 @@ class StdoutToStderr:
         os.close(self.saved)
 
 
+def bind_to_gpu_numa(gpu):
+    """Pin this rank to the CPUs NVML reports as local to its GPU BEFORE the pinned host buffers are allocated and first
+    touched, so that the pages of the e2e path sit on the GPU's NUMA node (a remote-socket buffer costs ~25 % of the
+    host->device rate).  Returns the previous affinity (restored before the CPU baseline runs on all cores)."""
+    try:
+        prev = os.sched_getaffinity(0)
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(gpu)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * i + b for i, w in enumerate(words) for b in range(64) if (w >> b) & 1} & prev
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return prev, sorted(cpus)
+    except Exception:
+        return None, None
+
+
 def cpu_baseline(logits, bboxes, Ks, obj, tables, n_sample, repeats=1):
     """reference CPU path on all host cores, bounded sample"""
     from oracle.reference_path import ReferencePool
@@ -235,6 +253,7 @@ def main():
     import zebrapose_b200 as zp
 
     args.warmup = max(args.warmup, 3)
+    prev_affinity, numa_cpus = bind_to_gpu_numa(local)
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
@@ -398,6 +417,8 @@ def main():
         except Exception as exc:          # the rows beside the path must never cost the headline line
             extras = {"error": repr(exc)[:200]}
         cpu = None
+        if prev_affinity:
+            os.sched_setaffinity(0, prev_affinity)          # the reference pool gets every host core again
         if not args.no_cpu_baseline:
             n_sample = max(256, 128 * (os.cpu_count() or 1))
             v, cores, secs, ref_poses = cpu_baseline(logits, bboxes, Ks, obj, tables, n_sample)
@@ -420,6 +441,7 @@ def main():
             "step_latency_ms": step_latency_ms,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "path": "zp_pose_batch_host_async + zp_sync (C ABI, pinned host logits -> pinned host poses), %d lanes" % args.lanes,
+                    "host_cpus": "%d CPUs local to the GPU (NVML affinity)" % len(numa_cpus) if numa_cpus else "unbound",
                     "steps": e2e_steps},
             "gpu_launches": launches,
             "clocks": sampler.summary(),
