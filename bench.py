@@ -373,19 +373,29 @@ def main():
             tot += a.elapsed_time(b)
         return tot / reps
 
+    def ktimed(fn, names, reps=20):
+        """per-kernel durations from the library's own event pairs, recorded on the launching stream directly around each
+        launch (zp_set_kernel_timing), L2 flushed before every repetition"""
+        for _ in range(3):
+            fn()
+        eng.set_kernel_timing(True)
+        for _ in range(reps):
+            flush2.zero_()
+            fn()
+        torch.cuda.synchronize()
+        out = {n: eng.kernel_time(n)[0] for n in names}
+        eng.set_kernel_timing(False)
+        return out
+
     line = None
     if rank == 0:
         corr, counts = eng.decode(d_logits, d_bbox, d_obj)
         cap = corr.shape[2]
-        samples = eng.make_samples(counts, cap, H, M)
-        hyp = eng.solve_minimal(corr, counts, d_K, samples)
-        k_ms = {
-            "zp_decode_stream_kernel": timed(lambda: eng.decode(d_logits, d_bbox, d_obj)),
-            "zp_samples_kernel": timed(lambda: eng.make_samples(counts, cap, H, M)),
-            "zp_minimal_kernel": timed(lambda: eng.solve_minimal(corr, counts, d_K, samples)),
-            "zp_score_kernel": timed(lambda: eng.score(corr, counts, d_K, hyp, THR)),
-            "ransac_chain(samples+minimal+score+select+final)": timed(lambda: eng.ransac(corr, counts, d_K, H=H, m=M, thr=THR)),
-        }
+        k_ms = ktimed(lambda: eng.decode(d_logits, d_bbox, d_obj), ["zp_decode_stream_kernel"])
+        k_ms.update(ktimed(lambda: eng.ransac(corr, counts, d_K, H=H, m=M, thr=THR),
+                           ["zp_samples_kernel", "zp_minimal_kernel", "zp_score_kernel", "zp_final_kernel"]))
+        chain_event_ms = timed(lambda: eng.ransac(corr, counts, d_K, H=H, m=M, thr=THR))     # python-level events: + launch gaps, memset
+        k_ms["ransac_chain(samples+minimal+score+select+final)"] = sum(k_ms[k] for k in ("zp_samples_kernel", "zp_minimal_kernel", "zp_score_kernel", "zp_final_kernel"))
         Mtot = int(counts.clamp(max=cap).sum().item())
         peaks = {}
         try:
@@ -407,7 +417,7 @@ def main():
         sc_tf = sc_flops / (k_ms["zp_score_kernel"] * 1e-3) / 1e12
         chain = k_ms["zp_decode_stream_kernel"] + k_ms["ransac_chain(samples+minimal+score+select+final)"]
         shares = {k: round(v / chain, 4) for k, v in k_ms.items()}
-        dominant = max(("zp_decode_stream_kernel", "zp_minimal_kernel", "zp_score_kernel"), key=lambda k: k_ms[k])
+        dominant = max(("zp_decode_stream_kernel", "zp_minimal_kernel", "zp_score_kernel", "zp_final_kernel"), key=lambda k: k_ms[k])
         if args.kernels:
             for k, v in k_ms.items():
                 print("%-55s %9.3f us  share %.3f" % (k, v * 1e3, v / chain), file=sys.stderr)
@@ -455,6 +465,9 @@ def main():
                                "peak_source": "max of zp_fp32_peak_probe (scalar FFMA chains, %.1f) and zp_fp32x2_peak_probe (packed FFMA2 chains, %.1f), measured on this GPU in this run" % (fp32_scalar, fp32_packed),
                                "algorithmic_flops_per_launch": sc_flops, "us_per_launch": k_ms["zp_score_kernel"] * 1e3},
             "kernel_us": {k: round(v * 1e3, 2) for k, v in k_ms.items()},
+            "kernel_us_method": "CUDA event pairs recorded by the library on the launching stream directly around each launch "
+                                "(zp_set_kernel_timing), 512 MiB L2 flush before every repetition, 20 repetitions",
+            "ransac_chain_us_python_events": round(chain_event_ms * 1e3, 2),
             "kernel_share_of_step": shares,
             "dominant_kernel": dominant,
             "cpu_baseline": cpu,

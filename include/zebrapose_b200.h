@@ -175,6 +175,14 @@ int zp_pose_batch_host_async(zp_ctx* ctx, const void* h_logits, int dtype, int B
 /* Waits for everything enqueued on the ctx's own stream (zp_pose_batch_host_async). */
 int zp_sync(zp_ctx* ctx);
 
+/* Measurement aid: while on, every launch of the path's main kernels is bracketed by two CUDA events recorded on the
+ * launching stream directly around it (the call then waits for that kernel), and the elapsed times accumulate per kernel
+ * name ("zp_decode_stream_kernel", "zp_samples_kernel", "zp_minimal_kernel", "zp_score_kernel", "zp_final_kernel",
+ * "zp_head_codes_kernel", "zp_decode_emit_kernel", "zp_adi_kernel", "zp_crop_kernel").  Switching it on clears the sums.
+ * bench.py's roofline figures are algorithmic bytes (flops) per launch / these durations. */
+int zp_set_kernel_timing(zp_ctx* ctx, int on);
+int zp_kernel_time(zp_ctx* ctx, const char* kernel_name, double* ms_sum, int64_t* launches);
+
 /* Number of kernels this ctx has launched since creation (bench.py's gpu_launches claim). */
 int64_t zp_launch_count(zp_ctx* ctx);
 

@@ -38,6 +38,8 @@ SIGNATURES = {
     "zp_remap_pixels": (_i, [_vp, _vp, _i64, _vp, _i, _vp, _vp]),
     "zp_codes_to_ids": (_i, [_vp, _vp, _i64, _i, _i, _vp, _vp]),
     "zp_launch_count": (_i64, [_vp]),
+    "zp_set_kernel_timing": (_i, [_vp, _i]),
+    "zp_kernel_time": (_i, [_vp, C.c_char_p, C.POINTER(_d), C.POINTER(_i64)]),
     "zp_set_decode_path": (_i, [_vp, _i]),
     "zp_debug_buffer": (_i, [_vp, _vp]),
     "zp_set_score_groups": (_i, [_vp, _i, _i]),

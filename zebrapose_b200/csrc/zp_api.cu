@@ -106,6 +106,8 @@ void zp_destroy(zp_ctx* ctx) {
     if (ctx->head_w32) cudaFree(ctx->head_w32);
     if (ctx->hdws) cudaFree(ctx->hdws);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    if (ctx->t_ev0) cudaEventDestroy(ctx->t_ev0);
+    if (ctx->t_ev1) cudaEventDestroy(ctx->t_ev1);
     delete ctx;
 }
 
@@ -119,6 +121,27 @@ int zp_set_score_groups(zp_ctx* ctx, int groups, int hyp_chunk) {
     if (hyp_chunk < -1 || hyp_chunk > ZP_MAX_HYPOTHESES) ZP_FAIL(ctx, -1, "zp_set_score_groups: bad hyp_chunk %d", hyp_chunk);
     ctx->score_groups = groups;
     ctx->score_hchunk = hyp_chunk;
+    return 0;
+}
+
+int zp_set_kernel_timing(zp_ctx* ctx, int on) {
+    if (!ctx) return -1;
+    ZP_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (on && !ctx->t_ev0) {
+        ZP_CUDA(ctx, cudaEventCreate(&ctx->t_ev0));
+        ZP_CUDA(ctx, cudaEventCreate(&ctx->t_ev1));
+    }
+    ctx->timing = on ? 1 : 0;
+    ctx->t_open = false;
+    if (on) ctx->t_acc.clear();
+    return 0;
+}
+
+int zp_kernel_time(zp_ctx* ctx, const char* kernel_name, double* ms_sum, int64_t* launches) {
+    if (!ctx || !kernel_name) return -1;
+    auto it = ctx->t_acc.find(kernel_name);
+    if (ms_sum) *ms_sum = it == ctx->t_acc.end() ? 0.0 : it->second.first;
+    if (launches) *launches = it == ctx->t_acc.end() ? 0 : it->second.second;
     return 0;
 }
 

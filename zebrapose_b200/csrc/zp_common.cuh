@@ -5,6 +5,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
+#include <map>
 #include <string>
 #include <vector>
 #include "../../include/zebrapose_b200.h"
@@ -54,6 +55,12 @@ struct zp_ctx {
     void* hdws = nullptr;
     size_t hdws_bytes = 0;
     cudaStream_t own_stream = nullptr;
+    // per-kernel timing (zp_set_kernel_timing): CUDA events recorded on the launching stream directly around a launch
+    int timing = 0;
+    bool t_open = false;
+    cudaEvent_t t_ev0 = nullptr, t_ev1 = nullptr;
+    cudaStream_t t_stream = nullptr;
+    std::map<std::string, std::pair<double, long long>> t_acc;      // kernel name -> (sum of ms, launches)
     int64_t launches = 0;
     int score_groups = 0;                    // 0 auto, else 1 | 2 | 4 warp-groups per scoring CTA (tests / tuning)
     int score_hchunk = 0;                    // 0 auto, -1 never cut, else hypotheses per scoring work item
@@ -77,12 +84,28 @@ struct zp_ctx {
             ZP_FAIL(ctx, -2, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__); \
     } while (0)
 
+// Profiling aid: ZP_TIME_BEGIN right before a kernel launch + the ZP_CHECK_LAUNCH after it bracket exactly that launch
+// with two events on its stream (only when zp_set_kernel_timing is on; the end side waits for the kernel).
+#define ZP_TIME_BEGIN(ctx, st)                                                               \
+    do {                                                                                     \
+        if ((ctx)->timing) { cudaEventRecord((ctx)->t_ev0, (st)); (ctx)->t_stream = (st); (ctx)->t_open = true; } \
+    } while (0)
+
 #define ZP_CHECK_LAUNCH(ctx, name)                                                           \
     do {                                                                                     \
         cudaError_t _e = cudaGetLastError();                                                 \
         if (_e != cudaSuccess)                                                               \
             ZP_FAIL(ctx, -3, "launch of %s failed: %s", name, cudaGetErrorString(_e));       \
         (ctx)->launches++;                                                                   \
+        if ((ctx)->t_open) {                                                                 \
+            float _ms = 0.f;                                                                 \
+            cudaEventRecord((ctx)->t_ev1, (ctx)->t_stream);                                  \
+            cudaEventSynchronize((ctx)->t_ev1);                                              \
+            cudaEventElapsedTime(&_ms, (ctx)->t_ev0, (ctx)->t_ev1);                          \
+            auto& _a = (ctx)->t_acc[name];                                                   \
+            _a.first += _ms; _a.second += 1;                                                 \
+            (ctx)->t_open = false;                                                           \
+        }                                                                                    \
     } while (0)
 
 int zp_ws_reserve(zp_ctx* ctx, size_t bytes);

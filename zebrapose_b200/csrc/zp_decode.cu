@@ -456,6 +456,7 @@ static int launch_stream(zp_ctx* ctx, const DecodeArgs& a, int runs, cudaStream_
     if (rpc > runs) rpc = runs;
     const int cpc = (runs + rpc - 1) / rpc;
     const bool full16 = a.nb == 16 && a.ext_mask == nullptr;
+    ZP_TIME_BEGIN(ctx, st);
     if (full16) zp_decode_stream_kernel<DT, true><<<(unsigned)(a.B * cpc), DEC_THREADS, smem, st>>>(a, cpc, rpc, runs);
     else zp_decode_stream_kernel<DT, false><<<(unsigned)(a.B * cpc), DEC_THREADS, smem, st>>>(a, cpc, rpc, runs);
     ZP_CHECK_LAUNCH(ctx, "zp_decode_stream_kernel");
@@ -660,6 +661,7 @@ int zp_launch_emit_codes(zp_ctx* ctx, int B, int S, const double* bbox, const in
         ZP_CUDA(ctx, cudaFuncSetAttribute(zp_decode_emit_kernel<PPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr_set = true;
     }
+    ZP_TIME_BEGIN(ctx, st);
     zp_decode_emit_kernel<PPT><<<(unsigned)(B * runs), DEC_THREADS, smem, st>>>(a, codes, maskw, segs, runs);
     ZP_CHECK_LAUNCH(ctx, "zp_decode_emit_kernel");
     return 0;

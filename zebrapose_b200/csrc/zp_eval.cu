@@ -423,6 +423,7 @@ int zp_crop_input(zp_ctx* ctx, const uint8_t* images, int n_img, int H, int W, c
     const float dm[3] = {0.485f, 0.456f, 0.406f}, ds[3] = {0.229f, 0.224f, 0.225f};       // bop_dataset_pytorch.py:336
     for (int c = 0; c < 3; c++) { a.mean[c] = mean3 ? mean3[c] : dm[c]; a.stdv[c] = std3 ? std3[c] : ds[c]; }
     a.out = out; a.out_u8 = out_u8;
+    ZP_TIME_BEGIN(ctx, (cudaStream_t)stream);
     zp_crop_kernel<<<dim3((crop_size + CROP_ROWS - 1) / CROP_ROWS, B), 256, 0, (cudaStream_t)stream>>>(a);
     ZP_CHECK_LAUNCH(ctx, "zp_crop_kernel");
     return 0;
@@ -490,6 +491,7 @@ int zp_pose_errors(zp_ctx* ctx, const double* poses_est, const double* poses_gt,
         nsplit = (a.Vs + tlen - 1) / tlen;
         a.nsplit = nsplit; a.tlen = tlen;
         if (nsplit > 1) ZP_CUDA(ctx, cudaMemsetAsync(a.qmin, 0x7f, (size_t)B * a.Vs * sizeof(uint32_t), st));   // 3.39e38f
+        ZP_TIME_BEGIN(ctx, st);
         zp_adi_kernel<<<dim3(qtiles, nsplit, B), EV_THREADS, 0, st>>>(a);
         ZP_CHECK_LAUNCH(ctx, "zp_adi_kernel");
     }

@@ -360,6 +360,7 @@ int zp_head_decode(zp_ctx* ctx, const void* x, int c1, const void* x_skip, int c
         attr_set = true;
     }
     const int grid = std::min(n_tiles, ctx->sm_count);
+    ZP_TIME_BEGIN(ctx, st);
     if (esz == 2) zp_head_codes_kernel<false><<<grid, HD_THREADS, smem, st>>>(mx, ms, mw, p);
     else zp_head_codes_kernel<true><<<grid, HD_THREADS, smem, st>>>(mx, ms, mw, p);
     ZP_CHECK_LAUNCH(ctx, "zp_head_codes_kernel");

@@ -936,6 +936,7 @@ __global__ void zp_fma_probe_kernel(float* out, int iters, float a, float b) {
 // ---------------------------------------------------------------------------------------------------------------
 int zp_launch_samples(zp_ctx* ctx, const int32_t* counts, int cap, int B, int H, int m, int mode, uint64_t seed,
                       int32_t* samples, cudaStream_t st) {
+    ZP_TIME_BEGIN(ctx, st);
     zp_samples_kernel<<<B, SMP_THREADS, 0, st>>>(counts, cap, B, H, m, mode, seed, ctx->d_rng, ctx->n_rng, samples);
     ZP_CHECK_LAUNCH(ctx, "zp_samples_kernel");
     return 0;
@@ -962,6 +963,7 @@ int zp_launch_minimal(zp_ctx* ctx, const float* corr, int cap, const int32_t* co
     // both take the same time alone but the 168-register build leaves
     // room for another lane's kernels on the SM (257 k vs 236 k poses/s with 3 lanes).  ZP_MIN_BLOCKS=2|3 pins it.
     const bool two = force ? force == 2 : grid > 12 * ctx->sm_count;
+    ZP_TIME_BEGIN(ctx, st);
     if (two) zp_minimal_kernel<2><<<grid, MIN_THREADS, MIN_SMEM_BYTES, st>>>(corr, cap, counts, K, samples, B, H, m, 1.0 / (double)thr_px, hyp_poses, hyp_P);
     else zp_minimal_kernel<3><<<grid, MIN_THREADS, MIN_SMEM_BYTES, st>>>(corr, cap, counts, K, samples, B, H, m, 1.0 / (double)thr_px, hyp_poses, hyp_P);
     ZP_CHECK_LAUNCH(ctx, "zp_minimal_kernel");
@@ -995,6 +997,7 @@ static int launch_score_ng(zp_ctx* ctx, ScoreArgs& a, int smem, cudaStream_t st)
         a.n_hc = (a.H + a.hchunk - 1) / a.hchunk;
     }
     if (grid > 2 * a.n_items * a.n_hc) grid = 2 * a.n_items * a.n_hc;
+    ZP_TIME_BEGIN(ctx, st);
     zp_score_kernel<NG><<<grid, SC_GROUP * NG, smem, st>>>(a);
     ZP_CHECK_LAUNCH(ctx, "zp_score_kernel");
     return 0;
@@ -1025,6 +1028,7 @@ int zp_launch_final(zp_ctx* ctx, const float* corr, int cap, const int32_t* coun
     a.final_mode = final_mode; a.poses = poses; a.n_inliers = n_inliers; a.status = status; a.best_idx = best_idx;
     a.inlier_mask = inlier_mask;
     size_t smem = (size_t)H * sizeof(double) + ((size_t)(cap + 31) / 32 + 2 * (size_t)H + (H + 31) / 32 + FIN_THREADS / 32) * sizeof(uint32_t);
+    ZP_TIME_BEGIN(ctx, st);
     zp_final_kernel<<<B, FIN_THREADS, smem, st>>>(a);
     ZP_CHECK_LAUNCH(ctx, "zp_final_kernel");
     return 0;

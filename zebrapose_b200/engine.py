@@ -411,6 +411,16 @@ class Engine:
     def launch_count(self):
         return int(self.lib.zp_launch_count(self.ctx.handle))
 
+    def set_kernel_timing(self, on=True):
+        """bracket every main-kernel launch with CUDA events on its stream (serialises; measurement passes only)"""
+        self.ctx.check(self.lib.zp_set_kernel_timing(self.ctx.handle, 1 if on else 0), "zp_set_kernel_timing")
+
+    def kernel_time(self, name):
+        """(average ms per launch, launches) of kernel `name` since set_kernel_timing(True)"""
+        ms, n = C.c_double(), C.c_int64()
+        self.ctx.check(self.lib.zp_kernel_time(self.ctx.handle, name.encode(), C.byref(ms), C.byref(n)), "zp_kernel_time")
+        return (ms.value / n.value if n.value else 0.0), int(n.value)
+
     def fp32_peak_tflops(self, iters=20000, packed=False):
         """measured FP32 FMA throughput of this GPU: scalar FFMA chains, or packed FFMA2 chains (packed=True)"""
         v = C.c_double()
