@@ -142,6 +142,7 @@ __device__ __forceinline__ void zp_resize_tap(int d, int dn, int sn, bool reset,
 
 constexpr int CROP_ROWS = 16;          // output rows per CTA: a thread owns a column, its tap and weights are computed once
 
+template <bool BF16, bool CL, bool U8>
 __global__ void __launch_bounds__(256) zp_crop_kernel(CropArgs a) {
     __shared__ float s_lut[3][256];      // ToTensor + Normalize of every uint8 value, per channel (exact IEEE divisions, once)
     __shared__ int s_row[CROP_ROWS][4];  // byte offset of source row r0 / r1 (-1: outside the copied rectangle), b0, b1
@@ -179,30 +180,35 @@ __global__ void __launch_bounds__(256) zp_crop_kernel(CropArgs a) {
             const uint8_t* q01 = img + ro0 + c1; const bool v01 = !empty && (ro0 | c1) >= 0;
             const uint8_t* q10 = img + ro1 + c0; const bool v10 = !empty && (ro1 | c0) >= 0;
             const uint8_t* q11 = img + ro1 + c1; const bool v11 = !empty && (ro1 | c1) >= 0;
-            int v[3];
+            int t00[3], t01[3], t10[3], t11[3], v[3];
 #pragma unroll
             for (int c = 0; c < 3; c++) {
-                const int t00 = v00 ? q00[c] : 0, t01 = v01 ? q01[c] : 0, t10 = v10 ? q10[c] : 0, t11 = v11 ? q11[c] : 0;
-                if (area2) v[c] = (t00 + t01 + t10 + t11 + 2) >> 2;
-                else {
-                    const int S0 = t00 * a0 + t01 * a1, S1 = t10 * a0 + t11 * a1;
+                t00[c] = v00 ? q00[c] : 0; t01[c] = v01 ? q01[c] : 0; t10[c] = v10 ? q10[c] : 0; t11[c] = v11 ? q11[c] : 0;
+            }
+            if (area2) {
+#pragma unroll
+                for (int c = 0; c < 3; c++) v[c] = (t00[c] + t01[c] + t10[c] + t11[c] + 2) >> 2;
+            } else {
+#pragma unroll
+                for (int c = 0; c < 3; c++) {
+                    const int S0 = t00[c] * a0 + t01[c] * a1, S1 = t10[c] * a0 + t11[c] * a1;
                     v[c] = ((((b0 * (S0 >> 4)) >> 16) + ((b1 * (S1 >> 4)) >> 16) + 2) >> 2) & 0xff;
                 }
             }
             const size_t p = (size_t)(oy0 + j) * cs + ox;
-            if (a.out_u8) {
+            if (U8) {
                 uint8_t* o = a.out_u8 + ((size_t)b * plane + p) * 3;
                 o[0] = (uint8_t)v[0]; o[1] = (uint8_t)v[1]; o[2] = (uint8_t)v[2];
             }
             if (a.out) {
                 const float f0 = s_lut[0][v[0]], f1 = s_lut[1][v[1]], f2 = s_lut[2][v[2]];
-                if (a.channels_last) {
+                if (CL) {
                     const size_t i3 = ((size_t)b * plane + p) * 3;
-                    if (a.out_bf16) { __nv_bfloat16* o = (__nv_bfloat16*)a.out + i3; o[0] = __float2bfloat16_rn(f0); o[1] = __float2bfloat16_rn(f1); o[2] = __float2bfloat16_rn(f2); }
+                    if (BF16) { __nv_bfloat16* o = (__nv_bfloat16*)a.out + i3; o[0] = __float2bfloat16_rn(f0); o[1] = __float2bfloat16_rn(f1); o[2] = __float2bfloat16_rn(f2); }
                     else { float* o = (float*)a.out + i3; o[0] = f0; o[1] = f1; o[2] = f2; }
                 } else {
                     const size_t i0 = (size_t)b * 3 * plane + p;
-                    if (a.out_bf16) { __nv_bfloat16* o = (__nv_bfloat16*)a.out + i0; o[0] = __float2bfloat16_rn(f0); o[plane] = __float2bfloat16_rn(f1); o[2 * plane] = __float2bfloat16_rn(f2); }
+                    if (BF16) { __nv_bfloat16* o = (__nv_bfloat16*)a.out + i0; o[0] = __float2bfloat16_rn(f0); o[plane] = __float2bfloat16_rn(f1); o[2 * plane] = __float2bfloat16_rn(f2); }
                     else { float* o = (float*)a.out + i0; o[0] = f0; o[plane] = f1; o[2 * plane] = f2; }
                 }
             }
@@ -424,7 +430,19 @@ int zp_crop_input(zp_ctx* ctx, const uint8_t* images, int n_img, int H, int W, c
     for (int c = 0; c < 3; c++) { a.mean[c] = mean3 ? mean3[c] : dm[c]; a.stdv[c] = std3 ? std3[c] : ds[c]; }
     a.out = out; a.out_u8 = out_u8;
     ZP_TIME_BEGIN(ctx, (cudaStream_t)stream);
-    zp_crop_kernel<<<dim3((crop_size + CROP_ROWS - 1) / CROP_ROWS, B), 256, 0, (cudaStream_t)stream>>>(a);
+    const dim3 grid((crop_size + CROP_ROWS - 1) / CROP_ROWS, B);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int variant = (a.out_bf16 ? 4 : 0) | (a.channels_last ? 2 : 0) | (out_u8 ? 1 : 0);
+    switch (variant) {      // output format fixed at compile time: no per-pixel branches in the gather / blend loop
+        case 0: zp_crop_kernel<false, false, false><<<grid, 256, 0, st>>>(a); break;
+        case 1: zp_crop_kernel<false, false, true><<<grid, 256, 0, st>>>(a); break;
+        case 2: zp_crop_kernel<false, true, false><<<grid, 256, 0, st>>>(a); break;
+        case 3: zp_crop_kernel<false, true, true><<<grid, 256, 0, st>>>(a); break;
+        case 4: zp_crop_kernel<true, false, false><<<grid, 256, 0, st>>>(a); break;
+        case 5: zp_crop_kernel<true, false, true><<<grid, 256, 0, st>>>(a); break;
+        case 6: zp_crop_kernel<true, true, false><<<grid, 256, 0, st>>>(a); break;
+        default: zp_crop_kernel<true, true, true><<<grid, 256, 0, st>>>(a); break;
+    }
     ZP_CHECK_LAUNCH(ctx, "zp_crop_kernel");
     return 0;
 }
