@@ -5,9 +5,9 @@
 
 int zp_launch_samples(zp_ctx*, const int32_t*, int, int, int, int, int, uint64_t, int32_t*, cudaStream_t);
 int zp_launch_minimal(zp_ctx*, const float*, int, const int32_t*, const double*, const int32_t*, int, int, int, float,
-                      double*, float*, cudaStream_t);
+                      double*, float*, int32_t*, cudaStream_t);
 int zp_launch_poses_to_P(zp_ctx*, const double*, const double*, int, int, float, float*, cudaStream_t);
-int zp_launch_score(zp_ctx*, const float*, int, const int32_t*, const float*, int, int, float, int32_t*, cudaStream_t);
+int zp_launch_score(zp_ctx*, const float*, int, const int32_t*, const float*, int, int, float, int32_t*, bool, cudaStream_t);
 int zp_launch_final(zp_ctx*, const float*, int, const int32_t*, const double*, const double*, const int32_t*, int, int, int,
                     double, int, float, int, double*, int32_t*, int32_t*, int32_t*, uint8_t*, cudaStream_t);
 int zp_launch_fma_probe(zp_ctx*, int, int, double*);
@@ -320,7 +320,7 @@ int zp_solve_minimal(zp_ctx* ctx, const float* corr, int cap, const int32_t* cou
     if (m < 4 || m > 8 || H < 1 || H > ZP_MAX_HYPOTHESES) ZP_FAIL(ctx, -1, "zp_solve_minimal: bad m/H %d/%d", m, H);
     ZP_CUDA(ctx, cudaSetDevice(ctx->device));
     if (zp_ws_reserve(ctx, (size_t)B * H * 24 * sizeof(float))) return -2;
-    return zp_launch_minimal(ctx, corr, cap, counts, K, samples, B, H, m, 2.0f, hyp_poses, (float*)ctx->ws,
+    return zp_launch_minimal(ctx, corr, cap, counts, K, samples, B, H, m, 2.0f, hyp_poses, (float*)ctx->ws, nullptr,
                              (cudaStream_t)stream);
 }
 
@@ -341,7 +341,7 @@ int zp_score(zp_ctx* ctx, const float* corr, int cap, const int32_t* counts, con
     ZP_CUDA(ctx, cudaSetDevice(ctx->device));
     if (zp_ws_reserve(ctx, (size_t)B * H * 24 * sizeof(float))) return -2;
     if (int r = zp_launch_poses_to_P(ctx, hyp_poses, K, B, H, thr_px, (float*)ctx->ws, (cudaStream_t)stream)) return r;
-    return zp_launch_score(ctx, corr, cap, counts, (const float*)ctx->ws, B, H, thr_px, hyp_inliers, (cudaStream_t)stream);
+    return zp_launch_score(ctx, corr, cap, counts, (const float*)ctx->ws, B, H, thr_px, hyp_inliers, false, (cudaStream_t)stream);
 }
 
 static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
@@ -374,8 +374,9 @@ int zp_ransac(zp_ctx* ctx, const float* corr, int cap, const int32_t* counts, co
     double* d_hp = hyp_poses ? hyp_poses : (double*)(ws + o_p);
     int32_t* d_hi = hyp_inliers ? hyp_inliers : (int32_t*)(ws + o_i);
     float* d_P = (float*)(ws + o_P);
-    if (int r = zp_launch_minimal(ctx, corr, cap, counts, K, samples ? samples : d_samples, B, H, m, thr_px, d_hp, d_P, st)) return r;
-    if (int r = zp_launch_score(ctx, corr, cap, counts, d_P, B, H, thr_px, d_hi, st)) return r;
+    // the minimal solver zeroes the inlier counters of its hypotheses: the scoring launch follows without a memset node
+    if (int r = zp_launch_minimal(ctx, corr, cap, counts, K, samples ? samples : d_samples, B, H, m, thr_px, d_hp, d_P, d_hi, st)) return r;
+    if (int r = zp_launch_score(ctx, corr, cap, counts, d_P, B, H, thr_px, d_hi, true, st)) return r;
     return zp_launch_final(ctx, corr, cap, counts, K, d_hp, d_hi, B, H, m, confidence, select_mode, thr_px, final_mode,
                            poses, n_inliers, status, best_idx, inlier_mask, st);
 }

@@ -255,7 +255,8 @@ template <int MINB>
 __global__ void __launch_bounds__(MIN_THREADS, MINB)
 zp_minimal_kernel(const float* __restrict__ corr, int cap, const int32_t* __restrict__ counts,
                   const double* __restrict__ Kmat, const int32_t* __restrict__ samples, int B, int H, int m,
-                  double inv_thr, double* __restrict__ hyp_poses, float* __restrict__ hyp_P) {
+                  double inv_thr, double* __restrict__ hyp_poses, float* __restrict__ hyp_P,
+                  int32_t* __restrict__ hyp_inliers /* nullable: zeroed here so the scoring launch needs no memset */) {
     extern __shared__ __align__(16) double s_min[];            // per hypothesis: z[12x13] | d[12] | e[12] | V[4x12]
     const int tid = threadIdx.x, lane = tid & 31, q = lane & 3, quad = tid >> 2;
     double* s_z = s_min + (size_t)quad * MIN_HYP_DOUBLES;
@@ -340,6 +341,7 @@ zp_minimal_kernel(const float* __restrict__ corr, int cap, const int32_t* __rest
         int oc = __shfl_sync(0xffffffffu, (int)ok, base + c);
         if (oc && (pick < 0 || ec < pe)) { pick = c; pe = ec; }
     }
+    if (live && q == 0 && hyp_inliers) hyp_inliers[g] = 0;
     if (live) {
         double* out = hyp_poses + (size_t)g * 12;
         float4* outP = (float4*)(hyp_P + (size_t)g * 24);       // every element twice: (P,P) pairs for FFMA2
@@ -944,7 +946,7 @@ int zp_launch_samples(zp_ctx* ctx, const int32_t* counts, int cap, int B, int H,
 
 int zp_launch_minimal(zp_ctx* ctx, const float* corr, int cap, const int32_t* counts, const double* K,
                       const int32_t* samples, int B, int H, int m, float thr_px, double* hyp_poses, float* hyp_P,
-                      cudaStream_t st) {
+                      int32_t* hyp_inliers_to_zero, cudaStream_t st) {
     const int per_cta = MIN_THREADS / 4;
     int total = B * H;
     static bool attr_set = false;
@@ -964,8 +966,8 @@ int zp_launch_minimal(zp_ctx* ctx, const float* corr, int cap, const int32_t* co
     // room for another lane's kernels on the SM (257 k vs 236 k poses/s with 3 lanes).  ZP_MIN_BLOCKS=2|3 pins it.
     const bool two = force ? force == 2 : grid > 12 * ctx->sm_count;
     ZP_TIME_BEGIN(ctx, st);
-    if (two) zp_minimal_kernel<2><<<grid, MIN_THREADS, MIN_SMEM_BYTES, st>>>(corr, cap, counts, K, samples, B, H, m, 1.0 / (double)thr_px, hyp_poses, hyp_P);
-    else zp_minimal_kernel<3><<<grid, MIN_THREADS, MIN_SMEM_BYTES, st>>>(corr, cap, counts, K, samples, B, H, m, 1.0 / (double)thr_px, hyp_poses, hyp_P);
+    if (two) zp_minimal_kernel<2><<<grid, MIN_THREADS, MIN_SMEM_BYTES, st>>>(corr, cap, counts, K, samples, B, H, m, 1.0 / (double)thr_px, hyp_poses, hyp_P, hyp_inliers_to_zero);
+    else zp_minimal_kernel<3><<<grid, MIN_THREADS, MIN_SMEM_BYTES, st>>>(corr, cap, counts, K, samples, B, H, m, 1.0 / (double)thr_px, hyp_poses, hyp_P, hyp_inliers_to_zero);
     ZP_CHECK_LAUNCH(ctx, "zp_minimal_kernel");
     return 0;
 }
@@ -1004,14 +1006,14 @@ static int launch_score_ng(zp_ctx* ctx, ScoreArgs& a, int smem, cudaStream_t st)
 }
 
 int zp_launch_score(zp_ctx* ctx, const float* corr, int cap, const int32_t* counts, const float* hyp_P, int B, int H,
-                    float thr_px, int32_t* hyp_inliers, cudaStream_t st) {
+                    float thr_px, int32_t* hyp_inliers, bool already_zeroed, cudaStream_t st) {
     ScoreArgs a;
     a.corr = corr; a.cap = cap; a.counts = counts; a.hyp_P = hyp_P; a.B = B; a.H = H; a.inv_thr = 1.0f / thr_px;
     a.hyp_inliers = hyp_inliers; a.counters = ctx->d_counters;
     const int max_tiles = (cap + SC_TILE - 1) / SC_TILE;
     a.n_items = B * max_tiles;
     const int smem = 5 * SC_TILE * sizeof(float) + SC_HB * (6 * sizeof(ulonglong2) + sizeof(int));
-    ZP_CUDA(ctx, cudaMemsetAsync(hyp_inliers, 0, (size_t)B * H * sizeof(int32_t), st));
+    if (!already_zeroed) ZP_CUDA(ctx, cudaMemsetAsync(hyp_inliers, 0, (size_t)B * H * sizeof(int32_t), st));
     const int ng = ctx->score_groups ? ctx->score_groups : 1;
     if (ng == 1) return launch_score_ng<1>(ctx, a, smem, st);
     if (ng == 2) return launch_score_ng<2>(ctx, a, smem, st);
