@@ -616,7 +616,11 @@ __global__ void __launch_bounds__(FIN_THREADS) zp_final_kernel(FinalArgs a) {
     int* s_hi = (int*)(s_mask + (a.cap + 31) / 32);
     int* s_rt = s_hi + a.H;
     unsigned* s_rec = (unsigned*)(s_rt + a.H);
+    // compacted inlier indices: warp w owns the points [w * chunk, (w + 1) * chunk) and packs the inliers among them
+    // at the start of its own segment (deterministic order, no cross-warp scan); s_wpre = exclusive prefix of the counts
+    uint16_t* s_idx = (uint16_t*)(s_rec + (a.H + 31) / 32 + FIN_THREADS / 32);
     __shared__ int s_wmax[FIN_THREADS / 32];
+    __shared__ int s_wcnt[FIN_THREADS / 32], s_wpre[FIN_THREADS / 32];
 
     ZP_STAMP(0);
     double* out = a.poses + 12 * (size_t)b;
@@ -715,26 +719,42 @@ __global__ void __launch_bounds__(FIN_THREADS) zp_final_kernel(FinalArgs a) {
     // ---- pass 0: inlier set of the winner (same predicate as zp_score_kernel), centroid
     double acc[52];
     for (int q = 0; q < 52; q++) acc[q] = 0;
-    int my_n = 0, my_first = 0x7fffffff;
+    int my_first = 0x7fffffff;
+    constexpr int FIN_WARPS = FIN_THREADS / 32;
+    const int warp = tid >> 5;
+    const int chunk = ((n + FIN_THREADS - 1) / FIN_THREADS) * 32;      // points per warp (whole 32-point groups)
+    int wcount = 0;                                                     // warp-uniform: inliers packed so far
 #pragma unroll 4
-    for (int i0 = 0; i0 < n; i0 += FIN_THREADS) {     // warp-aligned so the bitset is built with ballots
-        int i = i0 + tid;
-        bool in = i < n && zp_is_inlier(p0, p1, p2, pu[i] * a.inv_thr, pv[i] * a.inv_thr, pX[i], pY[i], pZ[i]);
-        unsigned bal = __ballot_sync(0xffffffffu, in);
+    for (int j = 0; j < chunk; j += 32) {             // warp-aligned so the bitset is built with ballots
+        const int i = warp * chunk + j + lane;
+        const bool in = i < n && zp_is_inlier(p0, p1, p2, pu[i] * a.inv_thr, pv[i] * a.inv_thr, pX[i], pY[i], pZ[i]);
+        const unsigned bal = __ballot_sync(0xffffffffu, in);
         if (lane == 0 && i < a.cap) s_mask[i >> 5] = bal;
         if (a.inlier_mask && i < n) a.inlier_mask[(size_t)b * a.cap + i] = in;
         if (in) {
-            my_n++; my_first = min(my_first, i);
+            s_idx[warp * chunk + wcount + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)i;
+            my_first = min(my_first, i);
             acc[0] += pX[i]; acc[1] += pY[i]; acc[2] += pZ[i];
         }
+        wcount += __popc(bal);
     }
     if (a.inlier_mask)
         for (int i = n + tid; i < a.cap; i += FIN_THREADS) a.inlier_mask[(size_t)b * a.cap + i] = 0;
-    my_n = __reduce_add_sync(0xffffffffu, my_n);
     my_first = __reduce_min_sync(0xffffffffu, my_first);
-    if (lane == 0) { atomicAdd(&s_n, my_n); atomicMin(&s_first, my_first); }
+    if (lane == 0) { s_wcnt[warp] = wcount; atomicAdd(&s_n, wcount); atomicMin(&s_first, my_first); }
     block_reduce<3>(acc, s_red, s_sum);
+    if (tid == 0) {
+        int run = 0;
+        for (int w = 0; w < FIN_WARPS; w++) { s_wpre[w] = run; run += s_wcnt[w]; }
+    }
     const int ni = s_n;
+    // k-th inlier (k < ni) in the packed per-warp segments
+    auto inlier_at = [&](int k) -> int {
+        int w = 0;
+#pragma unroll
+        for (int q = 1; q < FIN_WARPS; q++) w += k >= s_wpre[q];
+        return s_idx[w * chunk + (k - s_wpre[w])];
+    };
     if (tid == 0) a.n_inliers[b] = ni;
     if (ni < 4) {       // cannot happen after selection (good > m-1 >= 3) but keep the output defined
         if (tid < 12) out[tid] = hp[tid];
@@ -746,12 +766,12 @@ __global__ void __launch_bounds__(FIN_THREADS) zp_final_kernel(FinalArgs a) {
     // ---- pass 1: scatter matrix
     for (int q = 0; q < 9; q++) acc[q] = 0;
 #pragma unroll 4
-    for (int i = tid; i < n; i += FIN_THREADS)
-        if (s_mask[i >> 5] >> (i & 31) & 1u) {
-            double d0 = pX[i] - c0[0], d1 = pY[i] - c0[1], d2 = pZ[i] - c0[2];
-            acc[0] = fma(d0, d0, acc[0]); acc[1] = fma(d0, d1, acc[1]); acc[2] = fma(d0, d2, acc[2]);
-            acc[4] = fma(d1, d1, acc[4]); acc[5] = fma(d1, d2, acc[5]); acc[8] = fma(d2, d2, acc[8]);
-        }
+    for (int k = tid; k < ni; k += FIN_THREADS) {     // inliers only: every lane has work
+        const int i = inlier_at(k);
+        double d0 = pX[i] - c0[0], d1 = pY[i] - c0[1], d2 = pZ[i] - c0[2];
+        acc[0] = fma(d0, d0, acc[0]); acc[1] = fma(d0, d1, acc[1]); acc[2] = fma(d0, d2, acc[2]);
+        acc[4] = fma(d1, d1, acc[4]); acc[5] = fma(d1, d2, acc[5]); acc[8] = fma(d2, d2, acc[8]);
+    }
     acc[3] = acc[1]; acc[6] = acc[2]; acc[7] = acc[5];
     block_reduce<9>(acc, s_red, s_sum);
     ZP_STAMP(3);
@@ -770,20 +790,22 @@ __global__ void __launch_bounds__(FIN_THREADS) zp_final_kernel(FinalArgs a) {
         for (int q = 0; q < 12; q++) s.w[q] = 0;
         const ZpControl cp = s_cp;
         // the five loads of the next point are issued before the ~80 FP64 operations of the current one
-        int i = tid;
-        bool in = i < n && (s_mask[i >> 5] >> (i & 31) & 1u);
+        int k = tid;
+        bool in = k < ni;
+        int i = in ? inlier_at(k) : 0;
         float fX = in ? pX[i] : 0.f, fY = in ? pY[i] : 0.f, fZ = in ? pZ[i] : 0.f, fu = in ? pu[i] : 0.f, fv = in ? pv[i] : 0.f;
-        while (i < n) {
-            const int i2 = i + FIN_THREADS;
-            const bool in2 = i2 < n && (s_mask[i2 >> 5] >> (i2 & 31) & 1u);
+        while (in) {                                  // walks the packed inlier list: no idle lanes, no skipped points
+            const int k2 = k + FIN_THREADS;
+            const bool in2 = k2 < ni;
+            const int i2 = in2 ? inlier_at(k2) : 0;
             const float gX = in2 ? pX[i2] : 0.f, gY = in2 ? pY[i2] : 0.f, gZ = in2 ? pZ[i2] : 0.f, gu = in2 ? pu[i2] : 0.f, gv = in2 ? pv[i2] : 0.f;
-            if (in) {
+            {
                 double X = fX, Y = fY, Z = fZ;
                 double al[4];
                 zp_alphas(cp, X, Y, Z, al);
                 zp_accumulate(s, al, cam.uc - (double)fu, cam.vc - (double)fv, X - c0[0], Y - c0[1], Z - c0[2]);
             }
-            i = i2; in = in2; fX = gX; fY = gY; fZ = gZ; fu = gu; fv = gv;
+            k = k2; in = in2; fX = gX; fY = gY; fZ = gZ; fu = gu; fv = gv;
         }
         for (int q = 0; q < 10; q++) { acc[q] = s.s0[q]; acc[10 + q] = s.sx[q]; acc[20 + q] = s.sy[q]; acc[30 + q] = s.sr[q]; }
         for (int q = 0; q < 12; q++) acc[40 + q] = s.w[q];
@@ -816,8 +838,8 @@ __global__ void __launch_bounds__(FIN_THREADS) zp_final_kernel(FinalArgs a) {
     ZP_STAMP(8);
     // ---- pass 3: mean reprojection distance of the three candidates, pick the best
     for (int q = 0; q < 3; q++) acc[q] = 0;
-    // branch-free (a non-inlier contributes 0 through a select) so that the unrolled iterations interleave: with 8
-    // warps per SM the FP64 divide / square-root chains are latency-bound otherwise
+    // over the packed inlier list; unrolled so that the FP64 divide / square-root chains of two points interleave (with 8
+    // warps per SM they are latency-bound otherwise)
     {
         double cR[3][9], ct[3][3];
         bool cok[3];
@@ -830,14 +852,11 @@ __global__ void __launch_bounds__(FIN_THREADS) zp_final_kernel(FinalArgs a) {
             for (int e = 0; e < 3; e++) ct[c][e] = cok[c] ? s_candt[c][e] : (e == 2 ? 1.0 : 0.0);
         }
 #pragma unroll 2
-        for (int i = tid; i < n; i += FIN_THREADS) {
-            const bool in = s_mask[i >> 5] >> (i & 31) & 1u;
+        for (int k = tid; k < ni; k += FIN_THREADS) {
+            const int i = inlier_at(k);
             const double X = pX[i], Y = pY[i], Z = pZ[i], u = pu[i], v = pv[i];
 #pragma unroll
-            for (int c = 0; c < 3; c++) {
-                const double dist = zp_reproj_dist(cR[c], ct[c], cam, X, Y, Z, u, v);
-                acc[c] += in ? dist : 0.0;
-            }
+            for (int c = 0; c < 3; c++) acc[c] += zp_reproj_dist(cR[c], ct[c], cam, X, Y, Z, u, v);
         }
     }
     block_reduce<3>(acc, s_red, s_sum);
@@ -1029,7 +1048,14 @@ int zp_launch_final(zp_ctx* ctx, const float* corr, int cap, const int32_t* coun
     a.B = B; a.H = H; a.m = m; a.conf = conf; a.select_mode = select_mode; a.inv_thr = 1.0f / thr_px;
     a.final_mode = final_mode; a.poses = poses; a.n_inliers = n_inliers; a.status = status; a.best_idx = best_idx;
     a.inlier_mask = inlier_mask;
-    size_t smem = (size_t)H * sizeof(double) + ((size_t)(cap + 31) / 32 + 2 * (size_t)H + (H + 31) / 32 + FIN_THREADS / 32) * sizeof(uint32_t);
+    size_t smem = (size_t)H * sizeof(double) + ((size_t)(cap + 31) / 32 + 2 * (size_t)H + (H + 31) / 32 + FIN_THREADS / 32) * sizeof(uint32_t) +
+                  ((size_t)cap + FIN_THREADS + 32) * sizeof(uint16_t);          // + the packed inlier indices
+    static bool attr_set = false;
+    if (!attr_set) {
+        ZP_CUDA(ctx, cudaFuncSetAttribute(zp_final_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr_set = true;
+    }
+    if (smem > 200 * 1024) ZP_FAIL(ctx, -1, "zp_ransac: cap %d needs %zu bytes of shared memory in the final solve", cap, smem);
     ZP_TIME_BEGIN(ctx, st);
     zp_final_kernel<<<B, FIN_THREADS, smem, st>>>(a);
     ZP_CHECK_LAUNCH(ctx, "zp_final_kernel");
