@@ -569,9 +569,9 @@ __device__ inline int zp_update_iters(double p, double ep, int m, int maxit) {  
     return (den >= 0 || -num >= maxit * (-den)) ? maxit : (int)rint(num / den);
 }
 
-constexpr int FIN_THREADS = 256;
+constexpr int FIN_THREADS_MAX = 256;       // threads per crop: 256 (one CTA per SM) or 128 (two CTAs per SM), see zp_launch_final
 
-template <int NV>
+template <int NV, int FIN_THREADS>
 __device__ __forceinline__ void block_reduce(double* v, double* s_red /* [FIN_THREADS/32][NV] */, double* s_out) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
@@ -596,8 +596,10 @@ struct FinalArgs {
     double* poses; int32_t* n_inliers; int32_t* status; int32_t* best_idx; uint8_t* inlier_mask;
 };
 
-// (register budget measured: 255 regs / 1 CTA per SM beats 128 regs / 2 and 80 regs / 3 at 64 AND at 1024 crops --
-// 3.72 vs 3.89 vs 4.26 ms per 1024-crop step; profiles/README.md)
+// (register budget measured: 255 registers per thread beat 128 (2 x 256 threads per SM) and 80 at 64 AND at 1024 crops --
+// 3.72 vs 3.89 vs 4.26 ms per 1024-crop step; what does pay at saturation is two CTAs of 128 threads, still at 255
+// registers: zp_launch_final; profiles/README.md)
+template <int FIN_THREADS>
 __global__ void __launch_bounds__(FIN_THREADS) zp_final_kernel(FinalArgs a) {
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
     __shared__ double s_red[(FIN_THREADS / 32) * 52];
@@ -742,7 +744,7 @@ __global__ void __launch_bounds__(FIN_THREADS) zp_final_kernel(FinalArgs a) {
         for (int i = n + tid; i < a.cap; i += FIN_THREADS) a.inlier_mask[(size_t)b * a.cap + i] = 0;
     my_first = __reduce_min_sync(0xffffffffu, my_first);
     if (lane == 0) { s_wcnt[warp] = wcount; atomicAdd(&s_n, wcount); atomicMin(&s_first, my_first); }
-    block_reduce<3>(acc, s_red, s_sum);
+    block_reduce<3, FIN_THREADS>(acc, s_red, s_sum);
     if (tid == 0) {
         int run = 0;
         for (int w = 0; w < FIN_WARPS; w++) { s_wpre[w] = run; run += s_wcnt[w]; }
@@ -773,7 +775,7 @@ __global__ void __launch_bounds__(FIN_THREADS) zp_final_kernel(FinalArgs a) {
         acc[4] = fma(d1, d1, acc[4]); acc[5] = fma(d1, d2, acc[5]); acc[8] = fma(d2, d2, acc[8]);
     }
     acc[3] = acc[1]; acc[6] = acc[2]; acc[7] = acc[5];
-    block_reduce<9>(acc, s_red, s_sum);
+    block_reduce<9, FIN_THREADS>(acc, s_red, s_sum);
     ZP_STAMP(3);
     if (tid == 0) {
         double C[9];
@@ -810,7 +812,7 @@ __global__ void __launch_bounds__(FIN_THREADS) zp_final_kernel(FinalArgs a) {
         for (int q = 0; q < 10; q++) { acc[q] = s.s0[q]; acc[10 + q] = s.sx[q]; acc[20 + q] = s.sy[q]; acc[30 + q] = s.sr[q]; }
         for (int q = 0; q < 12; q++) acc[40 + q] = s.w[q];
     }
-    block_reduce<52>(acc, s_red, s_sum);
+    block_reduce<52, FIN_THREADS>(acc, s_red, s_sum);
     if (tid < 10) { s_sums.s0[tid] = s_sum[tid]; s_sums.sx[tid] = s_sum[10 + tid]; s_sums.sy[tid] = s_sum[20 + tid]; s_sums.sr[tid] = s_sum[30 + tid]; }
     if (tid < 12) s_sums.w[tid] = s_sum[40 + tid];
     if (tid == 0) s_sums.n = ni;
@@ -859,7 +861,7 @@ __global__ void __launch_bounds__(FIN_THREADS) zp_final_kernel(FinalArgs a) {
             for (int c = 0; c < 3; c++) acc[c] += zp_reproj_dist(cR[c], ct[c], cam, X, Y, Z, u, v);
         }
     }
-    block_reduce<3>(acc, s_red, s_sum);
+    block_reduce<3, FIN_THREADS>(acc, s_red, s_sum);
     if (tid == 0) {
         int pick = -1;
         double be = 0;
@@ -899,7 +901,7 @@ __global__ void __launch_bounds__(FIN_THREADS) zp_final_kernel(FinalArgs a) {
                         for (int c = r; c < 6; c++) { acc[q] += Ju[r] * Ju[c] + Jv[r] * Jv[c]; q++; }
                     for (int r = 0; r < 6; r++) acc[21 + r] += Ju[r] * ru + Jv[r] * rv;
                 }
-            block_reduce<27>(acc, s_red, s_sum);
+            block_reduce<27, FIN_THREADS>(acc, s_red, s_sum);
             if (tid == 0) {
                 double A[36], g[6], d[6];
                 int q = 0;
@@ -1048,16 +1050,25 @@ int zp_launch_final(zp_ctx* ctx, const float* corr, int cap, const int32_t* coun
     a.B = B; a.H = H; a.m = m; a.conf = conf; a.select_mode = select_mode; a.inv_thr = 1.0f / thr_px;
     a.final_mode = final_mode; a.poses = poses; a.n_inliers = n_inliers; a.status = status; a.best_idx = best_idx;
     a.inlier_mask = inlier_mask;
-    size_t smem = (size_t)H * sizeof(double) + ((size_t)(cap + 31) / 32 + 2 * (size_t)H + (H + 31) / 32 + FIN_THREADS / 32) * sizeof(uint32_t) +
-                  ((size_t)cap + FIN_THREADS + 32) * sizeof(uint16_t);          // + the packed inlier indices
+    size_t smem = (size_t)H * sizeof(double) + ((size_t)(cap + 31) / 32 + 2 * (size_t)H + (H + 31) / 32 + FIN_THREADS_MAX / 32) * sizeof(uint32_t) +
+                  ((size_t)cap + FIN_THREADS_MAX + 32) * sizeof(uint16_t);      // + the packed inlier indices
     static bool attr_set = false;
     if (!attr_set) {
-        ZP_CUDA(ctx, cudaFuncSetAttribute(zp_final_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        ZP_CUDA(ctx, cudaFuncSetAttribute(zp_final_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        ZP_CUDA(ctx, cudaFuncSetAttribute(zp_final_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
         attr_set = true;
     }
     if (smem > 200 * 1024) ZP_FAIL(ctx, -1, "zp_ransac: cap %d needs %zu bytes of shared memory in the final solve", cap, smem);
+    // threads per crop (measured, profiles/README.md): the solver phases keep one warp busy, so two 128-thread CTAs per SM
+    // (255 registers each) overlap one crop's solver with another's point loops: 789 vs 866 us at 1024 crops, the same
+    // 3-lane throughput at 64 crops (262 k vs 265 k poses/s) although one 64-crop launch alone takes 176 instead of 145 us.
+    // ONE shape for every batch size, so that a crop's pose does not depend on how the job was batched or sharded (the
+    // FP64 reduction trees differ between the two shapes); 256 threads only when the packed index list is too big for two
+    // CTAs per SM (cap > ~45 k correspondences).
+    const bool narrow = smem <= 100 * 1024;
     ZP_TIME_BEGIN(ctx, st);
-    zp_final_kernel<<<B, FIN_THREADS, smem, st>>>(a);
+    if (narrow) zp_final_kernel<128><<<B, 128, smem, st>>>(a);
+    else zp_final_kernel<256><<<B, 256, smem, st>>>(a);
     ZP_CHECK_LAUNCH(ctx, "zp_final_kernel");
     return 0;
 }
