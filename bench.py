@@ -226,6 +226,13 @@ def next_rows(eng, timed, d_bbox, d_K, d_obj, crops, tables, C, hbm_peak, fp32_p
                           "adi_tflops_9_per_pair": round(9 * pairs / us / 1e6, 2),
                           "adi_frac_of_fp32_peak": round(9 * pairs / us / 1e6 / fp32_peak, 3) if fp32_peak else None,
                           "pose_pairs_per_s": round(C / ms_e * 1e3)}
+    # configs[4]: the random-init network's bf16 forward feeding the path on the device (body = torch / cuDNN, not this
+    # repo's code; reported so the path's share of an end-to-end step is on record).  128 crops = 1024 over 8 GPUs.
+    try:
+        from tools import bench_net_e2e
+        out["network_feed"] = bench_net_e2e.measure(eng, 128, steps=5, warmup=3)
+    except Exception as exc:
+        out["network_feed"] = {"error": repr(exc)[:200]}
     return out
 
 
