@@ -79,3 +79,28 @@ def test_folded_batchnorm_equals_unfolded(run):
     # folding changes the rounding of every layer; activations are O(0.1 .. 1)
     assert float((fx - x[:1]).abs().max()) < 1e-4 * max(1.0, float(x[:1].abs().max()))
     assert float((fx_128 - x_128[:1]).abs().max()) < 1e-4 * max(1.0, float(x_128[:1].abs().max()))
+
+
+@pytest.mark.parametrize("H,W,d", [(32, 32, 18), (32, 32, 12), (32, 32, 6), (24, 40, 18), (16, 16, 18), (33, 20, 7)])
+def test_tap_conv_equals_dilated_conv(H, W, d):
+    """the nine-tap form of a dilated 3x3 convolution (used for the layer cuDNN runs pathologically) is the same sum"""
+    g = torch.Generator().manual_seed(H * 100 + d)
+    conv = torch.nn.Conv2d(12, 7, 3, 1, d, d)
+    with torch.no_grad():
+        conv.weight.copy_(torch.randn(conv.weight.shape, generator=g))
+        conv.bias.copy_(torch.randn(7, generator=g))
+        for x in (torch.randn(3, 12, H, W, generator=g),
+                  torch.randn(3, 12, H, W, generator=g).contiguous(memory_format=torch.channels_last)):
+            want = torch.nn.functional.conv2d(x.double(), conv.weight.double(), conv.bias.double(), 1, d, d)
+            got = znet.tap_conv3x3(conv, x)
+            assert got.shape == want.shape
+            assert float((got.double() - want).abs().max()) < 1e-5 * float(want.abs().max())
+
+
+def test_tap_form_of_the_network_equals_the_plain_one(run):
+    net, img, x, x_128, _ = run
+    tapped = znet.build(seed=0, tap_dilation=18)
+    assert tapped.aspp.tap_dilation == 18 and net.aspp.tap_dilation == 0
+    with torch.no_grad():
+        tx, _ = tapped(img[:1])
+    assert float((tx - x[:1]).abs().max()) < 1e-5 * max(1.0, float(x[:1].abs().max()))

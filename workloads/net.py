@@ -24,6 +24,26 @@ def _cb(conv, bn, x, relu=True):
     return F.relu(y, inplace=True) if relu else y
 
 
+def tap_conv3x3(conv, x):
+    """A dilated 3x3 convolution as its nine taps: tap (ky, kx) is a 1x1 convolution of the input shifted by
+    ((ky-1) d, (kx-1) d), and it only touches the output pixels whose shifted source lies inside the map.  On the 32 x 32
+    ASPP map with d = 18 the off-centre taps cover 14 of 32 rows / columns, so 3.5 of the 9 taps' products remain -- and
+    cuDNN's channels_last bf16 kernel for that shape is pathological (225 ms at 128 crops vs 0.25 ms for d = 6 / 12,
+    tools/prof_net_body.py).  Same sums as F.conv2d in a different order."""
+    d, (H, W) = conv.dilation[0], x.shape[2:]
+    assert conv.kernel_size == (3, 3) and conv.stride == (1, 1) and conv.padding == (d, d) and conv.dilation == (d, d)
+    w = conv.weight
+    out = F.conv2d(x, w[:, :, 1:2, 1:2], conv.bias)
+    for ky in range(3):
+        for kx in range(3):
+            dy, dx = (ky - 1) * d, (kx - 1) * d
+            y0, y1, x0, x1 = max(0, -dy), min(H, H - dy), max(0, -dx), min(W, W - dx)
+            if (ky, kx) == (1, 1) or y0 >= y1 or x0 >= x1:
+                continue
+            out[:, :, y0:y1, x0:x1] += F.conv2d(x[:, :, y0 + dy:y1 + dy, x0 + dx:x1 + dx], w[:, :, ky:ky + 1, kx:kx + 1])
+    return out
+
+
 class Residual(nn.Module):
     """3x3 -> 3x3 residual unit; keys conv1/bn1/conv2/bn2/downsample.{0,1} as torchvision's and model/resnet.py:20-51."""
 
@@ -91,10 +111,32 @@ class Decoder(nn.Module):
         self.upsample_2 = _up(256 + 64)
         self.conv_1x1_4 = nn.Conv2d(256 + 64, n_out, 1)
 
+    # cuDNN (9.x, B200) runs the dilation-18 convolution of the 32 x 32 map in 225 ms at 128 crops on channels_last bf16
+    # input (9.5 ms on NCHW; dilations 6 and 12 take 0.25 ms).  Two ways round it, both measured by tools/prof_net_body.py:
+    # `tap_dilation` (default on CUDA: that layer as nine 1x1 taps, everything stays channels_last) or `aspp_nchw` (the
+    # 134 MB feature map is re-laid once and the ASPP block alone runs in NCHW: layout only, same values).
+    aspp_nchw = False
+    tap_dilation = 0            # dilations >= this (and > 0) go through tap_conv3x3 instead of cuDNN's dilated kernel
+    _ASPP_CONVS = ("conv_1x1_1", "conv_3x3_1", "conv_3x3_2", "conv_3x3_3", "conv_1x1_2", "conv_1x1_3")
+
+    def use_nchw_aspp(self, on=True):
+        self.aspp_nchw = bool(on)
+        fmt = torch.contiguous_format if on else torch.channels_last
+        for n in self._ASPP_CONVS:
+            w = getattr(self, n).weight
+            w.data = w.data.contiguous(memory_format=fmt)
+        return self
+
     def forward(self, feat, x_64):
+        if self.aspp_nchw:
+            feat = feat.contiguous()
         branches = [_cb(self.conv_1x1_1, self.bn_conv_1x1_1, feat)]
         for i in (1, 2, 3):
-            branches.append(_cb(getattr(self, "conv_3x3_%d" % i), getattr(self, "bn_conv_3x3_%d" % i), feat))
+            conv, bn = getattr(self, "conv_3x3_%d" % i), getattr(self, "bn_conv_3x3_%d" % i)
+            if 0 < self.tap_dilation <= conv.dilation[0]:
+                branches.append(F.relu(bn(tap_conv3x3(conv, feat)), inplace=True))
+            else:
+                branches.append(_cb(conv, bn, feat))
         # image-level branch: bilinear interpolation of a 1x1 map is a broadcast
         pooled = _cb(self.conv_1x1_2, self.bn_conv_1x1_2, feat.mean((2, 3), keepdim=True))
         branches.append(pooled.expand(-1, -1, feat.shape[2], feat.shape[3]))
@@ -158,7 +200,7 @@ class ZebraNetBody(nn.Module):
         return self
 
 
-def build(seed=0, n_out=17, device="cpu", dtype=torch.float32, fold=False):
+def build(seed=0, n_out=17, device="cpu", dtype=torch.float32, fold=False, aspp_nchw=False, tap_dilation=None):
     """The random-init network of configs[4] (SURVEY 8(d) #5): torch.manual_seed(seed), default initialisers, eval."""
     gen_state = torch.random.get_rng_state()
     torch.manual_seed(seed)
@@ -178,6 +220,11 @@ def build(seed=0, n_out=17, device="cpu", dtype=torch.float32, fold=False):
     net = net.to(device=device, dtype=dtype)
     if dtype in (torch.bfloat16, torch.float16) or str(device).startswith("cuda"):
         net = net.to(memory_format=torch.channels_last)
+        if tap_dilation is None and not aspp_nchw:
+            tap_dilation = 18 if str(device).startswith("cuda") else 0
+    net.aspp.tap_dilation = int(tap_dilation or 0)
+    if aspp_nchw:
+        net.aspp.use_nchw_aspp(True)
     for p in net.parameters():
         p.requires_grad_(False)
     return net
