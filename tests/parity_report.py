@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Parity report (GPU): device decode + RANSAC-EPnP vs the reference path (oracle decode + cv2.solvePnPRansac) on the
 same seeded synthetic crops.  Prints a JSON summary; run on the GPU box, copy into profiles/.
-  python tools/parity_report.py [--crops 64] [--ignore-bit 0] [--out gpurun_out/parity.json]
+  python tests/parity_report.py [--crops 64] [--ignore-bit 0] [--out gpurun_out/parity.json]
 """
 import argparse
 import json

@@ -50,6 +50,13 @@ def test_no_gpu_fails_loudly():
 
 
 def test_product_does_not_import_oracle():
+    """oracle/ is the checker: only tests/, __graft_entry__.smoke() and bench.py's reference legs may import it"""
+    for sub in ("tools", "workloads"):
+        for dirpath, _, files in os.walk(os.path.join(ROOT, sub)):
+            for f in files:
+                if f.endswith(".py"):
+                    src = open(os.path.join(dirpath, f)).read()
+                    assert not re.search(r"^\s*(from|import)\s+oracle", src, re.M), os.path.join(sub, f)
     for dirpath, _, files in os.walk(os.path.join(ROOT, "zebrapose_b200")):
         for f in files:
             if f.endswith((".py", ".cu", ".cuh", ".h")):

@@ -34,7 +34,7 @@ def test_cnn_outputs_to_object_pose(golden, tables, tag):
         assert re < 0.2 and te < 2.0      # per-crop bound; the tolerance pass RATE is asserted in test_gpu_ransac
     else:
         # ignore_bit coarsens the 3D points: inlier ratios drop and the reference's own RANSAC becomes sampling-noise
-        # limited (tools/parity_report.py --ignore-bit 4), so the per-crop check is "as close to GT as the reference"
+        # limited (tests/parity_report.py --ignore-bit 4), so the per-crop check is "as close to GT as the reference"
         ref_gt = metrics.rot_err_deg(golden[tag + "_R"], c["R"])
         assert metrics.rot_err_deg(R, c["R"]) < max(2.0 * ref_gt, 1.0)
         assert metrics.trans_err(t, c["t"]) < max(2.0 * metrics.trans_err(golden[tag + "_t"], c["t"]), 10.0)
