@@ -111,7 +111,15 @@ def main():
     eng = zp.Engine(local)
     tab, _, _ = synth.make_dict(16, seed=5, radius=60.0, missing_frac=0.0)
     eng.upload_dict(0, tab)
-    row = measure(eng, B, steps=steps, dist=dist)
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)                       # NCCL prints its version banner on stdout at the first collective
+    try:
+        row = measure(eng, B, steps=steps, dist=dist)
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved, 1)
+        os.close(saved)
     if int(os.environ.get("RANK", "0")) == 0:
         print(json.dumps(row))
     if dist is not None:
