@@ -205,8 +205,8 @@ def build(seed=0, n_out=17, device="cpu", dtype=torch.float32, fold=False, aspp_
     gen_state = torch.random.get_rng_state()
     torch.manual_seed(seed)
     net = ZebraNetBody(n_out).eval()
-    # default-initialised BatchNorms of a 34-layer residual stack let the activations grow by orders of magnitude; give
-    # the running statistics seeded non-trivial values so the folded and the unfolded form are a real comparison
+    # a freshly constructed BatchNorm is the identity in eval mode (mean 0, var 1, weight 1, bias 0): give every one
+    # seeded non-trivial statistics and affine terms so that folding them (and the checkpoint round trip) is a real test
     g = torch.Generator().manual_seed(seed + 1)
     for m in net.modules():
         if isinstance(m, nn.BatchNorm2d):
