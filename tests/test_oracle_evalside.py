@@ -95,3 +95,24 @@ def test_input_crops_oracle_matches_reference():
         roi = evalside.get_roi_u8(img, boxes[i], 64, "crop_resize")
         assert np.array_equal(roi, g["full_u8_%d" % i])
         assert np.array_equal(evalside.to_tensor_normalize(roi), g["full_f32_%d" % i])
+
+
+def test_merge_csv_matches_reference(tmp_path):
+    """tools_for_BOP/merge_csv.py mirror against the bytes the reference's own main() wrote for the same three result
+    files (tests/golden/make_golden_merge.py): BOM, int -> float promotion of an all-integer score column, row order"""
+    from zebrapose_b200.tools_for_BOP import merge_csv, write_to_cvs
+    root = str(tmp_path / "results") + os.sep
+    for k, (ds, obj, obj_id, seed) in enumerate(synth_eval.MERGE_FILES):
+        d = os.path.join(root, ds, obj)
+        os.makedirs(d)
+        scene, img, Rs, ts, scores = synth_eval.make_csv_rows(seed)
+        if k == 1:
+            scores = [1, 1, 1, -1, 1, 1, 1]
+        write_to_cvs.write_cvs(d, "%s_%s" % (ds, obj), obj_id, scene, img, Rs, ts, scores)
+    out = str(tmp_path / "merged.csv")
+    assert merge_csv.main(root, out) == 3
+    want = open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_merged_v1.csv"), "rb").read()
+    assert open(out, "rb").read() == want
+    assert want.startswith(b"\xef\xbb\xbfscene_id,im_id,obj_id,score,R,t,time\n") and want.count(b"\n") == 1 + 3 * 6
+    with pytest.raises(ValueError):
+        merge_csv.main(str(tmp_path / "nothing") + os.sep, out)

@@ -58,6 +58,9 @@ def make_csv_rows(seed):
     return scene, img, Rs, ts, scores
 
 
+MERGE_FILES = [("lmo", "ape", 1, 9), ("lmo", "can", 5, 10), ("ycbv", "002_master_chef_can", 1, 11)]   # (dataset, object, obj_id, rows seed)
+
+
 CROP_CASES = [(256, "crop_square_resize"), (256, "crop_resize"), (128, "crop_square_resize"), (64, "crop_resize")]
 N_CROP_BOXES = 14
 
