@@ -1,5 +1,5 @@
 """One small pass over every kernel family for compute-sanitizer:
-    compute-sanitizer --tool memcheck python tools/sanitize_pass.py
+    compute-sanitizer --tool memcheck python tools/sanitize_pass.py      (closed on the shared pool: run natively there)
 2 crops, one dictionary; progress markers on stdout so a partial log still says how far it got."""
 import os
 import sys
@@ -39,7 +39,7 @@ eng.upload_model(0, verts)
 gt = np.stack([np.concatenate([np.asarray(c["R"], np.float64).ravel(), np.asarray(c["t"], np.float64).ravel()]) for c in crops])
 eng.pose_errors(r["poses"], gt, obj_default=0); mark("ADD / ADI V=%d" % len(verts))
 img = torch.from_numpy(synth_eval.make_image(5)).cuda()
-cb = torch.from_numpy(synth_eval.make_crop_boxes(B, 8).astype(np.float64)).cuda()
+cb = torch.from_numpy(synth_eval.make_crop_boxes(8, 8).astype(np.float64)).cuda()
 eng.crop_inputs(img, cb, crop_size=256); eng.final_bboxes(cb, 1.5, "crop_square_resize", 640, 480); mark("crops + boxes")
 g = torch.Generator(device="cpu").manual_seed(0)
 eng.upload_head(torch.randn(17, 320, generator=g) * 0.1, torch.randn(17, generator=g) * 0.1)
