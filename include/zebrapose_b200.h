@@ -39,6 +39,11 @@ enum { ZP_NONEXIST_ZERO = 0, ZP_NONEXIST_HAMMING = 1 };
 enum { ZP_SAMPLER_CV2 = 0, ZP_SAMPLER_PHILOX = 1 };
 enum { ZP_SELECT_CV2_REPLAY = 0, ZP_SELECT_ARGMAX = 1 };
 enum { ZP_FINAL_EPNP = 0, ZP_FINAL_EPNP_GN = 1 };
+/* minimal solver of the RANSAC hypotheses: CV2 = operation-by-operation replay of OpenCV's EPnP (hypotheses bit-identical
+ * to cv2.solvePnP(SOLVEPNP_EPNP), so the RANSAC winner is cv2's); FAST = float64 EPnP with a bisection / inverse-iteration
+ * null space (accurate, ~1e-5 deg from cv2 for m >= 6, but for 4/5-point samples it returns another null-space basis than
+ * cv2 and therefore other hypotheses). */
+enum { ZP_SOLVER_CV2 = 0, ZP_SOLVER_FAST = 1 };
 /* per-crop status written by zp_ransac */
 enum { ZP_OK = 0, ZP_NO_MASK_PIXELS = 1, ZP_TOO_FEW_POINTS = 2, ZP_RANSAC_NO_MODEL = 3 };
 
@@ -106,6 +111,14 @@ int zp_codes_to_ids(zp_ctx* ctx, const double* bits, int64_t N, int L, int base,
 int zp_make_samples(zp_ctx* ctx, const int32_t* counts, int cap, int B, int H, int m, int mode,
                     uint64_t seed, int32_t* samples, void* stream);
 
+/* Minimal solver used by zp_solve_minimal / zp_ransac / zp_pose_batch_host (ZP_SOLVER_*; default CV2). */
+int zp_set_solver(zp_ctx* ctx, int solver);
+/* Wave plan of zp_ransac: hypotheses are solved and scored in waves of sizes[0], sizes[1], ... (HOST int32[n], n <= 16;
+ * the last size repeats until H is covered) and after every wave cv2's adaptive-stop rule is replayed, so crops that
+ * have reached their stopping iteration skip the remaining waves.  n = 0: automatic.  Results do not depend on the plan
+ * (cv2 never consults a hypothesis at or past its stopping iteration). */
+int zp_set_waves(zp_ctx* ctx, int n, const int32_t* sizes);
+
 /* EPnP on each m-point minimal set (float64).  K double [B,9] row-major.  hyp_poses double [B,H,12] out;
  * hypotheses of crops with too few points or degenerate samples are written as NaN. */
 int zp_solve_minimal(zp_ctx* ctx, const float* corr, int cap, const int32_t* counts, const double* K,
@@ -124,11 +137,13 @@ int zp_score(zp_ctx* ctx, const float* corr, int cap, const int32_t* counts, con
  * (CV2_REPLAY: cv2's strictly-greater update with RANSACUpdateNumIters(confidence) replayed over the H counts;
  * ARGMAX: most inliers, lowest index on ties) -> EPnP on the winner's inliers (+ optional Gauss-Newton polish).
  * Outputs: poses double [B,12], n_inliers int32 [B], status int32 [B]; nullable hyp_poses double [B,H,12],
- * hyp_inliers int32 [B,H], best_idx int32 [B], inlier_mask uint8 [B,cap]. */
+ * hyp_inliers int32 [B,H], best_idx int32 [B], iters_run int32 [B] (iterations cv2's loop runs before its adaptive
+ * stop), inlier_mask uint8 [B,cap].  Asking for hyp_poses / hyp_inliers makes one wave of all H hypotheses; otherwise
+ * hypotheses at or past a crop's stopping iteration may not be computed (zp_set_waves). */
 int zp_ransac(zp_ctx* ctx, const float* corr, int cap, const int32_t* counts, const double* K,
               const int32_t* samples, int B, int H, int m, float thr_px, double confidence,
               int sampler, uint64_t seed, int select_mode, int final_mode,
-              double* hyp_poses, int32_t* hyp_inliers, int32_t* best_idx, uint8_t* inlier_mask,
+              double* hyp_poses, int32_t* hyp_inliers, int32_t* best_idx, int32_t* iters_run, uint8_t* inlier_mask,
               double* poses, int32_t* n_inliers, int32_t* status, void* stream);
 
 /* The reference-facing one-call form with HOST buffers (what a per-batch drop-in of test.py:250-273 calls):

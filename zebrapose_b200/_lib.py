@@ -11,6 +11,7 @@ NONEXIST = {"zero": 0, "hamming": 1}
 SAMPLER = {"cv2": 0, "philox": 1}
 SELECT = {"cv2_replay": 0, "argmax": 1}
 FINAL = {"epnp": 0, "epnp+gn": 1}
+SOLVER = {"cv2": 0, "fast": 1}
 RESIZE = {"crop_resize": 0, "crop_square_resize": 1, "crop_resize_by_warp_affine": 2, "none": 3}
 STATUS_OK, STATUS_NO_MASK, STATUS_TOO_FEW, STATUS_NO_MODEL = 0, 1, 2, 3
 
@@ -29,7 +30,10 @@ SIGNATURES = {
     "zp_make_samples": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _u64, _vp, _vp]),
     "zp_solve_minimal": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
     "zp_score": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _i, _i, _f, _vp, _vp]),
-    "zp_ransac": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _f, _d, _i, _u64, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "zp_ransac": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _f, _d, _i, _u64, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                       _vp]),
+    "zp_set_solver": (_i, [_vp, _i]),
+    "zp_set_waves": (_i, [_vp, _i, _vp]),
     "zp_pose_batch_host": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _i, _i, _f, _d, _i, _u64, _i, _i,
                                 _vp, _vp, _vp]),
     "zp_pose_batch_host_async": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _i, _i, _f, _d, _i, _u64, _i, _i,

@@ -4,12 +4,17 @@
 #include "zp_common.cuh"
 
 int zp_launch_samples(zp_ctx*, const int32_t*, int, int, int, int, int, uint64_t, int32_t*, cudaStream_t);
-int zp_launch_minimal(zp_ctx*, const float*, int, const int32_t*, const double*, const int32_t*, int, int, int, float,
-                      double*, float*, int32_t*, cudaStream_t);
+int zp_launch_minimal(zp_ctx*, const float*, int, const int32_t*, const double*, const int32_t*, int, int, int, int,
+                      const int32_t*, int, float, double*, float*, int32_t*, cudaStream_t);
 int zp_launch_poses_to_P(zp_ctx*, const double*, const double*, int, int, float, float*, cudaStream_t);
-int zp_launch_score(zp_ctx*, const float*, int, const int32_t*, const float*, int, int, float, int32_t*, bool, cudaStream_t);
+int zp_launch_score(zp_ctx*, const float*, int, const int32_t*, const float*, int, int, int, int, const int32_t*, float,
+                    int32_t*, bool, cudaStream_t);
 int zp_launch_final(zp_ctx*, const float*, int, const int32_t*, const double*, const double*, const int32_t*, int, int, int,
-                    double, int, float, int, double*, int32_t*, int32_t*, int32_t*, uint8_t*, cudaStream_t);
+                    double, int, float, int, double*, int32_t*, int32_t*, int32_t*, uint8_t*, const int32_t*, int32_t*,
+                    cudaStream_t);
+int zp_launch_rs_init(zp_ctx*, const int32_t*, int, int, int, int32_t*, int32_t*, int32_t*, cudaStream_t);
+int zp_launch_rs_replay(zp_ctx*, const int32_t*, int, const int32_t*, int, int, int, int, int, double, int, int32_t*,
+                        int32_t*, cudaStream_t);
 int zp_launch_fma_probe(zp_ctx*, int, int, double*);
 int zp_read_debug_clocks(long long*);
 int zp_launch_remap_pixels(zp_ctx*, const int64_t*, int64_t, const double*, int, int64_t*, cudaStream_t);
@@ -121,6 +126,22 @@ int zp_set_score_groups(zp_ctx* ctx, int groups, int hyp_chunk) {
     if (hyp_chunk < -1 || hyp_chunk > ZP_MAX_HYPOTHESES) ZP_FAIL(ctx, -1, "zp_set_score_groups: bad hyp_chunk %d", hyp_chunk);
     ctx->score_groups = groups;
     ctx->score_hchunk = hyp_chunk;
+    return 0;
+}
+
+int zp_set_solver(zp_ctx* ctx, int solver) {
+    if (!ctx) return -1;
+    if (solver != ZP_SOLVER_CV2 && solver != ZP_SOLVER_FAST) ZP_FAIL(ctx, -1, "zp_set_solver: bad solver %d", solver);
+    ctx->solver = solver;
+    return 0;
+}
+
+int zp_set_waves(zp_ctx* ctx, int n, const int32_t* sizes) {
+    if (!ctx) return -1;
+    if (n < 0 || n > 16 || (n > 0 && !sizes)) ZP_FAIL(ctx, -1, "zp_set_waves: 0 <= n <= 16 sizes");
+    for (int i = 0; i < n; i++) if (sizes[i] < 1) ZP_FAIL(ctx, -1, "zp_set_waves: wave size %d", sizes[i]);
+    ctx->n_waves = n;
+    for (int i = 0; i < n; i++) ctx->wave_sizes[i] = sizes[i];
     return 0;
 }
 
@@ -320,8 +341,8 @@ int zp_solve_minimal(zp_ctx* ctx, const float* corr, int cap, const int32_t* cou
     if (m < 4 || m > 8 || H < 1 || H > ZP_MAX_HYPOTHESES) ZP_FAIL(ctx, -1, "zp_solve_minimal: bad m/H %d/%d", m, H);
     ZP_CUDA(ctx, cudaSetDevice(ctx->device));
     if (zp_ws_reserve(ctx, (size_t)B * H * 24 * sizeof(float))) return -2;
-    return zp_launch_minimal(ctx, corr, cap, counts, K, samples, B, H, m, 2.0f, hyp_poses, (float*)ctx->ws, nullptr,
-                             (cudaStream_t)stream);
+    return zp_launch_minimal(ctx, corr, cap, counts, K, samples, B, H, 0, H, nullptr, m, 2.0f, hyp_poses, (float*)ctx->ws,
+                             nullptr, (cudaStream_t)stream);
 }
 
 static int check_corr(zp_ctx* ctx, const float* corr, int cap, const char* who) {
@@ -341,15 +362,25 @@ int zp_score(zp_ctx* ctx, const float* corr, int cap, const int32_t* counts, con
     ZP_CUDA(ctx, cudaSetDevice(ctx->device));
     if (zp_ws_reserve(ctx, (size_t)B * H * 24 * sizeof(float))) return -2;
     if (int r = zp_launch_poses_to_P(ctx, hyp_poses, K, B, H, thr_px, (float*)ctx->ws, (cudaStream_t)stream)) return r;
-    return zp_launch_score(ctx, corr, cap, counts, (const float*)ctx->ws, B, H, thr_px, hyp_inliers, false, (cudaStream_t)stream);
+    return zp_launch_score(ctx, corr, cap, counts, (const float*)ctx->ws, B, H, 0, H, nullptr, thr_px, hyp_inliers, false,
+                           (cudaStream_t)stream);
 }
 
 static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
+// hypotheses per wave: the caller's plan (zp_set_waves), or automatic -- cv2 stops after 24-46 iterations on crops with
+// ~70 % inliers, so the first wave covers most crops; small batches take fewer, larger waves because a wave costs a fixed
+// latency (three one-wave launches) whatever its size.
+static int wave_size(const zp_ctx* ctx, int w, int B) {
+    if (ctx->n_waves > 0) return ctx->wave_sizes[w < ctx->n_waves ? w : ctx->n_waves - 1];
+    if (B <= 128) return w == 0 ? 64 : ZP_MAX_HYPOTHESES;
+    return w < 3 ? 32 : ZP_MAX_HYPOTHESES;
+}
+
 int zp_ransac(zp_ctx* ctx, const float* corr, int cap, const int32_t* counts, const double* K, const int32_t* samples,
               int B, int H, int m, float thr_px, double confidence, int sampler, uint64_t seed, int select_mode,
-              int final_mode, double* hyp_poses, int32_t* hyp_inliers, int32_t* best_idx, uint8_t* inlier_mask,
-              double* poses, int32_t* n_inliers, int32_t* status, void* stream) {
+              int final_mode, double* hyp_poses, int32_t* hyp_inliers, int32_t* best_idx, int32_t* iters_run,
+              uint8_t* inlier_mask, double* poses, int32_t* n_inliers, int32_t* status, void* stream) {
     if (!ctx) return -1;
     if (B == 0) return 0;
     if (!corr || !counts || !K || !poses || !n_inliers || !status) ZP_FAIL(ctx, -1, "zp_ransac: null argument");
@@ -359,8 +390,10 @@ int zp_ransac(zp_ctx* ctx, const float* corr, int cap, const int32_t* counts, co
     ZP_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = (cudaStream_t)stream;
     if (!(thr_px > 0)) ZP_FAIL(ctx, -1, "zp_ransac: thr_px must be > 0");
-    // workspace: hyp_P | samples | hyp_poses | hyp_inliers (the last three only if the caller did not supply them)
-    size_t o_P = 0, o_s = o_P + align256((size_t)B * H * 24 * 4);
+    // workspace: hyp_P | RANSAC state | done flags | samples | hyp_poses | hyp_inliers (the last three only if the caller
+    // did not supply them)
+    size_t o_P = 0, o_rs = o_P + align256((size_t)B * H * 24 * 4), o_dn = o_rs + align256((size_t)B * 4 * 4);
+    size_t o_s = o_dn + align256((size_t)B * 4);
     size_t o_p = o_s + (samples ? 0 : align256((size_t)B * H * m * 4));
     size_t o_i = o_p + (hyp_poses ? 0 : align256((size_t)B * H * 12 * 8));
     size_t total = o_i + (hyp_inliers ? 0 : align256((size_t)B * H * 4));
@@ -374,11 +407,24 @@ int zp_ransac(zp_ctx* ctx, const float* corr, int cap, const int32_t* counts, co
     double* d_hp = hyp_poses ? hyp_poses : (double*)(ws + o_p);
     int32_t* d_hi = hyp_inliers ? hyp_inliers : (int32_t*)(ws + o_i);
     float* d_P = (float*)(ws + o_P);
-    // the minimal solver zeroes the inlier counters of its hypotheses: the scoring launch follows without a memset node
-    if (int r = zp_launch_minimal(ctx, corr, cap, counts, K, samples ? samples : d_samples, B, H, m, thr_px, d_hp, d_P, d_hi, st)) return r;
-    if (int r = zp_launch_score(ctx, corr, cap, counts, d_P, B, H, thr_px, d_hi, true, st)) return r;
+    int32_t* d_rs = (int32_t*)(ws + o_rs);
+    int32_t* d_done = (int32_t*)(ws + o_dn);
+    // exported hypothesis lists are diagnostic: all H hypotheses of every crop in one wave
+    const bool full = hyp_poses || hyp_inliers || select_mode != ZP_SELECT_CV2_REPLAY;
+    if (int r = zp_launch_rs_init(ctx, counts, cap, B, H, d_rs, d_done, nullptr, st)) return r;
+    for (int h0 = 0, w = 0; h0 < H; w++) {
+        int hw = full ? H : wave_size(ctx, w, B);
+        if (hw > H - h0) hw = H - h0;
+        // the minimal solver zeroes the inlier counters of its hypotheses: the scoring launch follows without a memset node
+        if (int r = zp_launch_minimal(ctx, corr, cap, counts, K, samples ? samples : d_samples, B, H, h0, hw, d_done, m, thr_px,
+                                      d_hp, d_P, d_hi, st)) return r;
+        if (int r = zp_launch_score(ctx, corr, cap, counts, d_P, B, H, h0, hw, d_done, thr_px, d_hi, true, st)) return r;
+        if (int r = zp_launch_rs_replay(ctx, counts, cap, d_hi, B, H, h0, h0 + hw, m, confidence, select_mode, d_rs, d_done, st))
+            return r;
+        h0 += hw;
+    }
     return zp_launch_final(ctx, corr, cap, counts, K, d_hp, d_hi, B, H, m, confidence, select_mode, thr_px, final_mode,
-                           poses, n_inliers, status, best_idx, inlier_mask, st);
+                           poses, n_inliers, status, best_idx, inlier_mask, d_rs, iters_run, st);
 }
 
 int zp_pose_batch_host_async(zp_ctx* ctx, const void* h_logits, int dtype, int B, int C, int S, int mask_ch, int bit0_ch,
@@ -415,7 +461,7 @@ int zp_pose_batch_host_async(zp_ctx* ctx, const void* h_logits, int dtype, int B
     if (int r = zp_decode(ctx, d_log, dtype, B, S, strides, mask_ch, bit0_ch, n_bits, ignore_bit, nullptr, d_box,
                           h_obj_ids ? d_obj : nullptr, obj_default, nullptr, d_corr, cap, d_cnt, st)) return r;
     if (int r = zp_ransac(ctx, d_corr, cap, d_cnt, d_K, nullptr, B, H, m, thr_px, confidence, sampler, seed, select_mode,
-                          final_mode, nullptr, nullptr, nullptr, nullptr, d_pose, d_ni, d_st, st)) return r;
+                          final_mode, nullptr, nullptr, nullptr, nullptr, nullptr, d_pose, d_ni, d_st, st)) return r;
     ZP_CUDA(ctx, cudaMemcpyAsync(h_poses, d_pose, (size_t)B * 12 * 8, cudaMemcpyDeviceToHost, st));
     ZP_CUDA(ctx, cudaMemcpyAsync(h_n_inliers, d_ni, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
     ZP_CUDA(ctx, cudaMemcpyAsync(h_status, d_st, (size_t)B * 4, cudaMemcpyDeviceToHost, st));

@@ -11,6 +11,7 @@
 #include "../../include/zebrapose_b200.h"
 
 #define ZP_SM_COUNT_FALLBACK 148
+#define ZP_MAX_DEVICES 64
 
 struct ZpTable {
     float4* pts = nullptr;      // [2^(n_bits-k)] x,y,z,exists  (L2-resident, gathered per masked pixel)
@@ -67,6 +68,14 @@ struct zp_ctx {
     void* dbg_buf = nullptr;                 // device buffer for per-CTA timestamps of the decode kernel (zp_debug_buffer)
     int decode_rpc = 0;                      // runs per CTA of the streaming decode kernel (0 = automatic)
     int force_decode_path = 0;               // 0 auto, 1 register-staged cluster kernel, 2 generic kernel (tests)
+    // RANSAC: minimal solver (ZP_SOLVER_*), wave plan (hypotheses per wave; n_waves = 0: automatic)
+    int solver = 0;
+    int n_waves = 0;
+    int wave_sizes[16] = {0};
+    // "function attribute set on this context's device" flags (cudaFuncSetAttribute is per device, a ctx is per device)
+    bool cvs_attr_set = false, min_attr_set = false, fin_attr_set = false;
+    int min_force = 0;
+    int score_per_sm[3] = {0, 0, 0};
 };
 
 #define ZP_FAIL(ctx, code, ...)                                  \

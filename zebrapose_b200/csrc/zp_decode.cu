@@ -441,7 +441,8 @@ __global__ void __launch_bounds__(DEC_THREADS, 2) zp_decode_stream_kernel(Decode
 template <int DT>
 static int launch_stream(zp_ctx* ctx, const DecodeArgs& a, int runs, cudaStream_t st) {
     const int smem = 5 * DEC_THREADS * Px<DT>::N * (int)sizeof(float);
-    static bool attr_set = false;
+    static bool attr_set_dev[ZP_MAX_DEVICES] = {};          // cudaFuncSetAttribute is per device
+    bool& attr_set = attr_set_dev[ctx->device % ZP_MAX_DEVICES];
     if (!attr_set) {
         ZP_CUDA(ctx, cudaFuncSetAttribute(zp_decode_stream_kernel<DT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         ZP_CUDA(ctx, cudaFuncSetAttribute(zp_decode_stream_kernel<DT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -631,7 +632,8 @@ static int launch_split(zp_ctx* ctx, const DecodeArgs& a, cudaStream_t st) {
     zp_decode_planes_kernel<DT><<<grid1, PL_THREADS, 0, st>>>(a, codes, maskw, segs);
     ZP_CHECK_LAUNCH(ctx, "zp_decode_planes_kernel");
     const int smem = 5 * DEC_THREADS * PPT * (int)sizeof(float);
-    static bool attr_set = false;
+    static bool attr_set_dev[ZP_MAX_DEVICES] = {};          // cudaFuncSetAttribute is per device
+    bool& attr_set = attr_set_dev[ctx->device % ZP_MAX_DEVICES];
     if (!attr_set) {
         ZP_CUDA(ctx, cudaFuncSetAttribute(zp_decode_emit_kernel<PPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr_set = true;
@@ -656,7 +658,8 @@ int zp_launch_emit_codes(zp_ctx* ctx, int B, int S, const double* bbox, const in
     const int runs = (segs + DEC_WARPS - 1) / DEC_WARPS;
     if (S % PPT != 0 || S > 1024 || runs > 64) ZP_FAIL(ctx, -1, "emit from codes: crop size %d not supported", S);
     const int smem = 5 * DEC_THREADS * PPT * (int)sizeof(float);
-    static bool attr_set = false;
+    static bool attr_set_dev[ZP_MAX_DEVICES] = {};          // cudaFuncSetAttribute is per device
+    bool& attr_set = attr_set_dev[ctx->device % ZP_MAX_DEVICES];
     if (!attr_set) {
         ZP_CUDA(ctx, cudaFuncSetAttribute(zp_decode_emit_kernel<PPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr_set = true;
@@ -975,7 +978,8 @@ __global__ void __launch_bounds__(TMA_THREADS, 2) zp_decode_tma_kernel(DecodeArg
 template <int DT>
 static int launch_tma(zp_ctx* ctx, const DecodeArgs& a, int parts, int part_px, cudaStream_t st) {
     const size_t smem = (size_t)TMA_SLOTS * TMA_SLOT_BYTES;
-    static bool smem_set = false;
+    static bool smem_set_dev[ZP_MAX_DEVICES] = {};
+    bool& smem_set = smem_set_dev[ctx->device % ZP_MAX_DEVICES];
     if (!smem_set) {
         ZP_CUDA(ctx, cudaFuncSetAttribute(zp_decode_tma_kernel<DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         smem_set = true;
@@ -1070,7 +1074,8 @@ static int launch_cluster(zp_ctx* ctx, const DecodeArgs& a, int csize, bool use_
     cfg.gridDim = dim3((unsigned)(a.B * csize));
     cfg.blockDim = dim3(DEC_THREADS);
     const int smem = 5 * DEC_THREADS * Px<DT>::N * (int)sizeof(float);
-    static bool attr_set = false;
+    static bool attr_set_dev[ZP_MAX_DEVICES] = {};          // cudaFuncSetAttribute is per device
+    bool& attr_set = attr_set_dev[ctx->device % ZP_MAX_DEVICES];
     if (!attr_set) {
         ZP_CUDA(ctx, cudaFuncSetAttribute(zp_decode_cluster_kernel<DT, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         ZP_CUDA(ctx, cudaFuncSetAttribute(zp_decode_cluster_kernel<DT, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));

@@ -353,7 +353,8 @@ int zp_head_decode(zp_ctx* ctx, const void* x, int c1, const void* x_skip, int c
     p.codes = d_codes; p.maskb = d_mask;
     for (int o = 0; o < HD_N; o++) p.bias[o] = ctx->head_bias[o];
     const int smem = HD_STAGES * HD_A_BYTES + HD_MAX_KB * HD_W_BYTES + 256 + 1024;
-    static bool attr_set = false;
+    static bool attr_set_dev[ZP_MAX_DEVICES] = {};          // cudaFuncSetAttribute is per device
+    bool& attr_set = attr_set_dev[ctx->device % ZP_MAX_DEVICES];
     if (!attr_set) {
         ZP_CUDA(ctx, cudaFuncSetAttribute(zp_head_codes_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         ZP_CUDA(ctx, cudaFuncSetAttribute(zp_head_codes_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));

@@ -27,6 +27,7 @@ __device__ long long zp_dbg_clk[24];
 #define ZP_STAMP(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) zp_dbg_clk[i] = clock64(); } while (0)
 #define ZP_EIG_STAMP(i) ZP_STAMP(i)
 #include "zp_epnp.cuh"
+#include "zp_proj.cuh"
 
 // ---------------------------------------------------------------------------------------------------------------
 // samples
@@ -183,23 +184,6 @@ zp_samples_kernel(const int32_t* __restrict__ counts, int cap, int B, int H, int
 // ---------------------------------------------------------------------------------------------------------------
 // projection matrices and the inlier predicate shared by the minimal solver (writes P), scoring and the final solve
 // ---------------------------------------------------------------------------------------------------------------
-// P = diag(1/thr, 1/thr, 1) K [R|t] evaluated in double, rounded once to float32.  Folding the threshold into rows 0,1
-// (and into u, v: see zp_inlier_d) turns the test into (x - u z)^2 + (y - v z)^2 <= z^2.  A non-finite pose gives P = 0,
-// for which the predicate is false for every point.
-__device__ __forceinline__ void zp_make_P(const double* pose, const double* K, double inv_thr, float P[12]) {
-    const double fx = K[0], sk = K[1], cx = K[2], fy = K[4], cy = K[5];
-    bool fin = true;
-#pragma unroll
-    for (int e = 0; e < 12; e++) fin = fin && isfinite(pose[e]);
-#pragma unroll
-    for (int c = 0; c < 4; c++) {
-        double r0 = c < 3 ? pose[c] : pose[9], r1 = c < 3 ? pose[3 + c] : pose[10], r2 = c < 3 ? pose[6 + c] : pose[11];
-        P[c] = fin ? (float)((fx * r0 + sk * r1 + cx * r2) * inv_thr) : 0.f;
-        P[4 + c] = fin ? (float)((fy * r1 + cy * r2) * inv_thr) : 0.f;
-        P[8 + c] = fin ? (float)r2 : 0.f;
-    }
-}
-
 // d = (x - u z)^2 + (y - v z)^2 - z^2 with [x y z] = P [X Y Z 1] and u, v already divided by thr; the point is an inlier
 // iff d < 0, i.e. iff the SIGN BIT of d is set (14 FP32-pipe instructions, no compare; explicit fmaf so every kernel
 // rounds identically).
@@ -254,18 +238,22 @@ constexpr int MIN_SMEM_BYTES = (MIN_THREADS / 4) * MIN_HYP_DOUBLES * (int)sizeof
 template <int MINB>
 __global__ void __launch_bounds__(MIN_THREADS, MINB)
 zp_minimal_kernel(const float* __restrict__ corr, int cap, const int32_t* __restrict__ counts,
-                  const double* __restrict__ Kmat, const int32_t* __restrict__ samples, int B, int H, int m,
+                  const double* __restrict__ Kmat, const int32_t* __restrict__ samples, int B, int H, int h0, int hw,
+                  const int32_t* __restrict__ crop_done /* nullable: crops that reached cv2's adaptive stop */, int m,
                   double inv_thr, double* __restrict__ hyp_poses, float* __restrict__ hyp_P,
                   int32_t* __restrict__ hyp_inliers /* nullable: zeroed here so the scoring launch needs no memset */) {
     extern __shared__ __align__(16) double s_min[];            // per hypothesis: z[12x13] | d[12] | e[12] | V[4x12]
     const int tid = threadIdx.x, lane = tid & 31, q = lane & 3, quad = tid >> 2;
     double* s_z = s_min + (size_t)quad * MIN_HYP_DOUBLES;
     double* s_Vq = s_z + ZP_SYM_DOUBLES + 24;
-    const int total = B * H;
+    // hypotheses [h0, h0 + hw) of every crop: local index -> (crop, hypothesis)
+    const int total = B * hw;
     const int g_raw = blockIdx.x * (MIN_THREADS / 4) + quad;
-    const bool live = g_raw < total;
-    const int g = live ? g_raw : total - 1;        // dead quads shadow the last hypothesis (all lanes take part in shuffles)
-    const int b = g / H;
+    const int gl = g_raw < total ? g_raw : total - 1;   // dead quads shadow the last hypothesis (all lanes take part in shuffles)
+    const int b = gl / hw;
+    const int g = b * H + h0 + (gl - b * hw);
+    const bool live = g_raw < total && !(crop_done && crop_done[b]);
+    if (!__syncthreads_or(live)) return;           // every hypothesis of this CTA belongs to a finished crop
     ZP_STAMP(10);
     const int32_t* sidx = samples + (size_t)g * m;
     const int n = min(counts[b], cap);
@@ -414,6 +402,8 @@ struct ScoreArgs {
     const float* corr; int cap; const int32_t* counts; const float* hyp_P;
     int B, H; float inv_thr; int32_t* hyp_inliers; int* counters; int n_items;
     int hchunk, n_hc;            // hypotheses per work item and items per tile (small batches are cut finer)
+    int h0, hw;                  // this launch scores hypotheses [h0, h0 + hw) ...
+    const int32_t* crop_done;    // ... of the crops that have not reached cv2's adaptive stop (nullable: all)
 };
 
 // Persistent CTAs pulling work items (crop b, tile of SC_TILE correspondences) from a global ticket counter; items are
@@ -453,6 +443,7 @@ __global__ void __launch_bounds__(SC_GROUP * SC_NG) zp_score_kernel(ScoreArgs a)
         const int hc = w % a.n_hc;
         w /= a.n_hc;
         const int b = w % a.B, tile = w / a.B;
+        if (a.crop_done && a.crop_done[b]) continue;
         const int n = min(a.counts[b], a.cap);
         const int start = tile * SC_TILE;
         if (start >= n) continue;
@@ -461,7 +452,7 @@ __global__ void __launch_bounds__(SC_GROUP * SC_NG) zp_score_kernel(ScoreArgs a)
         const float* cb = a.corr + (size_t)b * 5 * a.cap + start;
         const uint32_t bytes = (uint32_t)((cnt + 3) & ~3) * 4u;        // 16-byte granules; cap % 4 == 0 keeps it in bounds
         f32x2 nu[SC_PPT / 2], nv[SC_PPT / 2], X[SC_PPT / 2], Y[SC_PPT / 2], Z[SC_PPT / 2];   // point pairs (j, j+1)
-        const int h_begin = hc * a.hchunk, h_end = min(H, h_begin + a.hchunk);
+        const int h_begin = a.h0 + hc * a.hchunk, h_end = min(a.h0 + a.hw, h_begin + a.hchunk);
         for (int h0 = h_begin; h0 < h_end; h0 += SC_HB) {
             const int hb = min(SC_HB, h_end - h0);
             if (tid == 0) {
@@ -558,6 +549,15 @@ __global__ void __launch_bounds__(SC_GROUP * SC_NG) zp_score_kernel(ScoreArgs a)
 // ---------------------------------------------------------------------------------------------------------------
 // winner selection + final solve on the inliers of the winner: one CTA per crop
 // ---------------------------------------------------------------------------------------------------------------
+// ---------------------------------------------------------------------------------------------------------------
+// RANSAC control state: cv2's loop (RANSACPointSetRegistrator::run inside cv2.solvePnPRansac)
+//     niters = H; for (it = 0; it < niters; it++) { good = count[it];
+//         if (good > max(maxGood, m-1)) { best = it; maxGood = good; niters = RANSACUpdateNumIters(conf, (n-good)/n, m, niters); } }
+// replayed wave by wave: hypotheses [h0, h1) have just been scored; the loop advances through them and stops where cv2
+// would have stopped.  A crop is `done` once every remaining hypothesis lies at or past its niters -- the next waves
+// skip it, and since cv2 never looks at those hypotheses the result does not depend on the wave plan.
+// rs[b] = {niters, maxGood, best, iterations run}; one thread per crop (a handful of pow/log per crop).
+// ---------------------------------------------------------------------------------------------------------------
 __device__ inline int zp_update_iters(double p, double ep, int m, int maxit) {   // cv::RANSACUpdateNumIters
     p = fmin(fmax(p, 0.0), 1.0);
     ep = fmin(fmax(ep, 0.0), 1.0);
@@ -567,6 +567,44 @@ __device__ inline int zp_update_iters(double p, double ep, int m, int maxit) {  
     num = log(num);
     den = log(den);
     return (den >= 0 || -num >= maxit * (-den)) ? maxit : (int)rint(num / den);
+}
+
+__global__ void zp_rs_init_kernel(const int32_t* __restrict__ counts, int cap, int B, int H, int32_t* __restrict__ rs,
+                                  int32_t* __restrict__ crop_done, int32_t* __restrict__ hyp_inliers_fill) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < B) {
+        const int n = min(counts[b], cap);
+        rs[4 * b] = max(H, 1); rs[4 * b + 1] = 0; rs[4 * b + 2] = -1; rs[4 * b + 3] = 0;
+        crop_done[b] = n < 6 ? 1 : 0;                 // CNN_output_to_pose.py:126: no RANSAC below six correspondences
+    }
+    if (hyp_inliers_fill)                              // hypotheses that are never run read back as -1
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < B * H; i += gridDim.x * blockDim.x) hyp_inliers_fill[i] = -1;
+}
+
+__global__ void zp_rs_replay_kernel(const int32_t* __restrict__ counts, int cap, const int32_t* __restrict__ hyp_inliers,
+                                    int B, int H, int h0, int h1, int m, double conf, int select_mode,
+                                    int32_t* __restrict__ rs, int32_t* __restrict__ crop_done) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B || crop_done[b]) return;
+    const int n = min(counts[b], cap);
+    int niters = rs[4 * b], maxgood = rs[4 * b + 1], best = rs[4 * b + 2], it = h0;
+    const int32_t* hi = hyp_inliers + (size_t)b * H;
+    if (select_mode == ZP_SELECT_CV2_REPLAY) {
+        for (; it < h1 && it < niters; it++) {
+            const int good = hi[it];
+            if (good > max(maxgood, m - 1)) {
+                best = it; maxgood = good;
+                niters = zp_update_iters(conf, (double)(n - good) / n, m, niters);
+            }
+        }
+    } else {                                           // most inliers, lowest index on ties, every hypothesis consulted
+        for (; it < h1; it++) {
+            const int good = hi[it];
+            if (good > max(maxgood, m - 1)) { best = it; maxgood = good; }
+        }
+    }
+    rs[4 * b] = niters; rs[4 * b + 1] = maxgood; rs[4 * b + 2] = best; rs[4 * b + 3] = it;
+    if (h1 >= H || (select_mode == ZP_SELECT_CV2_REPLAY && h1 >= niters)) crop_done[b] = 1;
 }
 
 constexpr int FIN_THREADS_MAX = 256;       // threads per crop: 256 (one CTA per SM) or 128 (two CTAs per SM), see zp_launch_final
@@ -594,6 +632,7 @@ struct FinalArgs {
     const float* corr; int cap; const int32_t* counts; const double* K; const double* hyp_poses;
     const int32_t* hyp_inliers; int B, H, m; double conf; int select_mode; float inv_thr; int final_mode;
     double* poses; int32_t* n_inliers; int32_t* status; int32_t* best_idx; uint8_t* inlier_mask;
+    const int32_t* rs; int32_t* iters_run;      // per-crop RANSAC state {niters, maxGood, best, iterations run}
 };
 
 // (register budget measured: 255 registers per thread beat 128 (2 x 256 threads per SM) and 80 at 64 AND at 1024 crops --
@@ -612,92 +651,31 @@ __global__ void __launch_bounds__(FIN_THREADS) zp_final_kernel(FinalArgs a) {
     __shared__ int s_candok[3];
     __shared__ double s_pose[12];
     __shared__ int s_first, s_n, s_best, s_status;
-    extern __shared__ __align__(8) unsigned char s_dynb[];   // H log(den) | inlier bitset (cap+31)/32 words | H counts | H ratios | record bits
-    double* s_ld = (double*)s_dynb;
-    uint32_t* s_mask = (uint32_t*)(s_ld + a.H);
-    int* s_hi = (int*)(s_mask + (a.cap + 31) / 32);
-    int* s_rt = s_hi + a.H;
-    unsigned* s_rec = (unsigned*)(s_rt + a.H);
+    extern __shared__ __align__(8) unsigned char s_dynb[];   // inlier bitset (cap+31)/32 words | packed inlier indices
+    uint32_t* s_mask = (uint32_t*)s_dynb;
     // compacted inlier indices: warp w owns the points [w * chunk, (w + 1) * chunk) and packs the inliers among them
     // at the start of its own segment (deterministic order, no cross-warp scan); s_wpre = exclusive prefix of the counts
-    uint16_t* s_idx = (uint16_t*)(s_rec + (a.H + 31) / 32 + FIN_THREADS / 32);
-    __shared__ int s_wmax[FIN_THREADS / 32];
+    uint16_t* s_idx = (uint16_t*)(s_mask + (a.cap + 31) / 32 + 1);
     __shared__ int s_wcnt[FIN_THREADS / 32], s_wpre[FIN_THREADS / 32];
 
     ZP_STAMP(0);
     double* out = a.poses + 12 * (size_t)b;
     const int n_raw = a.counts[b];
     const int n = min(n_raw, a.cap);
-    // ---- winner: cv2's rule replayed over the H counts (PnPRansac / RANSACPointSetRegistrator::run):
-    //        niters = H; for it < niters: if good[it] > max(maxGood, m-1): best = it, maxGood = good[it],
-    //                                        niters = RANSACUpdateNumIters(conf, (n - good)/n, m, niters)
-    //      Only "records" (counts above everything before them) can change the state, so: a block-wide exclusive prefix
-    //      maximum flags the records, every record evaluates its own log/pow in parallel, and one thread walks the
-    //      handful of records in order (the serial loop over all H counts with a pow + 2 logs per record cost 20 us).
-    for (int h = tid; h < a.H; h += FIN_THREADS) s_hi[h] = a.hyp_inliers[(size_t)b * a.H + h];
-    __syncthreads();
-    {
-        const double lognum = log(fmax(1.0 - fmin(fmax(a.conf, 0.0), 1.0), ZP_DBL_MIN));
-        int carry = a.m - 1;
-        for (int c0 = 0; c0 < a.H; c0 += FIN_THREADS) {
-            const int h = c0 + tid;
-            const int good = h < a.H ? s_hi[h] : INT_MIN;
-            int v = good;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                int t = __shfl_up_sync(0xffffffffu, v, d);
-                if (lane >= d) v = max(v, t);
-            }
-            if (lane == 31) s_wmax[tid >> 5] = v;
-            int prev = __shfl_up_sync(0xffffffffu, v, 1);
-            if (lane == 0) prev = INT_MIN;
-            __syncthreads();
-            int base = carry;
-            for (int w = 0; w < (tid >> 5); w++) base = max(base, s_wmax[w]);
-            const bool rec = h < a.H && good > max(base, prev);
-            if (rec) {
-                const double ep = fmin(fmax((double)(n - good) / n, 0.0), 1.0);
-                const double den = 1.0 - pow(1.0 - ep, (double)a.m);
-                const double ld = den < ZP_DBL_MIN ? 1.0 : log(den);       // 1.0 (> 0) marks "return 0"
-                s_ld[h] = ld;
-                s_rt[h] = den < ZP_DBL_MIN ? 0 : (ld >= 0 ? INT_MAX : (int)rint(lognum / ld));
-            }
-            const unsigned bal = __ballot_sync(0xffffffffu, rec);
-            if (lane == 0) s_rec[(c0 >> 5) + (tid >> 5)] = bal;
-            for (int w = 0; w < FIN_THREADS / 32; w++) carry = max(carry, s_wmax[w]);
-            __syncthreads();
+    // ---- winner: chosen by zp_rs_replay_kernel (cv2's sequential rule over the counts of the hypotheses that were run)
+    if (tid == 0) {
+        int best = -1, st = ZP_OK;
+        if (n_raw == 0) st = ZP_NO_MASK_PIXELS;
+        else if (n < 6) st = ZP_TOO_FEW_POINTS;       // CNN_output_to_pose.py:126
+        else {
+            best = a.rs[4 * b + 2];
+            if (best < 0) st = ZP_RANSAC_NO_MODEL;
         }
-        if (tid == 0) {
-            int best = -1, st = ZP_OK;
-            if (n_raw == 0) st = ZP_NO_MASK_PIXELS;
-            else if (n < 6) st = ZP_TOO_FEW_POINTS;       // CNN_output_to_pose.py:126
-            else {
-                int niters = max(a.H, 1);
-                const int nwords = (a.H + 31) / 32;
-                for (int w = 0; w < nwords; w++) {
-                    unsigned bits = s_rec[w];
-                    while (bits) {
-                        const int h = 32 * w + __ffs(bits) - 1;
-                        bits &= bits - 1;
-                        if (a.select_mode == ZP_SELECT_CV2_REPLAY) {
-                            if (h >= niters) { w = nwords; break; }
-                            best = h;
-                            const double ld = s_ld[h];
-                            // cv::RANSACUpdateNumIters: den < DBL_MIN -> 0; log(den) >= 0 or -num >= maxIters * -den -> maxIters
-                            if (ld > 0.5) niters = 0;
-                            else if (!(ld >= 0 || -lognum >= niters * (-ld))) niters = s_rt[h];
-                        } else {
-                            best = h;
-                        }
-                    }
-                }
-                if (best < 0) st = ZP_RANSAC_NO_MODEL;
-            }
-            s_best = best; s_status = st;
-            a.status[b] = st;
-            if (a.best_idx) a.best_idx[b] = best;
-            s_first = 0x7fffffff; s_n = 0;
-        }
+        s_best = best; s_status = st;
+        a.status[b] = st;
+        if (a.best_idx) a.best_idx[b] = best;
+        if (a.iters_run) a.iters_run[b] = n < 6 ? 0 : a.rs[4 * b + 3];
+        s_first = 0x7fffffff; s_n = 0;
     }
     for (int i = tid; i < (a.cap + 31) / 32; i += FIN_THREADS) s_mask[i] = 0;
     __syncthreads();
@@ -965,20 +943,27 @@ int zp_launch_samples(zp_ctx* ctx, const int32_t* counts, int cap, int B, int H,
     return 0;
 }
 
+int zp_launch_minimal_cv(zp_ctx*, const float*, int, const int32_t*, const double*, const int32_t*, int, int, int, int,
+                         const int32_t*, int, float, double*, float*, int32_t*, cudaStream_t);
+
+// hypotheses [h0, h0 + hw) of the crops not flagged in crop_done (nullable).  ctx->solver picks the solver: the exact
+// replay of cv2's EPnP (zp_cvsolve.cu, default) or the fast float64 solver of this file.
 int zp_launch_minimal(zp_ctx* ctx, const float* corr, int cap, const int32_t* counts, const double* K,
-                      const int32_t* samples, int B, int H, int m, float thr_px, double* hyp_poses, float* hyp_P,
-                      int32_t* hyp_inliers_to_zero, cudaStream_t st) {
+                      const int32_t* samples, int B, int H, int h0, int hw, const int32_t* crop_done, int m, float thr_px,
+                      double* hyp_poses, float* hyp_P, int32_t* hyp_inliers_to_zero, cudaStream_t st) {
+    if (ctx->solver == ZP_SOLVER_CV2)
+        return zp_launch_minimal_cv(ctx, corr, cap, counts, K, samples, B, H, h0, hw, crop_done, m, thr_px, hyp_poses, hyp_P,
+                                    hyp_inliers_to_zero, st);
     const int per_cta = MIN_THREADS / 4;
-    int total = B * H;
-    static bool attr_set = false;
-    static int force = 0;
-    if (!attr_set) {
+    int total = B * hw;
+    if (!ctx->min_attr_set) {
         ZP_CUDA(ctx, cudaFuncSetAttribute(zp_minimal_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, MIN_SMEM_BYTES));
         ZP_CUDA(ctx, cudaFuncSetAttribute(zp_minimal_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, MIN_SMEM_BYTES));
         const char* e = getenv("ZP_MIN_BLOCKS");
-        force = e ? atoi(e) : 0;
-        attr_set = true;
+        ctx->min_force = e ? atoi(e) : 0;
+        ctx->min_attr_set = true;
     }
+    const int force = ctx->min_force;
     const int grid = (total + per_cta - 1) / per_cta;
     // register budget (measured, profiles/README.md): a saturating grid runs fastest with the 255-register build (two CTAs
     // per SM, 312 instead of 1220 bytes of spill stores on the FP64 dependency chains: 1267 vs 1396 us at 1024 crops);
@@ -987,9 +972,23 @@ int zp_launch_minimal(zp_ctx* ctx, const float* corr, int cap, const int32_t* co
     // room for another lane's kernels on the SM (257 k vs 236 k poses/s with 3 lanes).  ZP_MIN_BLOCKS=2|3 pins it.
     const bool two = force ? force == 2 : grid > 12 * ctx->sm_count;
     ZP_TIME_BEGIN(ctx, st);
-    if (two) zp_minimal_kernel<2><<<grid, MIN_THREADS, MIN_SMEM_BYTES, st>>>(corr, cap, counts, K, samples, B, H, m, 1.0 / (double)thr_px, hyp_poses, hyp_P, hyp_inliers_to_zero);
-    else zp_minimal_kernel<3><<<grid, MIN_THREADS, MIN_SMEM_BYTES, st>>>(corr, cap, counts, K, samples, B, H, m, 1.0 / (double)thr_px, hyp_poses, hyp_P, hyp_inliers_to_zero);
+    if (two) zp_minimal_kernel<2><<<grid, MIN_THREADS, MIN_SMEM_BYTES, st>>>(corr, cap, counts, K, samples, B, H, h0, hw, crop_done, m, 1.0 / (double)thr_px, hyp_poses, hyp_P, hyp_inliers_to_zero);
+    else zp_minimal_kernel<3><<<grid, MIN_THREADS, MIN_SMEM_BYTES, st>>>(corr, cap, counts, K, samples, B, H, h0, hw, crop_done, m, 1.0 / (double)thr_px, hyp_poses, hyp_P, hyp_inliers_to_zero);
     ZP_CHECK_LAUNCH(ctx, "zp_minimal_kernel");
+    return 0;
+}
+
+int zp_launch_rs_init(zp_ctx* ctx, const int32_t* counts, int cap, int B, int H, int32_t* rs, int32_t* crop_done,
+                      int32_t* hyp_inliers_fill, cudaStream_t st) {
+    zp_rs_init_kernel<<<(B + 127) / 128, 128, 0, st>>>(counts, cap, B, H, rs, crop_done, hyp_inliers_fill);
+    ZP_CHECK_LAUNCH(ctx, "zp_rs_init_kernel");
+    return 0;
+}
+
+int zp_launch_rs_replay(zp_ctx* ctx, const int32_t* counts, int cap, const int32_t* hyp_inliers, int B, int H, int h0, int h1,
+                        int m, double conf, int select_mode, int32_t* rs, int32_t* crop_done, cudaStream_t st) {
+    zp_rs_replay_kernel<<<(B + 63) / 64, 64, 0, st>>>(counts, cap, hyp_inliers, B, H, h0, h1, m, conf, select_mode, rs, crop_done);
+    ZP_CHECK_LAUNCH(ctx, "zp_rs_replay_kernel");
     return 0;
 }
 
@@ -1002,22 +1001,22 @@ int zp_launch_poses_to_P(zp_ctx* ctx, const double* poses, const double* K, int 
 
 template <int NG>
 static int launch_score_ng(zp_ctx* ctx, ScoreArgs& a, int smem, cudaStream_t st) {
-    static bool attr_set = false;
-    static int per_sm = 0;
-    if (!attr_set) {
+    constexpr int slot = NG == 1 ? 0 : NG == 2 ? 1 : 2;      // per context (= per device), not per process
+    if (!ctx->score_per_sm[slot]) {
+        int per_sm = 0;
         ZP_CUDA(ctx, cudaFuncSetAttribute(zp_score_kernel<NG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         ZP_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, zp_score_kernel<NG>, SC_GROUP * NG, smem));
-        if (per_sm < 1) per_sm = 1;
-        attr_set = true;
+        ctx->score_per_sm[slot] = per_sm < 1 ? 1 : per_sm;
     }
+    const int per_sm = ctx->score_per_sm[slot];
     int grid = ctx->sm_count * per_sm;
     // about one tile per CTA slot (64 crops: 832 tiles on 740 slots): cut the tiles into two items of H/2 hypotheses so
     // that the last round is short (measured -6 %; finer cuts or bigger batches lose more to the extra tile loads)
-    a.hchunk = a.H; a.n_hc = 1;
+    a.hchunk = a.hw; a.n_hc = 1;
     const int hc_req = ctx->score_hchunk;
-    if (hc_req > 0 || (hc_req == 0 && a.n_items <= 2 * grid && a.H >= 64)) {
-        a.hchunk = hc_req > 0 ? hc_req : (a.H + 1) / 2;
-        a.n_hc = (a.H + a.hchunk - 1) / a.hchunk;
+    if (hc_req > 0 || (hc_req == 0 && a.n_items <= 2 * grid && a.hw >= 64)) {
+        a.hchunk = hc_req > 0 ? hc_req : (a.hw + 1) / 2;
+        a.n_hc = (a.hw + a.hchunk - 1) / a.hchunk;
     }
     if (grid > 2 * a.n_items * a.n_hc) grid = 2 * a.n_items * a.n_hc;
     ZP_TIME_BEGIN(ctx, st);
@@ -1027,10 +1026,11 @@ static int launch_score_ng(zp_ctx* ctx, ScoreArgs& a, int smem, cudaStream_t st)
 }
 
 int zp_launch_score(zp_ctx* ctx, const float* corr, int cap, const int32_t* counts, const float* hyp_P, int B, int H,
-                    float thr_px, int32_t* hyp_inliers, bool already_zeroed, cudaStream_t st) {
+                    int h0, int hw, const int32_t* crop_done, float thr_px, int32_t* hyp_inliers, bool already_zeroed,
+                    cudaStream_t st) {
     ScoreArgs a;
     a.corr = corr; a.cap = cap; a.counts = counts; a.hyp_P = hyp_P; a.B = B; a.H = H; a.inv_thr = 1.0f / thr_px;
-    a.hyp_inliers = hyp_inliers; a.counters = ctx->d_counters;
+    a.hyp_inliers = hyp_inliers; a.counters = ctx->d_counters; a.h0 = h0; a.hw = hw; a.crop_done = crop_done;
     const int max_tiles = (cap + SC_TILE - 1) / SC_TILE;
     a.n_items = B * max_tiles;
     const int smem = 5 * SC_TILE * sizeof(float) + SC_HB * (6 * sizeof(ulonglong2) + sizeof(int));
@@ -1044,19 +1044,19 @@ int zp_launch_score(zp_ctx* ctx, const float* corr, int cap, const int32_t* coun
 int zp_launch_final(zp_ctx* ctx, const float* corr, int cap, const int32_t* counts, const double* K,
                     const double* hyp_poses, const int32_t* hyp_inliers, int B, int H, int m, double conf, int select_mode,
                     float thr_px, int final_mode, double* poses, int32_t* n_inliers, int32_t* status, int32_t* best_idx,
-                    uint8_t* inlier_mask, cudaStream_t st) {
+                    uint8_t* inlier_mask, const int32_t* rs, int32_t* iters_run, cudaStream_t st) {
     FinalArgs a;
+    a.rs = rs; a.iters_run = iters_run;
     a.corr = corr; a.cap = cap; a.counts = counts; a.K = K; a.hyp_poses = hyp_poses; a.hyp_inliers = hyp_inliers;
     a.B = B; a.H = H; a.m = m; a.conf = conf; a.select_mode = select_mode; a.inv_thr = 1.0f / thr_px;
     a.final_mode = final_mode; a.poses = poses; a.n_inliers = n_inliers; a.status = status; a.best_idx = best_idx;
     a.inlier_mask = inlier_mask;
-    size_t smem = (size_t)H * sizeof(double) + ((size_t)(cap + 31) / 32 + 2 * (size_t)H + (H + 31) / 32 + FIN_THREADS_MAX / 32) * sizeof(uint32_t) +
-                  ((size_t)cap + FIN_THREADS_MAX + 32) * sizeof(uint16_t);      // + the packed inlier indices
-    static bool attr_set = false;
-    if (!attr_set) {
+    size_t smem = ((size_t)(cap + 31) / 32 + 2) * sizeof(uint32_t) +
+                  ((size_t)cap + FIN_THREADS_MAX + 32) * sizeof(uint16_t);      // bitset + the packed inlier indices
+    if (!ctx->fin_attr_set) {
         ZP_CUDA(ctx, cudaFuncSetAttribute(zp_final_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         ZP_CUDA(ctx, cudaFuncSetAttribute(zp_final_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-        attr_set = true;
+        ctx->fin_attr_set = true;
     }
     if (smem > 200 * 1024) ZP_FAIL(ctx, -1, "zp_ransac: cap %d needs %zu bytes of shared memory in the final solve", cap, smem);
     // threads per crop (measured, profiles/README.md): the solver phases keep one warp busy, so two 128-thread CTAs per SM

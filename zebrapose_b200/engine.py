@@ -37,8 +37,8 @@ def _ptr(t):
     return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p()
 
 
-def _stream():
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+def _stream(device=None):
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
 class Engine:
@@ -80,6 +80,16 @@ class Engine:
         4 two kernels | 6 single-run fused, independent CTAs | 100+r: r runs per CTA -- identical results"""
         self.ctx.check(self.lib.zp_set_decode_path(self.ctx.handle, int(path)), "zp_set_decode_path")
 
+    def set_solver(self, solver="cv2"):
+        """minimal solver of the RANSAC hypotheses: "cv2" = exact replay of OpenCV's EPnP arithmetic (default; hypotheses
+        bit-identical to cv2.solvePnP), "fast" = the float64 bisection solver (other null-space basis for 4/5 points)"""
+        self.ctx.check(self.lib.zp_set_solver(self.ctx.handle, _lib.SOLVER[solver]), "zp_set_solver")
+
+    def set_waves(self, sizes=None):
+        """hypotheses per RANSAC wave (None / empty = automatic); results do not depend on the plan"""
+        arr = np.ascontiguousarray(np.asarray(sizes if sizes else [], np.int32))
+        self.ctx.check(self.lib.zp_set_waves(self.ctx.handle, int(arr.size), arr.ctypes.data_as(C.c_void_p)), "zp_set_waves")
+
     def set_score_groups(self, groups=0, hyp_chunk=0):
         """scheduling knobs of the scoring kernel (include/zebrapose_b200.h); results do not depend on them"""
         self.ctx.check(self.lib.zp_set_score_groups(self.ctx.handle, int(groups), int(hyp_chunk)), "zp_set_score_groups")
@@ -116,7 +126,7 @@ class Engine:
         strides = (C.c_int64 * 4)(*logits.stride())
         rc = self.lib.zp_decode(self.ctx.handle, _ptr(logits), _DT[logits.dtype], B, S, strides, int(mask_ch),
                                 int(bit0_ch), int(n_bits), int(ignore_bit), _ptr(em), _ptr(bb), _ptr(oid),
-                                int(obj_default), _ptr(codes), _ptr(corr), cap, _ptr(counts), _stream())
+                                int(obj_default), _ptr(codes), _ptr(corr), cap, _ptr(counts), _stream(self.device))
         self.ctx.check(rc, "zp_decode")
         return (corr, counts, codes) if return_codes else (corr, counts)
 
@@ -143,7 +153,7 @@ class Engine:
         strides = (C.c_int64 * 4)(*logits.stride())
         rc = self.lib.zp_decode_ce(self.ctx.handle, _ptr(logits), _DT[logits.dtype], B, S, strides, int(mask_ch),
                                    int(digit0_ch), int(base), int(n_digits), _ptr(em), _ptr(bb), _ptr(oid), int(obj_default),
-                                   _ptr(codes), _ptr(corr), cap, _ptr(counts), _stream())
+                                   _ptr(codes), _ptr(corr), cap, _ptr(counts), _stream(self.device))
         self.ctx.check(rc, "zp_decode_ce")
         return (corr, counts, codes) if return_codes else (corr, counts)
 
@@ -167,7 +177,7 @@ class Engine:
         B = counts.shape[0]
         s = torch.empty((B, H, m), dtype=torch.int32, device=self.device)
         rc = self.lib.zp_make_samples(self.ctx.handle, _ptr(counts), int(cap), B, H, m, _lib.SAMPLER[sampler],
-                                      int(seed), _ptr(s), _stream())
+                                      int(seed), _ptr(s), _stream(self.device))
         self.ctx.check(rc, "zp_make_samples")
         return s
 
@@ -183,7 +193,7 @@ class Engine:
         K = self._Ks(Ks, B)
         hp = torch.empty((B, H, 12), dtype=torch.float64, device=self.device)
         rc = self.lib.zp_solve_minimal(self.ctx.handle, _ptr(corr), cap, _ptr(counts), _ptr(K), _ptr(samples), B, H, m,
-                                       _ptr(hp), _stream())
+                                       _ptr(hp), _stream(self.device))
         self.ctx.check(rc, "zp_solve_minimal")
         return hp
 
@@ -194,7 +204,7 @@ class Engine:
         hp = torch.as_tensor(hyp_poses).to(device=self.device, dtype=torch.float64).contiguous()
         out = torch.empty((B, H), dtype=torch.int32, device=self.device)
         rc = self.lib.zp_score(self.ctx.handle, _ptr(corr), cap, _ptr(counts), _ptr(K), _ptr(hp), B, H, float(thr),
-                               _ptr(out), _stream())
+                               _ptr(out), _stream(self.device))
         self.ctx.check(rc, "zp_score")
         return out
 
@@ -209,16 +219,18 @@ class Engine:
         out = dict(poses=torch.empty((B, 12), dtype=torch.float64, device=self.device),
                    n_inliers=torch.empty((B,), dtype=torch.int32, device=self.device),
                    status=torch.empty((B,), dtype=torch.int32, device=self.device))
-        hp = hi = bi = im = None
-        if return_details:
-            hp = out["hyp_poses"] = torch.empty((B, H, 12), dtype=torch.float64, device=self.device)
-            hi = out["hyp_inliers"] = torch.empty((B, H), dtype=torch.int32, device=self.device)
+        hp = hi = bi = im = ir = None
+        if return_details:           # "hyps": also the hypothesis lists, which forces one wave of all H hypotheses
             bi = out["best_idx"] = torch.empty((B,), dtype=torch.int32, device=self.device)
+            ir = out["iters_run"] = torch.empty((B,), dtype=torch.int32, device=self.device)
             im = out["inlier_mask"] = torch.empty((B, cap), dtype=torch.uint8, device=self.device)
+            if return_details != "state":
+                hp = out["hyp_poses"] = torch.empty((B, H, 12), dtype=torch.float64, device=self.device)
+                hi = out["hyp_inliers"] = torch.empty((B, H), dtype=torch.int32, device=self.device)
         rc = self.lib.zp_ransac(self.ctx.handle, _ptr(corr), cap, _ptr(counts), _ptr(K), _ptr(samples), B, int(H),
                                 int(m), float(thr), float(conf), _lib.SAMPLER[sampler], int(seed),
-                                _lib.SELECT[select], _lib.FINAL[final], _ptr(hp), _ptr(hi), _ptr(bi), _ptr(im),
-                                _ptr(out["poses"]), _ptr(out["n_inliers"]), _ptr(out["status"]), _stream())
+                                _lib.SELECT[select], _lib.FINAL[final], _ptr(hp), _ptr(hi), _ptr(bi), _ptr(ir), _ptr(im),
+                                _ptr(out["poses"]), _ptr(out["n_inliers"]), _ptr(out["status"]), _stream(self.device))
         self.ctx.check(rc, "zp_ransac")
         return out
 
@@ -274,7 +286,7 @@ class Engine:
         out = torch.empty_like(px)
         bb = np.ascontiguousarray(np.asarray(bbox, np.float64).reshape(4))
         rc = self.lib.zp_remap_pixels(self.ctx.handle, _ptr(px), px.shape[0], bb.ctypes.data_as(C.c_void_p), int(S),
-                                      _ptr(out), _stream())
+                                      _ptr(out), _stream(self.device))
         self.ctx.check(rc, "zp_remap_pixels")
         return out
 
@@ -282,7 +294,7 @@ class Engine:
         b = torch.as_tensor(np.ascontiguousarray(bits, dtype=np.float64)).to(self.device)
         N, L = b.shape
         out = torch.empty((N,), dtype=torch.float64, device=self.device)
-        rc = self.lib.zp_codes_to_ids(self.ctx.handle, _ptr(b), N, L, int(base), _ptr(out), _stream())
+        rc = self.lib.zp_codes_to_ids(self.ctx.handle, _ptr(b), N, L, int(base), _ptr(out), _stream(self.device))
         self.ctx.check(rc, "zp_codes_to_ids")
         return out
 
@@ -334,7 +346,7 @@ class Engine:
         codes = torch.empty((B, S, S), dtype=torch.uint16, device=self.device) if return_codes else None
         rc = self.lib.zp_head_decode(self.ctx.handle, _ptr(x), int(c1), _ptr(x_skip), int(c2), _DT[x.dtype], B, S, int(mask_ch),
                                      int(bit0_ch), int(n_bits), int(ignore_bit), _ptr(bb), _ptr(oid), int(obj_default),
-                                     _ptr(codes), _ptr(corr), cap, _ptr(counts), _stream())
+                                     _ptr(codes), _ptr(corr), cap, _ptr(counts), _stream(self.device))
         self.ctx.check(rc, "zp_head_decode")
         return (corr, counts, codes) if return_codes else (corr, counts)
 
@@ -356,7 +368,7 @@ class Engine:
         bb = torch.as_tensor(det_boxes).to(device=self.device, dtype=torch.float64).contiguous().reshape(-1, 4)
         out = torch.empty_like(bb)
         rc = self.lib.zp_final_bbox(self.ctx.handle, _ptr(bb), bb.shape[0], float(padding_ratio),
-                                    _lib.RESIZE[resize_method], float(max_x), float(max_y), _ptr(out), _stream())
+                                    _lib.RESIZE[resize_method], float(max_x), float(max_y), _ptr(out), _stream(self.device))
         self.ctx.check(rc, "zp_final_bbox")
         return out
 
@@ -380,7 +392,7 @@ class Engine:
         u8 = torch.empty((B, cs, cs, 3), dtype=torch.uint8, device=self.device) if return_u8 else None
         rc = self.lib.zp_crop_input(self.ctx.handle, _ptr(im), im.shape[0], im.shape[1], im.shape[2], _ptr(ids), _ptr(bb), B,
                                     cs, _lib.RESIZE[resize_method], C.c_void_p(), C.c_void_p(), _DT[dtype],
-                                    1 if channels_last else 0, _ptr(out), _ptr(u8), _stream())
+                                    1 if channels_last else 0, _ptr(out), _ptr(u8), _stream(self.device))
         self.ctx.check(rc, "zp_crop_input")
         return (out, u8) if return_u8 else out
 
@@ -404,7 +416,7 @@ class Engine:
         o_add = torch.empty((B,), dtype=torch.float64, device=self.device) if add else None
         o_adi = torch.empty((B,), dtype=torch.float64, device=self.device) if adi else None
         rc = self.lib.zp_pose_errors(self.ctx.handle, _ptr(pe), _ptr(pg), _ptr(oid), int(obj_default), B,
-                                     _ptr(o_add), _ptr(o_adi), _stream())
+                                     _ptr(o_add), _ptr(o_adi), _stream(self.device))
         self.ctx.check(rc, "zp_pose_errors")
         return o_add, o_adi
 
