@@ -145,6 +145,9 @@ def test_product_solver_degenerate_inputs(host):
     for pw, uv in cases:
         pw32 = pw.astype(np.float32)
         corr = np.ascontiguousarray(np.concatenate([uv.T, pw32.T]).astype(np.float32))
-        R, t = cv_epnp.epnp(pw32, uv, K)
+        uv32 = uv.astype(np.float32)
+        R, t = cv_epnp.epnp(pw32, uv32, K)
         pose, _ = _host_epnp(host, corr, np.arange(6), K)
         assert np.array_equal(np.concatenate([R.ravel(), t]), pose, equal_nan=True)
+        ok, rv, tv = cv2.solvePnP(pw32, uv32, K, None, flags=cv2.SOLVEPNP_EPNP)
+        assert np.array_equal(tv.ravel(), t, equal_nan=True)
