@@ -21,7 +21,7 @@ def golden():
 @pytest.fixture(scope="session")
 def tables():
     """The two 16-bit dictionaries the golden crops were generated with (re-generated from seeds)."""
-    from oracle import synth
+    from workloads import synth
     tab16, nrm16, _ = synth.make_dict(16, seed=3, radius=51.0, missing_frac=0.0)
     tab16n, nrm16n, _ = synth.make_dict(16, seed=11, radius=51.0, missing_frac=0.2)
     return dict(full=(tab16, nrm16), nan20=(tab16n, nrm16n))

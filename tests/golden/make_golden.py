@@ -27,7 +27,7 @@ from binary_code_helper.class_id_encoder_decoder import class_code_images_to_cla
 from binary_code_helper.generate_new_dict import generate_new_corres_dict
 import common_ops
 
-from oracle import synth
+from workloads import synth
 
 
 def sha(*arrs):

@@ -23,7 +23,7 @@ sys.path.insert(0, REF)
 import numpy as np
 from scipy import spatial
 
-from oracle import synth_eval
+from workloads import synth_eval
 
 
 def ref_functions(path, names, ns):

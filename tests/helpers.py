@@ -3,7 +3,7 @@ import hashlib
 
 import numpy as np
 
-from oracle import synth
+from workloads import synth
 
 GOLDEN_CROPS = {  # tag -> (table key, seed, S, ignore_bit)
     "c1_full": ("full", 1001 * 65536 + 0, 128, 0),

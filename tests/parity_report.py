@@ -16,7 +16,8 @@ sys.path.insert(0, ROOT)
 import cv2
 import torch
 import zebrapose_b200 as zp
-from oracle import cvransac, decode, metrics, synth
+from oracle import cvransac, decode, metrics
+from workloads import synth
 
 
 def main():

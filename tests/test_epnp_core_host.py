@@ -6,7 +6,8 @@ import subprocess
 import numpy as np
 import pytest
 
-from oracle import cvransac, metrics, synth
+from oracle import cvransac, metrics
+from workloads import synth
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 

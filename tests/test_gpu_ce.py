@@ -8,7 +8,7 @@ import pytest
 import torch
 
 from oracle import decode as odec
-from oracle import synth
+from workloads import synth
 
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

@@ -5,7 +5,8 @@ import numpy as np
 import pytest
 import torch
 
-from oracle import decode, metrics, synth
+from oracle import decode, metrics
+from workloads import synth
 
 pytestmark = pytest.mark.gpu
 

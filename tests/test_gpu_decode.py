@@ -3,7 +3,8 @@ import numpy as np
 import pytest
 import torch
 
-from oracle import decode, synth
+from oracle import decode
+from workloads import synth
 from helpers import GOLDEN_CROPS, regen_crop, as_set
 
 pytestmark = pytest.mark.gpu

@@ -10,7 +10,8 @@ import numpy as np
 import pytest
 import torch
 
-from oracle import evalside, metrics, synth_eval
+from oracle import evalside, metrics
+from workloads import synth_eval
 
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

@@ -10,7 +10,7 @@ import pytest
 import torch
 
 from oracle import decode as odec
-from oracle import synth
+from workloads import synth
 
 pytestmark = pytest.mark.gpu
 LOGIT_TOL = 2e-3

@@ -1,14 +1,15 @@
 """GPU: RANSAC-PnP pieces and the whole chain (through the C ABI) vs the oracle / cv2.
 
 Tolerances (north_star): inlier counts given identical hypothesis poses exact except points within 1e-3 px of the
-threshold; final poses within 0.05 deg / 0.5 mm of cv2.solvePnPRansac; the fraction of crops meeting it is asserted
-(the reference's own sampling noise makes 100 %% unreachable)."""
+threshold; final poses within 0.05 deg / 0.5 mm of cv2.solvePnPRansac.  The minimal solver replays cv2's EPnP arithmetic exactly, so
+hypotheses are bit-identical and the winner is cv2's winner."""
 import cv2
 import numpy as np
 import pytest
 import torch
 
-from oracle import cvransac, decode, epnp, metrics, synth
+from oracle import cv_epnp, cvransac, decode, metrics
+from workloads import synth
 
 pytestmark = pytest.mark.gpu
 ROT_TOL_DEG, TRANS_TOL_MM = 0.05, 0.5
@@ -73,64 +74,82 @@ def test_score_exact_given_oracle_poses(eng, batch):
     assert got.max() > 1000
 
 
-def test_minimal_solver_vs_oracle_m6(eng, batch):
-    """6-point sets are well conditioned: device EPnP == oracle EPnP == cv2 on every hypothesis that the
-    oracle itself reproduces under a 1-ulp perturbation"""
+def _oracle_hyps(uv, xyz, K, S):
+    """(poses [H,12], counts [H], slack [H]) of the sample lists S as cv2 computes them: exact EPnP replay + cv2's
+    projectPoints scoring; slack = points within 1e-3 px of the 2 px threshold"""
+    H = len(S)
+    poses = np.full((H, 12), np.nan)
+    cnt = np.zeros(H, np.int64)
+    slack = np.zeros(H, np.int64)
+    for h in range(H):
+        R, t = cv_epnp.epnp(xyz[S[h]], uv[S[h]], K)
+        poses[h, :9] = R.ravel()
+        poses[h, 9:] = t
+        if np.all(np.isfinite(poses[h])):
+            mask, err = cvransac.score_pose(xyz, uv, K, R, t, 2.0)
+            cnt[h] = mask.sum()
+            slack[h] = (np.abs(np.sqrt(err.astype(np.float64)) - 2.0) < 1e-3).sum()
+    return poses, cnt, slack
+
+
+@pytest.mark.parametrize("m", [4, 5, 6, 7, 8])
+def test_minimal_solver_bit_identical_to_cv2_replay(eng, batch, m):
+    """every hypothesis of every crop, 4- to 8-point samples drawn as cv2 draws them: the device poses equal the
+    operation-by-operation replay of cv2.solvePnP(EPNP) (oracle/cv_epnp.c, pinned against cv2 in the CPU suite) BIT FOR
+    BIT -- including the 4/5-point samples whose null-space basis is decided by rounding"""
     corr, counts, Ks = batch["corr"], batch["counts"], batch["Ks"]
-    H = 64
-    s = eng.make_samples(counts, corr.shape[2], H=H, m=6, sampler="philox", seed=3)
+    H = 150
+    s = eng.make_samples(counts, corr.shape[2], H=H, m=m)
     hp = eng.solve_minimal(corr, counts, Ks, s).cpu().numpy()
     s = s.cpu().numpy()
-    checked = bad = 0
-    for i, (uv, xyz) in enumerate(batch["lists"][:4]):
+    n = 0
+    for i, (uv, xyz) in enumerate(batch["lists"]):
+        assert np.array_equal(s[i], cvransac.sample_lists(len(uv), H, m))
         for h in range(H):
-            idx = s[i, h]
-            Rc, tc = cvransac.cv2_solver(xyz[idx], uv[idx], Ks[i])
-            xyz_p = xyz[idx] * (1 + np.float32(6e-8))
-            Rp, tp = cvransac.cv2_solver(xyz_p, uv[idx], Ks[i])
-            if metrics.rot_err_deg(Rc, Rp) > 1e-3 or metrics.trans_err(tc, tp) > 1e-2:
-                continue                                   # cv2 itself is unstable on this sample
-            checked += 1
-            R, t = hp[i, h, :9].reshape(3, 3), hp[i, h, 9:]
-            if not (metrics.rot_err_deg(Rc, R) < 2e-3 and metrics.trans_err(tc, t) < 2e-2):
-                bad += 1
-    assert checked > 100
-    assert bad <= 0.02 * checked, (bad, checked)
+            R, t = cv_epnp.epnp(xyz[s[i, h]], uv[s[i, h]], Ks[i])
+            assert np.array_equal(np.concatenate([R.ravel(), t]), hp[i, h], equal_nan=True), (m, i, h)
+            n += 1
+    assert n == 8 * H
+    if m == 5:      # and against cv2 itself on a sample of them
+        for i in (0, 3):
+            uv, xyz = batch["lists"][i]
+            for h in range(0, H, 7):
+                ok, rv, tv = cv2.solvePnP(xyz[s[i, h]], uv[s[i, h]], Ks[i], None, flags=cv2.SOLVEPNP_EPNP)
+                assert np.array_equal(cv2.Rodrigues(hp[i, h, :9].reshape(3, 3))[0], rv) and np.array_equal(hp[i, h, 9:], tv.ravel())
 
 
-def test_minimal_solver_m5_stable_subset(eng, batch):
-    """cv2's own 5-point lists.  M^T M has a 2-D null space for 5 points, so cv2's answer is set by rounding noise on
-    most (outlier-bearing) samples; parity is asserted on the subset cv2 itself reproduces under a 1-ulp perturbation
-    of the 3D points, and the size of that subset is reported."""
+@pytest.mark.parametrize("m", [5, 6])
+def test_counts_exact_given_identical_sample_lists(eng, batch, m):
+    """north_star's contract: "given the identical exported minimal-sample index lists, inlier counts must match exactly
+    except for points within 1e-3 px of the threshold" -- device-SOLVED hypotheses, device scoring, against
+    cv2.solvePnP's arithmetic + cv2.projectPoints scoring"""
     corr, counts, Ks = batch["corr"], batch["counts"], batch["Ks"]
-    s = eng.make_samples(counts, corr.shape[2], H=150, m=5)
-    hp = eng.solve_minimal(corr, counts, Ks, s).cpu().numpy()
+    H = 150
+    s = eng.make_samples(counts, corr.shape[2], H=H, m=m)
+    res = eng.ransac(corr, counts, Ks, samples=s, return_details=True)
+    got = res["hyp_inliers"].cpu().numpy()
     s = s.cpu().numpy()
-    checked = good = unstable = 0
-    for i, (uv, xyz) in enumerate(batch["lists"][:4]):
-        for h in range(150):
-            idx = s[i, h]
-            Rc, tc = cvransac.cv2_solver(xyz[idx], uv[idx], Ks[i])
-            Rp, tp = cvransac.cv2_solver(xyz[idx] * (1 + np.float32(6e-8)), uv[idx], Ks[i])
-            if metrics.rot_err_deg(Rc, Rp) > 1e-2 or metrics.trans_err(tc, tp) > 0.1:
-                unstable += 1
-                continue
-            checked += 1
-            R, t = hp[i, h, :9].reshape(3, 3), hp[i, h, 9:]
-            good += metrics.rot_err_deg(Rc, R) < 5e-2 and metrics.trans_err(tc, t) < 0.5
-    print("m=5: stable %d, unstable %d, device agrees on %d" % (checked, unstable, good))
-    assert checked >= 10 and good >= 0.7 * checked
+    exact = total = 0
+    for i, (uv, xyz) in enumerate(batch["lists"]):
+        _, cnt, slack = _oracle_hyps(uv, xyz, Ks[i], s[i])
+        diff = np.abs(got[i] - cnt)
+        assert (diff <= slack).all(), (m, i, np.argwhere(diff > slack)[:5], diff.max())
+        exact += int((diff == 0).sum())
+        total += H
+    assert exact >= 0.99 * total, (exact, total)
 
 
 def test_full_chain_vs_cv2(eng, batch):
+    """same winning hypothesis, same iteration count, same inlier count as cv2.solvePnPRansac on every crop; final pose
+    within the north_star tolerance on every crop"""
     res = eng.ransac(batch["corr"], batch["counts"], batch["Ks"], return_details=True)
     poses = res["poses"].cpu().numpy()
     ninl = res["n_inliers"].cpu().numpy()
     status = res["status"].cpu().numpy()
     best = res["best_idx"].cpu().numpy()
+    iters = res["iters_run"].cpu().numpy()
     hyp_inl = res["hyp_inliers"].cpu().numpy()
     im = res["inlier_mask"].cpu().numpy()
-    within = same_winner = 0
     for i, (uv, xyz) in enumerate(batch["lists"]):
         K = batch["Ks"][i]
         ok, rv, tv, inl = cv2.solvePnPRansac(xyz, uv, K, None, reprojectionError=2, iterationsCount=150, flags=cv2.SOLVEPNP_EPNP)
@@ -138,19 +157,97 @@ def test_full_chain_vs_cv2(eng, batch):
         R, t = poses[i, :9].reshape(3, 3), poses[i, 9:]
         re, te = metrics.rot_err_deg(Rc, R), metrics.trans_err(tv, t)
         ok2, R2, t2, inl2, info = cvransac.solve_pnp_ransac(xyz, uv, K)
-        same_winner += int(best[i] == info["best"])
-        within += int(re <= ROT_TOL_DEG and te <= TRANS_TOL_MM)
+        print("crop %d: rot %.5f deg  trans %.5f mm  winner %d/%d  iterations %d/%d  inliers %d/%d"
+              % (i, re, te, best[i], info["best"], iters[i], info["iters_run"], ninl[i], len(inl)))
         assert status[i] == 0
         assert ninl[i] == im[i].sum() == hyp_inl[i, best[i]]
-        # replaying cv2's rule on the device counts must give the device winner
-        b2, _ = cvransac.replay_select(hyp_inl[i], len(uv))
-        assert b2 == best[i]
-        # and the pose is a sane one in any case
-        assert metrics.rot_err_deg(R, batch["crops"][i]["R"]) < 1.0
+        b2, it2 = cvransac.replay_select(hyp_inl[i], len(uv))      # cv2's rule replayed on the device counts
+        assert b2 == best[i] and it2 == iters[i]
+        assert best[i] == info["best"] and iters[i] == info["iters_run"]
+        assert abs(int(ninl[i]) - len(inl)) <= 2
+        assert re <= ROT_TOL_DEG and te <= TRANS_TOL_MM
         assert abs(np.linalg.det(R) - 1) < 1e-9
-        print("crop %d: rot %.4f deg  trans %.4f mm  winner %d/%d  inliers %d/%d" % (i, re, te, best[i], info["best"], ninl[i], len(inl)))
-    n = len(batch["lists"])
-    assert within >= 0.75 * n, (within, n)
+
+
+def test_waves_do_not_change_the_result(eng, batch):
+    """cv2 never consults a hypothesis at or past its stopping iteration, so solving + scoring the hypotheses in waves and
+    skipping finished crops must give bit-identical poses, winners and iteration counts for any wave plan"""
+    ref = None
+    try:
+        for plan in ([150], [32], [64, 86], [1, 2, 3, 50], [7], None):
+            eng.set_waves(plan)
+            r = eng.ransac(batch["corr"], batch["counts"], batch["Ks"], return_details="state")
+            cur = [r[k].cpu().numpy() for k in ("poses", "n_inliers", "status", "best_idx", "iters_run", "inlier_mask")]
+            if ref is None:
+                ref = cur
+                assert (cur[4] < 150).any()          # the adaptive stop does cut work on these crops
+            else:
+                assert all(np.array_equal(a, b) for a, b in zip(ref, cur)), plan
+    finally:
+        eng.set_waves(None)
+
+
+@pytest.mark.parametrize("m", [4, 6, 8])
+def test_other_sample_sizes_against_the_emulation(eng, batch, m):
+    """north_star names 4-point minimal sets; cv2 itself always draws 5 for EPnP, so the oracle for m != 5 is the verified
+    control-flow emulation run with the exact solver.  Winner, iteration count and (within the scoring slack) the inlier
+    count must agree; the run is deterministic."""
+    r1 = eng.ransac(batch["corr"], batch["counts"], batch["Ks"], m=m, return_details="state")
+    r2 = eng.ransac(batch["corr"], batch["counts"], batch["Ks"], m=m, return_details="state")
+    for k in ("poses", "n_inliers", "status", "best_idx", "iters_run"):
+        assert torch.equal(r1[k], r2[k])
+    poses, best, iters, ninl = (r1[k].cpu().numpy() for k in ("poses", "best_idx", "iters_run", "n_inliers"))
+    assert (r1["status"].cpu().numpy() == 0).all()
+    same = 0
+    for i, (uv, xyz) in enumerate(batch["lists"]):
+        ok, R2, t2, inl2, info = cvransac.solve_pnp_ransac(xyz, uv, batch["Ks"][i], m=m, solver=cv_epnp.solver)
+        R, t = poses[i, :9].reshape(3, 3), poses[i, 9:]
+        print("m=%d crop %d: winner %d/%d iterations %d/%d inliers %d/%d rot %.5f" % (
+            m, i, best[i], info["best"], iters[i], info["iters_run"], ninl[i], len(inl2), metrics.rot_err_deg(R2, R)))
+        if best[i] == info["best"]:
+            same += 1
+            assert iters[i] == info["iters_run"] and abs(int(ninl[i]) - len(inl2)) <= 2
+            assert metrics.rot_err_deg(R2, R) <= ROT_TOL_DEG and metrics.trans_err(t2, t) <= TRANS_TOL_MM
+        assert metrics.rot_err_deg(R, batch["crops"][i]["R"]) < 1.0
+    # 4-point EPnP hypotheses are chaotic (SURVEY H1): counts within the 1e-3 px slack can still flip a near-tie
+    assert same >= (6 if m == 4 else 7), same
+
+
+def test_fast_solver_stable_subset(eng, batch):
+    """the non-replay solver (solver="fast"): accurate, but for 5-point samples it returns another null-space basis than
+    cv2, so agreement is asserted only on the samples cv2 itself reproduces under a 1-ulp perturbation"""
+    corr, counts, Ks = batch["corr"], batch["counts"], batch["Ks"]
+    eng.set_solver("fast")
+    try:
+        s = eng.make_samples(counts, corr.shape[2], H=150, m=5)
+        hp = eng.solve_minimal(corr, counts, Ks, s).cpu().numpy()
+        s6 = eng.make_samples(counts, corr.shape[2], H=64, m=6, sampler="philox", seed=3)
+        hp6 = eng.solve_minimal(corr, counts, Ks, s6).cpu().numpy()
+        r = eng.ransac(corr, counts, Ks)
+    finally:
+        eng.set_solver("cv2")
+    s, s6 = s.cpu().numpy(), s6.cpu().numpy()
+    checked = good = 0
+    for i, (uv, xyz) in enumerate(batch["lists"][:4]):
+        for h in range(150):
+            idx = s[i, h]
+            Rc, tc = cvransac.cv2_solver(xyz[idx], uv[idx], Ks[i])
+            Rp, tp = cvransac.cv2_solver(xyz[idx] * (1 + np.float32(6e-8)), uv[idx], Ks[i])
+            if metrics.rot_err_deg(Rc, Rp) > 1e-2 or metrics.trans_err(tc, tp) > 0.1:
+                continue
+            checked += 1
+            good += metrics.rot_err_deg(Rc, hp[i, h, :9].reshape(3, 3)) < 5e-2 and metrics.trans_err(tc, hp[i, h, 9:]) < 0.5
+    assert checked >= 10 and good >= 0.7 * checked, (checked, good)
+    bad = n6 = 0
+    for i, (uv, xyz) in enumerate(batch["lists"][:4]):
+        for h in range(64):
+            Rc, tc = cv_epnp.epnp(xyz[s6[i, h]], uv[s6[i, h]], Ks[i])
+            n6 += 1
+            bad += not (metrics.rot_err_deg(Rc, hp6[i, h, :9].reshape(3, 3)) < 2e-3 and metrics.trans_err(tc, hp6[i, h, 9:]) < 2e-2)
+    assert bad <= 0.03 * n6, (bad, n6)
+    p = r["poses"].cpu().numpy()
+    for i, c in enumerate(batch["crops"]):
+        assert metrics.rot_err_deg(p[i, :9].reshape(3, 3), c["R"]) < 1.0
 
 
 def test_final_epnp_on_given_inliers(eng, batch):
@@ -238,7 +335,7 @@ def test_add_metric_agreement(eng, tables):
         within += metrics.rot_err_deg(Rc, R) <= ROT_TOL_DEG and metrics.trans_err(tv, t) <= TRANS_TOL_MM
     print("ADD@0.1d pass: device %d/%d reference %d/%d; pose tolerance pass rate %d/%d" % (pass_dev, B, pass_ref, B, within, B))
     assert abs(pass_dev - pass_ref) / B <= 0.005 + 1e-9
-    assert within >= 0.8 * B
+    assert within >= B - 1
 
 
 def test_score_groups_identical(eng, batch):

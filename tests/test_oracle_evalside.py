@@ -6,7 +6,8 @@ import os
 import numpy as np
 import pytest
 
-from oracle import evalside, metrics, synth_eval
+from oracle import evalside, metrics
+from workloads import synth_eval
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 

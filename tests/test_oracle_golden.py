@@ -4,7 +4,8 @@ import os
 import numpy as np
 import pytest
 
-from oracle import decode, synth, cvransac, metrics
+from oracle import decode, cvransac, metrics
+from workloads import synth
 from helpers import GOLDEN_CROPS, regen_crop, sha
 
 HERE = os.path.dirname(os.path.abspath(__file__))

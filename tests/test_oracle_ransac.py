@@ -3,7 +3,8 @@ import cv2
 import numpy as np
 import pytest
 
-from oracle import cvransac, decode, epnp, metrics, synth
+from oracle import cvransac, decode, epnp, metrics
+from workloads import synth
 
 
 def _problem(seed, n, noise=True, sigma=0.0):
