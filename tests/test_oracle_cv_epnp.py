@@ -102,7 +102,7 @@ def host(tmp_path_factory):
 
 def _host_epnp(host, corr, idx, K):
     K4 = np.array([K[0, 0], K[1, 1], K[0, 2], K[1, 2]])
-    pose, st = np.zeros(12), (C.c_int * 5)()
+    pose, st = np.zeros(12), (C.c_int * 1)()
     idx = np.ascontiguousarray(idx, np.int32)
     vp = C.c_void_p
     host.cve_host_epnp(corr.ctypes.data_as(vp), corr.shape[1], idx.ctypes.data_as(vp), len(idx), K4.ctypes.data_as(vp),
@@ -112,7 +112,8 @@ def _host_epnp(host, corr, idx, K):
 
 @pytest.mark.parametrize("m", [4, 5, 6, 7, 8])
 def test_product_solver_bit_identical_to_oracle(host, m):
-    """six emulated lanes, wave-front pair order: identical bits to the serial restatement (and so to cv2)"""
+    """stage A / C serial, stage B on six emulated lanes in the wave-front pair order: identical bits to the serial
+    restatement (and so to cv2)"""
     tot, steps = 0, []
     for seed, flip in ((700, 0.0), (701, 0.02)):
         c, uv, xyz = _crop_lists(seed, flip)
@@ -125,7 +126,7 @@ def test_product_solver_bit_identical_to_oracle(host, m):
             tot += 1
             steps.append(sum(st))
     assert tot == 200
-    assert np.mean(steps) < 200          # the serial pair order needs ~520 steps
+    assert np.mean(steps) < 110          # 12x12: the serial pair order needs ~400 pair steps
 
 
 def test_product_solver_degenerate_inputs(host):

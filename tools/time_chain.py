@@ -12,7 +12,7 @@ sys.path.insert(0, ROOT)
 import bench  # noqa: E402
 import zebrapose_b200 as zp  # noqa: E402
 
-NAMES = ["zp_samples_kernel", "zp_minimal_cv_kernel", "zp_minimal_kernel", "zp_score_kernel", "zp_rs_replay_kernel",
+NAMES = ["zp_samples_kernel", "zp_cvs_prep_kernel", "zp_cvs_null_kernel", "zp_cvs_cand_kernel", "zp_cvs_pick_kernel", "zp_minimal_kernel", "zp_score_kernel", "zp_rs_replay_kernel",
          "zp_final_kernel"]
 
 

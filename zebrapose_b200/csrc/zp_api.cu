@@ -102,6 +102,7 @@ void zp_destroy(zp_ctx* ctx) {
     if (ctx->d_counters) cudaFree(ctx->d_counters);
     if (ctx->ws) cudaFree(ctx->ws);
     if (ctx->hws) cudaFree(ctx->hws);
+    if (ctx->cvws) cudaFree(ctx->cvws);
     if (ctx->dws) cudaFree(ctx->dws);
     for (auto& m : ctx->models) if (m.pts) cudaFree(m.pts);
     if (ctx->d_model_ptrs) cudaFree((void*)ctx->d_model_ptrs);

@@ -68,6 +68,9 @@ struct zp_ctx {
     void* dbg_buf = nullptr;                 // device buffer for per-CTA timestamps of the decode kernel (zp_debug_buffer)
     int decode_rpc = 0;                      // runs per CTA of the streaming decode kernel (0 = automatic)
     int force_decode_path = 0;               // 0 auto, 1 register-staged cluster kernel, 2 generic kernel (tests)
+    // hand-off records between the stages of the exact minimal solver (zp_cvsolve.cu)
+    void* cvws = nullptr;
+    size_t cvws_bytes = 0;
     // RANSAC: minimal solver (ZP_SOLVER_*), wave plan (hypotheses per wave; n_waves = 0: automatic)
     int solver = 0;
     int n_waves = 0;

@@ -11,19 +11,27 @@
 //   * sums run sequentially in index order; the Jacobi's hypot is |a|*sqrt(1+(b/a)^2); division and sqrt are IEEE;
 //   * image points pass through float32 normalised coordinates: u' = double(float((u-cx)*(1/fx)))*fx + cx.
 //
-// What is NOT the same is the schedule.  The cyclic Jacobi visits the pairs (0,1),(0,2)..(n-2,n-1) one after the other;
-// a pair only depends on the last earlier pairs that touched its two rows, so pair (i,j) of sweep s can run at time
-// T = n*s + i + j: up to n/2 pairs per step, a sweep every n steps, and a result that is bit-identical to the serial
-// order because every rotation sees exactly the operands it would have seen (tests/test_cvepnp_host.py).  Six lanes
-// share one hypothesis: the 12x12 problem keeps all six busy (66 pairs in 12 steps), the three beta candidates run on
-// lanes 0-4.  The squared row norms the serial code carries along are sequential sums of the stored row, so a lane
-// recomputes them from the row it loads (same values, same order) instead of passing them between lanes.
-//
-// The code is written as per-lane "phases" separated by group barriers, so that the kernel (zp_cvsolve.cu) and the host
-// harness (tests/native/cvepnp_host.cu, lanes emulated by a loop) execute the same source.
+// What is NOT the same is the schedule, because the FP64 pipe of an SM (16 lanes per scheduler) is the resource this
+// work is bound by and a warp instruction costs the same whether 1 or 32 of its lanes do something useful:
+//   stage A  "prep"  one THREAD per hypothesis: staging, centroid, 3x3 PCA, control points, their SVD inverse, the
+//                    barycentric coordinates (all short serial chains)
+//   stage B  "null"  SIX LANES per hypothesis: the 78 sums of M^T M, 13 per lane, then the 12x12 Jacobi SVD.  The cyclic order visits the pairs (0,1),(0,2)..
+//                    (10,11) one after the other, but a pair only depends on the last earlier pairs that touched its two
+//                    rows, so pair (i,j) of sweep s runs at step T = 12 s + i + j: six pairs per step, a sweep every 12
+//                    steps, and a result bit-identical to the serial order because every rotation sees exactly the
+//                    operands it would have seen (tests/test_oracle_cv_epnp.py).  The squared row norms the serial code
+//                    carries along are sequential sums of the stored row, so a lane recomputes them from the rows it loads.
+//                    Then L (6x10) and rho, a row per lane.
+//   stage C  "cand"  one THREAD per (beta initialisation, hypothesis): the 6xN least-squares problem through the same
+//                    Jacobi SVD (serial order), 5 Gauss-Newton steps, camera-frame points, 3x3 alignment SVD, error
+//   stage D  "pick"  EPnP's choice among the three candidates
+// Arrays of stages A and C are strided views (element k at p[k * s]): thread-private data is interleaved over the threads
+// of a CTA (conflict-free shared memory) and the hand-off between the stages is structure-of-arrays in global memory
+// (coalesced), with one piece of code for both and for the host harness (tests/native/cvepnp_host.cpp, stride 1).
 #pragma once
 #include <float.h>
 #include <math.h>
+#include <stddef.h>
 #include <stdint.h>
 
 #ifndef ZP_HD
@@ -34,40 +42,31 @@
 #endif
 #endif
 
-#ifdef __CUDA_ARCH__
-#define CVE_NOINLINE __noinline__      // the SVD tail and the pair step are called from many phases: one copy each
-#else
-#define CVE_NOINLINE
-#endif
-
-#define CVE_G 6              // lanes per hypothesis
+#define CVE_G 6              // lanes per hypothesis in stage B
 #define CVE_MAXM 8           // largest minimal-sample size
-#define CVE_RS 13            // row stride (doubles) of the 12x12 matrix: rows of one hypothesis fall on distinct banks
-
-// per-hypothesis scratch (offsets in doubles)
-#define CVE_A 0              // [12][13] M^T M -> rotated rows; later: the three least-squares systems, then the pose slots
-#define CVE_PW 156           // [m][3] object points
-#define CVE_US 180           // [m][2] image points after the float32 staging
-#define CVE_AL 196           // [m][4] barycentric coordinates
-#define CVE_CW 228           // [4][3] control points
-#define CVE_V4 240           // [4][12] rows 11,10,9,8 of U^T
-#define CVE_L 288            // [6][10]
-#define CVE_RHO 348          // [6]
-#define CVE_A3 354           // [3][3] small Jacobi problem (PCA, control-point inverse)
-#define CVE_V3 363           // [3][3]
-#define CVE_W 372            // [12] singular values
-#define CVE_CI 384           // [3][3] inverse of the control-point basis
-#define CVE_OUT 393          // [3][13] per candidate: R[9] t[3] err
-#define CVE_FLAGS 432        // 3 x 4 ints: "sweep s of problem q rotated something", slot s & 3
-#define CVE_HB 439           // doubles per hypothesis (odd: consecutive hypotheses start on different banks)
-
-// sub-layout of CVE_A during the beta stage: candidate c solves a 6 x NC[c] least-squares problem (rows of At = columns)
-//   c = 0 (N = 1): NC 4   At @0   Vt @24   w @40   x @134
-//   c = 1 (N = 2): NC 3   At @44  Vt @62   w @71   x @138
-//   c = 2 (N = 3): NC 5   At @74  Vt @104  w @129  x @141
-// and during the pose stage candidate c owns 48 doubles @48c: pcs[m][3] @0, At3 @24, Vt3 @33, W3 @42
+#define CVE_RS 13            // row stride (doubles) of the 12x12 matrix in stage B: rows fall on distinct banks
 
 struct CveCam { double fu, fv, uc, vc; };
+
+// strided view of a small array
+struct Dv {
+    double* p;
+    int s;
+    ZP_HD double& operator[](int k) const { return p[(size_t)k * s]; }
+    ZP_HD Dv at(int k) const { Dv v; v.p = p + (size_t)k * s; v.s = s; return v; }
+};
+ZP_HD inline Dv cve_dv(double* p, int s) { Dv v; v.p = p; v.s = s; return v; }
+
+// hand-off record of one hypothesis between the stages (offsets in doubles; stored as [field][hypothesis])
+#define CVH_PW 0             // [8][3]
+#define CVH_US 24            // [8][2]
+#define CVH_AL 40            // [8][4]
+#define CVH_CW 72            // [4][3]
+#define CVH_V4 84            // [4][12] rows 11,10,9,8 of U^T
+#define CVH_L 132            // [6][10]
+#define CVH_RHO 192          // [6]
+#define CVH_OUT 198          // [3][13] per candidate: R[9] t[3] err
+#define CVH_DOUBLES 237
 
 ZP_HD inline double cve_hypot(double a, double b) {
     a = fabs(a); b = fabs(b);
@@ -80,7 +79,7 @@ ZP_HD inline double cve_hypot(double a, double b) {
 // one Jacobi pair: rows Ai, Aj of length M (and rows Vi, Vj of length n of the accumulated rotations)
 // ------------------------------------------------------------------------------------------------------------------
 template <int M, bool HASV>
-ZP_HD inline bool cve_pair(double* Ai, double* Aj, double* Vi, double* Vj, int n) {
+ZP_HD inline bool cve_pair(Dv Ai, Dv Aj, Dv Vi, Dv Vj, int n) {
     const double eps = DBL_EPSILON * 10;
     double ri[M], rj[M];
 #pragma unroll
@@ -116,40 +115,49 @@ ZP_HD inline bool cve_pair(double* Ai, double* Aj, double* Vi, double* Vj, int n
     return true;
 }
 
-// one lane's view of one Jacobi problem: n rows of length M at At (row stride astep), worked on by nl lanes of which this
-// one is number l.  chg = 4 ints shared by the problem's lanes.
+// serial cyclic Jacobi (stages A and C): n rows of length M, row r of At at At.at(r * astep); Vt likewise
+template <int M, bool HASV>
+ZP_HD inline void cve_jserial(Dv At, int astep, Dv Vt, int vstep, int n) {
+    if (HASV)
+        for (int i = 0; i < n; i++)
+            for (int k = 0; k < n; k++) Vt[i * vstep + k] = i == k ? 1.0 : 0.0;
+    const int max_iter = M > 30 ? M : 30;
+    for (int iter = 0; iter < max_iter; iter++) {
+        bool changed = false;
+        for (int i = 0; i < n - 1; i++)
+            for (int j = i + 1; j < n; j++)
+                changed |= cve_pair<M, HASV>(At.at(i * astep), At.at(j * astep), HASV ? Vt.at(i * vstep) : Vt,
+                                             HASV ? Vt.at(j * vstep) : Vt, n);
+        if (!changed) break;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// wave-front Jacobi (stage B): one lane's view of the problem, worked on by nl lanes of which this one is number l;
+// chg = 4 ints shared by the problem's lanes ("sweep s rotated something", slot s & 3)
+// ------------------------------------------------------------------------------------------------------------------
 struct CveJ {
-    double* At; double* Vt; int* chg;
-    int astep, vstep, n, l, nl, max_iter;
-    bool active, done;
+    double* At; int* chg;
+    int astep, n, l, nl, max_iter;
+    bool done;
 };
 
-ZP_HD inline CveJ cve_j_none() {
+ZP_HD inline CveJ cve_j_make(double* At, int astep, int n, int m_cols, int l, int nl, int* chg, bool active) {
     CveJ j;
-    j.At = nullptr; j.Vt = nullptr; j.chg = nullptr; j.astep = j.vstep = 0; j.n = 2; j.l = 0; j.nl = 0; j.max_iter = 0;
-    j.active = false; j.done = true;
-    return j;
-}
-
-ZP_HD inline CveJ cve_j_make(double* At, int astep, double* Vt, int vstep, int n, int m_cols, int l, int nl, int* chg) {
-    CveJ j;
-    j.At = At; j.Vt = Vt; j.chg = chg; j.astep = astep; j.vstep = vstep; j.n = n; j.l = l; j.nl = nl;
+    j.At = At; j.chg = chg; j.astep = astep; j.n = n; j.l = l; j.nl = nl;
     j.max_iter = m_cols > 30 ? m_cols : 30;
-    j.active = l < nl; j.done = !j.active;
+    j.done = !(active && l < nl);
     return j;
 }
 
-// identity in Vt and cleared flags; called by lane l == 0 of the problem before the first step (then a barrier)
+// cleared flags; called by lane l == 0 of the problem before the first step (then a barrier)
 ZP_HD inline void cve_j_init(const CveJ& j) {
-    if (!j.active || j.l != 0) return;
-    if (j.Vt)
-        for (int i = 0; i < j.n; i++)
-            for (int k = 0; k < j.n; k++) j.Vt[i * j.vstep + k] = i == k ? 1.0 : 0.0;
+    if (j.done || j.l != 0) return;
     j.chg[0] = j.chg[1] = j.chg[2] = j.chg[3] = 0;
 }
 
 // step T (1, 2, ...): this lane's pair, if it has one.  Pairs of sweep s = (T - tau)/n with i + j = tau; two sweeps overlap.
-template <int M, bool HASV>
+template <int M>
 ZP_HD inline void cve_jstep_a(CveJ& j, int T) {
     const int n = j.n;
     const int ta = (T - 1) % n + 1, sa = (T - ta) / n;
@@ -165,9 +173,8 @@ ZP_HD inline void cve_jstep_a(CveJ& j, int T) {
     else if (j.l - cnt_a < cnt_b) { ii = lo_b + (j.l - cnt_a); jj = tb - ii; s = sb; }
     else return;
     if (jj >= n || ii >= jj) return;
-    double* Vi = HASV ? j.Vt + ii * j.vstep : nullptr;
-    double* Vj = HASV ? j.Vt + jj * j.vstep : nullptr;
-    if (cve_pair<M, HASV>(j.At + ii * j.astep, j.At + jj * j.astep, Vi, Vj, n)) j.chg[s & 3] = 1;
+    const Dv none = cve_dv(nullptr, 1);
+    if (cve_pair<M, false>(cve_dv(j.At + ii * j.astep, 1), cve_dv(j.At + jj * j.astep, 1), none, none, n)) j.chg[s & 3] = 1;
 }
 
 // after the barrier that follows step T: if a sweep completed at T, stop when it rotated nothing (or at the sweep cap)
@@ -183,9 +190,10 @@ ZP_HD inline void cve_jstep_c(CveJ& j, int T) {
 
 // ------------------------------------------------------------------------------------------------------------------
 // the tail of the SVD routine: singular values = row norms, selection sort (descending, rows swapped physically),
-// rows normalised (an exactly-zero singular value gets a pseudo-random row orthogonalised against the rows above it)
+// rows normalised (an exactly-zero singular value gets a pseudo-random row orthogonalised against the rows above it).
+// have_v = false: no Vt storage (the rows are still swapped: every call replayed here has a Vt in the library).
 // ------------------------------------------------------------------------------------------------------------------
-ZP_HD CVE_NOINLINE inline void cve_finish(double* At, int astep, double* W, double* Vt, int vstep, int m, int n, int n1) {
+ZP_HD inline void cve_finish(Dv At, int astep, Dv W, Dv Vt, int vstep, bool have_v, int m, int n, int n1) {
     const double eps = DBL_EPSILON * 10, minval = DBL_MIN;
     int i, j, k;
     double sd;
@@ -198,9 +206,8 @@ ZP_HD CVE_NOINLINE inline void cve_finish(double* At, int astep, double* W, doub
         for (k = i + 1; k < n; k++) if (W[j] < W[k]) j = k;
         if (i != j) {
             double t = W[i]; W[i] = W[j]; W[j] = t;
-            // (the library swaps the rows "if Vt"; every call replayed here has a Vt, stored or not)
             for (k = 0; k < m; k++) { t = At[i * astep + k]; At[i * astep + k] = At[j * astep + k]; At[j * astep + k] = t; }
-            if (Vt) for (k = 0; k < n; k++) { t = Vt[i * vstep + k]; Vt[i * vstep + k] = Vt[j * vstep + k]; Vt[j * vstep + k] = t; }
+            if (have_v) for (k = 0; k < n; k++) { t = Vt[i * vstep + k]; Vt[i * vstep + k] = Vt[j * vstep + k]; Vt[j * vstep + k] = t; }
         }
     }
     uint64_t rng = 0x12345678;
@@ -236,7 +243,7 @@ ZP_HD CVE_NOINLINE inline void cve_finish(double* At, int astep, double* W, doub
 
 // x = pinv(A) b from the finished SVD of a 6 x NC system (At rows = left vectors, Vt): singular values at or below
 // 2 eps sum(w) are dropped
-ZP_HD inline void cve_backsubst6(const double* At, const double* w, const double* Vt, int nc, const double* b, double* x) {
+ZP_HD inline void cve_backsubst6(Dv At, Dv w, Dv Vt, int nc, const double* b, double* x) {
     double thr = 0;
     for (int i = 0; i < nc; i++) { x[i] = 0; thr += w[i]; }
     thr *= DBL_EPSILON * 2;
@@ -259,6 +266,7 @@ ZP_HD inline void cve_qr_solve64(double* A, double* b, double* X) {
 #pragma unroll
     for (int k = 0; k < nc; k++) {
         double eta = fabs(A[k * nc + k]);
+#pragma unroll
         for (int i = k + 1; i < nr; i++) {
             const double elt = fabs(A[(i - 1) * nc + k]);
             if (eta < elt) eta = elt;
@@ -266,6 +274,7 @@ ZP_HD inline void cve_qr_solve64(double* A, double* b, double* X) {
         if (eta == 0) { A1[k] = A2[k] = 0.0; return; }
         double sum2 = 0.0;
         const double inv_eta = 1. / eta;
+#pragma unroll
         for (int i = k; i < nr; i++) { A[i * nc + k] *= inv_eta; sum2 += A[i * nc + k] * A[i * nc + k]; }
         double sigma = sqrt(sum2);
         if (A[k * nc + k] < 0) sigma = -sigma;
@@ -275,33 +284,41 @@ ZP_HD inline void cve_qr_solve64(double* A, double* b, double* X) {
 #pragma unroll
         for (int j = k + 1; j < nc; j++) {
             double sum = 0;
+#pragma unroll
             for (int i = k; i < nr; i++) sum += A[i * nc + k] * A[i * nc + j];
             const double tau = sum / A1[k];
+#pragma unroll
             for (int i = k; i < nr; i++) A[i * nc + j] -= tau * A[i * nc + k];
         }
     }
 #pragma unroll
     for (int j = 0; j < nc; j++) {
         double tau = 0;
+#pragma unroll
         for (int i = j; i < nr; i++) tau += A[i * nc + j] * b[i];
         tau /= A1[j];
+#pragma unroll
         for (int i = j; i < nr; i++) b[i] -= tau * A[i * nc + j];
     }
     X[nc - 1] = b[nc - 1] / A2[nc - 1];
 #pragma unroll
     for (int i = nc - 2; i >= 0; i--) {
         double sum = 0;
+#pragma unroll
         for (int j = i + 1; j < nc; j++) sum += A[i * nc + j] * X[j];
         X[i] = (b[i] - sum) / A2[i];
     }
 }
 
-ZP_HD inline void cve_gauss_newton(const double* L, const double* rho, double* betas) {
+// 5 Gauss-Newton steps on the betas; L (6x10) and rho (6) are strided views (read-only)
+ZP_HD inline void cve_gauss_newton(Dv L, Dv rho, double* betas) {
     double a[24], b[6], x[4] = {0, 0, 0, 0};
     for (int it = 0; it < 5; it++) {
 #pragma unroll
         for (int i = 0; i < 6; i++) {
-            const double* rowL = L + i * 10;
+            double rowL[10];
+#pragma unroll
+            for (int q = 0; q < 10; q++) rowL[q] = L[10 * i + q];
             double* rowA = a + i * 4;
             rowA[0] = 2 * rowL[0] * betas[0] + rowL[1] * betas[1] + rowL[3] * betas[2] + rowL[6] * betas[3];
             rowA[1] = rowL[1] * betas[0] + 2 * rowL[2] * betas[1] + rowL[4] * betas[2] + rowL[7] * betas[3];
@@ -318,19 +335,15 @@ ZP_HD inline void cve_gauss_newton(const double* L, const double* rho, double* b
 }
 
 ZP_HD inline double cve_dot3(const double* a, const double* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
-ZP_HD inline double cve_dist2(const double* a, const double* b) {
-    return (a[0] - b[0]) * (a[0] - b[0]) + (a[1] - b[1]) * (a[1] - b[1]) + (a[2] - b[2]) * (a[2] - b[2]);
-}
 
 // ------------------------------------------------------------------------------------------------------------------
-// phases.  S = the hypothesis' scratch block, lane = 0..CVE_G-1; a group barrier separates consecutive phases.
+// stage A: everything up to the barycentric coordinates.  Views: pw [m][3], us [m][2], al [m][4], cw [4][3] (kept for the
+// later stages), wk = 33 doubles of scratch (A3 9 | V3 9 | W 3 | CI 9 | spare 3).
+// corr: the five float planes of the crop (u | v | X | Y | Z, `cap` apart); idx: the m sample indices (all valid)
 // ------------------------------------------------------------------------------------------------------------------
-
-// phase 0 (lane 0): stage the m sampled correspondences, centroid, scatter matrix -> A3 (transposed = itself)
-// uvxyz: the five float planes of the crop (u | v | X | Y | Z, `cap` apart); idx: the m sample indices (all valid)
-ZP_HD inline void cve_ph0(double* S, int lane, const float* corr, int cap, const int32_t* idx, int m, const CveCam& cam) {
-    if (lane != 0) return;
-    double* pw = S + CVE_PW; double* us = S + CVE_US; double* cws = S + CVE_CW;
+ZP_HD inline void cve_stage_a(const float* corr, int cap, const int32_t* idx, int m, const CveCam& cam,
+                              Dv pw, Dv us, Dv al, Dv cw, Dv wk) {
+    const Dv A3 = wk, V3 = wk.at(9), W = wk.at(18), ci = wk.at(21);
     const double ifx = 1. / cam.fu, ify = 1. / cam.fv;
     for (int p = 0; p < m; p++) {
         const int i = idx[p];
@@ -338,45 +351,34 @@ ZP_HD inline void cve_ph0(double* S, int lane, const float* corr, int cap, const
         pw[3 * p] = (double)corr[2 * (size_t)cap + i];
         pw[3 * p + 1] = (double)corr[3 * (size_t)cap + i];
         pw[3 * p + 2] = (double)corr[4 * (size_t)cap + i];
+        // undistortPoints (no distortion) -> float32 normalised coordinates -> back to pixels
         const double x = (u - cam.uc) * ifx, y = (v - cam.vc) * ify;
         us[2 * p] = (double)(float)x * cam.fu + cam.uc;
         us[2 * p + 1] = (double)(float)y * cam.fv + cam.vc;
     }
-    cws[0] = cws[1] = cws[2] = 0;
-    for (int p = 0; p < m; p++) for (int j = 0; j < 3; j++) cws[j] += pw[3 * p + j];
-    for (int j = 0; j < 3; j++) cws[j] /= m;
-    double* A3 = S + CVE_A3;
+    // control points: centroid + PCA axes of the object points
+    double c0[3] = {0, 0, 0};
+    for (int p = 0; p < m; p++) for (int j = 0; j < 3; j++) c0[j] += pw[3 * p + j];
+    for (int j = 0; j < 3; j++) { c0[j] /= m; cw[j] = c0[j]; }
     for (int i = 0; i < 3; i++)
         for (int j = i; j < 3; j++) {
             double s = 0;
-            for (int p = 0; p < m; p++) s += (pw[3 * p + i] - cws[i]) * (pw[3 * p + j] - cws[j]);
+            for (int p = 0; p < m; p++) s += (pw[3 * p + i] - c0[i]) * (pw[3 * p + j] - c0[j]);
             A3[i * 3 + j] = s; A3[j * 3 + i] = s;
         }
-}
-
-// phase 1 (lane 0): PCA finished -> control points -> their basis matrix, transposed, into A3 for the SVD inverse
-ZP_HD inline void cve_ph1(double* S, int lane, int m) {
-    if (lane != 0) return;
-    double* A3 = S + CVE_A3; double* V3 = S + CVE_V3; double* W = S + CVE_W; double* cws = S + CVE_CW;
-    cve_finish(A3, 3, W, V3, 3, 3, 3, 3);
+    cve_jserial<3, true>(A3, 3, V3, 3, 3);
+    cve_finish(A3, 3, W, V3, 3, true, 3, 3, 3);
     for (int i = 1; i < 4; i++) {
         const double k = sqrt(W[i - 1] / m);
-        for (int j = 0; j < 3; j++) cws[3 * i + j] = cws[j] + k * A3[3 * (i - 1) + j];
+        for (int j = 0; j < 3; j++) cw[3 * i + j] = c0[j] + k * A3[3 * (i - 1) + j];
     }
-    // cc[3*i + j-1] = cws[j][i] - cws[0][i]; the SVD works on the transpose: At[r][c] = cc[c][r]
-    double cc[9];
-    for (int i = 0; i < 3; i++) for (int j = 1; j < 4; j++) cc[3 * i + j - 1] = cws[3 * j + i] - cws[i];
-    for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) A3[r * 3 + c] = cc[c * 3 + r];
-}
-
-// phase 2 (lane 0): inverse of the control-point basis from its SVD: V diag(1/w) U^T, one singular value at a time
-ZP_HD inline void cve_ph2(double* S, int lane) {
-    if (lane != 0) return;
-    double* A3 = S + CVE_A3; double* V3 = S + CVE_V3; double* W = S + CVE_W; double* ci = S + CVE_CI;
-    cve_finish(A3, 3, W, V3, 3, 3, 3, 3);
+    // inverse of the control-point basis through its SVD: cc[3*i + j-1] = cw[j][i] - cw[0][i]; At = cc^T
+    for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) A3[r * 3 + c] = cw[3 * (r + 1) + c] - c0[c];
+    cve_jserial<3, true>(A3, 3, V3, 3, 3);
+    cve_finish(A3, 3, W, V3, 3, true, 3, 3, 3);
     const double thr = (W[0] + W[1] + W[2]) * (DBL_EPSILON * 2);
     for (int i = 0; i < 9; i++) ci[i] = 0;
-    for (int i = 0; i < 3; i++) {
+    for (int i = 0; i < 3; i++) {           // V diag(1/w) U^T, one singular value at a time
         double wi = W[i];
         if (fabs(wi) <= thr) continue;
         wi = 1 / wi;
@@ -387,24 +389,23 @@ ZP_HD inline void cve_ph2(double* S, int lane) {
             for (int j = 0; j < 3; j++) ci[r * 3 + j] = ci[r * 3 + j] + s * buf[j];
         }
     }
-}
-
-// phase 3 (all lanes): barycentric coordinates, point p on lane p % G
-ZP_HD inline void cve_ph3(double* S, int lane, int m) {
-    const double* pw = S + CVE_PW; const double* cws = S + CVE_CW; const double* ci = S + CVE_CI;
-    for (int p = lane; p < m; p += CVE_G) {
-        const double* pi = pw + 3 * p;
-        double* a = S + CVE_AL + 4 * p;
-        for (int j = 0; j < 3; j++)
-            a[1 + j] = ci[3 * j] * (pi[0] - cws[0]) + ci[3 * j + 1] * (pi[1] - cws[1]) + ci[3 * j + 2] * (pi[2] - cws[2]);
-        a[0] = 1.0f - a[1] - a[2] - a[3];
+    // barycentric coordinates
+    for (int p = 0; p < m; p++) {
+        const double d0 = pw[3 * p] - c0[0], d1 = pw[3 * p + 1] - c0[1], d2 = pw[3 * p + 2] - c0[2];
+        double a1 = ci[0] * d0 + ci[1] * d1 + ci[2] * d2;
+        double a2 = ci[3] * d0 + ci[4] * d1 + ci[5] * d2;
+        double a3 = ci[6] * d0 + ci[7] * d1 + ci[8] * d2;
+        al[4 * p + 1] = a1; al[4 * p + 2] = a2; al[4 * p + 3] = a3;
+        al[4 * p] = 1.0f - a1 - a2 - a3;
     }
 }
 
-// phase 4 (all lanes): M^T M, entry (i, j >= i) = sequential sum over the 2m rows of M, 13 entries per lane
-ZP_HD inline void cve_ph4(double* S, int lane, int m, const CveCam& cam) {
-    const double* al = S + CVE_AL; const double* us = S + CVE_US;
-    double* A = S + CVE_A;
+// ------------------------------------------------------------------------------------------------------------------
+// stage B pieces (A = the hypothesis' [12][13] matrix in shared memory, unit stride)
+// ------------------------------------------------------------------------------------------------------------------
+// lane l of the six: its 13 of the 78 entries of M^T M.  Entry (i, j >= i) = sequential sum over the 2m rows of M (rows
+// [a fu, 0, a (uc-u)] and [0, a fv, a (vc-v)] per point); al [m][4] and us [m][2] in shared memory, unit stride
+ZP_HD inline void cve_b_mtm(double* A, int lane, const double* al, const double* us, int m, const CveCam& cam) {
     for (int e = lane; e < 78; e += CVE_G) {
         int i = 0, r = e;
         while (r >= 12 - i) { r -= 12 - i; i++; }
@@ -425,75 +426,57 @@ ZP_HD inline void cve_ph4(double* S, int lane, int m, const CveCam& cam) {
     }
 }
 
-// phase 5 (lane 0): finish the 12x12 SVD, keep rows 11, 10, 9, 8 of U^T
-ZP_HD inline void cve_ph5(double* S, int lane) {
-    if (lane != 0) return;
-    double* A = S + CVE_A; double* W = S + CVE_W; double* V4 = S + CVE_V4;
-    cve_finish(A, CVE_RS, W, nullptr, 0, 12, 12, 12);
+// lane 0: finish the SVD, keep rows 11, 10, 9, 8 of U^T in V4 [4][12] (unit stride, shared memory); W: 12 doubles
+ZP_HD inline void cve_b_finish(double* A, double* W, double* V4) {
+    cve_finish(cve_dv(A, 1), CVE_RS, cve_dv(W, 1), cve_dv(nullptr, 1), 0, false, 12, 12, 12);
     for (int q = 0; q < 4; q++)
         for (int k = 0; k < 12; k++) V4[q * 12 + k] = A[(11 - q) * CVE_RS + k];
 }
 
-// phase 6 (lane r): row r of L (6x10) and rho[r]
-ZP_HD inline void cve_ph6(double* S, int lane) {
+// lane r: row r of L (6x10) and rho[r]; V4 in shared memory, cw / L / rho strided views
+ZP_HD inline void cve_b_L_rho(const double* V4, int r, Dv cw, Dv L, Dv rho) {
     const int pa[6] = {0, 0, 0, 1, 1, 2}, pb[6] = {1, 2, 3, 2, 3, 3};
-    const double* V4 = S + CVE_V4; const double* cws = S + CVE_CW;
-    for (int r = lane; r < 6; r += CVE_G) {
-        double dv[4][3];
-        for (int q = 0; q < 4; q++)
-            for (int e = 0; e < 3; e++) dv[q][e] = V4[q * 12 + 3 * pa[r] + e] - V4[q * 12 + 3 * pb[r] + e];
-        double* row = S + CVE_L + 10 * r;
-        row[0] = cve_dot3(dv[0], dv[0]);
-        row[1] = 2.0f * cve_dot3(dv[0], dv[1]);
-        row[2] = cve_dot3(dv[1], dv[1]);
-        row[3] = 2.0f * cve_dot3(dv[0], dv[2]);
-        row[4] = 2.0f * cve_dot3(dv[1], dv[2]);
-        row[5] = cve_dot3(dv[2], dv[2]);
-        row[6] = 2.0f * cve_dot3(dv[0], dv[3]);
-        row[7] = 2.0f * cve_dot3(dv[1], dv[3]);
-        row[8] = 2.0f * cve_dot3(dv[2], dv[3]);
-        row[9] = cve_dot3(dv[3], dv[3]);
-        S[CVE_RHO + r] = cve_dist2(cws + 3 * pa[r], cws + 3 * pb[r]);
-    }
+    double dv[4][3];
+    for (int q = 0; q < 4; q++)
+        for (int e = 0; e < 3; e++) dv[q][e] = V4[q * 12 + 3 * pa[r] + e] - V4[q * 12 + 3 * pb[r] + e];
+    L[10 * r + 0] = cve_dot3(dv[0], dv[0]);
+    L[10 * r + 1] = 2.0f * cve_dot3(dv[0], dv[1]);
+    L[10 * r + 2] = cve_dot3(dv[1], dv[1]);
+    L[10 * r + 3] = 2.0f * cve_dot3(dv[0], dv[2]);
+    L[10 * r + 4] = 2.0f * cve_dot3(dv[1], dv[2]);
+    L[10 * r + 5] = cve_dot3(dv[2], dv[2]);
+    L[10 * r + 6] = 2.0f * cve_dot3(dv[0], dv[3]);
+    L[10 * r + 7] = 2.0f * cve_dot3(dv[1], dv[3]);
+    L[10 * r + 8] = 2.0f * cve_dot3(dv[2], dv[3]);
+    L[10 * r + 9] = cve_dot3(dv[3], dv[3]);
+    const double a0 = cw[3 * pa[r]] - cw[3 * pb[r]], a1 = cw[3 * pa[r] + 1] - cw[3 * pb[r] + 1], a2 = cw[3 * pa[r] + 2] - cw[3 * pb[r] + 2];
+    rho[r] = a0 * a0 + a1 * a1 + a2 * a2;
 }
 
-struct CveCand { int nc, at, vt, w, x, lane0, nl; };
-ZP_HD inline CveCand cve_cand(int c) {
-    CveCand k;
-    if (c == 0) { k.nc = 4; k.at = 0; k.vt = 24; k.w = 40; k.x = 134; k.lane0 = 0; k.nl = 2; }
-    else if (c == 1) { k.nc = 3; k.at = 44; k.vt = 62; k.w = 71; k.x = 138; k.lane0 = 2; k.nl = 1; }
-    else { k.nc = 5; k.at = 74; k.vt = 104; k.w = 129; k.x = 141; k.lane0 = 3; k.nl = 2; }
-    return k;
-}
-// candidate a lane works for during the beta stage (-1: none) and whether it is the candidate's owner lane
-ZP_HD inline int cve_lane_cand(int lane) { return lane < 2 ? 0 : lane == 2 ? 1 : lane < 5 ? 2 : -1; }
-
-// phase 7 (owner lanes): the three sub-systems of L, transposed (rows of At = columns of the 6 x NC matrix)
-ZP_HD inline void cve_ph7(double* S, int lane) {
-    const int c = cve_lane_cand(lane);
-    if (c < 0) return;
-    const CveCand k = cve_cand(c);
-    if (lane != k.lane0) return;
+// ------------------------------------------------------------------------------------------------------------------
+// stage C: one beta initialisation c (0, 1, 2 = OpenCV's N = 1, 2, 3) of one hypothesis.  Read-only views: L, rho, V4,
+// al, pw, us.  wk: 84 doubles of scratch (At 30 | Vt 25 | w 5 | pcs 24).  out: R[9] t[3] err (13 doubles).
+// ------------------------------------------------------------------------------------------------------------------
+template <int NC>
+ZP_HD inline void cve_c_solve(Dv L, Dv rho, Dv wk, int c, double* x) {
+    const Dv At = wk, Vt = wk.at(30), w = wk.at(55);
     const int cols0[4] = {0, 1, 3, 6};
-    const double* L = S + CVE_L;
-    double* At = S + CVE_A + k.at;
-    for (int q = 0; q < k.nc; q++) {
+    for (int q = 0; q < NC; q++) {
         const int col = c == 0 ? cols0[q] : q;
         for (int r = 0; r < 6; r++) At[q * 6 + r] = L[10 * r + col];
     }
+    cve_jserial<6, true>(At, 6, Vt, NC, NC);
+    cve_finish(At, 6, w, Vt, NC, true, 6, NC, NC);
+    double rh[6];
+    for (int r = 0; r < 6; r++) rh[r] = rho[r];
+    cve_backsubst6(At, w, Vt, NC, rh, x);
 }
 
-// phase 8 (owner lanes): least-squares solution -> beta initialisation -> 5 Gauss-Newton steps -> camera-frame control
-// points and points, sign, centroids, the 3x3 correlation matrix (transposed into the candidate's At3)
-ZP_HD inline void cve_ph8(double* S, int lane, int m, double* betas_out) {
-    const int c = cve_lane_cand(lane);
-    if (c < 0) return;
-    const CveCand k = cve_cand(c);
-    if (lane != k.lane0) return;
-    double* At = S + CVE_A + k.at; double* Vt = S + CVE_A + k.vt; double* w = S + CVE_A + k.w;
-    cve_finish(At, 6, w, Vt, k.nc, 6, k.nc, k.nc);
+ZP_HD inline void cve_stage_c(int c, int m, const CveCam& cam, Dv L, Dv rho, Dv V4, Dv al, Dv pws, Dv us, Dv wk, Dv out) {
     double x[5], be[4];
-    cve_backsubst6(At, w, Vt, k.nc, S + CVE_RHO, x);
+    if (c == 0) cve_c_solve<4>(L, rho, wk, c, x);
+    else if (c == 1) cve_c_solve<3>(L, rho, wk, c, x);
+    else cve_c_solve<5>(L, rho, wk, c, x);
     if (c == 0) {
         if (x[0] < 0) { be[0] = sqrt(-x[0]); be[1] = -x[1] / be[0]; be[2] = -x[2] / be[0]; be[3] = -x[3] / be[0]; }
         else { be[0] = sqrt(x[0]); be[1] = x[1] / be[0]; be[2] = x[2] / be[0]; be[3] = x[3] / be[0]; }
@@ -504,33 +487,17 @@ ZP_HD inline void cve_ph8(double* S, int lane, int m, double* betas_out) {
         be[2] = c == 2 ? x[3] / be[0] : 0.0;
         be[3] = 0.0;
     }
-    double L[60], rho[6];
-    for (int i = 0; i < 60; i++) L[i] = S[CVE_L + i];
-    for (int i = 0; i < 6; i++) rho[i] = S[CVE_RHO + i];
     cve_gauss_newton(L, rho, be);
-    for (int i = 0; i < 4; i++) betas_out[i] = be[i];
-}
-
-// phase 9 (owner lanes, after a barrier: the least-squares scratch is dead): pose slots
-ZP_HD inline void cve_ph9(double* S, int lane, int m, const double* be) {
-    const int c = cve_lane_cand(lane);
-    if (c < 0) return;
-    const CveCand k = cve_cand(c);
-    if (lane != k.lane0) return;
-    const double* V4 = S + CVE_V4; const double* al = S + CVE_AL; const double* pws = S + CVE_PW;
-    double* slot = S + CVE_A + 48 * c;
-    double* pcs = slot; double* At3 = slot + 24;
+    // camera-frame control points and points, sign
+    const Dv A3 = wk, V3 = wk.at(9), W3 = wk.at(18), pcs = wk.at(60);
     double ccs[4][3];
     for (int i = 0; i < 4; i++) ccs[i][0] = ccs[i][1] = ccs[i][2] = 0.0;
-    for (int i = 0; i < 4; i++) {
-        const double* v = V4 + 12 * i;
+    for (int i = 0; i < 4; i++)
         for (int j = 0; j < 4; j++)
-            for (int q = 0; q < 3; q++) ccs[j][q] += be[i] * v[3 * j + q];
-    }
+            for (int q = 0; q < 3; q++) ccs[j][q] += be[i] * V4[12 * i + 3 * j + q];
     for (int p = 0; p < m; p++) {
-        const double* a = al + 4 * p;
-        for (int j = 0; j < 3; j++)
-            pcs[3 * p + j] = a[0] * ccs[0][j] + a[1] * ccs[1][j] + a[2] * ccs[2][j] + a[3] * ccs[3][j];
+        const double a0 = al[4 * p], a1 = al[4 * p + 1], a2 = al[4 * p + 2], a3 = al[4 * p + 3];
+        for (int j = 0; j < 3; j++) pcs[3 * p + j] = a0 * ccs[0][j] + a1 * ccs[1][j] + a2 * ccs[2][j] + a3 * ccs[3][j];
     }
     if (pcs[2] < 0.0)
         for (int i = 0; i < 3 * m; i++) pcs[i] = -pcs[i];
@@ -540,37 +507,21 @@ ZP_HD inline void cve_ph9(double* S, int lane, int m, const double* be) {
     for (int j = 0; j < 3; j++) { pc0[j] /= m; pw0[j] /= m; }
     double abt[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
     for (int p = 0; p < m; p++) {
-        const double* pc = pcs + 3 * p;
-        const double* pw = pws + 3 * p;
+        const double w0 = pws[3 * p] - pw0[0], w1 = pws[3 * p + 1] - pw0[1], w2 = pws[3 * p + 2] - pw0[2];
         for (int j = 0; j < 3; j++) {
-            abt[3 * j] += (pc[j] - pc0[j]) * (pw[0] - pw0[0]);
-            abt[3 * j + 1] += (pc[j] - pc0[j]) * (pw[1] - pw0[1]);
-            abt[3 * j + 2] += (pc[j] - pc0[j]) * (pw[2] - pw0[2]);
+            const double d = pcs[3 * p + j] - pc0[j];
+            abt[3 * j] += d * w0;
+            abt[3 * j + 1] += d * w1;
+            abt[3 * j + 2] += d * w2;
         }
     }
-    for (int r = 0; r < 3; r++) for (int q = 0; q < 3; q++) At3[r * 3 + q] = abt[q * 3 + r];
-    // the centroids are needed again after the SVD: keep them where pcs of points >= 6 would be only if m <= 6;
-    // recomputing them in phase 10 is cheaper than finding room
-}
-
-// phase 10 (owner lanes): R = U V^T, det fix, t, mean reprojection distance -> CVE_OUT slot of the candidate
-ZP_HD inline void cve_ph10(double* S, int lane, int m, const CveCam& cam) {
-    const int c = cve_lane_cand(lane);
-    if (c < 0) return;
-    const CveCand k = cve_cand(c);
-    if (lane != k.lane0) return;
-    const double* pws = S + CVE_PW; const double* us = S + CVE_US;
-    double* slot = S + CVE_A + 48 * c;
-    double* pcs = slot; double* ut3 = slot + 24; double* vt3 = slot + 33; double* W3 = slot + 42;
-    cve_finish(ut3, 3, W3, vt3, 3, 3, 3, 3);
-    double pc0[3] = {0, 0, 0}, pw0[3] = {0, 0, 0};
-    for (int p = 0; p < m; p++)
-        for (int j = 0; j < 3; j++) { pc0[j] += pcs[3 * p + j]; pw0[j] += pws[3 * p + j]; }
-    for (int j = 0; j < 3; j++) { pc0[j] /= m; pw0[j] /= m; }
+    for (int r = 0; r < 3; r++) for (int q = 0; q < 3; q++) A3[r * 3 + q] = abt[q * 3 + r];
+    cve_jserial<3, true>(A3, 3, V3, 3, 3);
+    cve_finish(A3, 3, W3, V3, 3, true, 3, 3, 3);
     double R[3][3], t[3];
     for (int i = 0; i < 3; i++)
         for (int j = 0; j < 3; j++)
-            R[i][j] = ut3[0 * 3 + i] * vt3[0 * 3 + j] + ut3[1 * 3 + i] * vt3[1 * 3 + j] + ut3[2 * 3 + i] * vt3[2 * 3 + j];
+            R[i][j] = A3[0 * 3 + i] * V3[0 * 3 + j] + A3[1 * 3 + i] * V3[1 * 3 + j] + A3[2 * 3 + i] * V3[2 * 3 + j];
     const double det = R[0][0] * R[1][1] * R[2][2] + R[0][1] * R[1][2] * R[2][0] + R[0][2] * R[1][0] * R[2][1] -
                        R[0][2] * R[1][1] * R[2][0] - R[0][1] * R[1][0] * R[2][2] - R[0][0] * R[1][2] * R[2][1];
     if (det < 0) { R[2][0] = -R[2][0]; R[2][1] = -R[2][1]; R[2][2] = -R[2][2]; }
@@ -579,7 +530,7 @@ ZP_HD inline void cve_ph10(double* S, int lane, int m, const CveCam& cam) {
     t[2] = pc0[2] - cve_dot3(R[2], pw0);
     double sum2 = 0.0;
     for (int p = 0; p < m; p++) {
-        const double* pw = pws + 3 * p;
+        const double pw[3] = {pws[3 * p], pws[3 * p + 1], pws[3 * p + 2]};
         const double Xc = cve_dot3(R[0], pw) + t[0];
         const double Yc = cve_dot3(R[1], pw) + t[1];
         const double inv_Zc = 1.0 / (cve_dot3(R[2], pw) + t[2]);
@@ -588,17 +539,15 @@ ZP_HD inline void cve_ph10(double* S, int lane, int m, const CveCam& cam) {
         const double u = us[2 * p], v = us[2 * p + 1];
         sum2 += sqrt((u - ue) * (u - ue) + (v - ve) * (v - ve));
     }
-    double* out = S + CVE_OUT + 13 * c;
     for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) out[3 * i + j] = R[i][j];
     for (int i = 0; i < 3; i++) out[9 + i] = t[i];
     out[12] = sum2 / m;
 }
 
-// phase 11 (any lane after a barrier): EPnP's choice among the three candidates; returns the slot (R[9] t[3] err)
-ZP_HD inline const double* cve_pick(const double* S) {
-    const double* o = S + CVE_OUT;
+// stage D: EPnP's choice among the three candidates ([3][13] view); returns the candidate index
+ZP_HD inline int cve_pick(Dv o) {
     int N = 0;
     if (o[13 + 12] < o[12]) N = 1;
     if (o[26 + 12] < o[13 * N + 12]) N = 2;
-    return o + 13 * N;
+    return N;
 }

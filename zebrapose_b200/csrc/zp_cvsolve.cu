@@ -4,135 +4,185 @@
 // cv2's winner.  THIS TRANSLATION UNIT IS COMPILED WITH -fmad=false (zebrapose_b200/_build.py): a contracted multiply-add
 // anywhere in the replayed chain changes the null-space basis of a 5-point sample.
 //
-//   zp_minimal_cv_kernel   six lanes per hypothesis, five hypotheses per warp; the hypothesis' matrices live in shared
-//                          memory (3.4 KB each).  The Jacobi SVDs (3x3 PCA, 3x3 inverse, 12x12 null space, the three
-//                          6xN least-squares problems, three 3x3 alignments) run in the dependency-preserving
-//                          wave-front order of zp_cvepnp.cuh: ~145 pair steps instead of ~520 in the serial order.
-//                          FP64 latency bound by construction (a step is one dependent chain of 3 divisions, 3 square
-//                          roots and a 12-term sequential sum); throughput comes from the 9600+ hypotheses in flight.
-//
+// The work is bound by the FP64 pipe (16 lanes per scheduler; tools/micro/fp64_lat.cu: a division chain costs 119 cycles
+// per link, a square root 88, a warp-wide DADD/DMUL issues every 2 cycles), and a warp instruction costs the same
+// whether 1 or 32 lanes are useful -- a first single-kernel version that kept six lanes per hypothesis through all phases
+// spent 55 % of its time in phases that use one to three of them (profiles/r2b_cv_phases.txt).  Hence four kernels with
+// the lane mapping each stage wants, handing a [field][hypothesis] record through global memory (L2-resident at
+// BASELINE's batch sizes):
+//   zp_cvs_prep_kernel   thread per hypothesis            stage A: staging ... barycentric coordinates
+//   zp_cvs_null_kernel   six lanes per hypothesis         stage B: M^T M, 12x12 Jacobi SVD in the wave-front order, L, rho
+//   zp_cvs_cand_kernel   thread per (candidate, hyp.)     stage C: least squares, Gauss-Newton, alignment, error
+//   zp_cvs_pick_kernel   thread per hypothesis            stage D: EPnP's choice -> pose, projection matrix
 // Hypotheses are solved in waves [h0, h0 + hw) of every crop that has not reached cv2's adaptive stop yet (crop_done).
 #include "zp_common.cuh"
 #include "zp_cvepnp.cuh"
 #include "zp_proj.cuh"
 
-constexpr int CVS_HPW = 5;                     // hypotheses per warp (5 x 6 lanes; lanes 30 and 31 idle)
-constexpr int CVS_WARPS = 2;
-constexpr int CVS_THREADS = 32 * CVS_WARPS;
-constexpr int CVS_SMEM = CVS_WARPS * CVS_HPW * CVE_HB * (int)sizeof(double);
+constexpr int CVA_THREADS = 64;                // stage A: private data 117 doubles per thread, interleaved over the CTA
+constexpr int CVA_PRIV = 24 + 16 + 32 + 12 + 33;
+constexpr int CVB_HPW = 5;                     // stage B: hypotheses per warp (5 x 6 lanes; lanes 30 and 31 idle)
+constexpr int CVB_WARPS = 2;
+constexpr int CVB_HB = 219;                    // doubles per hypothesis: A 156 | W 12 | V4 48 (first: al 32 | us 16) | flags 2 (+1: odd stride)
+constexpr int CVC_THREADS = 64;                // stage C: 84 doubles of scratch per thread
+constexpr int CVC_PRIV = 84;
 
-template <int M, bool HASV>
-__device__ __noinline__ void cvs_jrun(CveJ& j) {
+struct CvsArgs {
+    const float* corr; int cap; const int32_t* counts; const double* K; const int32_t* samples;
+    int B, H, h0, hw; const int32_t* crop_done; int m; double inv_thr;
+    double* rec; int nhp;                      // hand-off records: field f of local hypothesis g at rec[f * nhp + g]
+    double* hyp_poses; float* hyp_P; int32_t* hyp_inliers;
+};
+
+// local hypothesis index -> (crop, global hypothesis index, must it be solved?)
+struct CvsHyp { int b; size_t g; bool live, run; };
+__device__ __forceinline__ CvsHyp cvs_hyp(const CvsArgs& a, long long gloc) {
+    CvsHyp h;
+    h.live = gloc < (long long)a.B * a.hw;
+    h.b = h.live ? (int)(gloc / a.hw) : 0;
+    h.g = (size_t)h.b * a.H + a.h0 + (h.live ? (int)(gloc - (long long)h.b * a.hw) : 0);
+    if (h.live && a.crop_done && a.crop_done[h.b]) h.live = false;
+    h.run = false;
+    if (h.live) {
+        const int n = min(a.counts[h.b], a.cap);
+        const int32_t* sidx = a.samples + h.g * a.m;
+        bool valid = n >= a.m;
+        if (valid)
+            for (int j = 0; j < a.m; j++) valid = valid && sidx[j] >= 0 && sidx[j] < n;
+        h.run = valid;
+    }
+    return h;
+}
+
+__device__ __forceinline__ CveCam cvs_cam(const CvsArgs& a, int b) {
+    const double* Kb = a.K + 9 * (size_t)b;
+    return CveCam{Kb[0], Kb[4], Kb[2], Kb[5]};
+}
+
+__global__ void __launch_bounds__(CVA_THREADS) zp_cvs_prep_kernel(CvsArgs a) {
+    extern __shared__ __align__(16) double s_a[];
+    const int tid = threadIdx.x;
+    const long long gloc = (long long)blockIdx.x * CVA_THREADS + tid;
+    const CvsHyp h = cvs_hyp(a, gloc);
+    if (!h.run) return;
+    const Dv priv = cve_dv(s_a + tid, CVA_THREADS);
+    const Dv pw = priv, us = priv.at(24), al = priv.at(40), cw = priv.at(72), wk = priv.at(84);
+    cve_stage_a(a.corr + (size_t)h.b * 5 * a.cap, a.cap, a.samples + h.g * a.m, a.m, cvs_cam(a, h.b), pw, us, al, cw, wk);
+    const Dv out = cve_dv(a.rec + gloc, a.nhp);
+    for (int k = 0; k < 3 * a.m; k++) out[CVH_PW + k] = pw[k];
+    for (int k = 0; k < 2 * a.m; k++) out[CVH_US + k] = us[k];
+    for (int k = 0; k < 4 * a.m; k++) out[CVH_AL + k] = al[k];
+    for (int k = 0; k < 12; k++) out[CVH_CW + k] = cw[k];
+}
+
+__global__ void __launch_bounds__(32 * CVB_WARPS, 8) zp_cvs_null_kernel(CvsArgs a) {
+    extern __shared__ __align__(16) double s_b[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int slot = lane / CVE_G, gl = lane - slot * CVE_G;
+    const long long gloc = ((long long)blockIdx.x * CVB_WARPS + warp) * CVB_HPW + slot;
+    CvsHyp h;
+    h.live = false; h.run = false; h.b = 0; h.g = 0;
+    if (slot < CVB_HPW) h = cvs_hyp(a, gloc);
+    const bool run = h.run;
+    if (!__any_sync(0xffffffffu, run)) return;
+    double* S = s_b + (size_t)(warp * CVB_HPW + (slot < CVB_HPW ? slot : 0)) * CVB_HB;
+    double* A = S; double* W = S + 156; double* V4 = S + 168;
+    int* flags = (int*)(S + 216);
+    const Dv rec = cve_dv(a.rec + gloc, a.nhp);
+    if (run) {                                 // al | us staged where V4 will be written later
+        for (int k = gl; k < 4 * a.m; k += CVE_G) V4[k] = rec[CVH_AL + k];
+        for (int k = gl; k < 2 * a.m; k += CVE_G) V4[32 + k] = rec[CVH_US + k];
+    }
+    __syncwarp();
+    if (run) cve_b_mtm(A, gl, V4, V4 + 32, a.m, cvs_cam(a, h.b));
+    CveJ j = cve_j_make(A, CVE_RS, 12, 12, gl, CVE_G, flags, run);
     cve_j_init(j);
     __syncwarp();
     for (int T = 1;; T++) {
-        if (!j.done) cve_jstep_a<M, HASV>(j, T);
+        if (!j.done) cve_jstep_a<12>(j, T);
         __syncwarp();
         if (!j.done) cve_jstep_c(j, T);
         if (__all_sync(0xffffffffu, j.done)) break;
     }
     __syncwarp();
+    if (run && gl == 0) cve_b_finish(A, W, V4);
+    __syncwarp();
+    if (run) {
+        cve_b_L_rho(V4, gl, rec.at(CVH_CW), rec.at(CVH_L), rec.at(CVH_RHO));
+        for (int k = gl; k < 48; k += CVE_G) rec[CVH_V4 + k] = V4[k];
+    }
 }
 
-__global__ void __launch_bounds__(CVS_THREADS, 7)
-zp_minimal_cv_kernel(const float* __restrict__ corr, int cap, const int32_t* __restrict__ counts,
-                     const double* __restrict__ Kmat, const int32_t* __restrict__ samples, int B, int H, int h0, int hw,
-                     const int32_t* __restrict__ crop_done, int m, double inv_thr, double* __restrict__ hyp_poses,
-                     float* __restrict__ hyp_P, int32_t* __restrict__ hyp_inliers) {
-    extern __shared__ __align__(16) double s_cvs[];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int slot = lane / CVE_G, gl = lane - slot * CVE_G;
-    const long long gloc = ((long long)blockIdx.x * CVS_WARPS + warp) * CVS_HPW + slot;
-    bool live = slot < CVS_HPW && gloc < (long long)B * hw;
-    const int b = live ? (int)(gloc / hw) : 0;
-    const int h = live ? h0 + (int)(gloc - (long long)b * hw) : 0;
-    if (live && crop_done && crop_done[b]) live = false;
-    if (!__any_sync(0xffffffffu, live)) return;
-    double* S = s_cvs + (size_t)(warp * CVS_HPW + (slot < CVS_HPW ? slot : 0)) * CVE_HB;
-    int* flags = (int*)(S + CVE_FLAGS);
-    const size_t g = (size_t)b * H + h;
-    const int32_t* sidx = samples + g * m;
-    const int n = live ? min(counts[b], cap) : 0;
-    bool valid = live && n >= m;
-    if (valid)
-        for (int j = 0; j < m; j++) valid = valid && sidx[j] >= 0 && sidx[j] < n;
-    const bool run = valid;
-    const double* Kb = Kmat + 9 * (size_t)b;
-    CveCam cam{1, 1, 0, 0};
-    if (run) { cam.fu = Kb[0]; cam.fv = Kb[4]; cam.uc = Kb[2]; cam.vc = Kb[5]; }
-    const float* cb = corr + (size_t)b * 5 * cap;
+__global__ void __launch_bounds__(CVC_THREADS) zp_cvs_cand_kernel(CvsArgs a) {
+    extern __shared__ __align__(16) double s_c[];
+    const int tid = threadIdx.x, c = blockIdx.y;
+    const long long gloc = (long long)blockIdx.x * CVC_THREADS + tid;
+    const CvsHyp h = cvs_hyp(a, gloc);
+    if (!h.run) return;
+    const Dv rec = cve_dv(a.rec + gloc, a.nhp);
+    cve_stage_c(c, a.m, cvs_cam(a, h.b), rec.at(CVH_L), rec.at(CVH_RHO), rec.at(CVH_V4), rec.at(CVH_AL), rec.at(CVH_PW),
+                rec.at(CVH_US), cve_dv(s_c + tid, CVC_THREADS), rec.at(CVH_OUT + 13 * c));
+}
 
-    if (run) cve_ph0(S, gl, cb, cap, sidx, m, cam);
-    CveJ j = run && gl == 0 ? cve_j_make(S + CVE_A3, 3, S + CVE_V3, 3, 3, 3, 0, 1, flags) : cve_j_none();
-    cvs_jrun<3, true>(j);
-    if (run) cve_ph1(S, gl, m);
-    j = run && gl == 0 ? cve_j_make(S + CVE_A3, 3, S + CVE_V3, 3, 3, 3, 0, 1, flags) : cve_j_none();
-    cvs_jrun<3, true>(j);
-    if (run) cve_ph2(S, gl);
-    __syncwarp();
-    if (run) cve_ph3(S, gl, m);
-    __syncwarp();
-    if (run) cve_ph4(S, gl, m, cam);
-    j = run ? cve_j_make(S + CVE_A, CVE_RS, nullptr, 0, 12, 12, gl, 6, flags) : cve_j_none();
-    cvs_jrun<12, false>(j);
-    if (run) cve_ph5(S, gl);
-    __syncwarp();
-    if (run) cve_ph6(S, gl);
-    __syncwarp();
-    if (run) cve_ph7(S, gl);
-    {
-        const int c = cve_lane_cand(gl);
-        if (run && c >= 0) {
-            const CveCand k = cve_cand(c);
-            j = cve_j_make(S + CVE_A + k.at, 6, S + CVE_A + k.vt, k.nc, k.nc, 6, gl - k.lane0, k.nl, flags + 4 * c);
-        } else j = cve_j_none();
+__global__ void __launch_bounds__(128) zp_cvs_pick_kernel(CvsArgs a) {
+    const long long gloc = (long long)blockIdx.x * 128 + threadIdx.x;
+    const CvsHyp h = cvs_hyp(a, gloc);
+    if (!h.live) return;
+    double* out = a.hyp_poses + h.g * 12;
+    float4* outP = (float4*)(a.hyp_P + h.g * 24);                // every element twice: (P,P) pairs for FFMA2
+    if (a.hyp_inliers) a.hyp_inliers[h.g] = 0;
+    if (!h.run) {
+        for (int e = 0; e < 12; e++) out[e] = nan("");
+        for (int e = 0; e < 6; e++) outP[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+        return;
     }
-    cvs_jrun<6, true>(j);
-    double betas[4] = {0, 0, 0, 0};
-    if (run) cve_ph8(S, gl, m, betas);
-    __syncwarp();
-    if (run) cve_ph9(S, gl, m, betas);
-    {
-        const int c = cve_lane_cand(gl);
-        if (run && c >= 0 && gl == cve_cand(c).lane0) {
-            double* sl = S + CVE_A + 48 * c;
-            j = cve_j_make(sl + 24, 3, sl + 33, 3, 3, 3, 0, 1, flags + 4 * c);
-        } else j = cve_j_none();
-    }
-    cvs_jrun<3, true>(j);
-    if (run) cve_ph10(S, gl, m, cam);
-    __syncwarp();
-    if (live && gl == 0) {
-        double* out = hyp_poses + g * 12;
-        float4* outP = (float4*)(hyp_P + g * 24);                // every element twice: (P,P) pairs for FFMA2
-        if (hyp_inliers) hyp_inliers[g] = 0;
-        if (!valid) {
-            for (int e = 0; e < 12; e++) out[e] = nan("");
-            for (int e = 0; e < 6; e++) outP[e] = make_float4(0.f, 0.f, 0.f, 0.f);
-        } else {
-            const double* o = cve_pick(S);
-            double pose[12];
-            for (int e = 0; e < 12; e++) { pose[e] = o[e]; out[e] = o[e]; }
-            float P[12];
-            zp_make_P(pose, Kb, inv_thr, P);
-            for (int e = 0; e < 6; e++) outP[e] = make_float4(P[2 * e], P[2 * e], P[2 * e + 1], P[2 * e + 1]);
-        }
-    }
+    const Dv o = cve_dv(a.rec + (size_t)CVH_OUT * a.nhp + gloc, a.nhp);
+    const int N = cve_pick(o);
+    double pose[12];
+    for (int e = 0; e < 12; e++) { pose[e] = o[13 * N + e]; out[e] = pose[e]; }
+    float P[12];
+    zp_make_P(pose, a.K + 9 * (size_t)h.b, a.inv_thr, P);
+    for (int e = 0; e < 6; e++) outP[e] = make_float4(P[2 * e], P[2 * e], P[2 * e + 1], P[2 * e + 1]);
 }
 
 int zp_launch_minimal_cv(zp_ctx* ctx, const float* corr, int cap, const int32_t* counts, const double* K,
                          const int32_t* samples, int B, int H, int h0, int hw, const int32_t* crop_done, int m,
                          float thr_px, double* hyp_poses, float* hyp_P, int32_t* hyp_inliers_to_zero, cudaStream_t st) {
+    const int smem_a = CVA_THREADS * CVA_PRIV * (int)sizeof(double);
+    const int smem_b = CVB_WARPS * CVB_HPW * CVB_HB * (int)sizeof(double);
+    const int smem_c = CVC_THREADS * CVC_PRIV * (int)sizeof(double);
     if (!ctx->cvs_attr_set) {
-        ZP_CUDA(ctx, cudaFuncSetAttribute(zp_minimal_cv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CVS_SMEM));
+        ZP_CUDA(ctx, cudaFuncSetAttribute(zp_cvs_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_a));
+        ZP_CUDA(ctx, cudaFuncSetAttribute(zp_cvs_null_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_b));
+        ZP_CUDA(ctx, cudaFuncSetAttribute(zp_cvs_cand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_c));
         ctx->cvs_attr_set = true;
     }
     const long long total = (long long)B * hw;
-    const int per_cta = CVS_WARPS * CVS_HPW;
-    const int grid = (int)((total + per_cta - 1) / per_cta);
+    const int nhp = (int)((total + 63) / 64 * 64);
+    const size_t need = (size_t)CVH_DOUBLES * nhp * sizeof(double);
+    if (need > ctx->cvws_bytes) {       // growing must not race with work still using the old buffer
+        ZP_CUDA(ctx, cudaDeviceSynchronize());
+        if (ctx->cvws) cudaFree(ctx->cvws);
+        ctx->cvws = nullptr; ctx->cvws_bytes = 0;
+        ZP_CUDA(ctx, cudaMalloc(&ctx->cvws, need + need / 8));
+        ctx->cvws_bytes = need + need / 8;
+    }
+    CvsArgs a;
+    a.corr = corr; a.cap = cap; a.counts = counts; a.K = K; a.samples = samples; a.B = B; a.H = H; a.h0 = h0; a.hw = hw;
+    a.crop_done = crop_done; a.m = m; a.inv_thr = 1.0 / (double)thr_px; a.rec = (double*)ctx->cvws; a.nhp = nhp;
+    a.hyp_poses = hyp_poses; a.hyp_P = hyp_P; a.hyp_inliers = hyp_inliers_to_zero;
     ZP_TIME_BEGIN(ctx, st);
-    zp_minimal_cv_kernel<<<grid, CVS_THREADS, CVS_SMEM, st>>>(corr, cap, counts, K, samples, B, H, h0, hw, crop_done, m,
-                                                               1.0 / (double)thr_px, hyp_poses, hyp_P, hyp_inliers_to_zero);
-    ZP_CHECK_LAUNCH(ctx, "zp_minimal_cv_kernel");
+    zp_cvs_prep_kernel<<<(unsigned)((total + CVA_THREADS - 1) / CVA_THREADS), CVA_THREADS, smem_a, st>>>(a);
+    ZP_CHECK_LAUNCH(ctx, "zp_cvs_prep_kernel");
+    const int per_cta = CVB_WARPS * CVB_HPW;
+    ZP_TIME_BEGIN(ctx, st);
+    zp_cvs_null_kernel<<<(unsigned)((total + per_cta - 1) / per_cta), 32 * CVB_WARPS, smem_b, st>>>(a);
+    ZP_CHECK_LAUNCH(ctx, "zp_cvs_null_kernel");
+    ZP_TIME_BEGIN(ctx, st);
+    zp_cvs_cand_kernel<<<dim3((unsigned)((total + CVC_THREADS - 1) / CVC_THREADS), 3), CVC_THREADS, smem_c, st>>>(a);
+    ZP_CHECK_LAUNCH(ctx, "zp_cvs_cand_kernel");
+    ZP_TIME_BEGIN(ctx, st);
+    zp_cvs_pick_kernel<<<(unsigned)((total + 127) / 128), 128, 0, st>>>(a);
+    ZP_CHECK_LAUNCH(ctx, "zp_cvs_pick_kernel");
     return 0;
 }
