@@ -15,19 +15,25 @@ extern "C" int cve_host_epnp(const float* corr, int cap, const int32_t* idx, int
     // stage B, six emulated lanes
     int flags[4] = {0, 0, 0, 0};
     CveJ j[CVE_G];
-    for (int l = 0; l < CVE_G; l++) cve_b_mtm(A.data(), l, r + CVH_AL, r + CVH_US, m, cam);
+    double sums[CVE_G][13];
+    for (int l = 0; l < CVE_G; l++) cve_b_mtm_table(A.data(), l, r + CVH_AL, r + CVH_US, m, cam);
+    for (int l = 0; l < CVE_G; l++) cve_b_mtm_sums(A.data(), l, r + CVH_AL, r + CVH_US, m, cam, sums[l]);
+    for (int l = 0; l < CVE_G; l++) cve_b_mtm_store(A.data(), l, sums[l]);
     for (int l = 0; l < CVE_G; l++) j[l] = cve_j_make(A.data(), CVE_RS, 12, 12, l, CVE_G, flags, true);
     for (int l = 0; l < CVE_G; l++) cve_j_init(j[l]);
     int T = 1;
     for (;; T++) {
-        for (int l = 0; l < CVE_G; l++) if (!j[l].done) cve_jstep_a<12>(j[l], T);
-        for (int l = 0; l < CVE_G; l++) if (!j[l].done) cve_jstep_c(j[l], T);
+        for (int l = 0; l < CVE_G; l++) if (!j[l].done) cve_jstep_a<12, 12>(j[l], T);
+        for (int l = 0; l < CVE_G; l++) if (!j[l].done) cve_jstep_c<12>(j[l], T);
         bool all = true;
         for (int l = 0; l < CVE_G; l++) all = all && j[l].done;
         if (all) break;
     }
     if (steps) steps[0] = T;
-    cve_b_finish(A.data(), W.data(), r + CVH_V4);
+    for (int l = 0; l < CVE_G; l++) cve_b_norms(A.data(), l, W.data());
+    bool fast = true;
+    for (int l = 0; l < CVE_G; l++) fast = cve_b_tail(A.data(), l, W.data(), r + CVH_V4) && fast;
+    if (!fast) cve_b_finish(A.data(), W.data(), r + CVH_V4);
     for (int l = 0; l < CVE_G; l++) cve_b_L_rho(r + CVH_V4, l, cve_dv(r + CVH_CW, 1), cve_dv(r + CVH_L, 1), cve_dv(r + CVH_RHO, 1));
     for (int c = 0; c < 3; c++)
         cve_stage_c(c, m, cam, cve_dv(r + CVH_L, 1), cve_dv(r + CVH_RHO, 1), cve_dv(r + CVH_V4, 1), cve_dv(r + CVH_AL, 1),

@@ -42,10 +42,12 @@ def main():
     res = eng.ransac(corr, counts, Ks, return_details=True)
     poses = res["poses"].cpu().numpy()
     best = res["best_idx"].cpu().numpy()
+    iters = res["iters_run"].cpu().numpy()
+    ninl = res["n_inliers"].cpu().numpy()
     hyp_inl = res["hyp_inliers"].cpu().numpy()
     im = res["inlier_mask"].cpu().numpy().astype(bool)
     corr_h, counts_h = corr.cpu().numpy(), counts.cpu().numpy()
-    rot, tr, rot_gt_dev, rot_gt_ref, jac, same_w, top_rel = [], [], [], [], [], [], []
+    rot, tr, rot_gt_dev, rot_gt_ref, jac, same_w, top_rel, same_it, misses = [], [], [], [], [], [], [], [], []
     dec_ok = 0
     pts = tab[::64]
     add_dev = add_ref = 0
@@ -70,6 +72,11 @@ def main():
         jac.append((dm & ref_mask).sum() / max(1, (dm | ref_mask).sum()))
         _, _, _, _, info = cvransac.solve_pnp_ransac(xyz, uv, c["K"])
         same_w.append(int(best[i] == info.get("best", -2)))
+        same_it.append(int(iters[i] == info["iters_run"]))
+        if not (rot[-1] <= 0.05 and tr[-1] <= 0.5) or not same_w[-1]:
+            misses.append({"crop": i, "rot_deg": float(rot[-1]), "trans_mm": float(tr[-1]), "winner_device": int(best[i]),
+                           "winner_cv2": int(info.get("best", -2)), "inliers_device": int(ninl[i]),
+                           "inliers_cv2": int(0 if inl is None else len(inl)), "n": int(len(uv))})
         cref = np.array(info["counts"]); cdev = hyp_inl[i, :len(cref)]
         good = cref >= 0.5 * cref.max()
         top_rel.append(float(np.abs(cdev[good] - cref[good]).max() / cref.max()))
@@ -84,6 +91,8 @@ def main():
                         "trans_mm": {"median": float(np.median(tr)), "p90": float(np.percentile(tr, 90)), "max": float(tr.max())},
                         "within_0.05deg_0.5mm": int(within.sum()), "pass_rate": float(within.mean())},
         "same_winning_hypothesis": int(np.sum(same_w)),
+        "same_iteration_count": int(np.sum(same_it)),
+        "crops_off_tolerance_or_other_winner": misses[:20],
         "inlier_set_jaccard": {"median": float(np.median(jac)), "min": float(np.min(jac))},
         "good_hypothesis_count_rel_diff_max": {"median": float(np.median(top_rel)), "max": float(np.max(top_rel))},
         "rot_err_vs_gt_deg": {"device_median": float(np.median(rot_gt_dev)), "reference_median": float(np.median(rot_gt_ref))},

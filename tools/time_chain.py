@@ -27,7 +27,10 @@ def main():
         d_logits = torch.from_numpy(logits).cuda()
         d_obj = torch.from_numpy(obj.astype(np.int32)).cuda()
         corr, counts = eng.decode(d_logits, bboxes, d_obj)
-        for solver, plan in (("cv2", [150]), ("cv2", None), ("cv2", [32]), ("cv2", [48, 102]), ("fast", [150]), ("fast", None)):
+        plans = (("cv2", [150]), ("cv2", None), ("cv2", [32]), ("cv2", [48, 102]), ("fast", [150]), ("fast", None))
+        if os.environ.get("TC_QUICK"):
+            plans = plans[:1]
+        for solver, plan in plans:
             eng.set_solver(solver)
             eng.set_waves(plan)
             fn = lambda: eng.ransac(corr, counts, Ks, H=150, m=5, thr=2.0)
@@ -47,7 +50,7 @@ def main():
             torch.cuda.synchronize()
             k = {n: eng.kernel_time(n) for n in NAMES}
             eng.set_kernel_timing(False)
-            row = {"crops": C, "solver": solver, "waves": plan, "chain_ms_median": round(float(np.median(tot)), 4),
+            row = {"env": {k: v for k, v in os.environ.items() if k.startswith("ZP_")}, "crops": C, "solver": solver, "waves": plan, "chain_ms_median": round(float(np.median(tot)), 4),
                    "kernel_us_per_call": {n: round(v[0] * v[1] * 1e3 / 10, 1) for n, v in k.items() if v[1]},
                    "launches_per_call": {n: v[1] // 10 for n, v in k.items() if v[1]}}
             print(json.dumps(row), flush=True)

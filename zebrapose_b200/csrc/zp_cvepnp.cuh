@@ -78,6 +78,13 @@ ZP_HD inline double cve_hypot(double a, double b) {
 // ------------------------------------------------------------------------------------------------------------------
 // one Jacobi pair: rows Ai, Aj of length M (and rows Vi, Vj of length n of the accumulated rotations)
 // ------------------------------------------------------------------------------------------------------------------
+// The library's control flow (skip test, two-branch hypot, two-branch c/s) is evaluated here WITHOUT divergent branches:
+// the lanes of a warp work on different pairs / hypotheses, and a divergent branch around a division + square root makes
+// the warp pay both sides.  Every lane still performs exactly the operations of its own branch:
+//   hypot(p, beta)  = big * sqrt(1 + (small/big)^2) with big/small = max/min(|p|, |beta|)  (0 when both are 0)
+//   beta < 0:  s = sqrt(((gamma-beta)*0.5) / gamma), c = p / (gamma*s*2);  else c = sqrt((gamma+beta) / (gamma*2)), s = p / (gamma*c*2)
+//   skip test |p| <= eps*sqrt(a*b): decided from p*p against eps^2*(a*b) when the two differ by more than 1e-9 relative
+//   (the rounding of the exact expression is 4 ulp at most); the square root is only taken in between or near underflow.
 template <int M, bool HASV>
 ZP_HD inline bool cve_pair(Dv Ai, Dv Aj, Dv Vi, Dv Vj, int n) {
     const double eps = DBL_EPSILON * 10;
@@ -87,18 +94,31 @@ ZP_HD inline bool cve_pair(Dv Ai, Dv Aj, Dv Vi, Dv Vj, int n) {
     double p = 0, a = 0, b = 0;
 #pragma unroll
     for (int k = 0; k < M; k++) { p += ri[k] * rj[k]; a += ri[k] * ri[k]; b += rj[k] * rj[k]; }
-    if (fabs(p) <= eps * sqrt(a * b)) return false;
-    p *= 2;
-    const double beta = a - b, gamma = cve_hypot(p, beta);
-    double c, s;
-    if (beta < 0) {
-        const double delta = (gamma - beta) * 0.5;
-        s = sqrt(delta / gamma);
-        c = p / (gamma * s * 2);
-    } else {
-        c = sqrt((gamma + beta) / (gamma * 2));
-        s = p / (gamma * c * 2);
+    {
+        const double ab = a * b, pp = p * p, lim = ab * (eps * eps);
+        bool skip;
+        if (lim > 1e-280 && ab < 1e300 && pp < 1e300 && pp > lim * (1 + 1e-9)) skip = false;
+        else if (lim > 1e-280 && ab < 1e300 && pp < lim * (1 - 1e-9)) skip = true;
+        else skip = fabs(p) <= eps * sqrt(ab);
+        if (skip) return false;
     }
+    p *= 2;
+    const double beta = a - b;
+    double gamma;
+    {
+        const double x = fabs(p), y = fabs(beta);
+        const bool xg = x > y;
+        const double big = xg ? x : y, small = xg ? y : x;
+        const double q = small / big;
+        const double r = big * sqrt(1 + q * q);
+        gamma = (xg || y > 0) ? r : 0.0;
+    }
+    const bool neg = beta < 0;
+    const double num = neg ? (gamma - beta) * 0.5 : gamma + beta;
+    const double den = neg ? gamma : gamma * 2;
+    const double first = sqrt(num / den);
+    const double second = p / (gamma * first * 2);
+    const double c = neg ? second : first, s = neg ? first : second;
 #pragma unroll
     for (int k = 0; k < M; k++) {
         const double t0 = c * ri[k] + s * rj[k];
@@ -157,9 +177,9 @@ ZP_HD inline void cve_j_init(const CveJ& j) {
 }
 
 // step T (1, 2, ...): this lane's pair, if it has one.  Pairs of sweep s = (T - tau)/n with i + j = tau; two sweeps overlap.
-template <int M>
+template <int M, int N>
 ZP_HD inline void cve_jstep_a(CveJ& j, int T) {
-    const int n = j.n;
+    constexpr int n = N;
     const int ta = (T - 1) % n + 1, sa = (T - ta) / n;
     const int tb = ta + n, sb = sa - 1;
     const int lo_a = ta - n + 1 > 0 ? ta - n + 1 : 0;
@@ -178,8 +198,9 @@ ZP_HD inline void cve_jstep_a(CveJ& j, int T) {
 }
 
 // after the barrier that follows step T: if a sweep completed at T, stop when it rotated nothing (or at the sweep cap)
+template <int N>
 ZP_HD inline void cve_jstep_c(CveJ& j, int T) {
-    const int n = j.n;
+    constexpr int n = N;
     const int num = T - (2 * n - 3);
     if (num < 0 || num % n != 0) return;
     const int s = num / n;
@@ -403,30 +424,125 @@ ZP_HD inline void cve_stage_a(const float* corr, int cap, const int32_t* idx, in
 // ------------------------------------------------------------------------------------------------------------------
 // stage B pieces (A = the hypothesis' [12][13] matrix in shared memory, unit stride)
 // ------------------------------------------------------------------------------------------------------------------
-// lane l of the six: its 13 of the 78 entries of M^T M.  Entry (i, j >= i) = sequential sum over the 2m rows of M (rows
-// [a fu, 0, a (uc-u)] and [0, a fv, a (vc-v)] per point); al [m][4] and us [m][2] in shared memory, unit stride
-ZP_HD inline void cve_b_mtm(double* A, int lane, const double* al, const double* us, int m, const CveCam& cam) {
-    for (int e = lane; e < 78; e += CVE_G) {
+// M^T M by the six lanes: entry (i, j >= i) = sequential sum over the 2m rows of M (per point the rows [a fu, 0, a (uc-u)]
+// and [0, a fv, a (vc-v)]), 13 entries per lane.  al [m][4] and us [m][2] in shared memory, unit stride.
+// Two steps with a group barrier between them: (1) the rows of M are tabulated once -- in the A region itself, which is
+// free until the entries are written -- as X1[x][p][c] / X2[x][p][c] (x = column type 0..2, explicit zero planes), so an
+// entry costs 4 loads + 2 multiplies + 2 additions per point and no selects; (2) entries accumulated in registers, then
+// (after the barrier of the caller) written.  m > 6 does not fit the region and takes the direct form.
+ZP_HD inline bool cve_b_mtm_tabulated(int m) { return 24 * m <= 12 * CVE_RS; }
+
+ZP_HD inline void cve_b_mtm_table(double* A, int lane, const double* al, const double* us, int m, const CveCam& cam) {
+    if (!cve_b_mtm_tabulated(m)) return;
+    double* X1 = A; double* X2 = A + 12 * m;
+    for (int t = lane; t < 4 * m; t += CVE_G) {
+        const int p = t >> 2;
+        const double a = al[t];
+        const double du = cam.uc - us[2 * p], dv = cam.vc - us[2 * p + 1];
+        X1[t] = a * cam.fu; X1[4 * m + t] = 0.0; X1[8 * m + t] = a * du;
+        X2[t] = 0.0; X2[4 * m + t] = a * cam.fv; X2[8 * m + t] = a * dv;
+    }
+}
+
+// returns this lane's 13 sums in out[13] (entry e = lane + 6 t)
+ZP_HD inline void cve_b_mtm_sums(const double* A, int lane, const double* al, const double* us, int m, const CveCam& cam,
+                                 double* out) {
+    const bool tab = cve_b_mtm_tabulated(m);
+    const double* X1 = A; const double* X2 = A + 12 * m;
+#pragma unroll
+    for (int t = 0; t < 13; t++) {
+        const int e = lane + CVE_G * t;
         int i = 0, r = e;
         while (r >= 12 - i) { r -= 12 - i; i++; }
         const int j = i + r;
         const int ci = i / 3, xi = i - 3 * ci, cj = j / 3, xj = j - 3 * cj;
         double s = 0;
-        for (int p = 0; p < m; p++) {
-            const double ai = al[4 * p + ci], aj = al[4 * p + cj];
-            const double du = cam.uc - us[2 * p], dv = cam.vc - us[2 * p + 1];
-            const double r1i = xi == 0 ? ai * cam.fu : xi == 1 ? 0.0 : ai * du;
-            const double r1j = xj == 0 ? aj * cam.fu : xj == 1 ? 0.0 : aj * du;
-            const double r2i = xi == 0 ? 0.0 : xi == 1 ? ai * cam.fv : ai * dv;
-            const double r2j = xj == 0 ? 0.0 : xj == 1 ? aj * cam.fv : aj * dv;
-            s += r1i * r1j;
-            s += r2i * r2j;
+        if (tab) {
+            const double *p1i = X1 + 4 * m * xi + ci, *p1j = X1 + 4 * m * xj + cj, *p2i = X2 + 4 * m * xi + ci, *p2j = X2 + 4 * m * xj + cj;
+            for (int p = 0; p < m; p++) {
+                s += p1i[4 * p] * p1j[4 * p];
+                s += p2i[4 * p] * p2j[4 * p];
+            }
+        } else {
+            for (int p = 0; p < m; p++) {
+                const double ai = al[4 * p + ci], aj = al[4 * p + cj];
+                const double du = cam.uc - us[2 * p], dv = cam.vc - us[2 * p + 1];
+                const double r1i = xi == 0 ? ai * cam.fu : xi == 1 ? 0.0 : ai * du;
+                const double r1j = xj == 0 ? aj * cam.fu : xj == 1 ? 0.0 : aj * du;
+                const double r2i = xi == 0 ? 0.0 : xi == 1 ? ai * cam.fv : ai * dv;
+                const double r2j = xj == 0 ? 0.0 : xj == 1 ? aj * cam.fv : aj * dv;
+                s += r1i * r1j;
+                s += r2i * r2j;
+            }
         }
-        A[i * CVE_RS + j] = s; A[j * CVE_RS + i] = s;
+        out[t] = s;
     }
 }
 
-// lane 0: finish the SVD, keep rows 11, 10, 9, 8 of U^T in V4 [4][12] (unit stride, shared memory); W: 12 doubles
+ZP_HD inline void cve_b_mtm_store(double* A, int lane, const double* in) {
+#pragma unroll
+    for (int t = 0; t < 13; t++) {
+        const int e = lane + CVE_G * t;
+        int i = 0, r = e;
+        while (r >= 12 - i) { r -= 12 - i; i++; }
+        const int j = i + r;
+        A[i * CVE_RS + j] = in[t]; A[j * CVE_RS + i] = in[t];
+    }
+}
+
+// the tail of the 12x12 SVD, of which only rows 11, 10, 9, 8 of the sorted, normalised U^T are needed:
+//   (1) lane l: singular values of rows l and l + 6 (sequential sums) -> W          [group barrier]
+//   (2) every lane: the library's selection sort replayed on (W, index) in registers; V4 row q = row perm[11-q] * (1/W)
+//       written by lanes 0..3.  Returns false when a singular value is not > DBL_MIN (zero or NaN): the pseudo-random-row
+//       branch needs the whole sorted matrix, so the caller then runs cve_b_finish on one lane instead.
+ZP_HD inline void cve_b_norms(const double* A, int lane, double* W) {
+    for (int r = lane; r < 12; r += CVE_G) {
+        double sd = 0;
+#pragma unroll
+        for (int k = 0; k < 12; k++) { const double t = A[r * CVE_RS + k]; sd += t * t; }
+        W[r] = sqrt(sd);
+    }
+}
+
+ZP_HD inline bool cve_b_tail(const double* A, int lane, const double* W, double* V4) {
+    double w[12];
+    int idx[12];
+    bool ok = true;
+#pragma unroll
+    for (int i = 0; i < 12; i++) { w[i] = W[i]; idx[i] = i; ok = ok && w[i] > DBL_MIN; }
+    if (!ok) return false;
+#pragma unroll
+    for (int i = 0; i < 11; i++) {
+        double wj = w[i];
+        int j = i;
+#pragma unroll
+        for (int k = i + 1; k < 12; k++) { const bool lt = wj < w[k]; wj = lt ? w[k] : wj; j = lt ? k : j; }
+        // swap positions i and j (j is dynamic: a select per later position)
+        const double wi = w[i];
+        const int ii = idx[i];
+        int ij = ii;
+#pragma unroll
+        for (int k = i + 1; k < 12; k++) {
+            const bool hit = k == j;
+            ij = hit ? idx[k] : ij;
+            w[k] = hit ? wi : w[k];
+            idx[k] = hit ? ii : idx[k];
+        }
+        w[i] = wj; idx[i] = ij;
+    }
+    if (lane < 4) {
+        int src = 0;
+        double ws = 0;
+#pragma unroll
+        for (int i = 8; i < 12; i++) if (11 - i == lane) { src = idx[i]; ws = w[i]; }
+        const double s = 1 / ws;
+#pragma unroll
+        for (int k = 0; k < 12; k++) V4[lane * 12 + k] = A[src * CVE_RS + k] * s;
+    }
+    return true;
+}
+
+// one lane: the generic tail (any singular values); keeps rows 11, 10, 9, 8 of U^T in V4 [4][12]; W: 12 doubles
 ZP_HD inline void cve_b_finish(double* A, double* W, double* V4) {
     cve_finish(cve_dv(A, 1), CVE_RS, cve_dv(W, 1), cve_dv(nullptr, 1), 0, false, 12, 12, 12);
     for (int q = 0; q < 4; q++)
@@ -455,7 +571,8 @@ ZP_HD inline void cve_b_L_rho(const double* V4, int r, Dv cw, Dv L, Dv rho) {
 
 // ------------------------------------------------------------------------------------------------------------------
 // stage C: one beta initialisation c (0, 1, 2 = OpenCV's N = 1, 2, 3) of one hypothesis.  Read-only views: L, rho, V4,
-// al, pw, us.  wk: 84 doubles of scratch (At 30 | Vt 25 | w 5 | pcs 24).  out: R[9] t[3] err (13 doubles).
+// al, pw, us.  wk: 60 doubles of scratch (least squares: At 30 | Vt 25 | w 5; then A3 9 | V3 9 | W3 3 | - | pcs 24).
+// out: R[9] t[3] err (13 doubles).
 // ------------------------------------------------------------------------------------------------------------------
 template <int NC>
 ZP_HD inline void cve_c_solve(Dv L, Dv rho, Dv wk, int c, double* x) {
@@ -489,7 +606,7 @@ ZP_HD inline void cve_stage_c(int c, int m, const CveCam& cam, Dv L, Dv rho, Dv 
     }
     cve_gauss_newton(L, rho, be);
     // camera-frame control points and points, sign
-    const Dv A3 = wk, V3 = wk.at(9), W3 = wk.at(18), pcs = wk.at(60);
+    const Dv A3 = wk, V3 = wk.at(9), W3 = wk.at(18), pcs = wk.at(24);
     double ccs[4][3];
     for (int i = 0; i < 4; i++) ccs[i][0] = ccs[i][1] = ccs[i][2] = 0.0;
     for (int i = 0; i < 4; i++)

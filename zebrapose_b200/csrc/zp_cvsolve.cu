@@ -18,20 +18,22 @@
 #include "zp_common.cuh"
 #include "zp_cvepnp.cuh"
 #include "zp_proj.cuh"
+#include <stdlib.h>
 
 constexpr int CVA_THREADS = 64;                // stage A: private data 117 doubles per thread, interleaved over the CTA
 constexpr int CVA_PRIV = 24 + 16 + 32 + 12 + 33;
 constexpr int CVB_HPW = 5;                     // stage B: hypotheses per warp (5 x 6 lanes; lanes 30 and 31 idle)
 constexpr int CVB_WARPS = 2;
 constexpr int CVB_HB = 219;                    // doubles per hypothesis: A 156 | W 12 | V4 48 (first: al 32 | us 16) | flags 2 (+1: odd stride)
-constexpr int CVC_THREADS = 64;                // stage C: 84 doubles of scratch per thread
-constexpr int CVC_PRIV = 84;
+constexpr int CVC_THREADS = 64;                // stage C: 60 doubles of scratch per thread
+constexpr int CVC_PRIV = 60;
 
 struct CvsArgs {
     const float* corr; int cap; const int32_t* counts; const double* K; const int32_t* samples;
     int B, H, h0, hw; const int32_t* crop_done; int m; double inv_thr;
     double* rec; int nhp;                      // hand-off records: field f of local hypothesis g at rec[f * nhp + g]
     double* hyp_poses; float* hyp_P; int32_t* hyp_inliers;
+    unsigned long long* dbg;                   // profiling aid (zp_debug_buffer): phase stamps of warp 0 of CTA 0 of stage B
 };
 
 // local hypothesis index -> (crop, global hypothesis index, must it be solved?)
@@ -75,7 +77,8 @@ __global__ void __launch_bounds__(CVA_THREADS) zp_cvs_prep_kernel(CvsArgs a) {
     for (int k = 0; k < 12; k++) out[CVH_CW + k] = cw[k];
 }
 
-__global__ void __launch_bounds__(32 * CVB_WARPS, 8) zp_cvs_null_kernel(CvsArgs a) {
+template <int MINB>
+__global__ void __launch_bounds__(32 * CVB_WARPS, MINB) zp_cvs_null_kernel(CvsArgs a) {
     extern __shared__ __align__(16) double s_b[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int slot = lane / CVE_G, gl = lane - slot * CVE_G;
@@ -89,31 +92,52 @@ __global__ void __launch_bounds__(32 * CVB_WARPS, 8) zp_cvs_null_kernel(CvsArgs 
     double* A = S; double* W = S + 156; double* V4 = S + 168;
     int* flags = (int*)(S + 216);
     const Dv rec = cve_dv(a.rec + gloc, a.nhp);
+    const bool stamp = a.dbg && blockIdx.x == 0 && tid == 0;
+    if (stamp) a.dbg[0] = clock64();
     if (run) {                                 // al | us staged where V4 will be written later
         for (int k = gl; k < 4 * a.m; k += CVE_G) V4[k] = rec[CVH_AL + k];
         for (int k = gl; k < 2 * a.m; k += CVE_G) V4[32 + k] = rec[CVH_US + k];
     }
     __syncwarp();
-    if (run) cve_b_mtm(A, gl, V4, V4 + 32, a.m, cvs_cam(a, h.b));
+    {
+        const CveCam cam = cvs_cam(a, h.b);
+        double sums[13];
+        if (run) cve_b_mtm_table(A, gl, V4, V4 + 32, a.m, cam);
+        __syncwarp();
+        if (run) cve_b_mtm_sums(A, gl, V4, V4 + 32, a.m, cam, sums);
+        __syncwarp();
+        if (run) cve_b_mtm_store(A, gl, sums);
+    }
     CveJ j = cve_j_make(A, CVE_RS, 12, 12, gl, CVE_G, flags, run);
     cve_j_init(j);
     __syncwarp();
-    for (int T = 1;; T++) {
-        if (!j.done) cve_jstep_a<12>(j, T);
+    if (stamp) a.dbg[1] = clock64();
+    int T = 1;
+    for (;; T++) {
+        if (!j.done) cve_jstep_a<12, 12>(j, T);
         __syncwarp();
-        if (!j.done) cve_jstep_c(j, T);
+        if (!j.done) cve_jstep_c<12>(j, T);
         if (__all_sync(0xffffffffu, j.done)) break;
     }
     __syncwarp();
-    if (run && gl == 0) cve_b_finish(A, W, V4);
+    if (stamp) { a.dbg[2] = clock64(); a.dbg[5] = (unsigned long long)T; }
+    if (run) cve_b_norms(A, gl, W);
     __syncwarp();
+    {
+        const bool fast = run ? cve_b_tail(A, gl, W, V4) : true;
+        if (run && !fast && gl == 0) cve_b_finish(A, W, V4);      // a zero or non-finite singular value (degenerate sample)
+    }
+    __syncwarp();
+    if (stamp) a.dbg[3] = clock64();
     if (run) {
         cve_b_L_rho(V4, gl, rec.at(CVH_CW), rec.at(CVH_L), rec.at(CVH_RHO));
         for (int k = gl; k < 48; k += CVE_G) rec[CVH_V4 + k] = V4[k];
     }
+    if (stamp) a.dbg[4] = clock64();
 }
 
-__global__ void __launch_bounds__(CVC_THREADS) zp_cvs_cand_kernel(CvsArgs a) {
+template <int MINB>
+__global__ void __launch_bounds__(CVC_THREADS, MINB) zp_cvs_cand_kernel(CvsArgs a) {
     extern __shared__ __align__(16) double s_c[];
     const int tid = threadIdx.x, c = blockIdx.y;
     const long long gloc = (long long)blockIdx.x * CVC_THREADS + tid;
@@ -153,8 +177,16 @@ int zp_launch_minimal_cv(zp_ctx* ctx, const float* corr, int cap, const int32_t*
     const int smem_c = CVC_THREADS * CVC_PRIV * (int)sizeof(double);
     if (!ctx->cvs_attr_set) {
         ZP_CUDA(ctx, cudaFuncSetAttribute(zp_cvs_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_a));
-        ZP_CUDA(ctx, cudaFuncSetAttribute(zp_cvs_null_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_b));
-        ZP_CUDA(ctx, cudaFuncSetAttribute(zp_cvs_cand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_c));
+        ZP_CUDA(ctx, cudaFuncSetAttribute(zp_cvs_null_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_b));
+        ZP_CUDA(ctx, cudaFuncSetAttribute(zp_cvs_null_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_b));
+        ZP_CUDA(ctx, cudaFuncSetAttribute(zp_cvs_null_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_b));
+        ZP_CUDA(ctx, cudaFuncSetAttribute(zp_cvs_cand_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_c));
+        ZP_CUDA(ctx, cudaFuncSetAttribute(zp_cvs_cand_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_c));
+        ZP_CUDA(ctx, cudaFuncSetAttribute(zp_cvs_cand_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_c));
+        const char* e = getenv("ZP_CVB_MINB");      // tuning aids: resident CTAs per SM of stage B (8 | 10 | 12) and C (4 | 6 | 8)
+        ctx->cvb_minb = e ? atoi(e) : 0;
+        e = getenv("ZP_CVC_MINB");
+        ctx->cvc_minb = e ? atoi(e) : 0;
         ctx->cvs_attr_set = true;
     }
     const long long total = (long long)B * hw;
@@ -171,15 +203,24 @@ int zp_launch_minimal_cv(zp_ctx* ctx, const float* corr, int cap, const int32_t*
     a.corr = corr; a.cap = cap; a.counts = counts; a.K = K; a.samples = samples; a.B = B; a.H = H; a.h0 = h0; a.hw = hw;
     a.crop_done = crop_done; a.m = m; a.inv_thr = 1.0 / (double)thr_px; a.rec = (double*)ctx->cvws; a.nhp = nhp;
     a.hyp_poses = hyp_poses; a.hyp_P = hyp_P; a.hyp_inliers = hyp_inliers_to_zero;
+    a.dbg = (unsigned long long*)ctx->dbg_buf;
     ZP_TIME_BEGIN(ctx, st);
     zp_cvs_prep_kernel<<<(unsigned)((total + CVA_THREADS - 1) / CVA_THREADS), CVA_THREADS, smem_a, st>>>(a);
     ZP_CHECK_LAUNCH(ctx, "zp_cvs_prep_kernel");
     const int per_cta = CVB_WARPS * CVB_HPW;
     ZP_TIME_BEGIN(ctx, st);
-    zp_cvs_null_kernel<<<(unsigned)((total + per_cta - 1) / per_cta), 32 * CVB_WARPS, smem_b, st>>>(a);
+    const unsigned grid_b = (unsigned)((total + per_cta - 1) / per_cta);
+    const int mb = ctx->cvb_minb ? ctx->cvb_minb : 10;     // measured (profiles/r2e_tune.jsonl): 8 | 10 | 12 -> 1958 | 1840 | 1861 us at 1024 crops
+    if (mb >= 12) zp_cvs_null_kernel<12><<<grid_b, 32 * CVB_WARPS, smem_b, st>>>(a);
+    else if (mb >= 10) zp_cvs_null_kernel<10><<<grid_b, 32 * CVB_WARPS, smem_b, st>>>(a);
+    else zp_cvs_null_kernel<8><<<grid_b, 32 * CVB_WARPS, smem_b, st>>>(a);
     ZP_CHECK_LAUNCH(ctx, "zp_cvs_null_kernel");
     ZP_TIME_BEGIN(ctx, st);
-    zp_cvs_cand_kernel<<<dim3((unsigned)((total + CVC_THREADS - 1) / CVC_THREADS), 3), CVC_THREADS, smem_c, st>>>(a);
+    const dim3 grid_c((unsigned)((total + CVC_THREADS - 1) / CVC_THREADS), 3);
+    const int mc = ctx->cvc_minb ? ctx->cvc_minb : 6;      // 4 | 6 | 8 -> 811 | 691 | 749 us at 1024 crops, 81 | 87 | 92 at 64
+    if (mc >= 8) zp_cvs_cand_kernel<8><<<grid_c, CVC_THREADS, smem_c, st>>>(a);
+    else if (mc >= 6) zp_cvs_cand_kernel<6><<<grid_c, CVC_THREADS, smem_c, st>>>(a);
+    else zp_cvs_cand_kernel<4><<<grid_c, CVC_THREADS, smem_c, st>>>(a);
     ZP_CHECK_LAUNCH(ctx, "zp_cvs_cand_kernel");
     ZP_TIME_BEGIN(ctx, st);
     zp_cvs_pick_kernel<<<(unsigned)((total + 127) / 128), 128, 0, st>>>(a);
