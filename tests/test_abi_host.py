@@ -32,13 +32,35 @@ def test_header_symbols_exported():
         assert re.search(r" T %s$" % name, out, re.M), name
 
 
+def _kernel_sass(sass, name):
+    """SASS text of the kernels whose mangled name contains `name`"""
+    out, on = [], False
+    for line in sass.splitlines():
+        if "Function :" in line:
+            on = name in line
+        if on:
+            out.append(line)
+    return "\n".join(out)
+
+
 def test_sass_is_blackwell_native():
-    """the scoring kernel uses TMA bulk copies (UBLKCP) and the decode kernel cluster barriers, compiled for sm_100a"""
+    """the kernels advertised on Blackwell machinery really contain it: the fused head on TMA tensor loads (UTMALDG),
+    tcgen05 MMA (UTCHMMA) and TMEM loads (LDTM); scoring on 1-D TMA bulk copies (UBLKCP) and packed FFMA2; the exact
+    solver's translation unit has no contracted multiply-add outside the division / square-root sequences"""
     lib_path = _built()
     sass = subprocess.run(["cuobjdump", "-sass", lib_path], capture_output=True, text=True).stdout
     assert "sm_100a" in sass
-    assert "UBLKCP" in sass            # cp.async.bulk (TMA 1-D)
-    assert "UCGABAR" in sass or "CGABAR" in sass or "BAR.SYNC" in sass
+    head = _kernel_sass(sass, "zp_head_codes_kernel")
+    for op in ("UTMALDG", "UTCHMMA", "LDTM"):
+        assert op in head, op
+    score = _kernel_sass(sass, "zp_score_kernel")
+    assert "UBLKCP" in score and "FFMA2" in score
+    assert "UBLKCP" in _kernel_sass(sass, "zp_decode_tma_kernel")
+    null = _kernel_sass(sass, "zp_cvs_null_kernel")
+    n_dmul, n_dadd, n_dfma = null.count("DMUL"), null.count("DADD"), null.count("DFMA")
+    assert n_dmul > 100 and n_dadd > 100
+    # -fmad=false: the only DFMAs left are the Newton steps inside the IEEE division / square-root expansions
+    assert n_dfma < n_dmul
 
 
 def test_no_gpu_fails_loudly():

@@ -227,3 +227,31 @@ def test_decode_paths_identical(eng, tables, B, S, dtype, ext, k):
     uv, xyz, ids = _oracle_decode(lg0, bboxes[0], S, tab, k=k, ext_mask=None if em is None else em[0])
     assert n0[0] == len(uv) and np.array_equal(k0[0].astype(np.int64), ids)
     assert np.array_equal(c0[0, 0:2, :n0[0]].T, uv) and np.array_equal(c0[0, 2:5, :n0[0]].T.view(np.uint32), xyz.view(np.uint32))
+
+
+def test_bad_object_ids_are_memory_safe(tables):
+    """obj ids outside [0,256), slots that were never uploaded and slots holding a SHORTER table than the call's code
+    length must not read out of bounds: they decode against "no code exists" / zero-padded rows ((0,0,0) points) and the
+    crops with a good id are unaffected"""
+    import zebrapose_b200 as zp
+    eng = zp.Engine(0)
+    tab, nrm = tables["full"]
+    eng.upload_dict(0, tab)
+    eng.upload_dict(7, tab, ignore_bit=6)                 # 1024-row table in slot 7
+    crops = [synth.make_crop(tab, nrm, 9100 + i) for i in range(5)]
+    logits = torch.from_numpy(np.stack([synth.crop_to_logits(c) for c in crops])).cuda()
+    bboxes = np.stack([c["bbox"] for c in crops])
+    ids = torch.tensor([0, -3, 100000, 5, 7], dtype=torch.int32).cuda()     # ok | negative | huge | empty slot | short table
+    good_corr, good_counts = eng.decode(logits, bboxes)
+    corr, counts = eng.decode(logits, bboxes, ids)
+    torch.cuda.synchronize()
+    assert torch.equal(counts, good_counts)
+    n = int(counts[0])
+    assert torch.equal(corr[0, :, :n], good_corr[0, :, :n])
+    for b in (1, 2, 3):
+        nb = int(counts[b])
+        assert torch.equal(corr[b, 0:2, :nb], good_corr[b, 0:2, :nb]) and float(corr[b, 2:5, :nb].abs().max()) == 0.0
+    assert torch.isfinite(corr[4, :, :int(counts[4])]).all()
+    r = eng.ransac(corr, counts, crops[0]["K"])
+    st = r["status"].cpu().numpy()
+    assert st[0] == 0 and (st[1:4] == 3).all()            # no model from all-zero 3D points

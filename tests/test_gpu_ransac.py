@@ -160,11 +160,12 @@ def test_full_chain_vs_cv2(eng, batch):
         print("crop %d: rot %.5f deg  trans %.5f mm  winner %d/%d  iterations %d/%d  inliers %d/%d"
               % (i, re, te, best[i], info["best"], iters[i], info["iters_run"], ninl[i], len(inl)))
         assert status[i] == 0
-        assert ninl[i] == im[i].sum() == hyp_inl[i, best[i]]
+        assert ninl[i] == im[i].sum() and abs(int(ninl[i]) - int(hyp_inl[i, best[i]])) <= 2
+        # the final inlier set is decided by cv2's own arithmetic for the points the float32 predicate leaves in doubt
+        assert ninl[i] == len(inl) and np.array_equal(np.nonzero(im[i])[0], inl.ravel())
         b2, it2 = cvransac.replay_select(hyp_inl[i], len(uv))      # cv2's rule replayed on the device counts
         assert b2 == best[i] and it2 == iters[i]
         assert best[i] == info["best"] and iters[i] == info["iters_run"]
-        assert abs(int(ninl[i]) - len(inl)) <= 2
         assert re <= ROT_TOL_DEG and te <= TRANS_TOL_MM
         assert abs(np.linalg.det(R) - 1) < 1e-9
 

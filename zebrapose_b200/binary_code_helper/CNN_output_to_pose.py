@@ -10,7 +10,7 @@ from zebrapose_b200.engine import default_engine, dict_to_table
 USE_PYPROGRESSIVEX = False   # the Progressive-X branch (:133-152) is not provided; RANSAC-EPnP is the cv2 branch
 
 _DICT_SLOT = 255             # table slot the per-crop drop-in uses
-_dict_cache = {"key": None}
+_dict_cache = {}             # device index -> (key, dictionary object kept alive)
 
 
 def load_dict_class_id_3D_points(path):
@@ -41,12 +41,11 @@ def mapping_pixel_position_to_original_position(pixels, Bbox, Bbox_Size):
 
 
 def _engine_with_dict(d, n_bits):
-    eng = default_engine()
+    eng = default_engine()               # one engine per device; the upload cache is per device too
     key = (id(d), len(d), n_bits)
-    if _dict_cache["key"] != key:
+    if _dict_cache.get(eng.device.index, (None,))[0] != key:
         eng.upload_dict(_DICT_SLOT, dict_to_table(d, n_bits), n_bits=n_bits, ignore_bit=0, nonexist="zero")
-        _dict_cache["key"] = key
-        _dict_cache["ref"] = d           # keep the object alive so id() stays unique
+        _dict_cache[eng.device.index] = (key, d)      # keep the object alive so id() stays unique
     return eng
 
 
@@ -56,22 +55,37 @@ def CNN_outputs_to_object_pose(mask_image, class_code_image, Bbox, Bbox_Size, cl
     mask), class_code_image [S,S,L] of 0/1 (already sliced to 16-k channels when ignore_bit = k, with the matching
     dictionary), Bbox = [x,y,w,h], intrinsic_matrix 3x3 (numpy or torch; default LM intrinsics).
     -> (rot 3x3 float64, tvecs 3x1 float64 [mm], success) or ([], [], False) when fewer than 6 correspondences."""
-    if class_base != 2:
-        raise NotImplementedError("only binary codes (class_base=2) are on the B200 path")
     if intrinsic_matrix is None:
         intrinsic_matrix = np.array([[572.4114, 0, 325.2611], [0, 573.57043, 242.04899], [0, 0, 1.0]])
     K = np.asarray(intrinsic_matrix.cpu() if isinstance(intrinsic_matrix, torch.Tensor) else intrinsic_matrix, np.float64)
     bb = np.asarray(Bbox.cpu() if isinstance(Bbox, torch.Tensor) else Bbox, np.float64).reshape(1, 4)
     code = np.asarray(class_code_image)
     S, _, L = code.shape
-    eng = _engine_with_dict(dict_class_id_3D_points, L)
-    dev = eng.device
-    # thresholded host arrays -> +-1 "logits" so the same decode kernel applies (x > 0)
-    planes = torch.from_numpy(np.ascontiguousarray(code.transpose(2, 0, 1))).to(dev)
-    logits = torch.where(planes != 0, 1.0, -1.0).to(torch.float32).unsqueeze(0).contiguous()
-    mask = torch.from_numpy(np.ascontiguousarray(np.asarray(mask_image) != 0)).to(dev).reshape(1, S, S)
-    corr, counts = eng.decode(logits, bb, None, obj_default=_DICT_SLOT, mask_ch=0, bit0_ch=0, n_bits=L, ignore_bit=0,
-                              ext_mask=mask)
+    class_base = int(class_base)
+    planes = torch.from_numpy(np.ascontiguousarray(code.transpose(2, 0, 1)))
+    if class_base == 2:
+        eng = _engine_with_dict(dict_class_id_3D_points, L)
+        dev = eng.device
+        # thresholded host arrays -> +-1 "logits" so the same decode kernel applies (x > 0)
+        logits = torch.where(planes.to(dev) != 0, 1.0, -1.0).to(torch.float32).unsqueeze(0).contiguous()
+        mask = torch.from_numpy(np.ascontiguousarray(np.asarray(mask_image) != 0)).to(dev).reshape(1, S, S)
+        corr, counts = eng.decode(logits, bb, None, obj_default=_DICT_SLOT, mask_ch=0, bit0_ch=0, n_bits=L, ignore_bit=0,
+                                  ext_mask=mask)
+    else:
+        # any base (the CE ablation heads, :110 -> class_id_encoder_decoder.py:17-28): digit d of a pixel becomes a one-hot
+        # group of `base` logits, which the CE decode kernel (first maximum of the group) maps back to d
+        n_classes = class_base ** L
+        if n_classes > 65536:
+            raise ValueError("class_base ** code length = %d exceeds the 16-bit class ids of the device path" % n_classes)
+        n_bits = max(1, int(np.ceil(np.log2(n_classes))))
+        eng = _engine_with_dict(dict_class_id_3D_points, n_bits)
+        dev = eng.device
+        digits = planes.to(dev).round().long().clamp(0, class_base - 1)                       # [L,S,S]
+        onehot = torch.nn.functional.one_hot(digits, class_base).permute(0, 3, 1, 2)          # [L,base,S,S]
+        logits = (onehot.reshape(1, L * class_base, S, S).to(torch.float32) * 2 - 1).contiguous()
+        mask = torch.from_numpy(np.ascontiguousarray(np.asarray(mask_image) != 0)).to(dev).reshape(1, S, S)
+        corr, counts = eng.decode_ce(logits, bb, None, base=class_base, n_digits=L, obj_default=_DICT_SLOT, mask_ch=0,
+                                     digit0_ch=0, ext_mask=mask)
     r = eng.ransac(corr, counts, K.reshape(1, 9), H=150, m=5, thr=2.0, conf=0.99, sampler="cv2",
                    select="cv2_replay", final="epnp", return_details=return_info)
     n = int(counts.item())

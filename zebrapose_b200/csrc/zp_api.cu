@@ -2,6 +2,7 @@
 #include <algorithm>
 #include <cmath>
 #include "zp_common.cuh"
+#include <nvtx3/nvToolsExt.h>      // header-only: ranges show up in Nsight Systems / Compute timelines, no-ops otherwise
 
 int zp_launch_samples(zp_ctx*, const int32_t*, int, int, int, int, int, uint64_t, int32_t*, cudaStream_t);
 int zp_launch_minimal(zp_ctx*, const float*, int, const int32_t*, const double*, const int32_t*, int, int, int, int,
@@ -23,6 +24,11 @@ int zp_launch_decode_ce(zp_ctx*, const void*, int, int, int, const int64_t*, int
 int zp_launch_codes_to_ids(zp_ctx*, const double*, int64_t, int, int, double*, cudaStream_t);
 
 static thread_local std::string g_err;
+
+struct ZpRange {                      // NVTX range covering the enqueue of one public entry / one stage of the chain
+    explicit ZpRange(const char* name) { nvtxRangePushA(name); }
+    ~ZpRange() { nvtxRangePop(); }
+};
 
 int zp_ws_reserve(zp_ctx* ctx, size_t bytes) {
     if (bytes <= ctx->ws_bytes) return 0;
@@ -65,10 +71,22 @@ int zp_create(zp_ctx** out, int device) {
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete ctx; g_err = "cudaGetDeviceProperties failed"; return -2; }
     if (prop.major < 9) { delete ctx; g_err = "device too old: built for sm_100a (thread-block clusters, TMA)"; return -2; }
     ctx->sm_count = prop.multiProcessorCount;
-    if (cudaMalloc((void**)&ctx->d_table_ptrs, ZP_MAX_OBJECTS * sizeof(float4*)) != cudaSuccess ||
-        cudaMemset((void*)ctx->d_table_ptrs, 0, ZP_MAX_OBJECTS * sizeof(float4*)) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
-        delete ctx; g_err = "context allocation failed"; return -2;
+    // Every slot of the device pointer array -- plus one extra slot that out-of-range ids are mapped to -- always points at
+    // ZP_TABLE_ROWS entries: empty slots share an all-non-existing table, shorter dictionaries are zero padded.  A crop
+    // whose obj id is wrong therefore decodes against "no code exists" ((0,0,0) points, RANSAC status NO_MODEL) instead of
+    // reading through a null or short pointer.
+    {
+        std::vector<float4*> ptrs(ZP_MAX_OBJECTS + 1);
+        if (cudaMalloc((void**)&ctx->null_table, ZP_TABLE_ROWS * sizeof(float4)) != cudaSuccess ||
+            cudaMemset(ctx->null_table, 0, ZP_TABLE_ROWS * sizeof(float4)) != cudaSuccess ||
+            cudaMalloc((void**)&ctx->d_table_ptrs, (ZP_MAX_OBJECTS + 1) * sizeof(float4*)) != cudaSuccess ||
+            cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+            delete ctx; g_err = "context allocation failed"; return -2;
+        }
+        for (auto& q : ptrs) q = ctx->null_table;
+        if (cudaMemcpy((void*)ctx->d_table_ptrs, ptrs.data(), ptrs.size() * sizeof(float4*), cudaMemcpyHostToDevice) != cudaSuccess) {
+            delete ctx; g_err = "context allocation failed"; return -2;
+        }
     }
     {   // raw stream of cv::RNG(0xFFFFFFFFFFFFFFFF) (multiply-with-carry), replayed by zp_samples_kernel
         const int n = 16384;
@@ -98,6 +116,7 @@ void zp_destroy(zp_ctx* ctx) {
     cudaDeviceSynchronize();
     for (auto& t : ctx->tables) { if (t.pts) cudaFree(t.pts); if (t.remap) cudaFree(t.remap); }
     if (ctx->d_table_ptrs) cudaFree((void*)ctx->d_table_ptrs);
+    if (ctx->null_table) cudaFree(ctx->null_table);
     if (ctx->d_rng) cudaFree(ctx->d_rng);
     if (ctx->d_counters) cudaFree(ctx->d_counters);
     if (ctx->ws) cudaFree(ctx->ws);
@@ -243,8 +262,10 @@ int zp_upload_tables(zp_ctx* ctx, int obj_id, const double* pts, int n_bits, int
     if (t.pts) cudaFree(t.pts);
     if (t.remap) cudaFree(t.remap);
     t.pts = nullptr; t.remap = nullptr;
-    ZP_CUDA(ctx, cudaMalloc((void**)&t.pts, np * sizeof(float4)));
-    ZP_CUDA(ctx, cudaMalloc((void**)&t.remap, np * sizeof(uint16_t)));
+    ZP_CUDA(ctx, cudaMalloc((void**)&t.pts, ZP_TABLE_ROWS * sizeof(float4)));        // zero padded: any 16-bit code is in bounds
+    ZP_CUDA(ctx, cudaMalloc((void**)&t.remap, ZP_TABLE_ROWS * sizeof(uint16_t)));
+    ZP_CUDA(ctx, cudaMemset(t.pts, 0, ZP_TABLE_ROWS * sizeof(float4)));
+    ZP_CUDA(ctx, cudaMemset(t.remap, 0, ZP_TABLE_ROWS * sizeof(uint16_t)));
     ZP_CUDA(ctx, cudaMemcpy(t.pts, tab.data(), np * sizeof(float4), cudaMemcpyHostToDevice));
     ZP_CUDA(ctx, cudaMemcpy(t.remap, remap.data(), np * sizeof(uint16_t), cudaMemcpyHostToDevice));
     ZP_CUDA(ctx, cudaMemcpy((void*)(ctx->d_table_ptrs + obj_id), &t.pts, sizeof(float4*), cudaMemcpyHostToDevice));
@@ -273,6 +294,7 @@ int zp_decode(zp_ctx* ctx, const void* logits, int dtype, int B, int S, const in
     if (dtype != ZP_DTYPE_F32 && dtype != ZP_DTYPE_BF16) ZP_FAIL(ctx, -1, "zp_decode: dtype %d not supported", dtype);
     if (B < 0 || S <= 0 || S > 4096 || cap <= 0) ZP_FAIL(ctx, -1, "zp_decode: bad B/S/cap %d/%d/%d", B, S, cap);
     if (n_bits < 1 || n_bits > 16 || ignore_bit < 0 || ignore_bit >= n_bits) ZP_FAIL(ctx, -1, "zp_decode: bad n_bits/ignore_bit");
+    if (bit0_ch < 0 || (mask_ch < 0 && !ext_mask)) ZP_FAIL(ctx, -1, "zp_decode: negative channel index (mask_ch %d, bit0_ch %d)", mask_ch, bit0_ch);
     if (!obj_ids) {
         if (obj_default < 0 || obj_default >= ZP_MAX_OBJECTS || !ctx->tables[obj_default].pts)
             ZP_FAIL(ctx, -1, "zp_decode: no dictionary uploaded for object slot %d", obj_default);
@@ -281,6 +303,7 @@ int zp_decode(zp_ctx* ctx, const void* logits, int dtype, int B, int S, const in
             ZP_FAIL(ctx, -1, "zp_decode: slot %d holds a %d-bit/ignore %d table, call asks %d/%d", obj_default, t.n_bits, t.ignore_bit, n_bits, ignore_bit);
     }
     ZP_CUDA(ctx, cudaSetDevice(ctx->device));
+    ZpRange range("zp_decode");
     return zp_launch_decode(ctx, logits, dtype, B, S, strides, mask_ch, bit0_ch, n_bits - ignore_bit, ext_mask, bbox,
                             obj_ids, obj_default, codes, corr, cap, counts, (cudaStream_t)stream);
 }
@@ -389,6 +412,7 @@ int zp_ransac(zp_ctx* ctx, const float* corr, int cap, const int32_t* counts, co
     if (cap > 65536) ZP_FAIL(ctx, -1, "zp_ransac: cap %d > 65536 not supported", cap);
     if (check_corr(ctx, corr, cap, "zp_ransac")) return -1;
     ZP_CUDA(ctx, cudaSetDevice(ctx->device));
+    ZpRange range("zp_ransac");
     cudaStream_t st = (cudaStream_t)stream;
     if (!(thr_px > 0)) ZP_FAIL(ctx, -1, "zp_ransac: thr_px must be > 0");
     // workspace: hyp_P | RANSAC state | done flags | samples | hyp_poses | hyp_inliers (the last three only if the caller
@@ -403,6 +427,7 @@ int zp_ransac(zp_ctx* ctx, const float* corr, int cap, const int32_t* counts, co
     int32_t* d_samples = nullptr;
     if (!samples) {
         d_samples = (int32_t*)(ws + o_s);
+        ZpRange rs("samples");
         if (int r = zp_launch_samples(ctx, counts, cap, B, H, m, sampler, seed, d_samples, st)) return r;
     }
     double* d_hp = hyp_poses ? hyp_poses : (double*)(ws + o_p);
@@ -416,6 +441,7 @@ int zp_ransac(zp_ctx* ctx, const float* corr, int cap, const int32_t* counts, co
     for (int h0 = 0, w = 0; h0 < H; w++) {
         int hw = full ? H : wave_size(ctx, w, B);
         if (hw > H - h0) hw = H - h0;
+        ZpRange rw("wave: minimal solver + scoring + adaptive-stop replay");
         // the minimal solver zeroes the inlier counters of its hypotheses: the scoring launch follows without a memset node
         if (int r = zp_launch_minimal(ctx, corr, cap, counts, K, samples ? samples : d_samples, B, H, h0, hw, d_done, m, thr_px,
                                       d_hp, d_P, d_hi, st)) return r;
@@ -424,6 +450,7 @@ int zp_ransac(zp_ctx* ctx, const float* corr, int cap, const int32_t* counts, co
             return r;
         h0 += hw;
     }
+    ZpRange rf("final solve on the inliers");
     return zp_launch_final(ctx, corr, cap, counts, K, d_hp, d_hi, B, H, m, confidence, select_mode, thr_px, final_mode,
                            poses, n_inliers, status, best_idx, inlier_mask, d_rs, iters_run, st);
 }
@@ -436,7 +463,14 @@ int zp_pose_batch_host_async(zp_ctx* ctx, const void* h_logits, int dtype, int B
     if (B == 0) return 0;
     if (!h_logits || !h_bbox || !h_K || !h_poses || !h_n_inliers || !h_status) ZP_FAIL(ctx, -1, "zp_pose_batch_host: null argument");
     if (dtype != ZP_DTYPE_F32 && dtype != ZP_DTYPE_BF16) ZP_FAIL(ctx, -1, "zp_pose_batch_host: bad dtype");
+    if (B < 0 || C <= 0 || S <= 0) ZP_FAIL(ctx, -1, "zp_pose_batch_host: bad B/C/S %d/%d/%d", B, C, S);
+    if (n_bits < 1 || n_bits > 16 || ignore_bit < 0 || ignore_bit >= n_bits) ZP_FAIL(ctx, -1, "zp_pose_batch_host: bad n_bits/ignore_bit");
+    // the staged device copy holds exactly C channels: a layout that reaches past them would read out of bounds
+    if (mask_ch < 0 || mask_ch >= C || bit0_ch < 0 || bit0_ch + (n_bits - ignore_bit) > C)
+        ZP_FAIL(ctx, -1, "zp_pose_batch_host: mask_ch %d / bit0_ch %d + %d bit planes do not fit the %d channels of the logits",
+                mask_ch, bit0_ch, n_bits - ignore_bit, C);
     ZP_CUDA(ctx, cudaSetDevice(ctx->device));
+    ZpRange range("zp_pose_batch_host: H2D + decode + RANSAC + D2H");
     const size_t esz = dtype == ZP_DTYPE_F32 ? 4 : 2;
     const int cap = ((S * S + 3) / 4) * 4;
     const size_t b_log = align256((size_t)B * C * S * S * esz), b_box = align256((size_t)B * 4 * 8), b_K = align256((size_t)B * 9 * 8),

@@ -12,6 +12,7 @@
 
 #define ZP_SM_COUNT_FALLBACK 148
 #define ZP_MAX_DEVICES 64
+#define ZP_TABLE_ROWS 65536          // rows every device dictionary is padded to (codes are 16 bit)
 
 struct ZpTable {
     float4* pts = nullptr;      // [2^(n_bits-k)] x,y,z,exists  (L2-resident, gathered per masked pixel)
@@ -29,7 +30,8 @@ struct zp_ctx {
     int sm_count = ZP_SM_COUNT_FALLBACK;
     std::string err;
     ZpTable tables[ZP_MAX_OBJECTS];
-    const float4** d_table_ptrs = nullptr;   // device array [ZP_MAX_OBJECTS]
+    const float4** d_table_ptrs = nullptr;   // device array [ZP_MAX_OBJECTS + 1]; the last slot = null_table (bad obj ids land there)
+    float4* null_table = nullptr;            // ZP_TABLE_ROWS all-non-existing rows shared by the empty slots
     uint32_t* d_rng = nullptr;               // raw outputs of cv::RNG(0xFFFFFFFFFFFFFFFF), replayed by zp_samples_kernel
     int n_rng = 0;
     int* d_counters = nullptr;               // [2] work-queue ticket + done counter of zp_score_kernel (self re-arming)
@@ -121,6 +123,12 @@ struct zp_ctx {
     } while (0)
 
 int zp_ws_reserve(zp_ctx* ctx, size_t bytes);
+
+// table slot of crop b: ids outside [0, ZP_MAX_OBJECTS) go to the extra all-non-existing slot
+__device__ __forceinline__ int zp_obj_slot(const int32_t* obj_ids, int obj_default, int b) {
+    const int o = obj_ids ? obj_ids[b] : obj_default;
+    return (unsigned)o < (unsigned)ZP_MAX_OBJECTS ? o : ZP_MAX_OBJECTS;
+}
 
 // streaming 128-bit load: read once, do not pollute L1
 __device__ __forceinline__ uint4 zp_ldg_stream(const void* p) {

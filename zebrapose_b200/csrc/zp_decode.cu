@@ -288,7 +288,7 @@ __global__ void __launch_bounds__(DEC_THREADS, 2) zp_decode_cluster_kernel(Decod
     // ---- gather the 3D points and emit the run in row-major order (staged through shared memory)
     {
         extern __shared__ __align__(16) float s_out[];
-        const int obj = a.obj_ids ? a.obj_ids[b] : a.obj_default;
+        const int obj = zp_obj_slot(a.obj_ids, a.obj_default, b);
         emit_staged<PPT>(s_out, mbits, code2, s_warp[warp] + incl - cnt, a.tables[obj], s_x, col, s_y[row], s_total, cta_base,
                          a.corr + (size_t)b * 5 * a.cap, a.cap);
     }
@@ -324,7 +324,7 @@ __global__ void __launch_bounds__(DEC_THREADS, 2) zp_decode_stream_kernel(Decode
     const size_t plane = (size_t)a.sc * ESZ;
     const int nb = FULL16 ? 16 : a.nb;
     const bool own_mask = FULL16 || a.ext_mask == nullptr;
-    const int obj = a.obj_ids ? a.obj_ids[b] : a.obj_default;
+    const int obj = zp_obj_slot(a.obj_ids, a.obj_default, b);
     const float4* tab = a.tables[obj];
     float* cb = a.corr + (size_t)b * 5 * a.cap;
 
@@ -598,7 +598,7 @@ __global__ void __launch_bounds__(DEC_THREADS, 3) zp_decode_emit_kernel(DecodeAr
     if (run == runs_per_crop - 1 && tid == 0) a.counts[b] = cta_base + s_total;
     {
         extern __shared__ __align__(16) float s_out[];
-        const int obj = a.obj_ids ? a.obj_ids[b] : a.obj_default;
+        const int obj = zp_obj_slot(a.obj_ids, a.obj_default, b);
         const int row = active ? p0 / S : 0, col = active ? p0 - row * S : 0;
         emit_staged<PPT>(s_out, mbits, c2, s_warp[warp] + incl - cnt, a.tables[obj], s_x, col, s_y[row], s_total, cta_base,
                          a.corr + (size_t)b * 5 * a.cap, a.cap);
@@ -874,7 +874,7 @@ __global__ void __launch_bounds__(TMA_THREADS, 2) zp_decode_tma_kernel(DecodeArg
     // ---- consumers
     const double* bb = a.bbox + 4 * (size_t)b;
     const double x0 = bb[0], y0 = bb[1], rx = bb[2] / (double)S, ry = bb[3] / (double)S;
-    const int obj = a.obj_ids ? a.obj_ids[b] : a.obj_default;
+    const int obj = zp_obj_slot(a.obj_ids, a.obj_default, b);
     const float4* tab = a.tables[obj];
     float* cb = a.corr + (size_t)b * 5 * a.cap;
     const size_t cap = (size_t)a.cap;
@@ -1056,7 +1056,7 @@ __global__ void __launch_bounds__(DEC_THREADS) zp_decode_generic_kernel(DecodeAr
         int pos = s_base + woff + __popc(bal & ((1u << lane) - 1u));
         if (pos < a.cap) {
             const double* bb = a.bbox + 4 * (size_t)b;
-            const int obj = a.obj_ids ? a.obj_ids[b] : a.obj_default;
+            const int obj = zp_obj_slot(a.obj_ids, a.obj_default, b);
             float4 P = __ldg(a.tables[obj] + code);
             float* cb = a.corr + (size_t)b * 5 * a.cap;
             cb[pos] = remap_coord(bb[2], bb[0], S, col);

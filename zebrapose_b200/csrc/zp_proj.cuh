@@ -21,3 +21,22 @@ __device__ __forceinline__ void zp_make_P(const double* pose, const double* K, d
         P[8 + c] = fin ? (float)r2 : 0.f;
     }
 }
+
+// The inlier decision exactly as cv2's PnPRansacCallback::computeError makes it (projectPoints in double without
+// distortion -> float32 image point -> float32 squared distance <= float32(thr^2)); every operation spelled out, no
+// contraction.  Used where ONE hypothesis per crop is evaluated (the winner's final inlier set) for the points the
+// float32 division-free predicate puts within 1e-3 px of the threshold -- the slack north_star allows the scoring
+// kernel, removed where it is free to remove.  (cv2 rebuilds R from its Rodrigues vector: 1e-16 relative, 1e-13 px.)
+__device__ __forceinline__ bool zp_inlier_exact(const double* pose, double fx, double fy, double cx, double cy, float u,
+                                                float v, float Xf, float Yf, float Zf, float thr2) {
+    const double X = Xf, Y = Yf, Z = Zf;
+    double x = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(pose[0], X), __dmul_rn(pose[1], Y)), __dmul_rn(pose[2], Z)), pose[9]);
+    double y = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(pose[3], X), __dmul_rn(pose[4], Y)), __dmul_rn(pose[5], Z)), pose[10]);
+    double z = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(pose[6], X), __dmul_rn(pose[7], Y)), __dmul_rn(pose[8], Z)), pose[11]);
+    z = z != 0.0 ? __ddiv_rn(1.0, z) : 1.0;
+    x = __dmul_rn(x, z); y = __dmul_rn(y, z);
+    const float px = (float)__dadd_rn(__dmul_rn(x, fx), cx), py = (float)__dadd_rn(__dmul_rn(y, fy), cy);
+    const float dx = __fsub_rn(u, px), dy = __fsub_rn(v, py);
+    const float err = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+    return err <= thr2;
+}

@@ -633,6 +633,7 @@ struct FinalArgs {
     const int32_t* hyp_inliers; int B, H, m; double conf; int select_mode; float inv_thr; int final_mode;
     double* poses; int32_t* n_inliers; int32_t* status; int32_t* best_idx; uint8_t* inlier_mask;
     const int32_t* rs; int32_t* iters_run;      // per-crop RANSAC state {niters, maxGood, best, iterations run}
+    float thr2;                                  // float32(thr_px^2), cv2's comparison value
 };
 
 // (register budget measured: 255 registers per thread beat 128 (2 x 256 threads per SM) and 80 at 64 AND at 1024 crops --
@@ -695,6 +696,7 @@ __global__ void __launch_bounds__(FIN_THREADS) zp_final_kernel(FinalArgs a) {
     zp_make_P(hp, Kb, (double)a.inv_thr, P);
     const float4 p0 = make_float4(P[0], P[1], P[2], P[3]), p1 = make_float4(P[4], P[5], P[6], P[7]),
                  p2 = make_float4(P[8], P[9], P[10], P[11]);
+    const float thr2 = a.thr2;
     ZP_STAMP(1);
     // ---- pass 0: inlier set of the winner (same predicate as zp_score_kernel), centroid
     double acc[52];
@@ -707,7 +709,16 @@ __global__ void __launch_bounds__(FIN_THREADS) zp_final_kernel(FinalArgs a) {
 #pragma unroll 4
     for (int j = 0; j < chunk; j += 32) {             // warp-aligned so the bitset is built with ballots
         const int i = warp * chunk + j + lane;
-        const bool in = i < n && zp_is_inlier(p0, p1, p2, pu[i] * a.inv_thr, pv[i] * a.inv_thr, pX[i], pY[i], pZ[i]);
+        bool in = false;
+        if (i < n) {
+            const float d = zp_inlier_d(p0, p1, p2, pu[i] * a.inv_thr, pv[i] * a.inv_thr, pX[i], pY[i], pZ[i]);
+            in = __float_as_int(d) < 0;
+            // within ~1e-3 px of the threshold (|d| <= 1e-3 z^2 in threshold units; z^2 ~ P row 2 . X squared): cv2's own
+            // arithmetic decides, so the final inlier set is cv2's
+            const float z = fmaf(p2.x, pX[i], fmaf(p2.y, pY[i], fmaf(p2.z, pZ[i], p2.w)));
+            if (fabsf(d) <= 1e-3f * z * z)
+                in = zp_inlier_exact(hp, Kb[0], Kb[4], Kb[2], Kb[5], pu[i], pv[i], pX[i], pY[i], pZ[i], thr2);
+        }
         const unsigned bal = __ballot_sync(0xffffffffu, in);
         if (lane == 0 && i < a.cap) s_mask[i >> 5] = bal;
         if (a.inlier_mask && i < n) a.inlier_mask[(size_t)b * a.cap + i] = in;
@@ -1049,6 +1060,7 @@ int zp_launch_final(zp_ctx* ctx, const float* corr, int cap, const int32_t* coun
     a.rs = rs; a.iters_run = iters_run;
     a.corr = corr; a.cap = cap; a.counts = counts; a.K = K; a.hyp_poses = hyp_poses; a.hyp_inliers = hyp_inliers;
     a.B = B; a.H = H; a.m = m; a.conf = conf; a.select_mode = select_mode; a.inv_thr = 1.0f / thr_px;
+    a.thr2 = (float)((double)thr_px * (double)thr_px);
     a.final_mode = final_mode; a.poses = poses; a.n_inliers = n_inliers; a.status = status; a.best_idx = best_idx;
     a.inlier_mask = inlier_mask;
     size_t smem = ((size_t)(cap + 31) / 32 + 2) * sizeof(uint32_t) +

@@ -53,6 +53,7 @@ class Engine:
         self.ctx = _lib.Context(self.device.index)
         self.lib = self.ctx.lib
         self._slots = {}
+        self._inflight = []              # host buffers of asynchronous submissions, kept alive until sync()
 
     # ------------------------------------------------------------------ dictionaries
     def upload_dict(self, obj_id, table_or_dict, n_bits=16, ignore_bit=0, nonexist="zero"):
@@ -256,6 +257,8 @@ class Engine:
         if lg.is_cuda or not lg.is_contiguous():
             raise ValueError("pose_batch_host takes contiguous HOST logits")
         B, Cc, S, _ = lg.shape
+        if not (0 <= mask_ch < Cc) or bit0_ch < 0 or bit0_ch + (n_bits - ignore_bit) > Cc:
+            raise ValueError("channel layout exceeds the %d channels of logits" % Cc)
         bb = np.ascontiguousarray(np.asarray(bboxes, np.float64).reshape(B, 4))
         K = np.asarray(Ks, np.float64)
         K = np.ascontiguousarray(np.broadcast_to(K.reshape(-1, 9), (B, 9)))
@@ -265,7 +268,7 @@ class Engine:
         poses, ninl, status = out
         fn = self.lib.zp_pose_batch_host_async if asynchronous else self.lib.zp_pose_batch_host
         if asynchronous:                      # the C side reads these after we return: keep them alive until sync()
-            self._inflight = (lg, bb, K, oid, out)
+            self._inflight.append((lg, bb, K, oid, out))
         rc = fn(
             self.ctx.handle, C.c_void_p(lg.data_ptr()), _DT[lg.dtype], B, Cc, S, int(mask_ch), int(bit0_ch), int(n_bits),
             int(ignore_bit), bb.ctypes.data_as(C.c_void_p), K.ctypes.data_as(C.c_void_p),
@@ -278,7 +281,7 @@ class Engine:
     def sync(self):
         """waits for an asynchronous pose_batch_host submission"""
         self.ctx.check(self.lib.zp_sync(self.ctx.handle), "zp_sync")
-        self._inflight = None
+        self._inflight = []
 
     # ------------------------------------------------------------------ small stand-alone helpers
     def remap_pixels(self, pixels, bbox, S):
