@@ -146,6 +146,21 @@ int zp_ransac(zp_ctx* ctx, const float* corr, int cap, const int32_t* counts, co
               double* hyp_poses, int32_t* hyp_inliers, int32_t* best_idx, int32_t* iters_run, uint8_t* inlier_mask,
               double* poses, int32_t* n_inliers, int32_t* status, void* stream);
 
+/* The whole path in ONE call on device-resident buffers: zp_decode + zp_ransac with the correspondence lists kept in the
+ * context (arguments as for those two; bbox double [B,4], K double [B,9]).  records (nullable): double [B,14] = pose |
+ * n_inliers | status, the fixed-size record the multi-GPU gather exchanges, written by the final-solve kernel itself.
+ * use_graph != 0: the first call with a given argument set (pointers, shapes, options, stream) runs eagerly and captures
+ * the 10+ dependent launches of the chain into a CUDA graph; later calls with the same arguments are one cudaGraphLaunch.
+ * The buffers a captured call names must stay allocated while the context lives (or until the arguments change); at most
+ * 32 argument sets are cached per context; calls on the legacy default stream (stream = NULL) cannot be captured and stay
+ * eager.  Results are identical with and without the graph. */
+int zp_pose_batch_device(zp_ctx* ctx, const void* logits, int dtype, int B, int S, const int64_t strides[4],
+                         int mask_ch, int bit0_ch, int n_bits, int ignore_bit, const uint8_t* ext_mask,
+                         const double* bbox, const double* K, const int32_t* obj_ids, int obj_default,
+                         int H, int m, float thr_px, double confidence, int sampler, uint64_t seed,
+                         int select_mode, int final_mode,
+                         double* poses, int32_t* n_inliers, int32_t* status, double* records, int use_graph, void* stream);
+
 /* The reference-facing one-call form with HOST buffers (what a per-batch drop-in of test.py:250-273 calls):
  * copies logits/bbox/K/obj_ids host->device, runs decode + RANSAC, copies poses/n_inliers/status back.
  * h_logits: HOST [B,C,S,S] contiguous (dtype as above); h_bbox HOST double [B,4]; h_K HOST double [B,9];

@@ -12,7 +12,7 @@ int zp_launch_score(zp_ctx*, const float*, int, const int32_t*, const float*, in
                     int32_t*, bool, cudaStream_t);
 int zp_launch_final(zp_ctx*, const float*, int, const int32_t*, const double*, const double*, const int32_t*, int, int, int,
                     double, int, float, int, double*, int32_t*, int32_t*, int32_t*, uint8_t*, const int32_t*, int32_t*,
-                    cudaStream_t);
+                    double*, cudaStream_t);
 int zp_launch_rs_init(zp_ctx*, const int32_t*, int, int, int, int32_t*, int32_t*, int32_t*, cudaStream_t);
 int zp_launch_rs_replay(zp_ctx*, const int32_t*, int, const int32_t*, int, int, int, int, int, double, int, int32_t*,
                         int32_t*, cudaStream_t);
@@ -122,6 +122,8 @@ void zp_destroy(zp_ctx* ctx) {
     if (ctx->ws) cudaFree(ctx->ws);
     if (ctx->hws) cudaFree(ctx->hws);
     if (ctx->cvws) cudaFree(ctx->cvws);
+    for (auto& g : ctx->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
+    if (ctx->gws) cudaFree(ctx->gws);
     if (ctx->dws) cudaFree(ctx->dws);
     for (auto& m : ctx->models) if (m.pts) cudaFree(m.pts);
     if (ctx->d_model_ptrs) cudaFree((void*)ctx->d_model_ptrs);
@@ -401,10 +403,10 @@ static int wave_size(const zp_ctx* ctx, int w, int B) {
     return w < 3 ? 32 : ZP_MAX_HYPOTHESES;
 }
 
-int zp_ransac(zp_ctx* ctx, const float* corr, int cap, const int32_t* counts, const double* K, const int32_t* samples,
-              int B, int H, int m, float thr_px, double confidence, int sampler, uint64_t seed, int select_mode,
-              int final_mode, double* hyp_poses, int32_t* hyp_inliers, int32_t* best_idx, int32_t* iters_run,
-              uint8_t* inlier_mask, double* poses, int32_t* n_inliers, int32_t* status, void* stream) {
+static int ransac_impl(zp_ctx* ctx, const float* corr, int cap, const int32_t* counts, const double* K, const int32_t* samples,
+                       int B, int H, int m, float thr_px, double confidence, int sampler, uint64_t seed, int select_mode,
+                       int final_mode, double* hyp_poses, int32_t* hyp_inliers, int32_t* best_idx, int32_t* iters_run,
+                       uint8_t* inlier_mask, double* poses, int32_t* n_inliers, int32_t* status, double* records, void* stream) {
     if (!ctx) return -1;
     if (B == 0) return 0;
     if (!corr || !counts || !K || !poses || !n_inliers || !status) ZP_FAIL(ctx, -1, "zp_ransac: null argument");
@@ -452,7 +454,98 @@ int zp_ransac(zp_ctx* ctx, const float* corr, int cap, const int32_t* counts, co
     }
     ZpRange rf("final solve on the inliers");
     return zp_launch_final(ctx, corr, cap, counts, K, d_hp, d_hi, B, H, m, confidence, select_mode, thr_px, final_mode,
-                           poses, n_inliers, status, best_idx, inlier_mask, d_rs, iters_run, st);
+                           poses, n_inliers, status, best_idx, inlier_mask, d_rs, iters_run, records, st);
+}
+
+int zp_ransac(zp_ctx* ctx, const float* corr, int cap, const int32_t* counts, const double* K, const int32_t* samples,
+              int B, int H, int m, float thr_px, double confidence, int sampler, uint64_t seed, int select_mode,
+              int final_mode, double* hyp_poses, int32_t* hyp_inliers, int32_t* best_idx, int32_t* iters_run,
+              uint8_t* inlier_mask, double* poses, int32_t* n_inliers, int32_t* status, void* stream) {
+    return ransac_impl(ctx, corr, cap, counts, K, samples, B, H, m, thr_px, confidence, sampler, seed, select_mode, final_mode,
+                       hyp_poses, hyp_inliers, best_idx, iters_run, inlier_mask, poses, n_inliers, status, nullptr, stream);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// The whole chain as ONE call on device-resident buffers, replayed from a CUDA graph: decode -> samples -> RANSAC state ->
+// [minimal solver (4 kernels) -> scoring -> adaptive-stop replay] per wave -> final solve is 10+ dependent launches whose
+// shapes depend only on the arguments, so the first call with a given argument set runs eagerly (sizing the workspaces,
+// setting the function attributes) and captures the same enqueue into a graph; later calls are one cudaGraphLaunch.
+// ---------------------------------------------------------------------------------------------------------------
+static int gws_reserve(zp_ctx* ctx, size_t bytes) {
+    if (bytes <= ctx->gws_bytes) return 0;
+    ZP_CUDA(ctx, cudaDeviceSynchronize());
+    for (auto& g : ctx->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);      // they point into the old buffer
+    ctx->graphs.clear();
+    if (ctx->gws) cudaFree(ctx->gws);
+    ctx->gws = nullptr; ctx->gws_bytes = 0;
+    ZP_CUDA(ctx, cudaMalloc(&ctx->gws, bytes + bytes / 4 + 4096));
+    ctx->gws_bytes = bytes + bytes / 4 + 4096;
+    return 0;
+}
+
+int zp_pose_batch_device(zp_ctx* ctx, const void* logits, int dtype, int B, int S, const int64_t strides[4], int mask_ch,
+                         int bit0_ch, int n_bits, int ignore_bit, const uint8_t* ext_mask, const double* bbox, const double* K,
+                         const int32_t* obj_ids, int obj_default, int H, int m, float thr_px, double confidence, int sampler,
+                         uint64_t seed, int select_mode, int final_mode, double* poses, int32_t* n_inliers, int32_t* status,
+                         double* records, int use_graph, void* stream) {
+    if (!ctx) return -1;
+    if (B == 0) return 0;
+    if (!logits || !strides || !bbox || !K || !poses || !n_inliers || !status) ZP_FAIL(ctx, -1, "zp_pose_batch_device: null argument");
+    if (S <= 0 || S > 4096) ZP_FAIL(ctx, -1, "zp_pose_batch_device: bad S %d", S);
+    ZP_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int cap = ((S * S + 3) / 4) * 4;
+    const size_t b_corr = align256((size_t)B * 5 * cap * 4), b_cnt = align256((size_t)B * 4);
+    if (gws_reserve(ctx, b_corr + b_cnt)) return -2;
+    float* d_corr = (float*)ctx->gws;
+    int32_t* d_cnt = (int32_t*)((char*)ctx->gws + b_corr);
+    cudaStream_t st = (cudaStream_t)stream;
+    auto enqueue = [&]() -> int {
+        if (int r = zp_decode(ctx, logits, dtype, B, S, strides, mask_ch, bit0_ch, n_bits, ignore_bit, ext_mask, bbox, obj_ids,
+                              obj_default, nullptr, d_corr, cap, d_cnt, st)) return r;
+        return ransac_impl(ctx, d_corr, cap, d_cnt, K, nullptr, B, H, m, thr_px, confidence, sampler, seed, select_mode, final_mode,
+                           nullptr, nullptr, nullptr, nullptr, nullptr, poses, n_inliers, status, records, st);
+    };
+    // (the legacy default stream cannot be captured: calls on it stay eager)
+    if (!use_graph || ctx->timing || st == nullptr) return enqueue();
+    ZpGraphKey key;
+    memset(&key, 0, sizeof key);
+    key.p[0] = logits; key.p[1] = ext_mask; key.p[2] = bbox; key.p[3] = K; key.p[4] = obj_ids; key.p[5] = poses; key.p[6] = n_inliers;
+    key.p[7] = status; key.p[8] = records; key.p[9] = stream;
+    for (int q = 0; q < 4; q++) key.s[q] = strides[q];
+    const int iv[16] = {dtype, B, S, mask_ch, bit0_ch, n_bits, ignore_bit, obj_default, H, m, sampler, select_mode, final_mode,
+                        ctx->solver, ctx->n_waves, ctx->force_decode_path * 1000 + ctx->decode_rpc};
+    for (int q = 0; q < 16; q++) key.i[q] = iv[q];
+    for (int q = 0; q < 16; q++) key.w[q] = q < ctx->n_waves ? ctx->wave_sizes[q] : 0;
+    key.f = thr_px; key.c = confidence; key.seed = seed;
+    for (auto& g : ctx->graphs)
+        if (!memcmp(&g.key, &key, sizeof key)) {
+            ZP_CUDA(ctx, cudaGraphLaunch(g.exec, st));
+            ctx->launches += g.kernels;
+            return 0;
+        }
+    // first use: an eager run (this call's result; grows workspaces, sets attributes), then the capture of the same enqueue
+    if (int r = enqueue()) return r;
+    if (ctx->graphs.size() >= 32) return 0;                         // cache full: stay eager for new argument sets
+    const int64_t before = ctx->launches;
+    cudaGraph_t graph = nullptr;
+    ZP_CUDA(ctx, cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    const int rc = enqueue();
+    cudaError_t ce = cudaStreamEndCapture(st, &graph);
+    const int kernels = (int)(ctx->launches - before);
+    ctx->launches = before;                                         // nothing ran during the capture
+    if (rc || ce != cudaSuccess || !graph) {
+        if (graph) cudaGraphDestroy(graph);
+        cudaGetLastError();
+        if (rc) return rc;
+        ZP_FAIL(ctx, -2, "zp_pose_batch_device: graph capture failed: %s", cudaGetErrorString(ce));
+    }
+    ZpGraph g;
+    g.key = key; g.kernels = kernels; g.exec = nullptr;
+    ce = cudaGraphInstantiate(&g.exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ce != cudaSuccess) ZP_FAIL(ctx, -2, "zp_pose_batch_device: cudaGraphInstantiate failed: %s", cudaGetErrorString(ce));
+    ctx->graphs.push_back(g);
+    return 0;
 }
 
 int zp_pose_batch_host_async(zp_ctx* ctx, const void* h_logits, int dtype, int B, int C, int S, int mask_ch, int bit0_ch,

@@ -25,6 +25,12 @@ struct ZpModel {
     int V = 0;
 };
 
+// one captured chain (zp_pose_batch_device): every argument the enqueue depends on, compared bytewise
+struct ZpGraphKey {
+    const void* p[10]; int64_t s[4]; int i[16]; int w[16]; float f; double c; uint64_t seed;
+};
+struct ZpGraph { ZpGraphKey key; cudaGraphExec_t exec; int kernels; };
+
 struct zp_ctx {
     int device = 0;
     int sm_count = ZP_SM_COUNT_FALLBACK;
@@ -70,6 +76,10 @@ struct zp_ctx {
     void* dbg_buf = nullptr;                 // device buffer for per-CTA timestamps of the decode kernel (zp_debug_buffer)
     int decode_rpc = 0;                      // runs per CTA of the streaming decode kernel (0 = automatic)
     int force_decode_path = 0;               // 0 auto, 1 register-staged cluster kernel, 2 generic kernel (tests)
+    // zp_pose_batch_device: correspondence lists between decode and RANSAC, and the captured graphs
+    void* gws = nullptr;
+    size_t gws_bytes = 0;
+    std::vector<ZpGraph> graphs;
     // hand-off records between the stages of the exact minimal solver (zp_cvsolve.cu)
     void* cvws = nullptr;
     size_t cvws_bytes = 0;

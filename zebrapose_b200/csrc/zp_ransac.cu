@@ -634,6 +634,7 @@ struct FinalArgs {
     double* poses; int32_t* n_inliers; int32_t* status; int32_t* best_idx; uint8_t* inlier_mask;
     const int32_t* rs; int32_t* iters_run;      // per-crop RANSAC state {niters, maxGood, best, iterations run}
     float thr2;                                  // float32(thr_px^2), cv2's comparison value
+    double* records;                             // nullable [B,14]: pose | n_inliers | status as doubles (the multi-GPU gather record)
 };
 
 // (register budget measured: 255 registers per thread beat 128 (2 x 256 threads per SM) and 80 at 64 AND at 1024 crops --
@@ -684,6 +685,8 @@ __global__ void __launch_bounds__(FIN_THREADS) zp_final_kernel(FinalArgs a) {
     if (best < 0) {     // no model: cv2 leaves rvec = tvec = 0 and the reference reports R = I, t = 0
         if (tid < 12) out[tid] = (tid == 0 || tid == 4 || tid == 8) ? 1.0 : 0.0;
         if (tid == 0) a.n_inliers[b] = 0;
+        if (a.records && tid < 14)
+            a.records[14 * (size_t)b + tid] = tid < 12 ? ((tid == 0 || tid == 4 || tid == 8) ? 1.0 : 0.0) : tid == 12 ? 0.0 : (double)s_status;
         if (a.inlier_mask)
             for (int i = tid; i < a.cap; i += FIN_THREADS) a.inlier_mask[(size_t)b * a.cap + i] = 0;
         return;
@@ -749,6 +752,7 @@ __global__ void __launch_bounds__(FIN_THREADS) zp_final_kernel(FinalArgs a) {
     if (tid == 0) a.n_inliers[b] = ni;
     if (ni < 4) {       // cannot happen after selection (good > m-1 >= 3) but keep the output defined
         if (tid < 12) out[tid] = hp[tid];
+        if (a.records && tid < 14) a.records[14 * (size_t)b + tid] = tid < 12 ? hp[tid] : tid == 12 ? (double)ni : (double)s_status;
         return;
     }
     const double c0[3] = {s_sum[0] / ni, s_sum[1] / ni, s_sum[2] / ni};
@@ -929,6 +933,7 @@ __global__ void __launch_bounds__(FIN_THREADS) zp_final_kernel(FinalArgs a) {
     }
     ZP_STAMP(9);
     if (tid < 12) out[tid] = s_pose[tid];
+    if (a.records && tid < 14) a.records[14 * (size_t)b + tid] = tid < 12 ? s_pose[tid] : tid == 12 ? (double)ni : (double)s_status;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -1055,9 +1060,9 @@ int zp_launch_score(zp_ctx* ctx, const float* corr, int cap, const int32_t* coun
 int zp_launch_final(zp_ctx* ctx, const float* corr, int cap, const int32_t* counts, const double* K,
                     const double* hyp_poses, const int32_t* hyp_inliers, int B, int H, int m, double conf, int select_mode,
                     float thr_px, int final_mode, double* poses, int32_t* n_inliers, int32_t* status, int32_t* best_idx,
-                    uint8_t* inlier_mask, const int32_t* rs, int32_t* iters_run, cudaStream_t st) {
+                    uint8_t* inlier_mask, const int32_t* rs, int32_t* iters_run, double* records, cudaStream_t st) {
     FinalArgs a;
-    a.rs = rs; a.iters_run = iters_run;
+    a.rs = rs; a.iters_run = iters_run; a.records = records;
     a.corr = corr; a.cap = cap; a.counts = counts; a.K = K; a.hyp_poses = hyp_poses; a.hyp_inliers = hyp_inliers;
     a.B = B; a.H = H; a.m = m; a.conf = conf; a.select_mode = select_mode; a.inv_thr = 1.0f / thr_px;
     a.thr2 = (float)((double)thr_px * (double)thr_px);

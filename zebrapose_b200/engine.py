@@ -54,6 +54,8 @@ class Engine:
         self.lib = self.ctx.lib
         self._slots = {}
         self._inflight = []              # host buffers of asynchronous submissions, kept alive until sync()
+        self._dev_out = {}               # batch size -> persistent outputs of the graph-replayed entry
+        self._graph_refs = {}            # tensors named by captured graphs
 
     # ------------------------------------------------------------------ dictionaries
     def upload_dict(self, obj_id, table_or_dict, n_bits=16, ignore_bit=0, nonexist="zero"):
@@ -183,6 +185,9 @@ class Engine:
         return s
 
     def _Ks(self, Ks, B):
+        if isinstance(Ks, torch.Tensor) and Ks.device == self.device and Ks.dtype == torch.float64 and Ks.is_contiguous() \
+                and tuple(Ks.shape) == (B, 9):
+            return Ks
         K = torch.as_tensor(Ks).to(device=self.device, dtype=torch.float64)
         if K.numel() == 9:
             K = K.reshape(1, 9).expand(B, 9)
@@ -238,14 +243,63 @@ class Engine:
     # ------------------------------------------------------------------ the batched entry (what the bench times)
     def decode_and_pose_batch(self, logits, bboxes, Ks, obj_ids=None, *, obj_default=0, mask_ch=0, bit0_ch=1,
                               n_bits=16, ignore_bit=0, ext_mask=None, m=5, iters=150, thr=2.0, conf=0.99,
-                              sampler="cv2", seed=0, select="cv2_replay", final="epnp"):
-        """Device logits in, device poses out, no host copy: poses f64 [B,12] (R row-major | t mm),
-        n_inliers i32 [B], status i32 [B] (0 ok, 1 no mask pixel, 2 < 6 correspondences, 3 RANSAC found no model)."""
-        corr, counts = self.decode(logits, bboxes, obj_ids, obj_default=obj_default, mask_ch=mask_ch, bit0_ch=bit0_ch,
-                                   n_bits=n_bits, ignore_bit=ignore_bit, ext_mask=ext_mask)
-        r = self.ransac(corr, counts, Ks, H=iters, m=m, thr=thr, conf=conf, sampler=sampler, seed=seed, select=select,
-                        final=final)
-        return r["poses"], r["n_inliers"], r["status"]
+                              sampler="cv2", seed=0, select="cv2_replay", final="epnp", graph=False, out=None, records=None):
+        """Device logits in, device poses out, no host copy, ONE C call (zp_pose_batch_device): poses f64 [B,12]
+        (R row-major | t mm), n_inliers i32 [B], status i32 [B] (0 ok, 1 no mask pixel, 2 < 6 correspondences, 3 RANSAC found
+        no model).  out = (poses, n_inliers, status) to write into caller-owned tensors; records = f64 [B,14] to also get
+        the packed pose | n_inliers | status record of the multi-GPU gather.
+        graph=True replays the chain from a CUDA graph: the first call with a given set of tensors captures it, so the
+        INPUT AND OUTPUT TENSORS MUST BE THE SAME OBJECTS from call to call (with out=None the engine then returns its own
+        persistent output tensors for this batch size, overwritten by the next call)."""
+        if isinstance(logits, (tuple, list)):
+            logits, mask_ch, bit0_ch = self._join_views(*logits)
+        if logits.dim() != 4 or logits.shape[2] != logits.shape[3]:
+            raise ValueError("logits must be [B,C,S,S]")
+        if logits.dtype not in _DT:
+            raise TypeError("logits dtype %s not supported (float32 | bfloat16)" % logits.dtype)
+        if logits.device != self.device:
+            raise ValueError("logits live on %s, engine on %s" % (logits.device, self.device))
+        B, Cc, S, _ = logits.shape
+        if bit0_ch + (n_bits - ignore_bit) > Cc or mask_ch >= Cc:
+            raise ValueError("channel layout exceeds the %d channels of logits" % Cc)
+        bb = self._dev_f64(bboxes, (B, 4))
+        K = self._Ks(Ks, B)
+        oid = None
+        if obj_ids is not None:
+            oid = obj_ids if (isinstance(obj_ids, torch.Tensor) and obj_ids.device == self.device and obj_ids.dtype == torch.int32
+                              and obj_ids.is_contiguous()) else torch.as_tensor(obj_ids).to(device=self.device, dtype=torch.int32).contiguous()
+        em = None
+        if ext_mask is not None:
+            em = (torch.as_tensor(ext_mask).to(device=self.device) != 0).to(torch.uint8).contiguous().reshape(B, S, S)
+        if out is None:
+            if graph:
+                if B not in self._dev_out:
+                    self._dev_out[B] = (torch.empty((B, 12), dtype=torch.float64, device=self.device),
+                                        torch.empty((B,), dtype=torch.int32, device=self.device),
+                                        torch.empty((B,), dtype=torch.int32, device=self.device))
+                out = self._dev_out[B]
+            else:
+                out = (torch.empty((B, 12), dtype=torch.float64, device=self.device),
+                       torch.empty((B,), dtype=torch.int32, device=self.device),
+                       torch.empty((B,), dtype=torch.int32, device=self.device))
+        poses, ninl, status = out
+        strides = (C.c_int64 * 4)(*logits.stride())
+        rc = self.lib.zp_pose_batch_device(
+            self.ctx.handle, _ptr(logits), _DT[logits.dtype], B, S, strides, int(mask_ch), int(bit0_ch), int(n_bits),
+            int(ignore_bit), _ptr(em), _ptr(bb), _ptr(K), _ptr(oid), int(obj_default), int(iters), int(m), float(thr),
+            float(conf), _lib.SAMPLER[sampler], int(seed), _lib.SELECT[select], _lib.FINAL[final], _ptr(poses), _ptr(ninl),
+            _ptr(status), _ptr(records), 1 if graph else 0, _stream(self.device))
+        self.ctx.check(rc, "zp_pose_batch_device")
+        if graph:                          # the graph names these buffers: keep them alive as long as the engine
+            self._graph_refs[(logits.data_ptr(), bb.data_ptr(), K.data_ptr())] = (logits, bb, K, oid, em, out, records)
+        return poses, ninl, status
+
+    def _dev_f64(self, x, shape):
+        """float64 device tensor of `shape`; a tensor that already is one is passed through untouched (stable pointer)"""
+        if isinstance(x, torch.Tensor) and x.device == self.device and x.dtype == torch.float64 and x.is_contiguous() \
+                and tuple(x.shape) == tuple(shape):
+            return x
+        return torch.as_tensor(x).to(device=self.device, dtype=torch.float64).contiguous().reshape(shape)
 
     def pose_batch_host(self, logits, bboxes, Ks, obj_ids=None, *, obj_default=0, mask_ch=0, bit0_ch=1, n_bits=16,
                         ignore_bit=0, m=5, iters=150, thr=2.0, conf=0.99, sampler="cv2", seed=0, select="cv2_replay",
