@@ -1,13 +1,16 @@
 #!/usr/bin/env python
 """bench.py -- crop-poses/s of the post-network pose path (decode + RANSAC-PnP) on N B200s.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--crops C]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config 1|3|4] [--crops C] [--lanes L]
 
 A step = one pass of the hot path over one batch of C synthetic crops per GPU (default: BASELINE.json configs[1],
 64 YCB-V-like 128x128 crops, 21 dictionaries, ignore_bit 0).  `value` = whole-job poses/s with the logits already
-resident in HBM, K steps enqueued round-robin on --lanes contexts/streams and timed as one region (`step_latency_ms` is
-one step alone); `e2e` = the same through zp_pose_batch_host_async/zp_sync (HOST pinned buffers, H2D + D2H inside the
-timed region).
+resident in HBM: K steps enqueued round-robin on --lanes contexts/streams (one cudaGraphLaunch each) and timed as one
+region with CUDA events, max over ranks, the final NCCL gather of the pose records inside (`step_latency_ms` is one step
+alone); `e2e` = the same through zp_pose_batch_host_async/zp_sync (HOST pinned buffers, H2D + D2H inside the timed region).
+Rank 0 then measures every kernel of the chain alone (per-kernel CUDA events) at the batch size of the run and on a full
+grid (1024 crops) and reports them against their rooflines: decode vs HBM, scoring vs FP32, the EPnP solvers vs FP64.
+`--config 3` = configs[3] (4096 crops sharded, strong scaling), `--config 4` = configs[4] (tools/bench_net_e2e.py).
 `--impl reference` times the reference's own CPU path (oracle/reference_path.py: restated per-pixel dict loop +
 cv2.solvePnPRansac) on all host cores.  Prints ONE JSON line on rank 0.
 """
@@ -39,33 +42,47 @@ def make_workload(crops, seed):
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock / throttle reasons / power sampled DURING the run, in process through NVML (no nvidia-smi fork: a process
+    spawn every 50 ms inside a millisecond-scale timed region costs more than the region).  Samples carry a host timestamp;
+    summary() takes the ones inside [t0, t1] (the timed region) when there are any, else all of them."""
+    REASONS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
-    def __init__(self, gpu):
+    def __init__(self, gpu, period=0.002):
         super().__init__(daemon=True)
-        self.gpu, self.rows, self.stop_flag = gpu, [], False
+        self.gpu, self.period, self.rows, self.stop_flag, self.err = gpu, period, [], False, None
 
     def run(self):
-        while not self.stop_flag:
-            try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.split(",")])
-            except Exception:
-                pass
-            time.sleep(0.05)
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.gpu)
+            self.sm_max = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+            while not self.stop_flag:
+                t = time.perf_counter()
+                sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+                try:
+                    rs = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    rs = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                try:
+                    pw = pynvml.nvmlDeviceGetPowerUsage(h) / 1000.0
+                except Exception:
+                    pw = None
+                self.rows.append((t, sm, rs, pw))
+                time.sleep(self.period)
+        except Exception as exc:            # no NVML: report it instead of failing the bench
+            self.err = repr(exc)[:120]
 
-    def summary(self):
-        sm = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in self.rows if r[2].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for r in self.rows for n, v in zip(names, r[4:8]) if v.lower().startswith("active")})
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(self.rows)}
+    def summary(self, t0=None, t1=None):
+        rows = [r for r in self.rows if t0 is not None and t0 <= r[0] <= t1] or self.rows
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "error": self.err}
+        sm = [r[1] for r in rows]
+        reasons = sorted({n for r in rows for n, bit in self.REASONS.items() if r[2] & bit})
+        pw = [r[3] for r in rows if r[3] is not None]
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": getattr(self, "sm_max", None), "reasons": reasons,
+                "samples": len(rows), "samples_total": len(self.rows), "power_w_max": max(pw) if pw else None,
+                "source": "NVML in process, %.0f ms period; samples inside the timed region when it is long enough to hold any" % (self.period * 1e3)}
 
 
 class StdoutToStderr:
@@ -236,15 +253,169 @@ def next_rows(eng, timed, d_bbox, d_K, d_obj, crops, tables, C, hbm_peak, fp32_p
     return out
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# algorithmic work of the kernels
+# ---------------------------------------------------------------------------------------------------------------------
+# FP64 operations (add, mul, div, sqrt each 1) of ONE 5-point hypothesis solved as OpenCV solves it, measured by the census
+# of oracle/cv_epnp.c on this workload's own samples (1200 hypotheses of 8 crops): 12x12 Jacobi SVD 50 836 (294.7 rotated +
+# 125.6 skipped pairs), the seven small Jacobi SVDs 10 663, and the closed-form remainder (M^T M 1 680, L/rho 400, three
+# candidates x (least-squares back-substitution, 5 Gauss-Newton steps with a 6x4 QR, pose, error) 10 500, staging 800)
+SOLVER_OPS_PER_HYP = 50836 + 10663 + 13380
+# final solve on the n_i inliers of the winner: barycentric coordinates + 52 EPnP sums (~190 ops per inlier), candidate
+# errors (3 x 40), centroid / scatter (15), plus the fixed 12x12 null space, betas and alignment (~30 k)
+FINAL_OPS_PER_INLIER, FINAL_OPS_FIXED = 190 + 120 + 15, 30000
+SOLVER_KERNELS = ("zp_cvs_prep_kernel", "zp_cvs_null_kernel", "zp_cvs_cand_kernel", "zp_cvs_pick_kernel")
+CHAIN_KERNELS = ("zp_decode_stream_kernel", "zp_samples_kernel") + SOLVER_KERNELS + ("zp_score_kernel", "zp_final_kernel")
+
+
+def kernel_table(eng, torch, fn_decode, fn_ransac, reps=20):
+    """per-kernel GPU time per call (ms): the library's own CUDA event pairs recorded on the launching stream directly around
+    each launch (zp_set_kernel_timing), 512 MiB L2 flush before every repetition; a kernel launched several times per call
+    (one launch per wave) is summed"""
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
+    out = {}
+    for fn, names in ((fn_decode, CHAIN_KERNELS[:1]), (fn_ransac, CHAIN_KERNELS[1:])):
+        for _ in range(3):
+            fn()
+        eng.set_kernel_timing(True)
+        for _ in range(reps):
+            flush.zero_()
+            fn()
+        torch.cuda.synchronize()
+        for n in names:
+            ms, launches = eng.kernel_time(n)
+            out[n] = ms * launches / reps
+        eng.set_kernel_timing(False)
+    del flush
+    return out
+
+
+def rooflines(k_ms, C, Mtot, n_inl, hyps, peaks, tag=""):
+    """roofline objects of the four kernel families from a kernel table (C crops, Mtot correspondences, n_inl inliers of
+    the winners, hyps hypotheses solved)"""
+    hbm_peak, fp32_peak, fp64_peak = peaks["hbm"], peaks["fp32"], peaks["fp64"]
+    dec_bytes = C * (1 + NBITS) * S * S * 4 + 20 * Mtot + 4 * C                 # SURVEY 8(d): algorithmic HBM bytes
+    dec_gbs = dec_bytes / (k_ms["zp_decode_stream_kernel"] * 1e-3) / 1e9
+    sc_flops = 27.0 * H * Mtot                                                  # SURVEY 8(d): 27 flop / (corr x hyp)
+    sc_tf = sc_flops / (k_ms["zp_score_kernel"] * 1e-3) / 1e12
+    sol_ms = sum(k_ms[k] for k in SOLVER_KERNELS)
+    sol_ops = float(SOLVER_OPS_PER_HYP) * hyps
+    sol_tf = sol_ops / (sol_ms * 1e-3) / 1e12
+    fin_ops = float(FINAL_OPS_PER_INLIER) * n_inl + float(FINAL_OPS_FIXED) * C
+    fin_tf = fin_ops / (k_ms["zp_final_kernel"] * 1e-3) / 1e12
+    unfused = fp64_peak / 2.0 if fp64_peak else None
+    return {
+        "roofline" + tag: {"kernel": "zp_decode_stream_kernel", "bound": "hbm", "achieved": dec_gbs, "peak": hbm_peak, "unit": "GB/s",
+                           "frac": dec_gbs / hbm_peak, "traffic": peaks.get("traffic" + tag), "crops": C,
+                           "peak_source": peaks["hbm_source"], "algorithmic_bytes_per_launch": dec_bytes,
+                           "us_per_launch": k_ms["zp_decode_stream_kernel"] * 1e3},
+        "roofline_score" + tag: {"kernel": "zp_score_kernel", "bound": "fp32", "achieved": sc_tf, "peak": fp32_peak, "unit": "TFLOP/s",
+                                 "frac": sc_tf / fp32_peak if fp32_peak else None, "crops": C, "peak_source": peaks["fp32_source"],
+                                 "algorithmic_flops_per_launch": sc_flops, "us_per_launch": k_ms["zp_score_kernel"] * 1e3},
+        "roofline_fp64" + tag: {"kernel": "+".join(SOLVER_KERNELS), "bound": "fp64 (unfused: the replay of cv2's arithmetic may not contract a*b+c)",
+                                "achieved": sol_tf, "peak": unfused, "unit": "TFLOP/s", "frac": sol_tf / unfused if unfused else None,
+                                "crops": C, "hypotheses": hyps, "algorithmic_ops_per_hypothesis": SOLVER_OPS_PER_HYP,
+                                "peak_source": peaks["fp64_source"], "us_per_call": sol_ms * 1e3},
+        "roofline_fp64_final" + tag: {"kernel": "zp_final_kernel", "bound": "fp64", "achieved": fin_tf, "peak": fp64_peak, "unit": "TFLOP/s",
+                                      "frac": fin_tf / fp64_peak if fp64_peak else None, "crops": C, "inliers": n_inl,
+                                      "algorithmic_ops_per_launch": fin_ops, "us_per_launch": k_ms["zp_final_kernel"] * 1e3},
+    }
+
+
+def run_config3(args, rank, world, local):
+    """BASELINE configs[3]: one job of 4096 T-LESS-style crops (30 dictionaries, up to 8 instances of an object per image),
+    sharded as contiguous ranges over the ranks, each shard walked in batches of <= 512 crops on the lanes; ONE all_gather of
+    the 112-byte pose records at the end of the job.  Strong scaling: a step = the whole job."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import zebrapose_b200 as zp
+    from workloads import synth
+    total, chunk = 4096, 512
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        with StdoutToStderr():
+            dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local))
+            dist.barrier()
+    lo, hi = zp.shard_range(total, rank, world)
+    n_loc = hi - lo
+    # the job's crops are regenerated from their global index on every rank: 64 distinct crops (8 images x 8 instances)
+    # tiled over the shard, rolled by the shard offset so that the ranks hold different crops
+    logits, bboxes, Ks, obj, tables, _ = synth.make_batch(64, S=S, n_bits=NBITS, n_dicts=30, seed=1004, K=synth.TLESS_K,
+                                                          outlier=0.3, bitflip=0.02, radius=(30.0, 150.0))
+    pipe = zp.Pipeline(local, lanes=args.lanes)
+    for j, t in enumerate(tables):
+        pipe.upload_dict(j, t, n_bits=NBITS, ignore_bit=0, nonexist="zero")
+    idx = (np.arange(lo, hi) * 7) % 64
+    batches = []
+    for c0 in range(0, n_loc, chunk):
+        ii = idx[c0:c0 + chunk]
+        batches.append((torch.from_numpy(logits[ii]).cuda(), torch.from_numpy(bboxes[ii].astype(np.float64)).cuda(),
+                        torch.from_numpy(Ks[ii].reshape(-1, 9)).cuda(), torch.from_numpy(obj[ii].astype(np.int32)).cuda(),
+                        torch.zeros((len(ii), 14), dtype=torch.float64, device="cuda")))
+    per = (total + world - 1) // world
+    send = torch.zeros((per, 14), dtype=torch.float64, device="cuda")
+    recv = torch.empty((world * per, 14), dtype=torch.float64, device="cuda")
+    kw = dict(n_bits=NBITS, iters=H, m=M, thr=THR, graph=True)
+
+    def job():
+        off = 0
+        for lg, bb, K, oi, rec in batches:
+            n = lg.shape[0]
+            pipe.submit(lg, bb, K, oi, records=rec, post=lambda o, off=off, n=n, rec=rec: (send[off:off + n].copy_(rec), o)[1], **kw)
+            off += n
+        pipe.join()
+        if world > 1:
+            dist.all_gather_into_tensor(recv, send)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        job()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = pipe.launch_count()
+    e0.record()
+    for _ in range(args.steps):
+        job()
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    ok = float((send[:n_loc, 13] == 0).double().mean().item())
+    if rank == 0:
+        print(json.dumps({"metric": METRIC, "value": total * args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                          "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
+                          "vs_baseline": None, "dtype": "f32 scoring / f64 EPnP / u16 codes", "data": "synthetic",
+                          "config": {"workload": "configs[3]: 4096 T-LESS-style crops (30 dictionaries), contiguous shards of %d crops per "
+                                                 "GPU in batches of %d on %d lanes, one all_gather of the pose records per job" % (per, chunk, args.lanes),
+                                     "crops_total": total, "lanes": args.lanes},
+                          "collective": None if world == 1 else "one all_gather_into_tensor of [%d,14] f64 per rank per job" % per,
+                          "gpu_launches": pipe.launch_count() - l0, "status_ok_fraction_rank0": ok}))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", type=int, default=1, choices=[1, 3, 4],
+                    help="BASELINE.json configs index: 1 = the headline (64 crops per GPU, weak scaling), 3 = 4096 crops sharded "
+                         "(strong scaling), 4 = the network-fed end-to-end step (tools/bench_net_e2e.py)")
     ap.add_argument("--crops", type=int, default=64, help="crops per GPU per step (configs[1] = 64)")
-    ap.add_argument("--lanes", type=int, default=3, help="batches in flight per GPU (one zp_ctx + CUDA stream each)")
+    ap.add_argument("--lanes", type=int, default=6, help="batches in flight per GPU (one zp_ctx + CUDA stream each)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the rows beside the path (next_rows) and the full-grid pass")
     ap.add_argument("--kernels", action="store_true", help="also print a per-kernel table to stderr")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -252,6 +423,14 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         run_reference(args, rank, world)
+        return
+    if args.config == 3:
+        run_config3(args, rank, world, local)
+        return
+    if args.config == 4:
+        from tools import bench_net_e2e
+        sys.argv = [sys.argv[0], str(args.crops if args.crops != 64 else 128), str(max(3, min(args.steps, 10)))]
+        bench_net_e2e.main()
         return
 
     import numpy as np
@@ -268,67 +447,82 @@ def main():
             dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local))
             dist.barrier()
             torch.cuda.synchronize()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     pipe = zp.Pipeline(local, lanes=args.lanes)
     eng = pipe.engines[0]
-    C = args.crops
+    C, K_steps, lanes = args.crops, args.steps, args.lanes
     # weak scaling: every rank owns its own batch of C crops (contiguous shard [rank*C, (rank+1)*C) of the job)
     logits, bboxes, Ks, obj, tables, crops = make_workload(C, 1002 + rank)
     for j, t in enumerate(tables):
         pipe.upload_dict(j, t, n_bits=NBITS, ignore_bit=0, nonexist="zero")
-    # Rotating input buffers: consecutive steps read DIFFERENT device buffers whose total exceeds the 126 MB L2 twice over,
-    # so no step finds its logits in L2 (the timing rule's "inputs larger than L2"); buffer j is the batch rolled by j crops.
-    L2_BYTES = 126 << 20
-    n_buf = max(1, min(8, -(-2 * L2_BYTES // logits.nbytes) + 1)) if logits.nbytes < 2 * L2_BYTES else 1
+    # One fixed input set per lane (the lane's CUDA graph names its buffers): lane l reads the batch rolled by 7 l crops.
+    # Consecutive steps go to consecutive lanes, so a buffer is re-read only after `lanes` steps = lanes x 71 MB later --
+    # several times the 126 MB L2 (the timing rule's "inputs larger than L2").
     bufs = []
-    for j in range(n_buf):
-        r = (j * 7) % C
-        bufs.append((torch.from_numpy(np.roll(logits, r, 0)).cuda(),
-                     torch.from_numpy(np.roll(bboxes, r, 0).astype(np.float64)).cuda(),
-                     torch.from_numpy(np.roll(Ks.reshape(C, 9), r, 0)).cuda(),
-                     torch.from_numpy(np.roll(obj, r, 0).astype(np.int32)).cuda()))
-    d_logits, d_bbox, d_K, d_obj = bufs[0]
-    flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device="cuda")
+    for l in range(lanes):
+        r = (l * 7) % C
+        bufs.append((torch.from_numpy(np.roll(logits, r, 0)).cuda(), torch.from_numpy(np.roll(bboxes, r, 0).astype(np.float64)).cuda(),
+                     torch.from_numpy(np.roll(Ks.reshape(C, 9), r, 0)).cuda(), torch.from_numpy(np.roll(obj, r, 0).astype(np.int32)).cuda(),
+                     torch.zeros((C, 14), dtype=torch.float64, device="cuda")))
+    d_logits, d_bbox, d_K, d_obj, _ = bufs[0]
     n_total = C * world
     kw = dict(n_bits=NBITS, iters=H, m=M, thr=THR)
+    # SURVEY 8(e) / configs[3]: the path has ONE exchange step, at the very end of the job -- the 112-byte records of all K
+    # steps of all ranks in one all_gather.  The final-solve kernel writes a step's records into its lane's buffer; a 7 KB
+    # device copy on the lane's stream files them in the preallocated send buffer; the gather uses preallocated tensors.
+    send = torch.zeros((K_steps * C, 14), dtype=torch.float64, device="cuda")
+    recv = torch.empty((world * K_steps * C, 14), dtype=torch.float64, device="cuda") if world > 1 else None
 
-    def final_gather(outs):
-        """SURVEY 8(e) / configs[3]: the path has ONE exchange step, at the very end of the job -- the poses of all K
-        steps of all ranks in one all_gather (112 B per crop), inside the timed region."""
-        if world == 1:
-            return outs
-        poses = torch.cat([o[0] for o in outs]); ninl = torch.cat([o[1] for o in outs]); st = torch.cat([o[2] for o in outs])
-        return zp.gather_poses(poses, ninl, st, poses.shape[0] * world)
+    def step(i):
+        lg, bb, K, oi, rec = bufs[pipe.next_lane]
+        pipe.submit(lg, bb, K, oi, graph=True, records=rec,
+                    post=lambda o, i=i, rec=rec: (send[(i % K_steps) * C:(i % K_steps + 1) * C].copy_(rec), o)[1], **kw)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    outs = [pipe.submit(*bufs[i % n_buf], **kw) for i in range(max(args.warmup, args.lanes))]
+    for i in range(max(args.warmup, 3 * lanes)):        # every lane: eager run + graph capture + replays
+        step(i)
     pipe.join()
-    final_gather(outs)
+    if world > 1:
+        dist.all_gather_into_tensor(recv, send)         # the exact shape of the timed gather
     barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0, ec, e1 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
     l0 = pipe.launch_count()
     barrier()
     # ---- timed region: exactly K steps, enqueued round-robin over the lanes, bracketed by barrier + synchronize
+    t_host0 = time.perf_counter()
     e0.record()
-    outs = [pipe.submit(*bufs[i % n_buf], **kw) for i in range(args.steps)]
+    for i in range(K_steps):
+        step(i)
     pipe.join()
-    gathered = final_gather(outs)
+    ec.record()
+    if world > 1:
+        dist.all_gather_into_tensor(recv, send)
     e1.record()
     barrier()
+    t_host1 = time.perf_counter()
     launches = pipe.launch_count() - l0
-    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+    tt = torch.tensor([e0.elapsed_time(e1), e0.elapsed_time(ec), ec.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+    allt = tt.clone().reshape(1, 3)
     if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total = float(t.item())
-    value = n_total * args.steps / (ms_total * 1e-3)
+        allt = torch.empty((world, 3), dtype=torch.float64, device="cuda")
+        dist.all_gather_into_tensor(allt, tt.reshape(1, 3))
+    allt = allt.cpu().numpy()
+    ms_total = float(allt[:, 0].max())
+    value = n_total * K_steps / (ms_total * 1e-3)
+    scale_breakdown = {"compute_done_ms_max": float(allt[:, 1].max()), "compute_done_ms_min": float(allt[:, 1].min()),
+                       "skew_ms": float(allt[:, 1].max() - allt[:, 1].min()), "gather_ms_max": float(allt[:, 2].max()),
+                       "gather_ms_min": float(allt[:, 2].min()),
+                       "note": "per rank: e0 -> all lanes joined (compute) -> all_gather returned; skew = slowest minus fastest rank's compute"}
+    status_ok = float((send[:, 13] == 0).double().mean().item())
 
-    # ---- latency of ONE step alone (single lane, L2 flushed by a 256 MiB write before it): reported beside the throughput
+    # ---- latency of ONE step alone (single lane, eager, L2 flushed by a 256 MiB write before it)
+    flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device="cuda")
     lat = []
     for _ in range(10):
         flush.zero_()
@@ -337,17 +531,18 @@ def main():
         b.synchronize()
         lat.append(a.elapsed_time(b))
     step_latency_ms = statistics.median(lat)
+    del flush
 
     # ---- e2e: HOST pinned buffers through the C-ABI host entry (zp_pose_batch_host_async on every lane + zp_sync): the
     # H2D copy of the logits and the D2H read of the poses are inside the timed region, every step
     h_logits = torch.from_numpy(logits).pin_memory()
     outs = [(torch.empty((C, 12), dtype=torch.float64).pin_memory().numpy(), torch.empty(C, dtype=torch.int32).pin_memory().numpy(),
-             torch.empty(C, dtype=torch.int32).pin_memory().numpy()) for _ in range(args.lanes)]
-    for i in range(max(3, args.lanes)):
+             torch.empty(C, dtype=torch.int32).pin_memory().numpy()) for _ in range(lanes)]
+    for i in range(max(3, lanes)):
         pipe.submit_host(h_logits, bboxes, Ks, obj, out=outs[pipe.next_lane])
     pipe.wait_host()
     barrier()
-    e2e_steps = max(6, min(args.steps, 30))
+    e2e_steps = max(6, min(K_steps, 60))
     t0 = time.perf_counter()
     for i in range(e2e_steps):
         pipe.submit_host(h_logits, bboxes, Ks, obj, out=outs[pipe.next_lane])   # waits for (and so reads) that lane's previous result
@@ -356,83 +551,88 @@ def main():
     dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-    e2e_value = n_total * e2e_steps / float(dt.item())
+    e2e_s = float(dt.item())
+    e2e_value = n_total * e2e_steps / e2e_s
     h2d = logits.nbytes + C * 4 * 8 + C * 9 * 8 + C * 4
     d2h = C * 12 * 8 + C * 4 + C * 4
     if rank == 0:
         sampler.stop_flag = True
         sampler.join(timeout=2)
 
-    # ---- per-kernel timing (separate instrumented pass; CUDA events on the launching stream, L2 flushed)
-    # the flush (512 MiB write, ~90 us of GPU time) also hides the CPU cost of enqueueing fn: the event pair and the
-    # kernel are all queued before the flush retires, so the events bracket GPU time only
-    flush2 = torch.empty(2 * L2_FLUSH_BYTES, dtype=torch.uint8, device="cuda")
-
-    def timed(fn, reps=20):
-        for _ in range(3):
-            fn()
-        tot = 0.0
-        for _ in range(reps):
-            flush2.zero_()
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record(); fn(); b.record()
-            b.synchronize()
-            tot += a.elapsed_time(b)
-        return tot / reps
-
-    def ktimed(fn, names, reps=20):
-        """per-kernel durations from the library's own event pairs, recorded on the launching stream directly around each
-        launch (zp_set_kernel_timing), L2 flushed before every repetition"""
-        for _ in range(3):
-            fn()
-        eng.set_kernel_timing(True)
-        for _ in range(reps):
-            flush2.zero_()
-            fn()
-        torch.cuda.synchronize()
-        out = {n: eng.kernel_time(n)[0] for n in names}
-        eng.set_kernel_timing(False)
-        return out
-
     line = None
     if rank == 0:
-        corr, counts = eng.decode(d_logits, d_bbox, d_obj)
-        cap = corr.shape[2]
-        k_ms = ktimed(lambda: eng.decode(d_logits, d_bbox, d_obj), ["zp_decode_stream_kernel"])
-        k_ms.update(ktimed(lambda: eng.ransac(corr, counts, d_K, H=H, m=M, thr=THR),
-                           ["zp_samples_kernel", "zp_minimal_kernel", "zp_score_kernel", "zp_final_kernel"]))
-        chain_event_ms = timed(lambda: eng.ransac(corr, counts, d_K, H=H, m=M, thr=THR))     # python-level events: + launch gaps, memset
-        k_ms["ransac_chain(samples+minimal+score+select+final)"] = sum(k_ms[k] for k in ("zp_samples_kernel", "zp_minimal_kernel", "zp_score_kernel", "zp_final_kernel"))
-        Mtot = int(counts.clamp(max=cap).sum().item())
-        peaks = {}
+        peaks_file = {}
         try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+            peaks_file = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except Exception:
             pass
-        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-        traffic = None
+        fp32_scalar, fp32_packed = eng.fp32_peak_tflops(), eng.fp32_peak_tflops(packed=True)
+        fp64 = eng.fp64_peak_tflops()
+        traffic = {}
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["zp_decode_stream_kernel"].get(str(C))
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["zp_decode_stream_kernel"]
         except Exception:
             pass
-        dec_bytes = C * (1 + NBITS) * S * S * 4 + 20 * Mtot + 4 * C          # SURVEY 8(d): algorithmic HBM bytes
-        dec_gbs = dec_bytes / (k_ms["zp_decode_stream_kernel"] * 1e-3) / 1e9
-        fp32_scalar = eng.fp32_peak_tflops()
-        fp32_packed = eng.fp32_peak_tflops(packed=True)
-        fp32_peak = max(fp32_scalar, fp32_packed)
-        sc_flops = 27.0 * H * Mtot                                            # SURVEY 8(d): 27 flop / (corr x hyp)
-        sc_tf = sc_flops / (k_ms["zp_score_kernel"] * 1e-3) / 1e12
-        chain = k_ms["zp_decode_stream_kernel"] + k_ms["ransac_chain(samples+minimal+score+select+final)"]
+        peaks = {"hbm": float(peaks_file.get("hbm_gbs", 6650.0)),
+                 "hbm_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks_file else "fallback 6650 (B200_PROFILING.md)",
+                 "fp32": max(fp32_scalar, fp32_packed),
+                 "fp32_source": "max of zp_fp32_peak_probe (scalar FFMA chains, %.1f) and zp_fp32x2_peak_probe (packed FFMA2 chains, %.1f), measured on this GPU in this run" % (fp32_scalar, fp32_packed),
+                 "fp64": fp64, "fp64_source": "zp_fp64_peak_probe (DFMA chains, %.1f TFLOP/s at 2 flop per instruction), measured on this GPU in this run" % fp64,
+                 "traffic": (traffic.get(str(C)) or {}).get("bytes"), "traffic_full_grid": (traffic.get("1024") or {}).get("bytes")}
+
+        def table_for(lg, bb, K, oi):
+            corr, counts = eng.decode(lg, bb, oi)
+            k_ms = kernel_table(eng, torch, lambda: eng.decode(lg, bb, oi), lambda: eng.ransac(corr, counts, K, H=H, m=M, thr=THR))
+            r = eng.ransac(corr, counts, K, H=H, m=M, thr=THR, return_details="state")
+            cap = corr.shape[2]
+            n_valid = int((counts >= 6).sum().item())
+            return k_ms, int(counts.clamp(max=cap).sum().item()), int(r["n_inliers"].sum().item()), n_valid * H, r
+
+        for e in pipe.engines:
+            e.set_waves([H])                      # one wave: the per-kernel figures are per launch
+        k_ms, Mtot, n_inl, hyps, r_state = table_for(d_logits, d_bbox, d_K, d_obj)
+        roof = rooflines(k_ms, C, Mtot, n_inl, hyps, peaks)
+        chain = sum(k_ms[k] for k in CHAIN_KERNELS)
         shares = {k: round(v / chain, 4) for k, v in k_ms.items()}
-        dominant = max(("zp_decode_stream_kernel", "zp_minimal_kernel", "zp_score_kernel", "zp_final_kernel"), key=lambda k: k_ms[k])
+        dominant = max(CHAIN_KERNELS, key=lambda k: k_ms[k])
+        iters_run = r_state["iters_run"].cpu().numpy()
+        full = None
+        if not args.no_extras:
+            # the same kernels on a full grid: the batch tiled to 1024 crops (16 x the same 64), where one launch is many waves
+            rep = max(1, 1024 // C)
+            try:
+                big = (d_logits.repeat(rep, 1, 1, 1), d_bbox.repeat(rep, 1), d_K.repeat(rep, 1), d_obj.repeat(rep))
+                k_big, M_big, inl_big, hyps_big, _ = table_for(*big)
+                full = rooflines(k_big, C * rep, M_big, inl_big, hyps_big, peaks, tag="_full_grid")
+                full["kernel_us_full_grid"] = {k: round(v * 1e3, 1) for k, v in k_big.items()}
+                del big
+            except Exception as exc:
+                full = {"error": repr(exc)[:200]}
+        for e in pipe.engines:
+            e.set_waves(None)
         if args.kernels:
             for k, v in k_ms.items():
-                print("%-55s %9.3f us  share %.3f" % (k, v * 1e3, v / chain), file=sys.stderr)
+                print("%-30s %9.3f us  share %.3f" % (k, v * 1e3, v / chain), file=sys.stderr)
+
+        def timed(fn, reps=20):
+            fl = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
+            for _ in range(3):
+                fn()
+            tot = 0.0
+            for _ in range(reps):
+                fl.zero_()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(); fn(); b.record()
+                b.synchronize()
+                tot += a.elapsed_time(b)
+            return tot / reps
+
         extras = None
-        try:
-            extras = next_rows(eng, timed, d_bbox, d_K, d_obj, crops, tables, C, hbm_peak, fp32_peak)
-        except Exception as exc:          # the rows beside the path must never cost the headline line
-            extras = {"error": repr(exc)[:200]}
+        if not args.no_extras:
+            try:
+                extras = next_rows(eng, timed, d_bbox, d_K, d_obj, crops, tables, C, peaks["hbm"], peaks["fp32"])
+            except Exception as exc:          # the rows beside the path must never cost the headline line
+                extras = {"error": repr(exc)[:200]}
         cpu = None
         if prev_affinity:
             os.sched_setaffinity(0, prev_affinity)          # the reference pool gets every host core again
@@ -446,40 +646,34 @@ def main():
             except Exception as exc:
                 cpu["agreement"] = {"error": repr(exc)[:200]}
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "collective": None if world == 1 else "one NCCL all_gather_into_tensor of the K steps' pose records (112 B/crop) at the end of the timed region",
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K_steps, "warmup": args.warmup,
+            "ms_per_step": ms_total / K_steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "collective": None if world == 1 else "one NCCL all_gather_into_tensor of the K steps' pose records (112 B/crop, preallocated send/recv) at the end of the timed region",
             "dtype": "f32 scoring / f64 EPnP / u16 codes", "data": "synthetic",
-            "config": {"workload": WORKLOAD % C,
-                       "crops_per_gpu": C, "lanes": args.lanes,
-                       "l2": "inputs larger than L2: %d rotating device batches of %.0f MB, a step never re-reads the buffer of "
-                             "the previous %d steps (per-kernel figures: 512 MiB flush write before each launch)" % (n_buf, logits.nbytes / 1e6, n_buf - 1),
-                       "masked_px_per_crop": Mtot / C},
+            "config": {"workload": WORKLOAD % C, "crops_per_gpu": C, "lanes": lanes, "solver": "cv2 (exact replay of OpenCV's EPnP arithmetic)",
+                       "launch": "one cudaGraphLaunch per step (zp_pose_batch_device, chain captured per lane)",
+                       "l2": "inputs larger than L2: %d lanes with their own %.0f MB input batch each, a buffer is re-read %d steps "
+                             "(%.0f MB of other logits) later; per-kernel figures: 512 MiB flush write before each launch" % (
+                                 lanes, logits.nbytes / 1e6, lanes, (lanes - 1) * logits.nbytes / 1e6),
+                       "masked_px_per_crop": Mtot / C, "ransac_iterations_run": {"median": float(np.median(iters_run)), "mean": float(iters_run.mean())}},
             "step_latency_ms": step_latency_ms,
+            "timed_region_ms": ms_total, "scale_breakdown": scale_breakdown, "status_ok_fraction": status_ok,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "path": "zp_pose_batch_host_async + zp_sync (C ABI, pinned host logits -> pinned host poses), %d lanes" % args.lanes,
+                    "bound": "pcie", "h2d_gbs": h2d * e2e_steps / e2e_s / 1e9 * world, "h2d_gbs_per_gpu": h2d * e2e_steps / e2e_s / 1e9,
+                    "path": "zp_pose_batch_host_async + zp_sync (C ABI, pinned host logits -> pinned host poses), %d lanes" % lanes,
                     "host_cpus": "%d CPUs local to the GPU (NVML affinity)" % len(numa_cpus) if numa_cpus else "unbound",
                     "steps": e2e_steps},
             "gpu_launches": launches,
-            "clocks": sampler.summary(),
-            "roofline": {"kernel": "zp_decode_stream_kernel", "bound": "hbm", "achieved": dec_gbs, "peak": hbm_peak,
-                         "unit": "GB/s", "frac": dec_gbs / hbm_peak, "traffic": traffic["bytes"] if traffic else None,
-                         "traffic_source": traffic["source"] if traffic else None,
-                         "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650",
-                         "algorithmic_bytes_per_launch": dec_bytes, "us_per_launch": k_ms["zp_decode_stream_kernel"] * 1e3},
-            "roofline_score": {"kernel": "zp_score_kernel", "bound": "fp32", "achieved": sc_tf, "peak": fp32_peak,
-                               "unit": "TFLOP/s", "frac": sc_tf / fp32_peak if fp32_peak else None,
-                               "peak_source": "max of zp_fp32_peak_probe (scalar FFMA chains, %.1f) and zp_fp32x2_peak_probe (packed FFMA2 chains, %.1f), measured on this GPU in this run" % (fp32_scalar, fp32_packed),
-                               "algorithmic_flops_per_launch": sc_flops, "us_per_launch": k_ms["zp_score_kernel"] * 1e3},
+            "clocks": sampler.summary(t_host0, t_host1),
             "kernel_us": {k: round(v * 1e3, 2) for k, v in k_ms.items()},
             "kernel_us_method": "CUDA event pairs recorded by the library on the launching stream directly around each launch "
-                                "(zp_set_kernel_timing), 512 MiB L2 flush before every repetition, 20 repetitions",
-            "ransac_chain_us_python_events": round(chain_event_ms * 1e3, 2),
-            "kernel_share_of_step": shares,
-            "dominant_kernel": dominant,
-            "cpu_baseline": cpu,
-            "next_rows": extras,
+                                "(zp_set_kernel_timing), 512 MiB L2 flush before every repetition, 20 repetitions, one wave of all 150 hypotheses",
+            "kernel_share_of_step": shares, "dominant_kernel": dominant,
+            "cpu_baseline": cpu, "next_rows": extras,
         }
+        line.update(roof)
+        if full:
+            line.update(full)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -224,6 +224,9 @@ int zp_debug_clocks(zp_ctx* ctx, int64_t* out24);
  * runs `iters` dependent-chain FMAs x 8 chains per thread on the whole chip, returns achieved TFLOP/s in *out.
  * Synchronises. */
 int zp_fp32_peak_probe(zp_ctx* ctx, int iters, double* out_tflops);
+/* FP64 counterpart (DFMA chains, 2 flop per instruction): the roofline denominator of the EPnP solver kernels.  The exact
+ * solver uses unfused multiplies and adds (one flop per instruction), so its ceiling is half this figure. */
+int zp_fp64_peak_probe(zp_ctx* ctx, int iters, double* out_tflops);
 /* Same with packed FFMA2 (fma.rn.f32x2) chains: the form zp_score_kernel uses. */
 int zp_fp32x2_peak_probe(zp_ctx* ctx, int iters, double* out_tflops);
 

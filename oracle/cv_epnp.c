@@ -25,6 +25,13 @@
 
 #define MAXN 16  /* largest matrix side that goes through the Jacobi SVD here */
 
+/* arithmetic-operation census of the Jacobi SVDs (add, mul, div, sqrt each count 1), by problem size: [0] n = 12 (the
+ * null space of M^T M), [1] every other size; [2] / [3] rotated / skipped pairs of the n = 12 problems.  bench.py turns
+ * the per-hypothesis averages into the algorithmic FP64 work of the solver kernels. */
+static double zpo_census[4];
+void zpo_census_reset(void) { zpo_census[0] = zpo_census[1] = zpo_census[2] = zpo_census[3] = 0; }
+void zpo_census_read(double* out4) { for (int i = 0; i < 4; i++) out4[i] = zpo_census[i]; }
+
 static double cv_hypot(double a, double b) {
     a = fabs(a); b = fabs(b);
     if (a > b) { b /= a; return a * sqrt(1 + b * b); }
@@ -51,7 +58,11 @@ int zpo_jacobi_svd(double* At, int astep, double* Wout, double* Vt, int vstep, i
                 double *Ai = At + i * astep, *Aj = At + j * astep;
                 double a = W[i], p = 0, b = W[j];
                 for (k = 0; k < m; k++) p += Ai[k] * Aj[k];
-                if (fabs(p) <= eps * sqrt(a * b)) continue;
+                zpo_census[n == 12 ? 0 : 1] += 2.0 * m + 3;
+                if (fabs(p) <= eps * sqrt(a * b)) { if (n == 12) zpo_census[3] += 1; continue; }
+                /* hypot 5, c/s 8, rotation 6m, norms 4m, Vt rotation 6n */
+                zpo_census[n == 12 ? 0 : 1] += 14.0 + 10.0 * m + (Vt ? 6.0 * n : 0.0);
+                if (n == 12) zpo_census[2] += 1;
                 p *= 2;
                 double beta = a - b, gamma = cv_hypot(p, beta);
                 if (beta < 0) {

@@ -89,3 +89,17 @@ def solve_svd(A, b):
     x = np.zeros(A.shape[1])
     lib().zpo_solve_svd(_p(A), A.shape[0], A.shape[1], _p(b), _p(x))
     return x
+
+
+def census(samples):
+    """average arithmetic operations of the Jacobi SVDs per solve over `samples` = [(pw, uv, K), ...]: dict(ops_n12, ops_other,
+    rotated_n12, skipped_n12).  (OpenCV also rotates a 12 x 12 Vt for the n = 12 problem, which the device kernel does not
+    need and the census therefore leaves out there: 6 n per rotated pair.)"""
+    L = lib()
+    L.zpo_census_reset()
+    for pw, uv, K in samples:
+        epnp(pw, uv, K)
+    out = np.zeros(4)
+    L.zpo_census_read(_p(out))
+    n = max(1, len(samples))
+    return dict(ops_n12=(out[0] - 72.0 * out[2]) / n, ops_other=out[1] / n, rotated_n12=out[2] / n, skipped_n12=out[3] / n)

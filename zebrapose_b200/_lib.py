@@ -52,6 +52,7 @@ SIGNATURES = {
     "zp_debug_clocks": (_i, [_vp, _vp]),
     "zp_fp32_peak_probe": (_i, [_vp, _i, C.POINTER(_d)]),
     "zp_fp32x2_peak_probe": (_i, [_vp, _i, C.POINTER(_d)]),
+    "zp_fp64_peak_probe": (_i, [_vp, _i, C.POINTER(_d)]),
     "zp_final_bbox": (_i, [_vp, _vp, _i, _d, _i, _d, _d, _vp, _vp]),
     "zp_crop_input": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _i, _i, _i, _vp, _vp, _i, _i, _vp, _vp, _vp]),
     "zp_upload_model": (_i, [_vp, _i, _vp, _i]),

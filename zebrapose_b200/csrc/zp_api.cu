@@ -17,6 +17,7 @@ int zp_launch_rs_init(zp_ctx*, const int32_t*, int, int, int, int32_t*, int32_t*
 int zp_launch_rs_replay(zp_ctx*, const int32_t*, int, const int32_t*, int, int, int, int, int, double, int, int32_t*,
                         int32_t*, cudaStream_t);
 int zp_launch_fma_probe(zp_ctx*, int, int, double*);
+int zp_launch_dfma_probe(zp_ctx*, int, double*);
 int zp_read_debug_clocks(long long*);
 int zp_launch_remap_pixels(zp_ctx*, const int64_t*, int64_t, const double*, int, int64_t*, cudaStream_t);
 int zp_launch_decode_ce(zp_ctx*, const void*, int, int, int, const int64_t*, int, int, int, int, const uint8_t*, const double*,
@@ -624,6 +625,12 @@ int zp_fp32_peak_probe(zp_ctx* ctx, int iters, double* out_tflops) {
     if (!ctx || !out_tflops) return -1;
     ZP_CUDA(ctx, cudaSetDevice(ctx->device));
     return zp_launch_fma_probe(ctx, iters, 0, out_tflops);
+}
+
+int zp_fp64_peak_probe(zp_ctx* ctx, int iters, double* out_tflops) {
+    if (!ctx || !out_tflops) return -1;
+    ZP_CUDA(ctx, cudaSetDevice(ctx->device));
+    return zp_launch_dfma_probe(ctx, iters, out_tflops);
 }
 
 int zp_fp32x2_peak_probe(zp_ctx* ctx, int iters, double* out_tflops) {

@@ -1102,6 +1102,42 @@ __global__ void zp_fma2_probe_kernel(float* out, int iters, float a, float b) {
     out[blockIdx.x * blockDim.x + threadIdx.x] = __uint_as_float((uint32_t)s ^ (uint32_t)(s >> 32));
 }
 
+// FP64 peak probe (roofline denominator of the solver kernels): 8 independent DFMA chains per thread
+__global__ void zp_dfma_probe_kernel(double* out, int iters, double a, double b) {
+    double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+    for (int i = 0; i < iters; i++) {
+        x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+        x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+}
+
+int zp_launch_dfma_probe(zp_ctx* ctx, int iters, double* out_tflops) {
+    const int blocks = ctx->sm_count * 8, threads = 256;
+    double* d = nullptr;
+    ZP_CUDA(ctx, cudaMalloc(&d, (size_t)blocks * threads * sizeof(double)));
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    double best = 0;
+    for (int rep = 0; rep < 5; rep++) {
+        cudaEventRecord(e0);
+        zp_dfma_probe_kernel<<<blocks, threads>>>(d, iters, 0.999, 0.001);
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        ctx->launches++;
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        double tf = 2.0 * 8.0 * (double)iters * blocks * threads / (ms * 1e-3) / 1e12;
+        if (rep > 0 && tf > best) best = tf;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(d);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) ZP_FAIL(ctx, -3, "dfma probe failed: %s", cudaGetErrorString(e));
+    *out_tflops = best;
+    return 0;
+}
+
 int zp_read_debug_clocks(long long* host16) {
     return cudaMemcpyFromSymbol(host16, zp_dbg_clk, sizeof(long long) * 24) == cudaSuccess ? 0 : -2;
 }

@@ -490,6 +490,12 @@ class Engine:
         self.ctx.check(self.lib.zp_kernel_time(self.ctx.handle, name.encode(), C.byref(ms), C.byref(n)), "zp_kernel_time")
         return (ms.value / n.value if n.value else 0.0), int(n.value)
 
+    def fp64_peak_tflops(self, iters=10000):
+        """measured FP64 FMA throughput of this GPU (DFMA chains, 2 flop per instruction)"""
+        v = C.c_double()
+        self.ctx.check(self.lib.zp_fp64_peak_probe(self.ctx.handle, int(iters), C.byref(v)), "zp_fp64_peak_probe")
+        return v.value
+
     def fp32_peak_tflops(self, iters=20000, packed=False):
         """measured FP32 FMA throughput of this GPU: scalar FFMA chains, or packed FFMA2 chains (packed=True)"""
         v = C.c_double()
