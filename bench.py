@@ -331,7 +331,7 @@ def run_config3(args, rank, world, local):
     import torch.distributed as dist
     import zebrapose_b200 as zp
     from workloads import synth
-    total, chunk = 4096, 512
+    total = 4096
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
@@ -340,6 +340,9 @@ def run_config3(args, rank, world, local):
             dist.barrier()
     lo, hi = zp.shard_range(total, rank, world)
     n_loc = hi - lo
+    # batches small enough that every lane gets one (a shard walked as ONE batch leaves the latency-bound kernels of the
+    # chain nothing to overlap with), at most 512 crops
+    chunk = max(64, min(512, -(-n_loc // args.lanes)))
     # the job's crops are regenerated from their global index on every rank: 64 distinct crops (8 images x 8 instances)
     # tiled over the shard, rolled by the shard offset so that the ranks hold different crops
     logits, bboxes, Ks, obj, tables, _ = synth.make_batch(64, S=S, n_bits=NBITS, n_dicts=30, seed=1004, K=synth.TLESS_K,
