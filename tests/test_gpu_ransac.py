@@ -386,7 +386,7 @@ def test_graph_replay_identical(eng, batch):
 def test_gn_refine_against_twin(eng, batch):
     """north_star's "batched Gauss-Newton refine on the inliers" (final="epnp+gn"; not in the reference, whose cv2 call ends
     with EPnP on the inliers).  Device vs the float64 twin started from the device's own EPnP pose on the device's inlier
-    set: <= 1e-6 deg / 1e-5 mm.  Independent cross-check: cv2.solvePnPRefineLM from the same start converges to the same
+    set: R equal to 1e-9 elementwise (< 1e-6 deg), t to 1e-5 mm.  Independent cross-check: cv2.solvePnPRefineLM from the same start converges to the same
     pose within 2e-3 deg / 2e-2 mm.  Reported: how far the polish moves the EPnP pose (SURVEY App. C expects ~0.015 deg /
     0.14 mm median -- a third of the 0.05 deg / 0.5 mm tolerance, which is why it is off by default)."""
     r0 = eng.ransac(batch["corr"], batch["counts"], batch["Ks"], final="epnp", return_details="state")
@@ -401,7 +401,8 @@ def test_gn_refine_against_twin(eng, batch):
         R0, t0 = p0[i, :9].reshape(3, 3), p0[i, 9:]
         Rt, tt = gn_refine.gn_refine(R0, t0, xyz[sel], uv[sel], K, iters=5)
         R1, t1 = p1[i, :9].reshape(3, 3), p1[i, 9:]
-        assert metrics.rot_err_deg(Rt, R1) <= 1e-6 and metrics.trans_err(tt, t1) <= 1e-5, i
+        # (elementwise on R: the arccos of the angle formula resolves only ~1.2e-6 deg)
+        assert np.abs(Rt - R1).max() <= 1e-9 and metrics.trans_err(tt, t1) <= 1e-5, (i, np.abs(Rt - R1).max(), metrics.trans_err(tt, t1))
         rv, tv = cv2.solvePnPRefineLM(xyz[sel].astype(np.float64), uv[sel].astype(np.float64), K, None,
                                       cv2.Rodrigues(R0)[0], t0.reshape(3, 1).copy())
         assert metrics.rot_err_deg(cv2.Rodrigues(rv)[0], R1) <= 2e-3 and metrics.trans_err(tv, t1) <= 2e-2, i

@@ -581,30 +581,53 @@ __global__ void zp_rs_init_kernel(const int32_t* __restrict__ counts, int cap, i
         for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < B * H; i += gridDim.x * blockDim.x) hyp_inliers_fill[i] = -1;
 }
 
-__global__ void zp_rs_replay_kernel(const int32_t* __restrict__ counts, int cap, const int32_t* __restrict__ hyp_inliers,
-                                    int B, int H, int h0, int h1, int m, double conf, int select_mode,
-                                    int32_t* __restrict__ rs, int32_t* __restrict__ crop_done) {
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+// One WARP per crop.  Only "records" (counts above everything before them) can change the state, so a chunk of 32 counts
+// is loaded coalesced, an inclusive prefix maximum flags the records, and the warp walks the few flagged ones in order
+// (pow / log only there).  (A first version -- one thread per crop walking the counts one by one -- took 54 us per wave.)
+constexpr int RS_WARPS = 4;
+__global__ void __launch_bounds__(32 * RS_WARPS)
+zp_rs_replay_kernel(const int32_t* __restrict__ counts, int cap, const int32_t* __restrict__ hyp_inliers, int B, int H, int h0,
+                    int h1, int m, double conf, int select_mode, int32_t* __restrict__ rs, int32_t* __restrict__ crop_done) {
+    const int lane = threadIdx.x & 31;
+    const int b = blockIdx.x * RS_WARPS + (threadIdx.x >> 5);
     if (b >= B || crop_done[b]) return;
     const int n = min(counts[b], cap);
-    int niters = rs[4 * b], maxgood = rs[4 * b + 1], best = rs[4 * b + 2], it = h0;
+    int niters = rs[4 * b], maxgood = rs[4 * b + 1], best = rs[4 * b + 2];
     const int32_t* hi = hyp_inliers + (size_t)b * H;
-    if (select_mode == ZP_SELECT_CV2_REPLAY) {
-        for (; it < h1 && it < niters; it++) {
-            const int good = hi[it];
-            if (good > max(maxgood, m - 1)) {
-                best = it; maxgood = good;
-                niters = zp_update_iters(conf, (double)(n - good) / n, m, niters);
-            }
+    int last = h0 - 1;                                  // last iteration that changed the state
+    bool stop = false;
+    for (int c0 = h0; c0 < h1 && !stop; c0 += 32) {
+        const int h = c0 + lane;
+        const int good = h < h1 ? hi[h] : INT_MIN;
+        int v = good;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, v, d);
+            if (lane >= d) v = max(v, t);
         }
-    } else {                                           // most inliers, lowest index on ties, every hypothesis consulted
-        for (; it < h1; it++) {
-            const int good = hi[it];
-            if (good > max(maxgood, m - 1)) { best = it; maxgood = good; }
+        int prev = __shfl_up_sync(0xffffffffu, v, 1);
+        if (lane == 0) prev = INT_MIN;
+        unsigned bal = __ballot_sync(0xffffffffu, h < h1 && good > max(max(prev, maxgood), m - 1));
+        if (select_mode == ZP_SELECT_CV2_REPLAY) {
+            while (bal) {
+                const int l = __ffs(bal) - 1;
+                bal &= bal - 1;
+                if (c0 + l >= niters) { stop = true; break; }       // cv2's loop has ended before this iteration
+                const int g = __shfl_sync(0xffffffffu, good, l);
+                best = c0 + l; maxgood = g; last = c0 + l;
+                niters = zp_update_iters(conf, (double)(n - g) / n, m, niters);
+            }
+            if (c0 + 32 >= niters) stop = true;
+        } else if (bal) {                                  // most inliers, lowest index on ties, every hypothesis consulted
+            const int l = 31 - __clz(bal);
+            best = c0 + l; maxgood = __shfl_sync(0xffffffffu, good, l);
         }
     }
-    rs[4 * b] = niters; rs[4 * b + 1] = maxgood; rs[4 * b + 2] = best; rs[4 * b + 3] = it;
-    if (h1 >= H || (select_mode == ZP_SELECT_CV2_REPLAY && h1 >= niters)) crop_done[b] = 1;
+    if (lane == 0) {
+        const int it = select_mode == ZP_SELECT_CV2_REPLAY ? max(last + 1, max(h0, min(h1, niters))) : h1;
+        rs[4 * b] = niters; rs[4 * b + 1] = maxgood; rs[4 * b + 2] = best; rs[4 * b + 3] = it;
+        if (h1 >= H || (select_mode == ZP_SELECT_CV2_REPLAY && h1 >= niters)) crop_done[b] = 1;
+    }
 }
 
 constexpr int FIN_THREADS_MAX = 256;       // threads per crop: 256 (one CTA per SM) or 128 (two CTAs per SM), see zp_launch_final
@@ -1003,7 +1026,8 @@ int zp_launch_rs_init(zp_ctx* ctx, const int32_t* counts, int cap, int B, int H,
 
 int zp_launch_rs_replay(zp_ctx* ctx, const int32_t* counts, int cap, const int32_t* hyp_inliers, int B, int H, int h0, int h1,
                         int m, double conf, int select_mode, int32_t* rs, int32_t* crop_done, cudaStream_t st) {
-    zp_rs_replay_kernel<<<(B + 63) / 64, 64, 0, st>>>(counts, cap, hyp_inliers, B, H, h0, h1, m, conf, select_mode, rs, crop_done);
+    ZP_TIME_BEGIN(ctx, st);
+    zp_rs_replay_kernel<<<(B + RS_WARPS - 1) / RS_WARPS, 32 * RS_WARPS, 0, st>>>(counts, cap, hyp_inliers, B, H, h0, h1, m, conf, select_mode, rs, crop_done);
     ZP_CHECK_LAUNCH(ctx, "zp_rs_replay_kernel");
     return 0;
 }
