@@ -119,6 +119,11 @@ int zp_set_solver(zp_ctx* ctx, int solver);
  * (cv2 never consults a hypothesis at or past its stopping iteration). */
 int zp_set_waves(zp_ctx* ctx, int n, const int32_t* sizes);
 
+/* Shape of the final solve on the winner's inliers: 4 = a thread-block cluster of four CTAs per crop (partial sums combined
+ * through distributed shared memory), 1 = one CTA per crop walking the same four point partitions in turn, 0 = automatic
+ * (the cluster while 4 B CTAs fit one wave).  Both forms produce identical bits. */
+int zp_set_final_form(zp_ctx* ctx, int form);
+
 /* EPnP on each m-point minimal set (float64).  K double [B,9] row-major.  hyp_poses double [B,H,12] out;
  * hypotheses of crops with too few points or degenerate samples are written as NaN. */
 int zp_solve_minimal(zp_ctx* ctx, const float* corr, int cap, const int32_t* counts, const double* K,

@@ -416,3 +416,25 @@ def test_gn_refine_against_twin(eng, batch):
     print("GN polish moves the EPnP pose by median %.4f deg / %.4f mm (max %.4f / %.4f)" % (
         np.median(moved_r), np.median(moved_t), max(moved_r), max(moved_t)))
     assert np.median(moved_r) < 0.05 and np.median(moved_t) < 0.5
+
+
+def test_final_solve_forms_identical(eng, batch):
+    """the final solve as a 4-CTA cluster per crop (partial sums through distributed shared memory) and as one CTA per crop
+    walking the same four point partitions: identical bits, also for the Gauss-Newton polish and for a no-model crop"""
+    outs = []
+    try:
+        for form in (1, 4, 0):
+            eng.set_final_form(form)
+            row = []
+            for final in ("epnp", "epnp+gn"):
+                r = eng.ransac(batch["corr"], batch["counts"], batch["Ks"], final=final, return_details="state")
+                row += [r[k].cpu().numpy() for k in ("poses", "n_inliers", "status", "best_idx", "inlier_mask")]
+            z = torch.zeros_like(batch["corr"][:2]); z[:, 0:2] = batch["corr"][:2, 0:2]        # all 3D points (0,0,0): no model
+            r = eng.ransac(z, batch["counts"][:2], batch["Ks"][:2], return_details="state")
+            row += [r[k].cpu().numpy() for k in ("poses", "n_inliers", "status")]
+            outs.append(row)
+    finally:
+        eng.set_final_form(0)
+    assert (outs[0][12] == 3).all() and np.array_equal(outs[0][10][0], [1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0])
+    for o in outs[1:]:
+        assert all(np.array_equal(a, b) for a, b in zip(outs[0], o))

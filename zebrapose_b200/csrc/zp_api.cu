@@ -6,10 +6,10 @@
 
 int zp_launch_samples(zp_ctx*, const int32_t*, int, int, int, int, int, uint64_t, int32_t*, cudaStream_t);
 int zp_launch_minimal(zp_ctx*, const float*, int, const int32_t*, const double*, const int32_t*, int, int, int, int,
-                      const int32_t*, int, float, double*, float*, int32_t*, cudaStream_t);
+                      const int32_t*, const int32_t*, int, float, double*, float*, int32_t*, cudaStream_t);
 int zp_launch_poses_to_P(zp_ctx*, const double*, const double*, int, int, float, float*, cudaStream_t);
-int zp_launch_score(zp_ctx*, const float*, int, const int32_t*, const float*, int, int, int, int, const int32_t*, float,
-                    int32_t*, bool, cudaStream_t);
+int zp_launch_score(zp_ctx*, const float*, int, const int32_t*, const float*, int, int, int, int, const int32_t*,
+                    const int32_t*, float, int32_t*, bool, cudaStream_t);
 int zp_launch_final(zp_ctx*, const float*, int, const int32_t*, const double*, const double*, const int32_t*, int, int, int,
                     double, int, float, int, double*, int32_t*, int32_t*, int32_t*, uint8_t*, const int32_t*, int32_t*,
                     double*, cudaStream_t);
@@ -156,6 +156,14 @@ int zp_set_solver(zp_ctx* ctx, int solver) {
     if (!ctx) return -1;
     if (solver != ZP_SOLVER_CV2 && solver != ZP_SOLVER_FAST) ZP_FAIL(ctx, -1, "zp_set_solver: bad solver %d", solver);
     ctx->solver = solver;
+    return 0;
+}
+
+int zp_set_final_form(zp_ctx* ctx, int form) {
+    if (!ctx) return -1;
+    if (form != 0 && form != 1 && form != 4) ZP_FAIL(ctx, -1, "zp_set_final_form: 0 (automatic), 1 (one CTA per crop) or 4 (cluster of 4)");
+    ctx->fin_force = form;
+    ctx->fin_form_set = true;
     return 0;
 }
 
@@ -368,8 +376,8 @@ int zp_solve_minimal(zp_ctx* ctx, const float* corr, int cap, const int32_t* cou
     if (m < 4 || m > 8 || H < 1 || H > ZP_MAX_HYPOTHESES) ZP_FAIL(ctx, -1, "zp_solve_minimal: bad m/H %d/%d", m, H);
     ZP_CUDA(ctx, cudaSetDevice(ctx->device));
     if (zp_ws_reserve(ctx, (size_t)B * H * 24 * sizeof(float))) return -2;
-    return zp_launch_minimal(ctx, corr, cap, counts, K, samples, B, H, 0, H, nullptr, m, 2.0f, hyp_poses, (float*)ctx->ws,
-                             nullptr, (cudaStream_t)stream);
+    return zp_launch_minimal(ctx, corr, cap, counts, K, samples, B, H, 0, H, nullptr, nullptr, m, 2.0f, hyp_poses,
+                             (float*)ctx->ws, nullptr, (cudaStream_t)stream);
 }
 
 static int check_corr(zp_ctx* ctx, const float* corr, int cap, const char* who) {
@@ -389,19 +397,20 @@ int zp_score(zp_ctx* ctx, const float* corr, int cap, const int32_t* counts, con
     ZP_CUDA(ctx, cudaSetDevice(ctx->device));
     if (zp_ws_reserve(ctx, (size_t)B * H * 24 * sizeof(float))) return -2;
     if (int r = zp_launch_poses_to_P(ctx, hyp_poses, K, B, H, thr_px, (float*)ctx->ws, (cudaStream_t)stream)) return r;
-    return zp_launch_score(ctx, corr, cap, counts, (const float*)ctx->ws, B, H, 0, H, nullptr, thr_px, hyp_inliers, false,
-                           (cudaStream_t)stream);
+    return zp_launch_score(ctx, corr, cap, counts, (const float*)ctx->ws, B, H, 0, H, nullptr, nullptr, thr_px, hyp_inliers,
+                           false, (cudaStream_t)stream);
 }
 
 static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
-// hypotheses per wave: the caller's plan (zp_set_waves), or automatic -- cv2 stops after 24-46 iterations on crops with
-// ~70 % inliers, so the first wave covers most crops; small batches take fewer, larger waves because a wave costs a fixed
-// latency (three one-wave launches) whatever its size.
+// hypotheses per wave: the caller's plan (zp_set_waves), or automatic.  cv2 stops after 24-46 iterations on crops with
+// ~70 % inliers and after ~137 at 50 %.  A wave costs a fixed latency (six dependent launches) whatever its size, so a batch
+// that does not fill the GPU (<= 128 crops) takes ONE wave; larger batches probe with 32 hypotheses and then run, per crop,
+// only the hypotheses below the niters that probe left (the kernels skip the rest hypothesis by hypothesis).
 static int wave_size(const zp_ctx* ctx, int w, int B) {
     if (ctx->n_waves > 0) return ctx->wave_sizes[w < ctx->n_waves ? w : ctx->n_waves - 1];
-    if (B <= 128) return w == 0 ? 64 : ZP_MAX_HYPOTHESES;
-    return w < 3 ? 32 : ZP_MAX_HYPOTHESES;
+    if (B <= 128) return ZP_MAX_HYPOTHESES;            // latency-bound: one wave of everything
+    return w == 0 ? 32 : ZP_MAX_HYPOTHESES;           // throughput-bound: probe 32, then only what each crop's niters still asks for
 }
 
 static int ransac_impl(zp_ctx* ctx, const float* corr, int cap, const int32_t* counts, const double* K, const int32_t* samples,
@@ -446,9 +455,10 @@ static int ransac_impl(zp_ctx* ctx, const float* corr, int cap, const int32_t* c
         if (hw > H - h0) hw = H - h0;
         ZpRange rw("wave: minimal solver + scoring + adaptive-stop replay");
         // the minimal solver zeroes the inlier counters of its hypotheses: the scoring launch follows without a memset node
-        if (int r = zp_launch_minimal(ctx, corr, cap, counts, K, samples ? samples : d_samples, B, H, h0, hw, d_done, m, thr_px,
-                                      d_hp, d_P, d_hi, st)) return r;
-        if (int r = zp_launch_score(ctx, corr, cap, counts, d_P, B, H, h0, hw, d_done, thr_px, d_hi, true, st)) return r;
+        const int32_t* d_lim = select_mode == ZP_SELECT_CV2_REPLAY && !full ? d_rs : nullptr;
+        if (int r = zp_launch_minimal(ctx, corr, cap, counts, K, samples ? samples : d_samples, B, H, h0, hw, d_done, d_lim, m,
+                                      thr_px, d_hp, d_P, d_hi, st)) return r;
+        if (int r = zp_launch_score(ctx, corr, cap, counts, d_P, B, H, h0, hw, d_done, d_lim, thr_px, d_hi, true, st)) return r;
         if (int r = zp_launch_rs_replay(ctx, counts, cap, d_hi, B, H, h0, h0 + hw, m, confidence, select_mode, d_rs, d_done, st))
             return r;
         h0 += hw;

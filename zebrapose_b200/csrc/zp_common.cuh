@@ -88,8 +88,8 @@ struct zp_ctx {
     int n_waves = 0;
     int wave_sizes[16] = {0};
     // "function attribute set on this context's device" flags (cudaFuncSetAttribute is per device, a ctx is per device)
-    bool cvs_attr_set = false, min_attr_set = false, fin_attr_set = false;
-    int min_force = 0, cvb_minb = 0, cvc_minb = 0;
+    bool cvs_attr_set = false, min_attr_set = false, fin_attr_set = false, fin_form_set = false;
+    int min_force = 0, cvb_minb = 0, cvc_minb = 0, fin_force = 0;
     int score_per_sm[3] = {0, 0, 0};
 };
 

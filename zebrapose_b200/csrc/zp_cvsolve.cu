@@ -30,7 +30,7 @@ constexpr int CVC_PRIV = 60;
 
 struct CvsArgs {
     const float* corr; int cap; const int32_t* counts; const double* K; const int32_t* samples;
-    int B, H, h0, hw; const int32_t* crop_done; int m; double inv_thr;
+    int B, H, h0, hw; const int32_t* crop_done; const int32_t* rs; int m; double inv_thr;
     double* rec; int nhp;                      // hand-off records: field f of local hypothesis g at rec[f * nhp + g]
     double* hyp_poses; float* hyp_P; int32_t* hyp_inliers;
     unsigned long long* dbg;                   // profiling aid (zp_debug_buffer): phase stamps of warp 0 of CTA 0 of stage B
@@ -44,6 +44,8 @@ __device__ __forceinline__ CvsHyp cvs_hyp(const CvsArgs& a, long long gloc) {
     h.b = h.live ? (int)(gloc / a.hw) : 0;
     h.g = (size_t)h.b * a.H + a.h0 + (h.live ? (int)(gloc - (long long)h.b * a.hw) : 0);
     if (h.live && a.crop_done && a.crop_done[h.b]) h.live = false;
+    // hypotheses at or past the crop's current stopping iteration (cv2's niters after the waves so far) are never consulted
+    if (h.live && a.rs && (int)(h.g - (size_t)h.b * a.H) >= a.rs[4 * h.b]) h.live = false;
     h.run = false;
     if (h.live) {
         const int n = min(a.counts[h.b], a.cap);
@@ -170,8 +172,8 @@ __global__ void __launch_bounds__(128) zp_cvs_pick_kernel(CvsArgs a) {
 }
 
 int zp_launch_minimal_cv(zp_ctx* ctx, const float* corr, int cap, const int32_t* counts, const double* K,
-                         const int32_t* samples, int B, int H, int h0, int hw, const int32_t* crop_done, int m,
-                         float thr_px, double* hyp_poses, float* hyp_P, int32_t* hyp_inliers_to_zero, cudaStream_t st) {
+                         const int32_t* samples, int B, int H, int h0, int hw, const int32_t* crop_done, const int32_t* rs,
+                         int m, float thr_px, double* hyp_poses, float* hyp_P, int32_t* hyp_inliers_to_zero, cudaStream_t st) {
     const int smem_a = CVA_THREADS * CVA_PRIV * (int)sizeof(double);
     const int smem_b = CVB_WARPS * CVB_HPW * CVB_HB * (int)sizeof(double);
     const int smem_c = CVC_THREADS * CVC_PRIV * (int)sizeof(double);
@@ -201,7 +203,7 @@ int zp_launch_minimal_cv(zp_ctx* ctx, const float* corr, int cap, const int32_t*
     }
     CvsArgs a;
     a.corr = corr; a.cap = cap; a.counts = counts; a.K = K; a.samples = samples; a.B = B; a.H = H; a.h0 = h0; a.hw = hw;
-    a.crop_done = crop_done; a.m = m; a.inv_thr = 1.0 / (double)thr_px; a.rec = (double*)ctx->cvws; a.nhp = nhp;
+    a.crop_done = crop_done; a.rs = rs; a.m = m; a.inv_thr = 1.0 / (double)thr_px; a.rec = (double*)ctx->cvws; a.nhp = nhp;
     a.hyp_poses = hyp_poses; a.hyp_P = hyp_P; a.hyp_inliers = hyp_inliers_to_zero;
     a.dbg = (unsigned long long*)ctx->dbg_buf;
     ZP_TIME_BEGIN(ctx, st);

@@ -5,20 +5,23 @@
 //                       precomputed table of its raw 32-bit outputs; redraws on duplicates shift later hypotheses, which
 //                       is resolved by a fixed-point iteration over a block prefix sum (exact; usually 1-2 rounds).
 //                       Philox4x32-10 mode is counter based and needs no iteration.
-//   zp_minimal_kernel   one thread per hypothesis: float64 EPnP on the m sampled points (12x12 problem interleaved in
-//                       shared memory so a warp's accesses are conflict-free, row i of the Jacobi held in registers)
+//   zp_minimal_kernel   the FAST solver (zp_set_solver): a quad per hypothesis, float64 EPnP with a bisection / inverse-
+//                       iteration null space.  The default solver is the exact replay of OpenCV's arithmetic, zp_cvsolve.cu.
 //   zp_score_kernel     FP32-FMA bound: every correspondence x every hypothesis.  Correspondence tiles (SoA planes) are
 //                       staged into shared memory with 1-D TMA bulk copies (cp.async.bulk + mbarrier, double buffered),
 //                       hypotheses K[R|t] live in shared memory and are broadcast; the test is division free:
 //                       (x - u z)^2 + (y - v z)^2 <= thr^2 z^2.  Counts: per-thread -> warp REDUX -> shared -> global.
-//   zp_final_kernel     one CTA per crop: cv2's sequential "strictly greater + RANSACUpdateNumIters" rule replayed over
-//                       the H counts (or argmax), then EPnP on all inliers of the winner: block reductions of the 52
-//                       EPnP sums, 16-lane cooperative Jacobi for the 12x12 null space, the three beta candidates on
-//                       three lanes, optional Gauss-Newton polish of the reprojection error
+//   zp_rs_*_kernel      cv2's loop state per crop (niters, maxGood, best) advanced wave by wave: "strictly greater" update +
+//                       RANSACUpdateNumIters; crops that have reached their stopping iteration skip the later waves
+//   zp_final_cl_kernel  EPnP on all inliers of the winner, a 4-CTA thread-block cluster per crop (or one CTA walking the same
+//                       four partitions): inlier set (doubtful points by cv2's own arithmetic), reductions of the 52 EPnP
+//                       sums through distributed shared memory, 16-lane null space, the three beta candidates on three
+//                       lanes, optional Gauss-Newton polish of the reprojection error
 //
 // Algorithmic FP32 work of scoring: 27 flop per (correspondence, hypothesis).
 #include <climits>
 #include <stdlib.h>
+#include <cooperative_groups.h>
 #include "zp_common.cuh"
 
 // phase timestamps of thread 0 of CTA 0 (profiling aid, read with zp_debug_clocks): slots 0-9 final kernel, 10-15 minimal
@@ -239,7 +242,8 @@ template <int MINB>
 __global__ void __launch_bounds__(MIN_THREADS, MINB)
 zp_minimal_kernel(const float* __restrict__ corr, int cap, const int32_t* __restrict__ counts,
                   const double* __restrict__ Kmat, const int32_t* __restrict__ samples, int B, int H, int h0, int hw,
-                  const int32_t* __restrict__ crop_done /* nullable: crops that reached cv2's adaptive stop */, int m,
+                  const int32_t* __restrict__ crop_done /* nullable: crops that reached cv2's adaptive stop */,
+                  const int32_t* __restrict__ rs /* nullable: [B,4] loop state, rs[4b] = the crop's current niters */, int m,
                   double inv_thr, double* __restrict__ hyp_poses, float* __restrict__ hyp_P,
                   int32_t* __restrict__ hyp_inliers /* nullable: zeroed here so the scoring launch needs no memset */) {
     extern __shared__ __align__(16) double s_min[];            // per hypothesis: z[12x13] | d[12] | e[12] | V[4x12]
@@ -252,7 +256,7 @@ zp_minimal_kernel(const float* __restrict__ corr, int cap, const int32_t* __rest
     const int gl = g_raw < total ? g_raw : total - 1;   // dead quads shadow the last hypothesis (all lanes take part in shuffles)
     const int b = gl / hw;
     const int g = b * H + h0 + (gl - b * hw);
-    const bool live = g_raw < total && !(crop_done && crop_done[b]);
+    const bool live = g_raw < total && !(crop_done && crop_done[b]) && !(rs && h0 + (gl - b * hw) >= rs[4 * b]);
     if (!__syncthreads_or(live)) return;           // every hypothesis of this CTA belongs to a finished crop
     ZP_STAMP(10);
     const int32_t* sidx = samples + (size_t)g * m;
@@ -404,6 +408,7 @@ struct ScoreArgs {
     int hchunk, n_hc;            // hypotheses per work item and items per tile (small batches are cut finer)
     int h0, hw;                  // this launch scores hypotheses [h0, h0 + hw) ...
     const int32_t* crop_done;    // ... of the crops that have not reached cv2's adaptive stop (nullable: all)
+    const int32_t* rs;           // nullable [B,4]: rs[4b] = the crop's current niters; hypotheses at or past it are not scored
 };
 
 // Persistent CTAs pulling work items (crop b, tile of SC_TILE correspondences) from a global ticket counter; items are
@@ -452,7 +457,8 @@ __global__ void __launch_bounds__(SC_GROUP * SC_NG) zp_score_kernel(ScoreArgs a)
         const float* cb = a.corr + (size_t)b * 5 * a.cap + start;
         const uint32_t bytes = (uint32_t)((cnt + 3) & ~3) * 4u;        // 16-byte granules; cap % 4 == 0 keeps it in bounds
         f32x2 nu[SC_PPT / 2], nv[SC_PPT / 2], X[SC_PPT / 2], Y[SC_PPT / 2], Z[SC_PPT / 2];   // point pairs (j, j+1)
-        const int h_begin = a.h0 + hc * a.hchunk, h_end = min(a.h0 + a.hw, h_begin + a.hchunk);
+        const int h_begin = a.h0 + hc * a.hchunk;
+        const int h_end = min(min(a.h0 + a.hw, h_begin + a.hchunk), a.rs ? a.rs[4 * b] : INT_MAX);
         for (int h0 = h_begin; h0 < h_end; h0 += SC_HB) {
             const int hb = min(SC_HB, h_end - h0);
             if (tid == 0) {
@@ -630,7 +636,6 @@ zp_rs_replay_kernel(const int32_t* __restrict__ counts, int cap, const int32_t* 
     }
 }
 
-constexpr int FIN_THREADS_MAX = 256;       // threads per crop: 256 (one CTA per SM) or 128 (two CTAs per SM), see zp_launch_final
 
 template <int NV, int FIN_THREADS>
 __device__ __forceinline__ void block_reduce(double* v, double* s_red /* [FIN_THREADS/32][NV] */, double* s_out) {
@@ -660,14 +665,54 @@ struct FinalArgs {
     double* records;                             // nullable [B,14]: pose | n_inliers | status as doubles (the multi-GPU gather record)
 };
 
-// (register budget measured: 255 registers per thread beat 128 (2 x 256 threads per SM) and 80 at 64 AND at 1024 crops --
-// 3.72 vs 3.89 vs 4.26 ms per 1024-crop step; what does pay at saturation is two CTAs of 128 threads, still at 255
-// registers: zp_launch_final; profiles/README.md)
-template <int FIN_THREADS>
-__global__ void __launch_bounds__(FIN_THREADS) zp_final_kernel(FinalArgs a) {
-    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
-    __shared__ double s_red[(FIN_THREADS / 32) * 52];
-    __shared__ double s_sum[52];
+// ---------------------------------------------------------------------------------------------------------------
+// Winner's inliers -> final EPnP, spread over a THREAD-BLOCK CLUSTER.  Round 1's form -- one CTA per crop -- kept 64 of the
+// 148 SMs busy at BASELINE's 64-crop batches, and its point passes (inlier set, scatter, 52 EPnP sums, candidate errors:
+// 83 of CTA 0's 127 us, profiles/r2k_final_phases.txt) ran on 4 warps that can each issue one FP64 instruction every ~3.3
+// cycles: 172 us at 64 crops against 119 us for the cluster (693 vs 1280 us at 1024 crops, where the GPU is full anyway).  Here a
+// crop's points are cut into FIN_VR = 4 "virtual ranks" of 4 warps each (16 warp chunks); with CL = 4 a virtual rank is a
+// CTA of a 4-CTA cluster and the partial sums are combined through distributed shared memory, with CL = 1 one CTA walks the
+// four virtual ranks in turn.  Partition, per-rank reduction tree and the order ((p0 + p1) + p2) + p3 are the same in
+// both, so a crop's pose does not depend on which form ran (small batches take the cluster, saturating ones the single
+// CTA).  The serial solver phases run redundantly in every CTA of a cluster -- same inputs, same bits, no broadcast.
+// ---------------------------------------------------------------------------------------------------------------
+namespace cg = cooperative_groups;
+constexpr int FIN_VR = 4;              // virtual ranks per crop
+constexpr int FCL_THREADS = 128;
+constexpr int FCL_WARPS = FCL_THREADS / 32;
+
+template <int CL>
+__device__ __forceinline__ void fcl_sync() {
+    if (CL > 1) cg::this_cluster().sync();
+    else __syncthreads();
+}
+
+// s_part[vr_local][q] of every virtual rank -> s_sum[q] = ((p0 + p1) + p2) + p3, identical in every CTA
+template <int CL, int NV>
+__device__ __forceinline__ void fcl_total(double (*s_part)[56], double* s_sum) {
+    constexpr int NR = FIN_VR / CL;
+    fcl_sync<CL>();
+    for (int q = threadIdx.x; q < NV; q += FCL_THREADS) {
+        double t = 0;
+#pragma unroll
+        for (int vr = 0; vr < FIN_VR; vr++) {
+            const double* src = &s_part[vr % NR][q];
+            if (CL > 1) src = cg::this_cluster().map_shared_rank(src, vr / NR);
+            t += *src;
+        }
+        s_sum[q] = t;
+    }
+    fcl_sync<CL>();
+}
+
+template <int CL>
+__global__ void __launch_bounds__(FCL_THREADS) zp_final_cl_kernel(FinalArgs a) {
+    constexpr int NR = FIN_VR / CL;                 // virtual ranks walked by this CTA
+    const int b = blockIdx.x / CL, rank = blockIdx.x % CL;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    __shared__ double s_red[FCL_WARPS * 52];
+    __shared__ double s_part[NR][56];               // per virtual rank: up to 52 sums | inlier count | first inlier index
+    __shared__ double s_sum[56];
     __shared__ double s_V[48];
     __shared__ __align__(16) double s_eig[ZP_SYM_DOUBLES + 24];
     __shared__ ZpControl s_cp;
@@ -675,19 +720,15 @@ __global__ void __launch_bounds__(FIN_THREADS) zp_final_kernel(FinalArgs a) {
     __shared__ double s_candR[3][9], s_candt[3][3];
     __shared__ int s_candok[3];
     __shared__ double s_pose[12];
-    __shared__ int s_first, s_n, s_best, s_status;
-    extern __shared__ __align__(8) unsigned char s_dynb[];   // inlier bitset (cap+31)/32 words | packed inlier indices
-    uint32_t* s_mask = (uint32_t*)s_dynb;
-    // compacted inlier indices: warp w owns the points [w * chunk, (w + 1) * chunk) and packs the inliers among them
-    // at the start of its own segment (deterministic order, no cross-warp scan); s_wpre = exclusive prefix of the counts
-    uint16_t* s_idx = (uint16_t*)(s_mask + (a.cap + 31) / 32 + 1);
-    __shared__ int s_wcnt[FIN_THREADS / 32], s_wpre[FIN_THREADS / 32];
+    __shared__ int s_best, s_status;
+    __shared__ int s_wcnt[NR][FCL_WARPS], s_wpre[NR][FCL_WARPS], s_nvr[NR];
+    extern __shared__ __align__(8) unsigned char s_dynb[];
+    uint16_t* s_idx = (uint16_t*)s_dynb;            // packed inlier indices: [NR][FCL_WARPS][chunk]
 
-    ZP_STAMP(0);
+    const bool writer = rank == 0;
     double* out = a.poses + 12 * (size_t)b;
     const int n_raw = a.counts[b];
     const int n = min(n_raw, a.cap);
-    // ---- winner: chosen by zp_rs_replay_kernel (cv2's sequential rule over the counts of the hypotheses that were run)
     if (tid == 0) {
         int best = -1, st = ZP_OK;
         if (n_raw == 0) st = ZP_NO_MASK_PIXELS;
@@ -697,21 +738,24 @@ __global__ void __launch_bounds__(FIN_THREADS) zp_final_kernel(FinalArgs a) {
             if (best < 0) st = ZP_RANSAC_NO_MODEL;
         }
         s_best = best; s_status = st;
-        a.status[b] = st;
-        if (a.best_idx) a.best_idx[b] = best;
-        if (a.iters_run) a.iters_run[b] = n < 6 ? 0 : a.rs[4 * b + 3];
-        s_first = 0x7fffffff; s_n = 0;
+        if (writer) {
+            a.status[b] = st;
+            if (a.best_idx) a.best_idx[b] = best;
+            if (a.iters_run) a.iters_run[b] = n < 6 ? 0 : a.rs[4 * b + 3];
+        }
     }
-    for (int i = tid; i < (a.cap + 31) / 32; i += FIN_THREADS) s_mask[i] = 0;
     __syncthreads();
     const int best = s_best;
+    const int chunk = ((n + FIN_VR * FCL_THREADS - 1) / (FIN_VR * FCL_THREADS)) * 32;   // points per virtual warp
     if (best < 0) {     // no model: cv2 leaves rvec = tvec = 0 and the reference reports R = I, t = 0
-        if (tid < 12) out[tid] = (tid == 0 || tid == 4 || tid == 8) ? 1.0 : 0.0;
-        if (tid == 0) a.n_inliers[b] = 0;
-        if (a.records && tid < 14)
-            a.records[14 * (size_t)b + tid] = tid < 12 ? ((tid == 0 || tid == 4 || tid == 8) ? 1.0 : 0.0) : tid == 12 ? 0.0 : (double)s_status;
+        if (writer) {
+            if (tid < 12) out[tid] = (tid == 0 || tid == 4 || tid == 8) ? 1.0 : 0.0;
+            if (tid == 0) a.n_inliers[b] = 0;
+            if (a.records && tid < 14)
+                a.records[14 * (size_t)b + tid] = tid < 12 ? ((tid == 0 || tid == 4 || tid == 8) ? 1.0 : 0.0) : tid == 12 ? 0.0 : (double)s_status;
+        }
         if (a.inlier_mask)
-            for (int i = tid; i < a.cap; i += FIN_THREADS) a.inlier_mask[(size_t)b * a.cap + i] = 0;
+            for (int i = rank * FCL_THREADS + tid; i < a.cap; i += CL * FCL_THREADS) a.inlier_mask[(size_t)b * a.cap + i] = 0;
         return;
     }
     const float* cb = a.corr + (size_t)b * 5 * a.cap;
@@ -723,99 +767,129 @@ __global__ void __launch_bounds__(FIN_THREADS) zp_final_kernel(FinalArgs a) {
     const float4 p0 = make_float4(P[0], P[1], P[2], P[3]), p1 = make_float4(P[4], P[5], P[6], P[7]),
                  p2 = make_float4(P[8], P[9], P[10], P[11]);
     const float thr2 = a.thr2;
-    ZP_STAMP(1);
-    // ---- pass 0: inlier set of the winner (same predicate as zp_score_kernel), centroid
     double acc[52];
-    for (int q = 0; q < 52; q++) acc[q] = 0;
-    int my_first = 0x7fffffff;
-    constexpr int FIN_WARPS = FIN_THREADS / 32;
-    const int warp = tid >> 5;
-    const int chunk = ((n + FIN_THREADS - 1) / FIN_THREADS) * 32;      // points per warp (whole 32-point groups)
-    int wcount = 0;                                                     // warp-uniform: inliers packed so far
-#pragma unroll 4
-    for (int j = 0; j < chunk; j += 32) {             // warp-aligned so the bitset is built with ballots
-        const int i = warp * chunk + j + lane;
-        bool in = false;
-        if (i < n) {
-            const float d = zp_inlier_d(p0, p1, p2, pu[i] * a.inv_thr, pv[i] * a.inv_thr, pX[i], pY[i], pZ[i]);
-            in = __float_as_int(d) < 0;
-            // within ~1e-3 px of the threshold (|d| <= 1e-3 z^2 in threshold units; z^2 ~ P row 2 . X squared): cv2's own
-            // arithmetic decides, so the final inlier set is cv2's
-            const float z = fmaf(p2.x, pX[i], fmaf(p2.y, pY[i], fmaf(p2.z, pZ[i], p2.w)));
-            if (fabsf(d) <= 1e-3f * z * z)
-                in = zp_inlier_exact(hp, Kb[0], Kb[4], Kb[2], Kb[5], pu[i], pv[i], pX[i], pY[i], pZ[i], thr2);
+    // ---- pass 0: inlier set of the winner (same predicate as zp_score_kernel, doubtful points by cv2's arithmetic), centroid
+    for (int vl = 0; vl < NR; vl++) {
+        const int vw = (rank * NR + vl) * FCL_WARPS + warp;          // virtual warp: points [vw * chunk, (vw + 1) * chunk)
+        uint16_t* seg = s_idx + ((size_t)vl * FCL_WARPS + warp) * chunk;
+        acc[0] = acc[1] = acc[2] = 0;
+        int my_first = 0x7fffffff, wcount = 0;
+        for (int j0 = 0; j0 < chunk; j0 += 128) {                    // four 32-point groups per trip, their 20 loads up front
+            float fu[4], fv[4], fX[4], fY[4], fZ[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const int i = vw * chunk + j0 + 32 * q + lane;
+                const bool ld = j0 + 32 * q < chunk && i < n;
+                fu[q] = ld ? pu[i] : 0.f; fv[q] = ld ? pv[i] : 0.f; fX[q] = ld ? pX[i] : 0.f; fY[q] = ld ? pY[i] : 0.f; fZ[q] = ld ? pZ[i] : 0.f;
+            }
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                if (j0 + 32 * q >= chunk) break;                     // warp-uniform
+                const int i = vw * chunk + j0 + 32 * q + lane;
+                bool in = false;
+                if (i < n) {
+                    const float d = zp_inlier_d(p0, p1, p2, fu[q] * a.inv_thr, fv[q] * a.inv_thr, fX[q], fY[q], fZ[q]);
+                    in = __float_as_int(d) < 0;
+                    const float z = fmaf(p2.x, fX[q], fmaf(p2.y, fY[q], fmaf(p2.z, fZ[q], p2.w)));
+                    if (fabsf(d) <= 1e-3f * z * z)                   // within ~1e-3 px of the threshold: cv2's own arithmetic decides
+                        in = zp_inlier_exact(hp, Kb[0], Kb[4], Kb[2], Kb[5], fu[q], fv[q], fX[q], fY[q], fZ[q], thr2);
+                }
+                const unsigned bal = __ballot_sync(0xffffffffu, in);
+                if (a.inlier_mask && i < n) a.inlier_mask[(size_t)b * a.cap + i] = in;
+                if (in) {
+                    seg[wcount + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)i;
+                    my_first = min(my_first, i);
+                    acc[0] += (double)fX[q]; acc[1] += (double)fY[q]; acc[2] += (double)fZ[q];
+                }
+                wcount += __popc(bal);
+            }
         }
-        const unsigned bal = __ballot_sync(0xffffffffu, in);
-        if (lane == 0 && i < a.cap) s_mask[i >> 5] = bal;
-        if (a.inlier_mask && i < n) a.inlier_mask[(size_t)b * a.cap + i] = in;
-        if (in) {
-            s_idx[warp * chunk + wcount + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)i;
-            my_first = min(my_first, i);
-            acc[0] += pX[i]; acc[1] += pY[i]; acc[2] += pZ[i];
+        my_first = __reduce_min_sync(0xffffffffu, my_first);
+        if (lane == 0) { s_wcnt[vl][warp] = wcount; s_red[FCL_WARPS * 3 + warp] = (double)my_first; }
+        block_reduce<3, FCL_THREADS>(acc, s_red, s_part[vl]);
+        if (tid == 0) {
+            int run = 0;
+            double fi = 2147483647.0;
+            for (int w = 0; w < FCL_WARPS; w++) { s_wpre[vl][w] = run; run += s_wcnt[vl][w]; fi = fmin(fi, s_red[FCL_WARPS * 3 + w]); }
+            s_nvr[vl] = run;
+            s_part[vl][3] = (double)run;
+            s_part[vl][4] = fi;
         }
-        wcount += __popc(bal);
+        __syncthreads();
     }
     if (a.inlier_mask)
-        for (int i = n + tid; i < a.cap; i += FIN_THREADS) a.inlier_mask[(size_t)b * a.cap + i] = 0;
-    my_first = __reduce_min_sync(0xffffffffu, my_first);
-    if (lane == 0) { s_wcnt[warp] = wcount; atomicAdd(&s_n, wcount); atomicMin(&s_first, my_first); }
-    block_reduce<3, FIN_THREADS>(acc, s_red, s_sum);
-    if (tid == 0) {
-        int run = 0;
-        for (int w = 0; w < FIN_WARPS; w++) { s_wpre[w] = run; run += s_wcnt[w]; }
-    }
-    const int ni = s_n;
-    // k-th inlier (k < ni) in the packed per-warp segments
-    auto inlier_at = [&](int k) -> int {
-        int w = 0;
+        for (int i = n + rank * FCL_THREADS + tid; i < a.cap; i += CL * FCL_THREADS) a.inlier_mask[(size_t)b * a.cap + i] = 0;
+    // totals: centroid sums and the inlier count add up, the first inlier index is a minimum
+    {
+        fcl_sync<CL>();
+        if (tid < 5) {
+            double t = tid == 4 ? 2147483647.0 : 0.0;
 #pragma unroll
-        for (int q = 1; q < FIN_WARPS; q++) w += k >= s_wpre[q];
-        return s_idx[w * chunk + (k - s_wpre[w])];
-    };
-    if (tid == 0) a.n_inliers[b] = ni;
+            for (int vr = 0; vr < FIN_VR; vr++) {
+                const double* src = &s_part[vr % NR][tid];
+                if (CL > 1) src = cg::this_cluster().map_shared_rank(src, vr / NR);
+                t = tid == 4 ? fmin(t, *src) : t + *src;
+            }
+            s_sum[tid] = t;
+        }
+        fcl_sync<CL>();
+    }
+    const int ni = (int)s_sum[3];
+    const int first = (int)s_sum[4];
+    if (writer && tid == 0) a.n_inliers[b] = ni;
     if (ni < 4) {       // cannot happen after selection (good > m-1 >= 3) but keep the output defined
-        if (tid < 12) out[tid] = hp[tid];
-        if (a.records && tid < 14) a.records[14 * (size_t)b + tid] = tid < 12 ? hp[tid] : tid == 12 ? (double)ni : (double)s_status;
+        if (writer) {
+            if (tid < 12) out[tid] = hp[tid];
+            if (a.records && tid < 14) a.records[14 * (size_t)b + tid] = tid < 12 ? hp[tid] : tid == 12 ? (double)ni : (double)s_status;
+        }
         return;
     }
     const double c0[3] = {s_sum[0] / ni, s_sum[1] / ni, s_sum[2] / ni};
-    __syncthreads();
-    ZP_STAMP(2);
+    // k-th inlier of local virtual rank vl (k < s_nvr[vl]) in its packed per-warp segments
+    auto inlier_at = [&](int vl, int k) -> int {
+        int w = 0;
+#pragma unroll
+        for (int q = 1; q < FCL_WARPS; q++) w += k >= s_wpre[vl][q];
+        return s_idx[((size_t)vl * FCL_WARPS + w) * chunk + (k - s_wpre[vl][w])];
+    };
     // ---- pass 1: scatter matrix
-    for (int q = 0; q < 9; q++) acc[q] = 0;
+    for (int vl = 0; vl < NR; vl++) {
+        for (int q = 0; q < 9; q++) acc[q] = 0;
+        const int nv = s_nvr[vl];
 #pragma unroll 4
-    for (int k = tid; k < ni; k += FIN_THREADS) {     // inliers only: every lane has work
-        const int i = inlier_at(k);
-        double d0 = pX[i] - c0[0], d1 = pY[i] - c0[1], d2 = pZ[i] - c0[2];
-        acc[0] = fma(d0, d0, acc[0]); acc[1] = fma(d0, d1, acc[1]); acc[2] = fma(d0, d2, acc[2]);
-        acc[4] = fma(d1, d1, acc[4]); acc[5] = fma(d1, d2, acc[5]); acc[8] = fma(d2, d2, acc[8]);
+        for (int k = tid; k < nv; k += FCL_THREADS) {
+            const int i = inlier_at(vl, k);
+            double d0 = pX[i] - c0[0], d1 = pY[i] - c0[1], d2 = pZ[i] - c0[2];
+            acc[0] = fma(d0, d0, acc[0]); acc[1] = fma(d0, d1, acc[1]); acc[2] = fma(d0, d2, acc[2]);
+            acc[4] = fma(d1, d1, acc[4]); acc[5] = fma(d1, d2, acc[5]); acc[8] = fma(d2, d2, acc[8]);
+        }
+        acc[3] = acc[1]; acc[6] = acc[2]; acc[7] = acc[5];
+        block_reduce<9, FCL_THREADS>(acc, s_red, s_part[vl]);
     }
-    acc[3] = acc[1]; acc[6] = acc[2]; acc[7] = acc[5];
-    block_reduce<9, FIN_THREADS>(acc, s_red, s_sum);
-    ZP_STAMP(3);
+    fcl_total<CL, 9>(s_part, s_sum);
     if (tid == 0) {
         double C[9];
         for (int q = 0; q < 9; q++) C[q] = s_sum[q];
         zp_control_points(c0, C, (double)ni, s_cp);
     }
     __syncthreads();
-    ZP_STAMP(4);
     // ---- pass 2: the 52 EPnP sums
     const ZpCam cam{Kb[0], Kb[4], Kb[2], Kb[5]};
-    {
+    for (int vl = 0; vl < NR; vl++) {
         ZpSums s;
         for (int q = 0; q < 10; q++) { s.s0[q] = 0; s.sx[q] = 0; s.sy[q] = 0; s.sr[q] = 0; }
         for (int q = 0; q < 12; q++) s.w[q] = 0;
         const ZpControl cp = s_cp;
+        const int nv = s_nvr[vl];
         // the five loads of the next point are issued before the ~80 FP64 operations of the current one
         int k = tid;
-        bool in = k < ni;
-        int i = in ? inlier_at(k) : 0;
+        bool in = k < nv;
+        int i = in ? inlier_at(vl, k) : 0;
         float fX = in ? pX[i] : 0.f, fY = in ? pY[i] : 0.f, fZ = in ? pZ[i] : 0.f, fu = in ? pu[i] : 0.f, fv = in ? pv[i] : 0.f;
-        while (in) {                                  // walks the packed inlier list: no idle lanes, no skipped points
-            const int k2 = k + FIN_THREADS;
-            const bool in2 = k2 < ni;
-            const int i2 = in2 ? inlier_at(k2) : 0;
+        while (in) {
+            const int k2 = k + FCL_THREADS;
+            const bool in2 = k2 < nv;
+            const int i2 = in2 ? inlier_at(vl, k2) : 0;
             const float gX = in2 ? pX[i2] : 0.f, gY = in2 ? pY[i2] : 0.f, gZ = in2 ? pZ[i2] : 0.f, gu = in2 ? pu[i2] : 0.f, gv = in2 ? pv[i2] : 0.f;
             {
                 double X = fX, Y = fY, Z = fZ;
@@ -827,37 +901,29 @@ __global__ void __launch_bounds__(FIN_THREADS) zp_final_kernel(FinalArgs a) {
         }
         for (int q = 0; q < 10; q++) { acc[q] = s.s0[q]; acc[10 + q] = s.sx[q]; acc[20 + q] = s.sy[q]; acc[30 + q] = s.sr[q]; }
         for (int q = 0; q < 12; q++) acc[40 + q] = s.w[q];
+        block_reduce<52, FCL_THREADS>(acc, s_red, s_part[vl]);
     }
-    block_reduce<52, FIN_THREADS>(acc, s_red, s_sum);
+    fcl_total<CL, 52>(s_part, s_sum);
     if (tid < 10) { s_sums.s0[tid] = s_sum[tid]; s_sums.sx[tid] = s_sum[10 + tid]; s_sums.sy[tid] = s_sum[20 + tid]; s_sums.sr[tid] = s_sum[30 + tid]; }
     if (tid < 12) s_sums.w[tid] = s_sum[40 + tid];
     if (tid == 0) s_sums.n = ni;
     __syncthreads();
-    ZP_STAMP(5);
-    // ---- 12x12 null space on 16 lanes of warp 0 (cooperative Householder; bisection + inverse iteration on 4 of them)
+    // ---- 12x12 null space on 16 lanes of warp 0, the three beta candidates on three lanes (every CTA of a cluster: same bits)
     if (tid < 32) {
         if (tid < 16) zp_nullspace4<16>(ZpSym12{s_eig}, s_eig + ZP_SYM_DOUBLES, s_eig + ZP_SYM_DOUBLES + 12, s_sums.s0, cam, tid, 0xFFFFu, s_V);
-        ZP_STAMP(6);
         __syncwarp();
-        ZP_STAMP(7);
-        // ---- the three beta candidates on three lanes
         if (lane < 3) {
             ZpMat V{s_V, 1};
             double L[60], rho[6], af[4];
             zp_L_rho(V, s_cp, L, rho);
             ZpHorn hs;
             zp_horn_inputs(s_sums, hs);
-            int f = s_first;
-            zp_alphas(s_cp, pX[f], pY[f], pZ[f], af);
+            zp_alphas(s_cp, pX[first], pY[first], pZ[first], af);
             s_candok[lane] = zp_candidate(lane, L, rho, V, hs, af, c0, s_candR[lane], s_candt[lane]) ? 1 : 0;
         }
     }
     __syncthreads();
-    ZP_STAMP(8);
     // ---- pass 3: mean reprojection distance of the three candidates, pick the best
-    for (int q = 0; q < 3; q++) acc[q] = 0;
-    // over the packed inlier list; unrolled so that the FP64 divide / square-root chains of two points interleave (with 8
-    // warps per SM they are latency-bound otherwise)
     {
         double cR[3][9], ct[3][3];
         bool cok[3];
@@ -869,15 +935,20 @@ __global__ void __launch_bounds__(FIN_THREADS) zp_final_kernel(FinalArgs a) {
 #pragma unroll
             for (int e = 0; e < 3; e++) ct[c][e] = cok[c] ? s_candt[c][e] : (e == 2 ? 1.0 : 0.0);
         }
+        for (int vl = 0; vl < NR; vl++) {
+            for (int q = 0; q < 3; q++) acc[q] = 0;
+            const int nv = s_nvr[vl];
 #pragma unroll 2
-        for (int k = tid; k < ni; k += FIN_THREADS) {
-            const int i = inlier_at(k);
-            const double X = pX[i], Y = pY[i], Z = pZ[i], u = pu[i], v = pv[i];
+            for (int k = tid; k < nv; k += FCL_THREADS) {
+                const int i = inlier_at(vl, k);
+                const double X = pX[i], Y = pY[i], Z = pZ[i], u = pu[i], v = pv[i];
 #pragma unroll
-            for (int c = 0; c < 3; c++) acc[c] += zp_reproj_dist(cR[c], ct[c], cam, X, Y, Z, u, v);
+                for (int c = 0; c < 3; c++) acc[c] += zp_reproj_dist(cR[c], ct[c], cam, X, Y, Z, u, v);
+            }
+            block_reduce<3, FCL_THREADS>(acc, s_red, s_part[vl]);
         }
     }
-    block_reduce<3, FIN_THREADS>(acc, s_red, s_sum);
+    fcl_total<CL, 3>(s_part, s_sum);
     if (tid == 0) {
         int pick = -1;
         double be = 0;
@@ -901,9 +972,11 @@ __global__ void __launch_bounds__(FIN_THREADS) zp_final_kernel(FinalArgs a) {
             double R[9], t[3];
             for (int e = 0; e < 9; e++) R[e] = s_pose[e];
             for (int e = 0; e < 3; e++) t[e] = s_pose[9 + e];
-            for (int q = 0; q < 27; q++) acc[q] = 0;     // 21 JtJ (upper) + 6 Jtr
-            for (int i = tid; i < n; i += FIN_THREADS)
-                if (s_mask[i >> 5] >> (i & 31) & 1u) {
+            for (int vl = 0; vl < NR; vl++) {
+                for (int q = 0; q < 27; q++) acc[q] = 0;     // 21 JtJ (upper) + 6 Jtr
+                const int nv = s_nvr[vl];
+                for (int k = tid; k < nv; k += FCL_THREADS) {
+                    const int i = inlier_at(vl, k);
                     double X = pX[i], Y = pY[i], Z = pZ[i];
                     double px = R[0] * X + R[1] * Y + R[2] * Z, py = R[3] * X + R[4] * Y + R[5] * Z, pz = R[6] * X + R[7] * Y + R[8] * Z;
                     double xc = px + t[0], yc = py + t[1], zc = pz + t[2], iz = 1.0 / zc;
@@ -917,7 +990,9 @@ __global__ void __launch_bounds__(FIN_THREADS) zp_final_kernel(FinalArgs a) {
                         for (int c = r; c < 6; c++) { acc[q] += Ju[r] * Ju[c] + Jv[r] * Jv[c]; q++; }
                     for (int r = 0; r < 6; r++) acc[21 + r] += Ju[r] * ru + Jv[r] * rv;
                 }
-            block_reduce<27, FIN_THREADS>(acc, s_red, s_sum);
+                block_reduce<27, FCL_THREADS>(acc, s_red, s_part[vl]);
+            }
+            fcl_total<CL, 27>(s_part, s_sum);
             if (tid == 0) {
                 double A[36], g[6], d[6];
                 int q = 0;
@@ -954,9 +1029,11 @@ __global__ void __launch_bounds__(FIN_THREADS) zp_final_kernel(FinalArgs a) {
             __syncthreads();
         }
     }
-    ZP_STAMP(9);
-    if (tid < 12) out[tid] = s_pose[tid];
-    if (a.records && tid < 14) a.records[14 * (size_t)b + tid] = tid < 12 ? s_pose[tid] : tid == 12 ? (double)ni : (double)s_status;
+    if (writer) {
+        if (tid < 12) out[tid] = s_pose[tid];
+        if (a.records && tid < 14) a.records[14 * (size_t)b + tid] = tid < 12 ? s_pose[tid] : tid == 12 ? (double)ni : (double)s_status;
+    }
+    if (CL > 1) cg::this_cluster().sync();          // no CTA may exit while a peer can still read its shared memory
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -983,15 +1060,15 @@ int zp_launch_samples(zp_ctx* ctx, const int32_t* counts, int cap, int B, int H,
 }
 
 int zp_launch_minimal_cv(zp_ctx*, const float*, int, const int32_t*, const double*, const int32_t*, int, int, int, int,
-                         const int32_t*, int, float, double*, float*, int32_t*, cudaStream_t);
+                         const int32_t*, const int32_t*, int, float, double*, float*, int32_t*, cudaStream_t);
 
 // hypotheses [h0, h0 + hw) of the crops not flagged in crop_done (nullable).  ctx->solver picks the solver: the exact
 // replay of cv2's EPnP (zp_cvsolve.cu, default) or the fast float64 solver of this file.
 int zp_launch_minimal(zp_ctx* ctx, const float* corr, int cap, const int32_t* counts, const double* K,
-                      const int32_t* samples, int B, int H, int h0, int hw, const int32_t* crop_done, int m, float thr_px,
-                      double* hyp_poses, float* hyp_P, int32_t* hyp_inliers_to_zero, cudaStream_t st) {
+                      const int32_t* samples, int B, int H, int h0, int hw, const int32_t* crop_done, const int32_t* rs, int m,
+                      float thr_px, double* hyp_poses, float* hyp_P, int32_t* hyp_inliers_to_zero, cudaStream_t st) {
     if (ctx->solver == ZP_SOLVER_CV2)
-        return zp_launch_minimal_cv(ctx, corr, cap, counts, K, samples, B, H, h0, hw, crop_done, m, thr_px, hyp_poses, hyp_P,
+        return zp_launch_minimal_cv(ctx, corr, cap, counts, K, samples, B, H, h0, hw, crop_done, rs, m, thr_px, hyp_poses, hyp_P,
                                     hyp_inliers_to_zero, st);
     const int per_cta = MIN_THREADS / 4;
     int total = B * hw;
@@ -1011,8 +1088,8 @@ int zp_launch_minimal(zp_ctx* ctx, const float* corr, int cap, const int32_t* co
     // room for another lane's kernels on the SM (257 k vs 236 k poses/s with 3 lanes).  ZP_MIN_BLOCKS=2|3 pins it.
     const bool two = force ? force == 2 : grid > 12 * ctx->sm_count;
     ZP_TIME_BEGIN(ctx, st);
-    if (two) zp_minimal_kernel<2><<<grid, MIN_THREADS, MIN_SMEM_BYTES, st>>>(corr, cap, counts, K, samples, B, H, h0, hw, crop_done, m, 1.0 / (double)thr_px, hyp_poses, hyp_P, hyp_inliers_to_zero);
-    else zp_minimal_kernel<3><<<grid, MIN_THREADS, MIN_SMEM_BYTES, st>>>(corr, cap, counts, K, samples, B, H, h0, hw, crop_done, m, 1.0 / (double)thr_px, hyp_poses, hyp_P, hyp_inliers_to_zero);
+    if (two) zp_minimal_kernel<2><<<grid, MIN_THREADS, MIN_SMEM_BYTES, st>>>(corr, cap, counts, K, samples, B, H, h0, hw, crop_done, rs, m, 1.0 / (double)thr_px, hyp_poses, hyp_P, hyp_inliers_to_zero);
+    else zp_minimal_kernel<3><<<grid, MIN_THREADS, MIN_SMEM_BYTES, st>>>(corr, cap, counts, K, samples, B, H, h0, hw, crop_done, rs, m, 1.0 / (double)thr_px, hyp_poses, hyp_P, hyp_inliers_to_zero);
     ZP_CHECK_LAUNCH(ctx, "zp_minimal_kernel");
     return 0;
 }
@@ -1066,11 +1143,11 @@ static int launch_score_ng(zp_ctx* ctx, ScoreArgs& a, int smem, cudaStream_t st)
 }
 
 int zp_launch_score(zp_ctx* ctx, const float* corr, int cap, const int32_t* counts, const float* hyp_P, int B, int H,
-                    int h0, int hw, const int32_t* crop_done, float thr_px, int32_t* hyp_inliers, bool already_zeroed,
-                    cudaStream_t st) {
+                    int h0, int hw, const int32_t* crop_done, const int32_t* rs, float thr_px, int32_t* hyp_inliers,
+                    bool already_zeroed, cudaStream_t st) {
     ScoreArgs a;
     a.corr = corr; a.cap = cap; a.counts = counts; a.hyp_P = hyp_P; a.B = B; a.H = H; a.inv_thr = 1.0f / thr_px;
-    a.hyp_inliers = hyp_inliers; a.counters = ctx->d_counters; a.h0 = h0; a.hw = hw; a.crop_done = crop_done;
+    a.hyp_inliers = hyp_inliers; a.counters = ctx->d_counters; a.h0 = h0; a.hw = hw; a.crop_done = crop_done; a.rs = rs;
     const int max_tiles = (cap + SC_TILE - 1) / SC_TILE;
     a.n_items = B * max_tiles;
     const int smem = 5 * SC_TILE * sizeof(float) + SC_HB * (6 * sizeof(ulonglong2) + sizeof(int));
@@ -1092,24 +1169,36 @@ int zp_launch_final(zp_ctx* ctx, const float* corr, int cap, const int32_t* coun
     a.thr2 = (float)((double)thr_px * (double)thr_px);
     a.final_mode = final_mode; a.poses = poses; a.n_inliers = n_inliers; a.status = status; a.best_idx = best_idx;
     a.inlier_mask = inlier_mask;
-    size_t smem = ((size_t)(cap + 31) / 32 + 2) * sizeof(uint32_t) +
-                  ((size_t)cap + FIN_THREADS_MAX + 32) * sizeof(uint16_t);      // bitset + the packed inlier indices
     if (!ctx->fin_attr_set) {
-        ZP_CUDA(ctx, cudaFuncSetAttribute(zp_final_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        ZP_CUDA(ctx, cudaFuncSetAttribute(zp_final_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        ZP_CUDA(ctx, cudaFuncSetAttribute(zp_final_cl_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        ZP_CUDA(ctx, cudaFuncSetAttribute(zp_final_cl_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 48 * 1024));
+        const char* e = getenv("ZP_FINAL_CL");          // tuning aid: force the cluster (4) or the single-CTA (1) form
+        if (e && !ctx->fin_form_set) ctx->fin_force = atoi(e);
         ctx->fin_attr_set = true;
     }
-    if (smem > 200 * 1024) ZP_FAIL(ctx, -1, "zp_ransac: cap %d needs %zu bytes of shared memory in the final solve", cap, smem);
-    // threads per crop (measured, profiles/README.md): the solver phases keep one warp busy, so two 128-thread CTAs per SM
-    // (255 registers each) overlap one crop's solver with another's point loops: 789 vs 866 us at 1024 crops, the same
-    // 3-lane throughput at 64 crops (262 k vs 265 k poses/s) although one 64-crop launch alone takes 176 instead of 145 us.
-    // ONE shape for every batch size, so that a crop's pose does not depend on how the job was batched or sharded (the
-    // FP64 reduction trees differ between the two shapes); 256 threads only when the packed index list is too big for two
-    // CTAs per SM (cap > ~45 k correspondences).
-    const bool narrow = smem <= 100 * 1024;
+    // packed inlier indices: 16 virtual warps x chunk entries per crop (4 per CTA in the cluster form)
+    const int chunk = ((cap + FIN_VR * FCL_THREADS - 1) / (FIN_VR * FCL_THREADS)) * 32;
+    const size_t idx_bytes = (size_t)FIN_VR * FCL_WARPS * chunk * sizeof(uint16_t);
+    if (idx_bytes > 160 * 1024) ZP_FAIL(ctx, -1, "zp_ransac: cap %d needs %zu bytes of shared memory in the final solve", cap, idx_bytes);
+    // the cluster form while its 4 B CTAs fit one wave of two CTAs per SM: below that the GPU is not full and a crop's point
+    // passes are 4x shorter; above it the single-CTA form does the same arithmetic without the redundant solver phases.
+    // Both produce identical bits (same partition, same reduction order).
+    const bool cluster = ctx->fin_force ? ctx->fin_force == 4 : 4 * B <= 2 * ctx->sm_count;
     ZP_TIME_BEGIN(ctx, st);
-    if (narrow) zp_final_kernel<128><<<B, 128, smem, st>>>(a);
-    else zp_final_kernel<256><<<B, 256, smem, st>>>(a);
+    if (cluster) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)(4 * B));
+        cfg.blockDim = dim3(FCL_THREADS);
+        cfg.dynamicSmemBytes = idx_bytes / FIN_VR;
+        cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 4; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        ZP_CUDA(ctx, cudaLaunchKernelEx(&cfg, zp_final_cl_kernel<4>, a));
+    } else {
+        zp_final_cl_kernel<1><<<B, FCL_THREADS, idx_bytes, st>>>(a);
+    }
     ZP_CHECK_LAUNCH(ctx, "zp_final_kernel");
     return 0;
 }

@@ -93,6 +93,10 @@ class Engine:
         arr = np.ascontiguousarray(np.asarray(sizes if sizes else [], np.int32))
         self.ctx.check(self.lib.zp_set_waves(self.ctx.handle, int(arr.size), arr.ctypes.data_as(C.c_void_p)), "zp_set_waves")
 
+    def set_final_form(self, form=0):
+        """final solve as a 4-CTA cluster per crop (4), one CTA per crop (1) or automatic (0); identical results"""
+        self.ctx.check(self.lib.zp_set_final_form(self.ctx.handle, int(form)), "zp_set_final_form")
+
     def set_score_groups(self, groups=0, hyp_chunk=0):
         """scheduling knobs of the scoring kernel (include/zebrapose_b200.h); results do not depend on them"""
         self.ctx.check(self.lib.zp_set_score_groups(self.ctx.handle, int(groups), int(hyp_chunk)), "zp_set_score_groups")
