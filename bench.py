@@ -524,7 +524,9 @@ def main():
                        "note": "per rank: e0 -> all lanes joined (compute) -> all_gather returned; skew = slowest minus fastest rank's compute"}
     status_ok = float((send[:, 13] == 0).double().mean().item())
 
-    # ---- latency of ONE step alone (single lane, eager, L2 flushed by a 256 MiB write before it)
+    # ---- latency of ONE step alone (single lane, eager, L2 flushed by a 256 MiB write before it; the final solve in its
+    # automatic form = a 4-CTA cluster per crop at this batch size, which the lanes trade for SM residency)
+    eng.set_final_form(0)
     flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device="cuda")
     lat = []
     for _ in range(10):
@@ -534,6 +536,7 @@ def main():
         b.synchronize()
         lat.append(a.elapsed_time(b))
     step_latency_ms = statistics.median(lat)
+    eng.set_final_form(1)
     del flush
 
     # ---- e2e: HOST pinned buffers through the C-ABI host entry (zp_pose_batch_host_async on every lane + zp_sync): the
@@ -595,6 +598,10 @@ def main():
             e.set_waves([H])                      # one wave: the per-kernel figures are per launch
         k_ms, Mtot, n_inl, hyps, r_state = table_for(d_logits, d_bbox, d_K, d_obj)
         roof = rooflines(k_ms, C, Mtot, n_inl, hyps, peaks)
+        # the final solve in its other form (a 4-CTA cluster per crop: what a lone engine uses at this batch size)
+        eng.set_final_form(4)
+        final_cluster_us = table_for(d_logits, d_bbox, d_K, d_obj)[0]["zp_final_kernel"] * 1e3
+        eng.set_final_form(1)
         chain = sum(k_ms[k] for k in CHAIN_KERNELS)
         shares = {k: round(v / chain, 4) for k, v in k_ms.items()}
         dominant = max(CHAIN_KERNELS, key=lambda k: k_ms[k])
@@ -671,6 +678,7 @@ def main():
             "kernel_us": {k: round(v * 1e3, 2) for k, v in k_ms.items()},
             "kernel_us_method": "CUDA event pairs recorded by the library on the launching stream directly around each launch "
                                 "(zp_set_kernel_timing), 512 MiB L2 flush before every repetition, 20 repetitions, one wave of all 150 hypotheses",
+            "final_solve_forms_us": {"one_cta_per_crop (lanes)": round(k_ms["zp_final_kernel"] * 1e3, 2), "cluster_of_4 (lone engine)": round(final_cluster_us, 2)},
             "kernel_share_of_step": shares, "dominant_kernel": dominant,
             "cpu_baseline": cpu, "next_rows": extras,
         }

@@ -524,7 +524,7 @@ int zp_pose_batch_device(zp_ctx* ctx, const void* logits, int dtype, int B, int 
     key.p[7] = status; key.p[8] = records; key.p[9] = stream;
     for (int q = 0; q < 4; q++) key.s[q] = strides[q];
     const int iv[16] = {dtype, B, S, mask_ch, bit0_ch, n_bits, ignore_bit, obj_default, H, m, sampler, select_mode, final_mode,
-                        ctx->solver, ctx->n_waves, ctx->force_decode_path * 1000 + ctx->decode_rpc};
+                        ctx->solver, ctx->n_waves, ctx->fin_force * 100000 + ctx->force_decode_path * 1000 + ctx->decode_rpc};
     for (int q = 0; q < 16; q++) key.i[q] = iv[q];
     for (int q = 0; q < 16; q++) key.w[q] = q < ctx->n_waves ? ctx->wave_sizes[q] : 0;
     key.f = thr_px; key.c = confidence; key.seed = seed;

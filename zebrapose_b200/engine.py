@@ -514,8 +514,13 @@ class Pipeline:
     under half of the SMs' issue slots busy), and the host->device copy of one batch runs under the kernels of the
     previous one.  Every lane holds its own copy of the dictionaries and its own workspace."""
 
-    def __init__(self, device=None, lanes=3):
+    def __init__(self, device=None, lanes=6):
         self.engines = [Engine(device) for _ in range(int(lanes))]
+        if len(self.engines) > 1:
+            # several batches in flight compete for SM residency: the one-CTA-per-crop final solve holds a quarter of the
+            # cluster form's registers (212 k vs 183 k poses/s at 6 lanes); a lone engine keeps the cluster (latency)
+            for e in self.engines:
+                e.set_final_form(1)
         self.device = self.engines[0].device
         self.streams = [torch.cuda.Stream(device=self.device) for _ in self.engines]
         self._next = 0
