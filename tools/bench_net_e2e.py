@@ -105,16 +105,17 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dist = None
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    eng = zp.Engine(local)
-    tab, _, _ = synth.make_dict(16, seed=5, radius=60.0, missing_frac=0.0)
-    eng.upload_dict(0, tab)
     sys.stdout.flush()
     saved = os.dup(1)
-    os.dup2(2, 1)                       # NCCL prints its version banner on stdout at the first collective
+    os.dup2(2, 1)                       # NCCL prints its version banner on stdout (at init with device_id, or at the first collective)
     try:
+        if world > 1:
+            import torch.distributed as dist
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        eng = zp.Engine(local)
+        tab, _, _ = synth.make_dict(16, seed=5, radius=60.0, missing_frac=0.0)
+        eng.upload_dict(0, tab)
         row = measure(eng, B, steps=steps, dist=dist)
     finally:
         sys.stdout.flush()
