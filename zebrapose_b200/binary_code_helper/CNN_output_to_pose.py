@@ -54,7 +54,15 @@ def CNN_outputs_to_object_pose(mask_image, class_code_image, Bbox, Bbox_Size, cl
     """CNN_output_to_pose.py:100-160.  mask_image [S,S] (uint8 | float, != 0 is foreground, may be an external
     mask), class_code_image [S,S,L] of 0/1 (already sliced to 16-k channels when ignore_bit = k, with the matching
     dictionary), Bbox = [x,y,w,h], intrinsic_matrix 3x3 (numpy or torch; default LM intrinsics).
-    -> (rot 3x3 float64, tvecs 3x1 float64 [mm], success) or ([], [], False) when fewer than 6 correspondences."""
+    -> (rot 3x3 float64, tvecs 3x1 float64 [mm], success) or ([], [], False) when fewer than 6 correspondences.
+
+    How close to the reference's cv2.solvePnPRansac (:155-157), per crop: the RANSAC hypotheses are bit-identical to cv2's
+    (the minimal solver replays OpenCV's EPnP arithmetic), the winner, the iteration count and the final inlier set are
+    cv2's, and the pose agrees within 0.05 deg / 0.5 mm on 100 % of 768 measured crops at ignore_bit 0 and 99.6-99.8 % at
+    ignore_bit 2 / 4 (profiles/r2g_parity_*.json; median difference 0).  The rest: one inlier COUNT of a hypothesis off by a
+    point within 1e-3 px of the 2 px threshold (float32 scoring) can flip a near-tie between two hypotheses.  Pinned per
+    crop by tests/test_gpu_ransac.py (winner / iterations / inliers equal cv2's) and tests/test_gpu_dropin.py (tolerance on
+    every golden crop)."""
     if intrinsic_matrix is None:
         intrinsic_matrix = np.array([[572.4114, 0, 325.2611], [0, 573.57043, 242.04899], [0, 0, 1.0]])
     K = np.asarray(intrinsic_matrix.cpu() if isinstance(intrinsic_matrix, torch.Tensor) else intrinsic_matrix, np.float64)
