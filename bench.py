@@ -164,6 +164,11 @@ def run_reference(args, rank, world):
     print(json.dumps(line))
 
 
+def synth_logits_of(crop):
+    from workloads import synth
+    return synth.crop_to_logits(crop)
+
+
 def gt_poses(crops):
     import numpy as np
     return np.stack([np.concatenate([np.asarray(c["R"], np.float64).ravel(), np.asarray(c["t"], np.float64).ravel()]) for c in crops])
@@ -243,6 +248,26 @@ def next_rows(eng, timed, d_bbox, d_K, d_obj, crops, tables, C, hbm_peak, fp32_p
                           "adi_tflops_9_per_pair": round(9 * pairs / us / 1e6, 2),
                           "adi_frac_of_fp32_peak": round(9 * pairs / us / 1e6 / fp32_peak, 3) if fp32_peak else None,
                           "pose_pairs_per_s": round(C / ms_e * 1e3)}
+    # configs[0]: ONE crop through the reference-signature drop-in (host numpy arrays in, numpy pose out, as test.py calls it)
+    try:
+        from zebrapose_b200.binary_code_helper.CNN_output_to_pose import CNN_outputs_to_object_pose
+        from zebrapose_b200 import common_ops
+        c0 = crops[0]
+        lt = torch.from_numpy(synth_logits_of(c0))[None].cuda()
+        pm = common_ops.from_output_to_class_mask(lt[:, :1]).transpose(0, 2, 3, 1).squeeze(axis=-1).astype("uint8")
+        pc = common_ops.from_output_to_class_binary_code(lt[:, 1:], "BCE").transpose(0, 2, 3, 1)
+        tab0 = tables[int(d_obj[0].item())]
+        d0 = {float(i): tab0[i] for i in range(len(tab0))}
+        CNN_outputs_to_object_pose(pm[0], pc[0], c0["bbox"], S, 2, d0, intrinsic_matrix=c0["K"])       # uploads the dictionary
+        t0 = time.perf_counter()
+        for _ in range(20):
+            Rd, td, okd = CNN_outputs_to_object_pose(pm[0], pc[0], c0["bbox"], S, 2, d0, intrinsic_matrix=c0["K"])
+        out["dropin_single_crop"] = {"ms_per_crop": round((time.perf_counter() - t0) / 20 * 1e3, 3), "success": bool(okd),
+                                     "what": "configs[0]: CNN_outputs_to_object_pose(mask, code, Bbox, 128, 2, dict, K) per crop, host arrays in / "
+                                             "numpy pose out, wall clock incl. H2D, decode, RANSAC (150 hypotheses), D2H; the reference's own "
+                                             "function takes 31 ms (SURVEY section 6) to ~180 ms (this workload) per crop on one core"}
+    except Exception as exc:
+        out["dropin_single_crop"] = {"error": repr(exc)[:200]}
     # configs[4]: the random-init network's bf16 forward feeding the path on the device (body = torch / cuDNN, not this
     # repo's code; reported so the path's share of an end-to-end step is on record).  128 crops = 1024 over 8 GPUs.
     try:
