@@ -193,8 +193,8 @@ int zp_debug_buffer(zp_ctx* ctx, void* dev_u64);
 
 /* Tuning aid for zp_score / zp_ransac: `groups` = warp-groups (128 threads each) per scoring CTA that split the
  * hypotheses of a work item (0 = automatic = 1, else 1, 2 or 4); `hyp_chunk` = hypotheses per work item (0 = automatic:
- * H/2 when the batch has about one correspondence tile per CTA slot, all of them otherwise; -1 = never cut; else the chunk).
- * Results do not depend on either. */
+ * H/2 when the batch has about one correspondence tile per CTA slot, all of them otherwise; -1 = never cut; else equal
+ * chunks of that size).  Results do not depend on either. */
 int zp_set_score_groups(zp_ctx* ctx, int groups, int hyp_chunk);
 
 /* Asynchronous form of zp_pose_batch_host: enqueues the copies and the kernels on the ctx's own stream and returns; the

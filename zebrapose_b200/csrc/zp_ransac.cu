@@ -21,6 +21,8 @@
 // Algorithmic FP32 work of scoring: 27 flop per (correspondence, hypothesis).
 #include <climits>
 #include <stdlib.h>
+#include <algorithm>
+#include <vector>
 #include <cooperative_groups.h>
 #include "zp_common.cuh"
 
@@ -402,21 +404,26 @@ __global__ void zp_poses_to_P_kernel(const double* __restrict__ poses, const dou
     for (int e = 0; e < 6; e++) o[e] = make_float4(P[2 * e], P[2 * e], P[2 * e + 1], P[2 * e + 1]);
 }
 
+constexpr int SC_MAXCLS = 16;                      // hypothesis classes (chunks) a tile's work is cut into
+
 struct ScoreArgs {
     const float* corr; int cap; const int32_t* counts; const float* hyp_P;
     int B, H; float inv_thr; int32_t* hyp_inliers; int* counters; int n_items;
-    int hchunk, n_hc;            // hypotheses per work item and items per tile (small batches are cut finer)
     int h0, hw;                  // this launch scores hypotheses [h0, h0 + hw) ...
     const int32_t* crop_done;    // ... of the crops that have not reached cv2's adaptive stop (nullable: all)
     const int32_t* rs;           // nullable [B,4]: rs[4b] = the crop's current niters; hypotheses at or past it are not scored
+    int n_cls;                   // a tile's hypotheses are cut into n_cls chunks [cls_off[c], cls_off[c+1]) (relative to h0,
+    int cls_off[SC_MAXCLS + 1];  // each <= SC_HB); the queue hands out all tiles of chunk 0, then of chunk 1, ...
 };
 
-// Persistent CTAs pulling work items (crop b, tile of SC_TILE correspondences) from a global ticket counter; items are
-// ordered tile-major (w -> b = w % B, tile = w / B) so the empty tiles of short lists sit at the end of the queue.
-// Per item: one elected thread issues TMA bulk copies of the 5 correspondence planes and of the crop's projection
-// matrices into shared memory (mbarrier completion); each thread keeps SC_PPT correspondences in registers and walks
-// the hypotheses (3 x LDS.128 broadcast each); the sign bits of d are funnel-shifted into one register (1 instruction
-// per evaluation), popc'ed, warp-reduced with REDUX and accumulated lane-distributed (lane h%32 owns hypothesis h).
+// Persistent CTAs pulling work items (hypothesis chunk c, crop b, tile of SC_TILE correspondences) from a global ticket
+// counter.  The queue is ordered chunk-major; inside a chunk tile-major (w -> b = w % B, tile = w / B), so the empty tiles of
+// short lists sit at the end of each segment; thread 0 draws tickets until it holds a live item (no CTA-wide barrier per
+// skipped ticket).
+// Per item: thread 0 issues TMA bulk copies of the 5 correspondence planes and of the chunk's projection matrices into
+// shared memory (mbarrier completion); each thread keeps SC_PPT correspondences in registers and walks the hypotheses
+// (3 x LDS.128 broadcast each); the sign bits of d are funnel-shifted into one register (1 instruction per evaluation),
+// popc'ed, warp-reduced with REDUX and accumulated lane-distributed (lane h%32 owns hypothesis h).
 template <int SC_NG>
 __global__ void __launch_bounds__(SC_GROUP * SC_NG) zp_score_kernel(ScoreArgs a) {
     constexpr int SC_THREADS = SC_GROUP * SC_NG;
@@ -425,7 +432,7 @@ __global__ void __launch_bounds__(SC_GROUP * SC_NG) zp_score_kernel(ScoreArgs a)
     ulonglong2* s_P = (ulonglong2*)(s_pts + 5 * SC_TILE);              // [SC_HB][6]: (P,P) pairs, 96 B per hypothesis
     int* s_cnt = (int*)(s_P + 6 * SC_HB);                              // [SC_HB]
     __shared__ __align__(8) uint64_t s_bar;
-    __shared__ int s_item;
+    __shared__ int s_item[4];                                          // crop (-1: queue empty), first correspondence, hypotheses [begin, end)
     const int tid = threadIdx.x, lane = tid & 31, grp = tid / SC_GROUP, gt = tid % SC_GROUP;
     if (tid == 0) {
         mbar_init(&s_bar, 1);
@@ -434,114 +441,111 @@ __global__ void __launch_bounds__(SC_GROUP * SC_NG) zp_score_kernel(ScoreArgs a)
     for (int h = tid; h < SC_HB; h += SC_THREADS) s_cnt[h] = 0;
     uint32_t phase = 0;
     const int H = a.H;
+    const int total = a.n_items * a.n_cls;
     for (;;) {
         __syncthreads();                                               // everybody is done with s_item / the buffers
-        if (tid == 0) s_item = atomicAdd(&a.counters[0], 1);
+        if (tid == 0) {
+            int ib = -1, istart = 0, ih0 = 0, ih1 = 0, icnt = 0;
+            for (;;) {
+                int w = atomicAdd(&a.counters[0], 1);
+                if (w >= total) break;
+                const int cls = w / a.n_items;
+                w -= cls * a.n_items;
+                const int b = w % a.B, tile = w / a.B;
+                if (a.crop_done && a.crop_done[b]) continue;
+                const int n = min(a.counts[b], a.cap);
+                if (tile * SC_TILE >= n) continue;
+                const int hs = a.h0 + a.cls_off[cls];
+                const int he = min(a.h0 + a.cls_off[cls + 1], a.rs ? a.rs[4 * b] : INT_MAX);
+                if (hs >= he) continue;
+                ib = b; istart = tile * SC_TILE; ih0 = hs; ih1 = he; icnt = min(SC_TILE, n - istart);
+                break;
+            }
+            s_item[0] = ib; s_item[1] = icnt; s_item[2] = ih0; s_item[3] = ih1;
+            if (ib >= 0) {
+                const float* cb = a.corr + (size_t)ib * 5 * a.cap + istart;
+                const uint32_t bytes = (uint32_t)((icnt + 3) & ~3) * 4u;   // 16-byte granules; cap % 4 == 0 keeps it in bounds
+                const uint32_t pbytes = (uint32_t)(ih1 - ih0) * 96u;
+                mbar_expect_tx(&s_bar, 5 * bytes + pbytes);
+                for (int pl = 0; pl < 5; pl++) tma_load_1d(s_pts + pl * SC_TILE, cb + (size_t)pl * a.cap, bytes, &s_bar);
+                tma_load_1d(s_P, a.hyp_P + ((size_t)ib * H + ih0) * 24, pbytes, &s_bar);
+            }
+        }
         __syncthreads();
-        int w = s_item;
-        const int per_pass = a.n_items * a.n_hc;
-        if (w >= 2 * per_pass) break;
-        // pass 0 hands out the full tiles, pass 1 the partial (last) tile of every list: the small items come last,
-        // which bounds the finishing skew between SMs.  A tile is cut into n_hc items of hchunk hypotheses.
-        const bool second = w >= per_pass;
-        if (second) w -= per_pass;
-        const int hc = w % a.n_hc;
-        w /= a.n_hc;
-        const int b = w % a.B, tile = w / a.B;
-        if (a.crop_done && a.crop_done[b]) continue;
-        const int n = min(a.counts[b], a.cap);
-        const int start = tile * SC_TILE;
-        if (start >= n) continue;
-        const int cnt = min(SC_TILE, n - start);
-        if ((cnt == SC_TILE) == second) continue;
-        const float* cb = a.corr + (size_t)b * 5 * a.cap + start;
-        const uint32_t bytes = (uint32_t)((cnt + 3) & ~3) * 4u;        // 16-byte granules; cap % 4 == 0 keeps it in bounds
+        const int b = s_item[0];
+        if (b < 0) break;
+        const int cnt = s_item[1], h0 = s_item[2], hb = s_item[3] - s_item[2];
         f32x2 nu[SC_PPT / 2], nv[SC_PPT / 2], X[SC_PPT / 2], Y[SC_PPT / 2], Z[SC_PPT / 2];   // point pairs (j, j+1)
-        const int h_begin = a.h0 + hc * a.hchunk;
-        const int h_end = min(min(a.h0 + a.hw, h_begin + a.hchunk), a.rs ? a.rs[4 * b] : INT_MAX);
-        for (int h0 = h_begin; h0 < h_end; h0 += SC_HB) {
-            const int hb = min(SC_HB, h_end - h0);
-            if (tid == 0) {
-                const uint32_t pbytes = (uint32_t)hb * 96u;
-                mbar_expect_tx(&s_bar, (h0 == h_begin ? 5 * bytes : 0) + pbytes);
-                if (h0 == h_begin)
-                    for (int pl = 0; pl < 5; pl++) tma_load_1d(s_pts + pl * SC_TILE, cb + (size_t)pl * a.cap, bytes, &s_bar);
-                tma_load_1d(s_P, a.hyp_P + ((size_t)b * H + h0) * 24, pbytes, &s_bar);
-            }
-            mbar_wait(&s_bar, phase);
-            phase ^= 1;
-            if (h0 == h_begin) {
+        mbar_wait(&s_bar, phase);
+        phase ^= 1;
 #pragma unroll
-                for (int k = 0; k < SC_PPT / 2; k++) {
-                    float f[2][5];
+        for (int k = 0; k < SC_PPT / 2; k++) {
+            float f[2][5];
 #pragma unroll
-                    for (int q = 0; q < 2; q++) {
-                        int i = gt + (2 * k + q) * SC_GROUP;
-                        bool live = i < cnt;
-                        // a dead slot gets u = 1e30: d >= +0 for every finite projection, never counted
-                        f[q][0] = live ? -(s_pts[i] * a.inv_thr) : -1e30f;
-                        f[q][1] = live ? -(s_pts[SC_TILE + i] * a.inv_thr) : 0.f;
-                        f[q][2] = live ? s_pts[2 * SC_TILE + i] : 0.f;
-                        f[q][3] = live ? s_pts[3 * SC_TILE + i] : 0.f;
-                        f[q][4] = live ? s_pts[4 * SC_TILE + i] : 0.f;
-                    }
-                    nu[k] = zp_pack2(f[0][0], f[1][0]); nv[k] = zp_pack2(f[0][1], f[1][1]);
-                    X[k] = zp_pack2(f[0][2], f[1][2]); Y[k] = zp_pack2(f[0][3], f[1][3]); Z[k] = zp_pack2(f[0][4], f[1][4]);
-                }
+            for (int q = 0; q < 2; q++) {
+                int i = gt + (2 * k + q) * SC_GROUP;
+                bool live = i < cnt;
+                // a dead slot gets u = 1e30: d >= +0 for every finite projection, never counted
+                f[q][0] = live ? -(s_pts[i] * a.inv_thr) : -1e30f;
+                f[q][1] = live ? -(s_pts[SC_TILE + i] * a.inv_thr) : 0.f;
+                f[q][2] = live ? s_pts[2 * SC_TILE + i] : 0.f;
+                f[q][3] = live ? s_pts[3 * SC_TILE + i] : 0.f;
+                f[q][4] = live ? s_pts[4 * SC_TILE + i] : 0.f;
             }
-            // group g takes hypotheses h = SC_NG * i + g; lane (i % 32) of every warp accumulates hypothesis i's count
-            const int ni = (hb - grp + SC_NG - 1) / SC_NG;
-            for (int iq = 0; iq < ni; iq += 32) {
-                int acc = 0;
-                const int iend = min(32, ni - iq);
+            nu[k] = zp_pack2(f[0][0], f[1][0]); nv[k] = zp_pack2(f[0][1], f[1][1]);
+            X[k] = zp_pack2(f[0][2], f[1][2]); Y[k] = zp_pack2(f[0][3], f[1][3]); Z[k] = zp_pack2(f[0][4], f[1][4]);
+        }
+        // group g takes hypotheses h = SC_NG * i + g; lane (i % 32) of every warp accumulates hypothesis i's count
+        const int ni = (hb - grp + SC_NG - 1) / SC_NG;
+        for (int iq = 0; iq < ni; iq += 32) {
+            int acc = 0;
+            const int iend = min(32, ni - iq);
 #pragma unroll 2
-                for (int il = 0; il < iend; il++) {
-                    const ulonglong2* pp = s_P + 6 * (SC_NG * (iq + il) + grp);
-                    const ulonglong2 q0 = pp[0], q1 = pp[1], q2 = pp[2], q3 = pp[3], q4 = pp[4], q5 = pp[5];
-                    // element-major order: every projection element is applied to all point pairs back to back, so
-                    // consecutive FFMA2s share a source operand (operand-reuse cache) -- an FFMA2 with three distinct
-                    // 64-bit register sources needs 3 even + 3 odd register reads and issues every 3 cycles instead of 2
-                    constexpr int NPAIR = SC_PPT / 2;
-                    f32x2 x[NPAIR], y[NPAIR], z[NPAIR];
+            for (int il = 0; il < iend; il++) {
+                const ulonglong2* pp = s_P + 6 * (SC_NG * (iq + il) + grp);
+                const ulonglong2 q0 = pp[0], q1 = pp[1], q2 = pp[2], q3 = pp[3], q4 = pp[4], q5 = pp[5];
+                // element-major order: every projection element is applied to all point pairs back to back, so
+                // consecutive FFMA2s share a source operand (operand-reuse cache) -- an FFMA2 with three distinct
+                // 64-bit register sources needs 3 even + 3 odd register reads and issues every 3 cycles instead of 2
+                constexpr int NPAIR = SC_PPT / 2;
+                f32x2 x[NPAIR], y[NPAIR], z[NPAIR];
 #pragma unroll
-                    for (int k = 0; k < NPAIR; k++) z[k] = zp_fma2(q5.x, Z[k], q5.y);
+                for (int k = 0; k < NPAIR; k++) z[k] = zp_fma2(q5.x, Z[k], q5.y);
 #pragma unroll
-                    for (int k = 0; k < NPAIR; k++) z[k] = zp_fma2(q4.y, Y[k], z[k]);
+                for (int k = 0; k < NPAIR; k++) z[k] = zp_fma2(q4.y, Y[k], z[k]);
 #pragma unroll
-                    for (int k = 0; k < NPAIR; k++) z[k] = zp_fma2(q4.x, X[k], z[k]);
+                for (int k = 0; k < NPAIR; k++) z[k] = zp_fma2(q4.x, X[k], z[k]);
 #pragma unroll
-                    for (int k = 0; k < NPAIR; k++) x[k] = zp_fma2(q1.x, Z[k], q1.y);
+                for (int k = 0; k < NPAIR; k++) x[k] = zp_fma2(q1.x, Z[k], q1.y);
 #pragma unroll
-                    for (int k = 0; k < NPAIR; k++) x[k] = zp_fma2(q0.y, Y[k], x[k]);
+                for (int k = 0; k < NPAIR; k++) x[k] = zp_fma2(q0.y, Y[k], x[k]);
 #pragma unroll
-                    for (int k = 0; k < NPAIR; k++) x[k] = zp_fma2(q0.x, X[k], x[k]);
+                for (int k = 0; k < NPAIR; k++) x[k] = zp_fma2(q0.x, X[k], x[k]);
 #pragma unroll
-                    for (int k = 0; k < NPAIR; k++) y[k] = zp_fma2(q3.x, Z[k], q3.y);
+                for (int k = 0; k < NPAIR; k++) y[k] = zp_fma2(q3.x, Z[k], q3.y);
 #pragma unroll
-                    for (int k = 0; k < NPAIR; k++) y[k] = zp_fma2(q2.y, Y[k], y[k]);
+                for (int k = 0; k < NPAIR; k++) y[k] = zp_fma2(q2.y, Y[k], y[k]);
 #pragma unroll
-                    for (int k = 0; k < NPAIR; k++) y[k] = zp_fma2(q2.x, X[k], y[k]);
-                    uint32_t bits = 0;
+                for (int k = 0; k < NPAIR; k++) y[k] = zp_fma2(q2.x, X[k], y[k]);
+                uint32_t bits = 0;
 #pragma unroll
-                    for (int k = 0; k < NPAIR; k++) {
-                        f32x2 dx = zp_fma2(nu[k], z[k], x[k]), dy = zp_fma2(nv[k], z[k], y[k]);
-                        f32x2 e = zp_fma2(dx, dx, zp_mul2(dy, dy));
-                        f32x2 d = zp_fma2(z[k] ^ 0x8000000080000000ull, z[k], e);   // e - z*z; the sign flip runs on the ALU pipe
-                        bits = __funnelshift_l((uint32_t)d, bits, 1);
-                        bits = __funnelshift_l((uint32_t)(d >> 32), bits, 1);
-                    }
-                    int c = __reduce_add_sync(0xffffffffu, __popc(bits));
-                    if (lane == il) acc += c;
+                for (int k = 0; k < NPAIR; k++) {
+                    f32x2 dx = zp_fma2(nu[k], z[k], x[k]), dy = zp_fma2(nv[k], z[k], y[k]);
+                    f32x2 e = zp_fma2(dx, dx, zp_mul2(dy, dy));
+                    f32x2 d = zp_fma2(z[k] ^ 0x8000000080000000ull, z[k], e);   // e - z*z; the sign flip runs on the ALU pipe
+                    bits = __funnelshift_l((uint32_t)d, bits, 1);
+                    bits = __funnelshift_l((uint32_t)(d >> 32), bits, 1);
                 }
-                if (acc) atomicAdd(&s_cnt[SC_NG * (iq + lane) + grp], acc);
+                int c = __reduce_add_sync(0xffffffffu, __popc(bits));
+                if (lane == il) acc += c;
             }
-            __syncthreads();
-            int32_t* out = a.hyp_inliers + (size_t)b * H + h0;
-            for (int h = tid; h < hb; h += SC_THREADS) {
-                int c = s_cnt[h];
-                if (c) { atomicAdd(&out[h], c); s_cnt[h] = 0; }
-            }
-            __syncthreads();
+            if (acc) atomicAdd(&s_cnt[SC_NG * (iq + lane) + grp], acc);
+        }
+        __syncthreads();
+        int32_t* out = a.hyp_inliers + (size_t)b * H + h0;
+        for (int h = tid; h < hb; h += SC_THREADS) {
+            int c = s_cnt[h];
+            if (c) { atomicAdd(&out[h], c); s_cnt[h] = 0; }
         }
     }
     // the last CTA to leave re-arms the queue for the next launch
@@ -1116,6 +1120,21 @@ int zp_launch_poses_to_P(zp_ctx* ctx, const double* poses, const double* K, int 
     return 0;
 }
 
+// How a tile's hypotheses are cut into queue chunks: about one tile per CTA slot (64 crops: 832 tiles on 740 slots) -> two
+// halves, so that the last round is short (measured -12 % against uncut tiles); otherwise one chunk (finer cuts lose more
+// to the per-item work than they win in balance: equal thirds / fifths and shrinking plans such as 80 | 40 | 20 | 10 all
+// measured within 3 % of the halves at 64 crops, profiles/r2u_score_plans.txt, and 1-6 % behind one chunk at 1024).
+static std::vector<int> score_plan(zp_ctx* ctx, int n_items, int slots, int hw) {
+    std::vector<int> cls;
+    const int req = ctx->score_hchunk;
+    int chunk = req > 0 ? req : hw;
+    if (req == 0 && n_items <= 2 * slots && hw >= 64) chunk = (hw + 1) / 2;
+    if (chunk > SC_HB) chunk = SC_HB;
+    if ((hw + chunk - 1) / chunk > SC_MAXCLS) chunk = (hw + SC_MAXCLS - 1) / SC_MAXCLS;
+    for (int h = 0; h < hw; h += chunk) cls.push_back(std::min(chunk, hw - h));
+    return cls;
+}
+
 template <int NG>
 static int launch_score_ng(zp_ctx* ctx, ScoreArgs& a, int smem, cudaStream_t st) {
     constexpr int slot = NG == 1 ? 0 : NG == 2 ? 1 : 2;      // per context (= per device), not per process
@@ -1123,19 +1142,18 @@ static int launch_score_ng(zp_ctx* ctx, ScoreArgs& a, int smem, cudaStream_t st)
         int per_sm = 0;
         ZP_CUDA(ctx, cudaFuncSetAttribute(zp_score_kernel<NG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         ZP_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, zp_score_kernel<NG>, SC_GROUP * NG, smem));
+        const char* e = getenv("ZP_SCORE_PER_SM");          // tuning aid: resident scoring CTAs per SM (default: what fits)
+        if (e && atoi(e) > 0 && atoi(e) < per_sm) per_sm = atoi(e);
         ctx->score_per_sm[slot] = per_sm < 1 ? 1 : per_sm;
     }
     const int per_sm = ctx->score_per_sm[slot];
     int grid = ctx->sm_count * per_sm;
-    // about one tile per CTA slot (64 crops: 832 tiles on 740 slots): cut the tiles into two items of H/2 hypotheses so
-    // that the last round is short (measured -6 %; finer cuts or bigger batches lose more to the extra tile loads)
-    a.hchunk = a.hw; a.n_hc = 1;
-    const int hc_req = ctx->score_hchunk;
-    if (hc_req > 0 || (hc_req == 0 && a.n_items <= 2 * grid && a.hw >= 64)) {
-        a.hchunk = hc_req > 0 ? hc_req : (a.hw + 1) / 2;
-        a.n_hc = (a.hw + a.hchunk - 1) / a.hchunk;
-    }
-    if (grid > 2 * a.n_items * a.n_hc) grid = 2 * a.n_items * a.n_hc;
+    const std::vector<int> cls = score_plan(ctx, a.n_items, grid, a.hw);
+    a.n_cls = (int)cls.size();
+    a.cls_off[0] = 0;
+    for (int c = 0; c < a.n_cls; c++) a.cls_off[c + 1] = a.cls_off[c] + cls[c];
+    for (int c = a.n_cls + 1; c <= SC_MAXCLS; c++) a.cls_off[c] = a.cls_off[a.n_cls];
+    if (grid > a.n_items * a.n_cls) grid = a.n_items * a.n_cls;
     ZP_TIME_BEGIN(ctx, st);
     zp_score_kernel<NG><<<grid, SC_GROUP * NG, smem, st>>>(a);
     ZP_CHECK_LAUNCH(ctx, "zp_score_kernel");
