@@ -286,11 +286,13 @@ def next_rows(eng, timed, d_bbox, d_K, d_obj, crops, tables, C, hbm_peak, fp32_p
 # 125.6 skipped pairs), the seven small Jacobi SVDs 10 663, and the closed-form remainder (M^T M 1 680, L/rho 400, three
 # candidates x (least-squares back-substitution, 5 Gauss-Newton steps with a 6x4 QR, pose, error) 10 500, staging 800)
 SOLVER_OPS_PER_HYP = 50836 + 10663 + 13380
-# final solve on the n_i inliers of the winner: barycentric coordinates + 52 EPnP sums (~190 ops per inlier), candidate
-# errors (3 x 40), centroid / scatter (15), plus the fixed 12x12 null space, betas and alignment (~30 k)
-FINAL_OPS_PER_INLIER, FINAL_OPS_FIXED = 190 + 120 + 15, 30000
+# final solve on the n_i inliers of the winner (split form): 40 raw moments (~105 ops per inlier: 6 products, 9 adds, 30
+# multiply-adds counted twice, pivot / image offsets), candidate errors (3 x 40), plus per crop the contractions A T_f A^T
+# (~3 k), the 12x12 null space, betas and alignment (~30 k)
+FINAL_OPS_PER_INLIER, FINAL_OPS_FIXED = 105 + 120, 33000
 SOLVER_KERNELS = ("zp_cvs_prep_kernel", "zp_cvs_null_kernel", "zp_cvs_cand_kernel", "zp_cvs_pick_kernel")
-CHAIN_KERNELS = ("zp_decode_stream_kernel", "zp_samples_kernel") + SOLVER_KERNELS + ("zp_score_kernel", "zp_final_kernel")
+FINAL_KERNELS = ("zp_fin_moments_kernel", "zp_fin_solve_kernel", "zp_fin_errors_kernel")
+CHAIN_KERNELS = ("zp_decode_stream_kernel", "zp_samples_kernel") + SOLVER_KERNELS + ("zp_score_kernel",) + FINAL_KERNELS
 
 
 def kernel_table(eng, torch, fn_decode, fn_ransac, reps=20):
@@ -307,9 +309,10 @@ def kernel_table(eng, torch, fn_decode, fn_ransac, reps=20):
             flush.zero_()
             fn()
         torch.cuda.synchronize()
-        for n in names:
+        for n in names + (("zp_final_kernel",) if fn is fn_ransac else ()):     # zp_final_kernel: the one-kernel forms, when selected
             ms, launches = eng.kernel_time(n)
-            out[n] = ms * launches / reps
+            if launches or n != "zp_final_kernel":
+                out[n] = ms * launches / reps
         eng.set_kernel_timing(False)
     del flush
     return out
@@ -327,7 +330,8 @@ def rooflines(k_ms, C, Mtot, n_inl, hyps, peaks, tag=""):
     sol_ops = float(SOLVER_OPS_PER_HYP) * hyps
     sol_tf = sol_ops / (sol_ms * 1e-3) / 1e12
     fin_ops = float(FINAL_OPS_PER_INLIER) * n_inl + float(FINAL_OPS_FIXED) * C
-    fin_tf = fin_ops / (k_ms["zp_final_kernel"] * 1e-3) / 1e12
+    fin_ms = sum(k_ms[k] for k in FINAL_KERNELS)
+    fin_tf = fin_ops / (fin_ms * 1e-3) / 1e12
     unfused = fp64_peak / 2.0 if fp64_peak else None
     return {
         "roofline" + tag: {"kernel": "zp_decode_stream_kernel", "bound": "hbm", "achieved": dec_gbs, "peak": hbm_peak, "unit": "GB/s",
@@ -341,9 +345,9 @@ def rooflines(k_ms, C, Mtot, n_inl, hyps, peaks, tag=""):
                                 "achieved": sol_tf, "peak": unfused, "unit": "TFLOP/s", "frac": sol_tf / unfused if unfused else None,
                                 "crops": C, "hypotheses": hyps, "algorithmic_ops_per_hypothesis": SOLVER_OPS_PER_HYP,
                                 "peak_source": peaks["fp64_source"], "us_per_call": sol_ms * 1e3},
-        "roofline_fp64_final" + tag: {"kernel": "zp_final_kernel", "bound": "fp64", "achieved": fin_tf, "peak": fp64_peak, "unit": "TFLOP/s",
+        "roofline_fp64_final" + tag: {"kernel": "+".join(FINAL_KERNELS), "bound": "fp64", "achieved": fin_tf, "peak": fp64_peak, "unit": "TFLOP/s",
                                       "frac": fin_tf / fp64_peak if fp64_peak else None, "crops": C, "inliers": n_inl,
-                                      "algorithmic_ops_per_launch": fin_ops, "us_per_launch": k_ms["zp_final_kernel"] * 1e3},
+                                      "algorithmic_ops_per_call": fin_ops, "us_per_call": fin_ms * 1e3},
     }
 
 
@@ -549,9 +553,7 @@ def main():
                        "note": "per rank: e0 -> all lanes joined (compute) -> all_gather returned; skew = slowest minus fastest rank's compute"}
     status_ok = float((send[:, 13] == 0).double().mean().item())
 
-    # ---- latency of ONE step alone (single lane, eager, L2 flushed by a 256 MiB write before it; the final solve in its
-    # automatic form = a 4-CTA cluster per crop at this batch size, which the lanes trade for SM residency)
-    eng.set_final_form(0)
+    # ---- latency of ONE step alone (single lane, eager, L2 flushed by a 256 MiB write before it)
     flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device="cuda")
     lat = []
     for _ in range(10):
@@ -561,7 +563,6 @@ def main():
         b.synchronize()
         lat.append(a.elapsed_time(b))
     step_latency_ms = statistics.median(lat)
-    eng.set_final_form(1)
     del flush
 
     # ---- e2e: HOST pinned buffers through the C-ABI host entry (zp_pose_batch_host_async on every lane + zp_sync): the
@@ -623,10 +624,13 @@ def main():
             e.set_waves([H])                      # one wave: the per-kernel figures are per launch
         k_ms, Mtot, n_inl, hyps, r_state = table_for(d_logits, d_bbox, d_K, d_obj)
         roof = rooflines(k_ms, C, Mtot, n_inl, hyps, peaks)
-        # the final solve in its other form (a 4-CTA cluster per crop: what a lone engine uses at this batch size)
-        eng.set_final_form(4)
-        final_cluster_us = table_for(d_logits, d_bbox, d_K, d_obj)[0]["zp_final_kernel"] * 1e3
-        eng.set_final_form(1)
+        # the final solve in its one-kernel forms (round 2's: one CTA per crop, 4-CTA cluster per crop)
+        final_forms_us = {"split: moments + solve + errors (default)": round(sum(k_ms[k] for k in FINAL_KERNELS) * 1e3, 2)}
+        for form, label in ((1, "one_cta_per_crop"), (4, "cluster_of_4")):
+            eng.set_final_form(form)
+            final_forms_us[label] = round(table_for(d_logits, d_bbox, d_K, d_obj)[0]["zp_final_kernel"] * 1e3, 2)
+        eng.set_final_form(0)
+        k_ms.pop("zp_final_kernel", None)
         chain = sum(k_ms[k] for k in CHAIN_KERNELS)
         shares = {k: round(v / chain, 4) for k, v in k_ms.items()}
         dominant = max(CHAIN_KERNELS, key=lambda k: k_ms[k])
@@ -703,7 +707,7 @@ def main():
             "kernel_us": {k: round(v * 1e3, 2) for k, v in k_ms.items()},
             "kernel_us_method": "CUDA event pairs recorded by the library on the launching stream directly around each launch "
                                 "(zp_set_kernel_timing), 512 MiB L2 flush before every repetition, 20 repetitions, one wave of all 150 hypotheses",
-            "final_solve_forms_us": {"one_cta_per_crop (lanes)": round(k_ms["zp_final_kernel"] * 1e3, 2), "cluster_of_4 (lone engine)": round(final_cluster_us, 2)},
+            "final_solve_forms_us": final_forms_us,
             "kernel_share_of_step": shares, "dominant_kernel": dominant,
             "cpu_baseline": cpu, "next_rows": extras,
         }

@@ -119,9 +119,12 @@ int zp_set_solver(zp_ctx* ctx, int solver);
  * (cv2 never consults a hypothesis at or past its stopping iteration). */
 int zp_set_waves(zp_ctx* ctx, int n, const int32_t* sizes);
 
-/* Shape of the final solve on the winner's inliers: 4 = a thread-block cluster of four CTAs per crop (partial sums combined
- * through distributed shared memory), 1 = one CTA per crop walking the same four point partitions in turn, 0 = automatic
- * (the cluster while 4 B CTAs fit one wave).  Both forms produce identical bits. */
+/* Shape of the final solve on the winner's inliers: 2 = split into three kernels (point moments over 4 CTAs per crop ->
+ * a warp per crop for the solver chain -> candidate errors + pick; EPnP's sums as contractions of raw moments), 4 = a
+ * thread-block cluster of four CTAs per crop (partial sums combined through distributed shared memory), 1 = one CTA per
+ * crop walking the same four point partitions in turn, 0 = automatic (split; with final = "epnp+gn" the cluster while 4 B
+ * CTAs fit one wave, else one CTA).  Forms 1 and 4 produce identical bits; the split form agrees with them to rounding
+ * (1e-9 deg / 1e-9 mm on BASELINE's crops), and none of the forms depends on the batch a crop came in. */
 int zp_set_final_form(zp_ctx* ctx, int form);
 
 /* EPnP on each m-point minimal set (float64).  K double [B,9] row-major.  hyp_poses double [B,H,12] out;

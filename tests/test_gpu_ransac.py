@@ -420,10 +420,12 @@ def test_gn_refine_against_twin(eng, batch):
 
 def test_final_solve_forms_identical(eng, batch):
     """the final solve as a 4-CTA cluster per crop (partial sums through distributed shared memory) and as one CTA per crop
-    walking the same four point partitions: identical bits, also for the Gauss-Newton polish and for a no-model crop"""
+    walking the same four point partitions: identical bits, also for the Gauss-Newton polish and for a no-model crop.  The
+    split form (three kernels, EPnP's sums as contractions of raw moments; the default for final="epnp") has the same
+    inlier set, counts and status and the same pose to rounding."""
     outs = []
     try:
-        for form in (1, 4, 0):
+        for form in (1, 4, 0, 2):
             eng.set_final_form(form)
             row = []
             for final in ("epnp", "epnp+gn"):
@@ -436,5 +438,13 @@ def test_final_solve_forms_identical(eng, batch):
     finally:
         eng.set_final_form(0)
     assert (outs[0][12] == 3).all() and np.array_equal(outs[0][10][0], [1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0])
-    for o in outs[1:]:
-        assert all(np.array_equal(a, b) for a, b in zip(outs[0], o))
+    assert all(np.array_equal(a, b) for a, b in zip(outs[0], outs[1]))
+    for o in outs[2:]:                       # automatic (= split for "epnp", one-kernel forms for the polish) and split
+        for k in (1, 2, 3, 4, 6, 7, 8, 9, 10, 11, 12):
+            assert np.array_equal(outs[0][k], o[k]), k
+        worst_r = float(np.abs(outs[0][0][:, :9] - o[0][:, :9]).max())        # (the arccos of rot_err_deg resolves 1.7e-6 deg)
+        worst_t = float(np.abs(outs[0][0][:, 9:] - o[0][:, 9:]).max())
+        print("split vs one-kernel final solve: max difference %.3g in R, %.3g mm in t" % (worst_r, worst_t))
+        assert worst_r <= 1e-10 and worst_t <= 1e-8
+    assert np.array_equal(outs[2][5], outs[0][5]) and np.array_equal(outs[3][5], outs[0][5])      # the polish runs in the one-kernel forms
+    assert np.array_equal(outs[2][0], outs[3][0])      # automatic == split for final="epnp"

@@ -13,7 +13,7 @@ import bench  # noqa: E402
 import zebrapose_b200 as zp  # noqa: E402
 
 NAMES = ["zp_samples_kernel", "zp_cvs_prep_kernel", "zp_cvs_null_kernel", "zp_cvs_cand_kernel", "zp_cvs_pick_kernel", "zp_minimal_kernel", "zp_score_kernel", "zp_rs_replay_kernel",
-         "zp_final_kernel"]
+         "zp_fin_moments_kernel", "zp_fin_solve_kernel", "zp_fin_errors_kernel", "zp_final_kernel"]
 
 
 def main():

@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libzebrapose_b200.so")
 OBJDIR = os.path.join(HERE, "build")
-SOURCES = ["zp_api.cu", "zp_decode.cu", "zp_ransac.cu", "zp_cvsolve.cu", "zp_eval.cu", "zp_head.cu"]
+SOURCES = ["zp_api.cu", "zp_decode.cu", "zp_ransac.cu", "zp_cvsolve.cu", "zp_finsplit.cu", "zp_eval.cu", "zp_head.cu"]
 EXTRA_FLAGS = {"zp_cvsolve.cu": ["-fmad=false"]}
 HEADERS = ["zp_common.cuh", "zp_epnp.cuh", "zp_cvepnp.cuh", "zp_proj.cuh",
            os.path.join("..", "..", "include", "zebrapose_b200.h")]

@@ -123,6 +123,7 @@ void zp_destroy(zp_ctx* ctx) {
     if (ctx->ws) cudaFree(ctx->ws);
     if (ctx->hws) cudaFree(ctx->hws);
     if (ctx->cvws) cudaFree(ctx->cvws);
+    if (ctx->fws) cudaFree(ctx->fws);
     for (auto& g : ctx->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
     if (ctx->gws) cudaFree(ctx->gws);
     if (ctx->dws) cudaFree(ctx->dws);
@@ -161,7 +162,7 @@ int zp_set_solver(zp_ctx* ctx, int solver) {
 
 int zp_set_final_form(zp_ctx* ctx, int form) {
     if (!ctx) return -1;
-    if (form != 0 && form != 1 && form != 4) ZP_FAIL(ctx, -1, "zp_set_final_form: 0 (automatic), 1 (one CTA per crop) or 4 (cluster of 4)");
+    if (form != 0 && form != 1 && form != 2 && form != 4) ZP_FAIL(ctx, -1, "zp_set_final_form: 0 (automatic), 1 (one CTA per crop), 2 (split: three kernels) or 4 (cluster of 4)");
     ctx->fin_force = form;
     ctx->fin_form_set = true;
     return 0;

@@ -83,6 +83,9 @@ struct zp_ctx {
     // hand-off records between the stages of the exact minimal solver (zp_cvsolve.cu)
     void* cvws = nullptr;
     size_t cvws_bytes = 0;
+    // workspace of the split final solve (zp_finsplit.cu): packed inlier lists, partial sums, candidates
+    void* fws = nullptr;
+    size_t fws_bytes = 0;
     // RANSAC: minimal solver (ZP_SOLVER_*), wave plan (hypotheses per wave; n_waves = 0: automatic)
     int solver = 0;
     int n_waves = 0;
@@ -131,6 +134,16 @@ struct zp_ctx {
             (ctx)->t_open = false;                                                           \
         }                                                                                    \
     } while (0)
+
+// arguments of the final solve (zp_final_cl_kernel in zp_ransac.cu, the split form in zp_finsplit.cu)
+struct FinalArgs {
+    const float* corr; int cap; const int32_t* counts; const double* K; const double* hyp_poses;
+    const int32_t* hyp_inliers; int B, H, m; double conf; int select_mode; float inv_thr; int final_mode;
+    double* poses; int32_t* n_inliers; int32_t* status; int32_t* best_idx; uint8_t* inlier_mask;
+    const int32_t* rs; int32_t* iters_run;      // per-crop RANSAC state {niters, maxGood, best, iterations run}
+    float thr2;                                  // float32(thr_px^2), cv2's comparison value
+    double* records;                             // nullable [B,14]: pose | n_inliers | status as doubles (the multi-GPU gather record)
+};
 
 int zp_ws_reserve(zp_ctx* ctx, size_t bytes);
 

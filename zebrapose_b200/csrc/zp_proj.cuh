@@ -22,6 +22,20 @@ __device__ __forceinline__ void zp_make_P(const double* pose, const double* K, d
     }
 }
 
+// d = (x - u z)^2 + (y - v z)^2 - z^2 with [x y z] = P [X Y Z 1] and u, v already divided by thr; the point is an inlier
+// iff d < 0, i.e. iff the SIGN BIT of d is set (14 FP32-pipe instructions, no compare; explicit fmaf so every kernel
+// rounds identically).
+__device__ __forceinline__ float zp_inlier_d(const float4& p0, const float4& p1, const float4& p2, float u, float v,
+                                             float X, float Y, float Z) {
+    float x = fmaf(p0.x, X, fmaf(p0.y, Y, fmaf(p0.z, Z, p0.w)));
+    float y = fmaf(p1.x, X, fmaf(p1.y, Y, fmaf(p1.z, Z, p1.w)));
+    float z = fmaf(p2.x, X, fmaf(p2.y, Y, fmaf(p2.z, Z, p2.w)));
+    float dx = fmaf(-u, z, x);
+    float dy = fmaf(-v, z, y);
+    float e = fmaf(dx, dx, __fmul_rn(dy, dy));
+    return fmaf(-z, z, e);                         // same roundings as the packed (FFMA2) form in zp_score_kernel
+}
+
 // The inlier decision exactly as cv2's PnPRansacCallback::computeError makes it (projectPoints in double without
 // distortion -> float32 image point -> float32 squared distance <= float32(thr^2)); every operation spelled out, no
 // contraction.  Used where ONE hypothesis per crop is evaluated (the winner's final inlier set) for the points the

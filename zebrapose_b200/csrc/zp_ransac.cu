@@ -189,20 +189,6 @@ zp_samples_kernel(const int32_t* __restrict__ counts, int cap, int B, int H, int
 // ---------------------------------------------------------------------------------------------------------------
 // projection matrices and the inlier predicate shared by the minimal solver (writes P), scoring and the final solve
 // ---------------------------------------------------------------------------------------------------------------
-// d = (x - u z)^2 + (y - v z)^2 - z^2 with [x y z] = P [X Y Z 1] and u, v already divided by thr; the point is an inlier
-// iff d < 0, i.e. iff the SIGN BIT of d is set (14 FP32-pipe instructions, no compare; explicit fmaf so every kernel
-// rounds identically).
-__device__ __forceinline__ float zp_inlier_d(const float4& p0, const float4& p1, const float4& p2, float u, float v,
-                                             float X, float Y, float Z) {
-    float x = fmaf(p0.x, X, fmaf(p0.y, Y, fmaf(p0.z, Z, p0.w)));
-    float y = fmaf(p1.x, X, fmaf(p1.y, Y, fmaf(p1.z, Z, p1.w)));
-    float z = fmaf(p2.x, X, fmaf(p2.y, Y, fmaf(p2.z, Z, p2.w)));
-    float dx = fmaf(-u, z, x);
-    float dy = fmaf(-v, z, y);
-    float e = fmaf(dx, dx, __fmul_rn(dy, dy));
-    return fmaf(-z, z, e);                         // same roundings as the packed (FFMA2) form in zp_score_kernel
-}
-
 // packed FP32 pairs (Blackwell FFMA2 / FMUL2 / FADD2): two independent IEEE fma.rn per instruction, one issue slot and
 // one 64-bit operand read per source
 typedef unsigned long long f32x2;
@@ -660,14 +646,6 @@ __device__ __forceinline__ void block_reduce(double* v, double* s_red /* [FIN_TH
     __syncthreads();
 }
 
-struct FinalArgs {
-    const float* corr; int cap; const int32_t* counts; const double* K; const double* hyp_poses;
-    const int32_t* hyp_inliers; int B, H, m; double conf; int select_mode; float inv_thr; int final_mode;
-    double* poses; int32_t* n_inliers; int32_t* status; int32_t* best_idx; uint8_t* inlier_mask;
-    const int32_t* rs; int32_t* iters_run;      // per-crop RANSAC state {niters, maxGood, best, iterations run}
-    float thr2;                                  // float32(thr_px^2), cv2's comparison value
-    double* records;                             // nullable [B,14]: pose | n_inliers | status as doubles (the multi-GPU gather record)
-};
 
 // ---------------------------------------------------------------------------------------------------------------
 // Winner's inliers -> final EPnP, spread over a THREAD-BLOCK CLUSTER.  Round 1's form -- one CTA per crop -- kept 64 of the
@@ -1176,6 +1154,8 @@ int zp_launch_score(zp_ctx* ctx, const float* corr, int cap, const int32_t* coun
     return launch_score_ng<4>(ctx, a, smem, st);
 }
 
+int zp_launch_final_split(zp_ctx* ctx, const FinalArgs& a, cudaStream_t st);
+
 int zp_launch_final(zp_ctx* ctx, const float* corr, int cap, const int32_t* counts, const double* K,
                     const double* hyp_poses, const int32_t* hyp_inliers, int B, int H, int m, double conf, int select_mode,
                     float thr_px, int final_mode, double* poses, int32_t* n_inliers, int32_t* status, int32_t* best_idx,
@@ -1201,7 +1181,9 @@ int zp_launch_final(zp_ctx* ctx, const float* corr, int cap, const int32_t* coun
     // the cluster form while its 4 B CTAs fit one wave of two CTAs per SM: below that the GPU is not full and a crop's point
     // passes are 4x shorter; above it the single-CTA form does the same arithmetic without the redundant solver phases.
     // Both produce identical bits (same partition, same reduction order).
-    const bool cluster = ctx->fin_force ? ctx->fin_force == 4 : 4 * B <= 2 * ctx->sm_count;
+    // default: the split form (zp_finsplit.cu); the Gauss-Newton polish and explicitly selected forms run here
+    if ((ctx->fin_force == 2 || ctx->fin_force == 0) && final_mode == ZP_FINAL_EPNP) return zp_launch_final_split(ctx, a, st);
+    const bool cluster = ctx->fin_force == 1 || ctx->fin_force == 4 ? ctx->fin_force == 4 : 4 * B <= 2 * ctx->sm_count;
     ZP_TIME_BEGIN(ctx, st);
     if (cluster) {
         cudaLaunchConfig_t cfg = {};

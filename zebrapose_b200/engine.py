@@ -94,7 +94,8 @@ class Engine:
         self.ctx.check(self.lib.zp_set_waves(self.ctx.handle, int(arr.size), arr.ctypes.data_as(C.c_void_p)), "zp_set_waves")
 
     def set_final_form(self, form=0):
-        """final solve as a 4-CTA cluster per crop (4), one CTA per crop (1) or automatic (0); identical results"""
+        """final solve split into three kernels (2; the default 0 for final="epnp"), as a 4-CTA cluster per crop (4) or one CTA
+        per crop (1): forms 1 and 4 give identical bits, the split form the same pose to rounding"""
         self.ctx.check(self.lib.zp_set_final_form(self.ctx.handle, int(form)), "zp_set_final_form")
 
     def set_score_groups(self, groups=0, hyp_chunk=0):
@@ -516,11 +517,6 @@ class Pipeline:
 
     def __init__(self, device=None, lanes=6):
         self.engines = [Engine(device) for _ in range(int(lanes))]
-        if len(self.engines) > 1:
-            # several batches in flight compete for SM residency: the one-CTA-per-crop final solve holds a quarter of the
-            # cluster form's registers (212 k vs 183 k poses/s at 6 lanes); a lone engine keeps the cluster (latency)
-            for e in self.engines:
-                e.set_final_form(1)
         self.device = self.engines[0].device
         self.streams = [torch.cuda.Stream(device=self.device) for _ in self.engines]
         self._next = 0
