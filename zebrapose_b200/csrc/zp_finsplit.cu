@@ -328,19 +328,30 @@ __global__ void __launch_bounds__(FS_THREADS, 4) zp_fin_errors_kernel(FinalArgs 
     const uint16_t* gl = w.idx + (size_t)b * a.cap + (size_t)list * chunk;
     const int wcount = w.wcnt[b * FS_LISTS + list];
     double acc[3] = {0, 0, 0};
-#pragma unroll 2
-    for (int k = lane; k < wcount; k += 32) {
-        const int i = gl[k];
-        const double X = pX[i], Y = pY[i], Z = pZ[i], u = pu[i], v = pv[i];
+    for (int k0 = 0; k0 < wcount; k0 += 128) {            // four points per trip: their indices, then their 20 gathers, up front
+        int idx[4];
+        float fX[4], fY[4], fZ[4], fu[4], fv[4];
 #pragma unroll
-        for (int c = 0; c < 3; c++) {
-            // candidates are re-read from shared memory per point (volatile: hoisted out of the loop they would take 72 registers)
-            const volatile double* q = s_c[c];
-            const double Xc = q[0] * X + q[1] * Y + q[2] * Z + q[9];
-            const double Yc = q[3] * X + q[4] * Y + q[5] * Z + q[10];
-            const double iz = 1.0 / (q[6] * X + q[7] * Y + q[8] * Z + q[11]);
-            const double du = u - (cam.uc + cam.fu * Xc * iz), dv = v - (cam.vc + cam.fv * Yc * iz);
-            acc[c] += sqrt(du * du + dv * dv);           // = zp_reproj_dist (epnp::reprojection_error)
+        for (int q = 0; q < 4; q++) idx[q] = k0 + 32 * q + lane < wcount ? (int)gl[k0 + 32 * q + lane] : -1;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const int i = idx[q] < 0 ? 0 : idx[q];
+            fX[q] = pX[i]; fY[q] = pY[i]; fZ[q] = pZ[i]; fu[q] = pu[i]; fv[q] = pv[i];
+        }
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            if (idx[q] < 0) continue;                     // the sums stay in list order: k0 + lane, + 32, + 64, + 96
+            const double X = fX[q], Y = fY[q], Z = fZ[q], u = fu[q], v = fv[q];
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                // candidates are re-read from shared memory per point (volatile: hoisted out of the loop they would take 72 registers)
+                const volatile double* p = s_c[c];
+                const double Xc = p[0] * X + p[1] * Y + p[2] * Z + p[9];
+                const double Yc = p[3] * X + p[4] * Y + p[5] * Z + p[10];
+                const double iz = 1.0 / (p[6] * X + p[7] * Y + p[8] * Z + p[11]);
+                const double du = u - (cam.uc + cam.fu * Xc * iz), dv = v - (cam.vc + cam.fv * Yc * iz);
+                acc[c] += sqrt(du * du + dv * dv);           // = zp_reproj_dist (epnp::reprojection_error)
+            }
         }
     }
 #pragma unroll
