@@ -119,6 +119,13 @@ int zp_set_solver(zp_ctx* ctx, int solver);
  * (cv2 never consults a hypothesis at or past its stopping iteration). */
 int zp_set_waves(zp_ctx* ctx, int n, const int32_t* sizes);
 
+/* Near-ties in the replay of cv2's update rule (`good > maxGood`, CNN_output_to_pose.py:155-157 -> cv2.solvePnPRansac): on = 1
+ * (default) re-counts, with cv2's own double -> float32 arithmetic for the points the FP32 scoring predicate puts within
+ * 1e-3 px of the threshold, every hypothesis that comes within 3 inliers of the running maximum (and, once, the record
+ * holder), so those decisions are taken on cv2's counts; on = 0 lets the FP32 counts decide everything (they can differ by
+ * one for such a point, the slack north_star allows). */
+int zp_set_exact_ties(zp_ctx* ctx, int on);
+
 /* Shape of the final solve on the winner's inliers: 2 = split into three kernels (point moments over 4 CTAs per crop ->
  * a warp per crop for the solver chain -> candidate errors + pick; EPnP's sums as contractions of raw moments), 4 = a
  * thread-block cluster of four CTAs per crop (partial sums combined through distributed shared memory), 1 = one CTA per

@@ -170,6 +170,38 @@ def test_full_chain_vs_cv2(eng, batch):
         assert abs(np.linalg.det(R) - 1) < 1e-9
 
 
+def test_near_ties_are_decided_on_exact_counts(eng, batch):
+    """cv2 replaces its best model only on a STRICTLY greater inlier count.  With every hypothesis of a crop drawn from the
+    same sample all 150 counts tie, so every decision after the first is a near-tie: the replay re-counts the holder and the
+    challenger with cv2's arithmetic and must keep hypothesis 0, with the iteration count the first record set.  Also: the
+    switch only matters for near-ties (same result on the ordinary batch for all crops but at most one), and the result is
+    deterministic."""
+    B = len(batch["lists"])
+    s = eng.make_samples(batch["counts"], batch["corr"].shape[2], H=150, m=5)
+    tied = s[:, :1, :].expand(-1, 150, -1).contiguous()
+    try:
+        outs = {}
+        for on in (True, False):
+            eng.set_exact_ties(on)
+            r = eng.ransac(batch["corr"], batch["counts"], batch["Ks"], samples=tied, return_details="state")
+            outs[on] = {k: r[k].cpu().numpy() for k in ("poses", "n_inliers", "best_idx", "iters_run", "status")}
+            r = eng.ransac(batch["corr"], batch["counts"], batch["Ks"], return_details="state")
+            outs[on, "plain"] = {k: r[k].cpu().numpy() for k in ("poses", "n_inliers", "best_idx", "iters_run", "status")}
+    finally:
+        eng.set_exact_ties(True)
+    ok = outs[True]["status"] == 0
+    assert ok.any()
+    assert (outs[True]["best_idx"][ok] == 0).all() and (outs[False]["best_idx"][ok] == 0).all()
+    assert np.array_equal(outs[True]["iters_run"], outs[False]["iters_run"])
+    assert np.array_equal(outs[True]["poses"], outs[False]["poses"])
+    a, b = outs[True, "plain"], outs[False, "plain"]
+    same = a["best_idx"] == b["best_idx"]
+    assert same.sum() >= B - 1
+    assert np.array_equal(a["poses"][same], b["poses"][same])
+    r = eng.ransac(batch["corr"], batch["counts"], batch["Ks"], return_details="state")
+    assert np.array_equal(r["poses"].cpu().numpy(), a["poses"]) and np.array_equal(r["best_idx"].cpu().numpy(), a["best_idx"])
+
+
 def test_waves_do_not_change_the_result(eng, batch):
     """cv2 never consults a hypothesis at or past its stopping iteration, so solving + scoring the hypotheses in waves and
     skipping finished crops must give bit-identical poses, winners and iteration counts for any wave plan"""

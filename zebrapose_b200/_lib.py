@@ -35,6 +35,7 @@ SIGNATURES = {
     "zp_set_solver": (_i, [_vp, _i]),
     "zp_set_waves": (_i, [_vp, _i, _vp]),
     "zp_set_final_form": (_i, [_vp, _i]),
+    "zp_set_exact_ties": (_i, [_vp, _i]),
     "zp_pose_batch_device": (_i, [_vp, _vp, _i, _i, _i, C.POINTER(_i64), _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _d, _i,
                                   _u64, _i, _i, _vp, _vp, _vp, _vp, _i, _vp]),
     "zp_pose_batch_host": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _i, _i, _f, _d, _i, _u64, _i, _i,

@@ -15,7 +15,7 @@ int zp_launch_final(zp_ctx*, const float*, int, const int32_t*, const double*, c
                     double*, cudaStream_t);
 int zp_launch_rs_init(zp_ctx*, const int32_t*, int, int, int, int32_t*, int32_t*, int32_t*, cudaStream_t);
 int zp_launch_rs_replay(zp_ctx*, const int32_t*, int, const int32_t*, int, int, int, int, int, double, int, int32_t*,
-                        int32_t*, cudaStream_t);
+                        int32_t*, const float*, const double*, const double*, float, cudaStream_t);
 int zp_launch_fma_probe(zp_ctx*, int, int, double*);
 int zp_launch_dfma_probe(zp_ctx*, int, double*);
 int zp_read_debug_clocks(long long*);
@@ -157,6 +157,12 @@ int zp_set_solver(zp_ctx* ctx, int solver) {
     if (!ctx) return -1;
     if (solver != ZP_SOLVER_CV2 && solver != ZP_SOLVER_FAST) ZP_FAIL(ctx, -1, "zp_set_solver: bad solver %d", solver);
     ctx->solver = solver;
+    return 0;
+}
+
+int zp_set_exact_ties(zp_ctx* ctx, int on) {
+    if (!ctx) return -1;
+    ctx->rs_no_recount = on ? 0 : 1;
     return 0;
 }
 
@@ -431,7 +437,7 @@ static int ransac_impl(zp_ctx* ctx, const float* corr, int cap, const int32_t* c
     // workspace: hyp_P | RANSAC state | done flags | samples | hyp_poses | hyp_inliers (the last three only if the caller
     // did not supply them)
     size_t o_P = 0, o_rs = o_P + align256((size_t)B * H * 24 * 4), o_dn = o_rs + align256((size_t)B * 4 * 4);
-    size_t o_s = o_dn + align256((size_t)B * 4);
+    size_t o_s = o_dn + align256((size_t)B * 4 * 5);        // done flags [B] | near-tie state [B][4]
     size_t o_p = o_s + (samples ? 0 : align256((size_t)B * H * m * 4));
     size_t o_i = o_p + (hyp_poses ? 0 : align256((size_t)B * H * 12 * 8));
     size_t total = o_i + (hyp_inliers ? 0 : align256((size_t)B * H * 4));
@@ -460,7 +466,8 @@ static int ransac_impl(zp_ctx* ctx, const float* corr, int cap, const int32_t* c
         if (int r = zp_launch_minimal(ctx, corr, cap, counts, K, samples ? samples : d_samples, B, H, h0, hw, d_done, d_lim, m,
                                       thr_px, d_hp, d_P, d_hi, st)) return r;
         if (int r = zp_launch_score(ctx, corr, cap, counts, d_P, B, H, h0, hw, d_done, d_lim, thr_px, d_hi, true, st)) return r;
-        if (int r = zp_launch_rs_replay(ctx, counts, cap, d_hi, B, H, h0, h0 + hw, m, confidence, select_mode, d_rs, d_done, st))
+        if (int r = zp_launch_rs_replay(ctx, counts, cap, d_hi, B, H, h0, h0 + hw, m, confidence, select_mode, d_rs, d_done, corr, K, d_hp,
+                                        thr_px, st))
             return r;
         h0 += hw;
     }
@@ -525,7 +532,7 @@ int zp_pose_batch_device(zp_ctx* ctx, const void* logits, int dtype, int B, int 
     key.p[7] = status; key.p[8] = records; key.p[9] = stream;
     for (int q = 0; q < 4; q++) key.s[q] = strides[q];
     const int iv[16] = {dtype, B, S, mask_ch, bit0_ch, n_bits, ignore_bit, obj_default, H, m, sampler, select_mode, final_mode,
-                        ctx->solver, ctx->n_waves, ctx->fin_force * 100000 + ctx->force_decode_path * 1000 + ctx->decode_rpc};
+                        ctx->solver, ctx->n_waves, ctx->rs_no_recount * 10000000 + ctx->fin_force * 100000 + ctx->force_decode_path * 1000 + ctx->decode_rpc};
     for (int q = 0; q < 16; q++) key.i[q] = iv[q];
     for (int q = 0; q < 16; q++) key.w[q] = q < ctx->n_waves ? ctx->wave_sizes[q] : 0;
     key.f = thr_px; key.c = confidence; key.seed = seed;

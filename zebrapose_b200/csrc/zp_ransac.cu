@@ -572,29 +572,92 @@ __global__ void zp_rs_init_kernel(const int32_t* __restrict__ counts, int cap, i
         const int n = min(counts[b], cap);
         rs[4 * b] = max(H, 1); rs[4 * b + 1] = 0; rs[4 * b + 2] = -1; rs[4 * b + 3] = 0;
         crop_done[b] = n < 6 ? 1 : 0;                 // CNN_output_to_pose.py:126: no RANSAC below six correspondences
+        int32_t* tie = crop_done + B + 4 * (size_t)b;  // near-tie state of zp_rs_replay_kernel: nothing exact, nothing parked
+        tie[0] = 0; tie[1] = -1; tie[2] = -1; tie[3] = 0;
     }
     if (hyp_inliers_fill)                              // hypotheses that are never run read back as -1
         for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < B * H; i += gridDim.x * blockDim.x) hyp_inliers_fill[i] = -1;
 }
 
-// One WARP per crop.  Only "records" (counts above everything before them) can change the state, so a chunk of 32 counts
-// is loaded coalesced, an inclusive prefix maximum flags the records, and the warp walks the few flagged ones in order
-// (pow / log only there).  (A first version -- one thread per crop walking the counts one by one -- took 54 us per wave.)
-constexpr int RS_WARPS = 4;
-__global__ void __launch_bounds__(32 * RS_WARPS)
-zp_rs_replay_kernel(const int32_t* __restrict__ counts, int cap, const int32_t* __restrict__ hyp_inliers, int B, int H, int h0,
-                    int h1, int m, double conf, int select_mode, int32_t* __restrict__ rs, int32_t* __restrict__ crop_done) {
-    const int lane = threadIdx.x & 31;
-    const int b = blockIdx.x * RS_WARPS + (threadIdx.x >> 5);
-    if (b >= B || crop_done[b]) return;
-    const int n = min(counts[b], cap);
-    int niters = rs[4 * b], maxgood = rs[4 * b + 1], best = rs[4 * b + 2];
-    const int32_t* hi = hyp_inliers + (size_t)b * H;
-    int last = h0 - 1;                                  // last iteration that changed the state
-    bool stop = false;
-    for (int c0 = h0; c0 < h1 && !stop; c0 += 32) {
+// One CTA per crop; every warp of it replays the same state machine on the same data (uniform control flow), so that the
+// whole CTA can re-count a hypothesis when a decision needs exact counts.  Only "records" (counts above everything before
+// them) can change the state, so a chunk of 32 counts is loaded coalesced, an inclusive prefix maximum flags the records, and
+// the flagged ones are walked in order (pow / log only there).  (A first version -- one thread per crop walking the counts
+// one by one -- took 54 us per wave.)
+//
+// Near-ties.  The scoring kernel's FP32 predicate may differ from cv2's float32 projectPoints error for a point within
+// ~1e-4 px of the threshold (north_star allows 1e-3 px), so a count can be off by one, and when a hypothesis comes within
+// RS_SLACK of the running maximum that is enough to flip cv2's strictly-greater decision (measured: 1 crop in 1536).  Such
+// decisions are taken on EXACT counts instead: the CTA re-counts the hypothesis -- and, once, the current record holder --
+// over all correspondences with the same predicate, re-deciding the doubtful points with cv2's own arithmetic
+// (zp_inlier_exact), exactly as the final solve builds the winner's inlier set.  Clear decisions keep the FP32 counts.
+constexpr int RS_THREADS = 256;                  // one CTA per crop: every warp replays the same state machine, all threads re-count
+constexpr int RS_SLACK = 3;
+
+// all RS_THREADS threads of the crop's CTA call this together (the replay's control flow is CTA-uniform); every thread gets the count
+__device__ int zp_exact_count_cta(const float* __restrict__ cb, int cap, int n, const double* __restrict__ hp,
+                                  const double* __restrict__ Kb, float inv_thr, float thr2, int* s_part) {
+    const int tid = threadIdx.x;
+    float P[12];
+    zp_make_P(hp, Kb, (double)inv_thr, P);
+    const float4 p0 = make_float4(P[0], P[1], P[2], P[3]), p1 = make_float4(P[4], P[5], P[6], P[7]),
+                 p2 = make_float4(P[8], P[9], P[10], P[11]);
+    const float *pu = cb, *pv = cb + cap, *pX = cb + 2 * (size_t)cap, *pY = cb + 3 * (size_t)cap, *pZ = cb + 4 * (size_t)cap;
+    int c = 0;
+    for (int i0 = 0; i0 < n; i0 += 4 * RS_THREADS) {      // four points per thread and trip, their 20 loads up front
+        float fu[4], fv[4], fX[4], fY[4], fZ[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const int i = i0 + RS_THREADS * q + tid;
+            const bool ld = i < n;
+            fu[q] = ld ? pu[i] : 0.f; fv[q] = ld ? pv[i] : 0.f; fX[q] = ld ? pX[i] : 0.f; fY[q] = ld ? pY[i] : 0.f; fZ[q] = ld ? pZ[i] : 0.f;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            if (i0 + RS_THREADS * q + tid >= n) continue;
+            const float d = zp_inlier_d(p0, p1, p2, fu[q] * inv_thr, fv[q] * inv_thr, fX[q], fY[q], fZ[q]);
+            bool in = __float_as_int(d) < 0;
+            const float z = fmaf(p2.x, fX[q], fmaf(p2.y, fY[q], fmaf(p2.z, fZ[q], p2.w)));
+            if (fabsf(d) <= 1e-3f * z * z) in = zp_inlier_exact(hp, Kb[0], Kb[4], Kb[2], Kb[5], fu[q], fv[q], fX[q], fY[q], fZ[q], thr2);
+            c += in;
+        }
+    }
+    c = __reduce_add_sync(0xffffffffu, c);
+    __syncthreads();                                       // the previous call's s_part has been read by everybody
+    if ((tid & 31) == 0) s_part[tid >> 5] = c;
+    __syncthreads();
+    int t = 0;
+#pragma unroll
+    for (int w = 0; w < RS_THREADS / 32; w++) t += s_part[w];
+    return t;
+}
+
+struct RsExact {            // inputs of the near-tie recount (corr == nullptr: FP32 counts decide everything)
+    const float* corr; const double* K; const double* hyp_poses; float inv_thr, thr2;
+    int32_t* tie;           // [B][4] per crop: {flags (1: maxGood is an exact count, 2: so is the parked state's), first parked iteration or -1, parked best, parked maxGood}
+};
+
+// cv2's loop state of one crop while the replay walks it (registers of the crop's warp, all lanes hold the same values)
+struct RsState { int niters, maxgood, best, exact, last; };
+
+// Walks iterations [from, to) of crop b.  Returns -1 when it reached `to` or cv2's stopping iteration (`stop` says which),
+// or -- only with `park` -- the index of a near-tie that must be decided on exact counts while earlier near-ties are still
+// parked: the caller resolves those first (an exact walk from the first parked one) and calls again from that index.
+//
+// Parking.  Before the first good hypothesis the counts are a few dozen and near-ties among them are frequent (measured: up to
+// ~25 per crop, 8 us of re-counting each), but they are irrelevant as soon as a later hypothesis beats the running maximum
+// by more than 2 RS_SLACK: it is a record on the exact counts too, whichever way the parked decisions went, and as long as the
+// counts involved leave niters at the cap H the state after it is the same.  So a near-tie whose counts cannot move niters
+// is decided on the FP32 counts and only remembered (`pend`: the state before the first such decision); a clear record
+// forgets it; anything else that needs exact counts -- or the end of the last wave -- first replays from the parked state
+// with re-counting.
+__device__ int zp_rs_walk(int from, int to, RsState& s, bool& stop, bool park, int& pend_from, RsState& pend, const int32_t* hi,
+                          int n, int m, int H, double conf, bool recount, const float* cb, int cap, const double* Kb,
+                          const double* hp_crop, const RsExact& ex, int lane, int* s_part) {
+    const int slack = recount ? RS_SLACK : 0;
+    for (int c0 = from; c0 < to && !stop; c0 += 32) {
         const int h = c0 + lane;
-        const int good = h < h1 ? hi[h] : INT_MIN;
+        const int good = h < to ? hi[h] : INT_MIN;
         int v = good;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
@@ -603,26 +666,108 @@ zp_rs_replay_kernel(const int32_t* __restrict__ counts, int cap, const int32_t* 
         }
         int prev = __shfl_up_sync(0xffffffffu, v, 1);
         if (lane == 0) prev = INT_MIN;
-        unsigned bal = __ballot_sync(0xffffffffu, h < h1 && good > max(max(prev, maxgood), m - 1));
-        if (select_mode == ZP_SELECT_CV2_REPLAY) {
-            while (bal) {
-                const int l = __ffs(bal) - 1;
-                bal &= bal - 1;
-                if (c0 + l >= niters) { stop = true; break; }       // cv2's loop has ended before this iteration
-                const int g = __shfl_sync(0xffffffffu, good, l);
-                best = c0 + l; maxgood = g; last = c0 + l;
-                niters = zp_update_iters(conf, (double)(n - g) / n, m, niters);
+        // a hypothesis more than `slack` below an earlier count of its chunk cannot become a record on exact counts either
+        unsigned bal = __ballot_sync(0xffffffffu, h < to && good > INT_MIN + slack && good + slack > max(max(prev, s.maxgood), m - 1));
+        while (bal) {
+            const int l = __ffs(bal) - 1;
+            bal &= bal - 1;
+            if (c0 + l >= s.niters) { stop = true; break; }       // cv2's loop has ended before this iteration
+            int g = __shfl_sync(0xffffffffu, good, l);
+            const int ref = max(s.maxgood, m - 1);
+            if (g + slack <= ref) continue;                        // the maximum has moved on since the flags were taken
+            int g_exact = 0;
+            if (recount && g - ref <= slack) {                     // near-tie
+                if (park && s.niters == H && zp_update_iters(conf, (double)(n - min(n, max(g, ref) + slack)) / n, m, H) == H) {
+                    if (pend_from < 0) { pend_from = c0 + l; pend = s; }
+                    if (g <= ref) continue;                        // FP32 decision for now; niters stays at the cap
+                } else {
+                    if (pend_from >= 0) return c0 + l;             // parked decisions come first
+                    if (!s.exact && s.best >= 0) {
+                        s.maxgood = zp_exact_count_cta(cb, cap, n, hp_crop + (size_t)s.best * 12, Kb, ex.inv_thr, ex.thr2, s_part);
+                        s.exact = 1;
+                    }
+                    g = zp_exact_count_cta(cb, cap, n, hp_crop + (size_t)(c0 + l) * 12, Kb, ex.inv_thr, ex.thr2, s_part);
+                    g_exact = 1;
+                    if (g <= max(s.maxgood, m - 1)) continue;
+                }
+            } else if (pend_from >= 0 && g - ref > 2 * slack) {
+                pend_from = -1;                                    // a record on any counts: the parked near-ties no longer matter
             }
-            if (c0 + 32 >= niters) stop = true;
-        } else if (bal) {                                  // most inliers, lowest index on ties, every hypothesis consulted
-            const int l = 31 - __clz(bal);
-            best = c0 + l; maxgood = __shfl_sync(0xffffffffu, good, l);
+            s.best = c0 + l; s.maxgood = g; s.last = c0 + l; s.exact = g_exact;
+            s.niters = zp_update_iters(conf, (double)(n - g) / n, m, s.niters);
         }
+        if (c0 + 32 >= s.niters) stop = true;
     }
-    if (lane == 0) {
-        const int it = select_mode == ZP_SELECT_CV2_REPLAY ? max(last + 1, max(h0, min(h1, niters))) : h1;
-        rs[4 * b] = niters; rs[4 * b + 1] = maxgood; rs[4 * b + 2] = best; rs[4 * b + 3] = it;
-        if (h1 >= H || (select_mode == ZP_SELECT_CV2_REPLAY && h1 >= niters)) crop_done[b] = 1;
+    return -1;
+}
+
+__global__ void __launch_bounds__(RS_THREADS)
+zp_rs_replay_kernel(const int32_t* __restrict__ counts, int cap, const int32_t* __restrict__ hyp_inliers, int B, int H, int h0,
+                    int h1, int m, double conf, int select_mode, int32_t* __restrict__ rs, int32_t* __restrict__ crop_done, RsExact ex) {
+    const int lane = threadIdx.x & 31;
+    const int b = blockIdx.x;
+    __shared__ int s_part[RS_THREADS / 32];
+    if (crop_done[b]) return;
+    const int n = min(counts[b], cap);
+    const int32_t* hi = hyp_inliers + (size_t)b * H;
+    if (select_mode != ZP_SELECT_CV2_REPLAY) {             // most inliers, lowest index on ties, every hypothesis consulted
+        if (threadIdx.x >= 32) return;
+        int maxgood = rs[4 * b + 1], best = rs[4 * b + 2];
+        for (int c0 = h0; c0 < h1; c0 += 32) {
+            const int h = c0 + lane;
+            const int good = h < h1 ? hi[h] : INT_MIN;
+            int v = good;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, v, d);
+                if (lane >= d) v = max(v, t);
+            }
+            int prev = __shfl_up_sync(0xffffffffu, v, 1);
+            if (lane == 0) prev = INT_MIN;
+            const unsigned bal = __ballot_sync(0xffffffffu, h < h1 && good > max(max(prev, maxgood), m - 1));
+            if (bal) {
+                const int l = 31 - __clz(bal);
+                best = c0 + l; maxgood = __shfl_sync(0xffffffffu, good, l);
+            }
+        }
+        if (lane == 0) {
+            rs[4 * b + 1] = maxgood; rs[4 * b + 2] = best; rs[4 * b + 3] = h1;
+            if (h1 >= H) crop_done[b] = 1;
+        }
+        return;
+    }
+    const bool recount = ex.corr != nullptr;
+    const float* cb = recount ? ex.corr + (size_t)b * 5 * cap : nullptr;
+    const double* Kb = recount ? ex.K + 9 * (size_t)b : nullptr;
+    const double* hp_crop = recount ? ex.hyp_poses + (size_t)b * H * 12 : nullptr;
+    int32_t* tie = ex.tie + 4 * (size_t)b;
+    RsState s, pend;
+    s.niters = rs[4 * b]; s.maxgood = rs[4 * b + 1]; s.best = rs[4 * b + 2]; s.exact = tie[0] & 1; s.last = h0 - 1;
+    int pend_from = tie[1];
+    pend.niters = H; pend.best = tie[2]; pend.maxgood = tie[3]; pend.exact = (tie[0] >> 1) & 1; pend.last = h0 - 1;
+    bool stop = false;
+    int cur = h0;
+    for (;;) {
+        const int at = zp_rs_walk(cur, h1, s, stop, true, pend_from, pend, hi, n, m, H, conf, recount, cb, cap, Kb, hp_crop, ex, lane, s_part);
+        // parked near-ties must be settled before a decision that needs exact counts, and before this crop's last wave ends
+        const bool closing = at < 0 && (stop || h1 >= H || h1 >= s.niters);
+        if (pend_from < 0 || (at < 0 && !closing)) break;
+        const int upto = at >= 0 ? at : h1;
+        s = pend;
+        stop = false;
+        int none = -1;
+        RsState dummy = s;
+        zp_rs_walk(pend_from, upto, s, stop, false, none, dummy, hi, n, m, H, conf, recount, cb, cap, Kb, hp_crop, ex, lane, s_part);
+        pend_from = -1;
+        if (at < 0 || stop) break;
+        cur = at;
+    }
+    __syncthreads();                                       // every warp has read the crop's state before it is overwritten
+    if (threadIdx.x == 0) {
+        const int it = max(s.last + 1, max(h0, min(h1, s.niters)));
+        rs[4 * b] = s.niters; rs[4 * b + 1] = s.maxgood; rs[4 * b + 2] = s.best; rs[4 * b + 3] = it;
+        tie[0] = s.exact | (pend.exact << 1); tie[1] = pend_from; tie[2] = pend.best; tie[3] = pend.maxgood;
+        if (h1 >= H || h1 >= s.niters) crop_done[b] = 1;
     }
 }
 
@@ -1084,9 +1229,14 @@ int zp_launch_rs_init(zp_ctx* ctx, const int32_t* counts, int cap, int B, int H,
 }
 
 int zp_launch_rs_replay(zp_ctx* ctx, const int32_t* counts, int cap, const int32_t* hyp_inliers, int B, int H, int h0, int h1,
-                        int m, double conf, int select_mode, int32_t* rs, int32_t* crop_done, cudaStream_t st) {
+                        int m, double conf, int select_mode, int32_t* rs, int32_t* crop_done, const float* corr, const double* K,
+                        const double* hyp_poses, float thr_px, cudaStream_t st) {
+    RsExact ex;
+    ex.corr = ctx->rs_no_recount ? nullptr : corr; ex.K = K; ex.hyp_poses = hyp_poses;
+    ex.inv_thr = 1.0f / thr_px; ex.thr2 = (float)((double)thr_px * (double)thr_px);
+    ex.tie = crop_done + B;
     ZP_TIME_BEGIN(ctx, st);
-    zp_rs_replay_kernel<<<(B + RS_WARPS - 1) / RS_WARPS, 32 * RS_WARPS, 0, st>>>(counts, cap, hyp_inliers, B, H, h0, h1, m, conf, select_mode, rs, crop_done);
+    zp_rs_replay_kernel<<<B, RS_THREADS, 0, st>>>(counts, cap, hyp_inliers, B, H, h0, h1, m, conf, select_mode, rs, crop_done, ex);
     ZP_CHECK_LAUNCH(ctx, "zp_rs_replay_kernel");
     return 0;
 }
