@@ -587,6 +587,25 @@ def main():
     e2e_value = n_total * e2e_steps / e2e_s
     h2d = logits.nbytes + C * 4 * 8 + C * 9 * 8 + C * 4
     d2h = C * 12 * 8 + C * 4 + C * 4
+    # the same with bf16 logits on the host (what a bf16 network, configs[4], hands over; identical codes: only the sign of a
+    # logit is used): half the bytes on a PCIe-bound path.  Reported beside the headline, which stays float32 like the reference.
+    e2e_bf16 = None
+    if world == 1:
+        h_bf16 = torch.from_numpy(logits).to(torch.bfloat16).pin_memory()
+        for i in range(max(3, lanes)):
+            pipe.submit_host(h_bf16, bboxes, Ks, obj, out=outs[pipe.next_lane])
+        pipe.wait_host()
+        t0 = time.perf_counter()
+        for i in range(e2e_steps):
+            pipe.submit_host(h_bf16, bboxes, Ks, obj, out=outs[pipe.next_lane])
+        pipe.wait_host()
+        torch.cuda.synchronize()
+        s_bf16 = time.perf_counter() - t0
+        b_bf16 = h_bf16.numel() * 2 + C * 4 * 8 + C * 9 * 8 + C * 4
+        e2e_bf16 = {"value": n_total * e2e_steps / s_bf16, "unit": UNIT, "h2d_bytes_per_step": b_bf16,
+                    "h2d_gbs": b_bf16 * e2e_steps / s_bf16 / 1e9,
+                    "note": "same call with bfloat16 host logits (a bf16 network's output); not the headline: the reference's host logits are float32"}
+        del h_bf16
     if rank == 0:
         sampler.stop_flag = True
         sampler.join(timeout=2)
@@ -701,7 +720,7 @@ def main():
                     "bound": "pcie", "h2d_gbs": h2d * e2e_steps / e2e_s / 1e9 * world, "h2d_gbs_per_gpu": h2d * e2e_steps / e2e_s / 1e9,
                     "path": "zp_pose_batch_host_async + zp_sync (C ABI, pinned host logits -> pinned host poses), %d lanes" % lanes,
                     "host_cpus": "%d CPUs local to the GPU (NVML affinity)" % len(numa_cpus) if numa_cpus else "unbound",
-                    "steps": e2e_steps},
+                    "steps": e2e_steps, "bf16_logits": e2e_bf16},
             "gpu_launches": launches,
             "clocks": sampler.summary(t_host0, t_host1),
             "kernel_us": {k: round(v * 1e3, 2) for k, v in k_ms.items()},

@@ -44,7 +44,7 @@
 
 #define CVE_G 6              // lanes per hypothesis in stage B
 #define CVE_MAXM 8           // largest minimal-sample size
-#define CVE_RS 13            // row stride (doubles) of the 12x12 matrix in stage B: rows fall on distinct banks
+#define CVE_RS 14            // row stride (doubles) of the 12x12 matrix in stage B: even, so that rows are 16-byte aligned (128-bit shared-memory accesses)
 
 struct CveCam { double fu, fv, uc, vc; };
 
@@ -85,12 +85,11 @@ ZP_HD inline double cve_hypot(double a, double b) {
 //   beta < 0:  s = sqrt(((gamma-beta)*0.5) / gamma), c = p / (gamma*s*2);  else c = sqrt((gamma+beta) / (gamma*2)), s = p / (gamma*c*2)
 //   skip test |p| <= eps*sqrt(a*b): decided from p*p against eps^2*(a*b) when the two differ by more than 1e-9 relative
 //   (the rounding of the exact expression is 4 ulp at most); the square root is only taken in between or near underflow.
-template <int M, bool HASV>
-ZP_HD inline bool cve_pair(Dv Ai, Dv Aj, Dv Vi, Dv Vj, int n) {
+// the arithmetic of one pair on rows held in registers: returns false (rows untouched) when the pair is skipped, else the
+// rotation factors in c, s and the rotated rows in ri, rj
+template <int M>
+ZP_HD inline bool cve_pair_core(double* ri, double* rj, double& c, double& s) {
     const double eps = DBL_EPSILON * 10;
-    double ri[M], rj[M];
-#pragma unroll
-    for (int k = 0; k < M; k++) { ri[k] = Ai[k]; rj[k] = Aj[k]; }
     double p = 0, a = 0, b = 0;
 #pragma unroll
     for (int k = 0; k < M; k++) { p += ri[k] * rj[k]; a += ri[k] * ri[k]; b += rj[k] * rj[k]; }
@@ -118,13 +117,24 @@ ZP_HD inline bool cve_pair(Dv Ai, Dv Aj, Dv Vi, Dv Vj, int n) {
     const double den = neg ? gamma : gamma * 2;
     const double first = sqrt(num / den);
     const double second = p / (gamma * first * 2);
-    const double c = neg ? second : first, s = neg ? first : second;
+    c = neg ? second : first; s = neg ? first : second;
 #pragma unroll
     for (int k = 0; k < M; k++) {
         const double t0 = c * ri[k] + s * rj[k];
         const double t1 = -s * ri[k] + c * rj[k];
-        Ai[k] = t0; Aj[k] = t1;
+        ri[k] = t0; rj[k] = t1;
     }
+    return true;
+}
+
+template <int M, bool HASV>
+ZP_HD inline bool cve_pair(Dv Ai, Dv Aj, Dv Vi, Dv Vj, int n) {
+    double ri[M], rj[M], c, s;
+#pragma unroll
+    for (int k = 0; k < M; k++) { ri[k] = Ai[k]; rj[k] = Aj[k]; }
+    if (!cve_pair_core<M>(ri, rj, c, s)) return false;
+#pragma unroll
+    for (int k = 0; k < M; k++) { Ai[k] = ri[k]; Aj[k] = rj[k]; }
     if (HASV) {
         for (int k = 0; k < n; k++) {
             const double t0 = c * Vi[k] + s * Vj[k];
@@ -132,6 +142,34 @@ ZP_HD inline bool cve_pair(Dv Ai, Dv Aj, Dv Vi, Dv Vj, int n) {
             Vi[k] = t0; Vj[k] = t1;
         }
     }
+    return true;
+}
+
+// the same for two contiguous, 16-byte aligned rows (stage B): on the device the rows move as 128-bit shared-memory accesses
+// (half the load / store instructions of the pair step, whose shared-memory queue was a top stall: ncu mio_throttle)
+template <int M>
+ZP_HD inline bool cve_pair_rows(double* Ai, double* Aj) {
+    static_assert(M % 2 == 0, "rows are moved two doubles at a time");
+    double ri[M], rj[M], c, s;
+#ifdef __CUDA_ARCH__
+#pragma unroll
+    for (int k = 0; k < M; k += 2) {
+        const double2 u = *reinterpret_cast<const double2*>(Ai + k), v = *reinterpret_cast<const double2*>(Aj + k);
+        ri[k] = u.x; ri[k + 1] = u.y; rj[k] = v.x; rj[k + 1] = v.y;
+    }
+#else
+    for (int k = 0; k < M; k++) { ri[k] = Ai[k]; rj[k] = Aj[k]; }
+#endif
+    if (!cve_pair_core<M>(ri, rj, c, s)) return false;
+#ifdef __CUDA_ARCH__
+#pragma unroll
+    for (int k = 0; k < M; k += 2) {
+        *reinterpret_cast<double2*>(Ai + k) = make_double2(ri[k], ri[k + 1]);
+        *reinterpret_cast<double2*>(Aj + k) = make_double2(rj[k], rj[k + 1]);
+    }
+#else
+    for (int k = 0; k < M; k++) { Ai[k] = ri[k]; Aj[k] = rj[k]; }
+#endif
     return true;
 }
 
@@ -193,8 +231,7 @@ ZP_HD inline void cve_jstep_a(CveJ& j, int T) {
     else if (j.l - cnt_a < cnt_b) { ii = lo_b + (j.l - cnt_a); jj = tb - ii; s = sb; }
     else return;
     if (jj >= n || ii >= jj) return;
-    const Dv none = cve_dv(nullptr, 1);
-    if (cve_pair<M, false>(cve_dv(j.At + ii * j.astep, 1), cve_dv(j.At + jj * j.astep, 1), none, none, n)) j.chg[s & 3] = 1;
+    if (cve_pair_rows<M>(j.At + ii * j.astep, j.At + jj * j.astep)) j.chg[s & 3] = 1;     // At 16-byte aligned, astep even
 }
 
 // after the barrier that follows step T: if a sweep completed at T, stop when it rotated nothing (or at the sweep cap)

@@ -24,7 +24,7 @@ constexpr int CVA_THREADS = 64;                // stage A: private data 117 doub
 constexpr int CVA_PRIV = 24 + 16 + 32 + 12 + 33;
 constexpr int CVB_HPW = 5;                     // stage B: hypotheses per warp (5 x 6 lanes; lanes 30 and 31 idle)
 constexpr int CVB_WARPS = 2;
-constexpr int CVB_HB = 219;                    // doubles per hypothesis: A 156 | W 12 | V4 48 (first: al 32 | us 16) | flags 2 (+1: odd stride)
+constexpr int CVB_HB = 230;                    // doubles per hypothesis: A 12 x 14 = 168 | W 12 | V4 48 (first: al 32 | us 16) | flags 2; even: 16-byte aligned rows
 constexpr int CVC_THREADS = 64;                // stage C: 60 doubles of scratch per thread
 constexpr int CVC_PRIV = 60;
 
@@ -91,8 +91,8 @@ __global__ void __launch_bounds__(32 * CVB_WARPS, MINB) zp_cvs_null_kernel(CvsAr
     const bool run = h.run;
     if (!__any_sync(0xffffffffu, run)) return;
     double* S = s_b + (size_t)(warp * CVB_HPW + (slot < CVB_HPW ? slot : 0)) * CVB_HB;
-    double* A = S; double* W = S + 156; double* V4 = S + 168;
-    int* flags = (int*)(S + 216);
+    double* A = S; double* W = S + 12 * CVE_RS; double* V4 = W + 12;
+    int* flags = (int*)(V4 + 48);
     const Dv rec = cve_dv(a.rec + gloc, a.nhp);
     const bool stamp = a.dbg && blockIdx.x == 0 && tid == 0;
     if (stamp) a.dbg[0] = clock64();
