@@ -57,10 +57,10 @@ def CNN_outputs_to_object_pose(mask_image, class_code_image, Bbox, Bbox_Size, cl
     -> (rot 3x3 float64, tvecs 3x1 float64 [mm], success) or ([], [], False) when fewer than 6 correspondences.
 
     How close to the reference's cv2.solvePnPRansac (:155-157), per crop: the RANSAC hypotheses are bit-identical to cv2's
-    (the minimal solver replays OpenCV's EPnP arithmetic), the winner, the iteration count and the final inlier set are
-    cv2's, and the pose agrees within 0.05 deg / 0.5 mm on 100 % of 768 measured crops at ignore_bit 0 and 99.6-99.8 % at
-    ignore_bit 2 / 4 (profiles/r2g_parity_*.json; median difference 0).  The rest: one inlier COUNT of a hypothesis off by a
-    point within 1e-3 px of the 2 px threshold (float32 scoring) can flip a near-tie between two hypotheses.  Pinned per
+    (the minimal solver replays OpenCV's EPnP arithmetic), near-ties of cv2's strictly-greater record rule are decided on
+    counts taken with cv2's own arithmetic, so the winner, the iteration count and the final inlier set are cv2's, and the
+    pose agrees within 0.05 deg / 0.5 mm on all 1536 measured crops at ignore_bit 0 / 2 / 4 (profiles/r2x_parity_*.json;
+    largest difference 2.4e-6 deg / 1.2e-8 mm: the final EPnP on the inliers sums in another order than cv2).  Pinned per
     crop by tests/test_gpu_ransac.py (winner / iterations / inliers equal cv2's) and tests/test_gpu_dropin.py (tolerance on
     every golden crop)."""
     if intrinsic_matrix is None:
