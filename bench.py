@@ -574,16 +574,22 @@ def main():
         pipe.submit_host(h_logits, bboxes, Ks, obj, out=outs[pipe.next_lane])
     pipe.wait_host()
     barrier()
-    e2e_steps = max(6, min(K_steps, 60))
-    t0 = time.perf_counter()
-    for i in range(e2e_steps):
-        pipe.submit_host(h_logits, bboxes, Ks, obj, out=outs[pipe.next_lane])   # waits for (and so reads) that lane's previous result
-    pipe.wait_host()
-    torch.cuda.synchronize()
-    dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-    e2e_s = float(dt.item())
+    # three timed blocks of >= 60 steps each, the MEDIAN block is reported: the path is bound by the host side of the PCIe link
+    # (pinned-memory reads), which other tenants of the box share -- single 20-step blocks (26 ms) ranged 33-49 k poses/s
+    e2e_steps = max(60, min(K_steps, 200))
+    blocks = []
+    for _ in range(3):
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(e2e_steps):
+            pipe.submit_host(h_logits, bboxes, Ks, obj, out=outs[pipe.next_lane])   # waits for (and so reads) that lane's previous result
+        pipe.wait_host()
+        torch.cuda.synchronize()
+        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        blocks.append(float(dt.item()))
+    e2e_s = sorted(blocks)[1]
     e2e_value = n_total * e2e_steps / e2e_s
     h2d = logits.nbytes + C * 4 * 8 + C * 9 * 8 + C * 4
     d2h = C * 12 * 8 + C * 4 + C * 4
@@ -720,7 +726,8 @@ def main():
                     "bound": "pcie", "h2d_gbs": h2d * e2e_steps / e2e_s / 1e9 * world, "h2d_gbs_per_gpu": h2d * e2e_steps / e2e_s / 1e9,
                     "path": "zp_pose_batch_host_async + zp_sync (C ABI, pinned host logits -> pinned host poses), %d lanes" % lanes,
                     "host_cpus": "%d CPUs local to the GPU (NVML affinity)" % len(numa_cpus) if numa_cpus else "unbound",
-                    "steps": e2e_steps, "bf16_logits": e2e_bf16},
+                    "steps": e2e_steps, "blocks_poses_per_s": [round(n_total * e2e_steps / b) for b in blocks],
+                    "timing": "median of three blocks of %d steps" % e2e_steps, "bf16_logits": e2e_bf16},
             "gpu_launches": launches,
             "clocks": sampler.summary(t_host0, t_host1),
             "kernel_us": {k: round(v * 1e3, 2) for k, v in k_ms.items()},

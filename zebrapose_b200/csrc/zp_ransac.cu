@@ -604,16 +604,17 @@ __device__ int zp_exact_count_cta(const float* __restrict__ cb, int cap, int n, 
                  p2 = make_float4(P[8], P[9], P[10], P[11]);
     const float *pu = cb, *pv = cb + cap, *pX = cb + 2 * (size_t)cap, *pY = cb + 3 * (size_t)cap, *pZ = cb + 4 * (size_t)cap;
     int c = 0;
-    for (int i0 = 0; i0 < n; i0 += 4 * RS_THREADS) {      // four points per thread and trip, their 20 loads up front
-        float fu[4], fv[4], fX[4], fY[4], fZ[4];
+    constexpr int PT = 4;                                  // points per thread and trip, their 20 loads up front (8: 170 registers, no faster)
+    for (int i0 = 0; i0 < n; i0 += PT * RS_THREADS) {
+        float fu[PT], fv[PT], fX[PT], fY[PT], fZ[PT];
 #pragma unroll
-        for (int q = 0; q < 4; q++) {
+        for (int q = 0; q < PT; q++) {
             const int i = i0 + RS_THREADS * q + tid;
             const bool ld = i < n;
             fu[q] = ld ? pu[i] : 0.f; fv[q] = ld ? pv[i] : 0.f; fX[q] = ld ? pX[i] : 0.f; fY[q] = ld ? pY[i] : 0.f; fZ[q] = ld ? pZ[i] : 0.f;
         }
 #pragma unroll
-        for (int q = 0; q < 4; q++) {
+        for (int q = 0; q < PT; q++) {
             if (i0 + RS_THREADS * q + tid >= n) continue;
             const float d = zp_inlier_d(p0, p1, p2, fu[q] * inv_thr, fv[q] * inv_thr, fX[q], fY[q], fZ[q]);
             bool in = __float_as_int(d) < 0;
