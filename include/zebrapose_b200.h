@@ -222,7 +222,9 @@ int zp_sync(zp_ctx* ctx);
 
 /* Measurement aid: while on, every launch of the path's main kernels is bracketed by two CUDA events recorded on the
  * launching stream directly around it (the call then waits for that kernel), and the elapsed times accumulate per kernel
- * name ("zp_decode_stream_kernel", "zp_samples_kernel", "zp_minimal_kernel", "zp_score_kernel", "zp_final_kernel",
+ * name ("zp_decode_stream_kernel", "zp_samples_kernel", "zp_cvs_prep_kernel" / "_null_" / "_cand_" / "_pick_" (exact solver) or
+ * "zp_minimal_kernel" (fast solver), "zp_score_kernel", "zp_rs_replay_kernel", "zp_fin_moments_kernel" / "_solve_" / "_errors_"
+ * (split final solve) or "zp_final_kernel" (one-kernel forms),
  * "zp_head_codes_kernel", "zp_decode_emit_kernel", "zp_adi_kernel", "zp_crop_kernel").  Switching it on clears the sums.
  * bench.py's roofline figures are algorithmic bytes (flops) per launch / these durations. */
 int zp_set_kernel_timing(zp_ctx* ctx, int on);

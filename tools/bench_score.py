@@ -5,6 +5,7 @@ import numpy as np, torch
 import zebrapose_b200 as zp
 argv = sys.argv[1:]; sys.argv = ['x']
 import bench
+print('ZP_SCORE_PER_SM', os.environ.get('ZP_SCORE_PER_SM'))
 for C in [int(x) for x in argv] or [64, 1024]:
     logits, bboxes, Ks, obj, tables, crops = bench.make_workload(C, 1002)
     eng = zp.Engine(0)
@@ -18,7 +19,7 @@ for C in [int(x) for x in argv] or [64, 1024]:
     M = int(counts.clamp(max=cap).sum())
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     peak = max(eng.fp32_peak_tflops(), eng.fp32_peak_tflops(packed=True))
-    for g, hc in ((1, -1), (1, 75), (1, 50), (1, 30), (0, 0)):
+    for g, hc in ((1, -1), (1, 100), (1, 90), (1, 75), (1, 60), (1, 50), (1, 30), (0, 0)):
         eng.set_score_groups(g, hc)
         for _ in range(3): eng.score(corr, counts, K, hyp, 2.0)
         tot = 0.0

@@ -8,15 +8,17 @@
 //   zp_minimal_kernel   the FAST solver (zp_set_solver): a quad per hypothesis, float64 EPnP with a bisection / inverse-
 //                       iteration null space.  The default solver is the exact replay of OpenCV's arithmetic, zp_cvsolve.cu.
 //   zp_score_kernel     FP32-FMA bound: every correspondence x every hypothesis.  Correspondence tiles (SoA planes) are
-//                       staged into shared memory with 1-D TMA bulk copies (cp.async.bulk + mbarrier, double buffered),
+//                       staged into shared memory with 1-D TMA bulk copies (cp.async.bulk + mbarrier) and kept in registers,
 //                       hypotheses K[R|t] live in shared memory and are broadcast; the test is division free:
 //                       (x - u z)^2 + (y - v z)^2 <= thr^2 z^2.  Counts: per-thread -> warp REDUX -> shared -> global.
 //   zp_rs_*_kernel      cv2's loop state per crop (niters, maxGood, best) advanced wave by wave: "strictly greater" update +
-//                       RANSACUpdateNumIters; crops that have reached their stopping iteration skip the later waves
-//   zp_final_cl_kernel  EPnP on all inliers of the winner, a 4-CTA thread-block cluster per crop (or one CTA walking the same
-//                       four partitions): inlier set (doubtful points by cv2's own arithmetic), reductions of the 52 EPnP
-//                       sums through distributed shared memory, 16-lane null space, the three beta candidates on three
-//                       lanes, optional Gauss-Newton polish of the reprojection error
+//                       RANSACUpdateNumIters; near-ties decided on exact re-counts (cv2's arithmetic); crops that have reached
+//                       their stopping iteration skip the later waves
+//   zp_final_cl_kernel  the one-kernel final solve (zp_set_final_form 1 / 4, and the Gauss-Newton polish): EPnP on all inliers
+//                       of the winner, a 4-CTA thread-block cluster per crop (or one CTA walking the same four partitions):
+//                       inlier set (doubtful points by cv2's own arithmetic), reductions of the 52 EPnP sums through
+//                       distributed shared memory, 16-lane null space, the three beta candidates on three lanes.  The
+//                       default final solve is the split form, zp_finsplit.cu.
 //
 // Algorithmic FP32 work of scoring: 27 flop per (correspondence, hypothesis).
 #include <climits>
