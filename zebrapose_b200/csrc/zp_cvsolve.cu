@@ -24,7 +24,7 @@ constexpr int CVA_THREADS = 64;                // stage A: private data 117 doub
 constexpr int CVA_PRIV = 24 + 16 + 32 + 12 + 33;
 constexpr int CVB_HPW = 5;                     // stage B: hypotheses per warp (5 x 6 lanes; lanes 30 and 31 idle)
 constexpr int CVB_WARPS = 2;
-constexpr int CVB_HB = 236;                    // doubles per hypothesis: A 12 x 14 = 168 | W 12 | V4 48 (first: al 32 | us 16) | flags 2; even: 16-byte aligned rows
+constexpr int CVB_HB = 230;                    // doubles per hypothesis: A 12 x 14 = 168 | W 12 | V4 48 (first: al 32 | us 16) | flags 2; even: 16-byte aligned rows
 constexpr int CVC_THREADS = 64;                // stage C: 60 doubles of scratch per thread
 constexpr int CVC_PRIV = 60;
 
