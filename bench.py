@@ -118,6 +118,13 @@ def bind_to_gpu_numa(gpu):
         return None, None
 
 
+def ref_kind():
+    """ "reference": the reference's own functions, imported in place where /root/reference exists (the build container);
+    "port": their bit-identical restatement in oracle/reference_path.py (the GPU box, where the reference tree is absent) """
+    from oracle import reference_path
+    return reference_path.kind()
+
+
 def cpu_baseline(logits, bboxes, Ks, obj, tables, n_sample, repeats=1):
     """reference CPU path on all host cores, bounded sample"""
     from oracle.reference_path import ReferencePool
@@ -158,7 +165,7 @@ def run_reference(args, rank, world):
             "config": {"workload": WORKLOAD % args.crops, "crops_per_gpu": args.crops,
                        "arm": "reference CPU path (host threshold of all logits, per-pixel dict loop, cv2.solvePnPRansac EPnP), "
                               "one step = the same batch on all host cores"},
-            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": ref_kind(),
                              "sample": "%d crops per step, fork pool of %d workers, cv2.setNumThreads(1)" % (args.crops, cores)},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
@@ -703,7 +710,7 @@ def main():
         if not args.no_cpu_baseline:
             n_sample = max(256, 128 * (os.cpu_count() or 1))
             v, cores, secs, ref_poses = cpu_baseline(logits, bboxes, Ks, obj, tables, n_sample)
-            cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+            cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": ref_kind(),
                    "sample": "%d crops of the same workload, fork pool of %d workers (cv2.setNumThreads(1)), %.1f s" % (n_sample, cores, secs)}
             try:
                 cpu["agreement"] = agreement(eng, d_logits, d_bbox, d_K, d_obj, crops, tables, ref_poses, kw)

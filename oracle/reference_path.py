@@ -1,5 +1,8 @@
 """The reference's CPU path for one crop, end to end, as test.py:250-273 + CNN_output_to_pose.py:100-160 run it
-(test infrastructure / timed CPU baseline; restated, not copied -- the reference sources cannot travel to the GPU box).
+(test infrastructure / timed CPU baseline).  Two forms with identical results (tests/test_oracle_vs_reference_inplace.py):
+`kind() == "reference"` -- the reference's OWN functions imported in place from /root/reference (oracle/ref_inplace.py; only
+where that tree exists, i.e. the build container: nothing is copied, the reference sources cannot travel to the GPU box);
+`"port"` -- the restatement below, which is what runs on the GPU box.
 
 Step by step: sigmoid + 0.5 threshold of ALL logits into float64 {0,1} arrays (common_ops.py:5-19), NCHW->NHWC
 transposes and uint8 mask (test.py:254-257), code -> class id in float64 (class_id_encoder_decoder.py:17-28),
@@ -11,7 +14,26 @@ import numpy as np
 import cv2
 import torch
 
-from . import decode
+from . import decode, ref_inplace
+
+
+def kind():
+    """ "reference" where /root/reference exists (its own functions are imported in place), else "port" """
+    return "reference" if ref_inplace.modules() else "port"
+
+
+def reference_pose_from_logits_ref(logits, bbox, K, dict_float_keys, ignore_bit=0, S=None):
+    """the same call sequence as test.py:250-273 through the reference's own functions (imported in place)"""
+    co, cnn, _ = ref_inplace.modules()
+    lt = torch.from_numpy(np.ascontiguousarray(logits))[None]
+    nb = lt.shape[1] - 1
+    pred_masks = co.from_output_to_class_mask(lt[:, :1])
+    pred_code_images = co.from_output_to_class_binary_code(lt[:, 1:], "BCE", divided_num_each_interation=2, binary_code_length=nb)
+    pred_code_images = pred_code_images.transpose(0, 2, 3, 1)
+    pred_masks = pred_masks.transpose(0, 2, 3, 1)
+    pred_masks = pred_masks.squeeze(axis=-1).astype('uint8')
+    code = pred_code_images[0][:, :, :-ignore_bit] if ignore_bit else pred_code_images[0]
+    return cnn.CNN_outputs_to_object_pose(pred_masks[0], code, bbox, S or logits.shape[-1], 2, dict_float_keys, intrinsic_matrix=K)
 
 
 def reference_pose_from_logits(logits, bbox, K, dict_float_keys, ignore_bit=0, S=None):
@@ -51,11 +73,12 @@ _G = {}
 def _init(logits, bboxes, Ks, obj, dicts):
     cv2.setNumThreads(1)
     torch.set_num_threads(1)
-    _G.update(logits=logits, bboxes=bboxes, Ks=Ks, obj=obj, dicts=dicts)
+    _G.update(logits=logits, bboxes=bboxes, Ks=Ks, obj=obj, dicts=dicts, ref=kind() == "reference")
 
 
 def _work(i):
-    R, t, ok = reference_pose_from_logits(_G["logits"][i], _G["bboxes"][i], _G["Ks"][i], _G["dicts"][_G["obj"][i]])
+    fn = reference_pose_from_logits_ref if _G.get("ref") else reference_pose_from_logits
+    R, t, ok = fn(_G["logits"][i], _G["bboxes"][i], _G["Ks"][i], _G["dicts"][_G["obj"][i]])
     if not ok:
         return np.zeros(12)
     return np.concatenate([np.asarray(R).ravel(), np.asarray(t).ravel()])
