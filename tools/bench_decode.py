@@ -15,7 +15,7 @@ for C in [int(x) for x in argv] or [64, 1024]:
         flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
         flush2 = torch.zeros(64 << 20, dtype=torch.float32, device="cuda")
         clean = len(os.environ.get("ZP_CLEAN_FLUSH", "")) > 0
-        for path in (0, 6, 3, 4, 102, 104):
+        for path in (0,) if os.environ.get('ZP_DECODE_ONLY_DEFAULT') else (0, 6, 3, 4, 102, 104):
             eng.set_decode_path(path)
             for _ in range(3): corr, counts = eng.decode(lg, bb, oi)
             tot = 0.0
