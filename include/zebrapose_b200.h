@@ -123,7 +123,8 @@ int zp_set_waves(zp_ctx* ctx, int n, const int32_t* sizes);
  * (default) re-counts, with cv2's own double -> float32 arithmetic for the points the FP32 scoring predicate puts within
  * 1e-3 px of the threshold, every hypothesis that comes within 3 inliers of the running maximum (and, once, the record
  * holder), so those decisions are taken on cv2's counts; on = 0 lets the FP32 counts decide everything (they can differ by
- * one for such a point, the slack north_star allows). */
+ * one for such a point, the slack north_star allows); on = 2 (test aid) re-counts every near-tie at once instead of parking
+ * the early low-count ones -- the rule that parking must reproduce. */
 int zp_set_exact_ties(zp_ctx* ctx, int on);
 
 /* Shape of the final solve on the winner's inliers: 2 = split into three kernels (point moments over 4 CTAs per crop ->

@@ -202,6 +202,33 @@ def test_near_ties_are_decided_on_exact_counts(eng, batch):
     assert np.array_equal(r["poses"].cpu().numpy(), a["poses"]) and np.array_equal(r["best_idx"].cpu().numpy(), a["best_idx"])
 
 
+@pytest.mark.parametrize("outlier,bitflip,seed", [(0.3, 0.02, 11), (0.6, 0.05, 12), (0.8, 0.0, 13), (0.1, 0.0, 14)])
+def test_parking_reproduces_immediate_recounts(eng, outlier, bitflip, seed):
+    """Parking the early low-count near-ties (decide on FP32 counts, forget them at the next clear record, replay with
+    re-counts only if they still matter) must give exactly what re-counting every near-tie at once gives: same winner,
+    iteration count, inlier count and pose on every crop, at inlier ratios from 20 % to 90 %, for one wave and for short waves
+    (parked state carried from wave to wave)."""
+    tab, nrm, _ = synth.make_dict(16, seed=3, radius=51.0, missing_frac=0.0)
+    eng.upload_dict(0, tab, n_bits=16, ignore_bit=0)
+    crops = [synth.make_crop(tab, nrm, seed * 65536 + i, outlier=outlier, bitflip=bitflip) for i in range(24)]
+    logits = np.stack([synth.crop_to_logits(c) for c in crops])
+    corr, counts = eng.decode(torch.from_numpy(logits).cuda(), np.stack([c["bbox"] for c in crops]))
+    Ks = np.stack([c["K"] for c in crops])
+    res = {}
+    try:
+        for mode in (1, 2):
+            for plan in ([150], [5, 9, 16]):
+                eng.set_exact_ties(mode); eng.set_waves(plan)
+                r = eng.ransac(corr, counts, Ks, return_details="state")
+                res[mode, len(plan)] = [r[k].cpu().numpy() for k in ("poses", "n_inliers", "status", "best_idx", "iters_run")]
+    finally:
+        eng.set_exact_ties(True); eng.set_waves(None)
+    ref = res[2, 1]
+    assert (ref[2] == 0).any()
+    for key, cur in res.items():
+        assert all(np.array_equal(a, b) for a, b in zip(ref, cur)), key
+
+
 def test_waves_do_not_change_the_result(eng, batch):
     """cv2 never consults a hypothesis at or past its stopping iteration, so solving + scoring the hypotheses in waves and
     skipping finished crops must give bit-identical poses, winners and iteration counts for any wave plan"""

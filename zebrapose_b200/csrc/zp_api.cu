@@ -162,7 +162,8 @@ int zp_set_solver(zp_ctx* ctx, int solver) {
 
 int zp_set_exact_ties(zp_ctx* ctx, int on) {
     if (!ctx) return -1;
-    ctx->rs_no_recount = on ? 0 : 1;
+    if (on < 0 || on > 2) ZP_FAIL(ctx, -1, "zp_set_exact_ties: 0 (off), 1 (on) or 2 (on, no parking)");
+    ctx->rs_no_recount = on == 1 ? 0 : on == 0 ? 1 : 2;
     return 0;
 }
 

@@ -94,7 +94,7 @@ struct zp_ctx {
     bool cvs_attr_set = false, min_attr_set = false, fin_attr_set = false, fin_form_set = false;
     int min_force = 0, cvb_minb = 0, cvc_minb = 0, fin_force = 0;
     int score_per_sm[3] = {0, 0, 0};
-    int rs_no_recount = 0;                   // 1: the adaptive-stop replay decides near-ties on the FP32 counts (round 2's behaviour; tests)
+    int rs_no_recount = 0;                   // 1: the adaptive-stop replay decides near-ties on the FP32 counts (tests); 2: exact re-counts without parking (tests)
 };
 
 #define ZP_FAIL(ctx, code, ...)                                  \

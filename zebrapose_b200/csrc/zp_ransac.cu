@@ -637,6 +637,7 @@ __device__ int zp_exact_count_cta(const float* __restrict__ cb, int cap, int n, 
 
 struct RsExact {            // inputs of the near-tie recount (corr == nullptr: FP32 counts decide everything)
     const float* corr; const double* K; const double* hyp_poses; float inv_thr, thr2;
+    int park;               // 0: every near-tie is re-counted at once (test aid: the rule parking must reproduce)
     int32_t* tie;           // [B][4] per crop: {flags (1: maxGood is an exact count, 2: so is the parked state's), first parked iteration or -1, parked best, parked maxGood}
 };
 
@@ -751,7 +752,7 @@ zp_rs_replay_kernel(const int32_t* __restrict__ counts, int cap, const int32_t* 
     bool stop = false;
     int cur = h0;
     for (;;) {
-        const int at = zp_rs_walk(cur, h1, s, stop, true, pend_from, pend, hi, n, m, H, conf, recount, cb, cap, Kb, hp_crop, ex, lane, s_part);
+        const int at = zp_rs_walk(cur, h1, s, stop, ex.park != 0, pend_from, pend, hi, n, m, H, conf, recount, cb, cap, Kb, hp_crop, ex, lane, s_part);
         // parked near-ties must be settled before a decision that needs exact counts, and before this crop's last wave ends
         const bool closing = at < 0 && (stop || h1 >= H || h1 >= s.niters);
         if (pend_from < 0 || (at < 0 && !closing)) break;
@@ -1235,7 +1236,8 @@ int zp_launch_rs_replay(zp_ctx* ctx, const int32_t* counts, int cap, const int32
                         int m, double conf, int select_mode, int32_t* rs, int32_t* crop_done, const float* corr, const double* K,
                         const double* hyp_poses, float thr_px, cudaStream_t st) {
     RsExact ex;
-    ex.corr = ctx->rs_no_recount ? nullptr : corr; ex.K = K; ex.hyp_poses = hyp_poses;
+    ex.corr = ctx->rs_no_recount == 1 ? nullptr : corr; ex.K = K; ex.hyp_poses = hyp_poses;
+    ex.park = ctx->rs_no_recount == 2 ? 0 : 1;
     ex.inv_thr = 1.0f / thr_px; ex.thr2 = (float)((double)thr_px * (double)thr_px);
     ex.tie = crop_done + B;
     ZP_TIME_BEGIN(ctx, st);

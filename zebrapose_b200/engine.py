@@ -94,8 +94,9 @@ class Engine:
         self.ctx.check(self.lib.zp_set_waves(self.ctx.handle, int(arr.size), arr.ctypes.data_as(C.c_void_p)), "zp_set_waves")
 
     def set_exact_ties(self, on=True):
-        """near-ties of cv2's record rule decided on exact (cv2-arithmetic) inlier counts (default) or on the FP32 counts"""
-        self.ctx.check(self.lib.zp_set_exact_ties(self.ctx.handle, int(bool(on))), "zp_set_exact_ties")
+        """near-ties of cv2's record rule decided on exact (cv2-arithmetic) inlier counts (default) or on the FP32 counts;
+        on=2 (test aid): exact re-counts without parking the early low-count near-ties"""
+        self.ctx.check(self.lib.zp_set_exact_ties(self.ctx.handle, int(on)), "zp_set_exact_ties")
 
     def set_final_form(self, form=0):
         """final solve split into three kernels (2; the default 0 for final="epnp"), as a 4-CTA cluster per crop (4) or one CTA
