@@ -1,5 +1,7 @@
 // Host build of the device EPnP core (zebrapose_b200/csrc/zp_epnp.cuh) so the CPU test-suite can check the very code
-// the kernels run against cv2 / the oracle.  stdin: n, f32flag, K(9), then n rows "X Y Z u v"; stdout: 12 doubles.
+// the kernels run against cv2 / the oracle.  stdin: n, mode, K(9), then n rows "X Y Z u v"; stdout: 12 doubles.
+// mode 1: the 52 EPnP sums accumulated point by point (zp_final_cl_kernel); mode 2: from 40 raw moments relative to the
+// first point and their contractions (zp_finsplit.cu: zp_moment_add / zp_moment_frame / zp_moment_sum).
 #include <cstdio>
 #include <vector>
 #include "../../zebrapose_b200/csrc/zp_epnp.cuh"
@@ -25,17 +27,32 @@ int main() {
             for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) C[3 * r + c] += d[r] * d[c];
         }
         ZpControl cp;
-        zp_control_points(c0, C, (double)n, cp);
         ZpSums s;
-        for (int q = 0; q < 10; q++) { s.s0[q] = s.sx[q] = s.sy[q] = s.sr[q] = 0; }
-        for (int q = 0; q < 12; q++) s.w[q] = 0;
-        s.n = n;
         double af[4];
-        for (int i = 0; i < n; i++) {
-            double a[4];
-            zp_alphas(cp, X[i], Y[i], Z[i], a);
-            if (i == 0) for (int e = 0; e < 4; e++) af[e] = a[e];
-            zp_accumulate(s, a, cam.uc - x[i], cam.vc - y[i], X[i] - c0[0], Y[i] - c0[1], Z[i] - c0[2]);
+        if (f32 == 2) {
+            const double g[3] = {X[0], Y[0], Z[0]};
+            double T[40], A[16], c0p[3];
+            for (int q = 0; q < 40; q++) T[q] = 0;
+            for (int i = 0; i < n; i++)
+                zp_moment_add(T, T + 10, T + 20, T + 30, X[i] - g[0], Y[i] - g[1], Z[i] - g[2], cam.uc - x[i], cam.vc - y[i]);
+            T[9] = n;
+            zp_moment_frame(T, (double)n, cp, A, c0p);
+            double* S = (double*)&s;
+            for (int o = 0; o < 52; o++) S[o] = zp_moment_sum(o, T, A, c0p);
+            s.n = n;
+            zp_alphas(cp, 0.0, 0.0, 0.0, af);                 // the first point is the pivot
+            for (int e = 0; e < 3; e++) c0[e] = c0p[e] + g[e];   // t = pc0 - R c0 wants the world centroid
+        } else {
+            zp_control_points(c0, C, (double)n, cp);
+            for (int q = 0; q < 10; q++) { s.s0[q] = s.sx[q] = s.sy[q] = s.sr[q] = 0; }
+            for (int q = 0; q < 12; q++) s.w[q] = 0;
+            s.n = n;
+            for (int i = 0; i < n; i++) {
+                double a[4];
+                zp_alphas(cp, X[i], Y[i], Z[i], a);
+                if (i == 0) for (int e = 0; e < 4; e++) af[e] = a[e];
+                zp_accumulate(s, a, cam.uc - x[i], cam.vc - y[i], X[i] - c0[0], Y[i] - c0[1], Z[i] - c0[2]);
+            }
         }
         double zbuf[ZP_SYM_DOUBLES], dd[12], ee[12], at[48];
         zp_nullspace4<1>(ZpSym12{zbuf}, dd, ee, s.s0, cam, 0, 0u, at);

@@ -310,6 +310,67 @@ ZP_HD __forceinline__ void zp_accumulate(ZpSums& s, const double a[4], double x,
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// The same 52 sums from RAW MOMENTS (the split final solve, zp_finsplit.cu).  The barycentric coordinates are affine in the
+// point, alpha = A [X Y Z 1]^T, so with T_f = sum_i f_i P_i P_i^T (P = [X Y Z 1], f in {1, x, y, x^2 + y^2}; 4 x 10 packed
+// entries, a <= b: 00 01 02 03 11 12 13 22 23 33) the sums are contractions: sum a_j a_k f = (A T_f A^T)(j, k) and
+// sum a_j (X_c - c0_c) = A_j . (T_1[:, c] - c0_c T_1[:, 3]).  One pass over the points, independent of the control points.
+// Points are taken relative to a pivot (a point of the object) so that T_1 - n c c^T cancels at the object's own scale.
+// ------------------------------------------------------------------------------------------------------------------
+ZP_HD __forceinline__ int zp_pk4(int a, int b) {          // packed index of the symmetric 4x4, any order
+    const int lo = a < b ? a : b, hi = a < b ? b : a;
+    return 4 * lo - (lo * (lo - 1)) / 2 + (hi - lo);
+}
+
+// one point into the moments: T1[9] (entry 33 = the count, kept by the caller), Tx / Ty / Tr [10]
+ZP_HD __forceinline__ void zp_moment_add(double* T1, double* Tx, double* Ty, double* Tr, double X, double Y, double Z,
+                                         double x, double y) {
+    const double r = fma(x, x, y * y);
+    const double m[10] = {X * X, X * Y, X * Z, X, Y * Y, Y * Z, Y, Z * Z, Z, 1.0};
+#pragma unroll
+    for (int q = 0; q < 9; q++) T1[q] += m[q];
+#pragma unroll
+    for (int q = 0; q < 10; q++) {
+        Tx[q] = fma(m[q], x, Tx[q]); Ty[q] = fma(m[q], y, Ty[q]); Tr[q] = fma(m[q], r, Tr[q]);
+    }
+}
+
+// centroid c0 (relative to the pivot), control points and the affine map A [4][4] from T (T[9] = the point count n)
+ZP_HD inline void zp_moment_frame(const double* T, double n, ZpControl& cp, double* A, double* c0) {
+    c0[0] = T[3] / n; c0[1] = T[6] / n; c0[2] = T[8] / n;
+    double C[9];
+    for (int r = 0; r < 3; r++)
+        for (int c = 0; c < 3; c++) C[3 * r + c] = T[zp_pk4(r, c)] - c0[r] * T[zp_pk4(c, 3)];
+    C[3] = C[1]; C[6] = C[2]; C[7] = C[5];
+    zp_control_points(c0, C, n, cp);
+    for (int j = 0; j < 3; j++) {            // rows 1..3 from the control basis, row 0 = 1 - the others
+        double off = 0;
+        for (int k = 0; k < 3; k++) { A[4 * (j + 1) + k] = cp.cci[3 * j + k]; off += cp.cci[3 * j + k] * c0[k]; }
+        A[4 * (j + 1) + 3] = -off;
+    }
+    for (int k = 0; k < 4; k++) A[k] = (k == 3 ? 1.0 : 0.0) - A[4 + k] - A[8 + k] - A[12 + k];
+}
+
+// sum number o of ZpSums (s0[10] | sx[10] | sy[10] | sr[10] | w[12]) from the moments T[40], A and c0
+ZP_HD inline double zp_moment_sum(int o, const double* T, const double* A, const double* c0) {
+    double val = 0;
+    if (o < 40) {                                  // (A T_f A^T)(j, k)
+        const int f = o / 10, q = o - 10 * f;
+        const int j = q < 4 ? 0 : q < 7 ? 1 : q < 9 ? 2 : 3;
+        const int k = q - (j == 0 ? 0 : j == 1 ? 4 : j == 2 ? 7 : 9) + j;
+        const double* Tf = T + 10 * f;
+        for (int aa = 0; aa < 4; aa++) {
+            double row = 0;                        // (T_f A_k^T)[aa]
+            for (int bb = 0; bb < 4; bb++) row = fma(Tf[zp_pk4(aa, bb)], A[4 * k + bb], row);
+            val = fma(A[4 * j + aa], row, val);
+        }
+    } else {                                       // W_j[c]
+        const int e = o - 40, j = e / 3, c = e - 3 * j;
+        for (int aa = 0; aa < 4; aa++) val = fma(A[4 * j + aa], T[zp_pk4(aa, c)] - c0[c] * T[zp_pk4(aa, 3)], val);
+    }
+    return val;
+}
+
 // element (r, c) of M^T M; rows of M (epnp::fill_M): [a_j fu, 0, a_j (uc - u)] and [0, a_j fv, a_j (vc - v)]
 ZP_HD __forceinline__ double zp_mtm(const ZpSums& s, const ZpCam& cam, int r, int c) {
     int j = r / 3, rr = r - 3 * j, k = c / 3, cc = c - 3 * k;

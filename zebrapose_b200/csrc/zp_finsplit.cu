@@ -46,11 +46,6 @@ struct FsWs {
 
 __device__ __forceinline__ int fs_chunk(int n) { return ((n + FS_LISTS * 32 - 1) / (FS_LISTS * 32)) * 32; }
 
-__device__ __forceinline__ int fs_pk(int a, int b) {          // packed index of the symmetric 4x4, any order
-    const int lo = a < b ? a : b, hi = a < b ? b : a;
-    return 4 * lo - (lo * (lo - 1)) / 2 + (hi - lo);
-}
-
 __global__ void __launch_bounds__(FS_THREADS, 2) zp_fin_moments_kernel(FinalArgs a, FsWs w) {
     const int b = blockIdx.x / FS_SEG, rank = blockIdx.x % FS_SEG;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -154,16 +149,7 @@ __global__ void __launch_bounds__(FS_THREADS, 2) zp_fin_moments_kernel(FinalArgs
             const int i2 = in2 ? seg[k2] : 0;
             const float gX = in2 ? pX[i2] : 0.f, gY = in2 ? pY[i2] : 0.f, gZ = in2 ? pZ[i2] : 0.f, gu = in2 ? pu[i2] : 0.f, gv = in2 ? pv[i2] : 0.f;
             {
-                const double X = (double)fX - g0, Y = (double)fY - g1, Z = (double)fZ - g2;
-                const double x = uc - (double)fu, y = vc - (double)fv;
-                const double r = fma(x, x, y * y);
-                const double m[10] = {X * X, X * Y, X * Z, X, Y * Y, Y * Z, Y, Z * Z, Z, 1.0};
-#pragma unroll
-                for (int q = 0; q < 9; q++) T1[q] += m[q];
-#pragma unroll
-                for (int q = 0; q < 10; q++) {
-                    Tx[q] = fma(m[q], x, Tx[q]); Ty[q] = fma(m[q], y, Ty[q]); Tr[q] = fma(m[q], r, Tr[q]);
-                }
+                zp_moment_add(T1, Tx, Ty, Tr, (double)fX - g0, (double)fY - g1, (double)fZ - g2, uc - (double)fu, vc - (double)fv);
             }
             k = k2; in = in2; fX = gX; fY = gY; fZ = gZ; fu = gu; fv = gv;
         }
@@ -239,47 +225,17 @@ __global__ void __launch_bounds__(32) zp_fin_solve_kernel(FinalArgs a, FsWs w) {
     const double* Kb = a.K + 9 * (size_t)b;
     const ZpCam cam{Kb[0], Kb[4], Kb[2], Kb[5]};
     if (lane == 0) {
-        const double n = (double)ni;
-        const double c0[3] = {s_T[3] / n, s_T[6] / n, s_T[8] / n};        // centroid (relative to the pivot)
-        double C[9];
-        for (int r = 0; r < 3; r++)
-            for (int c = 0; c < 3; c++) C[3 * r + c] = s_T[fs_pk(r, c)] - c0[r] * s_T[fs_pk(c, 3)];
-        C[3] = C[1]; C[6] = C[2]; C[7] = C[5];
-        zp_control_points(c0, C, n, s_cp);
-        // alpha = A [X Y Z 1]^T: rows 1..3 from the control basis, row 0 = 1 - the others
-        double A[16];
-        for (int j = 0; j < 3; j++) {
-            double off = 0;
-            for (int k = 0; k < 3; k++) { A[4 * (j + 1) + k] = s_cp.cci[3 * j + k]; off += s_cp.cci[3 * j + k] * c0[k]; }
-            A[4 * (j + 1) + 3] = -off;
-        }
-        for (int k = 0; k < 4; k++) A[k] = (k == 3 ? 1.0 : 0.0) - A[4 + k] - A[8 + k] - A[12 + k];
+        double A[16], c0[3];
+        zp_moment_frame(s_T, (double)ni, s_cp, A, c0);
         for (int k = 0; k < 16; k++) s_A[k] = A[k];
         for (int k = 0; k < 3; k++) s_c0[k] = c0[k];
-        s_sums.n = n;
+        s_sums.n = (double)ni;
     }
     __syncwarp();
     if (stamp) w.dbg[10] = clock64();
     {
         double* S = (double*)&s_sums;                      // s0[10] | sx[10] | sy[10] | sr[10] | w[12]
-        for (int o = lane; o < 52; o += 32) {
-            double val = 0;
-            if (o < 40) {                                  // (A T_f A^T)(j, k)
-                const int f = o / 10, q = o - 10 * f;
-                const int j = q < 4 ? 0 : q < 7 ? 1 : q < 9 ? 2 : 3;
-                const int k = q - (j == 0 ? 0 : j == 1 ? 4 : j == 2 ? 7 : 9) + j;
-                const double* Tf = s_T + 10 * f;
-                for (int aa = 0; aa < 4; aa++) {
-                    double row = 0;                        // (T_f A_k^T)[aa]
-                    for (int bb = 0; bb < 4; bb++) row = fma(Tf[fs_pk(aa, bb)], s_A[4 * k + bb], row);
-                    val = fma(s_A[4 * j + aa], row, val);
-                }
-            } else {                                       // W_j[c] = sum_i alpha_ij (X_c - c0_c) = A_j . (T_1[:, c] - c0_c T_1[:, 3])
-                const int e = o - 40, j = e / 3, c = e - 3 * j;
-                for (int aa = 0; aa < 4; aa++) val = fma(s_A[4 * j + aa], s_T[fs_pk(aa, c)] - s_c0[c] * s_T[fs_pk(aa, 3)], val);
-            }
-            S[o] = val;
-        }
+        for (int o = lane; o < 52; o += 32) S[o] = zp_moment_sum(o, s_T, s_A, s_c0);
     }
     __syncwarp();
     if (stamp) w.dbg[11] = clock64();
