@@ -198,8 +198,11 @@ int zp_pose_batch_host(zp_ctx* ctx, const void* h_logits, int dtype, int B, int 
  * per CTA (100 = automatic again).  All produce identical output; DESIGN.md section 4 has the measured comparison. */
 int zp_set_decode_path(zp_ctx* ctx, int path);
 
-/* Profiling aid: when set (device pointer to 4 uint64 per decode CTA, or NULL to switch off), the fused decode kernel
- * stores %globaltimer stamps per CTA: [0] start, [1] planes read + ranks known, [3] end (tools/dbg_decode_ctas.py). */
+/* Profiling aid: when set (device pointer to 4 uint64 per decode CTA and at least 16 uint64, or NULL to switch off), the fused
+ * decode kernel stores %globaltimer stamps per CTA: [0] start, [1] planes read + ranks known, [3] end
+ * (tools/dbg_decode_ctas.py); the exact solver's null-space kernel stores clock64 stamps of its first warp in [0..5]
+ * (tools/dbg_null_phases.py) and the split final solve's solver kernel those of crop 0 in [8..13]
+ * (tools/dbg_finsolve_phases.py). */
 int zp_debug_buffer(zp_ctx* ctx, void* dev_u64);
 
 /* Tuning aid for zp_score / zp_ransac: `groups` = warp-groups (128 threads each) per scoring CTA that split the
