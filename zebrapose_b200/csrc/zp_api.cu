@@ -35,6 +35,7 @@ int zp_ws_reserve(zp_ctx* ctx, size_t bytes) {
     if (bytes <= ctx->ws_bytes) return 0;
     // growing the workspace must not race with work still using the old one
     ZP_CUDA(ctx, cudaDeviceSynchronize());
+    zp_drop_graphs(ctx);
     if (ctx->ws) cudaFree(ctx->ws);
     ctx->ws = nullptr; ctx->ws_bytes = 0;
     size_t want = bytes + bytes / 4 + 4096;
@@ -494,8 +495,7 @@ int zp_ransac(zp_ctx* ctx, const float* corr, int cap, const int32_t* counts, co
 static int gws_reserve(zp_ctx* ctx, size_t bytes) {
     if (bytes <= ctx->gws_bytes) return 0;
     ZP_CUDA(ctx, cudaDeviceSynchronize());
-    for (auto& g : ctx->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);      // they point into the old buffer
-    ctx->graphs.clear();
+    zp_drop_graphs(ctx);                                                        // they point into the old buffer
     if (ctx->gws) cudaFree(ctx->gws);
     ctx->gws = nullptr; ctx->gws_bytes = 0;
     ZP_CUDA(ctx, cudaMalloc(&ctx->gws, bytes + bytes / 4 + 4096));

@@ -146,6 +146,13 @@ struct FinalArgs {
     double* records;                             // nullable [B,14]: pose | n_inliers | status as doubles (the multi-GPU gather record)
 };
 
+// Captured graphs (zp_pose_batch_device) hold raw pointers into the ctx's device workspaces: whenever one of those is
+// re-allocated -- always in an eager call, after a cudaDeviceSynchronize -- the graphs are dropped and re-captured on next use.
+inline void zp_drop_graphs(zp_ctx* ctx) {
+    for (auto& g : ctx->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
+    ctx->graphs.clear();
+}
+
 int zp_ws_reserve(zp_ctx* ctx, size_t bytes);
 
 // table slot of crop b: ids outside [0, ZP_MAX_OBJECTS) go to the extra all-non-existing slot

@@ -196,6 +196,7 @@ int zp_launch_minimal_cv(zp_ctx* ctx, const float* corr, int cap, const int32_t*
     const size_t need = (size_t)CVH_DOUBLES * nhp * sizeof(double);
     if (need > ctx->cvws_bytes) {       // growing must not race with work still using the old buffer
         ZP_CUDA(ctx, cudaDeviceSynchronize());
+        zp_drop_graphs(ctx);
         if (ctx->cvws) cudaFree(ctx->cvws);
         ctx->cvws = nullptr; ctx->cvws_bytes = 0;
         ZP_CUDA(ctx, cudaMalloc(&ctx->cvws, need + need / 8));

@@ -608,6 +608,7 @@ __global__ void __launch_bounds__(DEC_THREADS, 3) zp_decode_emit_kernel(DecodeAr
 static int dws_reserve(zp_ctx* ctx, size_t bytes) {
     if (bytes <= ctx->dws_bytes) return 0;
     ZP_CUDA(ctx, cudaDeviceSynchronize());
+    zp_drop_graphs(ctx);
     if (ctx->dws) cudaFree(ctx->dws);
     ctx->dws = nullptr; ctx->dws_bytes = 0;
     size_t want = bytes + bytes / 4 + 4096;

@@ -357,6 +357,7 @@ int zp_launch_final_split(zp_ctx* ctx, const FinalArgs& a, cudaStream_t st) {
                  o_state = o_done + fs_align((size_t)B * 4), need = o_state + fs_align((size_t)B * 4);
     if (need > ctx->fws_bytes) {        // growing must not race with work still using the old buffer
         ZP_CUDA(ctx, cudaDeviceSynchronize());
+        zp_drop_graphs(ctx);
         if (ctx->fws) cudaFree(ctx->fws);
         ctx->fws = nullptr; ctx->fws_bytes = 0;
         ZP_CUDA(ctx, cudaMalloc(&ctx->fws, need + need / 8));
