@@ -442,6 +442,37 @@ def test_graph_replay_identical(eng, batch):
         assert all(torch.equal(a, b) for a, b in zip(want, out))
 
 
+def test_graph_survives_workspace_growth(batch, tables):
+    """a captured graph holds raw pointers into the context's workspaces; a later, larger batch re-allocates them -- the small
+    batch's graph must then be dropped and re-captured, not replayed on freed memory"""
+    import zebrapose_b200 as zp
+    e = zp.Engine(0)
+    e.upload_dict(0, tables["full"][0])
+    lg = torch.from_numpy(batch["logits"]).cuda()
+    bb = torch.from_numpy(batch["bboxes"].astype(np.float64)).cuda()
+    K = torch.from_numpy(batch["Ks"].reshape(-1, 9).copy()).cuda()
+    small = (lg[:2].contiguous(), bb[:2].contiguous(), K[:2].contiguous())
+    big = (lg.repeat(4, 1, 1, 1), bb.repeat(4, 1), K.repeat(4, 1))
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        ref = [t.clone() for t in e.decode_and_pose_batch(*small)]
+        for _ in range(3):                                   # eager + capture, then replays
+            out = e.decode_and_pose_batch(*small, graph=True)
+            side.synchronize()
+            assert all(torch.equal(a, b) for a, b in zip(ref, out))
+        outb = [t.clone() for t in e.decode_and_pose_batch(*big, graph=True)]      # grows every workspace
+        side.synchronize()
+        junk = torch.full((64 << 20,), 7, dtype=torch.uint8, device="cuda")        # reuse whatever memory was freed
+        for _ in range(3):
+            out = e.decode_and_pose_batch(*small, graph=True)
+            side.synchronize()
+            assert all(torch.equal(a, b) for a, b in zip(ref, out))
+        outb2 = e.decode_and_pose_batch(*big, graph=True)
+        side.synchronize()
+        assert all(torch.equal(a, b) for a, b in zip(outb, outb2))
+        del junk
+
+
 def test_gn_refine_against_twin(eng, batch):
     """north_star's "batched Gauss-Newton refine on the inliers" (final="epnp+gn"; not in the reference, whose cv2 call ends
     with EPnP on the inliers).  Device vs the float64 twin started from the device's own EPnP pose on the device's inlier
